@@ -1,0 +1,97 @@
+/*
+ * wgbs_b200.h -- C ABI of the B200-native wgbstools hot path.
+ *
+ * The reference (nloyfer/wgbs_tools v0.3.0) has no in-process FFI: its hot path sits behind PROCESS boundaries
+ * (argv + text on stdin/stdout of five small executables).  Every entry point below replaces
+ * one of those executables (or the coreutils / numpy step next to it) and documents the reference interface it
+ * stands in for.  INTEGRATION.md shows the ctypes binding a reference maintainer would add to
+ * src/python/{bam2pat,pat2beta,homog,segment}.py.
+ *
+ * Conventions
+ *   - plain C, no torch types.  All functions return 0 on success, <0 on error; wgbs_last_error() (thread-local)
+ *     has the message.  Bad READS are never errors: they are skipped and counted (reference patter.cpp:229-244).
+ *   - one wgbs_ctx per GPU (device ordinal + stream + stream-ordered scratch).  Calls on one ctx are serialised by the
+ *     caller; different ctxs are independent (mirrors the reference's one-process-per-chromosome model).
+ *   - every data pointer may be a HOST or a DEVICE pointer unless stated otherwise; the library detects which
+ *     (cudaPointerGetAttributes) and stages host buffers through pinned memory.  The caller owns all buffers.
+ *   - functions are asynchronous on ctx's stream when all their buffers are device buffers; any host output is
+ *     complete when the function returns.
+ *   - there is NO CPU fallback: every entry point fails (rc<0) when no CUDA device is usable.
+ */
+#ifndef WGBS_B200_H
+#define WGBS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WGBS_B200_ABI_VERSION 1
+
+typedef struct wgbs_ctx wgbs_ctx;
+typedef struct wgbs_pats wgbs_pats;   /* device-resident pat records: (idx, len, count, 2-bit symbol pool) */
+typedef struct wgbs_index wgbs_index; /* device-resident CpG dictionary of one chromosome / region */
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * context
+ * ------------------------------------------------------------------------------------------------------------- */
+int wgbs_abi_version(void);
+const char *wgbs_last_error(void);
+/* stream: a cudaStream_t to run on (e.g. torch.cuda.current_stream().cuda_stream), or NULL to create one. */
+wgbs_ctx *wgbs_create(int device, void *stream);
+void wgbs_destroy(wgbs_ctx *);
+int wgbs_sync(wgbs_ctx *);
+/* number of kernels this ctx has launched so far (bench.py's "gpu_launches") */
+uint64_t wgbs_launch_count(const wgbs_ctx *);
+/* device memory helpers so that callers without torch can keep inputs resident in HBM */
+int wgbs_dev_alloc(wgbs_ctx *, size_t nbytes, void **dptr);
+int wgbs_dev_free(wgbs_ctx *, void *dptr);
+int wgbs_memcpy(wgbs_ctx *, void *dst, const void *src, size_t nbytes); /* any host/device combination */
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * pat records  (on-disk format: reference docs/pat_format.md:3-47  "chr \t idx \t pattern \t count")
+ * Symbol codes (2 bit): '.'=0 'C'=1 'H'=2 'T'=3 -- the C-locale collation order the reference's `sort -k3,3` uses.
+ * Pool layout: record r owns words pool[off[r] .. off[r]+ceil(len[r]/16)), 16 symbols per uint32, first symbol in
+ * the two MOST significant bits, unused tail bits zero.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* Parse pat TEXT (what `gunzip -c X.pat.gz` prints; stdin of reference stdin2beta.cpp:95-123 / homog.cpp:262-313)
+ * on the GPU.  Lines with < 4 columns or a non-numeric idx/count make the call fail, like the reference
+ * ("failed calculating beta": stdin2beta.cpp:104-106,118-122).  Empty lines are skipped. */
+int wgbs_pats_from_text(wgbs_ctx *, const char *text, size_t nbytes, wgbs_pats **out);
+int wgbs_pats_count(const wgbs_pats *, uint64_t *n_records, uint64_t *n_pool_words);
+/* copy the SoA out (any pointer may be NULL to skip that array) */
+int wgbs_pats_download(wgbs_ctx *, const wgbs_pats *, uint32_t *idx, uint32_t *len, uint32_t *count, uint32_t *off,
+                       uint32_t *pool);
+void wgbs_pats_free(wgbs_ctx *, wgbs_pats *);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * pat -> beta   (replaces `stdin2beta START END`, reference src/pat2beta/stdin2beta.cpp:59-93, and
+ *                utils_wgbs.trim_to_uint8, reference src/python/utils_wgbs.py:277-290)
+ * ------------------------------------------------------------------------------------------------------------- */
+/* meth_cov: DEVICE int32[end-start, 2] rows (meth, cover) -- the numbers stdin2beta prints.  zero_first!=0 clears
+ * it first; otherwise the records are ADDED (multi-batch / multi-GPU partial sums). start is 1-based, end exclusive. */
+int wgbs_pat2beta(wgbs_ctx *, const wgbs_pats *, uint32_t start, uint32_t end, int32_t *meth_cov, int zero_first);
+/* rows with cover > max (255 | 65535): meth = trunc(float64(meth)/float64(cover)*max), cover = max; cast to
+ * uint8 / uint16 (nbits 8 | 16).  out: [n,2] of that type.  meth_cov / out: host or device. */
+int wgbs_trim(wgbs_ctx *, const int32_t *meth_cov, size_t n, int nbits, void *out);
+/* One call, host buffers: pat text -> .beta bytes (what pat2beta.py:32-37 writes).  meth_cov_out (int32[n,2], host)
+ * may be NULL. */
+int wgbs_pat2beta_text(wgbs_ctx *, const char *text, size_t nbytes, uint32_t start, uint32_t end, int nbits,
+                       void *beta_out, int32_t *meth_cov_out);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * homog   (replaces `homog -b BLOCKS -r r0,..,rk -l MINLEN [--inclusive]`, reference src/homog/homog.cpp:154-260)
+ * blocks: startCpG/endCpG (end exclusive) in the order the reference processes them (file order, which must be
+ * sorted by startCpG; the host side applies --sort_blocks / --chrom).  range: nbins+1 float32 edges as parsed by
+ * `istream >> float`.  out: int32[nblocks, nbins], one row per block in block order (what homog prints).
+ * Records must be sorted by idx (a pat file is, by definition).
+ * ------------------------------------------------------------------------------------------------------------- */
+int wgbs_homog(wgbs_ctx *, const wgbs_pats *, const int32_t *bstart, const int32_t *bend, size_t nblocks,
+               const float *range, int nbins, int min_cpgs, int inclusive, int32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WGBS_B200_H */

@@ -1,0 +1,56 @@
+"""ctypes binding of libwgbs_b200.so (include/wgbs_b200.h).
+
+There is no CPU path: importing this module loads the CUDA library and raises if it is missing; creating a
+``Context`` raises if no B200 is usable."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libwgbs_b200.so")
+
+
+class WgbsError(RuntimeError):
+    """Any rc<0 from the C ABI (message from wgbs_last_error)."""
+
+
+def _load():
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built (python -m wgbs_tools_b200.build). "
+            "wgbs_tools_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, sz, u32, i32, u64 = C.c_void_p, C.c_size_t, C.c_uint32, C.c_int32, C.c_uint64
+    sig = {
+        "wgbs_abi_version": (C.c_int, []),
+        "wgbs_last_error": (C.c_char_p, []),
+        "wgbs_create": (vp, [C.c_int, vp]),
+        "wgbs_destroy": (None, [vp]),
+        "wgbs_sync": (C.c_int, [vp]),
+        "wgbs_launch_count": (u64, [vp]),
+        "wgbs_dev_alloc": (C.c_int, [vp, sz, C.POINTER(vp)]),
+        "wgbs_dev_free": (C.c_int, [vp, vp]),
+        "wgbs_memcpy": (C.c_int, [vp, vp, vp, sz]),
+        "wgbs_pats_from_text": (C.c_int, [vp, vp, sz, C.POINTER(vp)]),
+        "wgbs_pats_count": (C.c_int, [vp, C.POINTER(u64), C.POINTER(u64)]),
+        "wgbs_pats_download": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
+        "wgbs_pats_free": (None, [vp, vp]),
+        "wgbs_pat2beta": (C.c_int, [vp, vp, u32, u32, vp, C.c_int]),
+        "wgbs_trim": (C.c_int, [vp, vp, sz, C.c_int, vp]),
+        "wgbs_pat2beta_text": (C.c_int, [vp, vp, sz, u32, u32, C.c_int, vp, vp]),
+        "wgbs_homog": (C.c_int, [vp, vp, vp, vp, sz, vp, C.c_int, C.c_int, C.c_int, vp]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    return L, sig
+
+
+lib, SIGNATURES = _load()
+
+
+def check(rc: int) -> None:
+    if rc < 0:
+        raise WgbsError(lib.wgbs_last_error().decode(errors="replace"))

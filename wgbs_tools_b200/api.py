@@ -1,0 +1,178 @@
+"""Python face of the C ABI: a Context per GPU, device-resident pat records, and the per-step operators.
+
+Buffers cross the boundary as raw addresses: numpy arrays / bytes for host data, ``DevBuf`` (or any object with a
+``data_ptr()`` such as a torch CUDA tensor) for device data."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import WgbsError, check, lib
+
+
+def _addr(x):
+    """address of a host numpy array / bytes-like, or of a device buffer (DevBuf / torch tensor)."""
+    if x is None:
+        return None
+    if isinstance(x, DevBuf):
+        return x.ptr
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    if isinstance(x, np.ndarray):
+        if not x.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous")
+        return x.ctypes.data
+    if isinstance(x, (bytes, bytearray, memoryview)):
+        return C.cast(C.c_char_p(bytes(x)) if not isinstance(x, bytes) else C.c_char_p(x), C.c_void_p).value
+    if isinstance(x, int):
+        return x
+    raise TypeError(type(x))
+
+
+class DevBuf:
+    """A device allocation owned by a Context (stream-ordered)."""
+
+    def __init__(self, ctx: "Context", nbytes: int):
+        self.ctx, self.nbytes = ctx, int(nbytes)
+        p = C.c_void_p()
+        check(lib.wgbs_dev_alloc(ctx.h, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    def free(self):
+        if self.ptr:
+            lib.wgbs_dev_free(self.ctx.h, self.ptr)
+            self.ptr = None
+
+    def to_host(self, dtype=np.uint8) -> np.ndarray:
+        out = np.empty(self.nbytes // np.dtype(dtype).itemsize, dtype)
+        check(lib.wgbs_memcpy(self.ctx.h, out.ctypes.data, self.ptr, out.nbytes))
+        return out
+
+
+class Pats:
+    """Device-resident pat records (idx, len, count, 2-bit symbol pool)."""
+
+    def __init__(self, ctx: "Context", handle):
+        self.ctx, self.h = ctx, handle
+
+    def __len__(self):
+        n = C.c_uint64(); w = C.c_uint64()
+        check(lib.wgbs_pats_count(self.h, C.byref(n), C.byref(w)))
+        return n.value
+
+    @property
+    def pool_words(self) -> int:
+        n = C.c_uint64(); w = C.c_uint64()
+        check(lib.wgbs_pats_count(self.h, C.byref(n), C.byref(w)))
+        return w.value
+
+    def download(self):
+        n, w = len(self), self.pool_words
+        idx = np.empty(n, np.uint32); ln = np.empty(n, np.uint32); cnt = np.empty(n, np.uint32)
+        off = np.empty(n + 1, np.uint32); pool = np.empty(max(w, 1), np.uint32)
+        check(lib.wgbs_pats_download(self.ctx.h, self.h, idx.ctypes.data, ln.ctypes.data, cnt.ctypes.data, off.ctypes.data, pool.ctypes.data))
+        return idx.view(np.int32), ln, cnt.view(np.int32), off, pool[:w]
+
+    def patterns(self) -> list[bytes]:
+        """decode the symbol pool back to ASCII patterns (host-side, for tests and small outputs)."""
+        idx, ln, cnt, off, pool = self.download()
+        lut = np.frombuffer(b".CHT", np.uint8)
+        out = []
+        for i in range(idx.size):
+            L = int(ln[i]); w = pool[off[i]: off[i] + (L + 15) // 16]
+            sh = (30 - 2 * np.arange(16, dtype=np.uint32))[None, :]
+            sym = ((w[:, None] >> sh) & 3).reshape(-1)[:L]
+            out.append(lut[sym].tobytes())
+        return out
+
+    def free(self):
+        if self.h:
+            lib.wgbs_pats_free(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One per GPU.  ``stream``: a raw cudaStream_t (int) to run on, e.g. torch.cuda.current_stream().cuda_stream."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.h = lib.wgbs_create(int(device), C.c_void_p(stream) if stream else None)
+        if not self.h:
+            raise WgbsError(lib.wgbs_last_error().decode(errors="replace"))
+        self.device = device
+
+    def close(self):
+        if self.h:
+            lib.wgbs_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def sync(self):
+        check(lib.wgbs_sync(self.h))
+
+    @property
+    def launches(self) -> int:
+        return int(lib.wgbs_launch_count(self.h))
+
+    # ---- memory -------------------------------------------------------------------------------------------------
+    def alloc(self, nbytes: int) -> DevBuf:
+        return DevBuf(self, nbytes)
+
+    def upload(self, data) -> DevBuf:
+        a = np.frombuffer(data, np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) else np.ascontiguousarray(data)
+        b = DevBuf(self, a.nbytes)
+        check(lib.wgbs_memcpy(self.h, b.ptr, a.ctypes.data, a.nbytes))
+        return b
+
+    # ---- pat ----------------------------------------------------------------------------------------------------
+    def pats_from_text(self, text, nbytes: int | None = None) -> Pats:
+        """text: bytes (host) or DevBuf (device-resident pat text)."""
+        if isinstance(text, DevBuf):
+            p, n = text.ptr, text.nbytes if nbytes is None else nbytes
+        else:
+            a = np.frombuffer(text, np.uint8)
+            p, n = a.ctypes.data, a.size
+        h = C.c_void_p()
+        check(lib.wgbs_pats_from_text(self.h, p, n, C.byref(h)))
+        return Pats(self, h.value)
+
+    def pat2beta(self, pats: Pats, start: int, end: int, meth_cov=None, zero_first: bool = True):
+        """device int32[end-start,2] (meth, cover) counts; returns the DevBuf (allocated if not given)."""
+        n = end - start
+        buf = meth_cov if meth_cov is not None else DevBuf(self, max(n, 1) * 8)
+        check(lib.wgbs_pat2beta(self.h, pats.h, start, end, _addr(buf), int(zero_first)))
+        return buf
+
+    def trim(self, meth_cov, n: int, nbits: int = 8) -> np.ndarray:
+        out = np.empty((n, 2), np.uint8 if nbits == 8 else np.uint16)
+        check(lib.wgbs_trim(self.h, _addr(meth_cov), n, nbits, out.ctypes.data))
+        return out
+
+    def pat2beta_text(self, text: bytes, start: int, end: int, nbits: int = 8, want_counts: bool = False):
+        """pat text (host) -> beta array (host), the whole of reference pat2beta.py:32-37 in one call."""
+        n = end - start
+        a = np.frombuffer(text, np.uint8)
+        out = np.empty((n, 2), np.uint8 if nbits == 8 else np.uint16)
+        mc = np.empty((n, 2), np.int32) if want_counts else None
+        check(lib.wgbs_pat2beta_text(self.h, a.ctypes.data, a.size, start, end, nbits, out.ctypes.data,
+                                     mc.ctypes.data if mc is not None else None))
+        return (out, mc) if want_counts else out
+
+    def homog(self, pats: Pats, blocks: np.ndarray, rng, min_cpgs: int, inclusive: bool = False) -> np.ndarray:
+        bs = np.ascontiguousarray(blocks[:, 0], np.int32); be = np.ascontiguousarray(blocks[:, 1], np.int32)
+        r = np.ascontiguousarray(rng, np.float32); nb = r.size - 1
+        out = np.empty((bs.size, nb), np.int32)
+        check(lib.wgbs_homog(self.h, pats.h, bs.ctypes.data, be.ctypes.data, bs.size, r.ctypes.data, nb, int(min_cpgs),
+                             int(inclusive), out.ctypes.data))
+        return out
