@@ -54,7 +54,7 @@ int wgbs_memcpy(wgbs_ctx *, void *dst, const void *src, size_t nbytes); /* any h
  * pat records  (on-disk format: reference docs/pat_format.md:3-47  "chr \t idx \t pattern \t count")
  * Symbol codes (2 bit): '.'=0 'C'=1 'H'=2 'T'=3 -- the C-locale collation order the reference's `sort -k3,3` uses.
  * Pool layout: record r owns words pool[off[r] .. off[r]+ceil(len[r]/16)), 16 symbols per uint32, first symbol in
- * the two MOST significant bits, unused tail bits zero.
+ * the two MOST significant bits, unused tail bits zero.  Records need not be contiguous in the pool (off has n entries).
  * ------------------------------------------------------------------------------------------------------------- */
 /* Parse pat TEXT (what `gunzip -c X.pat.gz` prints; stdin of reference stdin2beta.cpp:95-123 / homog.cpp:262-313)
  * on the GPU.  Lines with < 4 columns or a non-numeric idx/count make the call fail, like the reference
@@ -90,6 +90,41 @@ int wgbs_pat2beta_text(wgbs_ctx *, const char *text, size_t nbytes, uint32_t sta
  * ------------------------------------------------------------------------------------------------------------- */
 int wgbs_homog(wgbs_ctx *, const wgbs_pats *, const int32_t *bstart, const int32_t *bend, size_t nblocks,
                const float *range, int nbins, int min_cpgs, int inclusive, int32_t *out);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * bam -> pat pileup
+ *   replaces   [match_maker |] patter CPG_DICT REGION [--min_cpg N] [--clip N] [--nanopore --np_thresh F
+ *              --cpc_call C|H|. --combine_mods]            (reference src/pipeline_wgbs/{match_maker,main,patter,ont}.cpp)
+ *   and        sort -k2,2n -k3,3 | uniq -c | awk '{print $2,$3,$4,$1}'   (reference src/python/bam2pat.py:99-106)
+ * ------------------------------------------------------------------------------------------------------------- */
+/* CpG dictionary of one chromosome / region: `tabix CpG.bed.gz REGION | cut -f2-3` (reference patter.cpp:14-42).
+ * loci: sorted 1-based positions of the C of every CpG in the region; the CpG index of loci[k] is first_idx + k. */
+int wgbs_index_load(wgbs_ctx *, const uint32_t *loci, size_t n, uint32_t first_idx, wgbs_index **out);
+void wgbs_index_free(wgbs_ctx *, wgbs_index *);
+
+typedef struct wgbs_pileup_opts {
+    int32_t min_cpg;      /* --min_cpg  (patter main.cpp:16-22, default 1): drop templates whose pattern is shorter */
+    int32_t clip;         /* --clip     (main.cpp:23-29, default 0): ignore calls in the first/last `clip` positions */
+    int32_t paired;       /* 1 / 0, or -1 = decide from FLAG&1 of the first line like patter.cpp:324-333 */
+    int32_t nanopore;     /* --nanopore (MM/ML mode); also switched on when the first line carries an MM tag */
+    int32_t combine_mods; /* --combine_mods */
+    float np_thresh;      /* --np_thresh (float32, default 0.67) */
+    char cpc_call;        /* --cpc_call 'C' | 'H' | '.' (0 = 'C') */
+} wgbs_pileup_opts;
+
+/* sam: SAM text without header, one chromosome, coordinate sorted -- exactly what `samtools view BAM chr` feeds the
+ * reference pipeline (host or device pointer, < 4 GiB per call).  Mates are found by QNAME (match_maker's job).
+ * out: one record per template with >= min_cpg symbols, count = 1, in input order of the template's first record.
+ * stats[8]: lines, pairs, empty, short ("too few CpGs"), invalid, paired(0/1), nanopore(0/1), templates out
+ *           -- the counters of patter's summary line (patter.cpp:298-316). */
+int wgbs_pileup_sam(wgbs_ctx *, const wgbs_index *, const char *sam, size_t nbytes, const wgbs_pileup_opts *,
+                    wgbs_pats **out, uint64_t *stats);
+/* sort by (idx, pattern) in the C locale and merge identical records, summing counts (in place) */
+int wgbs_collapse(wgbs_ctx *, wgbs_pats *);
+/* "chrom \t idx \t pattern \t count \n" per record, record order.  out NULL: only *nbytes. out: host or device. */
+int wgbs_pats_format(wgbs_ctx *, const wgbs_pats *, const char *chrom, char *out, size_t cap, size_t *nbytes);
+/* utility: stable radix sort of (key, value) uint32 pairs, device pointers */
+int wgbs_sort_pairs_u32(wgbs_ctx *, uint32_t *keys, uint32_t *vals, size_t n);
 
 #ifdef __cplusplus
 }

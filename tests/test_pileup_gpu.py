@@ -1,0 +1,162 @@
+"""GPU parity of the bam->pat pileup (tokenizer, pairing, CIGAR/CpG calls, mate merge, collapse, text) through the C ABI
+against the reference pipeline  `[match_maker |] patter | sort -k2,2n -k3,3 | uniq -c | awk`  (oracle/_ref) and the C
+restatement."""
+import numpy as np
+import pytest
+
+from wgbs_tools_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def genome():
+    return synth.make_genome(7, "chrT", 1_000_000)
+
+
+def _oracle_pat(H, g, sam, paired, **kw):
+    """(raw patter lines sorted, collapsed text, stats) from the reference executables, else from the C port."""
+    if H.have_ref():
+        d = H.write_tmp(g.dict_text(), ".CpG.bed")
+        out, err = H.ref_patter(sam, d, g.chrom, paired, **kw)
+        return out, H.ref_collapse(out)
+    mm = H.port_match_maker(sam) if paired else sam
+    out, _ = H.port_patter(mm, g.loci, g.idx(), **kw)
+    return out, H.port_collapse(out)
+
+
+def _gpu_pat(ctx, g, sam, **kw):
+    ix = ctx.load_index(g.loci, g.first_idx)
+    P, st = ctx.pileup_sam(ix, sam, **kw)
+    raw = P.to_text(g.chrom)
+    P.collapse()
+    txt = P.to_text(g.chrom)
+    P.free(); ix.free()
+    return raw, txt, st
+
+
+def test_sort_pairs_is_a_stable_radix_sort(ctx):
+    rng = np.random.default_rng(0)
+    for n, hi in [(1, 10), (1000, 4), (70_001, 2**32), (300_000, 2**20)]:
+        k = rng.integers(0, hi, size=n, dtype=np.uint64).astype(np.uint32); v = np.arange(n, dtype=np.uint32)
+        ko, vo = ctx.sort_pairs(k, v)
+        order = np.argsort(k, kind="stable")
+        np.testing.assert_array_equal(ko, k[order]); np.testing.assert_array_equal(vo, v[order])
+
+
+@pytest.mark.parametrize("paired", [True, False])
+@pytest.mark.parametrize("clip,min_cpg", [(0, 1), (5, 2)])
+def test_pileup_matches_reference_pipeline(ctx, oracle, genome, paired, clip, min_cpg):
+    H = oracle
+    sam = synth.make_sam(genome, 20_000, 21 + clip, paired=paired)
+    ref_raw, ref_txt = _oracle_pat(H, genome, sam, paired, min_cpg=min_cpg, clip=clip)
+    raw, txt, st = _gpu_pat(ctx, genome, sam, min_cpg=min_cpg, clip=clip)
+    # templates before the collapse: same multiset of lines (the reference's own order depends on an unstable sort)
+    assert sorted(l + b"\t1" for l in ref_raw.splitlines()) == sorted(raw.splitlines())
+    assert txt == ref_txt                                   # the uncompressed .pat bytes
+    mm = H.port_match_maker(sam) if paired else sam
+    _, pst = H.port_patter(mm, genome.loci, genome.idx(), min_cpg=min_cpg, clip=clip)
+    assert [st[k] for k in ("lines", "pairs", "empty", "short", "invalid", "paired")] == pst
+    assert len(txt) > 10_000
+
+
+def test_pileup_invalid_and_odd_reads(ctx, oracle, genome):
+    H = oracle; g = genome
+    p = int(g.loci[100]) - 20
+    seq = g.bases[p:p + 60].tobytes()
+    lines = [
+        b"a\t0\tchrT\t%d\t60\t60M\t*\t0\t0\t%s\t*" % (p, seq),
+        b"b\t0\tchrT\t%d\t60\t*\t*\t0\t0\t%s\t*" % (p, seq),
+        b"c\t0\tchrT\t%d\t60\t70M\t*\t0\t0\t%s\t*" % (p, seq),
+        b"d\t0\tchrT\t%d\t60\t30M2P30M\t*\t0\t0\t%s\t*" % (p, seq),
+        b"e\t16\tchrT\t%d\t60\t10S40M10H\t*\t0\t0\t%s\t*" % (p, seq),
+        b"f\t0\tchrT\t%d\t60\t20M5N35M5S\t*\t0\t0\t%s\t*" % (p, seq),
+        b"g\t0\tchrT\t%d\t60\t20=5X35M\t*\t0\t0\t%s\t*" % (p, seq),
+        b"h\t0\tchrT",
+        b"i\t0\tchrT\t%d\t60\t60M\t*\t0\t0\t*\t*" % p,
+        b"j\t0\tchrT\t%d\t60\t60M\t*\t0\t0\t%s\t*" % (int(g.loci[-1]) - 5, seq),
+        b"k\t0\tchrT\t%d\t60\t5M\t*\t0\t0\t%s\t*" % (p, seq),
+        b"l\t16\tchrT\t%d\t60\t25M3I10M4D22M\t*\t0\t0\t%s\t*" % (p, seq),
+        b"m\t0\tchrT\t%d\t60\tM\t*\t0\t0\t%s\t*" % (p, seq),                   # op without a number
+        b"n\t0\tchrT\t%d\t60\t99999999999M\t*\t0\t0\t%s\t*" % (p, seq),        # int overflow
+        b"o\tx\tchrT\t%d\t60\t60M\t*\t0\t0\t%s\t*" % (p, seq),                 # non numeric flag
+        b"",
+        b"q\t16\tchrT\t%d\t60\t60M\t*\t0\t0\t%s\t*\tNM:i:0\tXX:Z:abc" % (p + 1, seq),
+    ]
+    sam = b"\n".join(lines) + b"\n"
+    ref_raw, ref_txt = _oracle_pat(H, g, sam, False)
+    raw, txt, st = _gpu_pat(ctx, g, sam)
+    assert txt == ref_txt
+    _, pst = H.port_patter(sam, g.loci, g.idx())
+    assert [st[k] for k in ("lines", "pairs", "empty", "short", "invalid", "paired")] == pst
+    assert st["invalid"] == 8
+
+
+def test_pileup_no_trailing_newline_and_single_line(ctx, oracle, genome):
+    H = oracle; g = genome
+    sam = synth.make_sam(g, 50, 3, paired=False).rstrip(b"\n")
+    ref_raw, ref_txt = _oracle_pat(H, g, sam + b"\n", False)
+    raw, txt, st = _gpu_pat(ctx, g, sam)
+    assert txt == ref_txt and st["lines"] == 50
+    raw, txt, st = _gpu_pat(ctx, g, b"")
+    assert txt == b"" and st["lines"] == 0
+
+
+def test_pairing_groups_of_three_and_far_mates(ctx, oracle, genome):
+    """supplementary alignments share a QNAME (FLAGS_FILTER 1796 keeps 0x800, bam2pat.py:27): greedy pairing in
+    whole-line order; a far-away mate still pairs; a dropped mate leaves a single."""
+    H = oracle; g = genome
+    base = synth.make_sam(g, 4_000, 5, paired=True, single_frac=0.05)
+    lines = base.splitlines()
+    # add supplementary copies (flag |= 2048, other position) of some read1 records, keeping coordinate order
+    extra = []
+    for l in lines[::97]:
+        t = l.split(b"\t")
+        t[1] = b"%d" % (int(t[1]) | 2048)
+        t[3] = b"%d" % (int(t[3]) + 5000)
+        extra.append(b"\t".join(t))
+    allr = sorted(lines + extra, key=lambda l: int(l.split(b"\t")[3]))
+    sam = b"\n".join(allr) + b"\n"
+    ref_raw, ref_txt = _oracle_pat(H, g, sam, True)
+    raw, txt, st = _gpu_pat(ctx, g, sam)
+    assert txt == ref_txt
+    assert st["pairs"] > 1500
+
+
+def test_long_patterns_multiword_sort(ctx, oracle):
+    """dense CpG island: >16 and >32 symbols per read (multi-word pool records, multi-pass collapse)"""
+    H = oracle
+    L = 60_000
+    loci = np.arange(1001, 50_000, 3, dtype=np.int64)             # CpG every 3 bp
+    g = synth.Genome("chrD", L, loci, 1, None, np.full(loci.size, 0.5, np.float32))
+    bases = np.full(L + 2, ord("A"), np.uint8); bases[loci] = ord("C"); bases[loci + 1] = ord("G"); g.bases = bases
+    sam = synth.make_sam(g, 6_000, 9, paired=True)
+    ref_raw, ref_txt = _oracle_pat(H, g, sam, True)
+    raw, txt, st = _gpu_pat(ctx, g, sam)
+    assert max(len(l.split(b"\t")[2]) for l in txt.splitlines()) > 48
+    assert txt == ref_txt
+
+
+def test_tutorial_like_real_cigars(ctx, oracle, genome):
+    """CIGAR diversity: many I/D/S/H/N events per read"""
+    H = oracle; g = genome
+    rng = np.random.default_rng(4)
+    lines = []
+    pos = 1000
+    for i in range(3000):
+        pos += int(rng.integers(1, 300))
+        ops = []; qlen = 0
+        for _ in range(int(rng.integers(1, 7))):
+            op = "MIDSNH=X"[int(rng.integers(0, 8))]; k = int(rng.integers(1, 40))
+            ops.append(f"{k}{op}")
+            if op in "MIS=X":
+                qlen += k
+        seq = bytes(rng.choice(list(b"ACGTN"), size=max(qlen + int(rng.integers(-2, 3)), 1), p=[.2, .3, .25, .2, .05]).tolist())
+        lines.append(b"r%d\t%d\tchrT\t%d\t60\t%s\t*\t0\t0\t%s\t*" % (i, 16 * int(rng.integers(0, 2)), pos, "".join(ops).encode(), seq))
+    sam = b"\n".join(lines) + b"\n"
+    ref_raw, ref_txt = _oracle_pat(H, g, sam, False)
+    raw, txt, st = _gpu_pat(ctx, g, sam)
+    assert txt == ref_txt
+    _, pst = H.port_patter(sam, g.loci, g.idx())
+    assert [st[k] for k in ("lines", "pairs", "empty", "short", "invalid", "paired")] == pst
+    assert st["invalid"] > 100

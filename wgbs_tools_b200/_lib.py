@@ -11,6 +11,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libwgbs_b200.so")
 
 
+class PileupOpts(C.Structure):
+    """mirror of wgbs_pileup_opts (include/wgbs_b200.h)"""
+    _fields_ = [("min_cpg", C.c_int32), ("clip", C.c_int32), ("paired", C.c_int32), ("nanopore", C.c_int32),
+                ("combine_mods", C.c_int32), ("np_thresh", C.c_float), ("cpc_call", C.c_char)]
+
+
 class WgbsError(RuntimeError):
     """Any rc<0 from the C ABI (message from wgbs_last_error)."""
 
@@ -40,6 +46,12 @@ def _load():
         "wgbs_trim": (C.c_int, [vp, vp, sz, C.c_int, vp]),
         "wgbs_pat2beta_text": (C.c_int, [vp, vp, sz, u32, u32, C.c_int, vp, vp]),
         "wgbs_homog": (C.c_int, [vp, vp, vp, vp, sz, vp, C.c_int, C.c_int, C.c_int, vp]),
+        "wgbs_index_load": (C.c_int, [vp, vp, sz, u32, C.POINTER(vp)]),
+        "wgbs_index_free": (None, [vp, vp]),
+        "wgbs_pileup_sam": (C.c_int, [vp, vp, vp, sz, vp, C.POINTER(vp), vp]),
+        "wgbs_collapse": (C.c_int, [vp, vp]),
+        "wgbs_pats_format": (C.c_int, [vp, vp, C.c_char_p, vp, sz, C.POINTER(sz)]),
+        "wgbs_sort_pairs_u32": (C.c_int, [vp, vp, vp, sz]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)

@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import WgbsError, check, lib
+from ._lib import PileupOpts, WgbsError, check, lib
 
 
 def _addr(x):
@@ -70,9 +70,9 @@ class Pats:
     def download(self):
         n, w = len(self), self.pool_words
         idx = np.empty(n, np.uint32); ln = np.empty(n, np.uint32); cnt = np.empty(n, np.uint32)
-        off = np.empty(n + 1, np.uint32); pool = np.empty(max(w, 1), np.uint32)
+        off = np.empty(max(n, 1), np.uint32); pool = np.empty(max(w, 1), np.uint32)
         check(lib.wgbs_pats_download(self.ctx.h, self.h, idx.ctypes.data, ln.ctypes.data, cnt.ctypes.data, off.ctypes.data, pool.ctypes.data))
-        return idx.view(np.int32), ln, cnt.view(np.int32), off, pool[:w]
+        return idx.view(np.int32), ln, cnt.view(np.int32), off[:n], pool[:w]
 
     def patterns(self) -> list[bytes]:
         """decode the symbol pool back to ASCII patterns (host-side, for tests and small outputs)."""
@@ -86,6 +86,18 @@ class Pats:
             out.append(lut[sym].tobytes())
         return out
 
+    def collapse(self) -> "Pats":
+        """sort -k2,2n -k3,3 | uniq -c (in place)"""
+        check(lib.wgbs_collapse(self.ctx.h, self.h))
+        return self
+
+    def to_text(self, chrom: str) -> bytes:
+        n = C.c_size_t()
+        check(lib.wgbs_pats_format(self.ctx.h, self.h, chrom.encode(), None, 0, C.byref(n)))
+        out = np.empty(max(n.value, 1), np.uint8)
+        check(lib.wgbs_pats_format(self.ctx.h, self.h, chrom.encode(), out.ctypes.data, n.value, C.byref(n)))
+        return out[:n.value].tobytes()
+
     def free(self):
         if self.h:
             lib.wgbs_pats_free(self.ctx.h, self.h)
@@ -96,6 +108,21 @@ class Pats:
             self.free()
         except Exception:
             pass
+
+
+class Index:
+    """Device-resident CpG dictionary of one chromosome / region."""
+
+    def __init__(self, ctx: "Context", loci, first_idx: int = 1):
+        a = np.ascontiguousarray(loci, np.uint32)
+        h = C.c_void_p()
+        check(lib.wgbs_index_load(ctx.h, a.ctypes.data, a.size, int(first_idx), C.byref(h)))
+        self.ctx, self.h, self.n, self.first_idx = ctx, h.value, a.size, int(first_idx)
+
+    def free(self):
+        if self.h:
+            lib.wgbs_index_free(self.ctx.h, self.h)
+            self.h = None
 
 
 class Context:
@@ -134,6 +161,32 @@ class Context:
         b = DevBuf(self, a.nbytes)
         check(lib.wgbs_memcpy(self.h, b.ptr, a.ctypes.data, a.nbytes))
         return b
+
+    # ---- pileup -------------------------------------------------------------------------------------------------
+    def load_index(self, loci, first_idx: int = 1) -> "Index":
+        return Index(self, loci, first_idx)
+
+    def pileup_sam(self, index: "Index", sam, min_cpg: int = 1, clip: int = 0, paired: int = -1, nanopore: bool = False,
+                   np_thresh: float = 0.67, cpc_call: str = "C", combine_mods: bool = False, nbytes: int | None = None):
+        """SAM text (bytes or DevBuf) -> (Pats of templates, stats dict).  The reference's
+        `samtools view ... | [match_maker |] patter DICT REGION ...` for one chromosome."""
+        if isinstance(sam, DevBuf):
+            p, n = sam.ptr, sam.nbytes if nbytes is None else nbytes
+        else:
+            a = np.frombuffer(sam, np.uint8)
+            p, n = a.ctypes.data, a.size
+        o = PileupOpts(min_cpg, clip, paired, int(nanopore), int(combine_mods), np_thresh, cpc_call.encode())
+        h = C.c_void_p(); st = (C.c_uint64 * 8)()
+        check(lib.wgbs_pileup_sam(self.h, index.h, p, n, C.addressof(o), C.byref(h), C.addressof(st)))
+        keys = ["lines", "pairs", "empty", "short", "invalid", "paired", "nanopore", "templates"]
+        return Pats(self, h.value), dict(zip(keys, [int(x) for x in st]))
+
+    def sort_pairs(self, keys: np.ndarray, vals: np.ndarray):
+        k = self.upload(np.ascontiguousarray(keys, np.uint32)); v = self.upload(np.ascontiguousarray(vals, np.uint32))
+        check(lib.wgbs_sort_pairs_u32(self.h, k.ptr, v.ptr, keys.size))
+        ko, vo = k.to_host(np.uint32), v.to_host(np.uint32)
+        k.free(); v.free()
+        return ko, vo
 
     # ---- pat ----------------------------------------------------------------------------------------------------
     def pats_from_text(self, text, nbytes: int | None = None) -> Pats:

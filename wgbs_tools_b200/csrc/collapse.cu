@@ -1,0 +1,165 @@
+// collapse.cu -- the collapse step and pat text formatting.
+//
+// Replaces, byte for byte on the uncompressed text, the reference's
+//     sort -k2,2n -k3,3 | uniq -c | awk -v OFS='\t' '{print $2,$3,$4,$1}'          (python/bam2pat.py:99-106, C locale)
+// Order = (CpG index numeric, pattern bytes with a shorter prefix first).  With symbol codes '.'<'C'<'H'<'T' = 0..3
+// packed MSB-first and zero padding, that order is the numeric order of (idx, word0, word1, ...): patterns never end
+// in '.', so zero padding is unambiguous.  LSD: sort by the last pattern word first, the index last; every pass is a
+// stable 32-bit radix sort that skips digits on which all keys agree.
+#include "reads.cuh"
+#include "sort.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256) max_words_k(const uint32_t *__restrict__ len, size_t n, uint32_t *__restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t w = i < n ? (len[i] + 15) >> 4 : 0;
+    w = __reduce_max_sync(0xffffffffu, w);
+    if ((threadIdx.x & 31) == 0 && w) atomicMax(out, w);
+}
+__global__ void __launch_bounds__(256) gather_word_k(PatsView P, const uint32_t *__restrict__ perm, uint32_t widx, uint32_t *__restrict__ keys) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    uint32_t r = perm[i];
+    keys[i] = widx < ((P.len[r] + 15) >> 4) ? P.pool[P.off[r] + widx] : 0u;
+}
+__global__ void __launch_bounds__(256) gather_idx_k(PatsView P, const uint32_t *__restrict__ perm, uint32_t *__restrict__ keys) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P.n) keys[i] = P.idx[perm[i]];
+}
+__device__ __forceinline__ bool same_rec(const PatsView &P, uint32_t a, uint32_t b) {
+    if (P.idx[a] != P.idx[b] || P.len[a] != P.len[b]) return false;
+    const uint32_t nw = (P.len[a] + 15) >> 4;
+    const uint32_t *x = P.pool + P.off[a], *y = P.pool + P.off[b];
+    for (uint32_t k = 0; k < nw; k++) if (x[k] != y[k]) return false;
+    return true;
+}
+__global__ void __launch_bounds__(256) head_flags_k(PatsView P, const uint32_t *__restrict__ perm, uint32_t *__restrict__ head) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    head[i] = (i == 0 || !same_rec(P, perm[i - 1], perm[i])) ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) emit_unique_k(PatsView P, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ head,
+                                                      const uint32_t *__restrict__ dst, uint32_t *__restrict__ o_idx, uint32_t *__restrict__ o_len,
+                                                      uint32_t *__restrict__ o_off, uint32_t *__restrict__ o_cnt) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n || !head[i]) return;
+    uint32_t r = perm[i];
+    uint32_t c = P.count[r];
+    for (size_t j = i + 1; j < P.n && !head[j]; j++) c += P.count[perm[j]];       // uniq -c
+    uint32_t k = dst[i];
+    o_idx[k] = P.idx[r]; o_len[k] = P.len[r]; o_off[k] = P.off[r]; o_cnt[k] = c;
+}
+
+// ---- text ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ndigits_i32(int32_t v) {
+    uint32_t n = v < 0 ? 1 : 0; uint32_t u = v < 0 ? (uint32_t)(-(int64_t)v) : (uint32_t)v;
+    uint32_t d = 1; while (u >= 10) { u /= 10; d++; }
+    return n + d;
+}
+__device__ __forceinline__ char *put_i32(char *p, int32_t v) {
+    uint32_t u = v < 0 ? (uint32_t)(-(int64_t)v) : (uint32_t)v;
+    if (v < 0) *p++ = '-';
+    char tmp[10]; int k = 0;
+    do { tmp[k++] = (char)('0' + u % 10); u /= 10; } while (u);
+    while (k) *p++ = tmp[--k];
+    return p;
+}
+__global__ void __launch_bounds__(256) line_len_k(PatsView P, uint32_t chrom_len, uint32_t *__restrict__ ll) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    ll[i] = chrom_len + 1 + ndigits_i32((int32_t)P.idx[i]) + 1 + P.len[i] + 1 + ndigits_i32((int32_t)P.count[i]) + 1;
+}
+__global__ void __launch_bounds__(256) line_write_k(PatsView P, const char *__restrict__ chrom, uint32_t chrom_len,
+                                                     const uint64_t *__restrict__ loff, char *__restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    char *p = out + loff[i];
+    for (uint32_t k = 0; k < chrom_len; k++) *p++ = chrom[k];
+    *p++ = '\t';
+    p = put_i32(p, (int32_t)P.idx[i]);
+    *p++ = '\t';
+    const uint32_t L = P.len[i];
+    const uint32_t *wp = P.pool + P.off[i];
+    for (uint32_t b = 0; b < L; b += 16) {
+        uint32_t w = *wp++, m = min(16u, L - b);
+        for (uint32_t k = 0; k < m; k++) *p++ = sym_char((w >> (30 - 2 * k)) & 3u);
+    }
+    *p++ = '\t';
+    p = put_i32(p, (int32_t)P.count[i]);
+    *p++ = '\n';
+}
+
+}  // namespace
+
+extern "C" int wgbs_collapse(wgbs_ctx *ctx, wgbs_pats *P) {
+    RC_TRY(wgbs_ctx_activate(ctx));
+    if (!P) return wgbs_set_err("null pats");
+    const size_t n = P->n;
+    if (n < 1) return 0;
+    if (n >= 0xffffffffull) return wgbs_set_err("wgbs_collapse: too many records");
+    Temps T(ctx);
+    uint32_t *d_mw = ctx->d_flags + 1;
+    CUDA_TRY(cudaMemsetAsync(d_mw, 0, 4, ctx->stream));
+    LAUNCH(ctx, max_words_k, grid_for(n, 256), 256, 0, P->len, n, d_mw);
+    uint32_t maxw = 0;
+    CUDA_TRY(cudaMemcpyAsync(&maxw, d_mw, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    uint32_t *k0, *v0, *k1, *v1;
+    RC_TRY(T.alloc(&k0, n)); RC_TRY(T.alloc(&v0, n)); RC_TRY(T.alloc(&k1, n)); RC_TRY(T.alloc(&v1, n));
+    uint32_t *k = k0, *v = v0, *ka = k1, *va = v1;
+    RC_TRY(fill_iota(ctx, v, n));
+    PatsView pv = view_of(P);
+    for (int w = (int)maxw - 1; w >= 0; w--) {
+        LAUNCH(ctx, gather_word_k, grid_for(n, 256), 256, 0, pv, v, (uint32_t)w, k);
+        RC_TRY(radix_sort_pairs(ctx, &k, &v, &ka, &va, n));
+    }
+    LAUNCH(ctx, gather_idx_k, grid_for(n, 256), 256, 0, pv, v, k);
+    RC_TRY(radix_sort_pairs(ctx, &k, &v, &ka, &va, n));
+    // run-length: heads, destinations, counts
+    uint32_t *head, *dst;
+    RC_TRY(T.alloc(&head, n)); RC_TRY(T.alloc(&dst, n + 1));
+    LAUNCH(ctx, head_flags_k, grid_for(n, 256), 256, 0, pv, v, head);
+    RC_TRY(scan_u32_u32(ctx, head, dst, n));
+    uint32_t nu = 0;
+    CUDA_TRY(cudaMemcpyAsync(&nu, dst + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    uint32_t *o_idx, *o_len, *o_off, *o_cnt;
+    int rc;
+    if ((rc = dalloc(ctx, &o_idx, nu)) < 0) return rc;
+    if ((rc = dalloc(ctx, &o_len, nu)) < 0) { dfree(ctx, o_idx); return rc; }
+    if ((rc = dalloc(ctx, &o_off, (size_t)nu + 1)) < 0) { dfree(ctx, o_idx); dfree(ctx, o_len); return rc; }
+    if ((rc = dalloc(ctx, &o_cnt, nu)) < 0) { dfree(ctx, o_idx); dfree(ctx, o_len); dfree(ctx, o_off); return rc; }
+    LAUNCH(ctx, emit_unique_k, grid_for(n, 256), 256, 0, pv, v, head, dst, o_idx, o_len, o_off, o_cnt);
+    LAUNCH_CHECK();
+    dfree(ctx, P->idx); dfree(ctx, P->len); dfree(ctx, P->off); dfree(ctx, P->count);
+    P->idx = o_idx; P->len = o_len; P->off = o_off; P->count = o_cnt; P->n = nu;
+    return 0;
+}
+
+// Write "chrom \t idx \t pattern \t count \n" per record, in record order (reference docs/pat_format.md:3-47).
+// out == NULL: only *nbytes is computed.  out may be host or device.
+extern "C" int wgbs_pats_format(wgbs_ctx *ctx, const wgbs_pats *P, const char *chrom, char *out, size_t cap, size_t *nbytes) {
+    RC_TRY(wgbs_ctx_activate(ctx));
+    if (!P || !chrom) return wgbs_set_err("wgbs_pats_format: null argument");
+    const size_t n = P->n;
+    const uint32_t cl = (uint32_t)strlen(chrom);
+    Temps T(ctx);
+    uint32_t *ll; uint64_t *loff;
+    RC_TRY(T.alloc(&ll, n)); RC_TRY(T.alloc(&loff, n + 1));
+    if (n) LAUNCH(ctx, line_len_k, grid_for(n, 256), 256, 0, view_of(P), cl, ll);
+    RC_TRY(scan_u32_u64(ctx, ll, loff, n));
+    uint64_t total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, loff + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (nbytes) *nbytes = (size_t)total;
+    if (!out) return 0;
+    if (cap < total) return wgbs_set_err("wgbs_pats_format: buffer too small (%zu < %llu)", cap, (unsigned long long)total);
+    char *dchrom; RC_TRY(T.alloc(&dchrom, (size_t)cl + 1));
+    RC_TRY(copy_any(ctx, dchrom, chrom, cl + 1));
+    char *dout = out;
+    if (!is_device_ptr(out)) RC_TRY(T.alloc(&dout, (size_t)total));
+    if (n) { LAUNCH(ctx, line_write_k, grid_for(n, 256), 256, 0, view_of(P), dchrom, cl, loff, dout); LAUNCH_CHECK(); }
+    if (dout != out) RC_TRY(copy_any(ctx, out, dout, (size_t)total));
+    return 0;
+}

@@ -6,83 +6,9 @@
 //   homog/homog.cpp:154-260         update_m2 / proc_line    -> homog_k
 #include "common.cuh"
 #include "pats.cuh"
+#include "lines.cuh"
 
 namespace {
-
-// ------------------------------------------------------------------------------------------------------------------
-// text -> lines.  One warp-iteration covers 512 contiguous bytes (16 B per lane); a CTA tile is 8 warps x 4 iters.
-// ------------------------------------------------------------------------------------------------------------------
-constexpr int NL_T = 256, NL_ITERS = 4, NL_TILE = NL_T * 16 * NL_ITERS;  // 16 KiB
-
-__device__ __forceinline__ uint4 load16_guard(const char *__restrict__ text, size_t pos, size_t n) {
-    if (pos + 16 <= n && ((uintptr_t)(text + pos) & 15) == 0) return *reinterpret_cast<const uint4 *>(text + pos);
-    uint32_t w[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int b = 0; b < 16; b++)
-        if (pos + b < n) w[b >> 2] |= (uint32_t)(uint8_t)text[pos + b] << ((b & 3) * 8);
-    return make_uint4(w[0], w[1], w[2], w[3]);
-}
-// bit b set iff byte b of the 16-byte chunk equals c
-__device__ __forceinline__ uint32_t eq_mask16(uint4 v, uint32_t c) {
-    const uint32_t rep = c * 0x01010101u;
-    uint32_t m = 0;
-    uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        uint32_t x = w[i] ^ rep;                                   // zero byte where equal
-        uint32_t z = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu);  // 0x80 in each zero byte
-        // gather the 4 high bits into 4 low bits
-        m |= (((z >> 7) & 1u) | ((z >> 14) & 2u) | ((z >> 21) & 4u) | ((z >> 28) & 8u)) << (4 * i);
-    }
-    return m;
-}
-
-__global__ void __launch_bounds__(NL_T) nl_count_k(const char *__restrict__ text, size_t n, uint32_t *__restrict__ bcount) {
-    const size_t tile0 = (size_t)blockIdx.x * NL_TILE;
-    const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t c = 0;
-#pragma unroll
-    for (int it = 0; it < NL_ITERS; it++) {
-        size_t pos = tile0 + ((size_t)(w * NL_ITERS + it) * 32 + lane) * 16;
-        if (pos < n) c += __popc(eq_mask16(load16_guard(text, pos, n), '\n'));
-    }
-    c = __reduce_add_sync(0xffffffffu, c);
-    __shared__ uint32_t ws[NL_T / 32];
-    if (lane == 0) ws[w] = c;
-    __syncthreads();
-    if (threadIdx.x == 0) { uint32_t s = 0; for (int i = 0; i < NL_T / 32; i++) s += ws[i]; bcount[blockIdx.x] = s; }
-}
-
-__global__ void __launch_bounds__(NL_T) nl_write_k(const char *__restrict__ text, size_t n, const uint32_t *__restrict__ boff,
-                                                    uint32_t *__restrict__ nlpos) {
-    const size_t tile0 = (size_t)blockIdx.x * NL_TILE;
-    const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t masks[NL_ITERS], cnt[NL_ITERS], wtot = 0;
-#pragma unroll
-    for (int it = 0; it < NL_ITERS; it++) {
-        size_t pos = tile0 + ((size_t)(w * NL_ITERS + it) * 32 + lane) * 16;
-        masks[it] = pos < n ? eq_mask16(load16_guard(text, pos, n), '\n') : 0;
-        cnt[it] = __popc(masks[it]);
-        wtot += cnt[it];
-    }
-    wtot = __reduce_add_sync(0xffffffffu, wtot);
-    __shared__ uint32_t ws[NL_T / 32];
-    if (lane == 0) ws[w] = wtot;
-    __syncthreads();
-    uint32_t base = boff[blockIdx.x];
-    for (unsigned i = 0; i < w; i++) base += ws[i];
-#pragma unroll
-    for (int it = 0; it < NL_ITERS; it++) {
-        uint32_t inc = cnt[it];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (unsigned)d) inc += t; }
-        uint32_t o = base + inc - cnt[it];
-        size_t pos = tile0 + ((size_t)(w * NL_ITERS + it) * 32 + lane) * 16;
-        uint32_t m = masks[it];
-        while (m) { int b = __ffs(m) - 1; m &= m - 1; nlpos[o++] = (uint32_t)(pos + b); }
-        base += __shfl_sync(0xffffffffu, inc, 31);
-    }
-}
 
 // ------------------------------------------------------------------------------------------------------------------
 // one thread per pat line: "chr \t idx \t pattern \t count [\t ...]"
@@ -281,18 +207,8 @@ extern "C" int wgbs_pats_from_text(wgbs_ctx *ctx, const char *text, size_t nbyte
     if (owned) T.v.push_back((void *)dtext);
     const uint32_t n = (uint32_t)nbytes;
     // 1. newline positions
-    unsigned ntiles = (unsigned)((nbytes + NL_TILE - 1) / NL_TILE); if (!ntiles) ntiles = 1;
-    uint32_t *bcount, *boff, *nlpos;
-    RC_TRY(T.alloc(&bcount, ntiles)); RC_TRY(T.alloc(&boff, ntiles + 1));
-    LAUNCH(ctx, nl_count_k, ntiles, NL_T, 0, dtext, nbytes, bcount);
-    RC_TRY(scan_u32_u32(ctx, bcount, boff, ntiles));
-    uint32_t n_nl = 0; char last = '\n';
-    CUDA_TRY(cudaMemcpyAsync(&n_nl, boff + ntiles, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (nbytes) CUDA_TRY(cudaMemcpyAsync(&last, dtext + nbytes - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    const uint32_t n_lines = n_nl + ((nbytes && last != '\n') ? 1 : 0);
-    RC_TRY(T.alloc(&nlpos, n_nl));
-    LAUNCH(ctx, nl_write_k, ntiles, NL_T, 0, dtext, nbytes, boff, nlpos);
+    uint32_t *nlpos = nullptr, n_nl = 0, n_lines = 0;
+    RC_TRY(find_lines(ctx, dtext, nbytes, T, &nlpos, &n_nl, &n_lines));
     // 2. per-line fields
     wgbs_pats *P = new wgbs_pats();
     P->n = n_lines;
@@ -334,7 +250,7 @@ extern "C" int wgbs_pats_download(wgbs_ctx *ctx, const wgbs_pats *P, uint32_t *i
     if (idx) RC_TRY(copy_any(ctx, idx, P->idx, P->n * 4));
     if (len) RC_TRY(copy_any(ctx, len, P->len, P->n * 4));
     if (count) RC_TRY(copy_any(ctx, count, P->count, P->n * 4));
-    if (off) RC_TRY(copy_any(ctx, off, P->off, (P->n + 1) * 4));
+    if (off) RC_TRY(copy_any(ctx, off, P->off, P->n * 4));
     if (pool) RC_TRY(copy_any(ctx, pool, P->pool, P->pool_words * 4));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return 0;

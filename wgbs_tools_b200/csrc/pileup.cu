@@ -1,0 +1,369 @@
+// pileup.cu -- the bam->pat pileup: per-record CIGAR walk + CpG-index lookup + C/T call, mate merge, template filter.
+//
+// Reference behaviour restated (paths relative to the reference's src/pipeline_wgbs/):
+//   patter_utils.cpp:209-251  clean_CIGAR        -> cig_validate / CigCursor (no adjusted string is materialised)
+//   patter_utils.cpp:163-168  is_bottom          -> is_bottom
+//   patter.cpp:96-184         is_cpg / compareSeqToRef -> pileup_call_k
+//   patter_utils.cpp:292-342  merge_PE (+strip)  -> merge_templates_k
+//   patter.cpp:247-290        proc2lines (min_cpg filter, counters) -> merge_templates_k
+//   patter.cpp:14-42,81-93    CpG dictionary: unordered_map + bool conv[chromlen]  -> sorted uint32 loci[] + binary search
+//
+// One thread per record.  CIGAR and SEQ bytes are read in place from the SAM text buffer.  Calls are written as 2-bit
+// symbols into a word pool (layout: include/wgbs_b200.h).
+#include "reads.cuh"
+
+int build_mates(wgbs_ctx *ctx, const ReadBatch &rb, bool paired, Temps &T, uint32_t **mate_out, unsigned long long *d_stats);
+int np_prepare(wgbs_ctx *ctx, const ReadBatch &rb, Temps &T);
+
+namespace {
+
+constexpr uint32_t NONE = 0xffffffffu;
+constexpr int MAX_PE_PAT_LEN = 300;     // patter_utils.h:21
+
+struct PileupOpts {
+    int min_cpg, clip, paired, nanopore, combine_mods;
+    float np_thresh;
+    char cpc_call;
+};
+
+__device__ __forceinline__ bool is_bottom(int flag, int paired) {
+    if (paired) return ((flag & 0x53) == 83) || ((flag & 0xA3) == 163);
+    return (flag & 0x10) == 16;
+}
+
+// ---- CIGAR ---------------------------------------------------------------------------------------------------------
+// clean_CIGAR throws (-> read counted invalid) when: an op char has no number before it, the number overflows int,
+// the op is not one of M = X D N I S H, or an M/=/X/I/S op consumes more read bases than remain.
+__device__ bool cig_validate(const char *__restrict__ t, uint32_t p, uint32_t e, uint32_t seq_len, int64_t *span_out) {
+    int64_t span = 0, q = 0;
+    bool ok = true;
+    uint64_t num = 0; bool have = false;
+    for (; p < e; p++) {
+        char c = t[p];
+        if (c >= '0' && c <= '9') { num = num * 10 + (uint64_t)(c - '0'); if (num > 0x7fffffffull) num = 0x80000000ull; have = true; continue; }
+        if (!have || num > 0x7fffffffull) { ok = false; break; }
+        if (c == 'M' || c == '=' || c == 'X' || c == 'I' || c == 'S') {
+            if ((int64_t)num > (int64_t)seq_len - q) ok = false;       // checked after the tokenising phase in the reference; same verdict
+            q += (int64_t)num;
+            if (c != 'I' && c != 'S') span += (int64_t)num;
+        } else if (c == 'D' || c == 'N') span += (int64_t)num;
+        else if (c == 'H') {}
+        else ok = false;
+        num = 0; have = false;
+    }
+    // an M op that overruns still appended the available bases before throwing; irrelevant: the read is invalid
+    *span_out = span;
+    return ok;
+}
+
+struct CigCursor {
+    const char *t; uint32_t p, e;
+    int64_t r0, q0, len;   // current ref-consuming op covers ref offsets [r0, r0+len); its first read base is q0 (op 'M')
+    char op;               // 'M' (M,=,X) or 'D' (D,N); 0 before the first op
+    __device__ void init(const char *text, uint32_t off, uint32_t n) { t = text; p = off; e = off + n; r0 = 0; q0 = 0; len = 0; op = 0; }
+    // position on the op covering ref offset x (x must be non-decreasing across calls); false past the end
+    __device__ bool seek(int64_t x) {
+        while (true) {
+            if (x < r0 + len) return true;
+            // leave the current op
+            r0 += len; if (op == 'M') q0 += len;
+            len = 0; op = 0;
+            // next op
+            bool found = false;
+            while (p < e) {
+                int64_t num = 0;
+                while (p < e && t[p] >= '0' && t[p] <= '9') { num = num * 10 + (t[p] - '0'); p++; }
+                if (p >= e) break;
+                char c = t[p++];
+                if (c == 'M' || c == '=' || c == 'X') { op = 'M'; len = num; found = true; break; }
+                if (c == 'D' || c == 'N') { op = 'D'; len = num; found = true; break; }
+                if (c == 'I' || c == 'S') q0 += num;
+            }
+            if (!found) return false;
+        }
+    }
+};
+
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *__restrict__ a, uint32_t n, int64_t key) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { uint32_t m = (lo + hi) >> 1; if ((int64_t)a[m] < key) lo = m + 1; else hi = m; }
+    return lo;
+}
+
+// ---- pass 1: validity, reference span, candidate CpG range ---------------------------------------------------------
+__global__ void __launch_bounds__(256) pileup_measure_k(ReadBatchView rb, const uint32_t *__restrict__ loci, uint32_t nloci, PileupOpts o,
+                                                         const uint8_t *__restrict__ np_bad, uint32_t *__restrict__ r_lo, uint32_t *__restrict__ r_ncand,
+                                                         uint32_t *__restrict__ words, unsigned long long *__restrict__ stats) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t inval = 0;
+    if (r < rb.n) {
+        uint32_t lo = 0, nc = 0;
+        uint8_t st = rb.status[r];
+        if (st == REC_INVALID) inval = 1;
+        else if (st == REC_OK) {
+            int64_t span = 0;
+            bool ok = cig_validate(rb.text, rb.cig_off[r], rb.cig_off[r] + rb.cig_len[r], rb.seq_len[r], &span);
+            if (o.nanopore && np_bad && np_bad[r] == 2) ok = false;          // MM/ML parse error or unsupported base
+            if (!ok) inval = 1;
+            else if (!(o.nanopore && np_bad && np_bad[r] == 1)) {              // np: 1 = "empty" verdict before the walk
+                int64_t pos = rb.pos[r];
+                // np bottom-strand reads also look at the CpG whose G is the first aligned base (ont.cpp:142-145)
+                int64_t first = (o.nanopore && ((rb.flag[r] & 0x10) == 16)) ? pos - 1 : pos;
+                lo = lower_bound_u32(loci, nloci, first);
+                uint32_t hi = lower_bound_u32(loci, nloci, pos + span);
+                nc = hi > lo ? hi - lo : 0;
+            }
+        }
+        r_lo[r] = lo; r_ncand[r] = inval ? NONE : nc;
+        words[r] = inval ? 0 : (nc + 15) >> 4;
+    }
+    for (int d = 16; d >= 1; d >>= 1) inval += __shfl_xor_sync(0xffffffffu, inval, d);
+    if ((threadIdx.x & 31) == 0 && inval) atomicAdd(&stats[ST_INVALID], (unsigned long long)inval);
+}
+
+// merged-slot size of a template head (bounded by MAX_PE_PAT_LEN symbols: longer merges are dropped)
+__global__ void __launch_bounds__(256) template_words_k(uint32_t n, const uint32_t *__restrict__ mate, const uint32_t *__restrict__ r_lo,
+                                                         const uint32_t *__restrict__ r_ncand, uint32_t *__restrict__ words_t) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    uint32_t m = mate[r], w = 0;
+    if (m != NONE && r < m && r_ncand[r] != NONE && r_ncand[m] != NONE && r_ncand[r] && r_ncand[m]) {
+        uint32_t lo = min(r_lo[r], r_lo[m]), hi = max(r_lo[r] + r_ncand[r], r_lo[m] + r_ncand[m]);
+        uint32_t u = min(hi - lo, (uint32_t)MAX_PE_PAT_LEN);
+        w = (u + 15) >> 4;
+    }
+    words_t[r] = w;
+}
+
+// ---- pass 2: the calls ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pileup_call_k(ReadBatchView rb, const uint32_t *__restrict__ loci, uint32_t first_idx, PileupOpts o,
+                                                      const uint32_t *__restrict__ r_lo, const uint32_t *__restrict__ r_ncand,
+                                                      const uint32_t *__restrict__ off, uint32_t *__restrict__ pool,
+                                                      int32_t *__restrict__ r_idx, uint32_t *__restrict__ r_len,
+                                                      unsigned long long *__restrict__ stats) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t empty = 0;
+    if (r < rb.n && rb.status[r] == REC_OK && r_ncand[r] != NONE) {
+        const uint32_t nc = r_ncand[r], lo = r_lo[r];
+        const int64_t pos = rb.pos[r];
+        const int flag = rb.flag[r];
+        const bool bottom = is_bottom(flag, o.paired);
+        int64_t span; cig_validate(rb.text, rb.cig_off[r], rb.cig_off[r] + rb.cig_len[r], rb.seq_len[r], &span);
+        CigCursor cc; cc.init(rb.text, rb.cig_off[r], rb.cig_len[r]);
+        const char *seq = rb.text + rb.seq_off[r];
+        uint32_t *wp = pool + off[r];
+        int32_t first = -1, last = -1;      // candidate ordinals of the first / last called ('C'/'T') site
+        uint32_t w = 0; int32_t nsym = 0;   // symbols emitted since `first`
+        for (uint32_t j = 0; j < nc; j++) {
+            const int64_t i = (int64_t)loci[lo + j] - pos;     // offset of the CpG's C in the reference-projected read
+            // adj[i] and adj[i+1]
+            char c0 = 0, c1 = 0;
+            if (cc.seek(i)) c0 = cc.op == 'M' ? seq[cc.q0 + (i - cc.r0)] : 'N';
+            if (i + 1 < span && cc.seek(i + 1)) c1 = cc.op == 'M' ? seq[cc.q0 + (i + 1 - cc.r0)] : 'N';
+            uint32_t code = SYM_DOT;
+            int64_t jx;
+            if (!bottom) {      // OT: C/T at the C position, G must follow (patter.cpp:96-103 is_cpg, shift 0)
+                jx = i;
+                if ((i < span - 1) && c1 == 'G') code = c0 == 'T' ? SYM_T : (c0 == 'C' ? SYM_C : SYM_DOT);
+            } else {            // OB: G/A at the G position, C must precede (shift 1)
+                jx = i + 1;
+                if (c0 == 'C') code = c1 == 'A' ? SYM_T : (c1 == 'G' ? SYM_C : SYM_DOT);
+            }
+            if (!((jx >= o.clip) && (jx < span - o.clip))) code = SYM_DOT;     // patter.cpp:169-172
+            if (first < 0) { if (code == SYM_DOT) continue; first = (int32_t)j; }
+            if (code != SYM_DOT) last = (int32_t)j;
+            w |= code << (30 - 2 * (nsym & 15));
+            if ((++nsym & 15) == 0) { *wp++ = w; w = 0; }
+        }
+        if (nsym & 15) *wp = w;
+        if (first < 0) { r_idx[r] = 0; r_len[r] = 0; empty = 1; }
+        else { r_idx[r] = (int32_t)(first_idx + lo + (uint32_t)first); r_len[r] = (uint32_t)(last - first + 1); }
+    } else if (r < rb.n) { r_idx[r] = 0; r_len[r] = 0; }
+    for (int d = 16; d >= 1; d >>= 1) empty += __shfl_xor_sync(0xffffffffu, empty, d);
+    if ((threadIdx.x & 31) == 0 && empty) atomicAdd(&stats[ST_EMPTY], (unsigned long long)empty);
+}
+
+// ---- mate merge + min_cpg filter ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t get_sym(const uint32_t *__restrict__ wp, uint32_t k) { return (wp[k >> 4] >> (30 - 2 * (k & 15))) & 3u; }
+
+__global__ void __launch_bounds__(256) merge_templates_k(uint32_t n, const uint8_t *__restrict__ status, const uint32_t *__restrict__ mate,
+                                                          PileupOpts o, const int32_t *__restrict__ r_idx, const uint32_t *__restrict__ r_len,
+                                                          const uint32_t *__restrict__ off /*[2n+1]*/, uint32_t *__restrict__ pool,
+                                                          uint32_t *__restrict__ t_idx, uint32_t *__restrict__ t_len, uint32_t *__restrict__ t_off,
+                                                          uint32_t *__restrict__ t_valid, unsigned long long *__restrict__ stats) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t nshort = 0;
+    if (r < n) {
+        uint32_t valid = 0, oi = 0, ol = 0, oo = 0;
+        const uint32_t m = mate[r];
+        if (status[r] != REC_BLANK && (m == NONE || r < m)) {          // r is a template head
+            const uint32_t la = r_len[r], lb = m == NONE ? 0 : r_len[m];
+            if (la && !lb) { oi = (uint32_t)r_idx[r]; ol = la; oo = off[r]; valid = 1; }
+            else if (lb && !la) { oi = (uint32_t)r_idx[m]; ol = lb; oo = off[m]; valid = 1; }
+            else if (la && lb) {
+                // merge_PE: l1 = the mate that starts first
+                uint32_t a = r, b = m;
+                if (r_idx[a] > r_idx[b]) { a = m; b = r; }
+                const int32_t s1 = r_idx[a], s2 = r_idx[b];
+                const uint32_t l1 = r_len[a], l2 = r_len[b];
+                const int32_t lastp = max(s1 + (int32_t)l1, s2 + (int32_t)l2);
+                const int32_t tot = lastp - s1;
+                if (tot <= MAX_PE_PAT_LEN) {                             // else: "merged read is too long" -> dropped, not counted
+                    const uint32_t *pa = pool + off[a], *pb = pool + off[b];
+                    uint32_t *po = pool + off[n + r];
+                    const uint32_t d = (uint32_t)(s2 - s1);
+                    int32_t first = -1, lastk = -1;
+                    // first pass: locate the first / last non-'.' merged symbol (conflicts become '.')
+                    for (int32_t k = 0; k < tot; k++) {
+                        uint32_t x = (uint32_t)k < l1 ? get_sym(pa, k) : 0;
+                        uint32_t y = ((uint32_t)k >= d && (uint32_t)k - d < l2) ? get_sym(pb, k - d) : 0;
+                        uint32_t z = x == 0 ? y : (y == 0 || y == x ? x : 0);
+                        if (z) { if (first < 0) first = k; lastk = k; }
+                    }
+                    if (first >= 0) {
+                        uint32_t w = 0; int32_t ns = 0;
+                        for (int32_t k = first; k <= lastk; k++) {
+                            uint32_t x = (uint32_t)k < l1 ? get_sym(pa, k) : 0;
+                            uint32_t y = ((uint32_t)k >= d && (uint32_t)k - d < l2) ? get_sym(pb, k - d) : 0;
+                            uint32_t z = x == 0 ? y : (y == 0 || y == x ? x : 0);
+                            w |= z << (30 - 2 * (ns & 15));
+                            if ((++ns & 15) == 0) { *po++ = w; w = 0; }
+                        }
+                        if (ns & 15) *po = w;
+                        oi = (uint32_t)(s1 + first); ol = (uint32_t)(lastk - first + 1); oo = off[n + r]; valid = 1;
+                    }
+                }
+            }
+            if (valid && (int32_t)ol < o.min_cpg) { valid = 0; nshort = 1; }   // patter.cpp:264-267
+        }
+        t_idx[r] = oi; t_len[r] = ol; t_off[r] = oo; t_valid[r] = valid;
+    }
+    for (int d = 16; d >= 1; d >>= 1) nshort += __shfl_xor_sync(0xffffffffu, nshort, d);
+    if ((threadIdx.x & 31) == 0 && nshort) atomicAdd(&stats[ST_SHORT], (unsigned long long)nshort);
+}
+
+__global__ void __launch_bounds__(256) compact_templates_k(uint32_t n, const uint32_t *__restrict__ t_valid, const uint32_t *__restrict__ dst,
+                                                            const uint32_t *__restrict__ t_idx, const uint32_t *__restrict__ t_len,
+                                                            const uint32_t *__restrict__ t_off, uint32_t *__restrict__ o_idx,
+                                                            uint32_t *__restrict__ o_len, uint32_t *__restrict__ o_off, uint32_t *__restrict__ o_cnt) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n || !t_valid[r]) return;
+    uint32_t k = dst[r];
+    o_idx[k] = t_idx[r]; o_len[k] = t_len[r]; o_off[k] = t_off[r]; o_cnt[k] = 1;
+}
+
+}  // namespace
+
+// ====================================================================================================================
+// C ABI
+// ====================================================================================================================
+extern "C" int wgbs_index_load(wgbs_ctx *ctx, const uint32_t *loci, size_t n, uint32_t first_idx, wgbs_index **out) {
+    RC_TRY(wgbs_ctx_activate(ctx));
+    if (!out) return wgbs_set_err("wgbs_index_load: out is null");
+    if (n >= 0x7fffffffull) return wgbs_set_err("wgbs_index_load: too many loci");
+    wgbs_index *ix = new wgbs_index();
+    ix->n = (uint32_t)n; ix->first_idx = first_idx;
+    int rc = dalloc(ctx, &ix->loci, n);
+    if (rc == 0) rc = copy_any(ctx, ix->loci, loci, n * 4);
+    if (rc < 0) { dfree(ctx, ix->loci); delete ix; return rc; }
+    *out = ix;
+    return 0;
+}
+extern "C" void wgbs_index_free(wgbs_ctx *ctx, wgbs_index *ix) {
+    if (!ix || !ctx) return;
+    cudaSetDevice(ctx->device);
+    dfree(ctx, ix->loci);
+    delete ix;
+}
+
+extern "C" int wgbs_pileup_sam(wgbs_ctx *ctx, const wgbs_index *ix, const char *sam, size_t nbytes, const wgbs_pileup_opts *opts,
+                               wgbs_pats **out, uint64_t *stats_out) {
+    RC_TRY(wgbs_ctx_activate(ctx));
+    if (!ix || !opts || !out) return wgbs_set_err("wgbs_pileup_sam: null argument");
+    *out = nullptr;
+    Temps T(ctx);
+    const void *dv = nullptr; bool owned = false;
+    RC_TRY(to_device(ctx, sam, nbytes, &dv, &owned));
+    const char *dtext = (const char *)dv;
+    if (owned) T.v.push_back((void *)dtext);
+
+    // first_line (patter.cpp:324-350) needs the first non-empty line's FLAG and whether it carries an MM tag; the
+    // tokenizer always records tags so that auto-detection and the MM/ML path share one pass.
+    ReadBatch rb;
+    RC_TRY(sam_tokenize(ctx, dtext, nbytes, true, T, &rb));
+    const uint32_t n = rb.n;
+    unsigned long long *d_stats;
+    RC_TRY(T.alloc(&d_stats, ST_N));
+    CUDA_TRY(cudaMemsetAsync(d_stats, 0, ST_N * 8, ctx->stream));
+
+    PileupOpts o;
+    o.min_cpg = opts->min_cpg; o.clip = opts->clip; o.nanopore = opts->nanopore; o.combine_mods = opts->combine_mods;
+    o.np_thresh = opts->np_thresh; o.cpc_call = opts->cpc_call ? opts->cpc_call : 'C';
+    o.paired = opts->paired;
+    {
+        // host-side peek at the head of the batch (tiny D2H): first non-blank record
+        const uint32_t PEEK = 64;
+        uint32_t m = n < PEEK ? n : PEEK;
+        std::vector<uint8_t> st(m); std::vector<int32_t> fl(m); std::vector<uint32_t> mml(m);
+        if (m) {
+            CUDA_TRY(cudaMemcpyAsync(st.data(), rb.status, m, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(fl.data(), rb.flag, m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(mml.data(), rb.mm_len, m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        }
+        uint32_t f = 0; while (f < m && st[f] == REC_BLANK) f++;
+        if (f < m) {
+            if (st[f] == REC_INVALID && o.paired < 0) return wgbs_set_err("Invalid first line (cannot determine paired/single end)");
+            if (o.paired < 0) o.paired = ((uint16_t)fl[f]) & 1;
+            if (mml[f] > 0) o.nanopore = 1;
+        } else if (o.paired < 0) o.paired = 0;
+        if (o.paired && o.nanopore) return wgbs_set_err("Unrecognized bam format: paired end and nanopore");   // patter.cpp:341-343
+    }
+
+    uint32_t *mate = nullptr;
+    RC_TRY(build_mates(ctx, rb, o.paired != 0, T, &mate, d_stats));
+
+    uint8_t *np_bad = nullptr;
+    if (o.nanopore) return wgbs_set_err("wgbs_pileup_sam: MM/ML (nanopore) mode is not built yet");
+
+    uint32_t *r_lo, *r_ncand, *words, *off;
+    RC_TRY(T.alloc(&r_lo, n)); RC_TRY(T.alloc(&r_ncand, n)); RC_TRY(T.alloc(&words, (size_t)2 * n)); RC_TRY(T.alloc(&off, (size_t)2 * n + 1));
+    if (n) {
+        LAUNCH(ctx, pileup_measure_k, grid_for(n, 256), 256, 0, view_of(rb), ix->loci, ix->n, o, np_bad, r_lo, r_ncand, words, d_stats);
+        LAUNCH(ctx, template_words_k, grid_for(n, 256), 256, 0, n, mate, r_lo, r_ncand, words + n);
+    }
+    RC_TRY(scan_u32_u32(ctx, words, off, (size_t)2 * n));
+    uint32_t pool_words = 0;
+    CUDA_TRY(cudaMemcpyAsync(&pool_words, off + (size_t)2 * n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+
+    wgbs_pats *P = new wgbs_pats();
+    int rc = dalloc(ctx, &P->pool, pool_words);
+    if (rc < 0) { delete P; return rc; }
+    P->pool_words = pool_words;
+    int32_t *r_idx; uint32_t *r_len, *t_idx, *t_len, *t_off, *t_valid, *dst;
+    if ((rc = T.alloc(&r_idx, n)) < 0 || (rc = T.alloc(&r_len, n)) < 0 || (rc = T.alloc(&t_idx, n)) < 0 || (rc = T.alloc(&t_len, n)) < 0 ||
+        (rc = T.alloc(&t_off, n)) < 0 || (rc = T.alloc(&t_valid, n)) < 0 || (rc = T.alloc(&dst, (size_t)n + 1)) < 0) { wgbs_pats_free(ctx, P); return rc; }
+    if (n) {
+        LAUNCH(ctx, pileup_call_k, grid_for(n, 256), 256, 0, view_of(rb), ix->loci, ix->first_idx, o, r_lo, r_ncand, off, P->pool, r_idx, r_len, d_stats);
+        LAUNCH(ctx, merge_templates_k, grid_for(n, 256), 256, 0, n, rb.status, mate, o, r_idx, r_len, off, P->pool, t_idx, t_len, t_off, t_valid, d_stats);
+    }
+    if ((rc = scan_u32_u32(ctx, t_valid, dst, n)) < 0) { wgbs_pats_free(ctx, P); return rc; }
+    uint32_t n_out = 0;
+    unsigned long long hstats[ST_N];
+    CUDA_TRY(cudaMemcpyAsync(&n_out, dst + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(hstats, d_stats, sizeof hstats, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    P->n = n_out;
+    if ((rc = dalloc(ctx, &P->idx, n_out)) < 0 || (rc = dalloc(ctx, &P->len, n_out)) < 0 || (rc = dalloc(ctx, &P->count, n_out)) < 0 ||
+        (rc = dalloc(ctx, &P->off, (size_t)n_out + 1)) < 0) { wgbs_pats_free(ctx, P); return rc; }
+    if (n) LAUNCH(ctx, compact_templates_k, grid_for(n, 256), 256, 0, n, t_valid, dst, t_idx, t_len, t_off, P->idx, P->len, P->off, P->count);
+    LAUNCH_CHECK();
+    if (stats_out) {
+        stats_out[0] = n;                       // lines (patter counts blank lines too)
+        stats_out[1] = hstats[ST_PAIRS]; stats_out[2] = hstats[ST_EMPTY]; stats_out[3] = hstats[ST_SHORT];
+        stats_out[4] = hstats[ST_INVALID]; stats_out[5] = (uint64_t)o.paired; stats_out[6] = (uint64_t)o.nanopore; stats_out[7] = n_out;
+    }
+    *out = P;
+    return 0;
+}

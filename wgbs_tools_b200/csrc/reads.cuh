@@ -1,0 +1,53 @@
+// reads.cuh -- device-side description of a batch of alignment records and of the templates built from them.
+#pragma once
+#include <stdint.h>
+
+#include "common.cuh"
+#include "pats.cuh"
+
+// status of a record
+enum : uint8_t { REC_OK = 0, REC_INVALID = 1, REC_BLANK = 2 /* empty input line: counted, never processed */ };
+
+// One entry per SAM line.  All *_off are byte offsets into the SAM text buffer (which stays resident: the pileup
+// reads CIGAR and SEQ bytes straight from it, nothing is re-packed).
+struct ReadBatch {
+    const char *text = nullptr;  // device
+    uint32_t nbytes = 0;
+    uint32_t n = 0;              // records (lines)
+    uint32_t *line_off = nullptr, *line_len = nullptr;
+    uint32_t *qn_len = nullptr;
+    int32_t *flag = nullptr, *pos = nullptr;
+    uint32_t *cig_off = nullptr, *cig_len = nullptr, *seq_off = nullptr, *seq_len = nullptr;
+    uint32_t *hash_lo = nullptr, *hash_hi = nullptr;
+    uint32_t *mm_off = nullptr, *mm_len = nullptr, *ml_off = nullptr, *ml_len = nullptr;  // MM:Z: / ML:B:C payloads (len 0: absent)
+    uint8_t *status = nullptr;
+};
+
+struct ReadBatchView {
+    const char *text; uint32_t nbytes, n;
+    const uint32_t *line_off, *line_len, *qn_len;
+    const int32_t *flag, *pos;
+    const uint32_t *cig_off, *cig_len, *seq_off, *seq_len, *hash_lo, *hash_hi, *mm_off, *mm_len, *ml_off, *ml_len;
+    const uint8_t *status;
+};
+static inline ReadBatchView view_of(const ReadBatch &b) {
+    return ReadBatchView{b.text, b.nbytes, b.n, b.line_off, b.line_len, b.qn_len, b.flag, b.pos, b.cig_off, b.cig_len, b.seq_off,
+                         b.seq_len, b.hash_lo, b.hash_hi, b.mm_off, b.mm_len, b.ml_off, b.ml_len, b.status};
+}
+
+// CpG dictionary of one chromosome / region: sorted 1-based loci; CpG index of loci[k] is first_idx + k
+// (replaces patter's unordered_map + bool conv[chromlen], reference pipeline_wgbs/patter.cpp:14-42)
+struct wgbs_index {
+    uint32_t *loci = nullptr;  // device
+    uint32_t n = 0;
+    uint32_t first_idx = 1;
+};
+
+// counters (reference patter.h:28-34 reads_stats + line counter)
+enum { ST_LINES = 0, ST_PAIRS, ST_EMPTY, ST_SHORT, ST_INVALID, ST_TEMPLATES, ST_N = 8 };
+
+// sam.cu
+int sam_tokenize(wgbs_ctx *ctx, const char *dtext, size_t nbytes, bool want_tags, Temps &T, ReadBatch *out);
+// pair.cu: mate[r] = record id of the mate of r (0xffffffff: none)
+int build_mates(wgbs_ctx *ctx, const ReadBatch &rb, bool paired, Temps &T, uint32_t **mate_out,
+                unsigned long long *d_stats);

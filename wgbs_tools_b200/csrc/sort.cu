@@ -1,0 +1,152 @@
+// sort.cu -- stable LSD radix sort of (uint32 key, uint32 value) pairs, 8-bit digits, with digit-pass skipping.
+//
+// Used by: template pairing (sort records by 64-bit QNAME hash = two calls) and the collapse step, which replaces the
+// reference's `sort -k2,2n -k3,3` (python/bam2pat.py:99) by a sequence of these sorts over successive key words.
+//
+// Per pass: (a) per-CTA digit histogram, (b) exclusive scan of the digit-major histogram table, (c) stable scatter
+// using warp match_any ranking.  A pre-pass builds the global histogram of all four digits at once; a digit whose
+// histogram has a single non-empty bin is skipped (this is what makes sorting zero-padded pattern words cheap).
+#include "common.cuh"
+#include "sort.cuh"
+
+namespace {
+
+constexpr int RS_T = 256;             // threads per CTA
+constexpr int RS_IPT = 16;            // items per thread
+constexpr int RS_TILE = RS_T * RS_IPT;
+constexpr int RS_WARPS = RS_T / 32;
+
+__global__ void __launch_bounds__(RS_T) rs_global_hist_k(const uint32_t *__restrict__ keys, size_t n, uint32_t *__restrict__ ghist /*[4][256]*/) {
+    __shared__ uint32_t h[4 * 256];
+    for (int i = threadIdx.x; i < 1024; i += RS_T) h[i] = 0;
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * RS_T + threadIdx.x; i < n; i += (size_t)gridDim.x * RS_T) {
+        uint32_t k = keys[i];
+        atomicAdd(&h[k & 255], 1u); atomicAdd(&h[256 + ((k >> 8) & 255)], 1u);
+        atomicAdd(&h[512 + ((k >> 16) & 255)], 1u); atomicAdd(&h[768 + (k >> 24)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 1024; i += RS_T) if (h[i]) atomicAdd(&ghist[i], h[i]);
+}
+
+// (a) per-CTA histogram of one digit, written digit-major: table[d * nblocks + b]
+__global__ void __launch_bounds__(RS_T) rs_block_hist_k(const uint32_t *__restrict__ keys, size_t n, int shift, uint32_t nblocks,
+                                                         uint32_t *__restrict__ table) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const size_t base = (size_t)blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int j = 0; j < RS_IPT; j++) {
+        size_t i = base + (size_t)j * RS_T + threadIdx.x;
+        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255], 1u);
+    }
+    __syncthreads();
+    table[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// (c) stable scatter.  Warp w of the CTA owns the contiguous items [base + w*512, base + (w+1)*512): 16 rounds of 32.
+__global__ void __launch_bounds__(RS_T) rs_scatter_k(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, size_t n, int shift,
+                                                      uint32_t nblocks, const uint32_t *__restrict__ table_scanned,
+                                                      uint32_t *__restrict__ kout, uint32_t *__restrict__ vout) {
+    __shared__ uint32_t cnt[RS_WARPS][256];   // per-warp digit counts -> per-warp digit bases
+    const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_T) (&cnt[0][0])[i] = 0;
+    __syncthreads();
+    const size_t wbase = (size_t)blockIdx.x * RS_TILE + (size_t)w * (RS_IPT * 32);
+    uint32_t key[RS_IPT], val[RS_IPT];
+    uint16_t rank[RS_IPT];
+#pragma unroll
+    for (int j = 0; j < RS_IPT; j++) {
+        size_t i = wbase + (size_t)j * 32 + lane;
+        bool ok = i < n;
+        key[j] = ok ? kin[i] : 0xffffffffu;
+        val[j] = ok ? vin[i] : 0;
+        uint32_t d = ok ? ((key[j] >> shift) & 255) : 256;          // 256: inactive lanes form their own group
+        uint32_t peers = __match_any_sync(0xffffffffu, d);
+        uint32_t below = __popc(peers & ((1u << lane) - 1));
+        int leader = __ffs(peers) - 1;
+        uint32_t b = 0;
+        if (ok && (int)lane == leader) { b = cnt[w][d]; cnt[w][d] = b + __popc(peers); }
+        b = __shfl_sync(0xffffffffu, b, leader);
+        rank[j] = (uint16_t)(b + below);
+        __syncwarp();
+    }
+    __syncthreads();
+    // digit d (one per thread): turn per-warp counts into global output bases in warp order
+    {
+        uint32_t d = threadIdx.x;
+        uint32_t run = table_scanned[(size_t)d * nblocks + blockIdx.x];
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ww++) { uint32_t c = cnt[ww][d]; cnt[ww][d] = run; run += c; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < RS_IPT; j++) {
+        size_t i = wbase + (size_t)j * 32 + lane;
+        if (i < n) {
+            uint32_t d = (key[j] >> shift) & 255;
+            uint32_t o = cnt[w][d] + rank[j];
+            kout[o] = key[j];
+            vout[o] = val[j];
+        }
+    }
+}
+
+__global__ void iota_k(uint32_t *p, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (uint32_t)i;
+}
+
+}  // namespace
+
+int fill_iota(wgbs_ctx *ctx, uint32_t *p, size_t n) {
+    if (n) { LAUNCH(ctx, iota_k, grid_for(n, 256), 256, 0, p, n); LAUNCH_CHECK(); }
+    return 0;
+}
+
+// Sorts in place in the sense that on return *keys / *vals point at the buffers holding the sorted data
+// (either the original pair or the alt pair).  Stable.  n < 2^32.
+int radix_sort_pairs(wgbs_ctx *ctx, uint32_t **keys, uint32_t **vals, uint32_t **keys_alt, uint32_t **vals_alt, size_t n) {
+    if (n < 2) return 0;
+    if (n >= 0xffffffffull) return wgbs_set_err("radix_sort_pairs: n too large");
+    Temps T(ctx);
+    uint32_t *ghist = nullptr;
+    RC_TRY(T.alloc(&ghist, 1024));
+    CUDA_TRY(cudaMemsetAsync(ghist, 0, 1024 * 4, ctx->stream));
+    unsigned hb = (unsigned)((n + RS_T * 8 - 1) / (RS_T * 8)); if (hb > (unsigned)ctx->sm_count * 8) hb = ctx->sm_count * 8;
+    LAUNCH(ctx, rs_global_hist_k, hb, RS_T, 0, *keys, n, ghist);
+    uint32_t hh[1024];
+    CUDA_TRY(cudaMemcpyAsync(hh, ghist, sizeof hh, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const uint32_t nblocks = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
+    uint32_t *table = nullptr, *table_s = nullptr;
+    for (int p = 0; p < 4; p++) {
+        bool uniform = false;
+        for (int b = 0; b < 256; b++) if (hh[p * 256 + b] == (uint32_t)n) { uniform = true; break; }
+        if (uniform) continue;
+        if (!table) { RC_TRY(T.alloc(&table, (size_t)256 * nblocks)); RC_TRY(T.alloc(&table_s, (size_t)256 * nblocks + 1)); }
+        LAUNCH(ctx, rs_block_hist_k, nblocks, RS_T, 0, *keys, n, p * 8, nblocks, table);
+        RC_TRY(scan_u32_u32(ctx, table, table_s, (size_t)256 * nblocks));
+        LAUNCH(ctx, rs_scatter_k, nblocks, RS_T, 0, *keys, *vals, n, p * 8, nblocks, table_s, *keys_alt, *vals_alt);
+        LAUNCH_CHECK();
+        uint32_t *t = *keys; *keys = *keys_alt; *keys_alt = t;
+        t = *vals; *vals = *vals_alt; *vals_alt = t;
+    }
+    return 0;
+}
+
+extern "C" int wgbs_sort_pairs_u32(wgbs_ctx *ctx, uint32_t *keys, uint32_t *vals, size_t n) {
+    RC_TRY(wgbs_ctx_activate(ctx));
+    if (!is_device_ptr(keys) || !is_device_ptr(vals)) return wgbs_set_err("wgbs_sort_pairs_u32: device pointers required");
+    Temps T(ctx);
+    uint32_t *ka, *va;
+    RC_TRY(T.alloc(&ka, n)); RC_TRY(T.alloc(&va, n));
+    uint32_t *k = keys, *v = vals, *k2 = ka, *v2 = va;
+    RC_TRY(radix_sort_pairs(ctx, &k, &v, &k2, &v2, n));
+    if (k != keys) {
+        CUDA_TRY(cudaMemcpyAsync(keys, k, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(vals, v, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return 0;
+}
