@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- bam2pat reads/s on BASELINE.json configs[1] (synthetic 150 bp PE WGBS reads, 1M records, chr19-sized
+CpG index) on N B200s, next to the reference's own CPU pipeline.
+
+A "step" = one pass of the whole bam2pat hot path over one batch of 1M alignment records per GPU:
+    SAM text -> tokenise -> pair mates -> CIGAR/CpG calls -> mate merge -> beta counts (+ NCCL reduce at N>1, + uint8 trim)
+             -> sort/collapse -> pat text
+`value`  : inputs resident in HBM, outputs left in HBM (device timed, CUDA events, max over ranks).
+`e2e`    : the same step through the public API with HOST buffers: pinned SAM text in, pat text + .beta bytes out.
+`--impl reference`: the reference's unmodified executables (oracle/_ref, flags of its setup.py) as
+    `match_maker | patter | sort -k2,2n -k3,3 | uniq -c | awk`, one pipeline per shard of the same workload, on the host cores.
+
+Multi-GPU (weak scaling): every rank piles up its own 1M-record batch over the same chromosome index (the reference
+shards the same way: one process per region, bam2pat.py:343); the only exchange is one NCCL reduce(sum) of the
+int32[nCpG,2] beta counts to rank 0, before the non-linear uint8 trim.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CHR = "chr19"
+CHR_LEN = 58_617_616
+N_CPG = 1_100_000
+METRIC = "bam2pat_reads_per_sec"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# workload
+# ----------------------------------------------------------------------------------------------------------------------
+_GENOME = None
+
+
+def genome():
+    global _GENOME
+    if _GENOME is None:
+        from wgbs_tools_b200 import synth
+        t = time.time()
+        _GENOME = synth.make_genome(19, CHR, CHR_LEN, n_cpg=N_CPG)
+        log(f"[bench] genome {CHR}: {CHR_LEN:,} bp, {_GENOME.n_cpg:,} CpGs ({time.time() - t:.1f}s)")
+    return _GENOME
+
+
+def make_batch(n_reads: int, seed: int) -> bytes:
+    from wgbs_tools_b200 import synth
+    t = time.time()
+    sam = synth.make_sam(genome(), n_reads, seed, paired=True)
+    log(f"[bench] SAM batch seed {seed}: {sam.count(10):,} records, {len(sam) / 1e6:.1f} MB ({time.time() - t:.1f}s)")
+    return sam
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.gpu, self.p, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.p.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the reference arm / CPU baseline  (the ONLY place bench.py executes oracle/: as the thing we are compared with)
+# ----------------------------------------------------------------------------------------------------------------------
+def reference_run(sam: bytes, shards: int, steps: int, warmup: int, opt: bool = False):
+    """Run the reference pipeline on `shards` contiguous shards of the workload concurrently; returns seconds per step."""
+    from oracle import harness as H
+    if not H.have_ref():
+        return None
+    g = genome()
+    tmp = tempfile.mkdtemp(prefix="wgbsref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    dpath = os.path.join(tmp, "CpG.bed")
+    with open(dpath, "wb") as f:
+        f.write(g.dict_text())
+    lines = sam.splitlines(keepends=True)
+    per = (len(lines) + shards - 1) // shards
+    paths = []
+    for s in range(shards):
+        chunk = lines[s * per:(s + 1) * per]
+        if not chunk:
+            continue
+        p = os.path.join(tmp, f"s{s}.sam")
+        with open(p, "wb") as f:
+            f.writelines(chunk)
+        paths.append(p)
+    env = dict(os.environ); env["PATH"] = H.SHIM + os.pathsep + env.get("PATH", ""); env["LC_ALL"] = "C"
+    cmd = (f"{H.tool('match_maker', opt)} < {{inp}} | {H.tool('patter', opt)} {dpath} {CHR} --min_cpg 1 --clip 0 2>/dev/null"
+           " | sort -k2,2n -k3,3 | uniq -c | awk -v OFS='\\t' '{{print $2,$3,$4,$1}}' > {inp}.pat")
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.time()
+        procs = [subprocess.Popen(cmd.format(inp=p), shell=True, env=env, stderr=subprocess.DEVNULL) for p in paths]
+        rcs = [p.wait() for p in procs]
+        dt = time.time() - t0
+        if any(rcs):
+            raise RuntimeError("reference pipeline failed")
+        if it >= warmup:
+            times.append(dt)
+    nlines = sum(1 for p in paths for _ in open(p + ".pat", "rb"))
+    subprocess.run(["rm", "-rf", tmp])
+    return float(np.mean(times)), len(paths), nlines
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# roofline bookkeeping: algorithmic bytes per launch of each hot kernel (DESIGN.md section "kernels")
+# ----------------------------------------------------------------------------------------------------------------------
+def algorithmic_bytes(kernel: str, n_rec: int, text_bytes: int, n_tmpl: int):
+    return {
+        "nl_count_k": text_bytes,                        # read the text once
+        "nl_write_k": text_bytes + 4 * n_rec,            # read the text, write one offset per line
+        "sam_fields_k": text_bytes + 52 * n_rec,         # read the text, write 13 descriptor words per record
+        "rs_scatter_k": 16 * n_rec,                      # (key,val) read + written
+        "rs_block_hist_k": 4 * n_rec,
+        "rs_global_hist_k": 4 * n_rec,
+        "pileup_measure_k": 36 * n_rec,
+        "pileup_call_k": 44 * n_rec,
+    }.get(kernel)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=1_000_000)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = f"bam2pat synthetic 150bp PE WGBS, {args.reads:,} records per GPU, {CHR} index ({N_CPG:,} CpGs)"
+    config = {"workload": workload, "records_per_gpu": args.reads, "read_len": 150, "paired": True, "n_cpg": N_CPG,
+              "sharding": "reads (one batch per GPU), beta counts NCCL-reduced" if args.gpus > 1 else "single GPU",
+              "l2": "inputs larger than L2 (SAM batch ~345 MB > 126 MB)"}
+
+    # ------------------------------------------------------------------------------------------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sam = make_batch(args.reads, 1000)
+        n_rec = sam.count(10)
+        cores = host_threads()
+        shards = max(1, min(cores // 4, 32))
+        r = reference_run(sam, shards, args.steps, args.warmup)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref executables missing"}))
+            return
+        sec, nsh, _ = r
+        val = n_rec / sec
+        unit = "reads/s"
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": val, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": "reference",
+                             "sample": f"whole batch ({n_rec:,} records) as {nsh} concurrent shard pipelines "
+                                       "(match_maker|patter|sort|uniq|awk, reference setup.py flags)"},
+            "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ------------------------------------------------------------------------------------------------------------------
+    import torch
+    import torch.distributed as dist
+    from wgbs_tools_b200.api import Context
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    g = genome()
+    sam = make_batch(args.reads, 1000 + rank)
+    n_rec = sam.count(10)
+    text_bytes = len(sam)
+    stream = torch.cuda.current_stream()
+    ctx = Context(local, stream=stream.cuda_stream)
+    ix = ctx.load_index(g.loci, 1)
+    start, end = 1, g.n_cpg + 1
+
+    h_sam = torch.frombuffer(bytearray(sam), dtype=torch.uint8).pin_memory()
+    d_sam = h_sam.cuda(non_blocking=False)
+    mc = torch.zeros((g.n_cpg, 2), dtype=torch.int32, device="cuda")
+    d_text = torch.empty(text_bytes // 4, dtype=torch.uint8, device="cuda")      # pat text is far smaller than the SAM text
+    d_beta = torch.empty((g.n_cpg, 2), dtype=torch.uint8, device="cuda")
+    h_text = torch.empty(text_bytes // 4, dtype=torch.uint8).pin_memory()
+    h_beta = torch.empty((g.n_cpg, 2), dtype=torch.uint8).pin_memory()
+    from wgbs_tools_b200._lib import PileupOpts, check, lib
+    import ctypes as C
+
+    last = {}
+
+    def run_step(host: bool):
+        src = h_sam if host else d_sam
+        o = PileupOpts(1, 0, -1, 0, 0, 0.67, b"C")
+        h = C.c_void_p(); st = (C.c_uint64 * 8)()
+        check(lib.wgbs_pileup_sam(ctx.h, ix.h, src.data_ptr(), text_bytes, C.addressof(o), C.byref(h), C.addressof(st)))
+        check(lib.wgbs_pat2beta(ctx.h, h, start, end, mc.data_ptr(), 1))
+        if world > 1:
+            dist.reduce(mc, dst=0, op=dist.ReduceOp.SUM)
+        bout = h_beta if host else d_beta
+        if rank == 0:
+            check(lib.wgbs_trim(ctx.h, mc.data_ptr(), g.n_cpg, 8, bout.data_ptr()))
+        check(lib.wgbs_collapse(ctx.h, h))
+        n = C.c_size_t()
+        tout = h_text if host else d_text
+        check(lib.wgbs_pats_format(ctx.h, h, CHR.encode(), tout.data_ptr(), tout.numel(), C.byref(n)))
+        last.update(text_bytes=n.value, stats=[int(x) for x in st])
+        lib.wgbs_pats_free(ctx.h, h)
+
+    def timed(host: bool, steps: int, warmup: int, sample_clocks: bool):
+        for _ in range(warmup):
+            run_step(host)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        cs = ClockSampler(local) if sample_clocks else None
+        if cs:
+            cs.start()
+        l0 = ctx.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            run_step(host)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        clocks = cs.stop() if cs else None
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), ctx.launches - l0, clocks
+
+    ms_dev, launches, clocks = timed(False, args.steps, args.warmup, True)
+    ms_e2e, _, _ = timed(True, args.steps, max(3, args.warmup), False)
+    nrec_t = torch.tensor([n_rec], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(nrec_t)
+    total_rec = int(nrec_t.item())
+    value = total_rec * args.steps / (ms_dev / 1e3)
+    e2e = total_rec * args.steps / (ms_e2e / 1e3)
+
+    # per-kernel breakdown (separate profiled steps: one event pair per launch)
+    roof = None
+    if rank == 0:
+        ctx.prof(True)
+        psteps = 3
+        for _ in range(psteps):
+            run_step(False)
+        rep = ctx.prof_report()
+        ctx.prof(False)
+        tot = sum(v[1] for v in rep.values())
+        top = sorted(rep.items(), key=lambda kv: -kv[1][1])
+        log("[bench] kernel breakdown (device ms per step, share):")
+        for k, (c, ms) in top[:12]:
+            log(f"    {k:24s} {c // psteps:4d} launches  {ms / psteps:8.3f} ms  {100 * ms / tot:5.1f}%")
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.isfile(peaks_path):
+            peak, how = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, how = 6650.0, "fallback (B200_PROFILING.md)"
+        dom, (dc, dms) = top[0]
+        ab = algorithmic_bytes(dom, n_rec, text_bytes, last["stats"][7])
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.isfile(tp):
+            traffic = json.load(open(tp)).get(dom)
+        if ab:
+            ach = ab / (dms / dc / 1e3) / 1e9
+            roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                    "peak_source": how, "algorithmic_bytes_per_launch": ab, "avg_launch_ms": dms / dc,
+                    "share_of_step": dms / tot,
+                    "breakdown_ms_per_step": {k: round(v[1] / psteps, 4) for k, v in top[:10]}}
+        else:
+            roof = {"bound": "hbm", "kernel": dom, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": traffic,
+                    "peak_source": how, "breakdown_ms_per_step": {k: round(v[1] / psteps, 4) for k, v in top[:10]}}
+
+    cpu = None
+    if rank == 0 and args.gpus == 1:
+        cores = host_threads()
+        shards = max(1, min(cores // 4, 32))
+        try:
+            r = reference_run(sam, shards, 1, 0)
+        except Exception as e:  # the baseline must not kill the bench line
+            log(f"[bench] cpu baseline failed: {e}")
+            r = None
+        if r:
+            sec, nsh, nlines = r
+            cpu = {"value": n_rec / sec, "unit": "reads/s", "cores": cores, "kind": "reference",
+                   "sample": f"whole batch ({n_rec:,} records) once, as {nsh} concurrent shard pipelines of the reference "
+                             "executables (match_maker|patter|sort|uniq|awk; reference setup.py flags, i.e. no -O)"}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": text_bytes, "d2h_bytes_per_step": last["text_bytes"] + 2 * g.n_cpg,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+            "outputs": {"pat_text_bytes": last["text_bytes"], "stats": dict(zip(["lines", "pairs", "empty", "short", "invalid", "paired", "nanopore", "templates"], last["stats"]))},
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

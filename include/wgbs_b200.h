@@ -45,6 +45,10 @@ void wgbs_destroy(wgbs_ctx *);
 int wgbs_sync(wgbs_ctx *);
 /* number of kernels this ctx has launched so far (bench.py's "gpu_launches") */
 uint64_t wgbs_launch_count(const wgbs_ctx *);
+/* per-kernel device timing (CUDA events on ctx's stream around every launch).  report: "kernel \t launches \t total_ms"
+ * lines for the launches since wgbs_prof_enable(ctx, 1); returns the number of bytes written. */
+int wgbs_prof_enable(wgbs_ctx *, int on);
+int wgbs_prof_report(wgbs_ctx *, char *buf, size_t cap);
 /* device memory helpers so that callers without torch can keep inputs resident in HBM */
 int wgbs_dev_alloc(wgbs_ctx *, size_t nbytes, void **dptr);
 int wgbs_dev_free(wgbs_ctx *, void *dptr);

@@ -35,6 +35,8 @@ def _load():
         "wgbs_destroy": (None, [vp]),
         "wgbs_sync": (C.c_int, [vp]),
         "wgbs_launch_count": (u64, [vp]),
+        "wgbs_prof_enable": (C.c_int, [vp, C.c_int]),
+        "wgbs_prof_report": (C.c_int, [vp, vp, sz]),
         "wgbs_dev_alloc": (C.c_int, [vp, sz, C.POINTER(vp)]),
         "wgbs_dev_free": (C.c_int, [vp, vp]),
         "wgbs_memcpy": (C.c_int, [vp, vp, vp, sz]),

@@ -91,12 +91,17 @@ class Pats:
         check(lib.wgbs_collapse(self.ctx.h, self.h))
         return self
 
-    def to_text(self, chrom: str) -> bytes:
+    def to_text(self, chrom: str, out=None):
+        """pat text.  out: optional preallocated host uint8 array or DevBuf (then the number of bytes is returned)."""
         n = C.c_size_t()
-        check(lib.wgbs_pats_format(self.ctx.h, self.h, chrom.encode(), None, 0, C.byref(n)))
-        out = np.empty(max(n.value, 1), np.uint8)
-        check(lib.wgbs_pats_format(self.ctx.h, self.h, chrom.encode(), out.ctypes.data, n.value, C.byref(n)))
-        return out[:n.value].tobytes()
+        if out is None:
+            check(lib.wgbs_pats_format(self.ctx.h, self.h, chrom.encode(), None, 0, C.byref(n)))
+            buf = np.empty(max(n.value, 1), np.uint8)
+            check(lib.wgbs_pats_format(self.ctx.h, self.h, chrom.encode(), buf.ctypes.data, n.value, C.byref(n)))
+            return buf[:n.value].tobytes()
+        cap = out.nbytes
+        check(lib.wgbs_pats_format(self.ctx.h, self.h, chrom.encode(), _addr(out), cap, C.byref(n)))
+        return n.value
 
     def free(self):
         if self.h:
@@ -151,6 +156,20 @@ class Context:
     @property
     def launches(self) -> int:
         return int(lib.wgbs_launch_count(self.h))
+
+    def prof(self, on: bool = True):
+        check(lib.wgbs_prof_enable(self.h, int(on)))
+
+    def prof_report(self) -> dict:
+        """{kernel: (launches, total_ms)} since prof(True)"""
+        buf = C.create_string_buffer(1 << 16)
+        n = lib.wgbs_prof_report(self.h, buf, len(buf))
+        check(n)
+        out = {}
+        for line in buf.raw[:n].decode().splitlines():
+            k, c, ms = line.split("\t")
+            out[k] = (int(c), float(ms))
+        return out
 
     # ---- memory -------------------------------------------------------------------------------------------------
     def alloc(self, nbytes: int) -> DevBuf:

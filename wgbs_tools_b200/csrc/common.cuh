@@ -39,12 +39,20 @@ struct wgbs_ctx {
     size_t pin_cap[2] = {0, 0};
     // small device scratch for flags / counters
     uint32_t *d_flags = nullptr;  // 64 words
+    // optional per-kernel timing (wgbs_prof_enable): one event pair per launch, aggregated by kernel name
+    bool prof = false;
+    struct ProfRec { const char *name; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> prof_recs;
 };
+void prof_begin(wgbs_ctx *ctx, const char *name);
+void prof_end(wgbs_ctx *ctx);
 
 // every kernel launch goes through this macro so ctx->launches is the number of OUR kernels launched
 #define LAUNCH(ctx, kern, grid, block, smem, ...)                              \
     do {                                                                       \
+        if ((ctx)->prof) prof_begin((ctx), #kern);                             \
         kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);         \
+        if ((ctx)->prof) prof_end((ctx));                                      \
         (ctx)->launches++;                                                     \
     } while (0)
 #define LAUNCH_CHECK() CUDA_TRY(cudaGetLastError())

@@ -74,6 +74,40 @@ extern "C" int wgbs_sync(wgbs_ctx *ctx) {
     return 0;
 }
 
+void prof_begin(wgbs_ctx *ctx, const char *name) {
+    wgbs_ctx::ProfRec r; r.name = name;
+    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, ctx->stream);
+    ctx->prof_recs.push_back(r);
+}
+void prof_end(wgbs_ctx *ctx) { cudaEventRecord(ctx->prof_recs.back().e1, ctx->stream); }
+
+extern "C" int wgbs_prof_enable(wgbs_ctx *ctx, int on) {
+    RC_TRY(wgbs_ctx_activate(ctx));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (auto &r : ctx->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    ctx->prof_recs.clear();
+    ctx->prof = on != 0;
+    return 0;
+}
+// "kernel \t launches \t total_ms \n" per kernel since wgbs_prof_enable(ctx, 1); returns bytes written (truncated to cap)
+extern "C" int wgbs_prof_report(wgbs_ctx *ctx, char *buf, size_t cap) {
+    RC_TRY(wgbs_ctx_activate(ctx));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    std::vector<std::string> names; std::vector<double> ms; std::vector<long> cnt;
+    for (auto &r : ctx->prof_recs) {
+        float t = 0; cudaEventElapsedTime(&t, r.e0, r.e1);
+        size_t k = 0; for (; k < names.size(); k++) if (names[k] == r.name) break;
+        if (k == names.size()) { names.push_back(r.name); ms.push_back(0); cnt.push_back(0); }
+        ms[k] += t; cnt[k]++;
+    }
+    std::string out;
+    for (size_t k = 0; k < names.size(); k++) { char line[256]; snprintf(line, sizeof line, "%s\t%ld\t%.6f\n", names[k].c_str(), cnt[k], ms[k]); out += line; }
+    size_t nb = out.size() < cap ? out.size() : (cap ? cap - 1 : 0);
+    if (buf && cap) { memcpy(buf, out.data(), nb); buf[nb] = 0; }
+    return (int)nb;
+}
+
 extern "C" uint64_t wgbs_launch_count(const wgbs_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int dmalloc(wgbs_ctx *ctx, void **p, size_t nbytes) {
