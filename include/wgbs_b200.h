@@ -130,6 +130,24 @@ int wgbs_pats_format(wgbs_ctx *, const wgbs_pats *, const char *chrom, char *out
 /* utility: stable radix sort of (key, value) uint32 pairs, device pointers */
 int wgbs_sort_pairs_u32(wgbs_ctx *, uint32_t *keys, uint32_t *vals, size_t n);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * segment   (replaces `segmentor B1.beta .. BK.beta -s START0 -n NSITES -max_cpg M -max_bp B -ps P < loci`,
+ *            reference src/segment_betas/{main,segmentor}.cpp; one call solves MANY chunks / stitching patches)
+ * betas: K pointers (host array) to uint8[nsites,2] beta arrays covering one site range (host or device memory;
+ *        device-resident arrays are used in place).  dists: uint32[nsites] bp locus of each site (the `tabix rev.CpG.bed.gz`
+ *        column the reference pipes to stdin, segment.py:53), non-decreasing inside a chunk.
+ * chunks: [start, start+n) site ranges relative to the arrays; each is an independent DP (segment.py:129-134).
+ * borders: int32, (n_c + 1) slots per chunk in chunk order; chunk c's borders (ascending, relative to its start,
+ *        first 0, last n_c -- exactly the line segmentor prints) occupy the first nborders[c] slots of its region.
+ * Errors: meth > cover anywhere (reference: `throw 0`), max_cpg >= 16384.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct wgbs_chunk { uint32_t start, n; } wgbs_chunk;
+int wgbs_segment(wgbs_ctx *, const uint8_t *const *betas, int K, const uint32_t *dists, size_t nsites,
+                 const wgbs_chunk *chunks, int nchunks, int max_cpg, uint32_t max_bp, float pseudo,
+                 int32_t *borders, int32_t *nborders);
+/* numerics self-test: log2f(p[i]) and log2(1.0 - (double)p[i]) exactly as glibc 2.39 (FMA build) computes them */
+int wgbs_glibc_log2_probe(wgbs_ctx *, const float *p, size_t n, float *out_log2f, double *out_log2_1mp);
+
 #ifdef __cplusplus
 }
 #endif

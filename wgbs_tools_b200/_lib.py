@@ -54,6 +54,8 @@ def _load():
         "wgbs_collapse": (C.c_int, [vp, vp]),
         "wgbs_pats_format": (C.c_int, [vp, vp, C.c_char_p, vp, sz, C.POINTER(sz)]),
         "wgbs_sort_pairs_u32": (C.c_int, [vp, vp, vp, sz]),
+        "wgbs_segment": (C.c_int, [vp, vp, C.c_int, vp, sz, vp, C.c_int, C.c_int, u32, C.c_float, vp, vp]),
+        "wgbs_glibc_log2_probe": (C.c_int, [vp, vp, sz, vp, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)

@@ -207,6 +207,32 @@ class Context:
         k.free(); v.free()
         return ko, vo
 
+    # ---- segment ------------------------------------------------------------------------------------------------
+    def segment(self, betas, dists, chunks, max_cpg: int, max_bp: int, pseudo: float):
+        """betas: list of K uint8[nsites,2] arrays (numpy, DevBuf or torch CUDA tensors) over one site range;
+        dists: uint32[nsites]; chunks: iterable of (start, n) relative to the arrays.
+        Returns a list of int64 border arrays (relative to each chunk's start), like `segmentor`'s stdout."""
+        K = len(betas)
+        keep = [np.ascontiguousarray(b, np.uint8) if isinstance(b, np.ndarray) else b for b in betas]
+        ptrs = (C.c_void_p * K)(*[_addr(b) for b in keep])
+        d = np.ascontiguousarray(dists, np.uint32) if isinstance(dists, np.ndarray) else dists
+        nsites = d.size if isinstance(d, np.ndarray) else d.nbytes // 4
+        ch = np.ascontiguousarray(np.asarray(list(chunks), dtype=np.uint32).reshape(-1, 2))
+        tot = int((ch[:, 1].astype(np.int64) + 1).sum())
+        borders = np.empty(max(tot, 1), np.int32); nb = np.empty(max(ch.shape[0], 1), np.int32)
+        check(lib.wgbs_segment(self.h, C.addressof(ptrs), K, _addr(d), nsites, ch.ctypes.data, ch.shape[0], int(max_cpg), int(max_bp),
+                               float(pseudo), borders.ctypes.data, nb.ctypes.data))
+        out = []; o = 0
+        for c in range(ch.shape[0]):
+            out.append(borders[o:o + nb[c]].astype(np.int64)); o += int(ch[c, 1]) + 1
+        return out
+
+    def glibc_log2_probe(self, p: np.ndarray):
+        p = np.ascontiguousarray(p, np.float32)
+        a = np.empty(p.size, np.float32); b = np.empty(p.size, np.float64)
+        check(lib.wgbs_glibc_log2_probe(self.h, p.ctypes.data, p.size, a.ctypes.data, b.ctypes.data))
+        return a, b
+
     # ---- pat ----------------------------------------------------------------------------------------------------
     def pats_from_text(self, text, nbytes: int | None = None) -> Pats:
         """text: bytes (host) or DevBuf (device-resident pat text)."""
