@@ -1,0 +1,100 @@
+"""Host-side mirrors of the reference's Python (segment.py stitching, homog.py thresholds / scaling) against golden
+vectors produced by the reference's own modules (tests/golden/make_golden.py).  CPU: the DP solver is the oracle port;
+the `-m gpu` variant runs the same flow on wgbs_segment."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from wgbs_tools_b200 import homog as hg
+from wgbs_tools_b200 import segment as sg
+from wgbs_tools_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _cases():
+    z = np.load(os.path.join(GOLD, "segment_stitch.npz"))
+    n = len({k.split("_")[0] for k in z.files})
+    return [{k.split("_", 1)[1]: z[k] for k in z.files if k.startswith(f"c{i}_")} for i in range(n)]
+
+
+def _inputs(c):
+    seed, N, K = int(c["seed"]), int(c["N"]), int(c["K"])
+    betas = synth.make_betas(100 + seed, K, N)
+    g = synth.make_genome(200 + seed, "chr1", 1_000_000, with_bases=False)
+    return betas, g.loci[:N]
+
+
+@pytest.mark.parametrize("i", range(5))
+def test_segment_stitching_matches_reference_golden_cpu(oracle, i):
+    c = _cases()[i]
+    betas, d = _inputs(c)
+    max_cpg, max_bp, ps = int(c["max_cpg"]), int(c["max_bp"]), float(c["ps"])
+
+    def solve(sites):
+        return [oracle.port_segment([x[s - 1:e - 1] for x in betas], d[s - 1:e - 1], max_cpg, max_bp, ps) + s for s, e in sites]
+
+    blocks = sg.segment_regions([(1, int(c["N"]) + 1)], solve, int(c["chunk"]))
+    merged = np.concatenate([blocks[:, 0], blocks[-1:, 1]])
+    np.testing.assert_array_equal(merged, c["merged"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("i", range(5))
+def test_segment_stitching_matches_reference_golden_gpu(ctx, i):
+    c = _cases()[i]
+    betas, d = _inputs(c)
+    solver = sg.GpuSolver(ctx, betas, d, int(c["max_cpg"]), int(c["max_bp"]), float(c["ps"]))
+    blocks = sg.segment_regions([(1, int(c["N"]) + 1)], solver, int(c["chunk"]))
+    solver.close()
+    merged = np.concatenate([blocks[:, 0], blocks[-1:, 1]])
+    np.testing.assert_array_equal(merged, c["merged"])
+
+
+def test_break_to_chunks_and_filters():
+    tags, s, e = sg.break_to_chunks([(1, 150_001), (200_000, 200_010)], 60_000)
+    assert s == [1, 60_001, 120_001, 200_000] and e == [60_001, 120_001, 150_001, 200_010]
+    assert tags == ["1-150001"] * 3 + ["200000-200010"]
+    assert sg.effective_max_cpg(1000, 2000) == 1000 and sg.effective_max_cpg(5000, 2000) == 1000
+    b = np.array([[1, 2], [2, 5], [5, 6]])
+    np.testing.assert_array_equal(sg.filter_min_cpg(b, 2), [[2, 5]])
+    assert sg.increase_patch(50, 60) == 60 and sg.increase_patch(60, 60) == 61 and sg.increase_patch(20, 100) == 40
+
+
+def test_homog_host_logic_matches_reference_golden():
+    G = json.load(open(os.path.join(GOLD, "homog_host.json")))
+    for l, s in G["rates"].items():
+        got, edges = hg.rate_edges(int(l))
+        assert got == s
+        assert edges.dtype == np.float32 and edges[0] == 0 and edges[-1] == 1
+    assert hg.rate_edges(3)[0] == "0,0.334,0.667,1"
+    assert hg.rate_edges(4, "0.25,0.75")[0] == "0,0.25,0.75,1"
+    d = np.array(G["trim_uxm"]["in"])
+    np.testing.assert_array_equal(hg.trim_uxm_to_uint8(d, 8), G["trim_uxm"]["u8"])
+    np.testing.assert_array_equal(hg.trim_uxm_to_uint8(d * 40, 16), G["trim_uxm"]["u16"])
+    with pytest.raises(hg.IllegalArgumentError):
+        hg.parse_range("0,0.5,0.4,1")
+    np.testing.assert_array_equal(hg.parse_range("0,0.334,0.667,1"), np.array([0, 0.334, 0.667, 1], np.float32))
+
+
+def test_homog_block_order_mirrors_sort_and_wrapper():
+    lines = [b"chr1\t10\t20\t7\t9\n", b"chr1\t1\t5\t2\t4\n", b"chr1\t10\t30\t7\t8\n", b"chr1\t6\t9\t5\t7\n"]
+    order = hg.sort_blocks_order(lines)
+    assert order.tolist() == [1, 3, 2, 0]                       # -k4,4n then -k5,5n
+    starts = np.array([7, 2, 7, 5])
+    counts_sorted = np.arange(12).reshape(4, 3)
+    back = hg.restore_block_order(counts_sorted, starts)
+    # homog.py:113-118 restores with a stable argsort of startCpG only: ties keep file order (reference behaviour)
+    assert back[1].tolist() == [0, 1, 2] and back[3].tolist() == [3, 4, 5]
+    assert not hg.blocks_are_sorted(starts, [9, 4, 8, 7]) and hg.blocks_are_sorted([1, 2, 2], [5, 3, 4])
+
+
+@pytest.mark.gpu
+def test_trim_golden_on_gpu(ctx):
+    G = json.load(open(os.path.join(GOLD, "homog_host.json")))
+    mc = np.array(G["trim_beta"]["in"], np.int64)
+    ok = mc.max(axis=1) < 2 ** 31
+    np.testing.assert_array_equal(ctx.trim(mc[ok].astype(np.int32), int(ok.sum()), 8), np.array(G["trim_beta"]["u8"])[ok])
+    np.testing.assert_array_equal(ctx.trim(mc[ok].astype(np.int32), int(ok.sum()), 16), np.array(G["trim_beta"]["u16"])[ok])

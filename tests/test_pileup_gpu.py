@@ -160,3 +160,57 @@ def test_tutorial_like_real_cigars(ctx, oracle, genome):
     _, pst = H.port_patter(sam, g.loci, g.idx())
     assert [st[k] for k in ("lines", "pairs", "empty", "short", "invalid", "paired")] == pst
     assert st["invalid"] > 100
+
+
+# ---- MM/ML (modification-aware) mode -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("kw", [dict(), dict(combine_mods=True), dict(cpc_call="H"), dict(np_thresh=0.8), dict(clip=3), dict(min_cpg=3)])
+def test_np_pileup_matches_reference(ctx, oracle, genome, kw):
+    H = oracle
+    sam = synth.make_np_sam(genome, 6000, 5)
+    rkw = dict(kw); rkw.setdefault("np_thresh", 0.67)
+    ref_raw, ref_txt = _oracle_pat(H, genome, sam, False, nanopore=True, **rkw)
+    raw, txt, st = _gpu_pat(ctx, genome, sam, nanopore=True, **rkw)
+    assert txt == ref_txt and len(txt) > 5000
+    _, pst = H.port_patter(sam, genome.loci, genome.idx(), nanopore=True, **rkw)
+    assert [st[k] for k in ("lines", "pairs", "empty", "short", "invalid", "paired")] == pst
+    assert st["nanopore"] == 1
+
+
+def test_np_autodetect_and_odd_tags(ctx, oracle, genome):
+    """first line carries MM -> nanopore mode without the flag (patter.cpp:337-338); malformed / unusual MM, ML"""
+    H = oracle; g = genome
+    k = 300
+    while g.loci[k + 5] - g.loci[k] > 100:
+        k += 1
+    p = int(g.loci[k]) - 2
+    n = int(g.loci[k + 5]) - p + 3
+    seq = g.bases[p:p + n].tobytes()
+    comp = bytes.maketrans(b"ACGTN", b"TGCAN")
+
+    def rec(name, flag, pos, cigar, s, tags):
+        return b"%s\t%d\tchrT\t%d\t60\t%s\t*\t0\t0\t%s\t*\tNM:i:0%s" % (name, flag, pos, cigar, s, tags)
+    M = b"%dM" % n
+    lines = [
+        rec(b"a", 0, p, M, seq, b"\tMM:Z:C+m?,0,0,0;C+h?,0,0,0;\tML:B:C,250,3,128,2,250,5"),
+        rec(b"b", 16, p, M, seq, b"\tMM:Z:C+m?,0,0,0;C+h?,0,0,0;\tML:B:C,250,3,128,2,250,5"),
+        rec(b"c", 0, p, M, seq, b"\tMM:Z:C+m.,1,0;\tML:B:C,255,0"),                       # dot convention: unlisted C -> T
+        rec(b"d", 16, p, M, seq, b"\tMm:Z:C+m.,1,0;"),                                       # no ML -> 255
+        rec(b"e", 0, p, M, seq, b"\tMM:Z:C+m?,0,0,0;\tML:B:C,250,3"),                       # ML count not a multiple -> invalid
+        rec(b"f", 0, p, M, seq, b"\tMM:Z:C+h?,0,1;C+C?,0,0,0;C+m?,2;\tML:B:C,200,10,255,255,255,90"),   # section order + C+C? (ML slicing quirk)
+        rec(b"g", 0, p, M, seq, b"\tMM:Z:C+C?,0,0,0;"),                                      # only C+C?
+        rec(b"h", 0, p, M, seq, b"\tMM:Z:G-m?,0;"),                                          # no C+ section, '?' -> empty
+        rec(b"i", 0, p, M, seq, b""),                                                        # no tags at all -> empty
+        rec(b"j", 16, p, M, seq.replace(b"A", b"R", 1), b"\tMM:Z:C+m?,0;\tML:B:C,255"),     # bottom + non ACGTN -> invalid
+        rec(b"k", 0, p, b"5M2D%dM3I5M" % (n - 13), seq, b"\tMM:Z:C+m.,0,0,0,0;\tML:B:C,255,1,255,1"),
+        rec(b"l", 16, p + 1, b"%dM" % (n - 1), seq[1:], b"\tMM:Z:C+m?,0,0,0,0,0,0,0,0;\tML:B:C,255,255,255,255,255,255,255,255"),
+        rec(b"m", 0, p, M, b"*", b"\tMM:Z:C+m?,0;\tML:B:C,255"),                             # SEQ '*' -> empty
+        rec(b"n", 0, p, b"*", seq, b"\tMM:Z:C+m?,0;\tML:B:C,255"),                           # bad CIGAR -> invalid
+    ]
+    sam = b"\n".join(lines) + b"\n"
+    for kw in (dict(), dict(combine_mods=True), dict(cpc_call="H"), dict(cpc_call=".")):
+        ref_raw, ref_txt = _oracle_pat(H, g, sam, False, **kw)                               # NB: no nanopore flag
+        raw, txt, st = _gpu_pat(ctx, g, sam, **kw)
+        assert txt == ref_txt, kw
+        _, pst = H.port_patter(sam, g.loci, g.idx(), **kw)
+        assert [st[k] for k in ("lines", "pairs", "empty", "short", "invalid", "paired")] == pst, kw
+        assert st["nanopore"] == 1 and st["invalid"] == 3

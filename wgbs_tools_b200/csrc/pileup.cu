@@ -10,106 +10,35 @@
 //
 // One thread per record.  CIGAR and SEQ bytes are read in place from the SAM text buffer.  Calls are written as 2-bit
 // symbols into a word pool (layout: include/wgbs_b200.h).
-#include "reads.cuh"
+#include "pileup_dev.cuh"
 
 int build_mates(wgbs_ctx *ctx, const ReadBatch &rb, bool paired, Temps &T, uint32_t **mate_out, unsigned long long *d_stats);
-int np_prepare(wgbs_ctx *ctx, const ReadBatch &rb, Temps &T);
+// np.cu (MM/ML mode)
+int np_measure(wgbs_ctx *ctx, const ReadBatch &rb, const uint32_t *loci, uint32_t nloci, PileupOpts o, uint32_t *r_lo, uint32_t *r_ncand,
+               uint32_t *words, unsigned long long *d_stats);
+int np_call(wgbs_ctx *ctx, const ReadBatch &rb, const uint32_t *loci, uint32_t first_idx, PileupOpts o, const uint32_t *r_lo,
+            const uint32_t *r_ncand, const uint32_t *off, uint32_t *pool, uint32_t pool_words, int32_t *r_idx, uint32_t *r_len,
+            unsigned long long *d_stats);
 
 namespace {
 
-constexpr uint32_t NONE = 0xffffffffu;
-constexpr int MAX_PE_PAT_LEN = 300;     // patter_utils.h:21
-
-struct PileupOpts {
-    int min_cpg, clip, paired, nanopore, combine_mods;
-    float np_thresh;
-    char cpc_call;
-};
-
-__device__ __forceinline__ bool is_bottom(int flag, int paired) {
-    if (paired) return ((flag & 0x53) == 83) || ((flag & 0xA3) == 163);
-    return (flag & 0x10) == 16;
-}
-
-// ---- CIGAR ---------------------------------------------------------------------------------------------------------
-// clean_CIGAR throws (-> read counted invalid) when: an op char has no number before it, the number overflows int,
-// the op is not one of M = X D N I S H, or an M/=/X/I/S op consumes more read bases than remain.
-__device__ bool cig_validate(const char *__restrict__ t, uint32_t p, uint32_t e, uint32_t seq_len, int64_t *span_out) {
-    int64_t span = 0, q = 0;
-    bool ok = true;
-    uint64_t num = 0; bool have = false;
-    for (; p < e; p++) {
-        char c = t[p];
-        if (c >= '0' && c <= '9') { num = num * 10 + (uint64_t)(c - '0'); if (num > 0x7fffffffull) num = 0x80000000ull; have = true; continue; }
-        if (!have || num > 0x7fffffffull) { ok = false; break; }
-        if (c == 'M' || c == '=' || c == 'X' || c == 'I' || c == 'S') {
-            if ((int64_t)num > (int64_t)seq_len - q) ok = false;       // checked after the tokenising phase in the reference; same verdict
-            q += (int64_t)num;
-            if (c != 'I' && c != 'S') span += (int64_t)num;
-        } else if (c == 'D' || c == 'N') span += (int64_t)num;
-        else if (c == 'H') {}
-        else ok = false;
-        num = 0; have = false;
-    }
-    // an M op that overruns still appended the available bases before throwing; irrelevant: the read is invalid
-    *span_out = span;
-    return ok;
-}
-
-struct CigCursor {
-    const char *t; uint32_t p, e;
-    int64_t r0, q0, len;   // current ref-consuming op covers ref offsets [r0, r0+len); its first read base is q0 (op 'M')
-    char op;               // 'M' (M,=,X) or 'D' (D,N); 0 before the first op
-    __device__ void init(const char *text, uint32_t off, uint32_t n) { t = text; p = off; e = off + n; r0 = 0; q0 = 0; len = 0; op = 0; }
-    // position on the op covering ref offset x (x must be non-decreasing across calls); false past the end
-    __device__ bool seek(int64_t x) {
-        while (true) {
-            if (x < r0 + len) return true;
-            // leave the current op
-            r0 += len; if (op == 'M') q0 += len;
-            len = 0; op = 0;
-            // next op
-            bool found = false;
-            while (p < e) {
-                int64_t num = 0;
-                while (p < e && t[p] >= '0' && t[p] <= '9') { num = num * 10 + (t[p] - '0'); p++; }
-                if (p >= e) break;
-                char c = t[p++];
-                if (c == 'M' || c == '=' || c == 'X') { op = 'M'; len = num; found = true; break; }
-                if (c == 'D' || c == 'N') { op = 'D'; len = num; found = true; break; }
-                if (c == 'I' || c == 'S') q0 += num;
-            }
-            if (!found) return false;
-        }
-    }
-};
-
-__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *__restrict__ a, uint32_t n, int64_t key) {
-    uint32_t lo = 0, hi = n;
-    while (lo < hi) { uint32_t m = (lo + hi) >> 1; if ((int64_t)a[m] < key) lo = m + 1; else hi = m; }
-    return lo;
-}
-
 // ---- pass 1: validity, reference span, candidate CpG range ---------------------------------------------------------
 __global__ void __launch_bounds__(256) pileup_measure_k(ReadBatchView rb, const uint32_t *__restrict__ loci, uint32_t nloci, PileupOpts o,
-                                                         const uint8_t *__restrict__ np_bad, uint32_t *__restrict__ r_lo, uint32_t *__restrict__ r_ncand,
+                                                         uint32_t *__restrict__ r_lo, uint32_t *__restrict__ r_ncand,
                                                          uint32_t *__restrict__ words, unsigned long long *__restrict__ stats) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t inval = 0;
     if (r < rb.n) {
         uint32_t lo = 0, nc = 0;
         uint8_t st = rb.status[r];
-        if (st == REC_INVALID) inval = 1;
+        if (st == REC_INVALID || st == REC_BADINT) inval = 1;
         else if (st == REC_OK) {
             int64_t span = 0;
             bool ok = cig_validate(rb.text, rb.cig_off[r], rb.cig_off[r] + rb.cig_len[r], rb.seq_len[r], &span);
-            if (o.nanopore && np_bad && np_bad[r] == 2) ok = false;          // MM/ML parse error or unsupported base
             if (!ok) inval = 1;
-            else if (!(o.nanopore && np_bad && np_bad[r] == 1)) {              // np: 1 = "empty" verdict before the walk
+            else {
                 int64_t pos = rb.pos[r];
-                // np bottom-strand reads also look at the CpG whose G is the first aligned base (ont.cpp:142-145)
-                int64_t first = (o.nanopore && ((rb.flag[r] & 0x10) == 16)) ? pos - 1 : pos;
-                lo = lower_bound_u32(loci, nloci, first);
+                lo = lower_bound_u32(loci, nloci, pos);
                 uint32_t hi = lower_bound_u32(loci, nloci, pos + span);
                 nc = hi > lo ? hi - lo : 0;
             }
@@ -323,13 +252,12 @@ extern "C" int wgbs_pileup_sam(wgbs_ctx *ctx, const wgbs_index *ix, const char *
     uint32_t *mate = nullptr;
     RC_TRY(build_mates(ctx, rb, o.paired != 0, T, &mate, d_stats));
 
-    uint8_t *np_bad = nullptr;
-    if (o.nanopore) return wgbs_set_err("wgbs_pileup_sam: MM/ML (nanopore) mode is not built yet");
 
     uint32_t *r_lo, *r_ncand, *words, *off;
     RC_TRY(T.alloc(&r_lo, n)); RC_TRY(T.alloc(&r_ncand, n)); RC_TRY(T.alloc(&words, (size_t)2 * n)); RC_TRY(T.alloc(&off, (size_t)2 * n + 1));
     if (n) {
-        LAUNCH(ctx, pileup_measure_k, grid_for(n, 256), 256, 0, view_of(rb), ix->loci, ix->n, o, np_bad, r_lo, r_ncand, words, d_stats);
+        if (o.nanopore) RC_TRY(np_measure(ctx, rb, ix->loci, ix->n, o, r_lo, r_ncand, words, d_stats));
+        else LAUNCH(ctx, pileup_measure_k, grid_for(n, 256), 256, 0, view_of(rb), ix->loci, ix->n, o, r_lo, r_ncand, words, d_stats);
         LAUNCH(ctx, template_words_k, grid_for(n, 256), 256, 0, n, mate, r_lo, r_ncand, words + n);
     }
     RC_TRY(scan_u32_u32(ctx, words, off, (size_t)2 * n));
@@ -345,7 +273,8 @@ extern "C" int wgbs_pileup_sam(wgbs_ctx *ctx, const wgbs_index *ix, const char *
     if ((rc = T.alloc(&r_idx, n)) < 0 || (rc = T.alloc(&r_len, n)) < 0 || (rc = T.alloc(&t_idx, n)) < 0 || (rc = T.alloc(&t_len, n)) < 0 ||
         (rc = T.alloc(&t_off, n)) < 0 || (rc = T.alloc(&t_valid, n)) < 0 || (rc = T.alloc(&dst, (size_t)n + 1)) < 0) { wgbs_pats_free(ctx, P); return rc; }
     if (n) {
-        LAUNCH(ctx, pileup_call_k, grid_for(n, 256), 256, 0, view_of(rb), ix->loci, ix->first_idx, o, r_lo, r_ncand, off, P->pool, r_idx, r_len, d_stats);
+        if (o.nanopore) { int rc2 = np_call(ctx, rb, ix->loci, ix->first_idx, o, r_lo, r_ncand, off, P->pool, pool_words, r_idx, r_len, d_stats); if (rc2 < 0) { wgbs_pats_free(ctx, P); return rc2; } }
+        else LAUNCH(ctx, pileup_call_k, grid_for(n, 256), 256, 0, view_of(rb), ix->loci, ix->first_idx, o, r_lo, r_ncand, off, P->pool, r_idx, r_len, d_stats);
         LAUNCH(ctx, merge_templates_k, grid_for(n, 256), 256, 0, n, rb.status, mate, o, r_idx, r_len, off, P->pool, t_idx, t_len, t_off, t_valid, d_stats);
     }
     if ((rc = scan_u32_u32(ctx, t_valid, dst, n)) < 0) { wgbs_pats_free(ctx, P); return rc; }

@@ -6,7 +6,8 @@
 #include "pats.cuh"
 
 // status of a record
-enum : uint8_t { REC_OK = 0, REC_INVALID = 1, REC_BLANK = 2 /* empty input line: counted, never processed */ };
+enum : uint8_t { REC_OK = 0, REC_INVALID = 1 /* < 11 fields */, REC_BLANK = 2 /* empty input line: counted, never processed */,
+                 REC_BADINT = 3 /* FLAG / POS not numeric: std::stoi throws when the read is processed */ };
 
 // One entry per SAM line.  All *_off are byte offsets into the SAM text buffer (which stays resident: the pileup
 // reads CIGAR and SEQ bytes straight from it, nothing is re-packed).

@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(TK_T) sam_fields_k(const char *__restrict__ te
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) h += __shfl_xor_sync(0xffffffffu, h, d);
     h = fmix64(h ^ (uint64_t)(qend - s));
+    if (e == s) h = fmix64(0x5851f42d4c957f2dULL ^ (uint64_t)line);   // blank lines: unique keys, never paired
     // tags: the last occurrence wins (get_np_tags, ont.cpp:418-438): highest lane that saw one
     if (want_tags) {
         uint32_t bm = __ballot_sync(0xffffffffu, mm_len || mm_off);
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(TK_T) sam_fields_k(const char *__restrict__ te
             if (nfields < 11) st = REC_INVALID;
             else {
                 const uint32_t *tb = tabs[w];
-                if (!parse_i32(text, tb[0] + 1, tb[1], &flag) || !parse_i32(text, tb[2] + 1, tb[3], &pos)) st = REC_INVALID;
+                if (!parse_i32(text, tb[0] + 1, tb[1], &flag) || !parse_i32(text, tb[2] + 1, tb[3], &pos)) st = REC_BADINT;
                 cig_off = tb[4] + 1; cig_len = tb[5] - tb[4] - 1;
                 seq_off = tb[8] + 1; seq_len = tb[9] - tb[8] - 1;
             }

@@ -1,0 +1,37 @@
+"""pat2beta -- `wgbstools pat2beta X.pat.gz` (reference src/python/pat2beta.py): pat text -> GPU -> uint8/uint16 beta."""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+
+
+def pat2beta(ctx, pat_path: str, out_dir: str, nr_sites: int, lbeta: bool = False, force: bool = True):
+    from .patio import read_pat_text, splitextgz
+    suff = ".lbeta" if lbeta else ".beta"
+    out_beta = os.path.join(out_dir, splitextgz(os.path.basename(pat_path)) + suff)
+    if os.path.exists(out_beta) and not force:                     # delete_or_skip (utils_wgbs.py:435-454)
+        print(f"File {out_beta} already exists. Skipping it. Use -f to overwrite", file=sys.stderr)
+        return None
+    text = read_pat_text(pat_path)
+    beta = ctx.pat2beta_text(text, 1, nr_sites + 1, 16 if lbeta else 8)   # `stdin2beta 1 N+1` + trim_to_uint8 (pat2beta.py:32-37)
+    beta.tofile(out_beta)
+    return out_beta
+
+
+def main(argv=None):
+    from .api import Context
+    from .genome import GenomeRef
+    p = argparse.ArgumentParser(description="Generate a beta file from a pat file")
+    p.add_argument("pat_paths", nargs="+"); p.add_argument("-f", "--force", action="store_true")
+    p.add_argument("-o", "--out_dir", default="."); p.add_argument("-l", "--lbeta", action="store_true")
+    p.add_argument("--genome"); p.add_argument("-@", "--threads", type=int, default=1)
+    a = p.parse_args(argv)
+    ref = GenomeRef(a.genome)
+    with Context(0) as ctx:
+        for pat in a.pat_paths:
+            pat2beta(ctx, pat, a.out_dir, ref.nr_sites, a.lbeta, a.force)
+
+
+if __name__ == "__main__":
+    main()
