@@ -223,10 +223,13 @@ int to_device(wgbs_ctx *ctx, const void *p, size_t nbytes, const void **dptr, bo
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// device-wide exclusive scan (reduce / scan-of-partials / downsweep). 2048 items per CTA.
+// device-wide exclusive scan: ONE kernel, single pass over the data (decoupled look-back).  4096 items per CTA; tiles are
+// handed out by an atomic ticket so a CTA only ever waits on tiles that are already resident or finished.
+// status[tile] = flag(2 bits) << 62 | value : flag 1 = tile aggregate, 2 = inclusive prefix up to and including the tile.
 // ------------------------------------------------------------------------------------------------------------------
 namespace {
-constexpr int SCAN_T = 256, SCAN_I = 8, SCAN_TILE = SCAN_T * SCAN_I;
+constexpr int SCAN_T = 256, SCAN_I = 16, SCAN_TILE = SCAN_T * SCAN_I;
+constexpr unsigned long long ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_VAL = (1ull << 62) - 1;
 
 __device__ __forceinline__ uint64_t warp_incl_scan(uint64_t v) {
     const unsigned lane = threadIdx.x & 31;
@@ -237,78 +240,93 @@ __device__ __forceinline__ uint64_t warp_incl_scan(uint64_t v) {
     }
     return v;
 }
-// block-wide exclusive scan of one value per thread; returns exclusive prefix, *total = block sum
-__device__ __forceinline__ uint64_t block_excl_scan(uint64_t v, uint64_t *total) {
-    __shared__ uint64_t wsum[32];
-    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    uint64_t inc = warp_incl_scan(v);
-    if (lane == 31) wsum[w] = inc;
-    __syncthreads();
-    if (w == 0) {
-        uint64_t s = lane < nw ? wsum[lane] : 0;
-        uint64_t si = warp_incl_scan(s);
-        wsum[lane] = si - s;
-        if (lane == nw - 1) *total = si;
-    }
-    __syncthreads();
-    uint64_t r = wsum[w] + inc - v;
-    __syncthreads();
-    return r;
-}
 
-__global__ void __launch_bounds__(SCAN_T) scan_reduce_k(const uint32_t *__restrict__ in, size_t n, uint64_t *__restrict__ bsum) {
-    size_t base = (size_t)blockIdx.x * SCAN_TILE;
-    uint64_t s = 0;
-#pragma unroll
-    for (int i = 0; i < SCAN_I; i++) {
-        size_t k = base + (size_t)i * SCAN_T + threadIdx.x;
-        if (k < n) s += in[k];
-    }
-    __shared__ uint64_t tot;
-    block_excl_scan(s, &tot);
-    if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
-}
-__global__ void __launch_bounds__(1024) scan_partials_k(uint64_t *bsum, size_t nb, uint64_t *total_out) {
-    __shared__ uint64_t carry, tot;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (size_t base = 0; base < nb; base += 1024) {
-        size_t k = base + threadIdx.x;
-        uint64_t v = k < nb ? bsum[k] : 0;
-        uint64_t ex = block_excl_scan(v, &tot);
-        if (k < nb) bsum[k] = carry + ex;
-        __syncthreads();
-        if (threadIdx.x == 0) carry += tot;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0 && total_out) *total_out = carry;
-}
 template <typename OutT>
-__global__ void __launch_bounds__(SCAN_T) scan_down_k(const uint32_t *__restrict__ in, size_t n, const uint64_t *__restrict__ bsum, OutT *__restrict__ out) {
-    // thread t owns SCAN_I consecutive items so the tile scan is a thread-serial scan + one block scan
-    size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_I;
+__global__ void __launch_bounds__(SCAN_T) scan_lookback_k(const uint32_t *__restrict__ in, size_t n, OutT *__restrict__ out,
+                                                          unsigned long long *__restrict__ status, unsigned int *__restrict__ ticket) {
+    __shared__ uint64_t wsum[SCAN_T / 32];
+    __shared__ uint64_t s_prefix;
+    __shared__ unsigned s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const size_t base = (size_t)tile * SCAN_TILE + (size_t)threadIdx.x * SCAN_I;
     uint32_t v[SCAN_I];
     uint64_t s = 0;
+    const bool vec_in = (((uintptr_t)in) & 15) == 0, vec_out = (((uintptr_t)out) & 15) == 0;
+    if (base + SCAN_I <= n && vec_in) {
+        const uint4 *p4 = reinterpret_cast<const uint4 *>(in + base);
 #pragma unroll
-    for (int i = 0; i < SCAN_I; i++) { size_t k = base + i; v[i] = k < n ? in[k] : 0; s += v[i]; }
-    __shared__ uint64_t tot;
-    uint64_t ex = block_excl_scan(s, &tot) + bsum[blockIdx.x];
+        for (int i = 0; i < SCAN_I / 4; i++) { uint4 q = p4[i]; v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w; }
+    } else {
 #pragma unroll
-    for (int i = 0; i < SCAN_I; i++) { size_t k = base + i; if (k < n) out[k] = (OutT)ex; ex += v[i]; }
+        for (int i = 0; i < SCAN_I; i++) v[i] = base + i < n ? in[base + i] : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < SCAN_I; i++) s += v[i];
+    const uint64_t inc = warp_incl_scan(s);
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    uint64_t wexcl = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_T / 32; i++) { uint64_t x = wsum[i]; if (i < (int)w) wexcl += x; total += x; }
+    if (w == 0) {
+        volatile unsigned long long *st = status;
+        uint64_t prefix = 0;
+        if (tile == 0) { if (lane == 0) st[0] = ST_INC | total; }
+        else {
+            if (lane == 0) st[tile] = ST_AGG | total;
+            long long idx = (long long)tile - 1;
+            while (true) {
+                const long long j = idx - lane;
+                unsigned long long x = ST_INC;                         // before tile 0: inclusive prefix 0
+                if (j >= 0) x = st[j];
+                // every lane must hold a published word before we decide (all lanes take part in the vote)
+                while (__any_sync(0xffffffffu, (x >> 62) == 0)) { if ((x >> 62) == 0) x = st[j]; }
+                const unsigned incm = __ballot_sync(0xffffffffu, (x >> 62) == 2);
+                uint64_t val = x & ST_VAL;
+                if (incm) {
+                    const int L = __ffs(incm) - 1;                     // closest predecessor holding an inclusive prefix
+                    if ((int)lane > L) val = 0;
+                }
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+                prefix += val;
+                if (incm) break;
+                idx -= 32;
+            }
+            if (lane == 0) st[tile] = ST_INC | ((prefix + total) & ST_VAL);
+        }
+        if (lane == 0) s_prefix = prefix;
+    }
+    __syncthreads();
+    uint64_t ex = s_prefix + wexcl + inc - s;
+    if (base + SCAN_I <= n && sizeof(OutT) == 4 && vec_out) {
+        uint32_t o[SCAN_I];
+#pragma unroll
+        for (int i = 0; i < SCAN_I; i++) { o[i] = (uint32_t)ex; ex += v[i]; }
+        uint4 *q4 = reinterpret_cast<uint4 *>(out + base);
+#pragma unroll
+        for (int i = 0; i < SCAN_I / 4; i++) q4[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_I; i++) { if (base + i < n) out[base + i] = (OutT)ex; ex += v[i]; }
+    }
+    if ((size_t)(tile + 1) * SCAN_TILE >= n && threadIdx.x == SCAN_T - 1) {
+        // last tile: the grand total goes to out[n]
+        out[n] = (OutT)(s_prefix + total);
+    }
 }
-template <typename OutT>
-__global__ void scan_total_k(const uint64_t *total, OutT *out_n) { *out_n = (OutT)*total; }
 
 template <typename OutT>
 int scan_impl(wgbs_ctx *ctx, const uint32_t *in, OutT *out, size_t n) {
     size_t nb = (n + SCAN_TILE - 1) / SCAN_TILE; if (nb == 0) nb = 1;
     Temps T(ctx);
-    uint64_t *bsum = nullptr, *total = nullptr;
-    RC_TRY(T.alloc(&bsum, nb)); RC_TRY(T.alloc(&total, 1));
-    LAUNCH(ctx, scan_reduce_k, (unsigned)nb, SCAN_T, 0, in, n, bsum);
-    LAUNCH(ctx, scan_partials_k, 1, 1024, 0, bsum, nb, total);
-    LAUNCH(ctx, scan_down_k<OutT>, (unsigned)nb, SCAN_T, 0, in, n, bsum, out);
-    LAUNCH(ctx, scan_total_k<OutT>, 1, 1, 0, total, out + n);
+    unsigned long long *status = nullptr;
+    RC_TRY(T.alloc(&status, nb + 1));
+    CUDA_TRY(cudaMemsetAsync(status, 0, (nb + 1) * 8, ctx->stream));
+    LAUNCH(ctx, scan_lookback_k<OutT>, (unsigned)nb, SCAN_T, 0, in, n, out, status, (unsigned int *)(status + nb));
     LAUNCH_CHECK();
     return 0;
 }

@@ -37,6 +37,13 @@ __device__ __forceinline__ bool is_tag(const char *__restrict__ t, uint32_t p, u
     return true;
 }
 
+// per-(byte, position) mixing summed over the name: independent of how the name is aligned to the 16-byte chunk grid
+__device__ __forceinline__ uint64_t name_byte_mix(uint32_t byte, uint32_t pos) {
+    uint64_t x = ((uint64_t)(byte | (pos << 8)) + 1) * 0x9e3779b97f4a7c15ULL;
+    x ^= x >> 29; x *= 0xbf58476d1ce4e5b9ULL; x ^= x >> 32;
+    return x;
+}
+
 __global__ void __launch_bounds__(TK_T) sam_fields_k(const char *__restrict__ text, uint32_t n, const uint32_t *__restrict__ nlpos,
                                                       uint32_t n_nl, uint32_t n_lines, int want_tags, ReadBatch rb) {
     __shared__ uint32_t tabs[TK_WARPS][NTAB];
@@ -47,15 +54,20 @@ __global__ void __launch_bounds__(TK_T) sam_fields_k(const char *__restrict__ te
     const uint32_t e = line < n_nl ? nlpos[line] : n;
     uint32_t ntab = 0;
     uint64_t h = 0;
+    uint32_t qend = e;                     // end of QNAME = first tab (or the line end)
     uint32_t mm_off = 0, mm_len = 0, ml_off = 0, ml_len = 0;
-    for (uint32_t base = s; base < e; base += 512) {
+    // chunks are aligned to the 16-byte grid of the (256 B aligned) text buffer: every load is one aligned LDG.128
+    const uint32_t a0 = s & ~15u;
+    for (uint32_t base = a0; base < e; base += 512) {
         const uint32_t p = base + lane * 16;
         uint4 v = make_uint4(0, 0, 0, 0);
-        uint32_t tm = 0;
-        if (p < e) {
-            v = load16_guard(text, p, n);
-            tm = eq_mask16(v, '\t');
-            if (e - p < 16) tm &= (1u << (e - p)) - 1;
+        uint32_t tm = 0, valid = 0;
+        if (p < e && p + 16 > s) {
+            v = (p + 16 <= n) ? *reinterpret_cast<const uint4 *>(text + p) : load16_guard(text, p, n);
+            valid = 0xffffu;
+            if (p < s) valid &= 0xffffu << (s - p);
+            if (e - p < 16) valid &= (1u << (e - p)) - 1;
+            tm = eq_mask16(v, '\t') & valid;
         }
         const uint32_t c = __popc(tm);
         uint32_t inc = c;
@@ -66,45 +78,32 @@ __global__ void __launch_bounds__(TK_T) sam_fields_k(const char *__restrict__ te
         while (m) {
             int b = __ffs(m) - 1; m &= m - 1;
             if (ord < NTAB) tabs[w][ord] = p + b;
+            if (want_tags && ord >= 10) {                           // a field with index >= 11 starts after this tab
+                uint32_t f = p + b + 1;
+                bool mm = is_tag(text, f, e, 'M', 'M', 'm', ':', 'Z', ':', 0, 5);
+                bool ml = !mm && is_tag(text, f, e, 'M', 'L', 'l', ':', 'B', ':', 'C', 6);
+                if (mm || ml) {
+                    uint32_t q = f + (mm ? 5 : 6), z = q;
+                    while (z < e && text[z] != '\t') z++;
+                    if (mm) { mm_off = q; mm_len = z - q; } else { ml_off = q; ml_len = z - q; }
+                }
+            }
             ord++;
         }
-        if (want_tags && tm) {
-            // fields with index >= 11 start after tab ordinal >= 10
-            uint32_t m2 = tm, o2 = ntab + inc - c;
-            while (m2) {
-                int b = __ffs(m2) - 1; m2 &= m2 - 1;
-                if (o2 >= 10) {
-                    uint32_t f = p + b + 1;
-                    bool mm = is_tag(text, f, e, 'M', 'M', 'm', ':', 'Z', ':', 0, 5);
-                    bool ml = !mm && is_tag(text, f, e, 'M', 'L', 'l', ':', 'B', ':', 'C', 6);
-                    if (mm || ml) {
-                        uint32_t q = f + (mm ? 5 : 6), z = q;
-                        while (z < e && text[z] != '\t') z++;
-                        if (mm) { mm_off = q; mm_len = z - q; } else { ml_off = q; ml_len = z - q; }
-                    }
-                }
-                o2++;
-            }
+        // QNAME: bytes before the first tab of the line
+        if (ntab == 0) {
+            const uint32_t first = __ballot_sync(0xffffffffu, c != 0);
+            uint32_t stop = e;                                       // exclusive end of name bytes seen so far
+            if (first) { const int fl = __ffs(first) - 1; const uint32_t ftm = __shfl_sync(0xffffffffu, tm, fl); stop = base + fl * 16 + (__ffs(ftm) - 1); }
+            if (first) qend = stop;
+            uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+            uint32_t nm = valid;
+            if (p + 16 > stop) nm &= p >= stop ? 0u : ((1u << (stop - p)) - 1);
+            while (nm) { int b = __ffs(nm) - 1; nm &= nm - 1; h += name_byte_mix((w4[b >> 2] >> ((b & 3) * 8)) & 255u, p + b - s); }
         }
         ntab += __shfl_sync(0xffffffffu, inc, 31);
     }
     __syncwarp();
-    // --- QNAME hash (the name is [s, tab0) or the whole line when there is no tab): every 8-byte half of every 16-byte
-    // chunk contributes fmix64(bytes ^ K*(position+1)); contributions are summed (order-free), then mixed with the length.
-    const uint32_t qend = ntab > 0 ? tabs[w][0] : e;
-    for (uint32_t base = s; base < qend; base += 512) {
-        const uint32_t p = base + lane * 16;
-        if (p < qend) {
-            uint4 v = load16_guard(text, p, n);
-            uint64_t lo = ((uint64_t)v.y << 32) | v.x, hi = ((uint64_t)v.w << 32) | v.z;
-            uint32_t rem = qend - p;                       // bytes of this chunk inside the name
-            if (rem < 8) { lo &= (1ULL << (8 * rem)) - 1; hi = 0; }
-            else if (rem < 16) { hi &= rem == 8 ? 0 : ((1ULL << (8 * (rem - 8))) - 1); }
-            uint64_t pos = (p - s) >> 3;
-            h += fmix64(lo ^ (0x9e3779b97f4a7c15ULL * (pos + 1)));
-            h += fmix64(hi ^ (0x9e3779b97f4a7c15ULL * (pos + 2)));
-        }
-    }
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) h += __shfl_xor_sync(0xffffffffu, h, d);
     h = fmix64(h ^ (uint64_t)(qend - s));

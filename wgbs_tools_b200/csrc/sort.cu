@@ -3,9 +3,9 @@
 // Used by: template pairing (sort records by 64-bit QNAME hash = two calls) and the collapse step, which replaces the
 // reference's `sort -k2,2n -k3,3` (python/bam2pat.py:99) by a sequence of these sorts over successive key words.
 //
-// Per pass: (a) per-CTA digit histogram, (b) exclusive scan of the digit-major histogram table, (c) stable scatter
-// using warp match_any ranking.  A pre-pass builds the global histogram of all four digits at once; a digit whose
-// histogram has a single non-empty bin is skipped (this is what makes sorting zero-padded pattern words cheap).
+// A pre-pass builds the global histogram of all four digits at once; a digit whose histogram has a single non-empty bin
+// is skipped (this is what makes sorting zero-padded pattern words cheap).  Every remaining pass is one kernel that reads
+// the keys once: warp match_any ranking + decoupled look-back for the tile offsets.
 #include "common.cuh"
 #include "sort.cuh"
 
@@ -29,31 +29,36 @@ __global__ void __launch_bounds__(RS_T) rs_global_hist_k(const uint32_t *__restr
     for (int i = threadIdx.x; i < 1024; i += RS_T) if (h[i]) atomicAdd(&ghist[i], h[i]);
 }
 
-// (a) per-CTA histogram of one digit, written digit-major: table[d * nblocks + b]
-__global__ void __launch_bounds__(RS_T) rs_block_hist_k(const uint32_t *__restrict__ keys, size_t n, int shift, uint32_t nblocks,
-                                                         uint32_t *__restrict__ table) {
-    __shared__ uint32_t h[256];
-    h[threadIdx.x] = 0;
-    __syncthreads();
-    const size_t base = (size_t)blockIdx.x * RS_TILE;
+// One pass = ONE kernel ("onesweep" style): per-tile digit counts are published and the exclusive offsets of a tile are
+// obtained by looking back over the preceding tiles' published words (decoupled look-back, one thread per digit), so the
+// keys are read exactly once per pass.  status[tile*256 + d] = flag(2 bits) << 30 | count : 1 = this tile's count,
+// 2 = inclusive count over tiles 0..tile.  Tiles are handed out by an atomic ticket (forward progress).
+constexpr uint32_t RS_AGG = 1u << 30, RS_INC = 2u << 30, RS_VAL = (1u << 30) - 1;
+
+__global__ void __launch_bounds__(RS_T) rs_onesweep_k(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, size_t n, int shift,
+                                                       const uint32_t *__restrict__ ghist /*[256] of this digit*/, uint32_t *__restrict__ status,
+                                                       unsigned int *__restrict__ ticket, uint32_t *__restrict__ kout, uint32_t *__restrict__ vout) {
+    __shared__ uint32_t cnt[RS_WARPS][256];   // per-warp digit counts -> per-warp output bases
+    __shared__ uint32_t gbase[256];           // exclusive scan of the global histogram
+    __shared__ uint32_t wtot[RS_WARPS];
+    __shared__ unsigned s_tile;
+    const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_T) (&cnt[0][0])[i] = 0;
+    // exclusive scan of the 256-bin global histogram (digit base offsets)
+    {
+        uint32_t h = ghist[threadIdx.x], inc = h;
 #pragma unroll
-    for (int j = 0; j < RS_IPT; j++) {
-        size_t i = base + (size_t)j * RS_T + threadIdx.x;
-        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255], 1u);
+        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (unsigned)d) inc += t; }
+        if (lane == 31) wtot[w] = inc;
+        __syncthreads();
+        uint32_t off = 0;
+        for (unsigned i = 0; i < w; i++) off += wtot[i];
+        gbase[threadIdx.x] = off + inc - h;
     }
     __syncthreads();
-    table[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
-}
-
-// (c) stable scatter.  Warp w of the CTA owns the contiguous items [base + w*512, base + (w+1)*512): 16 rounds of 32.
-__global__ void __launch_bounds__(RS_T) rs_scatter_k(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, size_t n, int shift,
-                                                      uint32_t nblocks, const uint32_t *__restrict__ table_scanned,
-                                                      uint32_t *__restrict__ kout, uint32_t *__restrict__ vout) {
-    __shared__ uint32_t cnt[RS_WARPS][256];   // per-warp digit counts -> per-warp digit bases
-    const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_T) (&cnt[0][0])[i] = 0;
-    __syncthreads();
-    const size_t wbase = (size_t)blockIdx.x * RS_TILE + (size_t)w * (RS_IPT * 32);
+    const unsigned tile = s_tile;
+    const size_t wbase = (size_t)tile * RS_TILE + (size_t)w * (RS_IPT * 32);
     uint32_t key[RS_IPT], val[RS_IPT];
     uint16_t rank[RS_IPT];
 #pragma unroll
@@ -62,6 +67,11 @@ __global__ void __launch_bounds__(RS_T) rs_scatter_k(const uint32_t *__restrict_
         bool ok = i < n;
         key[j] = ok ? kin[i] : 0xffffffffu;
         val[j] = ok ? vin[i] : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < RS_IPT; j++) {
+        size_t i = wbase + (size_t)j * 32 + lane;
+        bool ok = i < n;
         uint32_t d = ok ? ((key[j] >> shift) & 255) : 256;          // 256: inactive lanes form their own group
         uint32_t peers = __match_any_sync(0xffffffffu, d);
         uint32_t below = __popc(peers & ((1u << lane) - 1));
@@ -73,10 +83,28 @@ __global__ void __launch_bounds__(RS_T) rs_scatter_k(const uint32_t *__restrict_
         __syncwarp();
     }
     __syncthreads();
-    // digit d (one per thread): turn per-warp counts into global output bases in warp order
     {
-        uint32_t d = threadIdx.x;
-        uint32_t run = table_scanned[(size_t)d * nblocks + blockIdx.x];
+        // thread d owns digit d: tile count, publish, look back, per-warp bases
+        const uint32_t d = threadIdx.x;
+        uint32_t tc = 0;
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ww++) tc += cnt[ww][d];
+        volatile uint32_t *st = status;
+        uint32_t excl = 0;
+        if (tile == 0) st[d] = RS_INC | tc;
+        else {
+            st[(size_t)tile * 256 + d] = RS_AGG | tc;
+            long long t = (long long)tile - 1;
+            while (true) {
+                uint32_t x;
+                do { x = st[(size_t)t * 256 + d]; } while ((x >> 30) == 0);
+                excl += x & RS_VAL;
+                if ((x >> 30) == 2) break;
+                t--;
+            }
+            st[(size_t)tile * 256 + d] = RS_INC | ((excl + tc) & RS_VAL);
+        }
+        uint32_t run = gbase[d] + excl;
 #pragma unroll
         for (int ww = 0; ww < RS_WARPS; ww++) { uint32_t c = cnt[ww][d]; cnt[ww][d] = run; run += c; }
     }
@@ -109,7 +137,7 @@ int fill_iota(wgbs_ctx *ctx, uint32_t *p, size_t n) {
 // (either the original pair or the alt pair).  Stable.  n < 2^32.
 int radix_sort_pairs(wgbs_ctx *ctx, uint32_t **keys, uint32_t **vals, uint32_t **keys_alt, uint32_t **vals_alt, size_t n) {
     if (n < 2) return 0;
-    if (n >= 0xffffffffull) return wgbs_set_err("radix_sort_pairs: n too large");
+    if (n >= (1ull << 30)) return wgbs_set_err("radix_sort_pairs: n must be < 2^30 per call");
     Temps T(ctx);
     uint32_t *ghist = nullptr;
     RC_TRY(T.alloc(&ghist, 1024));
@@ -119,20 +147,29 @@ int radix_sort_pairs(wgbs_ctx *ctx, uint32_t **keys, uint32_t **vals, uint32_t *
     uint32_t hh[1024];
     CUDA_TRY(cudaMemcpyAsync(hh, ghist, sizeof hh, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    const uint32_t nblocks = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
-    uint32_t *table = nullptr, *table_s = nullptr;
+    const uint32_t ntiles = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
+    uint32_t *status = nullptr;
+    int active = 0;
+    bool act[4];
     for (int p = 0; p < 4; p++) {
-        bool uniform = false;
-        for (int b = 0; b < 256; b++) if (hh[p * 256 + b] == (uint32_t)n) { uniform = true; break; }
-        if (uniform) continue;
-        if (!table) { RC_TRY(T.alloc(&table, (size_t)256 * nblocks)); RC_TRY(T.alloc(&table_s, (size_t)256 * nblocks + 1)); }
-        LAUNCH(ctx, rs_block_hist_k, nblocks, RS_T, 0, *keys, n, p * 8, nblocks, table);
-        RC_TRY(scan_u32_u32(ctx, table, table_s, (size_t)256 * nblocks));
-        LAUNCH(ctx, rs_scatter_k, nblocks, RS_T, 0, *keys, *vals, n, p * 8, nblocks, table_s, *keys_alt, *vals_alt);
-        LAUNCH_CHECK();
+        act[p] = true;
+        for (int b = 0; b < 256; b++) if (hh[p * 256 + b] == (uint32_t)n) { act[p] = false; break; }
+        active += act[p];
+    }
+    if (!active) return 0;
+    // one zeroed status table (+ ticket) per active pass, cleared with a single memset
+    const size_t per = (size_t)ntiles * 256 + 4;
+    RC_TRY(T.alloc(&status, per * active));
+    CUDA_TRY(cudaMemsetAsync(status, 0, per * active * 4, ctx->stream));
+    int q = 0;
+    for (int p = 0; p < 4; p++) {
+        if (!act[p]) continue;
+        uint32_t *st = status + per * q++;
+        LAUNCH(ctx, rs_onesweep_k, ntiles, RS_T, 0, *keys, *vals, n, p * 8, ghist + p * 256, st, (unsigned int *)(st + (size_t)ntiles * 256), *keys_alt, *vals_alt);
         uint32_t *t = *keys; *keys = *keys_alt; *keys_alt = t;
         t = *vals; *vals = *vals_alt; *vals_alt = t;
     }
+    LAUNCH_CHECK();
     return 0;
 }
 
