@@ -4,19 +4,13 @@
 //     sort -k2,2n -k3,3 | uniq -c | awk -v OFS='\t' '{print $2,$3,$4,$1}'          (python/bam2pat.py:99-106, C locale)
 // Order = (CpG index numeric, pattern bytes with a shorter prefix first).  With symbol codes '.'<'C'<'H'<'T' = 0..3
 // packed MSB-first and zero padding, that order is the numeric order of (idx, word0, word1, ...): patterns never end
-// in '.', so zero padding is unambiguous.  LSD: sort by the last pattern word first, the index last; every pass is a
-// stable 32-bit radix sort that skips digits on which all keys agree.
+// in '.', so zero padding is unambiguous.  Two stable 32-bit radix sorts (word0, then idx; uniform digits skipped) order
+// everything except ties between patterns longer than 16 symbols, which fix_ties_k settles run by run.
 #include "reads.cuh"
 #include "sort.cuh"
 
 namespace {
 
-__global__ void __launch_bounds__(256) max_words_k(const uint32_t *__restrict__ len, size_t n, uint32_t *__restrict__ out) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t w = i < n ? (len[i] + 15) >> 4 : 0;
-    w = __reduce_max_sync(0xffffffffu, w);
-    if ((threadIdx.x & 31) == 0 && w) atomicMax(out, w);
-}
 __global__ void __launch_bounds__(256) gather_word_k(PatsView P, const uint32_t *__restrict__ perm, uint32_t widx, uint32_t *__restrict__ keys) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
@@ -27,6 +21,44 @@ __global__ void __launch_bounds__(256) gather_idx_k(PatsView P, const uint32_t *
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < P.n) keys[i] = P.idx[perm[i]];
 }
+// Records are first radix-sorted on (idx, pattern word 0) only.  Whatever order remains to be decided lies inside runs
+// of equal (idx, word0) that contain a pattern longer than 16 symbols: one thread orders such a run in place by the
+// remaining words (zero padded = shorter prefix first).  Runs are short (templates starting at one CpG with the same
+// first 16 calls), so an insertion sort is enough; it is stable, like `sort`'s last-resort comparison needs.
+__device__ __forceinline__ int tail_cmp(const PatsView &P, uint32_t a, uint32_t b) {
+    const uint32_t na = (P.len[a] + 15) >> 4, nb = (P.len[b] + 15) >> 4, m = max(na, nb);
+    const uint32_t *x = P.pool + P.off[a], *y = P.pool + P.off[b];
+    for (uint32_t k = 1; k < m; k++) {
+        const uint32_t u = k < na ? x[k] : 0u, v = k < nb ? y[k] : 0u;
+        if (u != v) return u < v ? -1 : 1;
+    }
+    return 0;
+}
+__global__ void __launch_bounds__(128) fix_ties_k(PatsView P, uint32_t *__restrict__ perm, const uint32_t *__restrict__ key_idx /*sorted idx*/) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    const uint32_t r = perm[i];
+    const uint32_t id = key_idx[i];
+    const uint32_t w0 = P.len[r] ? P.pool[P.off[r]] : 0u;
+    if (i > 0) {                                                   // only the first position of a run works
+        const uint32_t q = perm[i - 1];
+        if (key_idx[i - 1] == id && (P.len[q] ? P.pool[P.off[q]] : 0u) == w0) return;
+    }
+    size_t j = i + 1; bool any_long = P.len[r] > 16;
+    while (j < P.n && key_idx[j] == id) {
+        const uint32_t q = perm[j];
+        if ((P.len[q] ? P.pool[P.off[q]] : 0u) != w0) break;
+        any_long |= P.len[q] > 16;
+        j++;
+    }
+    if (!any_long || j - i < 2) return;
+    for (size_t k = i + 1; k < j; k++) {
+        const uint32_t v = perm[k]; size_t q = k;
+        while (q > i && tail_cmp(P, perm[q - 1], v) > 0) { perm[q] = perm[q - 1]; q--; }
+        perm[q] = v;
+    }
+}
+
 __device__ __forceinline__ bool same_rec(const PatsView &P, uint32_t a, uint32_t b) {
     if (P.idx[a] != P.idx[b] || P.len[a] != P.len[b]) return false;
     const uint32_t nw = (P.len[a] + 15) >> 4;
@@ -99,23 +131,16 @@ extern "C" int wgbs_collapse(wgbs_ctx *ctx, wgbs_pats *P) {
     if (n < 1) return 0;
     if (n >= 0xffffffffull) return wgbs_set_err("wgbs_collapse: too many records");
     Temps T(ctx);
-    uint32_t *d_mw = ctx->d_flags + 1;
-    CUDA_TRY(cudaMemsetAsync(d_mw, 0, 4, ctx->stream));
-    LAUNCH(ctx, max_words_k, grid_for(n, 256), 256, 0, P->len, n, d_mw);
-    uint32_t maxw = 0;
-    CUDA_TRY(cudaMemcpyAsync(&maxw, d_mw, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     uint32_t *k0, *v0, *k1, *v1;
     RC_TRY(T.alloc(&k0, n)); RC_TRY(T.alloc(&v0, n)); RC_TRY(T.alloc(&k1, n)); RC_TRY(T.alloc(&v1, n));
     uint32_t *k = k0, *v = v0, *ka = k1, *va = v1;
     RC_TRY(fill_iota(ctx, v, n));
     PatsView pv = view_of(P);
-    for (int w = (int)maxw - 1; w >= 0; w--) {
-        LAUNCH(ctx, gather_word_k, grid_for(n, 256), 256, 0, pv, v, (uint32_t)w, k);
-        RC_TRY(radix_sort_pairs(ctx, &k, &v, &ka, &va, n));
-    }
-    LAUNCH(ctx, gather_idx_k, grid_for(n, 256), 256, 0, pv, v, k);
+    LAUNCH(ctx, gather_word_k, grid_for(n, 256), 256, 0, pv, v, 0u, k);        // least significant key: pattern word 0
     RC_TRY(radix_sort_pairs(ctx, &k, &v, &ka, &va, n));
+    LAUNCH(ctx, gather_idx_k, grid_for(n, 256), 256, 0, pv, v, k);             // most significant key: CpG index
+    RC_TRY(radix_sort_pairs(ctx, &k, &v, &ka, &va, n));
+    LAUNCH(ctx, fix_ties_k, grid_for(n, 128), 128, 0, pv, v, k);                // longer patterns: order inside (idx, word0) runs
     // run-length: heads, destinations, counts
     uint32_t *head, *dst;
     RC_TRY(T.alloc(&head, n)); RC_TRY(T.alloc(&dst, n + 1));

@@ -4,9 +4,10 @@
 // (pipeline_wgbs/patter.cpp:395-412).  match_maker sorts buffered SAM lines as whole strings, pairs adjacent lines
 // with equal QNAME greedily and lets everything else through as singles; for a coordinate-sorted single-chromosome
 // stream with consistent PNEXT that is exactly "group records by QNAME; within a group, in whole-line order, pair
-// greedily".  Here: sort record ids by the 64-bit QNAME hash (two stable 32-bit radix sorts), then one thread per
+// greedily".  Here: sort record ids by the QNAME hash (one stable 32-bit radix sort), then one thread per
 // hash run: runs of 1 are singles, runs of 2 with byte-equal names are a pair, anything else (3+ records, or a hash
-// collision) is ordered by whole-line bytes by that thread and paired greedily.
+// collision) is ordered by whole-line bytes by that thread and paired greedily.  (Only the low 32 hash bits are sorted
+// on; names are always compared byte for byte, so collisions cost time, never correctness.)
 //
 // Output: mate[r] = record id of r's mate or NONE.  The template's slot is the smaller record id of the two, so
 // templates stay in coordinate order.
@@ -42,16 +43,15 @@ __device__ bool name_eq(const ReadBatchView &rb, uint32_t a, uint32_t b) {
 }
 
 __global__ void __launch_bounds__(256) pair_runs_k(ReadBatchView rb, uint32_t *__restrict__ perm, const uint32_t *__restrict__ hlo,
-                                                    const uint32_t *__restrict__ hhi, uint32_t n, uint32_t *__restrict__ mate,
-                                                    unsigned long long *__restrict__ stats) {
+                                                    uint32_t n, uint32_t *__restrict__ mate, unsigned long long *__restrict__ stats) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t npairs = 0;
     if (i < n) {
-        const uint32_t lo = hlo[i], hi = hhi[i];
-        bool head = (i == 0) || hlo[i - 1] != lo || hhi[i - 1] != hi;
+        const uint32_t lo = hlo[i];
+        bool head = (i == 0) || hlo[i - 1] != lo;
         if (head) {
             uint32_t j = i + 1;
-            while (j < n && hlo[j] == lo && hhi[j] == hi) j++;
+            while (j < n && hlo[j] == lo) j++;
             uint32_t run = j - i;
             if (run == 2) {
                 uint32_t a = perm[i], b = perm[i + 1];
@@ -85,19 +85,15 @@ int build_mates(wgbs_ctx *ctx, const ReadBatch &rb, bool paired, Temps &T, uint3
     if (n) LAUNCH(ctx, fill_u32_k, grid_for(n, 256), 256, 0, mate, (size_t)n, NONE);
     *mate_out = mate;
     if (!paired || n < 2) { LAUNCH_CHECK(); return 0; }
-    uint32_t *k0, *v0, *k1, *v1, *hlo_s;
-    RC_TRY(T.alloc(&k0, n)); RC_TRY(T.alloc(&v0, n)); RC_TRY(T.alloc(&k1, n)); RC_TRY(T.alloc(&v1, n)); RC_TRY(T.alloc(&hlo_s, n));
+    // sort record ids by the LOW 32 bits of the QNAME hash only (4 digit passes): equal-key runs then hold the mates plus
+    // the occasional 32-bit collision, which pair_runs_k separates with the high word and the name bytes themselves.
+    uint32_t *k0, *v0, *k1, *v1, *hhi_s;
+    RC_TRY(T.alloc(&k0, n)); RC_TRY(T.alloc(&v0, n)); RC_TRY(T.alloc(&k1, n)); RC_TRY(T.alloc(&v1, n)); RC_TRY(T.alloc(&hhi_s, n));
     CUDA_TRY(cudaMemcpyAsync(k0, rb.hash_lo, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     RC_TRY(fill_iota(ctx, v0, n));
     uint32_t *k = k0, *v = v0, *ka = k1, *va = v1;
     RC_TRY(radix_sort_pairs(ctx, &k, &v, &ka, &va, n));
-    // second key word, gathered through the current order
-    LAUNCH(ctx, gather_u32_k, grid_for(n, 256), 256, 0, rb.hash_hi, v, ka, (size_t)n);
-    { uint32_t *t = k; k = ka; ka = t; }
-    RC_TRY(radix_sort_pairs(ctx, &k, &v, &ka, &va, n));
-    // k = sorted hash_hi, v = record ids ordered by (hi, lo); fetch the matching lo words
-    LAUNCH(ctx, gather_u32_k, grid_for(n, 256), 256, 0, rb.hash_lo, v, hlo_s, (size_t)n);
-    LAUNCH(ctx, pair_runs_k, grid_for(n, 256), 256, 0, view_of(rb), v, hlo_s, k, n, mate, d_stats);
+    LAUNCH(ctx, pair_runs_k, grid_for(n, 256), 256, 0, view_of(rb), v, k, n, mate, d_stats);
     LAUNCH_CHECK();
     return 0;
 }
