@@ -171,6 +171,82 @@ def algorithmic_bytes(kernel: str, n_rec: int, text_bytes: int, n_tmpl: int):
     }.get(kernel)
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# the other hot-path steps (BASELINE.json metric: "pat2beta CpG-sites/sec", homog, segment) -- reported under "extra"
+# ----------------------------------------------------------------------------------------------------------------------
+def extras(ctx, torch, peak):
+    import ctypes as C
+    from oracle import harness as H
+    from wgbs_tools_b200 import synth
+    from wgbs_tools_b200._lib import check, lib
+    out = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    stream = torch.cuda.current_stream()
+
+    def dev_time(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = ev(), ev()
+        a.record(stream)
+        for _ in range(reps):
+            fn()
+        b.record(stream)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps / 1e3
+
+    # ---- pat2beta + homog on a sorted pat of 2M records over the chr19-sized index
+    N, R = N_CPG, 2_000_000
+    t0 = time.time()
+    txt = synth.make_pat_text_fast(3, R, N, chrom=CHR)
+    log(f"[bench] pat text: {R:,} records, {len(txt) / 1e6:.1f} MB ({time.time() - t0:.1f}s)")
+    d_txt = ctx.upload(txt)
+    mc = ctx.alloc(N * 8)
+    P = ctx.pats_from_text(d_txt)
+    sec_parse = dev_time(lambda: ctx.pats_from_text(d_txt).free())
+    sec_p2b = dev_time(lambda: ctx.pat2beta(P, 1, N + 1, meth_cov=mc))
+    words = P.pool_words
+    p2b_bytes = R * 16 + words * 4 + N * 8          # idx,len,count,off + symbol words + one int32 pair per site written
+    out["pat2beta"] = {"records": R, "sites": N, "parse_text_ms": sec_parse * 1e3, "kernel_ms": sec_p2b * 1e3,
+                       "sites_per_sec": N / (sec_parse + sec_p2b), "records_per_sec": R / (sec_parse + sec_p2b),
+                       "roofline": {"kernel": "pat2beta_k", "bound": "hbm", "achieved": p2b_bytes / sec_p2b / 1e9, "peak": peak, "unit": "GB/s",
+                                    "frac": p2b_bytes / sec_p2b / 1e9 / peak, "algorithmic_bytes": p2b_bytes}}
+    blocks = synth.make_blocks(5, 1, N)
+    rng = np.array([0, 0.334, 0.667, 1], np.float32)
+    bs = ctx.upload(np.ascontiguousarray(blocks[:, 0])); be = ctx.upload(np.ascontiguousarray(blocks[:, 1]))
+    d_rng = ctx.upload(rng); d_out = ctx.alloc(blocks.shape[0] * 12)
+    sec_h = dev_time(lambda: check(lib.wgbs_homog(ctx.h, P.h, bs.ptr, be.ptr, blocks.shape[0], d_rng.ptr, 3, 3, 0, d_out.ptr)))
+    out["homog"] = {"records": R, "blocks": int(blocks.shape[0]), "ms": sec_h * 1e3, "records_per_sec": R / sec_h, "sites_per_sec": N / sec_h}
+    # reference CPU (single process, reference flags) on the same text
+    if H.have_ref():
+        t0 = time.time(); H.ref_stdin2beta(txt, 1, N + 1); c1 = time.time() - t0
+        bp = H.write_tmp(synth.blocks_text(CHR, blocks), ".bed")
+        t0 = time.time(); H.ref_homog(txt, bp, "0,0.334,0.667,1", 3); c2 = time.time() - t0
+        os.remove(bp)
+        out["pat2beta"]["cpu_reference"] = {"sites_per_sec": N / c1, "records_per_sec": R / c1, "cores": 1}
+        out["homog"]["cpu_reference"] = {"records_per_sec": R / c2, "cores": 1}
+    P.free()
+    # ---- segment: K betas x S sites in 60000-site chunks (segment.py defaults: max_cpg 1000, max_bp 2000, pcount 15)
+    K, S = 10, 240_000
+    betas = synth.make_betas(9, K, S)
+    loci = genome().loci[:S]
+    dbet = [ctx.upload(b) for b in betas]; dd = ctx.upload(loci)
+    chunks = [(s, min(60_000, S - s)) for s in range(0, S, 60_000)]
+    t0 = time.time(); res = ctx.segment(dbet, dd, chunks, 1000, 2000, 15); torch.cuda.synchronize(); warm = time.time() - t0
+    t0 = time.time(); res = ctx.segment(dbet, dd, chunks, 1000, 2000, 15); torch.cuda.synchronize(); sec_s = time.time() - t0
+    out["segment"] = {"K": K, "sites": S, "chunks": len(chunks), "ms": sec_s * 1e3, "sites_per_sec": S / sec_s,
+                      "blocks": int(sum(len(r) - 1 for r in res)), "timing": "host wall clock around the C-ABI call (includes D2H of borders)"}
+    if H.have_ref():
+        paths = [H.write_tmp(b.tobytes(), f".{i}.beta") for i, b in enumerate(betas)]
+        t0 = time.time(); r0 = H.ref_segmentor(paths, 0, 60_000, 1000, 2000, 15, loci[:60_000]); c3 = time.time() - t0
+        out["segment"]["cpu_reference"] = {"sites_per_sec": 60_000 / c3, "cores": 1, "sample": "first 60000-site chunk", "identical_borders": bool(np.array_equal(r0, res[0]))}
+        for p in paths:
+            os.remove(p)
+    for b in dbet + [dd, d_txt, mc, bs, be, d_rng, d_out]:
+        b.free()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -178,6 +254,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=1_000_000)
+    ap.add_argument("--no-extras", dest="no_extras", action="store_true", help="skip the pat2beta / homog / segment side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -350,6 +427,14 @@ def main():
                    "sample": f"whole batch ({n_rec:,} records) once, as {nsh} concurrent shard pipelines of the reference "
                              "executables (match_maker|patter|sort|uniq|awk; reference setup.py flags, i.e. no -O)"}
 
+    extra = None
+    if rank == 0 and args.gpus == 1 and not args.no_extras:
+        try:
+            extra = extras(ctx, torch, roof["peak"] if roof else 6650.0)
+        except Exception as e:
+            log(f"[bench] extras failed: {e!r}")
+            extra = {"error": repr(e)}
+
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -357,7 +442,7 @@ def main():
             "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": text_bytes, "d2h_bytes_per_step": last["text_bytes"] + 2 * g.n_cpg,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "extra": extra,
             "outputs": {"pat_text_bytes": last["text_bytes"], "stats": dict(zip(["lines", "pairs", "empty", "short", "invalid", "paired", "nanopore", "templates"], last["stats"]))},
         }
         print(json.dumps(out))

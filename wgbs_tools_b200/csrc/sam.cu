@@ -48,23 +48,34 @@ __device__ __forceinline__ int tag_kind(const char *__restrict__ t, uint32_t p, 
 // The "tabs since the last newline" state is a segmented sum: combine(l, r) = (l.nl + r.nl, r.nl ? r.tail : l.tail + r.tail).
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int TK2_T = 256, TK2_CPT = 4, TK2_TILE = TK2_T * TK2_CPT * 16;   // 16 KiB
+static_assert(TK2_CPT == 4, "load_masks reads 4 masks per thread as one uint4");
 
 struct Seg { uint32_t nl, tail; };
 __device__ __forceinline__ Seg seg_combine(Seg l, Seg r) { Seg o; o.nl = l.nl + r.nl; o.tail = r.nl ? r.tail : l.tail + r.tail; return o; }
 
-// masks of the 64 bytes a thread owns: bit b of m[c] <-> byte 16*c + b
-__device__ __forceinline__ void load_masks(const char *__restrict__ text, size_t n, size_t p0, uint32_t *tabm, uint32_t *nlm) {
+// masks of the 64 bytes a thread owns: bit b of m[c] <-> byte 16*c + b.
+// Global loads are coalesced (consecutive lanes read consecutive 16-byte chunks, TK2_CPT rounds); the (tab, newline)
+// masks are then transposed through shared memory so that each thread ends up with its 4 CONSECUTIVE chunks.
+__device__ __forceinline__ void load_masks(const char *__restrict__ text, size_t n, size_t tile0, uint32_t *tabm, uint32_t *nlm) {
+    __shared__ uint32_t sm_mask[TK2_T * TK2_CPT];      // (nl << 16) | tab per chunk, chunk order
 #pragma unroll
     for (int c = 0; c < TK2_CPT; c++) {
-        const size_t p = p0 + (size_t)c * 16;
+        const uint32_t chunk = c * TK2_T + threadIdx.x;
+        const size_t p = tile0 + (size_t)chunk * 16;
         uint32_t tm = 0, nm = 0;
         if (p < n) {
             const uint4 v = (p + 16 <= n) ? *reinterpret_cast<const uint4 *>(text + p) : load16_guard(text, p, n);
             tm = eq_mask16(v, '\t'); nm = eq_mask16(v, '\n');
             if (n - p < 16) { const uint32_t ok = (1u << (n - p)) - 1; tm &= ok; nm &= ok; }
         }
-        tabm[c] = tm; nlm[c] = nm;
+        sm_mask[chunk] = (nm << 16) | tm;
     }
+    __syncthreads();
+    const uint4 q = *reinterpret_cast<const uint4 *>(&sm_mask[threadIdx.x * TK2_CPT]);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int c = 0; c < TK2_CPT; c++) { tabm[c] = w[c] & 0xffffu; nlm[c] = w[c] >> 16; }
+    __syncthreads();
 }
 __device__ __forceinline__ Seg thread_seg(const uint32_t *tabm, const uint32_t *nlm) {
     Seg s; s.nl = 0; s.tail = 0;
@@ -101,7 +112,7 @@ __device__ __forceinline__ Seg block_seg_excl(Seg v, Seg *total) {
 
 __global__ void __launch_bounds__(TK2_T) tk_count_k(const char *__restrict__ text, size_t n, uint2 *__restrict__ tile_seg) {
     uint32_t tabm[TK2_CPT], nlm[TK2_CPT];
-    load_masks(text, n, (size_t)blockIdx.x * TK2_TILE + (size_t)threadIdx.x * (TK2_CPT * 16), tabm, nlm);
+    load_masks(text, n, (size_t)blockIdx.x * TK2_TILE, tabm, nlm);
     Seg tot;
     block_seg_excl(thread_seg(tabm, nlm), &tot);
     if (threadIdx.x == 0) tile_seg[blockIdx.x] = make_uint2(tot.nl, tot.tail);
@@ -144,7 +155,7 @@ __global__ void __launch_bounds__(TK2_T) tk_mark_k(const char *__restrict__ text
                                                     uint32_t *__restrict__ mm_off, uint32_t *__restrict__ ml_off) {
     uint32_t tabm[TK2_CPT], nlm[TK2_CPT];
     const size_t p0 = (size_t)blockIdx.x * TK2_TILE + (size_t)threadIdx.x * (TK2_CPT * 16);
-    load_masks(text, n, p0, tabm, nlm);
+    load_masks(text, n, (size_t)blockIdx.x * TK2_TILE, tabm, nlm);
     Seg tot;
     const Seg pre_local = block_seg_excl(thread_seg(tabm, nlm), &tot);
     const uint2 ts = tile_start[blockIdx.x];
