@@ -13,16 +13,13 @@ __device__ __forceinline__ uint4 load16_guard(const char *__restrict__ text, siz
         if (pos + b < n) w[b >> 2] |= (uint32_t)(uint8_t)text[pos + b] << ((b & 3) * 8);
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
-// bit b set iff byte b of the 16-byte chunk equals c
+// bit b set iff byte b of the 16-byte chunk equals c.  Per word: SIMD byte compare (0xff per equal byte), keep bit 0 of
+// every byte, and gather the four bits into the top nibble with one multiply (2^24 + 2^17 + 2^10 + 2^3).
 __device__ __forceinline__ uint32_t eq_mask16(uint4 v, uint32_t c) {
     const uint32_t rep = c * 0x01010101u;
-    uint32_t m = 0;
-    uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        uint32_t x = w[i] ^ rep;                                   // zero byte where equal
-        uint32_t z = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu);  // 0x80 in each zero byte
-        m |= (((z >> 7) & 1u) | ((z >> 14) & 2u) | ((z >> 21) & 4u) | ((z >> 28) & 8u)) << (4 * i);
-    }
-    return m;
+    const uint32_t m0 = ((__vcmpeq4(v.x, rep) & 0x01010101u) * 0x01020408u) >> 24;
+    const uint32_t m1 = ((__vcmpeq4(v.y, rep) & 0x01010101u) * 0x01020408u) >> 24;
+    const uint32_t m2 = ((__vcmpeq4(v.z, rep) & 0x01010101u) * 0x01020408u) >> 24;
+    const uint32_t m3 = ((__vcmpeq4(v.w, rep) & 0x01010101u) * 0x01020408u) >> 24;
+    return m0 | (m1 << 4) | (m2 << 8) | (m3 << 12);
 }
