@@ -160,8 +160,7 @@ def algorithmic_bytes(kernel: str, n_rec: int, text_bytes: int, n_tmpl: int):
     """bytes one launch must move at minimum.  n for the sort kernels is not fixed (records when pairing,
     templates when collapsing): use the larger so the fraction is a lower bound."""
     return {
-        "tk_count_k": text_bytes,                        # read the text once
-        "tk_mark_k": text_bytes + 4 * n_rec + 44 * n_rec,   # read the text; write a newline offset and 11 tab offsets per line
+        "tk_scan_k": text_bytes + 4 * n_rec + 44 * n_rec,   # read the text ONCE; write a newline offset and 11 tab offsets per line
         "tk_records_k": 48 * n_rec + 52 * n_rec + 32 * n_rec,  # read offsets (+ QNAME/FLAG/POS bytes), write 13 descriptor words
         "rs_onesweep_k": 16 * n_rec,                     # (key,val) read + written
         "rs_global_hist_k": 4 * n_rec,
@@ -326,15 +325,18 @@ def main():
         h = C.c_void_p(); st = (C.c_uint64 * 8)()
         check(lib.wgbs_pileup_sam(ctx.h, ix.h, src.data_ptr(), text_bytes, C.addressof(o), C.byref(h), C.addressof(st)))
         check(lib.wgbs_pat2beta(ctx.h, h, start, end, mc.data_ptr(), 1))
-        if world > 1 and reduce:
-            dist.reduce(mc, dst=0, op=dist.ReduceOp.SUM)      # the one exchange step: int32[N,2] beta counts over NVLink
-        bout = h_beta if host else d_beta
-        if rank == 0:
-            check(lib.wgbs_trim(ctx.h, mc.data_ptr(), g.n_cpg, 8, bout.data_ptr()))
+        work = None
+        if world > 1 and reduce:                              # the one exchange step: int32[N,2] beta counts over NVLink,
+            work = dist.reduce(mc, dst=0, op=dist.ReduceOp.SUM, async_op=True)   # overlapped with collapse + formatting
         check(lib.wgbs_collapse(ctx.h, h))
         n = C.c_size_t()
         tout = h_text if host else d_text
         check(lib.wgbs_pats_format(ctx.h, h, CHR.encode(), tout.data_ptr(), tout.numel(), C.byref(n)))
+        if work is not None:
+            work.wait()                                       # current stream waits for the NCCL stream
+        bout = h_beta if host else d_beta
+        if rank == 0:
+            check(lib.wgbs_trim(ctx.h, mc.data_ptr(), g.n_cpg, 8, bout.data_ptr()))
         last.update(text_bytes=n.value, stats=[int(x) for x in st])
         lib.wgbs_pats_free(ctx.h, h)
 

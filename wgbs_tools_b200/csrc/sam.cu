@@ -39,139 +39,121 @@ __device__ __forceinline__ int tag_kind(const char *__restrict__ t, uint32_t p, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Flat tokenizer.  The text is cut into 16 KiB tiles; a thread owns 64 consecutive bytes (4 aligned LDG.128).
-//   tk_count_k     per tile: (#newlines, #tabs after the tile's last newline [all tabs if it has none])
-//   tk_tilescan_k  one CTA: running (newline count, tabs since the last newline) at every tile start
-//   tk_mark_k      per tile again: every newline -> nlpos[line]; every tab -> its ordinal inside its line; the first 11 go
-//                  to ftab[line*11 + ordinal]; tabs that start a tag field are checked for MM/ML
-//   tk_records_k   one thread per line: FLAG / POS, field spans, QNAME hash, MM/ML spans
-// The "tabs since the last newline" state is a segmented sum: combine(l, r) = (l.nl + r.nl, r.nl ? r.tail : l.tail + r.tail).
+// Flat single-pass tokenizer.  The text is cut into 16 KiB tiles (one CTA each, handed out by an atomic ticket); a thread
+// owns 64 consecutive bytes.  tk_scan_k reads every byte ONCE:
+//   - byte-compare masks for '\t' and '\n' (aligned LDG.128, coalesced; masks are re-distributed inside each warp through
+//     shared memory so that a lane ends up with its 4 consecutive chunks),
+//   - a segmented scan gives every tab its ordinal inside its line and every newline its line number:
+//       state = (newlines so far, tabs since the last newline);  combine(l, r) = (l.nl + r.nl, r.nl ? r.tail : l.tail + r.tail)
+//     lanes -> warp shuffles, warps -> shared memory (one __syncthreads), tiles -> decoupled look-back over a status word
+//     per tile (flag | newline count | tab tail), so no second pass over the text is needed,
+//   - newline offsets go to nlpos[line], the first 11 tab offsets of a line to ftab[line*11 + ordinal]; a tab that starts
+//     a tag field (ordinal >= 10) is checked for MM / ML.
+// tk_records_k then turns one line per thread into a ReadBatch record (FLAG / POS, field spans, QNAME hash, tag spans).
+// The line count is not known before the pass: output arrays are sized for an average line of >= 96 bytes, and the pass
+// is repeated with the exact size in the (pathological) case that this was not enough.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int TK2_T = 256, TK2_CPT = 4, TK2_TILE = TK2_T * TK2_CPT * 16;   // 16 KiB
-static_assert(TK2_CPT == 4, "load_masks reads 4 masks per thread as one uint4");
+static_assert(TK2_CPT == 4, "a lane reads its 4 masks as one uint4");
+constexpr unsigned long long TS_AGG = 1ull << 62, TS_INC = 2ull << 62;
 
 struct Seg { uint32_t nl, tail; };
 __device__ __forceinline__ Seg seg_combine(Seg l, Seg r) { Seg o; o.nl = l.nl + r.nl; o.tail = r.nl ? r.tail : l.tail + r.tail; return o; }
+__device__ __forceinline__ unsigned long long seg_pack(Seg s, unsigned long long flag) { return flag | ((unsigned long long)s.nl << 16) | (s.tail > 0xffffu ? 0xffffu : s.tail); }
+__device__ __forceinline__ Seg seg_unpack(unsigned long long w) { Seg s; s.nl = (uint32_t)(w >> 16); s.tail = (uint32_t)(w & 0xffffu); return s; }
 
-// masks of the 64 bytes a thread owns: bit b of m[c] <-> byte 16*c + b.
-// Global loads are coalesced (consecutive lanes read consecutive 16-byte chunks, TK2_CPT rounds); the (tab, newline)
-// masks are then transposed through shared memory so that each thread ends up with its 4 CONSECUTIVE chunks.
-__device__ __forceinline__ void load_masks(const char *__restrict__ text, size_t n, size_t tile0, uint32_t *tabm, uint32_t *nlm) {
-    __shared__ uint32_t sm_mask[TK2_T * TK2_CPT];      // (nl << 16) | tab per chunk, chunk order
+__global__ void __launch_bounds__(TK2_T) tk_scan_k(const char *__restrict__ text, size_t n, uint32_t line_cap, int want_tags,
+                                                    unsigned long long *__restrict__ status, unsigned int *__restrict__ ticket,
+                                                    uint32_t *__restrict__ nlpos, uint32_t *__restrict__ ftab,
+                                                    uint32_t *__restrict__ mm_off, uint32_t *__restrict__ ml_off, uint32_t *__restrict__ totals) {
+    __shared__ uint32_t sm_mask[TK2_T * TK2_CPT];      // (nl << 16) | tab per chunk; warp w owns [w*128, w*128+128)
+    __shared__ Seg ws[TK2_T / 32];
+    __shared__ Seg s_start;
+    __shared__ unsigned s_tile;
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const size_t warp0 = (size_t)tile * TK2_TILE + (size_t)w * (32 * TK2_CPT * 16);   // first byte of this warp's 2 KiB
+    // ---- masks, coalesced: round c, lane l -> chunk c*32 + l of the warp
 #pragma unroll
     for (int c = 0; c < TK2_CPT; c++) {
-        const uint32_t chunk = c * TK2_T + threadIdx.x;
-        const size_t p = tile0 + (size_t)chunk * 16;
+        const size_t p = warp0 + (size_t)(c * 32 + lane) * 16;
         uint32_t tm = 0, nm = 0;
         if (p < n) {
             const uint4 v = (p + 16 <= n) ? *reinterpret_cast<const uint4 *>(text + p) : load16_guard(text, p, n);
             tm = eq_mask16(v, '\t'); nm = eq_mask16(v, '\n');
             if (n - p < 16) { const uint32_t ok = (1u << (n - p)) - 1; tm &= ok; nm &= ok; }
         }
-        sm_mask[chunk] = (nm << 16) | tm;
+        sm_mask[w * 128 + c * 32 + lane] = (nm << 16) | tm;
     }
-    __syncthreads();
-    const uint4 q = *reinterpret_cast<const uint4 *>(&sm_mask[threadIdx.x * TK2_CPT]);
-    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-    for (int c = 0; c < TK2_CPT; c++) { tabm[c] = w[c] & 0xffffu; nlm[c] = w[c] >> 16; }
-    __syncthreads();
-}
-__device__ __forceinline__ Seg thread_seg(const uint32_t *tabm, const uint32_t *nlm) {
-    Seg s; s.nl = 0; s.tail = 0;
+    __syncwarp();
+    const uint4 q = *reinterpret_cast<const uint4 *>(&sm_mask[w * 128 + lane * TK2_CPT]);   // this lane's 4 consecutive chunks
+    const uint32_t mk[4] = {q.x, q.y, q.z, q.w};
+    // ---- lane state, warp scan, warp aggregate
+    Seg mine; mine.nl = 0; mine.tail = 0;
 #pragma unroll
     for (int c = 0; c < TK2_CPT; c++) {
-        const uint32_t nm = nlm[c], tm = tabm[c];
-        if (nm) { s.nl += __popc(nm); s.tail = __popc(tm & ~((2u << (31 - __clz(nm))) - 1)); }   // tabs after the chunk's last newline
-        else s.tail += __popc(tm);
+        const uint32_t nm = mk[c] >> 16, tm = mk[c] & 0xffffu;
+        if (nm) { mine.nl += __popc(nm); mine.tail = __popc(tm & ~((2u << (31 - __clz(nm))) - 1)); }   // tabs after the chunk's last newline
+        else mine.tail += __popc(tm);
     }
-    return s;
-}
-// block-wide EXCLUSIVE segmented scan of one Seg per thread (thread order = byte order); *total = all threads combined
-__device__ __forceinline__ Seg block_seg_excl(Seg v, Seg *total) {
-    __shared__ Seg ws[TK2_T / 32];
-    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    Seg inc = v;
+    Seg inc = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         Seg o; o.nl = __shfl_up_sync(0xffffffffu, inc.nl, d); o.tail = __shfl_up_sync(0xffffffffu, inc.tail, d);
         if (lane >= (unsigned)d) inc = seg_combine(o, inc);
     }
-    if (lane == 31) ws[w] = inc;
     Seg ex; ex.nl = __shfl_up_sync(0xffffffffu, inc.nl, 1); ex.tail = __shfl_up_sync(0xffffffffu, inc.tail, 1);
     if (lane == 0) { ex.nl = 0; ex.tail = 0; }
+    if (lane == 31) ws[w] = inc;
     __syncthreads();
     Seg pre; pre.nl = 0; pre.tail = 0;
     Seg tot; tot.nl = 0; tot.tail = 0;
 #pragma unroll
     for (int i = 0; i < TK2_T / 32; i++) { if (i < (int)w) pre = seg_combine(pre, ws[i]); tot = seg_combine(tot, ws[i]); }
-    *total = tot;
-    __syncthreads();
-    return seg_combine(pre, ex);
-}
-
-__global__ void __launch_bounds__(TK2_T) tk_count_k(const char *__restrict__ text, size_t n, uint2 *__restrict__ tile_seg) {
-    uint32_t tabm[TK2_CPT], nlm[TK2_CPT];
-    load_masks(text, n, (size_t)blockIdx.x * TK2_TILE, tabm, nlm);
-    Seg tot;
-    block_seg_excl(thread_seg(tabm, nlm), &tot);
-    if (threadIdx.x == 0) tile_seg[blockIdx.x] = make_uint2(tot.nl, tot.tail);
-}
-
-// in place: tile_seg[t] <- state at the START of tile t;  tile_seg[ntiles] <- state at the end of the text
-__global__ void __launch_bounds__(1024) tk_tilescan_k(uint2 *__restrict__ tile_seg, uint32_t ntiles) {
-    __shared__ Seg ws[32];
-    __shared__ Seg carry;
-    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (threadIdx.x == 0) { carry.nl = 0; carry.tail = 0; }
-    __syncthreads();
-    for (uint32_t base = 0; base < ntiles; base += 1024) {
-        const uint32_t t = base + threadIdx.x;
-        Seg v; v.nl = 0; v.tail = 0;
-        if (t < ntiles) { const uint2 q = tile_seg[t]; v.nl = q.x; v.tail = q.y; }
-        Seg inc = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            Seg o; o.nl = __shfl_up_sync(0xffffffffu, inc.nl, d); o.tail = __shfl_up_sync(0xffffffffu, inc.tail, d);
-            if (lane >= (unsigned)d) inc = seg_combine(o, inc);
+    // ---- tile start state: decoupled look-back (thread 0), states combine right-to-left
+    if (threadIdx.x == 0) {
+        volatile unsigned long long *st = status;
+        Seg start; start.nl = 0; start.tail = 0;
+        if (tile == 0) st[0] = seg_pack(tot, TS_INC);
+        else {
+            st[tile] = seg_pack(tot, TS_AGG);
+            Seg acc; acc.nl = 0; acc.tail = 0;           // combined state of tiles (t, tile)
+            long long t = (long long)tile - 1;
+            while (true) {
+                unsigned long long x;
+                do { x = st[t]; } while ((x >> 62) == 0);
+                acc = seg_combine(seg_unpack(x & ~(3ull << 62)), acc);
+                if ((x >> 62) == 2) break;
+                t--;
+            }
+            start = acc;
+            st[tile] = seg_pack(seg_combine(start, tot), TS_INC);
         }
-        if (lane == 31) ws[w] = inc;
-        Seg ex; ex.nl = __shfl_up_sync(0xffffffffu, inc.nl, 1); ex.tail = __shfl_up_sync(0xffffffffu, inc.tail, 1);
-        if (lane == 0) { ex.nl = 0; ex.tail = 0; }
-        __syncthreads();
-        Seg pre = carry;
-        for (unsigned i = 0; i < w; i++) pre = seg_combine(pre, ws[i]);
-        const Seg mine = seg_combine(pre, ex);
-        if (t < ntiles) tile_seg[t] = make_uint2(mine.nl, mine.tail);
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = seg_combine(mine, v);
-        __syncthreads();
+        s_start = start;
+        if ((size_t)(tile + 1) * TK2_TILE >= n) { const Seg e = seg_combine(start, tot); totals[0] = e.nl; }   // last tile: newline total
     }
-    if (threadIdx.x == 0) tile_seg[ntiles] = make_uint2(carry.nl, carry.tail);
-}
-
-__global__ void __launch_bounds__(TK2_T) tk_mark_k(const char *__restrict__ text, size_t n, const uint2 *__restrict__ tile_start,
-                                                    uint32_t n_lines, int want_tags, uint32_t *__restrict__ nlpos, uint32_t *__restrict__ ftab,
-                                                    uint32_t *__restrict__ mm_off, uint32_t *__restrict__ ml_off) {
-    uint32_t tabm[TK2_CPT], nlm[TK2_CPT];
-    const size_t p0 = (size_t)blockIdx.x * TK2_TILE + (size_t)threadIdx.x * (TK2_CPT * 16);
-    load_masks(text, n, (size_t)blockIdx.x * TK2_TILE, tabm, nlm);
-    Seg tot;
-    const Seg pre_local = block_seg_excl(thread_seg(tabm, nlm), &tot);
-    const uint2 ts = tile_start[blockIdx.x];
-    Seg g; g.nl = ts.x; g.tail = ts.y;
-    const Seg st = seg_combine(g, pre_local);          // state just before this thread's first byte
-    uint32_t line = st.nl, ord = st.tail;
+    __syncthreads();
+    const Seg stt = seg_combine(seg_combine(s_start, pre), ex);   // state just before this lane's first byte
+    uint32_t line = stt.nl, ord = stt.tail;
+    const size_t p0 = warp0 + (size_t)lane * (TK2_CPT * 16);
 #pragma unroll
     for (int c = 0; c < TK2_CPT; c++) {
-        uint32_t m = tabm[c] | nlm[c];
-        const uint32_t nm = nlm[c];
+        const uint32_t nm = mk[c] >> 16;
+        uint32_t m = (mk[c] & 0xffffu) | nm;
         while (m) {
             const int b = __ffs(m) - 1; m &= m - 1;
             const uint32_t x = (uint32_t)(p0 + (size_t)c * 16 + b);
-            if ((nm >> b) & 1u) { nlpos[line] = x; line++; ord = 0; }
+            if ((nm >> b) & 1u) {
+                if (line < line_cap) {
+                    nlpos[line] = x;
+                    for (uint32_t k = ord; k < NTAB; k++) ftab[(size_t)line * NTAB + k] = 0xffffffffu;   // fewer than 11 tabs: mark the rest absent
+                }
+                line++; ord = 0;
+            }
             else {
-                if (line < n_lines) {
+                if (line < line_cap) {
                     if (ord < NTAB) ftab[(size_t)line * NTAB + ord] = x;
                     if (want_tags && ord >= 10) {                      // field index ord+1 >= 11: a tag
                         const int k = tag_kind(text, x + 1, (uint32_t)n);
@@ -182,6 +164,9 @@ __global__ void __launch_bounds__(TK2_T) tk_mark_k(const char *__restrict__ text
             }
         }
     }
+    // a last line without a trailing newline is closed by the lane that owns the final byte
+    if (n && p0 <= n - 1 && n - 1 < p0 + TK2_CPT * 16 && text[n - 1] != '\n' && line < line_cap)
+        for (uint32_t k = ord; k < NTAB; k++) ftab[(size_t)line * NTAB + k] = 0xffffffffu;
 }
 
 // per-(byte, position) mixing summed over the name
@@ -234,36 +219,43 @@ __global__ void __launch_bounds__(256) tk_records_k(const char *__restrict__ tex
 int sam_tokenize(wgbs_ctx *ctx, const char *dtext, size_t nbytes, bool want_tags, Temps &T, ReadBatch *out) {
     if (nbytes >= 0xfffffff0ull) return wgbs_set_err("SAM text must be < 4 GiB per call (got %zu); split on line boundaries", nbytes);
     const uint32_t ntiles = (uint32_t)((nbytes + TK2_TILE - 1) / TK2_TILE);
-    uint2 *tile_seg;
-    RC_TRY(T.alloc(&tile_seg, (size_t)ntiles + 1));
+    ReadBatch rb;
+    rb.text = dtext; rb.nbytes = (uint32_t)nbytes;
+    uint32_t *nlpos = nullptr, *ftab = nullptr, *totals = ctx->d_flags + 8;
+    unsigned long long *status = nullptr;
+    if (ntiles) RC_TRY(T.alloc(&status, (size_t)ntiles + 1));
+    uint32_t cap = (uint32_t)(nbytes / 96 + 1024);            // optimistic: average line >= 96 bytes (a 50 bp SAM record is ~130)
     uint32_t n_nl = 0; char last = '\n';
-    if (ntiles) {
-        LAUNCH(ctx, tk_count_k, ntiles, TK2_T, 0, dtext, nbytes, tile_seg);
-        LAUNCH(ctx, tk_tilescan_k, 1, 1024, 0, tile_seg, ntiles);
-        CUDA_TRY(cudaMemcpyAsync(&n_nl, &tile_seg[ntiles].x, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<void *> sized;                                 // arrays sized by `cap`, re-made if the guess was too small
+    for (int attempt = 0; attempt < 2 && ntiles; attempt++) {
+        for (void *q : sized) { T.keep(q); dfree(ctx, q); }
+        sized.clear();
+        RC_TRY(T.alloc(&nlpos, cap)); sized.push_back(nlpos);
+        RC_TRY(T.alloc(&ftab, (size_t)cap * NTAB)); sized.push_back(ftab);
+        if (want_tags) {
+            RC_TRY(T.alloc(&rb.mm_off, cap)); sized.push_back(rb.mm_off); RC_TRY(T.alloc(&rb.ml_off, cap)); sized.push_back(rb.ml_off);
+            CUDA_TRY(cudaMemsetAsync(rb.mm_off, 0, (size_t)cap * 4, ctx->stream));
+            CUDA_TRY(cudaMemsetAsync(rb.ml_off, 0, (size_t)cap * 4, ctx->stream));
+        }
+        CUDA_TRY(cudaMemsetAsync(status, 0, ((size_t)ntiles + 1) * 8, ctx->stream));
+        LAUNCH(ctx, tk_scan_k, ntiles, TK2_T, 0, dtext, nbytes, cap, want_tags ? 1 : 0, status, (unsigned int *)(status + ntiles), nlpos, ftab,
+               rb.mm_off, rb.ml_off, totals);
+        CUDA_TRY(cudaMemcpyAsync(&n_nl, totals, 4, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(&last, dtext + nbytes - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (n_nl + 1 <= cap) break;
+        cap = n_nl + 1;                                       // many very short lines: repeat with the exact size
     }
     const uint32_t n_lines = n_nl + ((nbytes && last != '\n') ? 1 : 0);
-    ReadBatch rb;
-    rb.text = dtext; rb.nbytes = (uint32_t)nbytes; rb.n = n_lines;
-    uint32_t *nlpos, *ftab;
-    RC_TRY(T.alloc(&nlpos, n_nl)); RC_TRY(T.alloc(&ftab, (size_t)n_lines * NTAB));
+    rb.n = n_lines;
     RC_TRY(T.alloc(&rb.line_off, n_lines)); RC_TRY(T.alloc(&rb.line_len, n_lines)); RC_TRY(T.alloc(&rb.qn_len, n_lines));
     RC_TRY(T.alloc(&rb.flag, n_lines)); RC_TRY(T.alloc(&rb.pos, n_lines));
     RC_TRY(T.alloc(&rb.cig_off, n_lines)); RC_TRY(T.alloc(&rb.cig_len, n_lines));
     RC_TRY(T.alloc(&rb.seq_off, n_lines)); RC_TRY(T.alloc(&rb.seq_len, n_lines));
     RC_TRY(T.alloc(&rb.hash_lo, n_lines)); RC_TRY(T.alloc(&rb.hash_hi, n_lines));
     RC_TRY(T.alloc(&rb.status, n_lines));
-    if (want_tags) {
-        RC_TRY(T.alloc(&rb.mm_off, n_lines)); RC_TRY(T.alloc(&rb.mm_len, n_lines));
-        RC_TRY(T.alloc(&rb.ml_off, n_lines)); RC_TRY(T.alloc(&rb.ml_len, n_lines));
-        CUDA_TRY(cudaMemsetAsync(rb.mm_off, 0, (size_t)n_lines * 4, ctx->stream));
-        CUDA_TRY(cudaMemsetAsync(rb.ml_off, 0, (size_t)n_lines * 4, ctx->stream));
-    }
+    if (want_tags) { RC_TRY(T.alloc(&rb.mm_len, n_lines)); RC_TRY(T.alloc(&rb.ml_len, n_lines)); if (!ntiles) { RC_TRY(T.alloc(&rb.mm_off, 1)); RC_TRY(T.alloc(&rb.ml_off, 1)); } }
     if (n_lines) {
-        CUDA_TRY(cudaMemsetAsync(ftab, 0xff, (size_t)n_lines * NTAB * 4, ctx->stream));
-        LAUNCH(ctx, tk_mark_k, ntiles, TK2_T, 0, dtext, nbytes, tile_seg, n_lines, want_tags ? 1 : 0, nlpos, ftab, rb.mm_off, rb.ml_off);
         LAUNCH(ctx, tk_records_k, grid_for(n_lines, 256), 256, 0, dtext, (uint32_t)nbytes, nlpos, n_nl, n_lines, ftab, want_tags ? 1 : 0, rb);
         LAUNCH_CHECK();
     }
