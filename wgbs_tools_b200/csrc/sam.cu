@@ -112,27 +112,43 @@ __global__ void __launch_bounds__(TK2_T) tk_scan_k(const char *__restrict__ text
     Seg tot; tot.nl = 0; tot.tail = 0;
 #pragma unroll
     for (int i = 0; i < TK2_T / 32; i++) { if (i < (int)w) pre = seg_combine(pre, ws[i]); tot = seg_combine(tot, ws[i]); }
-    // ---- tile start state: decoupled look-back (thread 0), states combine right-to-left
-    if (threadIdx.x == 0) {
+    // ---- tile start state: decoupled look-back by warp 0, 32 predecessor tiles per probe.  Lane j holds tile-1-j; an
+    // ordered warp scan combines them (earlier tiles on the left) up to the nearest tile that already published an
+    // inclusive state.
+    if (w == 0) {
         volatile unsigned long long *st = status;
         Seg start; start.nl = 0; start.tail = 0;
-        if (tile == 0) st[0] = seg_pack(tot, TS_INC);
+        if (tile == 0) { if (lane == 0) st[0] = seg_pack(tot, TS_INC); }
         else {
-            st[tile] = seg_pack(tot, TS_AGG);
-            Seg acc; acc.nl = 0; acc.tail = 0;           // combined state of tiles (t, tile)
-            long long t = (long long)tile - 1;
+            if (lane == 0) st[tile] = seg_pack(tot, TS_AGG);
+            Seg acc; acc.nl = 0; acc.tail = 0;           // combined state of the tiles already folded in (nearest ones)
+            long long top = (long long)tile - 1;
             while (true) {
-                unsigned long long x;
-                do { x = st[t]; } while ((x >> 62) == 0);
-                acc = seg_combine(seg_unpack(x & ~(3ull << 62)), acc);
-                if ((x >> 62) == 2) break;
-                t--;
+                const long long j = top - lane;
+                unsigned long long x = TS_INC;           // before tile 0: the empty inclusive state
+                if (j >= 0) x = st[j];
+                while (__any_sync(0xffffffffu, (x >> 62) == 0)) { if ((x >> 62) == 0) x = st[j]; }
+                const unsigned incm = __ballot_sync(0xffffffffu, (x >> 62) == 2);
+                Seg v = seg_unpack(x & ~(3ull << 62));
+                // inclusive ordered scan: lane j <- S(top-j) o ... o S(top)
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    Seg o; o.nl = __shfl_up_sync(0xffffffffu, v.nl, d); o.tail = __shfl_up_sync(0xffffffffu, v.tail, d);
+                    if (lane >= (unsigned)d) v = seg_combine(v, o);
+                }
+                const int L = incm ? __ffs(incm) - 1 : 31;
+                Seg win; win.nl = __shfl_sync(0xffffffffu, v.nl, L); win.tail = __shfl_sync(0xffffffffu, v.tail, L);
+                acc = seg_combine(win, acc);
+                if (incm) break;
+                top -= 32;
             }
             start = acc;
-            st[tile] = seg_pack(seg_combine(start, tot), TS_INC);
+            if (lane == 0) st[tile] = seg_pack(seg_combine(start, tot), TS_INC);
         }
-        s_start = start;
-        if ((size_t)(tile + 1) * TK2_TILE >= n) { const Seg e = seg_combine(start, tot); totals[0] = e.nl; }   // last tile: newline total
+        if (lane == 0) {
+            s_start = start;
+            if ((size_t)(tile + 1) * TK2_TILE >= n) { const Seg e = seg_combine(start, tot); totals[0] = e.nl; }   // last tile: newline total
+        }
     }
     __syncthreads();
     const Seg stt = seg_combine(seg_combine(s_start, pre), ex);   // state just before this lane's first byte

@@ -11,7 +11,7 @@
 
 namespace {
 
-constexpr int RS_T = 256;             // threads per CTA
+constexpr int RS_T = 512;             // threads per CTA
 constexpr int RS_IPT = 16;            // items per thread
 constexpr int RS_TILE = RS_T * RS_IPT;
 constexpr int RS_WARPS = RS_T / 32;
@@ -47,14 +47,16 @@ __global__ void __launch_bounds__(RS_T) rs_onesweep_k(const uint32_t *__restrict
     for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_T) (&cnt[0][0])[i] = 0;
     // exclusive scan of the 256-bin global histogram (digit base offsets)
     {
-        uint32_t h = ghist[threadIdx.x], inc = h;
+        uint32_t h = threadIdx.x < 256 ? ghist[threadIdx.x] : 0, inc = h;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (unsigned)d) inc += t; }
-        if (lane == 31) wtot[w] = inc;
+        if (lane == 31 && w < 8) wtot[w] = inc;
         __syncthreads();
-        uint32_t off = 0;
-        for (unsigned i = 0; i < w; i++) off += wtot[i];
-        gbase[threadIdx.x] = off + inc - h;
+        if (threadIdx.x < 256) {
+            uint32_t off = 0;
+            for (unsigned i = 0; i < w; i++) off += wtot[i];
+            gbase[threadIdx.x] = off + inc - h;
+        }
     }
     __syncthreads();
     const unsigned tile = s_tile;
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(RS_T) rs_onesweep_k(const uint32_t *__restrict
         __syncwarp();
     }
     __syncthreads();
-    {
+    if (threadIdx.x < 256) {
         // thread d owns digit d: tile count, publish, look back, per-warp bases
         const uint32_t d = threadIdx.x;
         uint32_t tc = 0;
