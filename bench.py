@@ -156,11 +156,13 @@ def host_threads() -> int:
 # ----------------------------------------------------------------------------------------------------------------------
 # roofline bookkeeping: algorithmic bytes per launch of each hot kernel (DESIGN.md section "kernels")
 # ----------------------------------------------------------------------------------------------------------------------
-def algorithmic_bytes(kernel: str, n_rec: int, text_bytes: int, n_tmpl: int):
+def algorithmic_bytes(kernel: str, n_rec: int, text_bytes: int, n_tmpl: int, seq_end_avg: float = 0.0):
     """bytes one launch must move at minimum.  n for the sort kernels is not fixed (records when pairing,
     templates when collapsing): use the larger so the fraction is a lower bound."""
     return {
-        "tk_scan_k": text_bytes + 4 * n_rec + 44 * n_rec,   # read the text ONCE; write a newline offset and 11 tab offsets per line
+        "nl_scan_k": text_bytes + 4 * n_rec,             # read the text ONCE; write one newline offset per line
+        "sam_lines_k": int(seq_end_avg * n_rec) + 8 * n_rec + 49 * n_rec,   # read each line up to the end of SEQ (QUAL/tags are
+                                                         # never read in bisulfite mode) + 2 newline offsets; write 12 words + status
         "tk_records_k": 48 * n_rec + 52 * n_rec + 32 * n_rec,  # read offsets (+ QNAME/FLAG/POS bytes), write 13 descriptor words
         "rs_onesweep_k": 16 * n_rec,                     # (key,val) read + written
         "rs_global_hist_k": 4 * n_rec,
@@ -402,7 +404,9 @@ def main():
         else:
             peak, how = 6650.0, "fallback (B200_PROFILING.md)"
         dom, (dc, dms) = top[0]
-        ab = algorithmic_bytes(dom, n_rec, text_bytes, last["stats"][7])
+        head = sam[:2_000_000].splitlines()[:5000]
+        seq_end_avg = float(np.mean([len(b"\t".join(l.split(b"\t")[:10])) + 1 for l in head]))
+        ab = algorithmic_bytes(dom, n_rec, text_bytes, last["stats"][7], seq_end_avg)
         traffic = None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.isfile(tp):

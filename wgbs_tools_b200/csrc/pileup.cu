@@ -216,35 +216,33 @@ extern "C" int wgbs_pileup_sam(wgbs_ctx *ctx, const wgbs_index *ix, const char *
     const char *dtext = (const char *)dv;
     if (owned) T.v.push_back((void *)dtext);
 
-    // first_line (patter.cpp:324-350) needs the first non-empty line's FLAG and whether it carries an MM tag; the
-    // tokenizer always records tags so that auto-detection and the MM/ML path share one pass.
+    // first_line (patter.cpp:324-350): paired iff FLAG&1 of the first line; MM/ML mode iff requested or the first line
+    // carries an MM tag (the tokenizer checks that and only then records tag spans).
     ReadBatch rb;
-    RC_TRY(sam_tokenize(ctx, dtext, nbytes, true, T, &rb));
+    RC_TRY(sam_tokenize(ctx, dtext, nbytes, opts->nanopore ? 1 : -1, T, &rb));
     const uint32_t n = rb.n;
     unsigned long long *d_stats;
     RC_TRY(T.alloc(&d_stats, ST_N));
     CUDA_TRY(cudaMemsetAsync(d_stats, 0, ST_N * 8, ctx->stream));
 
     PileupOpts o;
-    o.min_cpg = opts->min_cpg; o.clip = opts->clip; o.nanopore = opts->nanopore; o.combine_mods = opts->combine_mods;
+    o.min_cpg = opts->min_cpg; o.clip = opts->clip; o.nanopore = (opts->nanopore || rb.mm_off != nullptr) ? 1 : 0; o.combine_mods = opts->combine_mods;
     o.np_thresh = opts->np_thresh; o.cpc_call = opts->cpc_call ? opts->cpc_call : 'C';
     o.paired = opts->paired;
     {
         // host-side peek at the head of the batch (tiny D2H): first non-blank record
         const uint32_t PEEK = 64;
         uint32_t m = n < PEEK ? n : PEEK;
-        std::vector<uint8_t> st(m); std::vector<int32_t> fl(m); std::vector<uint32_t> mml(m);
+        std::vector<uint8_t> st(m); std::vector<int32_t> fl(m);
         if (m) {
             CUDA_TRY(cudaMemcpyAsync(st.data(), rb.status, m, cudaMemcpyDeviceToHost, ctx->stream));
             CUDA_TRY(cudaMemcpyAsync(fl.data(), rb.flag, m * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CUDA_TRY(cudaMemcpyAsync(mml.data(), rb.mm_len, m * 4, cudaMemcpyDeviceToHost, ctx->stream));
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         }
         uint32_t f = 0; while (f < m && st[f] == REC_BLANK) f++;
         if (f < m) {
-            if (st[f] == REC_INVALID && o.paired < 0) return wgbs_set_err("Invalid first line (cannot determine paired/single end)");
+            if ((st[f] == REC_INVALID || st[f] == REC_BADINT) && o.paired < 0) return wgbs_set_err("Invalid first line (cannot determine paired/single end)");
             if (o.paired < 0) o.paired = ((uint16_t)fl[f]) & 1;
-            if (mml[f] > 0) o.nanopore = 1;
         } else if (o.paired < 0) o.paired = 0;
         if (o.paired && o.nanopore) return wgbs_set_err("Unrecognized bam format: paired end and nanopore");   // patter.cpp:341-343
     }

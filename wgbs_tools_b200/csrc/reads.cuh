@@ -48,7 +48,8 @@ struct wgbs_index {
 enum { ST_LINES = 0, ST_PAIRS, ST_EMPTY, ST_SHORT, ST_INVALID, ST_TEMPLATES, ST_N = 8 };
 
 // sam.cu
-int sam_tokenize(wgbs_ctx *ctx, const char *dtext, size_t nbytes, bool want_tags, Temps &T, ReadBatch *out);
+// want_tags: 1 record MM/ML tag spans, 0 do not, -1 decide from the first line (rb->mm_off != nullptr tells the outcome)
+int sam_tokenize(wgbs_ctx *ctx, const char *dtext, size_t nbytes, int want_tags, Temps &T, ReadBatch *out);
 // pair.cu: mate[r] = record id of the mate of r (0xffffffff: none)
 int build_mates(wgbs_ctx *ctx, const ReadBatch &rb, bool paired, Temps &T, uint32_t **mate_out,
                 unsigned long long *d_stats);

@@ -39,169 +39,124 @@ __device__ __forceinline__ int tag_kind(const char *__restrict__ t, uint32_t p, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Flat single-pass tokenizer.  The text is cut into 16 KiB tiles (one CTA each, handed out by an atomic ticket); a thread
-// owns 64 consecutive bytes.  tk_scan_k reads every byte ONCE:
-//   - byte-compare masks for '\t' and '\n' (aligned LDG.128, coalesced; masks are re-distributed inside each warp through
-//     shared memory so that a lane ends up with its 4 consecutive chunks),
-//   - a segmented scan gives every tab its ordinal inside its line and every newline its line number:
-//       state = (newlines so far, tabs since the last newline);  combine(l, r) = (l.nl + r.nl, r.nl ? r.tail : l.tail + r.tail)
-//     lanes -> warp shuffles, warps -> shared memory (one __syncthreads), tiles -> decoupled look-back over a status word
-//     per tile (flag | newline count | tab tail), so no second pass over the text is needed,
-//   - newline offsets go to nlpos[line], the first 11 tab offsets of a line to ftab[line*11 + ordinal]; a tab that starts
-//     a tag field (ordinal >= 10) is checked for MM / ML.
-// tk_records_k then turns one line per thread into a ReadBatch record (FLAG / POS, field spans, QNAME hash, tag spans).
-// The line count is not known before the pass: output arrays are sized for an average line of >= 96 bytes, and the pass
-// is repeated with the exact size in the (pathological) case that this was not enough.
+// Tokenizer = two kernels.
+//   nl_scan_k      newline positions in ONE pass over the text.  64 KiB tiles handed out by an atomic ticket; a warp owns
+//                  8 contiguous KiB (16 coalesced LDG.128 rounds, masks re-distributed through shared memory so that a
+//                  lane owns 16 consecutive chunks); tile offsets come from a warp-wide decoupled look-back.
+//   sam_lines_k    one thread per line: walks the line in aligned 16-byte chunks, finds the first ten tabs, parses FLAG and
+//                  POS, hashes the QNAME, and (MM/ML mode only) keeps walking to find the MM:Z: / ML:B:C tag fields.  In
+//                  bisulfite mode the walk stops at the end of SEQ: QUAL and the tags are never read.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int TK2_T = 256, TK2_CPT = 4, TK2_TILE = TK2_T * TK2_CPT * 16;   // 16 KiB
-static_assert(TK2_CPT == 4, "a lane reads its 4 masks as one uint4");
-constexpr unsigned long long TS_AGG = 1ull << 62, TS_INC = 2ull << 62;
+constexpr int NLS_T = 256, NLS_ROUNDS = 16, NLS_TILE = NLS_T * NLS_ROUNDS * 16;   // 64 KiB per CTA
+constexpr unsigned long long NS_AGG = 1ull << 62, NS_INC = 2ull << 62, NS_VAL = (1ull << 62) - 1;
 
-struct Seg { uint32_t nl, tail; };
-__device__ __forceinline__ Seg seg_combine(Seg l, Seg r) { Seg o; o.nl = l.nl + r.nl; o.tail = r.nl ? r.tail : l.tail + r.tail; return o; }
-__device__ __forceinline__ unsigned long long seg_pack(Seg s, unsigned long long flag) { return flag | ((unsigned long long)s.nl << 16) | (s.tail > 0xffffu ? 0xffffu : s.tail); }
-__device__ __forceinline__ Seg seg_unpack(unsigned long long w) { Seg s; s.nl = (uint32_t)(w >> 16); s.tail = (uint32_t)(w & 0xffffu); return s; }
-
-__global__ void __launch_bounds__(TK2_T) tk_scan_k(const char *__restrict__ text, size_t n, uint32_t line_cap, int want_tags,
+__global__ void __launch_bounds__(NLS_T) nl_scan_k(const char *__restrict__ text, size_t n, uint32_t cap,
                                                     unsigned long long *__restrict__ status, unsigned int *__restrict__ ticket,
-                                                    uint32_t *__restrict__ nlpos, uint32_t *__restrict__ ftab,
-                                                    uint32_t *__restrict__ mm_off, uint32_t *__restrict__ ml_off, uint32_t *__restrict__ totals) {
-    __shared__ uint32_t sm_mask[TK2_T * TK2_CPT];      // (nl << 16) | tab per chunk; warp w owns [w*128, w*128+128)
-    __shared__ Seg ws[TK2_T / 32];
-    __shared__ Seg s_start;
+                                                    uint32_t *__restrict__ nlpos, uint32_t *__restrict__ total) {
+    __shared__ uint16_t sm_mask[NLS_T * NLS_ROUNDS];   // one 16-bit newline mask per chunk; warp w owns [w*512, w*512+512)
+    __shared__ uint32_t ws[NLS_T / 32];
+    __shared__ uint64_t s_base;
     __shared__ unsigned s_tile;
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const unsigned tile = s_tile;
-    const size_t warp0 = (size_t)tile * TK2_TILE + (size_t)w * (32 * TK2_CPT * 16);   // first byte of this warp's 2 KiB
-    // ---- masks, coalesced: round c, lane l -> chunk c*32 + l of the warp
+    const size_t warp0 = (size_t)tile * NLS_TILE + (size_t)w * (32 * NLS_ROUNDS * 16);
 #pragma unroll
-    for (int c = 0; c < TK2_CPT; c++) {
+    for (int c = 0; c < NLS_ROUNDS; c++) {
         const size_t p = warp0 + (size_t)(c * 32 + lane) * 16;
-        uint32_t tm = 0, nm = 0;
+        uint32_t nm = 0;
         if (p < n) {
             const uint4 v = (p + 16 <= n) ? *reinterpret_cast<const uint4 *>(text + p) : load16_guard(text, p, n);
-            tm = eq_mask16(v, '\t'); nm = eq_mask16(v, '\n');
-            if (n - p < 16) { const uint32_t ok = (1u << (n - p)) - 1; tm &= ok; nm &= ok; }
+            nm = eq_mask16(v, '\n');
+            if (n - p < 16) nm &= (1u << (n - p)) - 1;
         }
-        sm_mask[w * 128 + c * 32 + lane] = (nm << 16) | tm;
+        sm_mask[w * 512 + c * 32 + lane] = (uint16_t)nm;
     }
     __syncwarp();
-    const uint4 q = *reinterpret_cast<const uint4 *>(&sm_mask[w * 128 + lane * TK2_CPT]);   // this lane's 4 consecutive chunks
-    const uint32_t mk[4] = {q.x, q.y, q.z, q.w};
-    // ---- lane state, warp scan, warp aggregate
-    Seg mine; mine.nl = 0; mine.tail = 0;
+    // this lane's 16 consecutive chunks (256 bytes): 32 contiguous bytes of shared memory
+    const uint4 q0 = *reinterpret_cast<const uint4 *>(&sm_mask[w * 512 + lane * 16]);
+    const uint4 q1 = *reinterpret_cast<const uint4 *>(&sm_mask[w * 512 + lane * 16 + 8]);
+    const uint32_t mk[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};   // two 16-bit masks per word
+    uint32_t cnt = 0;
 #pragma unroll
-    for (int c = 0; c < TK2_CPT; c++) {
-        const uint32_t nm = mk[c] >> 16, tm = mk[c] & 0xffffu;
-        if (nm) { mine.nl += __popc(nm); mine.tail = __popc(tm & ~((2u << (31 - __clz(nm))) - 1)); }   // tabs after the chunk's last newline
-        else mine.tail += __popc(tm);
-    }
-    Seg inc = mine;
+    for (int i = 0; i < 8; i++) cnt += __popc(mk[i]);
+    uint32_t inc = cnt;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        Seg o; o.nl = __shfl_up_sync(0xffffffffu, inc.nl, d); o.tail = __shfl_up_sync(0xffffffffu, inc.tail, d);
-        if (lane >= (unsigned)d) inc = seg_combine(o, inc);
-    }
-    Seg ex; ex.nl = __shfl_up_sync(0xffffffffu, inc.nl, 1); ex.tail = __shfl_up_sync(0xffffffffu, inc.tail, 1);
-    if (lane == 0) { ex.nl = 0; ex.tail = 0; }
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (unsigned)d) inc += t; }
     if (lane == 31) ws[w] = inc;
     __syncthreads();
-    Seg pre; pre.nl = 0; pre.tail = 0;
-    Seg tot; tot.nl = 0; tot.tail = 0;
+    uint32_t wpre = 0, tot = 0;
 #pragma unroll
-    for (int i = 0; i < TK2_T / 32; i++) { if (i < (int)w) pre = seg_combine(pre, ws[i]); tot = seg_combine(tot, ws[i]); }
-    // ---- tile start state: decoupled look-back by warp 0, 32 predecessor tiles per probe.  Lane j holds tile-1-j; an
-    // ordered warp scan combines them (earlier tiles on the left) up to the nearest tile that already published an
-    // inclusive state.
+    for (int i = 0; i < NLS_T / 32; i++) { const uint32_t x = ws[i]; if (i < (int)w) wpre += x; tot += x; }
     if (w == 0) {
         volatile unsigned long long *st = status;
-        Seg start; start.nl = 0; start.tail = 0;
-        if (tile == 0) { if (lane == 0) st[0] = seg_pack(tot, TS_INC); }
+        uint64_t base = 0;
+        if (tile == 0) { if (lane == 0) st[0] = NS_INC | tot; }
         else {
-            if (lane == 0) st[tile] = seg_pack(tot, TS_AGG);
-            Seg acc; acc.nl = 0; acc.tail = 0;           // combined state of the tiles already folded in (nearest ones)
+            if (lane == 0) st[tile] = NS_AGG | tot;
             long long top = (long long)tile - 1;
             while (true) {
                 const long long j = top - lane;
-                unsigned long long x = TS_INC;           // before tile 0: the empty inclusive state
+                unsigned long long x = NS_INC;
                 if (j >= 0) x = st[j];
                 while (__any_sync(0xffffffffu, (x >> 62) == 0)) { if ((x >> 62) == 0) x = st[j]; }
                 const unsigned incm = __ballot_sync(0xffffffffu, (x >> 62) == 2);
-                Seg v = seg_unpack(x & ~(3ull << 62));
-                // inclusive ordered scan: lane j <- S(top-j) o ... o S(top)
+                uint64_t val = x & NS_VAL;
+                if (incm) { const int L = __ffs(incm) - 1; if ((int)lane > L) val = 0; }
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    Seg o; o.nl = __shfl_up_sync(0xffffffffu, v.nl, d); o.tail = __shfl_up_sync(0xffffffffu, v.tail, d);
-                    if (lane >= (unsigned)d) v = seg_combine(v, o);
-                }
-                const int L = incm ? __ffs(incm) - 1 : 31;
-                Seg win; win.nl = __shfl_sync(0xffffffffu, v.nl, L); win.tail = __shfl_sync(0xffffffffu, v.tail, L);
-                acc = seg_combine(win, acc);
+                for (int d = 16; d >= 1; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+                base += val;
                 if (incm) break;
                 top -= 32;
             }
-            start = acc;
-            if (lane == 0) st[tile] = seg_pack(seg_combine(start, tot), TS_INC);
+            if (lane == 0) st[tile] = NS_INC | ((base + tot) & NS_VAL);
         }
-        if (lane == 0) {
-            s_start = start;
-            if ((size_t)(tile + 1) * TK2_TILE >= n) { const Seg e = seg_combine(start, tot); totals[0] = e.nl; }   // last tile: newline total
-        }
+        if (lane == 0) { s_base = base; if ((size_t)(tile + 1) * NLS_TILE >= n) *total = (uint32_t)(base + tot); }
     }
     __syncthreads();
-    const Seg stt = seg_combine(seg_combine(s_start, pre), ex);   // state just before this lane's first byte
-    uint32_t line = stt.nl, ord = stt.tail;
-    const size_t p0 = warp0 + (size_t)lane * (TK2_CPT * 16);
+    uint32_t o = (uint32_t)s_base + wpre + inc - cnt;
+    const size_t p0 = warp0 + (size_t)lane * 256;
 #pragma unroll
-    for (int c = 0; c < TK2_CPT; c++) {
-        const uint32_t nm = mk[c] >> 16;
-        uint32_t m = (mk[c] & 0xffffu) | nm;
-        while (m) {
-            const int b = __ffs(m) - 1; m &= m - 1;
-            const uint32_t x = (uint32_t)(p0 + (size_t)c * 16 + b);
-            if ((nm >> b) & 1u) {
-                if (line < line_cap) {
-                    nlpos[line] = x;
-                    for (uint32_t k = ord; k < NTAB; k++) ftab[(size_t)line * NTAB + k] = 0xffffffffu;   // fewer than 11 tabs: mark the rest absent
-                }
-                line++; ord = 0;
-            }
-            else {
-                if (line < line_cap) {
-                    if (ord < NTAB) ftab[(size_t)line * NTAB + ord] = x;
-                    if (want_tags && ord >= 10) {                      // field index ord+1 >= 11: a tag
-                        const int k = tag_kind(text, x + 1, (uint32_t)n);
-                        if (k == 1) atomicMax(&mm_off[line], x + 6); else if (k == 2) atomicMax(&ml_off[line], x + 7);   // last occurrence wins
-                    }
-                }
-                ord++;
-            }
-        }
+    for (int i = 0; i < 8; i++) {
+        uint32_t m = mk[i];
+        while (m) { const int b = __ffs(m) - 1; m &= m - 1; if (o < cap) nlpos[o] = (uint32_t)(p0 + (size_t)i * 32 + b); o++; }
     }
-    // a last line without a trailing newline is closed by the lane that owns the final byte
-    if (n && p0 <= n - 1 && n - 1 < p0 + TK2_CPT * 16 && text[n - 1] != '\n' && line < line_cap)
-        for (uint32_t k = ord; k < NTAB; k++) ftab[(size_t)line * NTAB + k] = 0xffffffffu;
 }
 
-// per-(byte, position) mixing summed over the name
+// per-(byte, position) mixing summed over the name: independent of alignment
 __device__ __forceinline__ uint64_t name_byte_mix(uint32_t byte, uint32_t pos) {
     uint64_t x = ((uint64_t)(byte | (pos << 8)) + 1) * 0x9e3779b97f4a7c15ULL;
     x ^= x >> 29; x *= 0xbf58476d1ce4e5b9ULL; x ^= x >> 32;
     return x;
 }
 
-__global__ void __launch_bounds__(256) tk_records_k(const char *__restrict__ text, uint32_t n, const uint32_t *__restrict__ nlpos, uint32_t n_nl,
-                                                     uint32_t n_lines, const uint32_t *__restrict__ ftab, int want_tags, ReadBatch rb) {
+__global__ void __launch_bounds__(128) sam_lines_k(const char *__restrict__ text, uint32_t n, const uint32_t *__restrict__ nlpos, uint32_t n_nl,
+                                                    uint32_t n_lines, int want_tags, ReadBatch rb) {
     const uint32_t line = blockIdx.x * blockDim.x + threadIdx.x;
     if (line >= n_lines) return;
     const uint32_t s = line == 0 ? 0 : nlpos[line - 1] + 1;
     const uint32_t e = line < n_nl ? nlpos[line] : n;
-    uint32_t tb[NTAB];
-#pragma unroll
-    for (int i = 0; i < NTAB; i++) tb[i] = ftab[(size_t)line * NTAB + i];
-    const uint32_t qend = tb[0] != 0xffffffffu ? tb[0] : e;
+    uint32_t tb[10];
+    uint32_t ntab = 0, mm_off = 0, ml_off = 0;
+    for (uint32_t base = s & ~15u; base < e; base += 16) {
+        const uint4 v = (base + 16 <= n) ? *reinterpret_cast<const uint4 *>(text + base) : load16_guard(text, base, n);
+        uint32_t m = eq_mask16(v, '\t');
+        if (base < s) m &= 0xffffu << (s - base);
+        if (e - base < 16) m &= (1u << (e - base)) - 1;
+        while (m) {
+            const int b = __ffs(m) - 1; m &= m - 1;
+            const uint32_t x = base + b;
+            if (ntab < 10) tb[ntab] = x;
+            else if (want_tags) {                                   // ntab >= 10: field index ntab+1 >= 11 starts at x+1
+                const int k = tag_kind(text, x + 1, e);
+                if (k == 1) mm_off = x + 6; else if (k == 2) ml_off = x + 7;                 // last occurrence wins
+            }
+            ntab++;
+        }
+        if (ntab >= 10 && !want_tags) break;                        // bisulfite mode: nothing beyond SEQ is needed
+    }
+    const uint32_t qend = ntab > 0 ? tb[0] : e;
     uint64_t h = 0;
     for (uint32_t p = s; p < qend; p++) h += name_byte_mix((uint8_t)text[p], p - s);
     h = fmix64(h ^ (uint64_t)(qend - s));
@@ -209,8 +164,11 @@ __global__ void __launch_bounds__(256) tk_records_k(const char *__restrict__ tex
     int32_t flag = 0, pos = 0;
     uint32_t cig_off = s, cig_len = 0, seq_off = s, seq_len = 0;
     if (e == s) { st = REC_BLANK; h = fmix64(0x5851f42d4c957f2dULL ^ (uint64_t)line); }   // blank lines: unique keys, never paired
-    else if (tb[9] == 0xffffffffu || (tb[10] == 0xffffffffu && tb[9] == e - 1)) st = REC_INVALID;   // line2tokens would give < 11 tokens
-    else {
+    else if (ntab < 10 || tb[9] == e - 1) {
+        // line2tokens yields < 11 tokens: fewer than 10 tabs, or exactly 10 with nothing after the last one.  (With > 10 tabs
+        // tb[9] == e-1 is impossible.)
+        st = REC_INVALID;
+    } else {
         if (!parse_i32(text, tb[0] + 1, tb[1], &flag) || !parse_i32(text, tb[2] + 1, tb[3], &pos)) st = REC_BADINT;
         cig_off = tb[4] + 1; cig_len = tb[5] - tb[4] - 1;
         seq_off = tb[8] + 1; seq_len = tb[9] - tb[8] - 1;
@@ -221,47 +179,57 @@ __global__ void __launch_bounds__(256) tk_records_k(const char *__restrict__ tex
     rb.hash_lo[line] = (uint32_t)h; rb.hash_hi[line] = (uint32_t)(h >> 32);
     rb.status[line] = st;
     if (want_tags) {
-        // mm_off / ml_off hold the payload start (0: no tag); the payload runs to the next tab or the line end
-        const uint32_t mo = rb.mm_off[line], lo = rb.ml_off[line];
-        uint32_t z = mo; if (mo) while (z < e && text[z] != '\t') z++;
-        rb.mm_len[line] = mo ? z - mo : 0;
-        z = lo; if (lo) while (z < e && text[z] != '\t') z++;
-        rb.ml_len[line] = lo ? z - lo : 0;
+        uint32_t z = mm_off; if (mm_off) while (z < e && text[z] != '\t') z++;
+        rb.mm_off[line] = mm_off; rb.mm_len[line] = mm_off ? z - mm_off : 0;
+        z = ml_off; if (ml_off) while (z < e && text[z] != '\t') z++;
+        rb.ml_off[line] = ml_off; rb.ml_len[line] = ml_off ? z - ml_off : 0;
     }
+}
+
+// does the FIRST non-empty line carry an MM tag?  (patter.cpp:337-338 switches to the MM/ML path on it.)  One thread.
+__global__ void first_line_mm_k(const char *__restrict__ text, uint32_t n, uint32_t *__restrict__ out) {
+    uint32_t p = 0;
+    while (p < n && text[p] == '\n') p++;
+    uint32_t ntab = 0, has = 0;
+    for (; p < n && text[p] != '\n'; p++) {
+        if (text[p] == '\t') {
+            ntab++;
+            if (ntab >= 11) {
+                uint32_t e = p + 1; while (e < n && text[e] != '\n' && text[e] != '\t') e++;
+                if (tag_kind(text, p + 1, e) == 1 && e - (p + 1) > 5) has = 1;               // non-empty MM payload
+            }
+        }
+    }
+    *out = has;
 }
 
 }  // namespace
 
-int sam_tokenize(wgbs_ctx *ctx, const char *dtext, size_t nbytes, bool want_tags, Temps &T, ReadBatch *out) {
+int sam_tokenize(wgbs_ctx *ctx, const char *dtext, size_t nbytes, int want_tags /* 1 yes, 0 no, -1 decide from the first line */, Temps &T,
+                 ReadBatch *out) {
     if (nbytes >= 0xfffffff0ull) return wgbs_set_err("SAM text must be < 4 GiB per call (got %zu); split on line boundaries", nbytes);
-    const uint32_t ntiles = (uint32_t)((nbytes + TK2_TILE - 1) / TK2_TILE);
+    const uint32_t ntiles = (uint32_t)((nbytes + NLS_TILE - 1) / NLS_TILE);
     ReadBatch rb;
     rb.text = dtext; rb.nbytes = (uint32_t)nbytes;
-    uint32_t *nlpos = nullptr, *ftab = nullptr, *totals = ctx->d_flags + 8;
+    uint32_t *nlpos = nullptr, *totals = ctx->d_flags + 8;
     unsigned long long *status = nullptr;
     if (ntiles) RC_TRY(T.alloc(&status, (size_t)ntiles + 1));
-    uint32_t cap = (uint32_t)(nbytes / 96 + 1024);            // optimistic: average line >= 96 bytes (a 50 bp SAM record is ~130)
-    uint32_t n_nl = 0; char last = '\n';
-    std::vector<void *> sized;                                 // arrays sized by `cap`, re-made if the guess was too small
+    uint32_t cap = (uint32_t)(nbytes / 64 + 1024);            // optimistic: average line >= 64 bytes (a 50 bp SAM record is ~130)
+    uint32_t n_nl = 0, first_mm = 0; char last = '\n';
     for (int attempt = 0; attempt < 2 && ntiles; attempt++) {
-        for (void *q : sized) { T.keep(q); dfree(ctx, q); }
-        sized.clear();
-        RC_TRY(T.alloc(&nlpos, cap)); sized.push_back(nlpos);
-        RC_TRY(T.alloc(&ftab, (size_t)cap * NTAB)); sized.push_back(ftab);
-        if (want_tags) {
-            RC_TRY(T.alloc(&rb.mm_off, cap)); sized.push_back(rb.mm_off); RC_TRY(T.alloc(&rb.ml_off, cap)); sized.push_back(rb.ml_off);
-            CUDA_TRY(cudaMemsetAsync(rb.mm_off, 0, (size_t)cap * 4, ctx->stream));
-            CUDA_TRY(cudaMemsetAsync(rb.ml_off, 0, (size_t)cap * 4, ctx->stream));
-        }
+        if (nlpos) { T.keep(nlpos); dfree(ctx, nlpos); }
+        RC_TRY(T.alloc(&nlpos, cap));
         CUDA_TRY(cudaMemsetAsync(status, 0, ((size_t)ntiles + 1) * 8, ctx->stream));
-        LAUNCH(ctx, tk_scan_k, ntiles, TK2_T, 0, dtext, nbytes, cap, want_tags ? 1 : 0, status, (unsigned int *)(status + ntiles), nlpos, ftab,
-               rb.mm_off, rb.ml_off, totals);
+        LAUNCH(ctx, nl_scan_k, ntiles, NLS_T, 0, dtext, nbytes, cap, status, (unsigned int *)(status + ntiles), nlpos, totals);
+        if (attempt == 0 && want_tags < 0) LAUNCH(ctx, first_line_mm_k, 1, 1, 0, dtext, (uint32_t)nbytes, totals + 1);
         CUDA_TRY(cudaMemcpyAsync(&n_nl, totals, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (attempt == 0 && want_tags < 0) CUDA_TRY(cudaMemcpyAsync(&first_mm, totals + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(&last, dtext + nbytes - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        if (n_nl + 1 <= cap) break;
-        cap = n_nl + 1;                                       // many very short lines: repeat with the exact size
+        if (n_nl <= cap) break;
+        cap = n_nl;                                            // many very short lines: repeat with the exact size
     }
+    const bool tags = want_tags > 0 || (want_tags < 0 && first_mm);
     const uint32_t n_lines = n_nl + ((nbytes && last != '\n') ? 1 : 0);
     rb.n = n_lines;
     RC_TRY(T.alloc(&rb.line_off, n_lines)); RC_TRY(T.alloc(&rb.line_len, n_lines)); RC_TRY(T.alloc(&rb.qn_len, n_lines));
@@ -270,9 +238,12 @@ int sam_tokenize(wgbs_ctx *ctx, const char *dtext, size_t nbytes, bool want_tags
     RC_TRY(T.alloc(&rb.seq_off, n_lines)); RC_TRY(T.alloc(&rb.seq_len, n_lines));
     RC_TRY(T.alloc(&rb.hash_lo, n_lines)); RC_TRY(T.alloc(&rb.hash_hi, n_lines));
     RC_TRY(T.alloc(&rb.status, n_lines));
-    if (want_tags) { RC_TRY(T.alloc(&rb.mm_len, n_lines)); RC_TRY(T.alloc(&rb.ml_len, n_lines)); if (!ntiles) { RC_TRY(T.alloc(&rb.mm_off, 1)); RC_TRY(T.alloc(&rb.ml_off, 1)); } }
+    if (tags) {
+        RC_TRY(T.alloc(&rb.mm_off, n_lines)); RC_TRY(T.alloc(&rb.mm_len, n_lines));
+        RC_TRY(T.alloc(&rb.ml_off, n_lines)); RC_TRY(T.alloc(&rb.ml_len, n_lines));
+    }
     if (n_lines) {
-        LAUNCH(ctx, tk_records_k, grid_for(n_lines, 256), 256, 0, dtext, (uint32_t)nbytes, nlpos, n_nl, n_lines, ftab, want_tags ? 1 : 0, rb);
+        LAUNCH(ctx, sam_lines_k, grid_for(n_lines, 128), 128, 0, dtext, (uint32_t)nbytes, nlpos, n_nl, n_lines, tags ? 1 : 0, rb);
         LAUNCH_CHECK();
     }
     *out = rb;
