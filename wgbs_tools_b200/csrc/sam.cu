@@ -186,23 +186,6 @@ __global__ void __launch_bounds__(128) sam_lines_k(const char *__restrict__ text
     }
 }
 
-// does the FIRST non-empty line carry an MM tag?  (patter.cpp:337-338 switches to the MM/ML path on it.)  One thread.
-__global__ void first_line_mm_k(const char *__restrict__ text, uint32_t n, uint32_t *__restrict__ out) {
-    uint32_t p = 0;
-    while (p < n && text[p] == '\n') p++;
-    uint32_t ntab = 0, has = 0;
-    for (; p < n && text[p] != '\n'; p++) {
-        if (text[p] == '\t') {
-            ntab++;
-            if (ntab >= 11) {
-                uint32_t e = p + 1; while (e < n && text[e] != '\n' && text[e] != '\t') e++;
-                if (tag_kind(text, p + 1, e) == 1 && e - (p + 1) > 5) has = 1;               // non-empty MM payload
-            }
-        }
-    }
-    *out = has;
-}
-
 }  // namespace
 
 int sam_tokenize(wgbs_ctx *ctx, const char *dtext, size_t nbytes, int want_tags /* 1 yes, 0 no, -1 decide from the first line */, Temps &T,
@@ -216,18 +199,40 @@ int sam_tokenize(wgbs_ctx *ctx, const char *dtext, size_t nbytes, int want_tags 
     if (ntiles) RC_TRY(T.alloc(&status, (size_t)ntiles + 1));
     uint32_t cap = (uint32_t)(nbytes / 64 + 1024);            // optimistic: average line >= 64 bytes (a 50 bp SAM record is ~130)
     uint32_t n_nl = 0, first_mm = 0; char last = '\n';
+    // first_line (patter.cpp:337-338): does the first non-empty line carry an MM tag?  Decided on the host from the head of the
+    // text (one small D2H that rides on the synchronisation the line count needs anyway).
+    std::vector<char> head(want_tags < 0 ? std::min<size_t>(nbytes, 1u << 16) : 0);
     for (int attempt = 0; attempt < 2 && ntiles; attempt++) {
         if (nlpos) { T.keep(nlpos); dfree(ctx, nlpos); }
         RC_TRY(T.alloc(&nlpos, cap));
         CUDA_TRY(cudaMemsetAsync(status, 0, ((size_t)ntiles + 1) * 8, ctx->stream));
         LAUNCH(ctx, nl_scan_k, ntiles, NLS_T, 0, dtext, nbytes, cap, status, (unsigned int *)(status + ntiles), nlpos, totals);
-        if (attempt == 0 && want_tags < 0) LAUNCH(ctx, first_line_mm_k, 1, 1, 0, dtext, (uint32_t)nbytes, totals + 1);
         CUDA_TRY(cudaMemcpyAsync(&n_nl, totals, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        if (attempt == 0 && want_tags < 0) CUDA_TRY(cudaMemcpyAsync(&first_mm, totals + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (attempt == 0 && !head.empty()) CUDA_TRY(cudaMemcpyAsync(head.data(), dtext, head.size(), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(&last, dtext + nbytes - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         if (n_nl <= cap) break;
         cap = n_nl;                                            // many very short lines: repeat with the exact size
+    }
+    if (!head.empty()) {
+        size_t p = 0, hn = head.size();
+        while (p < hn && head[p] == '\n') p++;
+        size_t le = p; while (le < hn && head[le] != '\n') le++;
+        if (le == hn && hn < nbytes) {                              // first line longer than the peek (long ONT read): fetch all of it
+            std::vector<uint32_t> nl0(1);
+            if (n_nl > p) { CUDA_TRY(cudaMemcpyAsync(nl0.data(), nlpos + p, 4, cudaMemcpyDeviceToHost, ctx->stream)); CUDA_TRY(cudaStreamSynchronize(ctx->stream)); }
+            size_t want = n_nl > p ? (size_t)nl0[0] + 1 : nbytes;
+            head.resize(want);
+            CUDA_TRY(cudaMemcpyAsync(head.data(), dtext, want, cudaMemcpyDeviceToHost, ctx->stream)); CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            hn = head.size(); le = p; while (le < hn && head[le] != '\n') le++;
+        }
+        int field = 0; size_t fs = p;
+        for (size_t i = p; i <= le; i++) {
+            if (i == le || head[i] == '\t') {
+                if (field >= 11 && i - fs > 5 && head[fs] == 'M' && (head[fs + 1] == 'M' || head[fs + 1] == 'm') && head[fs + 2] == ':' && head[fs + 3] == 'Z' && head[fs + 4] == ':') first_mm = 1;
+                field++; fs = i + 1;
+            }
+        }
     }
     const bool tags = want_tags > 0 || (want_tags < 0 && first_mm);
     const uint32_t n_lines = n_nl + ((nbytes && last != '\n') ? 1 : 0);
