@@ -148,6 +148,24 @@ int wgbs_segment(wgbs_ctx *, const uint8_t *const *betas, int K, const uint32_t 
 /* numerics self-test: log2f(p[i]) and log2(1.0 - (double)p[i]) exactly as glibc 2.39 (FMA build) computes them */
 int wgbs_glibc_log2_probe(wgbs_ctx *, const float *p, size_t n, float *out_log2f, double *out_log2_1mp);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * BAM ingest (host side; replaces the `samtools view BAM chr -q Q -F X [-f Y]` stage of reference bam2pat.py:165 where
+ * samtools is not available).  BGZF blocks are inflated on `threads` host threads (0 = all cores); the file must be
+ * coordinate sorted.  wgbs_bam_view returns, malloc'ed (release with wgbs_host_free), the SAM text samtools view would
+ * print for reference `refid` (-1 = all records), optionally restricted to the 1-based closed interval beg..end
+ * (end <= 0: whole reference).  No GPU is needed for these calls.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct wgbs_bam wgbs_bam;
+int wgbs_bam_open(const char *path, int threads, wgbs_bam **out);
+void wgbs_bam_close(wgbs_bam *);
+int wgbs_bam_nref(const wgbs_bam *);
+const char *wgbs_bam_ref_name(const wgbs_bam *, int i);
+const char *wgbs_bam_header(const wgbs_bam *);
+uint64_t wgbs_bam_nrecords(const wgbs_bam *, int refid);
+int wgbs_bam_view(const wgbs_bam *, int refid, int min_mapq, int exclude_flags, int include_flags, int64_t beg, int64_t end,
+                  char **text, size_t *nbytes, uint64_t *nrecords);
+void wgbs_host_free(void *);
+
 #ifdef __cplusplus
 }
 #endif

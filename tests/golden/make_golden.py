@@ -73,6 +73,25 @@ def make_homog():
     print("homog_host.json ok")
 
 
+
+
+def make_tutorial_reads():
+    """tests/golden/tutorial_reads.sam.gz: ~1000 REAL bisulfite reads (hg19 chr3, SE, CIGAR ops M/I/D/S/H) decoded from the
+    reference's tutorial BAMs (tutorial/bams/{Pancreas_STL002,Lung_STL002}.small.bam) with wgbs_tools_b200.bamio -- the
+    only real reads available offline; used as a CIGAR-diversity fixture against a synthetic CpG dictionary."""
+    import gzip
+    from wgbs_tools_b200 import bamio
+    out = []
+    for name in ("Pancreas_STL002.small", "Lung_STL002.small"):
+        lines = bamio.BamFile(f"/root/reference/tutorial/bams/{name}.bam").view().splitlines(keepends=True)
+        odd = [l for l in lines if any(c in l.split(b"\t")[5] for c in b"IDSHN")]
+        plain = [l for l in lines if l not in odd][:300]
+        out += odd[:300] + plain
+    out.sort(key=lambda l: (l.split(b"\t")[2], int(l.split(b"\t")[3])))
+    gzip.open(os.path.join(OUT, "tutorial_reads.sam.gz"), "wb").write(b"".join(out))
+
+
 if __name__ == "__main__":
     make_segment()
     make_homog()
+    make_tutorial_reads()

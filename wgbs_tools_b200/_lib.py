@@ -56,6 +56,14 @@ def _load():
         "wgbs_sort_pairs_u32": (C.c_int, [vp, vp, vp, sz]),
         "wgbs_segment": (C.c_int, [vp, vp, C.c_int, vp, sz, vp, C.c_int, C.c_int, u32, C.c_float, vp, vp]),
         "wgbs_glibc_log2_probe": (C.c_int, [vp, vp, sz, vp, vp]),
+        "wgbs_bam_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(vp)]),
+        "wgbs_bam_close": (None, [vp]),
+        "wgbs_bam_nref": (C.c_int, [vp]),
+        "wgbs_bam_ref_name": (C.c_char_p, [vp, C.c_int]),
+        "wgbs_bam_header": (C.c_char_p, [vp]),
+        "wgbs_bam_nrecords": (u64, [vp, C.c_int]),
+        "wgbs_bam_view": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.POINTER(vp), C.POINTER(sz), C.POINTER(u64)]),
+        "wgbs_host_free": (None, [vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)

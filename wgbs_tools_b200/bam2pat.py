@@ -4,8 +4,8 @@ becomes ONE wgbs_pileup_sam + wgbs_collapse + wgbs_pats_format per chromosome sh
 threads and concatenated in chromosome order (bam2pat.py:398-422), and the beta file comes from the same device-resident
 templates (no second pass over the pat text).
 
-Input: SAM text per chromosome (what `samtools view BAM chr -q 10 -F 1796 [-f 3]` prints).  Reading BAM directly
-(BGZF inflate + record decode) is the next row; samtools is not available in this image."""
+Input: a coordinate-sorted .bam (decoded by the library's own BGZF/BAM reader, csrc/bam.cu -- samtools is not needed) or
+SAM text (.sam, or '-' for stdin: what `samtools view BAM` prints)."""
 from __future__ import annotations
 
 import argparse
@@ -69,7 +69,7 @@ def main(argv=None):
     from .genome import GenomeRef
     from .patio import bgzf_compress
     p = argparse.ArgumentParser(description="Run the WGBS pipeline to generate pat & beta files out of an input alignment file")
-    p.add_argument("bam", nargs="+", help="coordinate-sorted SAM text (.sam) of the reads, or '-' for stdin")
+    p.add_argument("bam", nargs="+", help="coordinate-sorted .bam, SAM text (.sam), or '-' for SAM on stdin")
     p.add_argument("-s", "--sites"); p.add_argument("-r", "--region"); p.add_argument("--genome")
     p.add_argument("--include_flags", type=int); p.add_argument("-F", "--exclude_flags", type=int, default=FLAGS_FILTER)
     p.add_argument("-q", "--mapq", type=int, default=MAPQ)
@@ -90,18 +90,30 @@ def main(argv=None):
             if os.path.exists(pat_path) and not a.force:
                 print(f"File {pat_path} already exists. Skipping it. Use -f to overwrite", file=sys.stderr)
                 continue
-            sam = sys.stdin.buffer.read() if path == "-" else open(path, "rb").read()
             ex = FLAGS_FILTER_NANOPORE if a.nanopore else a.exclude_flags
-            by_chrom = split_sam_by_chrom(sam)
+            bam = None
+            if path.endswith(".bam"):
+                from .bamio import BamFile
+                bam = BamFile(path, a.threads)
+                by_chrom = {c: None for c in bam.refs if bam.nrecords(c)}
+            else:
+                sam = sys.stdin.buffer.read() if path == "-" else open(path, "rb").read()
+                by_chrom = split_sam_by_chrom(sam)
             mc = None if a.no_beta else ctx.alloc(ref.nr_sites * 8)
             if mc is not None:
                 ctx.pat2beta(ctx.pats_from_text(b""), 1, ref.nr_sites + 1, meth_cov=mc, zero_first=True)
             parts = []
             for chrom in [c for c in ref.chroms if c in by_chrom]:           # chromosome_order (init_genome.py:263-275)
-                s = by_chrom[chrom]
-                first_flag = int(s.split(b"\t", 2)[1])
-                inc = a.include_flags if a.include_flags is not None else (3 if first_flag & 1 else None)
-                s = filter_sam(s, 0 if a.nanopore else a.mapq, ex, inc)
+                if bam is not None:
+                    head = bam.view(chrom, beg=1, end=1 << 29)[:4096]         # is_pair_end: FLAG of the first read (bam2pat.py:262-267)
+                    first_flag = int(head.split(b"\t", 2)[1]) if head else 0
+                    inc = a.include_flags if a.include_flags is not None else (3 if first_flag & 1 else None)
+                    s = bam.view(chrom, 0 if a.nanopore else a.mapq, ex, inc or 0)
+                else:
+                    s = by_chrom[chrom]
+                    first_flag = int(s.split(b"\t", 2)[1])
+                    inc = a.include_flags if a.include_flags is not None else (3 if first_flag & 1 else None)
+                    s = filter_sam(s, 0 if a.nanopore else a.mapq, ex, inc)
                 if not s:
                     continue
                 txt, _ = proc_chr(ctx, ref, chrom, s, a, mc)

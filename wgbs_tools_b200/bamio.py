@@ -1,0 +1,115 @@
+"""BAM files: reader (native: csrc/bam.cu, BGZF inflate on host threads) and a small writer used to build test inputs.
+
+`BamFile.view(chrom, ...)` returns the SAM text `samtools view BAM chrom -q Q -F X [-f Y]` prints (reference
+bam2pat.py:165) -- the input of the pileup front end."""
+from __future__ import annotations
+
+import ctypes as C
+import re
+import struct
+
+import numpy as np
+
+from ._lib import check, lib
+from .patio import bgzf_compress
+
+
+class BamFile:
+    def __init__(self, path: str, threads: int = 0):
+        h = C.c_void_p()
+        check(lib.wgbs_bam_open(path.encode(), threads, C.byref(h)))
+        self.h = h.value
+        self.refs = [lib.wgbs_bam_ref_name(self.h, i).decode() for i in range(lib.wgbs_bam_nref(self.h))]
+
+    @property
+    def header(self) -> str:
+        return lib.wgbs_bam_header(self.h).decode(errors="replace")
+
+    def nrecords(self, chrom: str | None = None) -> int:
+        return int(lib.wgbs_bam_nrecords(self.h, -1 if chrom is None else self.refs.index(chrom)))
+
+    def view(self, chrom: str | None = None, mapq: int = 0, exclude_flags: int = 0, include_flags: int = 0, beg: int = 0, end: int = 0) -> bytes:
+        ptr = C.c_void_p(); n = C.c_size_t(); nr = C.c_uint64()
+        rid = -1 if chrom is None else self.refs.index(chrom)
+        check(lib.wgbs_bam_view(self.h, rid, mapq, exclude_flags, include_flags or 0, beg, end, C.byref(ptr), C.byref(n), C.byref(nr)))
+        try:
+            return C.string_at(ptr, n.value)
+        finally:
+            lib.wgbs_host_free(ptr)
+
+    def close(self):
+        if self.h:
+            lib.wgbs_bam_close(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# writer (test inputs): SAM text -> BAM bytes
+# ----------------------------------------------------------------------------------------------------------------------
+_SEQ = {c: i for i, c in enumerate("=ACMGRSVTWYHKDBN")}
+_CIG = {c: i for i, c in enumerate("MIDNSHP=X")}
+
+
+def _tag_bytes(tag: bytes) -> bytes:
+    name, ty, val = tag.split(b":", 2)
+    if ty == b"A":
+        return name + b"A" + val[:1]
+    if ty == b"i":
+        v = int(val)
+        for code, fmt, lo, hi in ((b"c", "<b", -128, 127), (b"C", "<B", 0, 255), (b"s", "<h", -32768, 32767), (b"S", "<H", 0, 65535), (b"i", "<i", -2**31, 2**31 - 1), (b"I", "<I", 0, 2**32 - 1)):
+            if lo <= v <= hi:
+                return name + code + struct.pack(fmt, v)
+    if ty == b"f":
+        return name + b"f" + struct.pack("<f", float(val))
+    if ty in (b"Z", b"H"):
+        return name + ty + val + b"\0"
+    if ty == b"B":
+        sub = val[:1]; items = [x for x in val[2:].split(b",") if x] if len(val) > 1 else []
+        fmt = {b"c": "b", b"C": "B", b"s": "h", b"S": "H", b"i": "i", b"I": "I", b"f": "f"}[sub]
+        conv = float if sub == b"f" else int
+        return name + b"B" + sub + struct.pack("<I", len(items)) + struct.pack("<%d%s" % (len(items), fmt), *[conv(x) for x in items])
+    raise ValueError(tag)
+
+
+def sam_to_bam(sam: bytes, refs: list[tuple[str, int]], header_text: str | None = None) -> bytes:
+    """SAM records (no header lines needed) + reference list -> BGZF-compressed BAM bytes"""
+    if header_text is None:
+        header_text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l in refs)
+    rid = {n: i for i, (n, _) in enumerate(refs)}
+    out = [b"BAM\1", struct.pack("<i", len(header_text)), header_text.encode(), struct.pack("<i", len(refs))]
+    for n, l in refs:
+        out += [struct.pack("<i", len(n) + 1), n.encode() + b"\0", struct.pack("<i", l)]
+    for line in sam.splitlines():
+        if not line or line.startswith(b"@"):
+            continue
+        t = line.split(b"\t")
+        name, flag, rname, pos, mapq, cigar, rnext, pnext, tlen, seq, qual = t[:11]
+        ops = re.findall(rb"(\d+)([MIDNSHP=X])", cigar) if cigar != b"*" else []
+        cig = b"".join(struct.pack("<I", int(n) << 4 | _CIG[o.decode()]) for n, o in ops)
+        l_seq = 0 if seq == b"*" else len(seq)
+        sq = bytearray((l_seq + 1) // 2)
+        for i in range(l_seq):
+            sq[i >> 1] |= _SEQ[chr(seq[i])] << (4 if i % 2 == 0 else 0)
+        ql = (b"\xff" * l_seq) if qual == b"*" else bytes(c - 33 for c in qual)
+        r = rid.get(rname.decode(), -1)
+        nr = r if rnext == b"=" else rid.get(rnext.decode(), -1)
+        end = int(pos) - 1 + sum(int(n) for n, o in ops if o in b"MDN=X") if ops else int(pos)
+        bin_ = _reg2bin(int(pos) - 1, max(end, int(pos)))
+        core = struct.pack("<iiBBHHHiiii", r, int(pos) - 1, len(name) + 1, int(mapq), bin_, len(ops), int(flag), l_seq, nr, int(pnext) - 1, int(tlen))
+        body = core + name + b"\0" + cig + bytes(sq) + ql + b"".join(_tag_bytes(x) for x in t[11:])
+        out.append(struct.pack("<i", len(body)) + body)
+    return bgzf_compress(b"".join(out))
+
+
+def _reg2bin(beg: int, end: int) -> int:
+    end -= 1
+    for shift, base in ((14, 4681), (17, 585), (20, 73), (23, 9), (26, 1)):
+        if beg >> shift == end >> shift:
+            return base + (beg >> shift)
+    return 0

@@ -44,7 +44,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=min(8, len(srcs) or 1)) as ex:
         list(ex.map(cc, zip(srcs, objs)))
     if force or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
-        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", *objs, "-o", LIB, "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
+        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", *objs, "-o", LIB, "-lcudart_static", "-lpthread", "-ldl", "-lrt", "-lz"]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}")

@@ -1,0 +1,240 @@
+// bam.cu -- host-side BAM ingest: BGZF inflate on a thread pool + BAM records -> the SAM text that
+// `samtools view BAM chr -q Q -F X [-f Y]` would print (reference src/python/bam2pat.py:165), which is what the pileup
+// front end (wgbs_pileup_sam) consumes.  No CUDA in this file; it lives in the library so that the drop-in covers the
+// reference's `samtools view |` stage where samtools is not installed.  Format: SAM/BAM specification v1, sections 4.1-4.2.
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+
+struct wgbs_bam {
+    std::vector<uint8_t> data;                 // uncompressed BAM stream
+    std::string header_text;
+    std::vector<std::string> ref_names;
+    std::vector<int32_t> ref_lens;
+    std::vector<uint64_t> rec_off;             // offset of every record's block_size field
+    std::vector<uint64_t> ref_first, ref_last; // record index range [first, last) per refID (coordinate-sorted input)
+    int threads = 1;
+};
+
+namespace {
+
+inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+inline int32_t rdi32(const uint8_t *p) { int32_t v; memcpy(&v, p, 4); return v; }
+inline uint16_t rd16(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
+
+struct Block { uint64_t coff; uint32_t csize, usize; uint64_t uoff; };
+
+int inflate_block(const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t usize) {
+    if (usize == 0) return 0;
+    z_stream zs; memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, -15) != Z_OK) return -1;
+    const uint16_t xlen = rd16(src + 10);
+    zs.next_in = const_cast<Bytef *>(src + 12 + xlen); zs.avail_in = csize - 12 - xlen - 8;
+    zs.next_out = dst; zs.avail_out = usize;
+    int rc = inflate(&zs, Z_FINISH);
+    inflateEnd(&zs);
+    return (rc == Z_STREAM_END && zs.avail_out == 0) ? 0 : -1;
+}
+
+void put_int(std::string &o, long long v) { char b[24]; int n = snprintf(b, sizeof b, "%lld", v); o.append(b, n); }
+
+// one record -> one SAM line (samtools view formatting)
+void format_record(const wgbs_bam *B, const uint8_t *r, std::string &o) {
+    const uint32_t bs = rd32(r);
+    const uint8_t *p = r + 4, *end = r + 4 + bs;
+    const int32_t refid = rdi32(p), pos = rdi32(p + 4);
+    const uint8_t l_name = p[8], mapq = p[9];
+    const uint16_t n_cig = rd16(p + 12), flag = rd16(p + 14);
+    const int32_t l_seq = rdi32(p + 16), nref = rdi32(p + 20), npos = rdi32(p + 24), tlen = rdi32(p + 28);
+    const char *name = (const char *)(p + 32);
+    const uint8_t *cig = p + 32 + l_name, *seq = cig + 4 * (size_t)n_cig, *qual = seq + (l_seq + 1) / 2, *tags = qual + l_seq;
+    o.append(name, l_name ? strnlen(name, l_name) : 0);          // l_read_name counts the trailing NUL
+    o.push_back('\t'); put_int(o, flag); o.push_back('\t');
+    if (refid >= 0 && refid < (int32_t)B->ref_names.size()) o += B->ref_names[refid]; else o.push_back('*');
+    o.push_back('\t'); put_int(o, (long long)pos + 1); o.push_back('\t'); put_int(o, mapq); o.push_back('\t');
+    if (n_cig == 0) o.push_back('*');
+    else for (uint16_t k = 0; k < n_cig; k++) { uint32_t c = rd32(cig + 4 * k); put_int(o, c >> 4); o.push_back("MIDNSHP=XB??????"[c & 15]); }
+    o.push_back('\t');
+    if (nref < 0) o.push_back('*'); else if (nref == refid) o.push_back('='); else if (nref < (int32_t)B->ref_names.size()) o += B->ref_names[nref]; else o.push_back('*');
+    o.push_back('\t'); put_int(o, (long long)npos + 1); o.push_back('\t'); put_int(o, tlen); o.push_back('\t');
+    if (l_seq == 0) o.push_back('*');
+    else for (int32_t k = 0; k < l_seq; k++) o.push_back("=ACMGRSVTWYHKDBN"[(seq[k >> 1] >> ((~k & 1) << 2)) & 15]);
+    o.push_back('\t');
+    if (l_seq == 0 || qual[0] == 0xff) o.push_back('*');
+    else for (int32_t k = 0; k < l_seq; k++) o.push_back((char)(qual[k] + 33));
+    // optional fields
+    const uint8_t *t = tags;
+    while (t + 3 <= end) {
+        o.push_back('\t'); o.push_back((char)t[0]); o.push_back((char)t[1]); o.push_back(':');
+        const char ty = (char)t[2]; t += 3;
+        char b[64];
+        switch (ty) {
+            case 'A': o += "A:"; o.push_back((char)*t); t += 1; break;
+            case 'c': o += "i:"; put_int(o, (int8_t)*t); t += 1; break;
+            case 'C': o += "i:"; put_int(o, *t); t += 1; break;
+            case 's': o += "i:"; put_int(o, (int16_t)rd16(t)); t += 2; break;
+            case 'S': o += "i:"; put_int(o, rd16(t)); t += 2; break;
+            case 'i': o += "i:"; put_int(o, rdi32(t)); t += 4; break;
+            case 'I': o += "i:"; put_int(o, rd32(t)); t += 4; break;
+            case 'f': { float f; memcpy(&f, t, 4); int n = snprintf(b, sizeof b, "%g", f); o += "f:"; o.append(b, n); t += 4; break; }
+            case 'Z': case 'H': { o.push_back(ty); o.push_back(':'); const char *z = (const char *)t; size_t l = strnlen(z, end - t); o.append(z, l); t += l + 1; break; }
+            case 'B': {
+                const char sub = (char)t[0]; const uint32_t cnt = rd32(t + 1); t += 5;
+                o += "B:"; o.push_back(sub);
+                for (uint32_t k = 0; k < cnt && t < end; k++) {
+                    o.push_back(',');
+                    switch (sub) {
+                        case 'c': put_int(o, (int8_t)*t); t += 1; break;
+                        case 'C': put_int(o, *t); t += 1; break;
+                        case 's': put_int(o, (int16_t)rd16(t)); t += 2; break;
+                        case 'S': put_int(o, rd16(t)); t += 2; break;
+                        case 'i': put_int(o, rdi32(t)); t += 4; break;
+                        case 'I': put_int(o, rd32(t)); t += 4; break;
+                        case 'f': { float f; memcpy(&f, t, 4); int n = snprintf(b, sizeof b, "%g", f); o.append(b, n); t += 4; break; }
+                        default: t = end; break;
+                    }
+                }
+                break;
+            }
+            default: t = end; break;   // unknown type: stop (malformed)
+        }
+    }
+    o.push_back('\n');
+}
+
+}  // namespace
+
+extern "C" int wgbs_bam_open(const char *path, int threads, wgbs_bam **out) {
+    if (!path || !out) return wgbs_set_err("wgbs_bam_open: null argument");
+    *out = nullptr;
+    FILE *f = fopen(path, "rb");
+    if (!f) return wgbs_set_err("wgbs_bam_open: cannot open %s", path);
+    fseek(f, 0, SEEK_END); const long fsz = ftell(f); fseek(f, 0, SEEK_SET);
+    std::vector<uint8_t> comp((size_t)fsz);
+    if (fsz && fread(comp.data(), 1, (size_t)fsz, f) != (size_t)fsz) { fclose(f); return wgbs_set_err("wgbs_bam_open: short read on %s", path); }
+    fclose(f);
+    // 1. BGZF block table
+    std::vector<Block> blocks; uint64_t off = 0, uoff = 0;
+    while (off + 28 <= (uint64_t)fsz) {
+        const uint8_t *h = comp.data() + off;
+        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return wgbs_set_err("%s: not a BGZF file (bad block header at %llu)", path, (unsigned long long)off);
+        const uint16_t xlen = rd16(h + 10);
+        uint32_t bsize = 0; bool found = false;
+        for (uint32_t x = 0; x + 4 <= xlen;) {
+            const uint8_t *sf = h + 12 + x; const uint16_t sl = rd16(sf + 2);
+            if (sf[0] == 'B' && sf[1] == 'C' && sl == 2) { bsize = rd16(sf + 4) + 1u; found = true; break; }
+            x += 4 + sl;
+        }
+        if (!found || off + bsize > (uint64_t)fsz) return wgbs_set_err("%s: corrupt BGZF block at %llu", path, (unsigned long long)off);
+        Block b; b.coff = off; b.csize = bsize; b.usize = rd32(h + bsize - 4); b.uoff = uoff;
+        blocks.push_back(b); off += bsize; uoff += b.usize;
+    }
+    wgbs_bam *B = new wgbs_bam();
+    B->threads = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    B->data.resize(uoff);
+    // 2. inflate in parallel
+    std::atomic<size_t> next(0); std::atomic<int> bad(0);
+    auto work = [&]() {
+        for (size_t i; (i = next.fetch_add(1)) < blocks.size();)
+            if (inflate_block(comp.data() + blocks[i].coff, blocks[i].csize, B->data.data() + blocks[i].uoff, blocks[i].usize)) bad.store(1);
+    };
+    {
+        std::vector<std::thread> th; int nt = std::min<int>(B->threads, (int)std::max<size_t>(1, blocks.size() / 4));
+        for (int t = 1; t < nt; t++) th.emplace_back(work);
+        work();
+        for (auto &t : th) t.join();
+    }
+    if (bad.load()) { delete B; return wgbs_set_err("%s: inflate failed (corrupt BGZF block)", path); }
+    // 3. header
+    const uint8_t *d = B->data.data(); const uint64_t n = B->data.size();
+    if (n < 12 || memcmp(d, "BAM\1", 4)) { delete B; return wgbs_set_err("%s: not a BAM file", path); }
+    const uint32_t l_text = rd32(d + 4);
+    if (8ull + l_text + 4 > n) { delete B; return wgbs_set_err("%s: truncated BAM header", path); }
+    B->header_text.assign((const char *)d + 8, strnlen((const char *)d + 8, l_text));
+    uint64_t p = 8ull + l_text; const uint32_t n_ref = rd32(d + p); p += 4;
+    for (uint32_t i = 0; i < n_ref; i++) {
+        if (p + 4 > n) { delete B; return wgbs_set_err("%s: truncated reference list", path); }
+        const uint32_t l = rd32(d + p); p += 4;
+        if (p + l + 4 > n) { delete B; return wgbs_set_err("%s: truncated reference list", path); }
+        B->ref_names.emplace_back((const char *)d + p, l ? l - 1 : 0); p += l;
+        B->ref_lens.push_back(rdi32(d + p)); p += 4;
+    }
+    // 4. record table (records are length-prefixed: a sequential walk) + per-reference ranges
+    B->ref_first.assign(n_ref + 1, 0); B->ref_last.assign(n_ref + 1, 0);
+    int32_t cur = -2; uint64_t idx = 0;
+    while (p + 4 <= n) {
+        const uint32_t bs = rd32(d + p);
+        if (bs < 32 || p + 4 + bs > n) { delete B; return wgbs_set_err("%s: corrupt BAM record at uncompressed offset %llu", path, (unsigned long long)p); }
+        const int32_t refid = rdi32(d + p + 4);
+        const uint32_t slot = (refid >= 0 && (uint32_t)refid < n_ref) ? (uint32_t)refid : n_ref;
+        if (refid != cur) {
+            if (B->ref_last[slot] != 0) { delete B; return wgbs_set_err("%s is not sorted by coordinate (reference %d appears in two separate runs)", path, refid); }
+            B->ref_first[slot] = idx; cur = refid;
+        }
+        B->ref_last[slot] = idx + 1;
+        B->rec_off.push_back(p); p += 4 + bs; idx++;
+    }
+    *out = B;
+    return 0;
+}
+
+extern "C" void wgbs_bam_close(wgbs_bam *B) { delete B; }
+extern "C" int wgbs_bam_nref(const wgbs_bam *B) { return B ? (int)B->ref_names.size() : -1; }
+extern "C" const char *wgbs_bam_ref_name(const wgbs_bam *B, int i) { return (B && i >= 0 && i < (int)B->ref_names.size()) ? B->ref_names[i].c_str() : nullptr; }
+extern "C" const char *wgbs_bam_header(const wgbs_bam *B) { return B ? B->header_text.c_str() : nullptr; }
+extern "C" uint64_t wgbs_bam_nrecords(const wgbs_bam *B, int refid) {
+    if (!B) return 0;
+    if (refid < 0) return B->rec_off.size();
+    return refid < (int)B->ref_names.size() ? B->ref_last[refid] - B->ref_first[refid] : 0;
+}
+
+// SAM text of the records of reference `refid` (-1: every record) that pass `-q min_mapq -F exclude -f include`
+// [and overlap the 1-based closed interval beg..end when end > 0].  *text is malloc'ed: release with wgbs_host_free.
+extern "C" int wgbs_bam_view(const wgbs_bam *B, int refid, int min_mapq, int exclude_flags, int include_flags, int64_t beg, int64_t end,
+                             char **text, size_t *nbytes, uint64_t *nrecords) {
+    if (!B || !text || !nbytes) return wgbs_set_err("wgbs_bam_view: null argument");
+    uint64_t r0 = 0, r1 = B->rec_off.size();
+    if (refid >= 0) { if (refid >= (int)B->ref_names.size()) return wgbs_set_err("wgbs_bam_view: no such reference"); r0 = B->ref_first[refid]; r1 = B->ref_last[refid]; }
+    const int nt = (int)std::max<uint64_t>(1, std::min<uint64_t>(B->threads, (r1 - r0) / 2048 + 1));
+    std::vector<std::string> parts(nt); std::vector<uint64_t> cnt(nt, 0);
+    auto work = [&](int t) {
+        const uint64_t a = r0 + (r1 - r0) * t / nt, b = r0 + (r1 - r0) * (t + 1) / nt;
+        std::string &o = parts[t]; o.reserve((b - a) * 360);
+        for (uint64_t i = a; i < b; i++) {
+            const uint8_t *r = B->data.data() + B->rec_off[i];
+            const uint16_t flag = rd16(r + 4 + 14); const uint8_t mapq = r[4 + 9];
+            if (mapq < min_mapq || (flag & exclude_flags) || (include_flags && (flag & include_flags) != include_flags)) continue;
+            if (end > 0) {
+                const int64_t pos = (int64_t)rdi32(r + 8) + 1; const uint16_t n_cig = rd16(r + 4 + 12); const uint8_t l_name = r[4 + 8];
+                int64_t span = 0; const uint8_t *cig = r + 36 + l_name;
+                for (uint16_t k = 0; k < n_cig; k++) { uint32_t c = rd32(cig + 4 * k); uint32_t op = c & 15; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += c >> 4; }
+                if (span < 1) span = 1;
+                if (pos > end || pos + span - 1 < beg) continue;
+            }
+            format_record(B, r, o); cnt[t]++;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &t : th) t.join();
+    size_t tot = 0; uint64_t nr = 0;
+    for (int t = 0; t < nt; t++) { tot += parts[t].size(); nr += cnt[t]; }
+    char *buf = (char *)malloc(tot ? tot : 1);
+    if (!buf) return wgbs_set_err("wgbs_bam_view: out of memory");
+    size_t o = 0;
+    for (int t = 0; t < nt; t++) { memcpy(buf + o, parts[t].data(), parts[t].size()); o += parts[t].size(); }
+    *text = buf; *nbytes = tot; if (nrecords) *nrecords = nr;
+    return 0;
+}
+
+extern "C" void wgbs_host_free(void *p) { free(p); }
