@@ -4,8 +4,8 @@
 //     sort -k2,2n -k3,3 | uniq -c | awk -v OFS='\t' '{print $2,$3,$4,$1}'          (python/bam2pat.py:99-106, C locale)
 // Order = (CpG index numeric, pattern bytes with a shorter prefix first).  With symbol codes '.'<'C'<'H'<'T' = 0..3
 // packed MSB-first and zero padding, that order is the numeric order of (idx, word0, word1, ...): patterns never end
-// in '.', so zero padding is unambiguous.  Two stable 32-bit radix sorts (word0, then idx; uniform digits skipped) order
-// everything except ties between patterns longer than 16 symbols, which fix_ties_k settles run by run.
+// in '.', so zero padding is unambiguous.  One stable 32-bit radix sort on (idx - idx_min, first few symbols) orders
+// everything except ties between longer patterns, which fix_ties_k settles run by run.
 #include "reads.cuh"
 #include "sort.cuh"
 
@@ -17,44 +17,46 @@ __global__ void __launch_bounds__(256) gather_word_k(PatsView P, const uint32_t 
     uint32_t r = perm[i];
     keys[i] = widx < ((P.len[r] + 15) >> 4) ? P.pool[P.off[r] + widx] : 0u;
 }
-__global__ void __launch_bounds__(256) gather_idx_k(PatsView P, const uint32_t *__restrict__ perm, uint32_t *__restrict__ keys) {
+__global__ void __launch_bounds__(256) idx_range_k(const uint32_t *__restrict__ idx, size_t n, uint32_t *__restrict__ mnmx) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < P.n) keys[i] = P.idx[perm[i]];
+    // idx has int32 semantics (`sort -k2,2n`): x ^ 0x80000000 maps it order-preservingly onto uint32
+    uint32_t lo = i < n ? (idx[i] ^ 0x80000000u) : 0xffffffffu, hi = i < n ? (idx[i] ^ 0x80000000u) : 0u;
+    lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&mnmx[0], lo); atomicMax(&mnmx[1], hi); }
 }
-// Records are first radix-sorted on (idx, pattern word 0) only.  Whatever order remains to be decided lies inside runs
-// of equal (idx, word0) that contain a pattern longer than 16 symbols: one thread orders such a run in place by the
-// remaining words (zero padded = shorter prefix first).  Runs are short (templates starting at one CpG with the same
-// first 16 calls), so an insertion sort is enough; it is stable, like `sort`'s last-resort comparison needs.
-__device__ __forceinline__ int tail_cmp(const PatsView &P, uint32_t a, uint32_t b) {
+// ONE 32-bit sort key per record: (idx - idx_min) in the high bits, the first `nsym` pattern symbols below it
+__global__ void __launch_bounds__(256) make_key_k(PatsView P, uint32_t idx_min, uint32_t nsym, uint32_t *__restrict__ keys, uint32_t *__restrict__ perm) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    const uint32_t w0 = P.len[i] ? P.pool[P.off[i]] : 0u;
+    const uint32_t rel = (P.idx[i] ^ 0x80000000u) - idx_min;       // idx_min is in the same biased representation
+    keys[i] = nsym ? ((rel << (2 * nsym)) | (w0 >> (32 - 2 * nsym))) : rel;
+    perm[i] = (uint32_t)i;
+}
+// Records are radix-sorted on ONE 32-bit key = (idx - idx_min, first nsym symbols).  Whatever order remains to be decided
+// lies inside runs of equal key that contain a pattern longer than nsym symbols: one thread orders such a run in place by
+// the full patterns (zero padded = shorter prefix first).  Runs are short (templates starting at one CpG with the same first
+// calls), so an insertion sort is enough; it is stable, like `sort`'s last-resort comparison needs.
+__device__ __forceinline__ int pat_cmp(const PatsView &P, uint32_t a, uint32_t b) {
     const uint32_t na = (P.len[a] + 15) >> 4, nb = (P.len[b] + 15) >> 4, m = max(na, nb);
     const uint32_t *x = P.pool + P.off[a], *y = P.pool + P.off[b];
-    for (uint32_t k = 1; k < m; k++) {
+    for (uint32_t k = 0; k < m; k++) {
         const uint32_t u = k < na ? x[k] : 0u, v = k < nb ? y[k] : 0u;
         if (u != v) return u < v ? -1 : 1;
     }
     return 0;
 }
-__global__ void __launch_bounds__(128) fix_ties_k(PatsView P, uint32_t *__restrict__ perm, const uint32_t *__restrict__ key_idx /*sorted idx*/) {
+__global__ void __launch_bounds__(128) fix_ties_k(PatsView P, uint32_t *__restrict__ perm, const uint32_t *__restrict__ key /*sorted*/, uint32_t nsym) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
-    const uint32_t r = perm[i];
-    const uint32_t id = key_idx[i];
-    const uint32_t w0 = P.len[r] ? P.pool[P.off[r]] : 0u;
-    if (i > 0) {                                                   // only the first position of a run works
-        const uint32_t q = perm[i - 1];
-        if (key_idx[i - 1] == id && (P.len[q] ? P.pool[P.off[q]] : 0u) == w0) return;
-    }
-    size_t j = i + 1; bool any_long = P.len[r] > 16;
-    while (j < P.n && key_idx[j] == id) {
-        const uint32_t q = perm[j];
-        if ((P.len[q] ? P.pool[P.off[q]] : 0u) != w0) break;
-        any_long |= P.len[q] > 16;
-        j++;
-    }
+    const uint32_t k0 = key[i];
+    if (i > 0 && key[i - 1] == k0) return;                          // only the first position of a run works
+    size_t j = i + 1; bool any_long = P.len[perm[i]] > nsym;
+    while (j < P.n && key[j] == k0) { any_long |= P.len[perm[j]] > nsym; j++; }
     if (!any_long || j - i < 2) return;
     for (size_t k = i + 1; k < j; k++) {
         const uint32_t v = perm[k]; size_t q = k;
-        while (q > i && tail_cmp(P, perm[q - 1], v) > 0) { perm[q] = perm[q - 1]; q--; }
+        while (q > i && pat_cmp(P, perm[q - 1], v) > 0) { perm[q] = perm[q - 1]; q--; }
         perm[q] = v;
     }
 }
@@ -134,13 +136,18 @@ extern "C" int wgbs_collapse(wgbs_ctx *ctx, wgbs_pats *P) {
     uint32_t *k0, *v0, *k1, *v1;
     RC_TRY(T.alloc(&k0, n)); RC_TRY(T.alloc(&v0, n)); RC_TRY(T.alloc(&k1, n)); RC_TRY(T.alloc(&v1, n));
     uint32_t *k = k0, *v = v0, *ka = k1, *va = v1;
-    RC_TRY(fill_iota(ctx, v, n));
     PatsView pv = view_of(P);
-    LAUNCH(ctx, gather_word_k, grid_for(n, 256), 256, 0, pv, v, 0u, k);        // least significant key: pattern word 0
+    // key layout from the index range of this batch
+    uint32_t *d_mm = ctx->d_flags + 12; const uint32_t init[2] = {0xffffffffu, 0u}; uint32_t mm[2];
+    CUDA_TRY(cudaMemcpyAsync(d_mm, init, 8, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, idx_range_k, grid_for(n, 256), 256, 0, P->idx, n, d_mm);
+    CUDA_TRY(cudaMemcpyAsync(mm, d_mm, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    uint32_t range = mm[1] - mm[0], ibits = 0; while (ibits < 32 && (range >> ibits)) ibits++;
+    const uint32_t nsym = (32 - ibits) / 2 > 16 ? 16 : (32 - ibits) / 2;
+    LAUNCH(ctx, make_key_k, grid_for(n, 256), 256, 0, pv, mm[0], nsym, k, v);
     RC_TRY(radix_sort_pairs(ctx, &k, &v, &ka, &va, n));
-    LAUNCH(ctx, gather_idx_k, grid_for(n, 256), 256, 0, pv, v, k);             // most significant key: CpG index
-    RC_TRY(radix_sort_pairs(ctx, &k, &v, &ka, &va, n));
-    LAUNCH(ctx, fix_ties_k, grid_for(n, 128), 128, 0, pv, v, k);                // longer patterns: order inside (idx, word0) runs
+    LAUNCH(ctx, fix_ties_k, grid_for(n, 128), 128, 0, pv, v, k, nsym);          // longer patterns: order inside equal-key runs
     // run-length: heads, destinations, counts
     uint32_t *head, *dst;
     RC_TRY(T.alloc(&head, n)); RC_TRY(T.alloc(&dst, n + 1));
