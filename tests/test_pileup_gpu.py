@@ -214,3 +214,44 @@ def test_np_autodetect_and_odd_tags(ctx, oracle, genome):
         _, pst = H.port_patter(sam, g.loci, g.idx(), **kw)
         assert [st[k] for k in ("lines", "pairs", "empty", "short", "invalid", "paired")] == pst, kw
         assert st["nanopore"] == 1 and st["invalid"] == 3
+
+
+def test_very_long_reads_multi_tile_lines(ctx, oracle):
+    """lines far longer than a tokenizer tile (64 KiB) / patterns of hundreds of words: SE long reads with many CIGAR ops"""
+    H = oracle
+    g = synth.make_genome(11, "chrL", 1_500_000)
+    rng = np.random.default_rng(8)
+    lines = []
+    for i, (p, L) in enumerate([(1000, 200_000), (150_000, 90_000), (150_000, 90_000), (600_000, 300_000), (1_200_000, 70_000)]):
+        seq = bytearray(g.bases[p:p + L].tobytes())
+        ops = []; q = 0
+        while q < L:
+            m = int(min(L - q, rng.integers(50, 4000)))
+            ops.append(b"%dM" % m); q += m
+            if q < L and rng.random() < 0.5:
+                d = int(rng.integers(1, 30)); ops.append(b"%dD" % d)          # deletion: later bases are shifted on the reference
+        span_shift = sum(int(o[:-1]) for o in ops if o.endswith(b"D"))
+        lines.append(b"long%d\t%d\tchrL\t%d\t60\t%s\t*\t0\t0\t%s\t*" % (i, 16 * (i % 2), p, b"".join(ops), bytes(seq)))
+    sam = b"\n".join(lines) + b"\n"
+    assert max(len(l) for l in lines) > 3 * 65536
+    ref_raw, ref_txt = _oracle_pat(H, g, sam, False)
+    raw, txt, st = _gpu_pat(ctx, g, sam)
+    assert txt == ref_txt
+    assert max(len(l.split(b"\t")[2]) for l in txt.splitlines()) > 1000
+
+
+def test_collapse_sums_counts_of_parsed_pat(ctx):
+    """wgbs_collapse on arbitrary records: (idx, pattern) order of `sort -k2,2n -k3,3`, identical records merged, counts summed"""
+    idx, pats, cnt = synth.make_pat_records(12, 30_000, 600, mean_len=9, max_len=80)
+    rng = np.random.default_rng(1)
+    sel = rng.integers(0, idx.size, size=60_000)                   # duplicates on purpose, shuffled
+    lines = [b"chr1\t%d\t%s\t%d\n" % (idx[i], pats[i], cnt[i]) for i in sel.tolist()]
+    P = ctx.pats_from_text(b"".join(lines))
+    P.collapse()
+    got = P.to_text("chr1")
+    P.free()
+    agg = {}
+    for i in sel.tolist():
+        k = (int(idx[i]), pats[i]); agg[k] = agg.get(k, 0) + int(cnt[i])
+    exp = b"".join(b"chr1\t%d\t%s\t%d\n" % (k[0], k[1], v) for k, v in sorted(agg.items()))
+    assert got == exp
