@@ -304,7 +304,11 @@ def main():
     sam = make_batch(args.reads, 1000 + rank)
     n_rec = sam.count(10)
     text_bytes = len(sam)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) torch stream is made current and handed to the library, so that torch's CUDA events, the NCCL
+    # work and every kernel of ours are ordered on ONE stream (the legacy default stream has handle 0 = "create your own")
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = Context(local, stream=stream.cuda_stream)
     ix = ctx.load_index(g.loci, 1)
     start, end = 1, g.n_cpg + 1
@@ -411,11 +415,17 @@ def main():
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.isfile(tp):
             traffic = json.load(open(tp)).get(dom)
+        others = []
+        for k, (c, ms) in top[:8]:
+            b = algorithmic_bytes(k, n_rec, text_bytes, last["stats"][7], seq_end_avg)
+            if b:
+                others.append({"kernel": k, "launches_per_step": c // psteps, "avg_launch_ms": ms / c, "achieved": b / (ms / c / 1e3) / 1e9,
+                               "frac": b / (ms / c / 1e3) / 1e9 / peak, "share_of_step": ms / tot})
         if ab:
             ach = ab / (dms / dc / 1e3) / 1e9
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                     "peak_source": how, "algorithmic_bytes_per_launch": ab, "avg_launch_ms": dms / dc,
-                    "share_of_step": dms / tot,
+                    "share_of_step": dms / tot, "per_kernel": others,
                     "breakdown_ms_per_step": {k: round(v[1] / psteps, 4) for k, v in top[:10]}}
         else:
             roof = {"bound": "hbm", "kernel": dom, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": traffic,

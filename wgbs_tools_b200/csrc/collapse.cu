@@ -22,7 +22,13 @@ __global__ void __launch_bounds__(256) idx_range_k(const uint32_t *__restrict__ 
     // idx has int32 semantics (`sort -k2,2n`): x ^ 0x80000000 maps it order-preservingly onto uint32
     uint32_t lo = i < n ? (idx[i] ^ 0x80000000u) : 0xffffffffu, hi = i < n ? (idx[i] ^ 0x80000000u) : 0u;
     lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
-    if ((threadIdx.x & 31) == 0) { atomicMin(&mnmx[0], lo); atomicMax(&mnmx[1], hi); }
+    __shared__ uint32_t slo[8], shi[8];
+    if ((threadIdx.x & 31) == 0) { slo[threadIdx.x >> 5] = lo; shi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {                                          // one atomic pair per CTA
+        for (int w = 1; w < 8; w++) { lo = min(lo, slo[w]); hi = max(hi, shi[w]); }
+        atomicMin(&mnmx[0], lo); atomicMax(&mnmx[1], hi);
+    }
 }
 // ONE 32-bit sort key per record: (idx - idx_min) in the high bits, the first `nsym` pattern symbols below it
 __global__ void __launch_bounds__(256) make_key_k(PatsView P, uint32_t idx_min, uint32_t nsym, uint32_t *__restrict__ keys, uint32_t *__restrict__ perm) {
