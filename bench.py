@@ -167,7 +167,9 @@ def algorithmic_bytes(kernel: str, n_rec: int, text_bytes: int, n_tmpl: int, seq
         "rs_onesweep_k": 16 * n_rec,                     # (key,val) read + written
         "rs_global_hist_k": 4 * n_rec,
         "pileup_measure_k": 36 * n_rec,
-        "pileup_call_k": 44 * n_rec,
+        # descriptors (44 B) + the CIGAR's sector + one 32-byte SEQ sector per candidate CpG (the two bases of a CpG are read
+        # in place from the SAM text; 150 bp x N_CPG / CHR_LEN candidates per read)
+        "pileup_call_k": int(n_rec * (44 + 32 + 32 * 150.0 * N_CPG / CHR_LEN)),
         "nl_count_k": text_bytes, "nl_write_k": text_bytes + 4 * n_rec,
     }.get(kernel)
 
