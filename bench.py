@@ -299,6 +299,8 @@ def main():
     from wgbs_tools_b200.api import Context
 
     torch.cuda.set_device(local)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"            # NCCL_DEBUG=VERSION prints a banner on STDOUT; rank 0's stdout is the one JSON line
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
