@@ -299,11 +299,22 @@ def main():
     from wgbs_tools_b200.api import Context
 
     torch.cuda.set_device(local)
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"            # NCCL_DEBUG=VERSION prints a banner on STDOUT; rank 0's stdout is the one JSON line
     if world > 1:
         import datetime
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
+        # NCCL prints its version banner on STDOUT at communicator creation whenever NCCL_DEBUG >= VERSION; rank 0's stdout
+        # must carry exactly one JSON line, so stdout points at stderr while the communicator comes up.
+        sys.stdout.flush()
+        keep = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
+            w = torch.zeros(1, device="cuda")
+            dist.all_reduce(w)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(keep, 1)
+            os.close(keep)
     g = genome()
     sam = make_batch(args.reads, 1000 + rank)
     n_rec = sam.count(10)
