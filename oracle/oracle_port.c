@@ -13,6 +13,7 @@
  * Each function cites the reference file:line it restates (paths relative to /root/reference/src).
  */
 #include <ctype.h>
+#include <errno.h>
 #include <limits.h>
 #include <math.h>
 #include <stdint.h>
@@ -36,6 +37,14 @@ static int cxx_stoi(const char *s, long n, long *out) {
     char *end; long v = strtol(tmp, &end, 10);
     if (end == tmp) return 0;
     if (v > INT_MAX || v < INT_MIN) return 0;
+    *out = v; return 1;
+}
+
+/* std::stoul semantics (strtoul base 10: optional blanks and sign, wraps negatives, throws when no digits / > ULONG_MAX) */
+static int cxx_stoul(const char *s, long n, unsigned long *out) {
+    char tmp[64]; if (n > 63) n = 63; memcpy(tmp, s, n); tmp[n] = 0;
+    char *end; errno = 0; unsigned long v = strtoul(tmp, &end, 10);
+    if (end == tmp || errno == ERANGE) return 0;
     *out = v; return 1;
 }
 
@@ -67,8 +76,6 @@ static int clean_cigar(const char *seq, long slen, const char *cig, long clen, s
     for (long i = 0; i < clen; i++) {
         if (isdigit((unsigned char)cig[i])) continue;
         long v; if (!cxx_stoi(cig + ds, i - ds, &v) || i == ds) { free(nums); free(ops); return 0; }
-        /* digit runs longer than an int overflow -> std::out_of_range */
-        if (i - ds > 10) { free(nums); free(ops); return 0; }
         nums[nops] = v; ops[nops++] = cig[i]; ds = i + 1;
     }
     long pos = 0; int ok = 1;
@@ -318,8 +325,10 @@ static int np_line_to_pat(patter_t *P, const dict_t *d, const tok *t, int nt, sb
     int rc = 0; sbuf seq = {0}, m2 = {0}; char *orig = NULL, *mask = NULL;
     if (!parse_np_fields(P, t, nt, &F)) { rc = -1; goto out; }
     if ((F.mm.n == 0 && (F.mm_h.n == 0 && !F.np_dot)) || tok_eq(t[9], "*")) { P->nr_empty++; rc = 0; goto out; }
-    long sl, fl;
-    if (!cxx_stoi(t[3].s, t[3].n, &sl) || !cxx_stoi(t[1].s, t[1].n, &fl)) { rc = -1; goto out; }
+    long sl, fl; unsigned long usl;
+    /* unsigned long start_locus = stoul(tokens[3]) (ont.cpp:102): kept 64-bit; arithmetic below is the same modulo 2^64 */
+    if (!cxx_stoul(t[3].s, t[3].n, &usl) || !cxx_stoi(t[1].s, t[1].n, &fl)) { rc = -1; goto out; }
+    sl = (long)usl;
     int bottom = ((fl & 0x10) == 16);
     if (!clean_cigar(t[9].s, t[9].n, t[5].s, t[5].n, &seq)) { rc = -1; goto out; }
     long n = t[9].n; orig = (char *)malloc(n + 1); mask = (char *)malloc(n + 1);
@@ -371,9 +380,10 @@ static void line_to_patvec(patter_t *P, const dict_t *d, const tok *t, int nt, p
         if (r == 1) { o->ok = 1; o->first = f; o->chr = t[2]; }
         return;
     }
-    long sl, fl;
-    /* stoul(tokens[3]) / stoi(tokens[1]) */
-    if (!cxx_stoi(t[3].s, t[3].n, &sl) || !cxx_stoi(t[1].s, t[1].n, &fl)) { P->nr_invalid++; return; }
+    long sl, fl; unsigned long usl;
+    /* stoul(tokens[3]) then passed as `int start_locus` to compareSeqToRef (patter.cpp:208,105): low 32 bits, signed */
+    if (!cxx_stoul(t[3].s, t[3].n, &usl) || !cxx_stoi(t[1].s, t[1].n, &fl)) { P->nr_invalid++; return; }
+    sl = (long)(int)(unsigned int)usl;
     sbuf adj = {0};
     if (!clean_cigar(t[9].s, t[9].n, t[5].s, t[5].n, &adj)) { P->nr_invalid++; free(adj.p); return; }
     int f = compare_seq_to_ref(P, d, adj.p, adj.n, sl, (int)fl, &o->pat);

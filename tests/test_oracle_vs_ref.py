@@ -156,3 +156,20 @@ def test_segment_port_matches_reference(H):
         ref = H.ref_segmentor(paths, 0, n, max_cpg, max_bp, ps, d)
         np.testing.assert_array_equal(ref, H.port_segment(betas, d, max_cpg, max_bp, ps))
         assert ref[0] == 0 and ref[-1] == n
+
+
+@pytest.mark.parametrize("seed,np_mode", [(1, False), (2, False), (3, True), (4, True)])
+def test_fuzzed_sam_port_matches_reference(H, genome, seed, np_mode):
+    """hostile SAM text (random CIGARs, truncated lines, odd FLAG/POS, malformed MM/ML): the port tracks the reference"""
+    from fuzz_sam import fuzz_sam
+    sam = fuzz_sam(genome, seed, 700, np_mode)
+    # the first line decides PE / MM mode and a broken first line is fatal in the reference: keep it valid
+    first = (synth.make_np_sam(genome, 1, 99) if np_mode else synth.make_sam(genome, 1, 99, paired=False))
+    sam = first + sam
+    kw = dict(nanopore=True, np_thresh=0.67) if np_mode else {}
+    out, err = H.ref_patter(sam, _dict(H, genome), genome.chrom, False, **kw)
+    pout, st = H.port_patter(sam, genome.loci, genome.idx(), **kw)
+    assert out == pout
+    msg = err.decode().strip().splitlines()[-1]
+    assert f"{st[2]:,} empty" in msg and f"{st[4]:,} invalid" in msg, (msg, st)
+    assert st[4] > 50

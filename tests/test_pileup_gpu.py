@@ -255,3 +255,18 @@ def test_collapse_sums_counts_of_parsed_pat(ctx):
         k = (int(idx[i]), pats[i]); agg[k] = agg.get(k, 0) + int(cnt[i])
     exp = b"".join(b"chr1\t%d\t%s\t%d\n" % (k[0], k[1], v) for k, v in sorted(agg.items()))
     assert got == exp
+
+
+@pytest.mark.parametrize("seed,np_mode", [(1, False), (2, False), (5, False), (3, True), (4, True), (6, True)])
+def test_fuzzed_sam_on_gpu(ctx, oracle, genome, seed, np_mode):
+    """hostile SAM text: same pat text and the same empty / invalid counters as the oracle, and no crash"""
+    from fuzz_sam import fuzz_sam
+    H = oracle
+    sam = fuzz_sam(genome, seed, 700, np_mode)
+    first = (synth.make_np_sam(genome, 1, 99) if np_mode else synth.make_sam(genome, 1, 99, paired=False))
+    sam = first + sam
+    kw = dict(nanopore=True, np_thresh=0.67) if np_mode else {}
+    raw, txt, st = _gpu_pat(ctx, genome, sam, **kw)
+    pout, pst = H.port_patter(sam, genome.loci, genome.idx(), **kw)
+    assert txt == H.port_collapse(pout)
+    assert [st[k] for k in ("lines", "pairs", "empty", "short", "invalid", "paired")] == pst

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(128) np_measure_k(ReadBatchView rb, const uint
                     }
                     if (!ok) inval = 1;
                     else {
-                        const int64_t pos = rb.pos[r];
+                        const int64_t pos = (int64_t)(((uint64_t)(uint32_t)rb.pos_hi[r] << 32) | (uint32_t)rb.pos[r]);   // 64-bit POS (ont.cpp:102)
                         // bottom-strand reads also see the CpG whose G is their first aligned base (ont.cpp:142-145)
                         lo = lower_bound_u32(loci, nloci, bottom ? pos - 1 : pos);
                         uint32_t hi = lower_bound_u32(loci, nloci, pos + span);
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(128) np_call_k(ReadBatchView rb, const uint32_
     if (r < rb.n) { r_idx[r] = 0; r_len[r] = 0; }
     if (r < rb.n && rb.status[r] == REC_OK && r_ncand[r] != NONE) {
         const uint32_t nc = r_ncand[r], lo = r_lo[r];
-        const int64_t pos = rb.pos[r];
+        const int64_t pos = (int64_t)(((uint64_t)(uint32_t)rb.pos_hi[r] << 32) | (uint32_t)rb.pos[r]);
         const bool bottom = (rb.flag[r] & 0x10) == 16;
         int64_t span; cig_validate(rb.text, rb.cig_off[r], rb.cig_off[r] + rb.cig_len[r], rb.seq_len[r], &span);
         const char *seq = rb.text + rb.seq_off[r];

@@ -29,6 +29,22 @@ __device__ __forceinline__ bool parse_i32(const char *__restrict__ t, uint32_t s
     return true;
 }
 
+// std::stoul semantics on text[s,e): optional blanks, sign (negation wraps modulo 2^64), >=1 digit, throws past ULONG_MAX
+__device__ __forceinline__ bool parse_u64(const char *__restrict__ t, uint32_t s, uint32_t e, uint64_t *out) {
+    while (s < e && (t[s] == ' ' || (t[s] >= 9 && t[s] <= 13))) s++;
+    bool neg = false;
+    if (s < e && (t[s] == '+' || t[s] == '-')) { neg = t[s] == '-'; s++; }
+    if (s >= e || t[s] < '0' || t[s] > '9') return false;
+    uint64_t v = 0;
+    while (s < e && t[s] >= '0' && t[s] <= '9') {
+        const uint64_t d = (uint64_t)(t[s] - '0');
+        if (v > (0xffffffffffffffffull - d) / 10) return false;     // out_of_range
+        v = v * 10 + d; s++;
+    }
+    *out = neg ? (0ull - v) : v;
+    return true;
+}
+
 // does the field starting at p carry an MM / ML tag?  1 = "MM:Z:" | "Mm:Z:", 2 = "ML:B:C" | "Ml:B:C"
 __device__ __forceinline__ int tag_kind(const char *__restrict__ t, uint32_t p, uint32_t e) {
     if (p + 5 > e || t[p] != 'M' || t[p + 2] != ':') return 0;
@@ -161,7 +177,7 @@ __global__ void __launch_bounds__(128) sam_lines_k(const char *__restrict__ text
     for (uint32_t p = s; p < qend; p++) h += name_byte_mix((uint8_t)text[p], p - s);
     h = fmix64(h ^ (uint64_t)(qend - s));
     uint8_t st = REC_OK;
-    int32_t flag = 0, pos = 0;
+    int32_t flag = 0; uint64_t pos64 = 0;
     uint32_t cig_off = s, cig_len = 0, seq_off = s, seq_len = 0;
     if (e == s) { st = REC_BLANK; h = fmix64(0x5851f42d4c957f2dULL ^ (uint64_t)line); }   // blank lines: unique keys, never paired
     else if (ntab < 10 || tb[9] == e - 1) {
@@ -169,12 +185,14 @@ __global__ void __launch_bounds__(128) sam_lines_k(const char *__restrict__ text
         // tb[9] == e-1 is impossible.)
         st = REC_INVALID;
     } else {
-        if (!parse_i32(text, tb[0] + 1, tb[1], &flag) || !parse_i32(text, tb[2] + 1, tb[3], &pos)) st = REC_BADINT;
+        // FLAG: std::stoi.  POS: std::stoul (patter.cpp:208), i.e. 64-bit with wrap-around; the bisulfite path then narrows it to
+        // `int` (compareSeqToRef's parameter), the MM/ML path keeps all 64 bits (ont.cpp:102).
+        if (!parse_i32(text, tb[0] + 1, tb[1], &flag) || !parse_u64(text, tb[2] + 1, tb[3], &pos64)) st = REC_BADINT;
         cig_off = tb[4] + 1; cig_len = tb[5] - tb[4] - 1;
         seq_off = tb[8] + 1; seq_len = tb[9] - tb[8] - 1;
     }
     rb.line_off[line] = s; rb.line_len[line] = e - s; rb.qn_len[line] = qend - s;
-    rb.flag[line] = flag; rb.pos[line] = pos;
+    rb.flag[line] = flag; rb.pos[line] = (int32_t)(uint32_t)pos64; rb.pos_hi[line] = (int32_t)(uint32_t)(pos64 >> 32);
     rb.cig_off[line] = cig_off; rb.cig_len[line] = cig_len; rb.seq_off[line] = seq_off; rb.seq_len[line] = seq_len;
     rb.hash_lo[line] = (uint32_t)h; rb.hash_hi[line] = (uint32_t)(h >> 32);
     rb.status[line] = st;
@@ -238,7 +256,7 @@ int sam_tokenize(wgbs_ctx *ctx, const char *dtext, size_t nbytes, int want_tags 
     const uint32_t n_lines = n_nl + ((nbytes && last != '\n') ? 1 : 0);
     rb.n = n_lines;
     RC_TRY(T.alloc(&rb.line_off, n_lines)); RC_TRY(T.alloc(&rb.line_len, n_lines)); RC_TRY(T.alloc(&rb.qn_len, n_lines));
-    RC_TRY(T.alloc(&rb.flag, n_lines)); RC_TRY(T.alloc(&rb.pos, n_lines));
+    RC_TRY(T.alloc(&rb.flag, n_lines)); RC_TRY(T.alloc(&rb.pos, n_lines)); RC_TRY(T.alloc(&rb.pos_hi, n_lines));
     RC_TRY(T.alloc(&rb.cig_off, n_lines)); RC_TRY(T.alloc(&rb.cig_len, n_lines));
     RC_TRY(T.alloc(&rb.seq_off, n_lines)); RC_TRY(T.alloc(&rb.seq_len, n_lines));
     RC_TRY(T.alloc(&rb.hash_lo, n_lines)); RC_TRY(T.alloc(&rb.hash_hi, n_lines));
