@@ -48,6 +48,10 @@ def test_pat_text_edge_cases(ctx, oracle):
     for s, e in [(1, 30), (5, 20), (19, 21), (25, 40)]:
         beta, mc = ctx.pat2beta_text(txt, s, e, want_counts=True)
         np.testing.assert_array_equal(mc, _ref_beta(H, txt, s, e))
+    # negative and zero counts are legal for std::stoi and simply add up
+    txt2 = b"chr1\t3\tCT.H\t5\nchr1\t4\tTC\t-2\nchr1\t4\tCC\t0\n"
+    beta, mc = ctx.pat2beta_text(txt2, 1, 12, want_counts=True)
+    np.testing.assert_array_equal(mc, H.port_pat2beta(txt2, 1, 12))
     # empty input
     beta, mc = ctx.pat2beta_text(b"", 1, 11, want_counts=True)
     assert mc.sum() == 0 and beta.shape == (10, 2)
