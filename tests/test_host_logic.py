@@ -98,3 +98,35 @@ def test_trim_golden_on_gpu(ctx):
     ok = mc.max(axis=1) < 2 ** 31
     np.testing.assert_array_equal(ctx.trim(mc[ok].astype(np.int32), int(ok.sum()), 8), np.array(G["trim_beta"]["u8"])[ok])
     np.testing.assert_array_equal(ctx.trim(mc[ok].astype(np.int32), int(ok.sum()), 16), np.array(G["trim_beta"]["u16"])[ok])
+
+
+def test_init_genome_matches_reference_definition(tmp_path):
+    """CpG dictionary from a FASTA: reference init_genome.py:246-281 (re.finditer('CG') on the upper-cased sequence,
+    chromosome_order, is_valid_chrome) restated here as the expectation"""
+    import gzip
+    import re
+    from wgbs_tools_b200 import init_genome as ig
+    from wgbs_tools_b200.genome import GenomeRef
+    rng = np.random.default_rng(0)
+    seqs = {}
+    for name, n in [("chr10", 5000), ("chr2", 7001), ("chrX", 3000), ("chrUn_gl0001", 800), ("chrM", 1200), ("chr1", 4000)]:
+        s = bytes(rng.choice(list(b"ACGTacgtN"), size=n, p=[.2, .2, .2, .2, .04, .04, .04, .04, .04]).tolist())
+        seqs[name] = s
+    fa = tmp_path / "g.fa"
+    with open(fa, "wb") as f:
+        for k, v in seqs.items():
+            f.write(b">" + k.encode() + b" some description\n")
+            for i in range(0, len(v), 60):
+                f.write(v[i:i + 60] + b"\n")
+    out = tmp_path / "ref"
+    r = ig.init_genome(str(fa), str(out))
+    assert r["chroms"] == ["chr1", "chr2", "chr10", "chrX", "chrM"]               # chrUn dropped, reference order
+    exp = []; idx = 1
+    for c in r["chroms"]:
+        for m in re.finditer("CG", seqs[c].decode().upper()):
+            exp.append(f"{c}\t{m.start() + 1}\t{idx}\n"); idx += 1
+    assert gzip.open(out / "CpG.bed.gz", "rt").read() == "".join(exp)
+    assert (out / "chrome.size").read_text().splitlines()[0] == "chr1\t4000"
+    ref = GenomeRef(str(out))
+    assert ref.nr_sites == idx - 1 and ref.chrom_of_site(1) == "chr1" and ref.chrom_of_site(idx - 1) == "chrM"
+    assert ig.chromosome_order("chrY") == 10001 and not ig.is_valid_chrome("chr1_random")

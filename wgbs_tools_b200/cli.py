@@ -1,9 +1,9 @@
 """`python -m wgbs_tools_b200.cli <command> [args]` -- the wgbstools dispatcher (reference src/python/wgbs_tools.py:50-79)
-for the four hot-path commands."""
+for the four hot-path commands (+ init_genome, which builds the CpG dictionary they need)."""
 import importlib
 import sys
 
-COMMANDS = ("bam2pat", "pat2beta", "homog", "segment")
+COMMANDS = ("bam2pat", "pat2beta", "homog", "segment", "init_genome")
 
 
 def main():
