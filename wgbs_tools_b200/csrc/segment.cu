@@ -13,8 +13,8 @@
 //   seg_cost_k     one thread per cell (e, j): the k-loop in file order with the reference's exact float/double mix and
 //                  bit-exact glibc log2f/log2 (glibc_log2.cuh).  The double sum over datasets is order dependent, so one
 //                  thread owns a cell's whole k-loop.
-//   seg_dp_k       one CTA per chunk: sequential over e, parallel max over the admissible block lengths, M in a
-//                  shared-memory ring.  End-major cell layout makes the candidates of step e contiguous.
+//   seg_dp_k       one WARP per chunk: sequential over e, parallel max over the admissible block lengths, M in a
+//                  shared-memory ring, next step's cells prefetched.  End-major layout: the candidates of step e are contiguous.
 //   seg_trace_k    traceback (segmentor.cpp:50-58)
 #include "common.cuh"
 #include "glibc_log2.cuh"
@@ -142,41 +142,51 @@ __global__ void __launch_bounds__(256) seg_cost_k(const uint32_t *__restrict__ P
     cost[c] = ll_sum != 0.0 ? ll_sum : 0.0;                                          // :137
 }
 
-// ---- DP: one CTA per chunk -------------------------------------------------------------------------------------------
-constexpr int DP_T = 128;
+// ---- DP: one WARP per chunk --------------------------------------------------------------------------------------------
+// The recurrence is a sequential chain over the chunk's sites; one step costs (shared-memory M read + 5 shuffle rounds), so
+// the latency of everything else is taken off the chain: W / cell offsets of 32 consecutive steps sit in registers (one per
+// lane, broadcast by shuffle), and the first 32 cost cells of step x+1 are loaded while step x is being reduced.  No block
+// barrier anywhere; many chunks share an SM.
+constexpr int DP_T = 32;
 __global__ void __launch_bounds__(DP_T) seg_dp_k(const Chunk *__restrict__ chunks, const uint32_t *__restrict__ W, const uint64_t *__restrict__ coff,
                                                   const double *__restrict__ cost, uint32_t ring, int32_t *__restrict__ Tb /* per site+chunk */,
                                                   const uint64_t *__restrict__ toff) {
     extern __shared__ double M[];                 // ring (power of two > max_cpg)
-    __shared__ double wv[DP_T / 32]; __shared__ uint32_t wj[DP_T / 32];
     const Chunk ch = chunks[blockIdx.x];
     int32_t *T = Tb + toff[blockIdx.x];           // n+1 entries
-    const uint32_t mask = ring - 1;
-    if (threadIdx.x == 0) { M[0] = 0.0; T[0] = 0; }
-    __syncthreads();
-    for (uint32_t x = 0; x < ch.n; x++) {         // x = i in the reference's loop (site index inside the chunk)
-        const uint32_t e = ch.start + x;
-        const uint32_t w = W[e];
-        const double *crow = cost + coff[e];
-        double best = -INFINITY; uint32_t bj = 0;
-        for (uint32_t j = threadIdx.x; j < w; j += DP_T) {
-            const double v = M[(x - j) & mask] + crow[j];
-            if (v > best || (v == best && j > bj)) { best = v; bj = j; }      // lowest k = largest j wins ties
-        }
+    const uint32_t mask = ring - 1, lane = threadIdx.x;
+    if (lane == 0) { M[0] = 0.0; T[0] = 0; }
+    __syncwarp();
+    for (uint32_t xb = 0; xb < ch.n; xb += 32) {
+        const bool have = xb + lane < ch.n;
+        const uint32_t myW = have ? W[ch.start + xb + lane] : 0u;
+        const unsigned long long myB = have ? coff[ch.start + xb + lane] : 0ull;
+        uint32_t w = __shfl_sync(0xffffffffu, myW, 0);
+        unsigned long long base = __shfl_sync(0xffffffffu, myB, 0);
+        double c_cur = lane < w ? cost[base + lane] : 0.0;
+        const uint32_t steps = min(32u, ch.n - xb);
+        for (uint32_t s = 0; s < steps; s++) {
+            const uint32_t x = xb + s;            // = i in the reference's loop (site index inside the chunk)
+            uint32_t wn = 0; unsigned long long bn = 0; double c_next = 0.0;
+            if (s + 1 < steps) {                  // software prefetch of the next step's first 32 cells
+                wn = __shfl_sync(0xffffffffu, myW, s + 1); bn = __shfl_sync(0xffffffffu, myB, s + 1);
+                if (lane < wn) c_next = cost[bn + lane];
+            }
+            double best = -INFINITY; uint32_t bj = 0;
+            if (lane < w) { best = M[(x - lane) & mask] + c_cur; bj = lane; }
+            for (uint32_t j = lane + 32; j < w; j += 32) {
+                const double v = M[(x - j) & mask] + cost[base + j];
+                if (v >= best) { best = v; bj = j; }                          // lowest k = largest j wins ties
+            }
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) {
-            double ov = __shfl_xor_sync(0xffffffffu, best, d); uint32_t oj = __shfl_xor_sync(0xffffffffu, bj, d);
-            if (ov > best || (ov == best && oj > bj)) { best = ov; bj = oj; }
+            for (int d = 16; d >= 1; d >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, best, d); const uint32_t oj = __shfl_xor_sync(0xffffffffu, bj, d);
+                if (ov > best || (ov == best && oj > bj)) { best = ov; bj = oj; }
+            }
+            if (lane == 0) { M[(x + 1) & mask] = best; T[x + 1] = (int32_t)(x - bj); }
+            __syncwarp();
+            w = wn; base = bn; c_cur = c_next;
         }
-        if ((threadIdx.x & 31) == 0) { wv[threadIdx.x >> 5] = best; wj[threadIdx.x >> 5] = bj; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-#pragma unroll
-            for (int q = 1; q < DP_T / 32; q++) if (wv[q] > best || (wv[q] == best && wj[q] > bj)) { best = wv[q]; bj = wj[q]; }
-            M[(x + 1) & mask] = best;
-            T[x + 1] = (int32_t)(x - bj);
-        }
-        __syncthreads();
     }
 }
 
