@@ -70,12 +70,10 @@ __global__ void __launch_bounds__(256) pat_pack_k(const char *__restrict__ text,
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int P2B_T = 256, P2B_RPT = 4, P2B_REC = P2B_T * P2B_RPT, P2B_W = 4096;
 
-// (meth, cover) of one site live in ONE 64-bit word -- exactly the int32[N,2] row the caller sees (meth in the low half) -- so a
-// symbol costs a single atomic: += cover<<32 | meth.  Neither half can carry into the other below 2^31 counts.
-__global__ void __launch_bounds__(P2B_T) pat2beta_k(PatsView P, int32_t start, int32_t nsites, unsigned long long *__restrict__ mc) {
-    __shared__ unsigned long long sm[P2B_W];
+__global__ void __launch_bounds__(P2B_T) pat2beta_k(PatsView P, int32_t start, int32_t nsites, int32_t *__restrict__ mc) {
+    __shared__ int32_t sm[2 * P2B_W];  // interleaved (meth, cover) like the output
     const size_t r0 = (size_t)blockIdx.x * P2B_REC;
-    for (int i = threadIdx.x; i < P2B_W; i += P2B_T) sm[i] = 0ull;
+    for (int i = threadIdx.x; i < 2 * P2B_W; i += P2B_T) sm[i] = 0;
     // window base: site offset of the first record in this CTA
     const int64_t base = (int64_t)(int32_t)P.idx[r0] - start;
     __syncthreads();
@@ -84,11 +82,9 @@ __global__ void __launch_bounds__(P2B_T) pat2beta_k(PatsView P, int32_t start, i
         size_t r = r0 + (size_t)j * P2B_T + threadIdx.x;
         if (r >= P.n) break;
         const uint32_t L = P.len[r];
-        const uint32_t cnt = P.count[r];
+        const int32_t cnt = (int32_t)P.count[r];
         int64_t k = (int64_t)(int32_t)P.idx[r] - start;   // site offset of symbol 0
         if (L == 0 || k >= nsites || k + (int64_t)L <= 0) continue;   // stdin2beta.cpp:72-75
-        const unsigned long long add_t = (unsigned long long)cnt << 32;             // 'T': cover only
-        const unsigned long long add_c = add_t | (unsigned long long)cnt;           // 'C' / 'H': cover and meth
         const uint32_t *wp = P.pool + P.off[r];
         for (uint32_t b = 0; b < L; b += 16, k += 16) {
             uint32_t w = *wp++;
@@ -99,20 +95,21 @@ __global__ void __launch_bounds__(P2B_T) pat2beta_k(PatsView P, int32_t start, i
                 int64_t site = k + lz;
                 if (site < 0 || site >= nsites) continue;
                 int64_t wofs = site - base;
-                const unsigned long long add = (code != SYM_T) ? add_c : add_t;
-                if ((int32_t)cnt < 0) {                     // a negative count (legal for std::stoi) would borrow across the halves
-                    int32_t *mi = reinterpret_cast<int32_t *>(mc);
-                    atomicAdd(&mi[2 * site + 1], (int32_t)cnt);
-                    if (code != SYM_T) atomicAdd(&mi[2 * site], (int32_t)cnt);
-                } else if (wofs >= 0 && wofs < P2B_W) atomicAdd(&sm[wofs], add);
-                else atomicAdd(&mc[site], add);
+                int add_m = (code != SYM_T) ? cnt : 0;      // 'C' or 'H'
+                if (wofs >= 0 && wofs < P2B_W) {
+                    atomicAdd(&sm[2 * wofs + 1], cnt);
+                    if (add_m) atomicAdd(&sm[2 * wofs], add_m);
+                } else {
+                    atomicAdd(&mc[2 * site + 1], cnt);
+                    if (add_m) atomicAdd(&mc[2 * site], add_m);
+                }
             }
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < P2B_W; i += P2B_T) {
-        unsigned long long v = sm[i];
-        if (v) atomicAdd(&mc[base + i], v);
+    for (int i = threadIdx.x; i < 2 * P2B_W; i += P2B_T) {
+        int32_t v = sm[i];
+        if (v) { int64_t g = 2 * base + i; atomicAdd(&mc[g], v); }
     }
 }
 
@@ -271,11 +268,10 @@ extern "C" int wgbs_pat2beta(wgbs_ctx *ctx, const wgbs_pats *P, uint32_t start, 
     if (!P) return wgbs_set_err("null pats");
     if (end < start) return wgbs_set_err("wgbs_pat2beta: end < start");
     if (!is_device_ptr(meth_cov)) return wgbs_set_err("wgbs_pat2beta: meth_cov must be a device pointer");
-    if (((uintptr_t)meth_cov) & 7) return wgbs_set_err("wgbs_pat2beta: meth_cov must be 8-byte aligned");
     const size_t ns = (size_t)end - start;
     if (zero_first) CUDA_TRY(cudaMemsetAsync(meth_cov, 0, ns * 2 * sizeof(int32_t), ctx->stream));
     if (P->n && ns) {
-        LAUNCH(ctx, pat2beta_k, grid_for(P->n, P2B_T, P2B_RPT), P2B_T, 0, view_of(P), (int32_t)start, (int32_t)ns, (unsigned long long *)meth_cov);
+        LAUNCH(ctx, pat2beta_k, grid_for(P->n, P2B_T, P2B_RPT), P2B_T, 0, view_of(P), (int32_t)start, (int32_t)ns, meth_cov);
         LAUNCH_CHECK();
     }
     return 0;
