@@ -11,12 +11,6 @@
 
 namespace {
 
-__global__ void __launch_bounds__(256) gather_word_k(PatsView P, const uint32_t *__restrict__ perm, uint32_t widx, uint32_t *__restrict__ keys) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n) return;
-    uint32_t r = perm[i];
-    keys[i] = widx < ((P.len[r] + 15) >> 4) ? P.pool[P.off[r] + widx] : 0u;
-}
 __global__ void __launch_bounds__(256) idx_range_k(const uint32_t *__restrict__ idx, size_t n, uint32_t *__restrict__ mnmx) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     // idx has int32 semantics (`sort -k2,2n`): x ^ 0x80000000 maps it order-preservingly onto uint32

@@ -22,11 +22,6 @@ __global__ void __launch_bounds__(256) fill_u32_k(uint32_t *p, size_t n, uint32_
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
-__global__ void __launch_bounds__(256) gather_u32_k(const uint32_t *__restrict__ src, const uint32_t *__restrict__ perm, uint32_t *__restrict__ dst, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = src[perm[i]];
-}
-
 // whole-line comparison, std::string operator< semantics (unsigned bytes, shorter prefix first)
 __device__ int line_cmp(const ReadBatchView &rb, uint32_t a, uint32_t b) {
     const unsigned char *x = (const unsigned char *)rb.text + rb.line_off[a], *y = (const unsigned char *)rb.text + rb.line_off[b];
@@ -86,9 +81,9 @@ int build_mates(wgbs_ctx *ctx, const ReadBatch &rb, bool paired, Temps &T, uint3
     *mate_out = mate;
     if (!paired || n < 2) { LAUNCH_CHECK(); return 0; }
     // sort record ids by the LOW 32 bits of the QNAME hash only (4 digit passes): equal-key runs then hold the mates plus
-    // the occasional 32-bit collision, which pair_runs_k separates with the high word and the name bytes themselves.
-    uint32_t *k0, *v0, *k1, *v1, *hhi_s;
-    RC_TRY(T.alloc(&k0, n)); RC_TRY(T.alloc(&v0, n)); RC_TRY(T.alloc(&k1, n)); RC_TRY(T.alloc(&v1, n)); RC_TRY(T.alloc(&hhi_s, n));
+    // the occasional 32-bit collision, which pair_runs_k separates by comparing the name bytes themselves.
+    uint32_t *k0, *v0, *k1, *v1;
+    RC_TRY(T.alloc(&k0, n)); RC_TRY(T.alloc(&v0, n)); RC_TRY(T.alloc(&k1, n)); RC_TRY(T.alloc(&v1, n));
     CUDA_TRY(cudaMemcpyAsync(k0, rb.hash_lo, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     RC_TRY(fill_iota(ctx, v0, n));
     uint32_t *k = k0, *v = v0, *ka = k1, *va = v1;
