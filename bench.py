@@ -177,7 +177,7 @@ def algorithmic_bytes(kernel: str, n_rec: int, text_bytes: int, n_tmpl: int, seq
 # ----------------------------------------------------------------------------------------------------------------------
 # the other hot-path steps (BASELINE.json metric: "pat2beta CpG-sites/sec", homog, segment) -- reported under "extra"
 # ----------------------------------------------------------------------------------------------------------------------
-def extras(ctx, torch, peak):
+def extras(ctx, torch, peak, sam_for_bam=b""):
     import ctypes as C
     from oracle import harness as H
     from wgbs_tools_b200 import synth
@@ -249,6 +249,24 @@ def extras(ctx, torch, peak):
             os.remove(p)
     for b in dbet + [dd, d_txt, mc, bs, be, d_rng, d_out]:
         b.free()
+    # ---- BAM ingest (host side: BGZF inflate + BAM -> SAM text on threads); what `samtools view` does in the reference pipeline
+    try:
+        from wgbs_tools_b200 import bamio
+        sub = sam_for_bam[: sam_for_bam.index(b"\n", len(sam_for_bam) // 8) + 1]
+        t0 = time.time(); bam = bamio.sam_to_bam(sub, [(CHR, CHR_LEN)]); tw = time.time() - t0
+        path = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp", f"wgbs_bench_{os.getpid()}.bam")
+        open(path, "wb").write(bam)
+        res = {}
+        for th in (1, host_threads()):
+            t0 = time.time(); bf = bamio.BamFile(path, th); t1 = time.time() - t0
+            t0 = time.time(); txt_out = bf.view(CHR, 10, 1796, 3); t2 = time.time() - t0
+            nrec = bf.nrecords(); bf.close()
+            res[f"threads_{th}"] = {"open_ms": t1 * 1e3, "view_ms": t2 * 1e3, "records_per_sec": nrec / (t1 + t2)}
+        os.remove(path)
+        out["bam_ingest"] = {"records": nrec, "bam_bytes": len(bam), "sam_bytes": len(txt_out), "identical_to_input_sam": bool(txt_out == sub), **res,
+                             "note": "host only (no GPU): inflate + record walk (open) and SAM formatting with -q 10 -F 1796 -f 3 (view)"}
+    except Exception as e:
+        out["bam_ingest"] = {"error": repr(e)}
     return out
 
 
@@ -464,7 +482,7 @@ def main():
     extra = None
     if rank == 0 and args.gpus == 1 and not args.no_extras:
         try:
-            extra = extras(ctx, torch, roof["peak"] if roof else 6650.0)
+            extra = extras(ctx, torch, roof["peak"] if roof else 6650.0, sam)
         except Exception as e:
             log(f"[bench] extras failed: {e!r}")
             extra = {"error": repr(e)}

@@ -3,6 +3,7 @@
 // front end (wgbs_pileup_sam) consumes.  No CUDA in this file; it lives in the library so that the drop-in covers the
 // reference's `samtools view |` stage where samtools is not installed.  Format: SAM/BAM specification v1, sections 4.1-4.2.
 #include <zlib.h>
+#include <chrono>
 
 #include <algorithm>
 #include <atomic>
@@ -45,11 +46,37 @@ int inflate_block(const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t usi
     return (rc == Z_STREAM_END && zs.avail_out == 0) ? 0 : -1;
 }
 
-void put_int(std::string &o, long long v) { char b[24]; int n = snprintf(b, sizeof b, "%lld", v); o.append(b, n); }
+// ---- formatting: raw pointer writes into a per-thread buffer that is grown per record, no per-char container calls ----
+struct OutBuf {
+    char *p = nullptr; size_t n = 0, cap = 0;
+    ~OutBuf() { free(p); }
+    bool reserve(size_t extra) {
+        if (n + extra <= cap) return true;
+        size_t nc = std::max(cap * 2, n + extra + (1u << 20));
+        char *q = (char *)realloc(p, nc);
+        if (!q) return false;
+        p = q; cap = nc; return true;
+    }
+};
+inline char *put_u64(char *o, unsigned long long v) {
+    char t[24]; int k = 0;
+    do { t[k++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (k) *o++ = t[--k];
+    return o;
+}
+inline char *put_i64(char *o, long long v) {
+    if (v < 0) { *o++ = '-'; return put_u64(o, 0ull - (unsigned long long)v); }
+    return put_u64(o, (unsigned long long)v);
+}
+inline char *put_str(char *o, const char *s, size_t n) { memcpy(o, s, n); return o + n; }
+struct SeqTable { char t[256][2]; SeqTable() { const char *a = "=ACMGRSVTWYHKDBN"; for (int i = 0; i < 256; i++) { t[i][0] = a[i >> 4]; t[i][1] = a[i & 15]; } } };
+static const SeqTable g_seq;
 
-// one record -> one SAM line (samtools view formatting)
-void format_record(const wgbs_bam *B, const uint8_t *r, std::string &o) {
+// one record -> one SAM line (samtools view formatting).  Worst-case growth: SEQ 2x, int8 B-array items "-128," 5x.
+bool format_record(const wgbs_bam *B, const uint8_t *r, OutBuf &ob) {
     const uint32_t bs = rd32(r);
+    if (!ob.reserve((size_t)bs * 6 + 256)) return false;
+    char *o = ob.p + ob.n;
     const uint8_t *p = r + 4, *end = r + 4 + bs;
     const int32_t refid = rdi32(p), pos = rdi32(p + 4);
     const uint8_t l_name = p[8], mapq = p[9];
@@ -57,49 +84,53 @@ void format_record(const wgbs_bam *B, const uint8_t *r, std::string &o) {
     const int32_t l_seq = rdi32(p + 16), nref = rdi32(p + 20), npos = rdi32(p + 24), tlen = rdi32(p + 28);
     const char *name = (const char *)(p + 32);
     const uint8_t *cig = p + 32 + l_name, *seq = cig + 4 * (size_t)n_cig, *qual = seq + (l_seq + 1) / 2, *tags = qual + l_seq;
-    o.append(name, l_name ? strnlen(name, l_name) : 0);          // l_read_name counts the trailing NUL
-    o.push_back('\t'); put_int(o, flag); o.push_back('\t');
-    if (refid >= 0 && refid < (int32_t)B->ref_names.size()) o += B->ref_names[refid]; else o.push_back('*');
-    o.push_back('\t'); put_int(o, (long long)pos + 1); o.push_back('\t'); put_int(o, mapq); o.push_back('\t');
-    if (n_cig == 0) o.push_back('*');
-    else for (uint16_t k = 0; k < n_cig; k++) { uint32_t c = rd32(cig + 4 * k); put_int(o, c >> 4); o.push_back("MIDNSHP=XB??????"[c & 15]); }
-    o.push_back('\t');
-    if (nref < 0) o.push_back('*'); else if (nref == refid) o.push_back('='); else if (nref < (int32_t)B->ref_names.size()) o += B->ref_names[nref]; else o.push_back('*');
-    o.push_back('\t'); put_int(o, (long long)npos + 1); o.push_back('\t'); put_int(o, tlen); o.push_back('\t');
-    if (l_seq == 0) o.push_back('*');
-    else for (int32_t k = 0; k < l_seq; k++) o.push_back("=ACMGRSVTWYHKDBN"[(seq[k >> 1] >> ((~k & 1) << 2)) & 15]);
-    o.push_back('\t');
-    if (l_seq == 0 || qual[0] == 0xff) o.push_back('*');
-    else for (int32_t k = 0; k < l_seq; k++) o.push_back((char)(qual[k] + 33));
+    const int nrefs = (int)B->ref_names.size();
+    o = put_str(o, name, l_name ? strnlen(name, l_name) : 0);       // l_read_name counts the trailing NUL
+    *o++ = '\t'; o = put_u64(o, flag); *o++ = '\t';
+    if (refid >= 0 && refid < nrefs) o = put_str(o, B->ref_names[refid].data(), B->ref_names[refid].size()); else *o++ = '*';
+    *o++ = '\t'; o = put_i64(o, (long long)pos + 1); *o++ = '\t'; o = put_u64(o, mapq); *o++ = '\t';
+    if (n_cig == 0) *o++ = '*';
+    else for (uint16_t k = 0; k < n_cig; k++) { const uint32_t c = rd32(cig + 4 * k); o = put_u64(o, c >> 4); *o++ = "MIDNSHP=XB??????"[c & 15]; }
+    *o++ = '\t';
+    if (nref < 0) *o++ = '*'; else if (nref == refid) *o++ = '='; else if (nref < nrefs) o = put_str(o, B->ref_names[nref].data(), B->ref_names[nref].size()); else *o++ = '*';
+    *o++ = '\t'; o = put_i64(o, (long long)npos + 1); *o++ = '\t'; o = put_i64(o, tlen); *o++ = '\t';
+    if (l_seq <= 0) *o++ = '*';
+    else {
+        const int32_t full = l_seq >> 1;
+        for (int32_t k = 0; k < full; k++) { o[0] = g_seq.t[seq[k]][0]; o[1] = g_seq.t[seq[k]][1]; o += 2; }
+        if (l_seq & 1) *o++ = g_seq.t[seq[full]][0];
+    }
+    *o++ = '\t';
+    if (l_seq <= 0 || qual[0] == 0xff) *o++ = '*';
+    else { for (int32_t k = 0; k < l_seq; k++) o[k] = (char)(qual[k] + 33); o += l_seq; }
     // optional fields
     const uint8_t *t = tags;
     while (t + 3 <= end) {
-        o.push_back('\t'); o.push_back((char)t[0]); o.push_back((char)t[1]); o.push_back(':');
+        *o++ = '\t'; *o++ = (char)t[0]; *o++ = (char)t[1]; *o++ = ':';
         const char ty = (char)t[2]; t += 3;
-        char b[64];
         switch (ty) {
-            case 'A': o += "A:"; o.push_back((char)*t); t += 1; break;
-            case 'c': o += "i:"; put_int(o, (int8_t)*t); t += 1; break;
-            case 'C': o += "i:"; put_int(o, *t); t += 1; break;
-            case 's': o += "i:"; put_int(o, (int16_t)rd16(t)); t += 2; break;
-            case 'S': o += "i:"; put_int(o, rd16(t)); t += 2; break;
-            case 'i': o += "i:"; put_int(o, rdi32(t)); t += 4; break;
-            case 'I': o += "i:"; put_int(o, rd32(t)); t += 4; break;
-            case 'f': { float f; memcpy(&f, t, 4); int n = snprintf(b, sizeof b, "%g", f); o += "f:"; o.append(b, n); t += 4; break; }
-            case 'Z': case 'H': { o.push_back(ty); o.push_back(':'); const char *z = (const char *)t; size_t l = strnlen(z, end - t); o.append(z, l); t += l + 1; break; }
+            case 'A': *o++ = 'A'; *o++ = ':'; *o++ = (char)*t; t += 1; break;
+            case 'c': *o++ = 'i'; *o++ = ':'; o = put_i64(o, (int8_t)*t); t += 1; break;
+            case 'C': *o++ = 'i'; *o++ = ':'; o = put_u64(o, *t); t += 1; break;
+            case 's': *o++ = 'i'; *o++ = ':'; o = put_i64(o, (int16_t)rd16(t)); t += 2; break;
+            case 'S': *o++ = 'i'; *o++ = ':'; o = put_u64(o, rd16(t)); t += 2; break;
+            case 'i': *o++ = 'i'; *o++ = ':'; o = put_i64(o, rdi32(t)); t += 4; break;
+            case 'I': *o++ = 'i'; *o++ = ':'; o = put_u64(o, rd32(t)); t += 4; break;
+            case 'f': { float f; memcpy(&f, t, 4); *o++ = 'f'; *o++ = ':'; o += snprintf(o, 32, "%g", f); t += 4; break; }
+            case 'Z': case 'H': { *o++ = ty; *o++ = ':'; const char *z = (const char *)t; size_t l = strnlen(z, end - t); o = put_str(o, z, l); t += l + 1; break; }
             case 'B': {
                 const char sub = (char)t[0]; const uint32_t cnt = rd32(t + 1); t += 5;
-                o += "B:"; o.push_back(sub);
+                *o++ = 'B'; *o++ = ':'; *o++ = sub;
                 for (uint32_t k = 0; k < cnt && t < end; k++) {
-                    o.push_back(',');
+                    *o++ = ',';
                     switch (sub) {
-                        case 'c': put_int(o, (int8_t)*t); t += 1; break;
-                        case 'C': put_int(o, *t); t += 1; break;
-                        case 's': put_int(o, (int16_t)rd16(t)); t += 2; break;
-                        case 'S': put_int(o, rd16(t)); t += 2; break;
-                        case 'i': put_int(o, rdi32(t)); t += 4; break;
-                        case 'I': put_int(o, rd32(t)); t += 4; break;
-                        case 'f': { float f; memcpy(&f, t, 4); int n = snprintf(b, sizeof b, "%g", f); o.append(b, n); t += 4; break; }
+                        case 'c': o = put_i64(o, (int8_t)*t); t += 1; break;
+                        case 'C': o = put_u64(o, *t); t += 1; break;
+                        case 's': o = put_i64(o, (int16_t)rd16(t)); t += 2; break;
+                        case 'S': o = put_u64(o, rd16(t)); t += 2; break;
+                        case 'i': o = put_i64(o, rdi32(t)); t += 4; break;
+                        case 'I': o = put_u64(o, rd32(t)); t += 4; break;
+                        case 'f': { float f; memcpy(&f, t, 4); o += snprintf(o, 32, "%g", f); t += 4; break; }
                         default: t = end; break;
                     }
                 }
@@ -108,7 +139,9 @@ void format_record(const wgbs_bam *B, const uint8_t *r, std::string &o) {
             default: t = end; break;   // unknown type: stop (malformed)
         }
     }
-    o.push_back('\n');
+    *o++ = '\n';
+    ob.n = (size_t)(o - ob.p);
+    return true;
 }
 
 }  // namespace
@@ -116,12 +149,15 @@ void format_record(const wgbs_bam *B, const uint8_t *r, std::string &o) {
 extern "C" int wgbs_bam_open(const char *path, int threads, wgbs_bam **out) {
     if (!path || !out) return wgbs_set_err("wgbs_bam_open: null argument");
     *out = nullptr;
+    const bool dbg = getenv("WGBS_BAM_DEBUG") != nullptr; auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) { if (dbg) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "[bam] %-10s %.3f s\n", what, std::chrono::duration<double>(t - T0).count()); T0 = t; } };
     FILE *f = fopen(path, "rb");
     if (!f) return wgbs_set_err("wgbs_bam_open: cannot open %s", path);
     fseek(f, 0, SEEK_END); const long fsz = ftell(f); fseek(f, 0, SEEK_SET);
     std::vector<uint8_t> comp((size_t)fsz);
     if (fsz && fread(comp.data(), 1, (size_t)fsz, f) != (size_t)fsz) { fclose(f); return wgbs_set_err("wgbs_bam_open: short read on %s", path); }
     fclose(f);
+    lap("read");
     // 1. BGZF block table
     std::vector<Block> blocks; uint64_t off = 0, uoff = 0;
     while (off + 28 <= (uint64_t)fsz) {
@@ -140,7 +176,9 @@ extern "C" int wgbs_bam_open(const char *path, int threads, wgbs_bam **out) {
     }
     wgbs_bam *B = new wgbs_bam();
     B->threads = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    lap("blocks");
     B->data.resize(uoff);
+    lap("alloc");
     // 2. inflate in parallel
     std::atomic<size_t> next(0); std::atomic<int> bad(0);
     auto work = [&]() {
@@ -153,6 +191,7 @@ extern "C" int wgbs_bam_open(const char *path, int threads, wgbs_bam **out) {
         work();
         for (auto &t : th) t.join();
     }
+    lap("inflate");
     if (bad.load()) { delete B; return wgbs_set_err("%s: inflate failed (corrupt BGZF block)", path); }
     // 3. header
     const uint8_t *d = B->data.data(); const uint64_t n = B->data.size();
@@ -183,6 +222,7 @@ extern "C" int wgbs_bam_open(const char *path, int threads, wgbs_bam **out) {
         B->ref_last[slot] = idx + 1;
         B->rec_off.push_back(p); p += 4 + bs; idx++;
     }
+    lap("walk");
     *out = B;
     return 0;
 }
@@ -205,10 +245,11 @@ extern "C" int wgbs_bam_view(const wgbs_bam *B, int refid, int min_mapq, int exc
     uint64_t r0 = 0, r1 = B->rec_off.size();
     if (refid >= 0) { if (refid >= (int)B->ref_names.size()) return wgbs_set_err("wgbs_bam_view: no such reference"); r0 = B->ref_first[refid]; r1 = B->ref_last[refid]; }
     const int nt = (int)std::max<uint64_t>(1, std::min<uint64_t>(B->threads, (r1 - r0) / 2048 + 1));
-    std::vector<std::string> parts(nt); std::vector<uint64_t> cnt(nt, 0);
+    std::vector<OutBuf> parts(nt); std::vector<uint64_t> cnt(nt, 0); std::atomic<int> oom(0);
     auto work = [&](int t) {
         const uint64_t a = r0 + (r1 - r0) * t / nt, b = r0 + (r1 - r0) * (t + 1) / nt;
-        std::string &o = parts[t]; o.reserve((b - a) * 360);
+        OutBuf &o = parts[t];
+        if (!o.reserve((b - a) * 384 + 4096)) { oom.store(1); return; }
         for (uint64_t i = a; i < b; i++) {
             const uint8_t *r = B->data.data() + B->rec_off[i];
             const uint16_t flag = rd16(r + 4 + 14); const uint8_t mapq = r[4 + 9];
@@ -220,19 +261,28 @@ extern "C" int wgbs_bam_view(const wgbs_bam *B, int refid, int min_mapq, int exc
                 if (span < 1) span = 1;
                 if (pos > end || pos + span - 1 < beg) continue;
             }
-            format_record(B, r, o); cnt[t]++;
+            if (!format_record(B, r, o)) { oom.store(1); return; }
+            cnt[t]++;
         }
     };
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; t++) th.emplace_back(work, t);
-    work(0);
-    for (auto &t : th) t.join();
-    size_t tot = 0; uint64_t nr = 0;
-    for (int t = 0; t < nt; t++) { tot += parts[t].size(); nr += cnt[t]; }
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) th.emplace_back(work, t);
+        work(0);
+        for (auto &t : th) t.join();
+    }
+    if (oom.load()) return wgbs_set_err("wgbs_bam_view: out of memory");
+    size_t tot = 0; uint64_t nr = 0; std::vector<size_t> at(nt);
+    for (int t = 0; t < nt; t++) { at[t] = tot; tot += parts[t].n; nr += cnt[t]; }
     char *buf = (char *)malloc(tot ? tot : 1);
     if (!buf) return wgbs_set_err("wgbs_bam_view: out of memory");
-    size_t o = 0;
-    for (int t = 0; t < nt; t++) { memcpy(buf + o, parts[t].data(), parts[t].size()); o += parts[t].size(); }
+    {
+        auto cp = [&](int t) { if (parts[t].n) memcpy(buf + at[t], parts[t].p, parts[t].n); };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) th.emplace_back(cp, t);
+        cp(0);
+        for (auto &t : th) t.join();
+    }
     *text = buf; *nbytes = tot; if (nrecords) *nrecords = nr;
     return 0;
 }
