@@ -123,6 +123,11 @@ typedef struct wgbs_pileup_opts {
  *           -- the counters of patter's summary line (patter.cpp:298-316). */
 int wgbs_pileup_sam(wgbs_ctx *, const wgbs_index *, const char *sam, size_t nbytes, const wgbs_pileup_opts *,
                     wgbs_pats **out, uint64_t *stats);
+/* Same, plus the M-bias tables of `patter --mbias` (reference patter.cpp:50-72,116-165): mbias = int32[2][2][1000][2]
+ * indexed [OT=0|OB=1][mate 1|2][read position][meth=0|unmeth=1] (host or device; NULL = off), zeroed by the call.  The
+ * reference's `<path>.OT.txt` / `.OB.txt` rows are `r1m r1u r2m r2u` per position.  Ignored in MM/ML mode, like the reference. */
+int wgbs_pileup_sam_mbias(wgbs_ctx *, const wgbs_index *, const char *sam, size_t nbytes, const wgbs_pileup_opts *,
+                          wgbs_pats **out, uint64_t *stats, int32_t *mbias);
 /* sort by (idx, pattern) in the C locale and merge identical records, summing counts (in place) */
 int wgbs_collapse(wgbs_ctx *, wgbs_pats *);
 /* "chrom \t idx \t pattern \t count \n" per record, record order.  out NULL: only *nbytes. out: host or device. */

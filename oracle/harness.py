@@ -43,7 +43,7 @@ def tool(name: str, opt: bool = False) -> str:
 
 def ref_patter(sam: bytes, dict_path: str, region: str, paired: bool, min_cpg: int = 1, clip: int = 0,
                nanopore: bool = False, np_thresh: float | None = None, cpc_call: str | None = None,
-               combine_mods: bool = False, opt: bool = False):
+               combine_mods: bool = False, opt: bool = False, mbias: str | None = None):
     """`[match_maker |] patter DICT REGION ...`  (reference bam2pat.py:186-204). returns (stdout, stderr)."""
     cmd = ""
     if paired:
@@ -57,8 +57,19 @@ def ref_patter(sam: bytes, dict_path: str, region: str, paired: bool, min_cpg: i
         cmd += f" --cpc_call {cpc_call}"
     if combine_mods:
         cmd += " --combine_mods"
+    if mbias:
+        cmd += f" --mbias {mbias}"
     p = subprocess.run(cmd, shell=True, input=sam, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=_env())
     return p.stdout, p.stderr
+
+
+def read_mbias(prefix: str) -> np.ndarray:
+    """<prefix>.OT.txt / .OB.txt written by `patter --mbias` (patter.cpp:50-72) -> int32[2][2][1000][2] = [OT|OB][mate][pos][meth|unmeth]"""
+    out = np.zeros((2, 2, 1000, 2), np.int32)
+    for s, x in enumerate(("OT", "OB")):
+        rows = np.loadtxt(f"{prefix}.{x}.txt", skiprows=1, dtype=np.int64).reshape(1000, 4)
+        out[s, 0, :, 0] = rows[:, 0]; out[s, 0, :, 1] = rows[:, 1]; out[s, 1, :, 0] = rows[:, 2]; out[s, 1, :, 1] = rows[:, 3]
+    return out
 
 
 def ref_collapse(txt: bytes) -> bytes:

@@ -270,3 +270,36 @@ def test_fuzzed_sam_on_gpu(ctx, oracle, genome, seed, np_mode):
     pout, pst = H.port_patter(sam, genome.loci, genome.idx(), **kw)
     assert txt == H.port_collapse(pout)
     assert [st[k] for k in ("lines", "pairs", "empty", "short", "invalid", "paired")] == pst
+
+
+@pytest.mark.parametrize("paired", [True, False])
+def test_mbias_tables_match_patter(ctx, oracle, genome, paired, tmp_path):
+    """`patter --mbias` (patter.cpp:116-165): per-read-position meth / unmeth counts, counted before the clip; reads of
+    1000+ reference bases are skipped entirely on the bottom strand and beyond position 999 on the top strand"""
+    H = oracle
+    if not H.have_ref():
+        pytest.skip("needs the reference patter executable")
+    g = genome
+    sam = synth.make_sam(g, 8000, 77, paired=paired)
+    if not paired:
+        # two long single-end reads (top and bottom) to exercise the MAX_READ_LEN guard
+        for flag, p in ((0, 20_000), (16, 40_000)):
+            seq = g.bases[p:p + 1500].tobytes()
+            sam += b"long%d\t%d\tchrT\t%d\t60\t1500M\t*\t0\t0\t%s\t*\n" % (flag, flag, p, seq)
+    else:
+        # improper-pair flags (not 83/163/99/147) take no part in the M-bias tables
+        lines = sam.splitlines(keepends=True)
+        for i in range(0, len(lines), 41):
+            t = lines[i].split(b"\t"); t[1] = b"%d" % (int(t[1]) & ~2); lines[i] = b"\t".join(t)
+        sam = b"".join(lines)
+    d = H.write_tmp(g.dict_text(), ".CpG.bed")
+    pref = str(tmp_path / "mb")
+    out, err = H.ref_patter(sam, d, g.chrom, paired, clip=4, mbias=pref)
+    exp = H.read_mbias(pref)
+    ix = ctx.load_index(g.loci, g.first_idx)
+    P, st = ctx.pileup_sam(ix, sam, clip=4, mbias=True)
+    P.collapse()
+    assert P.to_text(g.chrom) == H.ref_collapse(out)
+    P.free(); ix.free()
+    np.testing.assert_array_equal(st["mbias"], exp)
+    assert exp.sum() > 5000

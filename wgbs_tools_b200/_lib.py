@@ -51,6 +51,7 @@ def _load():
         "wgbs_index_load": (C.c_int, [vp, vp, sz, u32, C.POINTER(vp)]),
         "wgbs_index_free": (None, [vp, vp]),
         "wgbs_pileup_sam": (C.c_int, [vp, vp, vp, sz, vp, C.POINTER(vp), vp]),
+        "wgbs_pileup_sam_mbias": (C.c_int, [vp, vp, vp, sz, vp, C.POINTER(vp), vp, vp]),
         "wgbs_collapse": (C.c_int, [vp, vp]),
         "wgbs_pats_format": (C.c_int, [vp, vp, C.c_char_p, vp, sz, C.POINTER(sz)]),
         "wgbs_sort_pairs_u32": (C.c_int, [vp, vp, vp, sz]),

@@ -186,7 +186,8 @@ class Context:
         return Index(self, loci, first_idx)
 
     def pileup_sam(self, index: "Index", sam, min_cpg: int = 1, clip: int = 0, paired: int = -1, nanopore: bool = False,
-                   np_thresh: float = 0.67, cpc_call: str = "C", combine_mods: bool = False, nbytes: int | None = None):
+                   np_thresh: float = 0.67, cpc_call: str = "C", combine_mods: bool = False, nbytes: int | None = None,
+                   mbias: bool = False):
         """SAM text (bytes or DevBuf) -> (Pats of templates, stats dict).  The reference's
         `samtools view ... | [match_maker |] patter DICT REGION ...` for one chromosome."""
         if isinstance(sam, DevBuf):
@@ -196,9 +197,13 @@ class Context:
             p, n = a.ctypes.data, a.size
         o = PileupOpts(min_cpg, clip, paired, int(nanopore), int(combine_mods), np_thresh, cpc_call.encode())
         h = C.c_void_p(); st = (C.c_uint64 * 8)()
-        check(lib.wgbs_pileup_sam(self.h, index.h, p, n, C.addressof(o), C.byref(h), C.addressof(st)))
+        mb = np.zeros((2, 2, 1000, 2), np.int32) if mbias else None
+        check(lib.wgbs_pileup_sam_mbias(self.h, index.h, p, n, C.addressof(o), C.byref(h), C.addressof(st), mb.ctypes.data if mbias else None))
         keys = ["lines", "pairs", "empty", "short", "invalid", "paired", "nanopore", "templates"]
-        return Pats(self, h.value), dict(zip(keys, [int(x) for x in st]))
+        stats = dict(zip(keys, [int(x) for x in st]))
+        if mbias:
+            stats["mbias"] = mb          # [OT|OB][mate][position][meth|unmeth]
+        return Pats(self, h.value), stats
 
     def sort_pairs(self, keys: np.ndarray, vals: np.ndarray):
         k = self.upload(np.ascontiguousarray(keys, np.uint32)); v = self.upload(np.ascontiguousarray(vals, np.uint32))

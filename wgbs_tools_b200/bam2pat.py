@@ -49,7 +49,7 @@ def proc_chr(ctx, ref, chrom: str, sam: bytes, args, mc_buf):
     loci, first = ref.chrom_loci(chrom)
     ix = ctx.load_index(loci, first)
     P, st = ctx.pileup_sam(ix, sam, min_cpg=args.min_cpg, clip=args.clip, paired=-1, nanopore=args.nanopore,
-                           np_thresh=args.np_thresh, cpc_call=args.cpc_call, combine_mods=args.combine_mods)
+                           np_thresh=args.np_thresh, cpc_call=args.cpc_call, combine_mods=args.combine_mods, mbias=args.mbias)
     if mc_buf is not None:
         ctx.pat2beta(P, 1, ref.nr_sites + 1, meth_cov=mc_buf, zero_first=False)
     P.collapse()
@@ -79,6 +79,7 @@ def main(argv=None):
     p.add_argument("--no_beta", action="store_true"); p.add_argument("-l", "--lbeta", action="store_true")
     p.add_argument("--nanopore", "-np", action="store_true"); p.add_argument("--cpc_call", default="C", choices=["C", "H", "."])
     p.add_argument("--np_thresh", type=float, default=0.67); p.add_argument("--combine_mods", action="store_true")
+    p.add_argument("--mbias", "-mb", action="store_true", help="write the M-bias tables (<name>.mbias/<name>.mbias.{OT,OB}.txt); plots are out of scope")
     a = p.parse_args(argv)
     if not 0 < a.np_thresh < 1:
         raise ValueError("Invalid np_thresh range: must be in range (0,1)")
@@ -103,6 +104,7 @@ def main(argv=None):
             if mc is not None:
                 ctx.pat2beta(ctx.pats_from_text(b""), 1, ref.nr_sites + 1, meth_cov=mc, zero_first=True)
             parts = []
+            mb_total = None
             for chrom in [c for c in ref.chroms if c in by_chrom]:           # chromosome_order (init_genome.py:263-275)
                 if bam is not None:
                     head = bam.view(chrom, beg=1, end=1 << 29)[:4096]         # is_pair_end: FLAG of the first read (bam2pat.py:262-267)
@@ -116,7 +118,9 @@ def main(argv=None):
                     s = filter_sam(s, 0 if a.nanopore else a.mapq, ex, inc)
                 if not s:
                     continue
-                txt, _ = proc_chr(ctx, ref, chrom, s, a, mc)
+                txt, st = proc_chr(ctx, ref, chrom, s, a, mc)
+                if a.mbias and "mbias" in st:
+                    mb_total = st["mbias"].astype(np.int64) if mb_total is None else mb_total + st["mbias"]   # mbias_merge (bam2pat.py:375-395)
                 if txt:
                     parts.append(bgzf_compress(txt, a.threads))
             if not parts:
@@ -125,6 +129,15 @@ def main(argv=None):
             with open(pat_path, "wb") as f:
                 f.write(b"".join(parts))                                       # `cat parts` (bam2pat.py:408)
             print(f"[wt bam2pat] generated {pat_path}", file=sys.stderr)
+            if a.mbias and mb_total is not None:
+                mdir = os.path.join(a.out_dir, name) + ".mbias"
+                os.makedirs(mdir, exist_ok=True)
+                for si, x in enumerate(("OT", "OB")):
+                    with open(os.path.join(mdir, name) + f".mbias.{x}.txt", "w") as f:
+                        f.write("r1m1\tr1u1\tr2m2\tr2u2\n")
+                        for pos in range(1000):
+                            t = mb_total[si, :, pos, :]
+                            f.write(f"{t[0, 0]}\t{t[0, 1]}\t{t[1, 0]}\t{t[1, 1]}\n")
             if mc is not None:
                 beta = ctx.trim(mc, ref.nr_sites, 16 if a.lbeta else 8)
                 bp = os.path.join(a.out_dir, name + (".lbeta" if a.lbeta else ".beta"))

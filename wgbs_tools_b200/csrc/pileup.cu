@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) pileup_call_k(ReadBatchView rb, const uin
                                                       const uint32_t *__restrict__ r_lo, const uint32_t *__restrict__ r_ncand,
                                                       const uint32_t *__restrict__ off, uint32_t *__restrict__ pool,
                                                       int32_t *__restrict__ r_idx, uint32_t *__restrict__ r_len,
-                                                      unsigned long long *__restrict__ stats) {
+                                                      unsigned long long *__restrict__ stats, int32_t *__restrict__ mbias) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t empty = 0;
     if (r < rb.n && rb.status[r] == REC_OK && r_ncand[r] != NONE) {
@@ -83,6 +83,18 @@ __global__ void __launch_bounds__(256) pileup_call_k(ReadBatchView rb, const uin
         uint32_t *wp = pool + off[r];
         int32_t first = -1, last = -1;      // candidate ordinals of the first / last called ('C'/'T') site
         uint32_t w = 0; int32_t nsym = 0;   // symbols emitted since `first`
+        // M-bias table slot of this read (patter.cpp:116-129): [OT|OB][mate 0|1][1000 positions][meth|unmeth], or none
+        int32_t *mb = nullptr;
+        if (mbias) {
+            int mate = 0; bool skip = false;
+            if (o.paired) {
+                if ((flag & 0x53) == 0x53) mate = 0; else if ((flag & 0xA3) == 0xA3) mate = 1;
+                else if ((flag & 0x63) == 0x63) mate = 0; else if ((flag & 0x93) == 0x93) mate = 1; else skip = true;
+            }
+            // bottom reads index positions from the far end: the first step (mj = len-1) already trips the MAX_READ_LEN guard (:143)
+            if (bottom && span - 1 >= 1000) skip = true;
+            if (!skip) mb = mbias + ((bottom ? 1 : 0) * 2 + mate) * 2000;
+        }
         for (uint32_t j = 0; j < nc; j++) {
             const int64_t i = (int64_t)loci[lo + j] - pos;     // offset of the CpG's C in the reference-projected read
             // adj[i] and adj[i+1]
@@ -97,6 +109,10 @@ __global__ void __launch_bounds__(256) pileup_call_k(ReadBatchView rb, const uin
             } else {            // OB: G/A at the G position, C must precede (shift 1)
                 jx = i + 1;
                 if (c0 == 'C') code = c1 == 'A' ? SYM_T : (c1 == 'G' ? SYM_C : SYM_DOT);
+            }
+            if (mb && code != SYM_DOT) {                                       // counted before the clip (patter.cpp:152-165)
+                const int64_t mj = bottom ? span - i - 1 : i;
+                if (mj < 1000) atomicAdd(&mb[2 * mj + (code == SYM_T ? 1 : 0)], 1);
             }
             if (!((jx >= o.clip) && (jx < span - o.clip))) code = SYM_DOT;     // patter.cpp:169-172
             if (first < 0) { if (code == SYM_DOT) continue; first = (int32_t)j; }
@@ -207,6 +223,11 @@ extern "C" void wgbs_index_free(wgbs_ctx *ctx, wgbs_index *ix) {
 
 extern "C" int wgbs_pileup_sam(wgbs_ctx *ctx, const wgbs_index *ix, const char *sam, size_t nbytes, const wgbs_pileup_opts *opts,
                                wgbs_pats **out, uint64_t *stats_out) {
+    return wgbs_pileup_sam_mbias(ctx, ix, sam, nbytes, opts, out, stats_out, nullptr);
+}
+
+extern "C" int wgbs_pileup_sam_mbias(wgbs_ctx *ctx, const wgbs_index *ix, const char *sam, size_t nbytes, const wgbs_pileup_opts *opts,
+                                     wgbs_pats **out, uint64_t *stats_out, int32_t *mbias_out) {
     RC_TRY(wgbs_ctx_activate(ctx));
     if (!ix || !opts || !out) return wgbs_set_err("wgbs_pileup_sam: null argument");
     *out = nullptr;
@@ -267,12 +288,17 @@ extern "C" int wgbs_pileup_sam(wgbs_ctx *ctx, const wgbs_index *ix, const char *
     int rc = dalloc(ctx, &P->pool, pool_words);
     if (rc < 0) { delete P; return rc; }
     P->pool_words = pool_words;
+    int32_t *d_mbias = nullptr;
+    if (mbias_out) {
+        if (is_device_ptr(mbias_out)) d_mbias = mbias_out; else if ((rc = T.alloc(&d_mbias, 8000)) < 0) { wgbs_pats_free(ctx, P); return rc; }
+        CUDA_TRY(cudaMemsetAsync(d_mbias, 0, 8000 * sizeof(int32_t), ctx->stream));
+    }
     int32_t *r_idx; uint32_t *r_len, *t_idx, *t_len, *t_off, *t_valid, *dst;
     if ((rc = T.alloc(&r_idx, n)) < 0 || (rc = T.alloc(&r_len, n)) < 0 || (rc = T.alloc(&t_idx, n)) < 0 || (rc = T.alloc(&t_len, n)) < 0 ||
         (rc = T.alloc(&t_off, n)) < 0 || (rc = T.alloc(&t_valid, n)) < 0 || (rc = T.alloc(&dst, (size_t)n + 1)) < 0) { wgbs_pats_free(ctx, P); return rc; }
     if (n) {
         if (o.nanopore) { int rc2 = np_call(ctx, rb, ix->loci, ix->first_idx, o, r_lo, r_ncand, off, P->pool, pool_words, r_idx, r_len, d_stats); if (rc2 < 0) { wgbs_pats_free(ctx, P); return rc2; } }
-        else LAUNCH(ctx, pileup_call_k, grid_for(n, 256), 256, 0, view_of(rb), ix->loci, ix->first_idx, o, r_lo, r_ncand, off, P->pool, r_idx, r_len, d_stats);
+        else LAUNCH(ctx, pileup_call_k, grid_for(n, 256), 256, 0, view_of(rb), ix->loci, ix->first_idx, o, r_lo, r_ncand, off, P->pool, r_idx, r_len, d_stats, d_mbias);
         LAUNCH(ctx, merge_templates_k, grid_for(n, 256), 256, 0, n, rb.status, mate, o, r_idx, r_len, off, P->pool, t_idx, t_len, t_off, t_valid, d_stats);
     }
     if ((rc = scan_u32_u32(ctx, t_valid, dst, n)) < 0) { wgbs_pats_free(ctx, P); return rc; }
@@ -286,6 +312,7 @@ extern "C" int wgbs_pileup_sam(wgbs_ctx *ctx, const wgbs_index *ix, const char *
         (rc = dalloc(ctx, &P->off, (size_t)n_out + 1)) < 0) { wgbs_pats_free(ctx, P); return rc; }
     if (n) LAUNCH(ctx, compact_templates_k, grid_for(n, 256), 256, 0, n, t_valid, dst, t_idx, t_len, t_off, P->idx, P->len, P->off, P->count);
     LAUNCH_CHECK();
+    if (mbias_out && d_mbias != mbias_out) { if ((rc = copy_any(ctx, mbias_out, d_mbias, 8000 * sizeof(int32_t))) < 0) { wgbs_pats_free(ctx, P); return rc; } }
     if (stats_out) {
         stats_out[0] = n;                       // lines (patter counts blank lines too)
         stats_out[1] = hstats[ST_PAIRS]; stats_out[2] = hstats[ST_EMPTY]; stats_out[3] = hstats[ST_SHORT];
