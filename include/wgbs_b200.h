@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define WGBS_B200_ABI_VERSION 1
+#define WGBS_B200_ABI_VERSION 2
 
 typedef struct wgbs_ctx wgbs_ctx;
 typedef struct wgbs_pats wgbs_pats;   /* device-resident pat records: (idx, len, count, 2-bit symbol pool) */
@@ -114,6 +114,7 @@ typedef struct wgbs_pileup_opts {
     int32_t combine_mods; /* --combine_mods */
     float np_thresh;      /* --np_thresh (float32, default 0.67) */
     char cpc_call;        /* --cpc_call 'C' | 'H' | '.' (0 = 'C') */
+    int32_t keep_names;   /* --long (main.cpp:37): keep every template's read name for wgbs_collapse_long / wgbs_pats_format_long */
 } wgbs_pileup_opts;
 
 /* sam: SAM text without header, one chromosome, coordinate sorted -- exactly what `samtools view BAM chr` feeds the
@@ -130,6 +131,11 @@ int wgbs_pileup_sam_mbias(wgbs_ctx *, const wgbs_index *, const char *sam, size_
                           wgbs_pats **out, uint64_t *stats, int32_t *mbias);
 /* sort by (idx, pattern) in the C locale and merge identical records, summing counts (in place) */
 int wgbs_collapse(wgbs_ctx *, wgbs_pats *);
+/* --long variant (reference bam2pat.py:102-103: `sort -k2,2n -k3,3 | awk '{print $1,$2,$3,1,$4}'`, no uniq): records are only
+ * ordered -- by (idx, pattern, read name), the read name being what `sort`'s last-resort whole-line comparison sees -- and
+ * wgbs_pats_format_long writes "chrom \t idx \t pattern \t 1 \t qname \n".  Needs opts.keep_names. */
+int wgbs_collapse_long(wgbs_ctx *, wgbs_pats *);
+int wgbs_pats_format_long(wgbs_ctx *, const wgbs_pats *, const char *chrom, char *out, size_t cap, size_t *nbytes);
 /* "chrom \t idx \t pattern \t count \n" per record, record order.  out NULL: only *nbytes. out: host or device. */
 int wgbs_pats_format(wgbs_ctx *, const wgbs_pats *, const char *chrom, char *out, size_t cap, size_t *nbytes);
 /* utility: stable radix sort of (key, value) uint32 pairs, device pointers */

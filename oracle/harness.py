@@ -43,7 +43,7 @@ def tool(name: str, opt: bool = False) -> str:
 
 def ref_patter(sam: bytes, dict_path: str, region: str, paired: bool, min_cpg: int = 1, clip: int = 0,
                nanopore: bool = False, np_thresh: float | None = None, cpc_call: str | None = None,
-               combine_mods: bool = False, opt: bool = False, mbias: str | None = None):
+               combine_mods: bool = False, opt: bool = False, mbias: str | None = None, long: bool = False):
     """`[match_maker |] patter DICT REGION ...`  (reference bam2pat.py:186-204). returns (stdout, stderr)."""
     cmd = ""
     if paired:
@@ -59,6 +59,8 @@ def ref_patter(sam: bytes, dict_path: str, region: str, paired: bool, min_cpg: i
         cmd += " --combine_mods"
     if mbias:
         cmd += f" --mbias {mbias}"
+    if long:
+        cmd += " --long"
     p = subprocess.run(cmd, shell=True, input=sam, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=_env())
     return p.stdout, p.stderr
 
@@ -75,6 +77,12 @@ def read_mbias(prefix: str) -> np.ndarray:
 def ref_collapse(txt: bytes) -> bytes:
     """reference bam2pat.py:99-106 (without bgzip)."""
     cmd = "sort -k2,2n -k3,3 | uniq -c | awk -v OFS='\\t' '{print $2,$3,$4,$1}'"
+    return subprocess.run(cmd, shell=True, input=txt, stdout=subprocess.PIPE, env=_env(), check=True).stdout
+
+
+def ref_collapse_long(txt: bytes) -> bytes:
+    """reference bam2pat.py:102-103 (--long), without bgzip"""
+    cmd = "sort -k2,2n -k3,3 | awk -v OFS='\\t' '{print $1,$2,$3,1,$4}'"
     return subprocess.run(cmd, shell=True, input=txt, stdout=subprocess.PIPE, env=_env(), check=True).stdout
 
 

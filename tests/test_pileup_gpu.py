@@ -303,3 +303,25 @@ def test_mbias_tables_match_patter(ctx, oracle, genome, paired, tmp_path):
     P.free(); ix.free()
     np.testing.assert_array_equal(st["mbias"], exp)
     assert exp.sum() > 5000
+
+
+@pytest.mark.parametrize("paired", [True, False])
+def test_long_format_matches_reference(ctx, oracle, genome, paired):
+    """--long: `patter --long | sort -k2,2n -k3,3 | awk '{print $1,$2,$3,1,$4}'` (bam2pat.py:102-103): one line per template
+    with its read name, ordered by (idx, pattern, then the whole line = the read name)"""
+    H = oracle
+    if not H.have_ref():
+        pytest.skip("needs the reference patter executable")
+    # a tiny chromosome: many templates share (idx, pattern), so the order is decided by the read names ("q7" < "q70" < "q8")
+    g = synth.make_genome(5, "chrT", 40_000)
+    sam = synth.make_sam(g, 6000, 91, paired=paired, name_prefix="q")
+    d = H.write_tmp(g.dict_text(), ".CpG.bed")
+    out, _ = H.ref_patter(sam, d, g.chrom, paired, long=True)
+    exp = H.ref_collapse_long(out)
+    ix = ctx.load_index(g.loci, g.first_idx)
+    P, st = ctx.pileup_sam(ix, sam, keep_names=True)
+    P.collapse(long=True)
+    got = P.to_text(g.chrom, long=True)
+    # the same object still serves the beta path
+    assert got == exp and got.count(b"\n") == st["templates"]
+    P.free(); ix.free()

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libwgbs_b200.so")
 class PileupOpts(C.Structure):
     """mirror of wgbs_pileup_opts (include/wgbs_b200.h)"""
     _fields_ = [("min_cpg", C.c_int32), ("clip", C.c_int32), ("paired", C.c_int32), ("nanopore", C.c_int32),
-                ("combine_mods", C.c_int32), ("np_thresh", C.c_float), ("cpc_call", C.c_char)]
+                ("combine_mods", C.c_int32), ("np_thresh", C.c_float), ("cpc_call", C.c_char), ("keep_names", C.c_int32)]
 
 
 class WgbsError(RuntimeError):
@@ -53,6 +53,8 @@ def _load():
         "wgbs_pileup_sam": (C.c_int, [vp, vp, vp, sz, vp, C.POINTER(vp), vp]),
         "wgbs_pileup_sam_mbias": (C.c_int, [vp, vp, vp, sz, vp, C.POINTER(vp), vp, vp]),
         "wgbs_collapse": (C.c_int, [vp, vp]),
+        "wgbs_collapse_long": (C.c_int, [vp, vp]),
+        "wgbs_pats_format_long": (C.c_int, [vp, vp, C.c_char_p, vp, sz, C.POINTER(sz)]),
         "wgbs_pats_format": (C.c_int, [vp, vp, C.c_char_p, vp, sz, C.POINTER(sz)]),
         "wgbs_sort_pairs_u32": (C.c_int, [vp, vp, vp, sz]),
         "wgbs_segment": (C.c_int, [vp, vp, C.c_int, vp, sz, vp, C.c_int, C.c_int, u32, C.c_float, vp, vp]),

@@ -86,21 +86,23 @@ class Pats:
             out.append(lut[sym].tobytes())
         return out
 
-    def collapse(self) -> "Pats":
-        """sort -k2,2n -k3,3 | uniq -c (in place)"""
-        check(lib.wgbs_collapse(self.ctx.h, self.h))
+    def collapse(self, long: bool = False) -> "Pats":
+        """sort -k2,2n -k3,3 | uniq -c (in place); long=True: only sort (by idx, pattern, read name), no uniq (--long)"""
+        check((lib.wgbs_collapse_long if long else lib.wgbs_collapse)(self.ctx.h, self.h))
         return self
 
-    def to_text(self, chrom: str, out=None):
-        """pat text.  out: optional preallocated host uint8 array or DevBuf (then the number of bytes is returned)."""
+    def to_text(self, chrom: str, out=None, long: bool = False):
+        """pat text.  out: optional preallocated host uint8 array or DevBuf (then the number of bytes is returned).
+        long=True: `chr idx pattern 1 qname` lines (--long)."""
+        fmt = lib.wgbs_pats_format_long if long else lib.wgbs_pats_format
         n = C.c_size_t()
         if out is None:
-            check(lib.wgbs_pats_format(self.ctx.h, self.h, chrom.encode(), None, 0, C.byref(n)))
+            check(fmt(self.ctx.h, self.h, chrom.encode(), None, 0, C.byref(n)))
             buf = np.empty(max(n.value, 1), np.uint8)
-            check(lib.wgbs_pats_format(self.ctx.h, self.h, chrom.encode(), buf.ctypes.data, n.value, C.byref(n)))
+            check(fmt(self.ctx.h, self.h, chrom.encode(), buf.ctypes.data, n.value, C.byref(n)))
             return buf[:n.value].tobytes()
         cap = out.nbytes
-        check(lib.wgbs_pats_format(self.ctx.h, self.h, chrom.encode(), _addr(out), cap, C.byref(n)))
+        check(fmt(self.ctx.h, self.h, chrom.encode(), _addr(out), cap, C.byref(n)))
         return n.value
 
     def free(self):
@@ -187,7 +189,7 @@ class Context:
 
     def pileup_sam(self, index: "Index", sam, min_cpg: int = 1, clip: int = 0, paired: int = -1, nanopore: bool = False,
                    np_thresh: float = 0.67, cpc_call: str = "C", combine_mods: bool = False, nbytes: int | None = None,
-                   mbias: bool = False):
+                   mbias: bool = False, keep_names: bool = False):
         """SAM text (bytes or DevBuf) -> (Pats of templates, stats dict).  The reference's
         `samtools view ... | [match_maker |] patter DICT REGION ...` for one chromosome."""
         if isinstance(sam, DevBuf):
@@ -195,7 +197,7 @@ class Context:
         else:
             a = np.frombuffer(sam, np.uint8)
             p, n = a.ctypes.data, a.size
-        o = PileupOpts(min_cpg, clip, paired, int(nanopore), int(combine_mods), np_thresh, cpc_call.encode())
+        o = PileupOpts(min_cpg, clip, paired, int(nanopore), int(combine_mods), np_thresh, cpc_call.encode(), int(keep_names))
         h = C.c_void_p(); st = (C.c_uint64 * 8)()
         mb = np.zeros((2, 2, 1000, 2), np.int32) if mbias else None
         check(lib.wgbs_pileup_sam_mbias(self.h, index.h, p, n, C.addressof(o), C.byref(h), C.addressof(st), mb.ctypes.data if mbias else None))

@@ -49,11 +49,12 @@ def proc_chr(ctx, ref, chrom: str, sam: bytes, args, mc_buf):
     loci, first = ref.chrom_loci(chrom)
     ix = ctx.load_index(loci, first)
     P, st = ctx.pileup_sam(ix, sam, min_cpg=args.min_cpg, clip=args.clip, paired=-1, nanopore=args.nanopore,
-                           np_thresh=args.np_thresh, cpc_call=args.cpc_call, combine_mods=args.combine_mods, mbias=args.mbias)
+                           np_thresh=args.np_thresh, cpc_call=args.cpc_call, combine_mods=args.combine_mods, mbias=args.mbias,
+                           keep_names=args.long)
     if mc_buf is not None:
         ctx.pat2beta(P, 1, ref.nr_sites + 1, meth_cov=mc_buf, zero_first=False)
-    P.collapse()
-    txt = P.to_text(chrom)
+    P.collapse(long=args.long)                          # --long: `sort | awk '{print $1,$2,$3,1,$4}'`, no uniq (bam2pat.py:102-103)
+    txt = P.to_text(chrom, long=args.long)
     P.free(); ix.free()
     pe = f"({st['pairs']:,} pairs). " if st["paired"] else ""
     good = st["lines"] - st["empty"] - st["invalid"]
@@ -76,6 +77,7 @@ def main(argv=None):
     p.add_argument("--out_dir", "-o", default="."); p.add_argument("--min_cpg", type=int, default=1)
     p.add_argument("--force", "-f", action="store_true"); p.add_argument("--verbose", "-v", action="store_true")
     p.add_argument("--clip", type=int, default=0); p.add_argument("-@", "--threads", type=int, default=8)
+    p.add_argument("--long", action="store_true", help="Use long format for pat file (add read name to each line)")
     p.add_argument("--no_beta", action="store_true"); p.add_argument("-l", "--lbeta", action="store_true")
     p.add_argument("--nanopore", "-np", action="store_true"); p.add_argument("--cpc_call", default="C", choices=["C", "H", "."])
     p.add_argument("--np_thresh", type=float, default=0.67); p.add_argument("--combine_mods", action="store_true")

@@ -46,21 +46,40 @@ __device__ __forceinline__ int pat_cmp(const PatsView &P, uint32_t a, uint32_t b
     }
     return 0;
 }
-__global__ void __launch_bounds__(128) fix_ties_k(PatsView P, uint32_t *__restrict__ perm, const uint32_t *__restrict__ key /*sorted*/, uint32_t nsym) {
+// --long: `sort`'s last-resort comparison sees the whole line "chr \t idx \t pattern \t qname": after idx and pattern, the read name
+__device__ __forceinline__ int name_cmp(const PatsView &P, uint32_t a, uint32_t b) {
+    const unsigned char *x = (const unsigned char *)P.names + P.name_off[a], *y = (const unsigned char *)P.names + P.name_off[b];
+    const uint32_t la = P.name_len[a], lb = P.name_len[b], m = min(la, lb);
+    for (uint32_t k = 0; k < m; k++) if (x[k] != y[k]) return x[k] < y[k] ? -1 : 1;
+    return la < lb ? -1 : (la > lb ? 1 : 0);
+}
+__global__ void __launch_bounds__(128) fix_ties_k(PatsView P, uint32_t *__restrict__ perm, const uint32_t *__restrict__ key /*sorted*/, uint32_t nsym, int by_name) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
     const uint32_t k0 = key[i];
     if (i > 0 && key[i - 1] == k0) return;                          // only the first position of a run works
     size_t j = i + 1; bool any_long = P.len[perm[i]] > nsym;
     while (j < P.n && key[j] == k0) { any_long |= P.len[perm[j]] > nsym; j++; }
-    if (!any_long || j - i < 2) return;
+    if ((!any_long && !by_name) || j - i < 2) return;
     for (size_t k = i + 1; k < j; k++) {
         const uint32_t v = perm[k]; size_t q = k;
-        while (q > i && pat_cmp(P, perm[q - 1], v) > 0) { perm[q] = perm[q - 1]; q--; }
+        while (q > i) {
+            int c = pat_cmp(P, perm[q - 1], v);
+            if (c == 0 && by_name) c = name_cmp(P, perm[q - 1], v);
+            if (c <= 0) break;
+            perm[q] = perm[q - 1]; q--;
+        }
         perm[q] = v;
     }
 }
-
+__global__ void __launch_bounds__(256) permute_long_k(PatsView P, const uint32_t *__restrict__ perm, uint32_t *__restrict__ o_idx, uint32_t *__restrict__ o_len,
+                                                       uint32_t *__restrict__ o_off, uint32_t *__restrict__ o_cnt, uint32_t *__restrict__ o_noff,
+                                                       uint32_t *__restrict__ o_nlen) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    const uint32_t r = perm[i];
+    o_idx[i] = P.idx[r]; o_len[i] = P.len[r]; o_off[i] = P.off[r]; o_cnt[i] = P.count[r]; o_noff[i] = P.name_off[r]; o_nlen[i] = P.name_len[r];
+}
 __device__ __forceinline__ bool same_rec(const PatsView &P, uint32_t a, uint32_t b) {
     if (P.idx[a] != P.idx[b] || P.len[a] != P.len[b]) return false;
     const uint32_t nw = (P.len[a] + 15) >> 4;
@@ -124,11 +143,39 @@ __global__ void __launch_bounds__(256) line_write_k(PatsView P, const char *__re
     *p++ = '\n';
 }
 
+__global__ void __launch_bounds__(256) line_len_long_k(PatsView P, uint32_t chrom_len, uint32_t *__restrict__ ll) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    ll[i] = chrom_len + 1 + ndigits_i32((int32_t)P.idx[i]) + 1 + P.len[i] + 1 + 1 + 1 + P.name_len[i] + 1;      // ... \t 1 \t qname \n
+}
+__global__ void __launch_bounds__(256) line_write_long_k(PatsView P, const char *__restrict__ chrom, uint32_t chrom_len,
+                                                          const uint64_t *__restrict__ loff, char *__restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    char *p = out + loff[i];
+    for (uint32_t k = 0; k < chrom_len; k++) *p++ = chrom[k];
+    *p++ = '\t';
+    p = put_i32(p, (int32_t)P.idx[i]);
+    *p++ = '\t';
+    const uint32_t L = P.len[i];
+    const uint32_t *wp = P.pool + P.off[i];
+    for (uint32_t b = 0; b < L; b += 16) {
+        uint32_t w = *wp++, m = min(16u, L - b);
+        for (uint32_t k = 0; k < m; k++) *p++ = sym_char((w >> (30 - 2 * k)) & 3u);
+    }
+    *p++ = '\t'; *p++ = '1'; *p++ = '\t';
+    const char *nm = P.names + P.name_off[i];
+    for (uint32_t k = 0; k < P.name_len[i]; k++) *p++ = nm[k];
+    *p++ = '\n';
+}
+
+
 }  // namespace
 
-extern "C" int wgbs_collapse(wgbs_ctx *ctx, wgbs_pats *P) {
+static int collapse_impl(wgbs_ctx *ctx, wgbs_pats *P, bool long_mode) {
     RC_TRY(wgbs_ctx_activate(ctx));
     if (!P) return wgbs_set_err("null pats");
+    if (long_mode && P->n && !P->names) return wgbs_set_err("wgbs_collapse_long: records carry no read names (set opts.keep_names in the pileup)");
     const size_t n = P->n;
     if (n < 1) return 0;
     if (n >= 0xffffffffull) return wgbs_set_err("wgbs_collapse: too many records");
@@ -147,7 +194,19 @@ extern "C" int wgbs_collapse(wgbs_ctx *ctx, wgbs_pats *P) {
     const uint32_t nsym = (32 - ibits) / 2 > 16 ? 16 : (32 - ibits) / 2;
     LAUNCH(ctx, make_key_k, grid_for(n, 256), 256, 0, pv, mm[0], nsym, k, v);
     RC_TRY(radix_sort_pairs(ctx, &k, &v, &ka, &va, n));
-    LAUNCH(ctx, fix_ties_k, grid_for(n, 128), 128, 0, pv, v, k, nsym);          // longer patterns: order inside equal-key runs
+    LAUNCH(ctx, fix_ties_k, grid_for(n, 128), 128, 0, pv, v, k, nsym, long_mode ? 1 : 0);   // longer patterns (and names): order inside equal-key runs
+    if (long_mode) {
+        // no uniq in --long: the records are only re-ordered
+        uint32_t *o_idx, *o_len, *o_off, *o_cnt, *o_noff, *o_nlen;
+        int rc2;
+        if ((rc2 = dalloc(ctx, &o_idx, n)) < 0 || (rc2 = dalloc(ctx, &o_len, n)) < 0 || (rc2 = dalloc(ctx, &o_off, n + 1)) < 0 || (rc2 = dalloc(ctx, &o_cnt, n)) < 0 ||
+            (rc2 = dalloc(ctx, &o_noff, n + 1)) < 0 || (rc2 = dalloc(ctx, &o_nlen, n)) < 0) return rc2;
+        LAUNCH(ctx, permute_long_k, grid_for(n, 256), 256, 0, pv, v, o_idx, o_len, o_off, o_cnt, o_noff, o_nlen);
+        LAUNCH_CHECK();
+        dfree(ctx, P->idx); dfree(ctx, P->len); dfree(ctx, P->off); dfree(ctx, P->count); dfree(ctx, P->name_off); dfree(ctx, P->name_len);
+        P->idx = o_idx; P->len = o_len; P->off = o_off; P->count = o_cnt; P->name_off = o_noff; P->name_len = o_nlen;
+        return 0;
+    }
     // run-length: heads, destinations, counts
     uint32_t *head, *dst;
     RC_TRY(T.alloc(&head, n)); RC_TRY(T.alloc(&dst, n + 1));
@@ -168,6 +227,9 @@ extern "C" int wgbs_collapse(wgbs_ctx *ctx, wgbs_pats *P) {
     P->idx = o_idx; P->len = o_len; P->off = o_off; P->count = o_cnt; P->n = nu;
     return 0;
 }
+
+extern "C" int wgbs_collapse(wgbs_ctx *ctx, wgbs_pats *P) { return collapse_impl(ctx, P, false); }
+extern "C" int wgbs_collapse_long(wgbs_ctx *ctx, wgbs_pats *P) { return collapse_impl(ctx, P, true); }
 
 // Write "chrom \t idx \t pattern \t count \n" per record, in record order (reference docs/pat_format.md:3-47).
 // out == NULL: only *nbytes is computed.  out may be host or device.
@@ -192,6 +254,32 @@ extern "C" int wgbs_pats_format(wgbs_ctx *ctx, const wgbs_pats *P, const char *c
     char *dout = out;
     if (!is_device_ptr(out)) RC_TRY(T.alloc(&dout, (size_t)total));
     if (n) { LAUNCH(ctx, line_write_k, grid_for(n, 256), 256, 0, view_of(P), dchrom, cl, loff, dout); LAUNCH_CHECK(); }
+    if (dout != out) RC_TRY(copy_any(ctx, out, dout, (size_t)total));
+    return 0;
+}
+
+extern "C" int wgbs_pats_format_long(wgbs_ctx *ctx, const wgbs_pats *P, const char *chrom, char *out, size_t cap, size_t *nbytes) {
+    RC_TRY(wgbs_ctx_activate(ctx));
+    if (!P || !chrom) return wgbs_set_err("wgbs_pats_format_long: null argument");
+    const size_t n = P->n;
+    if (n && !P->names) return wgbs_set_err("wgbs_pats_format_long: records carry no read names (set opts.keep_names in the pileup)");
+    const uint32_t cl = (uint32_t)strlen(chrom);
+    Temps T(ctx);
+    uint32_t *ll; uint64_t *loff;
+    RC_TRY(T.alloc(&ll, n)); RC_TRY(T.alloc(&loff, n + 1));
+    if (n) LAUNCH(ctx, line_len_long_k, grid_for(n, 256), 256, 0, view_of(P), cl, ll);
+    RC_TRY(scan_u32_u64(ctx, ll, loff, n));
+    uint64_t total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, loff + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (nbytes) *nbytes = (size_t)total;
+    if (!out) return 0;
+    if (cap < total) return wgbs_set_err("wgbs_pats_format_long: buffer too small (%zu < %llu)", cap, (unsigned long long)total);
+    char *dchrom; RC_TRY(T.alloc(&dchrom, (size_t)cl + 1));
+    RC_TRY(copy_any(ctx, dchrom, chrom, cl + 1));
+    char *dout = out;
+    if (!is_device_ptr(out)) RC_TRY(T.alloc(&dout, (size_t)total));
+    if (n) { LAUNCH(ctx, line_write_long_k, grid_for(n, 256), 256, 0, view_of(P), dchrom, cl, loff, dout); LAUNCH_CHECK(); }
     if (dout != out) RC_TRY(copy_any(ctx, out, dout, (size_t)total));
     return 0;
 }

@@ -260,6 +260,7 @@ extern "C" void wgbs_pats_free(wgbs_ctx *ctx, wgbs_pats *P) {
     if (!P || !ctx) return;
     cudaSetDevice(ctx->device);
     dfree(ctx, P->idx); dfree(ctx, P->len); dfree(ctx, P->count); dfree(ctx, P->off); dfree(ctx, P->pool);
+    dfree(ctx, P->name_off); dfree(ctx, P->name_len); dfree(ctx, P->names);
     delete P;
 }
 

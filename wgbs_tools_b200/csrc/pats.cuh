@@ -12,13 +12,17 @@ struct wgbs_pats {
     uint32_t *count = nullptr;  // multiplicity (int32 semantics)
     uint32_t *off = nullptr;    // n+1 word offsets into pool
     uint32_t *pool = nullptr;   // 16 two-bit symbols per word, first symbol in bits 31:30
+    // --long only: read name of every record (patter --long prints it as a 4th column)
+    uint32_t *name_off = nullptr, *name_len = nullptr;
+    char *names = nullptr; size_t names_bytes = 0;
 };
 
 struct PatsView {
     size_t n;
     const uint32_t *idx, *len, *count, *off, *pool;
+    const uint32_t *name_off, *name_len; const char *names;    // null unless --long
 };
-static inline PatsView view_of(const wgbs_pats *P) { return PatsView{P->n, P->idx, P->len, P->count, P->off, P->pool}; }
+static inline PatsView view_of(const wgbs_pats *P) { return PatsView{P->n, P->idx, P->len, P->count, P->off, P->pool, P->name_off, P->name_len, P->names}; }
 
 // ASCII -> 2-bit code; anything that is not C/H/T is "unknown" ('.'), which is how every consumer in the reference
 // treats it (stdin2beta.cpp:82-84, homog.cpp:158-163).

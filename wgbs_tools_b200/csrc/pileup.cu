@@ -187,6 +187,20 @@ __global__ void __launch_bounds__(256) merge_templates_k(uint32_t n, const uint8
     if ((threadIdx.x & 31) == 0 && nshort) atomicAdd(&stats[ST_SHORT], (unsigned long long)nshort);
 }
 
+// --long: template k keeps the QNAME of its head record (tokens1[0] in patter.cpp:274-276; both mates share it)
+__global__ void __launch_bounds__(256) name_len_k(uint32_t n, const uint32_t *__restrict__ t_valid, const uint32_t *__restrict__ dst,
+                                                   const uint32_t *__restrict__ qn_len, uint32_t *__restrict__ o_len) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n && t_valid[r]) o_len[dst[r]] = qn_len[r];
+}
+__global__ void __launch_bounds__(256) name_copy_k(uint32_t n, const uint32_t *__restrict__ t_valid, const uint32_t *__restrict__ dst, ReadBatchView rb,
+                                                    const uint32_t *__restrict__ o_off, char *__restrict__ names) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n || !t_valid[r]) return;
+    const char *src = rb.text + rb.line_off[r]; char *d = names + o_off[dst[r]];
+    for (uint32_t k = 0; k < rb.qn_len[r]; k++) d[k] = src[k];
+}
+
 __global__ void __launch_bounds__(256) compact_templates_k(uint32_t n, const uint32_t *__restrict__ t_valid, const uint32_t *__restrict__ dst,
                                                             const uint32_t *__restrict__ t_idx, const uint32_t *__restrict__ t_len,
                                                             const uint32_t *__restrict__ t_off, uint32_t *__restrict__ o_idx,
@@ -311,6 +325,19 @@ extern "C" int wgbs_pileup_sam_mbias(wgbs_ctx *ctx, const wgbs_index *ix, const 
     if ((rc = dalloc(ctx, &P->idx, n_out)) < 0 || (rc = dalloc(ctx, &P->len, n_out)) < 0 || (rc = dalloc(ctx, &P->count, n_out)) < 0 ||
         (rc = dalloc(ctx, &P->off, (size_t)n_out + 1)) < 0) { wgbs_pats_free(ctx, P); return rc; }
     if (n) LAUNCH(ctx, compact_templates_k, grid_for(n, 256), 256, 0, n, t_valid, dst, t_idx, t_len, t_off, P->idx, P->len, P->off, P->count);
+    if (opts->keep_names && n_out) {
+        uint32_t *nl_tmp;
+        if ((rc = dalloc(ctx, &P->name_len, n_out)) < 0 || (rc = dalloc(ctx, &P->name_off, (size_t)n_out + 1)) < 0) { wgbs_pats_free(ctx, P); return rc; }
+        (void)nl_tmp;
+        LAUNCH(ctx, name_len_k, grid_for(n, 256), 256, 0, n, t_valid, dst, rb.qn_len, P->name_len);
+        if ((rc = scan_u32_u32(ctx, P->name_len, P->name_off, n_out)) < 0) { wgbs_pats_free(ctx, P); return rc; }
+        uint32_t nb = 0;
+        CUDA_TRY(cudaMemcpyAsync(&nb, P->name_off + n_out, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if ((rc = dalloc(ctx, &P->names, nb)) < 0) { wgbs_pats_free(ctx, P); return rc; }
+        P->names_bytes = nb;
+        LAUNCH(ctx, name_copy_k, grid_for(n, 256), 256, 0, n, t_valid, dst, view_of(rb), P->name_off, P->names);
+    }
     LAUNCH_CHECK();
     if (mbias_out && d_mbias != mbias_out) { if ((rc = copy_any(ctx, mbias_out, d_mbias, 8000 * sizeof(int32_t))) < 0) { wgbs_pats_free(ctx, P); return rc; } }
     if (stats_out) {
