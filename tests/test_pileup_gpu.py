@@ -325,3 +325,17 @@ def test_long_format_matches_reference(ctx, oracle, genome, paired):
     # the same object still serves the beta path
     assert got == exp and got.count(b"\n") == st["templates"]
     P.free(); ix.free()
+
+
+@pytest.mark.parametrize("bits", [4, 12])
+def test_pairing_survives_hash_collisions(ctx, oracle, genome, monkeypatch, bits):
+    """WGBS_PAIR_HASH_BITS truncates the QNAME hash (test hook): every slot overflows, so all mates are found on the
+    crowded-slot path (sort by hash, whole-line order, greedy pairing by name) -- same output as without collisions"""
+    H = oracle
+    sam = synth.make_sam(genome, 6_000, 33, paired=True, single_frac=0.1)
+    ref_raw, ref_txt = _oracle_pat(H, genome, sam, True)
+    monkeypatch.setenv("WGBS_PAIR_HASH_BITS", str(bits))
+    raw, txt, st = _gpu_pat(ctx, genome, sam)
+    assert txt == ref_txt
+    _, pst = H.port_patter(H.port_match_maker(sam), genome.loci, genome.idx())
+    assert [st[k] for k in ("lines", "pairs", "empty", "short", "invalid", "paired")] == pst

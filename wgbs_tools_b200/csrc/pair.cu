@@ -4,13 +4,17 @@
 // (pipeline_wgbs/patter.cpp:395-412).  match_maker sorts buffered SAM lines as whole strings, pairs adjacent lines
 // with equal QNAME greedily and lets everything else through as singles; for a coordinate-sorted single-chromosome
 // stream with consistent PNEXT that is exactly "group records by QNAME; within a group, in whole-line order, pair
-// greedily".  Here: sort record ids by the QNAME hash (one stable 32-bit radix sort), then one thread per
-// hash run: runs of 1 are singles, runs of 2 with byte-equal names are a pair, anything else (3+ records, or a hash
-// collision) is ordered by whole-line bytes by that thread and paired greedily.  (Only the low 32 hash bits are sorted
-// on; names are always compared byte for byte, so collisions cost time, never correctness.)
+// greedily".  Here: every record drops its 32-bit QNAME hash into an open-addressing table in global memory (L2-resident:
+// 16 B per slot, load <= 0.5) with atomicCAS and adds itself to the slot's (count, min id, max id).  A slot with exactly two
+// records whose names are byte-equal is a pair -- the common case, settled without any sort.  Records in slots holding 3+
+// records (supplementary alignments sharing a QNAME, or 32-bit collisions) are rare: they are gathered, radix-sorted by
+// hash, and each equal-hash run is ordered by whole-line bytes and paired greedily by one thread (pair_runs_k).  Names are
+// always compared byte for byte, so hash collisions cost time, never correctness.
 //
 // Output: mate[r] = record id of r's mate or NONE.  The template's slot is the smaller record id of the two, so
 // templates stay in coordinate order.
+#include <stdlib.h>
+
 #include "reads.cuh"
 #include "sort.cuh"
 
@@ -22,6 +26,26 @@ __global__ void __launch_bounds__(256) fill_u32_k(uint32_t *p, size_t n, uint32_
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
+struct Slot { uint32_t key, cnt, mn, mx; };
+constexpr uint32_t EMPTY = 0xffffffffu;
+
+__global__ void __launch_bounds__(256) slots_init_k(Slot *__restrict__ tab, size_t nslots) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nslots) { Slot s; s.key = EMPTY; s.cnt = 0; s.mn = EMPTY; s.mx = 0; tab[i] = s; }
+}
+__global__ void __launch_bounds__(256) pair_insert_k(ReadBatchView rb, Slot *__restrict__ tab, uint32_t mask, uint32_t hash_mask, uint32_t *__restrict__ slot_of) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rb.n) return;
+    if (rb.status[r] == REC_BLANK) { slot_of[r] = EMPTY; return; }
+    uint32_t h = rb.hash_lo[r] & hash_mask; if (h == EMPTY) h = 0xfffffffeu;
+    uint32_t s = (h * 0x9e3779b1u) & mask;
+    while (true) {
+        const uint32_t old = atomicCAS(&tab[s].key, EMPTY, h);
+        if (old == EMPTY || old == h) { atomicAdd(&tab[s].cnt, 1u); atomicMin(&tab[s].mn, r); atomicMax(&tab[s].mx, r); slot_of[r] = s; return; }
+        s = (s + 1) & mask;
+    }
+}
+
 // whole-line comparison, std::string operator< semantics (unsigned bytes, shorter prefix first)
 __device__ int line_cmp(const ReadBatchView &rb, uint32_t a, uint32_t b) {
     const unsigned char *x = (const unsigned char *)rb.text + rb.line_off[a], *y = (const unsigned char *)rb.text + rb.line_off[b];
@@ -71,6 +95,26 @@ __global__ void __launch_bounds__(256) pair_runs_k(ReadBatchView rb, uint32_t *_
     if ((threadIdx.x & 31) == 0 && npairs) atomicAdd(&stats[ST_PAIRS], (unsigned long long)npairs);
 }
 
+// one thread per record: slots of two byte-equal names are pairs; members of fuller slots go to the slow list
+__global__ void __launch_bounds__(256) pair_resolve_k(ReadBatchView rb, const Slot *__restrict__ tab, const uint32_t *__restrict__ slot_of,
+                                                       uint32_t hash_mask, uint32_t *__restrict__ mate, uint32_t *__restrict__ slow_key,
+                                                       uint32_t *__restrict__ slow_id, uint32_t *__restrict__ n_slow,
+                                                       unsigned long long *__restrict__ stats) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t npairs = 0;
+    if (r < rb.n && slot_of[r] != EMPTY) {
+        const Slot s = tab[slot_of[r]];
+        if (s.cnt == 2) {
+            if (r == s.mn && name_eq(rb, s.mn, s.mx)) { mate[s.mn] = s.mx; mate[s.mx] = s.mn; npairs = 1; }
+        } else if (s.cnt > 2) {
+            const uint32_t k = atomicAdd(n_slow, 1u);
+            slow_key[k] = rb.hash_lo[r] & hash_mask; slow_id[k] = r;
+        }
+    }
+    for (int d = 16; d >= 1; d >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, d);
+    if ((threadIdx.x & 31) == 0 && npairs) atomicAdd(&stats[ST_PAIRS], (unsigned long long)npairs);
+}
+
 }  // namespace
 
 int build_mates(wgbs_ctx *ctx, const ReadBatch &rb, bool paired, Temps &T, uint32_t **mate_out, unsigned long long *d_stats) {
@@ -80,15 +124,27 @@ int build_mates(wgbs_ctx *ctx, const ReadBatch &rb, bool paired, Temps &T, uint3
     if (n) LAUNCH(ctx, fill_u32_k, grid_for(n, 256), 256, 0, mate, (size_t)n, NONE);
     *mate_out = mate;
     if (!paired || n < 2) { LAUNCH_CHECK(); return 0; }
-    // sort record ids by the LOW 32 bits of the QNAME hash only (4 digit passes): equal-key runs then hold the mates plus
-    // the occasional 32-bit collision, which pair_runs_k separates by comparing the name bytes themselves.
-    uint32_t *k0, *v0, *k1, *v1;
-    RC_TRY(T.alloc(&k0, n)); RC_TRY(T.alloc(&v0, n)); RC_TRY(T.alloc(&k1, n)); RC_TRY(T.alloc(&v1, n));
-    CUDA_TRY(cudaMemcpyAsync(k0, rb.hash_lo, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-    RC_TRY(fill_iota(ctx, v0, n));
-    uint32_t *k = k0, *v = v0, *ka = k1, *va = v1;
-    RC_TRY(radix_sort_pairs(ctx, &k, &v, &ka, &va, n));
-    LAUNCH(ctx, pair_runs_k, grid_for(n, 256), 256, 0, view_of(rb), v, k, n, mate, d_stats);
+    // hash table: slots = next power of two >= 2n
+    size_t nslots = 1; while (nslots < (size_t)n * 2) nslots <<= 1;
+    uint32_t hash_mask = 0xffffffffu;
+    if (const char *e = getenv("WGBS_PAIR_HASH_BITS")) { int b = atoi(e); if (b > 0 && b < 32) hash_mask = (1u << b) - 1; }   // test hook: force collisions
+    Slot *tab; uint32_t *slot_of, *slow_key, *slow_id, *n_slow = ctx->d_flags + 16;
+    RC_TRY(T.alloc(&tab, nslots)); RC_TRY(T.alloc(&slot_of, n)); RC_TRY(T.alloc(&slow_key, n)); RC_TRY(T.alloc(&slow_id, n));
+    CUDA_TRY(cudaMemsetAsync(n_slow, 0, 4, ctx->stream));
+    LAUNCH(ctx, slots_init_k, grid_for(nslots, 256), 256, 0, tab, nslots);
+    LAUNCH(ctx, pair_insert_k, grid_for(n, 256), 256, 0, view_of(rb), tab, (uint32_t)(nslots - 1), hash_mask, slot_of);
+    LAUNCH(ctx, pair_resolve_k, grid_for(n, 256), 256, 0, view_of(rb), tab, slot_of, hash_mask, mate, slow_key, slow_id, n_slow, d_stats);
+    uint32_t m = 0;
+    CUDA_TRY(cudaMemcpyAsync(&m, n_slow, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (m >= 2) {
+        // rare path: order the crowded slots' members by hash, then whole-line order + greedy pairing inside every equal-hash run
+        uint32_t *ka, *va;
+        RC_TRY(T.alloc(&ka, m)); RC_TRY(T.alloc(&va, m));
+        uint32_t *k = slow_key, *v = slow_id;
+        RC_TRY(radix_sort_pairs(ctx, &k, &v, &ka, &va, m));
+        LAUNCH(ctx, pair_runs_k, grid_for(m, 256), 256, 0, view_of(rb), v, k, m, mate, d_stats);
+    }
     LAUNCH_CHECK();
     return 0;
 }
