@@ -4,10 +4,10 @@
 // (pipeline_wgbs/patter.cpp:395-412).  match_maker sorts buffered SAM lines as whole strings, pairs adjacent lines
 // with equal QNAME greedily and lets everything else through as singles; for a coordinate-sorted single-chromosome
 // stream with consistent PNEXT that is exactly "group records by QNAME; within a group, in whole-line order, pair
-// greedily".  Here: every record drops its 32-bit QNAME hash into an open-addressing table in global memory (L2-resident:
-// 16 B per slot, load <= 0.5) with atomicCAS and adds itself to the slot's (count, min id, max id).  A slot with exactly two
+// greedily".  Here: every record drops its 64-bit QNAME hash into an open-addressing table in global memory (L2-resident:
+// 24 B per slot, load <= 0.5) with atomicCAS and adds itself to the slot's (count, min id, max id).  A slot with exactly two
 // records whose names are byte-equal is a pair -- the common case, settled without any sort.  Records in slots holding 3+
-// records (supplementary alignments sharing a QNAME, or 32-bit collisions) are rare: they are gathered, radix-sorted by
+// records (supplementary alignments sharing a QNAME, or the astronomically rare 64-bit collision) are rare: they are gathered, radix-sorted by
 // hash, and each equal-hash run is ordered by whole-line bytes and paired greedily by one thread (pair_runs_k).  Names are
 // always compared byte for byte, so hash collisions cost time, never correctness.
 //
@@ -26,22 +26,27 @@ __global__ void __launch_bounds__(256) fill_u32_k(uint32_t *p, size_t n, uint32_
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
-struct Slot { uint32_t key, cnt, mn, mx; };
+struct Slot { unsigned long long key; uint32_t cnt, mn, mx, pad; };
 constexpr uint32_t EMPTY = 0xffffffffu;
+constexpr unsigned long long EMPTY_KEY = ~0ull;
+__device__ __forceinline__ unsigned long long rec_key(const ReadBatchView &rb, uint32_t r, unsigned long long hash_mask) {
+    unsigned long long h = (((unsigned long long)rb.hash_hi[r] << 32) | rb.hash_lo[r]) & hash_mask;
+    return h == EMPTY_KEY ? EMPTY_KEY - 1 : h;
+}
 
 __global__ void __launch_bounds__(256) slots_init_k(Slot *__restrict__ tab, size_t nslots) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nslots) { Slot s; s.key = EMPTY; s.cnt = 0; s.mn = EMPTY; s.mx = 0; tab[i] = s; }
+    if (i < nslots) { Slot s; s.key = EMPTY_KEY; s.cnt = 0; s.mn = EMPTY; s.mx = 0; s.pad = 0; tab[i] = s; }
 }
-__global__ void __launch_bounds__(256) pair_insert_k(ReadBatchView rb, Slot *__restrict__ tab, uint32_t mask, uint32_t hash_mask, uint32_t *__restrict__ slot_of) {
+__global__ void __launch_bounds__(256) pair_insert_k(ReadBatchView rb, Slot *__restrict__ tab, uint32_t mask, unsigned long long hash_mask, uint32_t *__restrict__ slot_of) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rb.n) return;
     if (rb.status[r] == REC_BLANK) { slot_of[r] = EMPTY; return; }
-    uint32_t h = rb.hash_lo[r] & hash_mask; if (h == EMPTY) h = 0xfffffffeu;
-    uint32_t s = (h * 0x9e3779b1u) & mask;
+    const unsigned long long h = rec_key(rb, r, hash_mask);
+    uint32_t s = (uint32_t)((h * 0x9e3779b97f4a7c15ULL) >> 32) & mask;
     while (true) {
-        const uint32_t old = atomicCAS(&tab[s].key, EMPTY, h);
-        if (old == EMPTY || old == h) { atomicAdd(&tab[s].cnt, 1u); atomicMin(&tab[s].mn, r); atomicMax(&tab[s].mx, r); slot_of[r] = s; return; }
+        const unsigned long long old = atomicCAS(&tab[s].key, EMPTY_KEY, h);
+        if (old == EMPTY_KEY || old == h) { atomicAdd(&tab[s].cnt, 1u); atomicMin(&tab[s].mn, r); atomicMax(&tab[s].mx, r); slot_of[r] = s; return; }
         s = (s + 1) & mask;
     }
 }
@@ -97,7 +102,7 @@ __global__ void __launch_bounds__(256) pair_runs_k(ReadBatchView rb, uint32_t *_
 
 // one thread per record: slots of two byte-equal names are pairs; members of fuller slots go to the slow list
 __global__ void __launch_bounds__(256) pair_resolve_k(ReadBatchView rb, const Slot *__restrict__ tab, const uint32_t *__restrict__ slot_of,
-                                                       uint32_t hash_mask, uint32_t *__restrict__ mate, uint32_t *__restrict__ slow_key,
+                                                       unsigned long long hash_mask, uint32_t *__restrict__ mate, uint32_t *__restrict__ slow_key,
                                                        uint32_t *__restrict__ slow_id, uint32_t *__restrict__ n_slow,
                                                        unsigned long long *__restrict__ stats) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -108,7 +113,7 @@ __global__ void __launch_bounds__(256) pair_resolve_k(ReadBatchView rb, const Sl
             if (r == s.mn && name_eq(rb, s.mn, s.mx)) { mate[s.mn] = s.mx; mate[s.mx] = s.mn; npairs = 1; }
         } else if (s.cnt > 2) {
             const uint32_t k = atomicAdd(n_slow, 1u);
-            slow_key[k] = rb.hash_lo[r] & hash_mask; slow_id[k] = r;
+            slow_key[k] = slot_of[r]; slow_id[k] = r;                // the slot index identifies the 64-bit key uniquely
         }
     }
     for (int d = 16; d >= 1; d >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, d);
@@ -126,8 +131,8 @@ int build_mates(wgbs_ctx *ctx, const ReadBatch &rb, bool paired, Temps &T, uint3
     if (!paired || n < 2) { LAUNCH_CHECK(); return 0; }
     // hash table: slots = next power of two >= 2n
     size_t nslots = 1; while (nslots < (size_t)n * 2) nslots <<= 1;
-    uint32_t hash_mask = 0xffffffffu;
-    if (const char *e = getenv("WGBS_PAIR_HASH_BITS")) { int b = atoi(e); if (b > 0 && b < 32) hash_mask = (1u << b) - 1; }   // test hook: force collisions
+    unsigned long long hash_mask = ~0ull;
+    if (const char *e = getenv("WGBS_PAIR_HASH_BITS")) { int b = atoi(e); if (b > 0 && b < 64) hash_mask = (1ull << b) - 1; }   // test hook: force collisions
     Slot *tab; uint32_t *slot_of, *slow_key, *slow_id, *n_slow = ctx->d_flags + 16;
     RC_TRY(T.alloc(&tab, nslots)); RC_TRY(T.alloc(&slot_of, n)); RC_TRY(T.alloc(&slow_key, n)); RC_TRY(T.alloc(&slow_id, n));
     CUDA_TRY(cudaMemsetAsync(n_slow, 0, 4, ctx->stream));

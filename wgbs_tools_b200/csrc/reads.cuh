@@ -19,7 +19,7 @@ struct ReadBatch {
     uint32_t *qn_len = nullptr;
     int32_t *flag = nullptr, *pos = nullptr, *pos_hi = nullptr;   // POS is parsed as 64 bits (stoul): low word (as int) / high word
     uint32_t *cig_off = nullptr, *cig_len = nullptr, *seq_off = nullptr, *seq_len = nullptr;
-    uint32_t *hash_lo = nullptr;      // low 32 bits of the 64-bit QNAME hash (pairing sorts on these; names are byte-verified)
+    uint32_t *hash_lo = nullptr, *hash_hi = nullptr;   // 64-bit QNAME hash (pairing keys; names are still byte-verified)
     uint32_t *mm_off = nullptr, *mm_len = nullptr, *ml_off = nullptr, *ml_len = nullptr;  // MM:Z: / ML:B:C payloads (len 0: absent)
     uint8_t *status = nullptr;
 };
@@ -28,12 +28,12 @@ struct ReadBatchView {
     const char *text; uint32_t nbytes, n;
     const uint32_t *line_off, *line_len, *qn_len;
     const int32_t *flag, *pos, *pos_hi;
-    const uint32_t *cig_off, *cig_len, *seq_off, *seq_len, *hash_lo, *mm_off, *mm_len, *ml_off, *ml_len;
+    const uint32_t *cig_off, *cig_len, *seq_off, *seq_len, *hash_lo, *hash_hi, *mm_off, *mm_len, *ml_off, *ml_len;
     const uint8_t *status;
 };
 static inline ReadBatchView view_of(const ReadBatch &b) {
     return ReadBatchView{b.text, b.nbytes, b.n, b.line_off, b.line_len, b.qn_len, b.flag, b.pos, b.pos_hi, b.cig_off, b.cig_len, b.seq_off,
-                         b.seq_len, b.hash_lo, b.mm_off, b.mm_len, b.ml_off, b.ml_len, b.status};
+                         b.seq_len, b.hash_lo, b.hash_hi, b.mm_off, b.mm_len, b.ml_off, b.ml_len, b.status};
 }
 
 // CpG dictionary of one chromosome / region: sorted 1-based loci; CpG index of loci[k] is first_idx + k

@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(128) sam_lines_k(const char *__restrict__ text
     rb.line_off[line] = s; rb.line_len[line] = e - s; rb.qn_len[line] = qend - s;
     rb.flag[line] = flag; rb.pos[line] = (int32_t)(uint32_t)pos64; rb.pos_hi[line] = (int32_t)(uint32_t)(pos64 >> 32);
     rb.cig_off[line] = cig_off; rb.cig_len[line] = cig_len; rb.seq_off[line] = seq_off; rb.seq_len[line] = seq_len;
-    rb.hash_lo[line] = (uint32_t)h;
+    rb.hash_lo[line] = (uint32_t)h; rb.hash_hi[line] = (uint32_t)(h >> 32);
     rb.status[line] = st;
     if (want_tags) {
         uint32_t z = mm_off; if (mm_off) while (z < e && text[z] != '\t') z++;
@@ -259,7 +259,7 @@ int sam_tokenize(wgbs_ctx *ctx, const char *dtext, size_t nbytes, int want_tags 
     RC_TRY(T.alloc(&rb.flag, n_lines)); RC_TRY(T.alloc(&rb.pos, n_lines)); RC_TRY(T.alloc(&rb.pos_hi, n_lines));
     RC_TRY(T.alloc(&rb.cig_off, n_lines)); RC_TRY(T.alloc(&rb.cig_len, n_lines));
     RC_TRY(T.alloc(&rb.seq_off, n_lines)); RC_TRY(T.alloc(&rb.seq_len, n_lines));
-    RC_TRY(T.alloc(&rb.hash_lo, n_lines));
+    RC_TRY(T.alloc(&rb.hash_lo, n_lines)); RC_TRY(T.alloc(&rb.hash_hi, n_lines));
     RC_TRY(T.alloc(&rb.status, n_lines));
     if (tags) {
         RC_TRY(T.alloc(&rb.mm_off, n_lines)); RC_TRY(T.alloc(&rb.mm_len, n_lines));
