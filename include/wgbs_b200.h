@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define WGBS_B200_ABI_VERSION 2
+#define WGBS_B200_ABI_VERSION 3
 
 typedef struct wgbs_ctx wgbs_ctx;
 typedef struct wgbs_pats wgbs_pats;   /* device-resident pat records: (idx, len, count, 2-bit symbol pool) */
@@ -175,6 +175,25 @@ const char *wgbs_bam_header(const wgbs_bam *);
 uint64_t wgbs_bam_nrecords(const wgbs_bam *, int refid);
 int wgbs_bam_view(const wgbs_bam *, int refid, int min_mapq, int exclude_flags, int include_flags, int64_t beg, int64_t end,
                   char **text, size_t *nbytes, uint64_t *nrecords);
+
+/* The full `samtools view` stage of reference bam2pat.py:126-159, one pass over the decoded records:
+ *   samtools view BAM region -q Q -F X [-f Y] [| awk '($2 == A || $2 == B)'] [-r RG] [-M -L whitelist.bed]
+ *   [... -b | bedtools intersect -sorted -v -abam stdin -b blacklist.bed | samtools view]        [| head -N]
+ * Intervals are 0-based half-open [iv_beg, iv_end) on reference `refid`, sorted by start and non-overlapping (merge
+ * them first); a record is tested by its reference span POS..POS+span (span from the CIGAR, at least 1). */
+typedef struct wgbs_view_opts {
+    int refid;                  /* -1: every record */
+    int min_mapq, exclude_flags, include_flags;
+    int64_t beg, end;           /* 1-based closed region; end <= 0: whole reference */
+    int n_flag_eq;              /* 0..4: keep only records whose FLAG equals one of flag_eq[] (--top_strand / --bottom_strand) */
+    int flag_eq[4];
+    const char *read_group;     /* keep only records whose RG:Z: tag equals this (samtools view -r); NULL: no filter */
+    const int64_t *iv_beg, *iv_end;
+    size_t n_iv;                /* 0: no interval filter */
+    int iv_exclude;             /* 0: keep records overlapping an interval (-L); 1: keep records overlapping none (bedtools -v) */
+    uint64_t max_records;       /* 0: all; else only the first max_records passing records (is_pair_end / detect_nanopore peeks) */
+} wgbs_view_opts;
+int wgbs_bam_view_ex(const wgbs_bam *, const wgbs_view_opts *, char **text, size_t *nbytes, uint64_t *nrecords);
 void wgbs_host_free(void *);
 
 #ifdef __cplusplus

@@ -129,3 +129,130 @@ def test_bam2pat_cli_reads_bam(ctx, oracle, bamio, tmp_path):
     assert gzip.decompress((out / "s.pat.gz").read_bytes()) == exp
     counts = H.port_pat2beta(exp, 1, g.n_cpg + 1)
     assert (out / "s.beta").read_bytes() == H.ref_trim(counts).tobytes()
+
+
+def test_view_filters_native_vs_sam_text(bamio, tmp_path):
+    """wgbs_bam_view_ex (region, strand awk filters, -r RG, -L whitelist, bedtools -v blacklist, head -N) against the
+    independent SAM-text implementation of the same samtools semantics (samfilter.filter_sam)"""
+    from wgbs_tools_b200 import samfilter
+    g = synth.make_genome(11, "chrT", 200_000)
+    sam = synth.make_sam(g, 4000, 5, paired=True)
+    rng = np.random.default_rng(3)
+    lines = []
+    for i, l in enumerate(sam.splitlines()):
+        lines.append(l + (b"\tNM:i:1\tRG:Z:grp%d" % (i % 3) if i % 4 else b"\tXS:B:s,1,2"))          # some records without RG
+    sam = b"\n".join(lines) + b"\n"
+    p = tmp_path / "f.bam"; p.write_bytes(bamio.sam_to_bam(sam, [("chrT", g.length)]))
+    starts = np.sort(rng.integers(0, g.length - 3000, 40)); bed = tmp_path / "l.bed"
+    bed.write_text("# comment\ntrack name=x\n" + "".join(f"chrT\t{s}\t{s + int(w)}\n" for s, w in zip(starts.tolist(), rng.integers(1, 2500, 40).tolist())) + "chrOther\t5\t9\n")
+    iv = samfilter.load_bed_intervals(str(bed))
+    assert set(iv) == {"chrT", "chrOther"} and np.all(iv["chrT"][0][1:] > iv["chrT"][1][:-1])                 # merged, disjoint
+    cases = [dict(), dict(beg=50_000, end=50_300), dict(flag_eq=(99, 147)), dict(flag_eq=(83, 163), mapq=10, exclude_flags=1796, include_flags=3),
+             dict(read_group="grp1"), dict(read_group="grp"), dict(intervals=iv["chrT"]), dict(intervals=iv["chrT"], exclude_intervals=True),
+             dict(intervals=iv["chrT"], beg=20_000, end=90_000, read_group="grp2", flag_eq=(99, 147)), dict(max_records=7),
+             dict(max_records=5, flag_eq=(163,)), dict(intervals=(np.zeros(0, np.int64), np.zeros(0, np.int64))),
+             dict(intervals=(np.zeros(0, np.int64), np.zeros(0, np.int64)), exclude_intervals=True)]
+    with bamio.BamFile(str(p), threads=3) as b:
+        for kw in cases:
+            got = b.view("chrT", **kw)
+            exp = samfilter.filter_sam(sam, chrom="chrT", **kw)
+            assert got == exp, kw
+            if kw is cases[5] or kw is cases[-2]:
+                assert got == b""
+            elif "max_records" in kw:
+                assert got.count(b"\n") == kw["max_records"]
+            else:
+                assert 0 < got.count(b"\n") <= sam.count(b"\n")
+        # a read ending exactly at an interval's start does not overlap; one base earlier does
+        l0 = sam.splitlines()[10].split(b"\t"); pos0 = int(l0[3]) - 1; span = samfilter.ref_span(l0[5]); key = b"\t".join(l0[:4]) + b"\t"
+        touch = (np.array([pos0 + span], np.int64), np.array([pos0 + span + 1], np.int64))
+        assert not any(x.startswith(key) for x in b.view("chrT", intervals=touch).splitlines())
+        over = (np.array([pos0 + span - 1], np.int64), np.array([pos0 + span + 1], np.int64))
+        assert any(x.startswith(key) for x in b.view("chrT", intervals=over).splitlines())
+        before = (np.array([max(0, pos0 - 3)], np.int64), np.array([pos0], np.int64))
+        assert not any(x.startswith(key) for x in b.view("chrT", intervals=before).splitlines())
+
+
+def test_genomic_region_follows_reference_rules(tmp_path):
+    """-r / -s resolution (genomic_region.py:76-176): a CpG sitting exactly on the region's end is excluded; sites are
+    end-exclusive; single positions; errors"""
+    from wgbs_tools_b200.genome import GenomeRef, GenomicRegion, IllegalArgumentError, extend_region
+    d = tmp_path / "g"; d.mkdir()
+    loci = {"chr1": [100, 200, 300, 400, 500], "chr2": [50, 60], "chrX": [7]}
+    i = 1; rows = []
+    for c, ls in loci.items():
+        for l in ls:
+            rows.append(f"{c}\t{l}\t{i}\n"); i += 1
+    (d / "CpG.bed.gz").write_bytes(gzip.compress("".join(rows).encode()))
+    (d / "CpG.chrome.size").write_text("chr1\t5\nchr2\t2\nchrX\t1\n")
+    (d / "chrome.size").write_text("chr1\t1000\nchr2\t100\nchrX\t10\n")
+    ref = GenomeRef(str(d))
+    G = lambda **kw: GenomicRegion(ref, **kw)
+    assert G().is_whole() and G().region_str is None
+    r = G(region="chr1:150-400"); assert r.sites == (2, 4) and r.bp_tuple == (150, 400) and r.region_str == "chr1:150-400" and r.nr_sites == 2
+    assert G(region="chr1:150-401").sites == (2, 5)
+    assert G(region="chr1:1,00-2,01").sites == (1, 3)
+    assert G(region="chr1").sites == (1, 6) and G(region="chr1").region_str == "chr1"
+    assert G(region="chr2").sites == (6, 8) and G(region="chrX").sites == (8, 9)
+    assert G(region="chr1:200").sites == (2, 3) and G(region="chr1:200").region_str == "chr1:200-201"
+    s = G(sites="2-4"); assert s.sites == (2, 4) and s.region_str == "chr1:200-301" and s.chrom == "chr1"
+    assert G(sites="7").sites == (7, 8) and G(sites="7").region_str == "chr2:60-61"
+    assert G(sites="3-3").sites == (3, 4)
+    for bad in (dict(region="chr3"), dict(region="chr1:400-300"), dict(region="chr1:900-2000"), dict(region="chr1:101-199"), dict(region="chr1:150-200"),
+                dict(region="1:5"), dict(region="chr1:x-y"), dict(sites="5-7"), dict(sites="0-3"), dict(sites="3-100"), dict(sites="a-b")):
+        with pytest.raises(IllegalArgumentError):
+            G(**bad)
+    assert extend_region("chr1:1500-1800") == "chr1:500-2800" and extend_region("chr1:20-30") == "chr1:1-1030" and extend_region("chr1") == "chr1"
+
+
+@pytest.mark.gpu
+def test_bam2pat_cli_region_strand_readgroup_and_lists(ctx, oracle, bamio, tmp_path):
+    """bam2pat -r / --top_strand / -rg / -L / --blacklist on a .bam: same pat + beta as the reference executables fed
+    with the equivalently filtered SAM text and the dictionary of the region extended by 1000 bp (bam2pat.py:126-204)"""
+    from wgbs_tools_b200 import bam2pat, samfilter
+    from wgbs_tools_b200.genome import extend_region
+    H = oracle
+    g = synth.make_genome(43, "chr1", 500_000)
+    refdir = tmp_path / "ref"; refdir.mkdir()
+    with gzip.open(refdir / "CpG.bed.gz", "wb") as f:
+        f.write(g.dict_text())
+    (refdir / "CpG.chrome.size").write_text(f"chr1\t{g.n_cpg}\n"); (refdir / "chrome.size").write_text(f"chr1\t{g.length}\n")
+    sam = synth.make_sam(g, 9000, 13, paired=True)
+    sam = b"".join(l.rstrip(b"\n") + b"\tRG:Z:lib%d\n" % (i // 2 % 2) for i, l in enumerate(sam.splitlines(keepends=True)))   # mates share an RG... mostly
+    bam = tmp_path / "s.bam"; bam.write_bytes(bamio.sam_to_bam(sam, [("chr1", g.length)]))
+    rng = np.random.default_rng(1)
+    st = np.sort(rng.integers(0, g.length - 5000, 60))
+    bed = tmp_path / "list.bed"; bed.write_text("".join(f"chr1\t{s}\t{s + 1500}\n" for s in st.tolist()))
+    iv = samfilter.load_bed_intervals(str(bed))["chr1"]
+    dpath = H.write_tmp(g.dict_text(), ".CpG.bed")
+
+    def expect(region, **kw):
+        c, b, e = samfilter.parse_region_str(region)
+        kept = samfilter.filter_sam(sam, 10, 1796, 3, chrom=c, beg=b, end=e, **kw)
+        if H.have_ref():
+            out, _ = H.ref_patter(kept, dpath, extend_region(region), True)
+            return H.ref_collapse(out)
+        _, xb, xe = samfilter.parse_region_str(extend_region(region))
+        m = (g.loci >= xb) & (g.loci <= xe) if xe else np.ones(g.n_cpg, bool)
+        out, _ = H.port_patter(H.port_match_maker(kept), g.loci[m], g.idx()[m])
+        return H.port_collapse(out)
+
+    runs = [(["-r", "chr1:100,000-180,000"], "chr1:100000-180000", {}, "s"),
+            (["-r", "chr1:100000-180000", "--top_strand"], "chr1:100000-180000", dict(flag_eq=(147, 99)), "s"),
+            (["--bottom_strand", "-rg", "lib1"], "chr1", dict(flag_eq=(83, 163), read_group="lib1"), "s.lib1"),
+            (["-L", str(bed)], "chr1", dict(intervals=iv), "s"),
+            (["--blacklist", str(bed), "-r", "chr1:200000-400000"], "chr1:200000-400000", dict(intervals=iv, exclude_intervals=True), "s")]
+    for k, (argv, region, kw, name) in enumerate(runs):
+        out = tmp_path / f"out{k}"; out.mkdir()
+        bam2pat.main([str(bam), "--genome", str(refdir), "-o", str(out)] + argv)
+        exp = expect(region, **kw)
+        assert len(exp) > 1000
+        assert gzip.decompress((out / f"{name}.pat.gz").read_bytes()) == exp, argv
+        counts = H.port_pat2beta(exp, 1, g.n_cpg + 1)
+        assert (out / f"{name}.beta").read_bytes() == H.ref_trim(counts).tobytes(), argv
+    # -s: sites 1000-1200 -> region of their loci
+    out = tmp_path / "outs"; out.mkdir()
+    bam2pat.main([str(bam), "--genome", str(refdir), "-o", str(out), "-s", "1000-1200", "--no_beta"])
+    reg = f"chr1:{g.loci[999]}-{g.loci[1198] + 1}"
+    assert gzip.decompress((out / "s.pat.gz").read_bytes()) == expect(reg)
+    assert not (out / "s.beta").exists()

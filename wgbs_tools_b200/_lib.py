@@ -17,6 +17,14 @@ class PileupOpts(C.Structure):
                 ("combine_mods", C.c_int32), ("np_thresh", C.c_float), ("cpc_call", C.c_char), ("keep_names", C.c_int32)]
 
 
+class ViewOpts(C.Structure):
+    """mirror of wgbs_view_opts (include/wgbs_b200.h)"""
+    _fields_ = [("refid", C.c_int), ("min_mapq", C.c_int), ("exclude_flags", C.c_int), ("include_flags", C.c_int),
+                ("beg", C.c_int64), ("end", C.c_int64), ("n_flag_eq", C.c_int), ("flag_eq", C.c_int * 4),
+                ("read_group", C.c_char_p), ("iv_beg", C.c_void_p), ("iv_end", C.c_void_p), ("n_iv", C.c_size_t),
+                ("iv_exclude", C.c_int), ("max_records", C.c_uint64)]
+
+
 class WgbsError(RuntimeError):
     """Any rc<0 from the C ABI (message from wgbs_last_error)."""
 
@@ -66,6 +74,7 @@ def _load():
         "wgbs_bam_header": (C.c_char_p, [vp]),
         "wgbs_bam_nrecords": (u64, [vp, C.c_int]),
         "wgbs_bam_view": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.POINTER(vp), C.POINTER(sz), C.POINTER(u64)]),
+        "wgbs_bam_view_ex": (C.c_int, [vp, C.POINTER(ViewOpts), C.POINTER(vp), C.POINTER(sz), C.POINTER(u64)]),
         "wgbs_host_free": (None, [vp]),
     }
     for name, (res, args) in sig.items():

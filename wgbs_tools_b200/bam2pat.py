@@ -14,6 +14,9 @@ import sys
 
 import numpy as np
 
+from .genome import IllegalArgumentError, extend_region
+from .samfilter import filter_sam, load_bed_intervals, parse_region_str
+
 MAPQ = 10
 FLAGS_FILTER = 1796
 FLAGS_FILTER_NANOPORE = 3844
@@ -30,23 +33,14 @@ def split_sam_by_chrom(sam: bytes) -> dict[str, bytes]:
     return {c: b"".join(v) for c, v in out.items()}
 
 
-def filter_sam(sam: bytes, mapq: int, exclude_flags: int, include_flags: int | None) -> bytes:
-    """samtools view -q MAPQ -F EXCL [-f INCL] on SAM text (bam2pat.py:165)"""
-    keep = []
-    for l in sam.splitlines(keepends=True):
-        t = l.split(b"\t", 5)
-        if len(t) < 5:
-            keep.append(l); continue
-        f, q = int(t[1]), int(t[4])
-        if q < mapq or (f & exclude_flags) or (include_flags and (f & include_flags) != include_flags):
-            continue
-        keep.append(l)
-    return b"".join(keep)
-
-
-def proc_chr(ctx, ref, chrom: str, sam: bytes, args, mc_buf):
-    """one chromosome: returns (pat text bytes, stats); adds the chromosome's beta counts into mc_buf (device)"""
+def proc_chr(ctx, ref, region: str, sam: bytes, args, mc_buf):
+    """one chromosome / region: returns (pat text bytes, stats); adds its beta counts into mc_buf (device).  patter is
+    given the dictionary of the region extended by MAX_READ_SIZE (bam2pat.py:190): CpGs outside it are not called."""
+    chrom, beg, end = parse_region_str(extend_region(region))
     loci, first = ref.chrom_loci(chrom)
+    if end > 0:
+        lo = int(np.searchsorted(loci, beg, side="left")); hi = int(np.searchsorted(loci, end, side="right"))
+        loci, first = loci[lo:hi], first + lo
     ix = ctx.load_index(loci, first)
     P, st = ctx.pileup_sam(ix, sam, min_cpg=args.min_cpg, clip=args.clip, paired=-1, nanopore=args.nanopore,
                            np_thresh=args.np_thresh, cpc_call=args.cpc_call, combine_mods=args.combine_mods, mbias=args.mbias,
@@ -65,68 +59,187 @@ def proc_chr(ctx, ref, chrom: str, sam: bytes, args, mc_buf):
     return txt, st
 
 
+class _Source:
+    """the alignments of one input: a .bam (native reader) or SAM text (what `samtools view -h BAM` prints)"""
+
+    def __init__(self, path: str, threads: int):
+        self.bam = None; self.sam = None
+        if path.endswith(".bam"):
+            from .bamio import BamFile
+            self.bam = BamFile(path, threads)
+            self.header = self.bam.header
+            self.chroms = set(self.bam.refs)                 # `samtools idxstats | cut -f1` lists every @SQ (bam2pat.py:59)
+        elif path.endswith(".cram"):
+            raise IllegalArgumentError("CRAM input is not supported: convert to BAM first")
+        else:
+            raw = sys.stdin.buffer.read() if path == "-" else open(path, "rb").read()
+            self.header = b"".join(l for l in raw.splitlines(keepends=True) if l.startswith(b"@")).decode(errors="replace")
+            self.sam = split_sam_by_chrom(raw)
+            self.chroms = set(self.sam)
+            self._first = next((l for l in raw.splitlines(keepends=True) if l.strip() and not l.startswith(b"@")), b"")
+
+    def head(self, n: int) -> bytes:
+        """samtools view BAM | head -n  (no filters)"""
+        if self.bam is not None:
+            return self.bam.view(None, max_records=n)
+        if n == 1:
+            return self._first
+        return filter_sam(b"".join(self.sam.values()), max_records=n)
+
+    def view(self, region: str, **kw) -> bytes:
+        chrom, beg, end = parse_region_str(region)
+        if self.bam is not None:
+            if chrom not in self.bam.refs:
+                return b""
+            return self.bam.view(chrom, beg=beg, end=end, **kw)
+        return filter_sam(self.sam.get(chrom, b""), chrom=chrom, beg=beg, end=end, **kw)
+
+    def close(self):
+        if self.bam is not None:
+            self.bam.close()
+
+
+def is_sorted_header(header: str) -> bool:
+    """bam2pat.py:228-234: an @HD line without 'coordinate' means the input is not coordinate sorted"""
+    first = header.split("\n", 1)[0]
+    return not (first.startswith("@HD") and "coordinate" not in first)
+
+
+def detect_nanopore(src: "_Source") -> bool:
+    """bam2pat.py:248-266: @RG PL:ONT in the header, or MM:Z:/Mm:Z: tags within the first 200 reads"""
+    if "\tPL:ONT" in src.header:
+        return True
+    return any(b"\tMM:Z:" in l or b"\tMm:Z:" in l for l in src.head(200).splitlines())
+
+
+def strand_flags(paired: bool, top: bool, bottom: bool):
+    """the awk FLAG filters of bam2pat.py:135-144; both switches together leave nothing (the awk stages are chained)"""
+    if top and bottom:
+        return None
+    if top:
+        return (147, 99) if paired else (0,)
+    if bottom:
+        return (83, 163) if paired else (16,)
+    return ()
+
+
+def add_args(p):
+    p.add_argument("bam", nargs="+", help="coordinate-sorted .bam, SAM text (.sam), or '-' for SAM on stdin")
+    p.add_argument("-s", "--sites", help="a CpG index range, of the form: 'start-end'")
+    p.add_argument("-r", "--region", help="genomic region of the form 'chr1:10,000-10,500'")
+    p.add_argument("--genome", help="Genome reference name")
+    p.add_argument("--include_flags", type=int, help="flags to include (samtools view -f) [3 for PE, None for SE]")
+    p.add_argument("-F", "--exclude_flags", type=int, default=FLAGS_FILTER, help=f"flags to exclude (samtools view -F) [{FLAGS_FILTER}]")
+    p.add_argument("-q", "--mapq", type=int, default=MAPQ, help=f"Minimal mapping quality [{MAPQ}]")
+    p.add_argument("-rg", "--read_group", help="filter reads by read group (samtools view -r)")
+    p.add_argument("--top_strand", action="store_true", help="Consider only top strand reads")
+    p.add_argument("--bottom_strand", action="store_true", help="Consider only bottom strand reads")
+    p.add_argument("--out_dir", "-o", default=".")
+    p.add_argument("--min_cpg", type=int, default=1, help="Reads covering less than MIN_CPG sites are removed [1]")
+    p.add_argument("--debug", "-d", action="store_true")
+    p.add_argument("--force", "-f", action="store_true", help="overwrite existing files if exists")
+    p.add_argument("--verbose", "-v", action="store_true")
+    p.add_argument("--clip", type=int, default=0, help="Clip for each read the first and last CLIP characters [0]")
+    p.add_argument("--long", action="store_true", help="Use long format for pat file (add read name to each line)")
+    p.add_argument("-@", "--threads", type=int, default=8, help="host threads for BGZF inflate/deflate")
+    p.add_argument("--no_beta", action="store_true", help="Do not generate a beta file")
+    p.add_argument("-l", "--lbeta", action="store_true", help="Use lbeta file (uint16) instead of beta (uint8)")
+    p.add_argument("-T", "--temp_dir", help="accepted for CLI compatibility (the collapse is a device sort: no temp files)")
+    lists = p.add_mutually_exclusive_group()
+    lists.add_argument("--blacklist", nargs="?", const=True, default=False, help="bed file. Ignore reads overlapping this bed file")
+    lists.add_argument("-L", "--whitelist", nargs="?", const=True, default=False, help="bed file. Consider only reads overlapping this bed file")
+    p.add_argument("--mbias", "-mb", action="store_true", help="write the M-bias tables (<name>.mbias/<name>.mbias.{OT,OB}.txt); plots are out of scope")
+    p.add_argument("--blueprint", "-bp", action="store_true", help="legacy filter: not supported")
+    p.add_argument("--nanopore", "-np", action="store_true", help="Input has MM/ML modification tags. Auto-detected. Sets -q 0 and -F 3844")
+    p.add_argument("--cpc_call", default="C", choices=["C", "H", "."])
+    p.add_argument("--np_thresh", type=float, default=0.67)
+    p.add_argument("--combine_mods", action="store_true")
+    return p
+
+
 def main(argv=None):
     from .api import Context
-    from .genome import GenomeRef
+    from .genome import GenomeRef, GenomicRegion
     from .patio import bgzf_compress
-    p = argparse.ArgumentParser(description="Run the WGBS pipeline to generate pat & beta files out of an input alignment file")
-    p.add_argument("bam", nargs="+", help="coordinate-sorted .bam, SAM text (.sam), or '-' for SAM on stdin")
-    p.add_argument("-s", "--sites"); p.add_argument("-r", "--region"); p.add_argument("--genome")
-    p.add_argument("--include_flags", type=int); p.add_argument("-F", "--exclude_flags", type=int, default=FLAGS_FILTER)
-    p.add_argument("-q", "--mapq", type=int, default=MAPQ)
-    p.add_argument("--out_dir", "-o", default="."); p.add_argument("--min_cpg", type=int, default=1)
-    p.add_argument("--force", "-f", action="store_true"); p.add_argument("--verbose", "-v", action="store_true")
-    p.add_argument("--clip", type=int, default=0); p.add_argument("-@", "--threads", type=int, default=8)
-    p.add_argument("--long", action="store_true", help="Use long format for pat file (add read name to each line)")
-    p.add_argument("--no_beta", action="store_true"); p.add_argument("-l", "--lbeta", action="store_true")
-    p.add_argument("--nanopore", "-np", action="store_true"); p.add_argument("--cpc_call", default="C", choices=["C", "H", "."])
-    p.add_argument("--np_thresh", type=float, default=0.67); p.add_argument("--combine_mods", action="store_true")
-    p.add_argument("--mbias", "-mb", action="store_true", help="write the M-bias tables (<name>.mbias/<name>.mbias.{OT,OB}.txt); plots are out of scope")
-    a = p.parse_args(argv)
+    a = add_args(argparse.ArgumentParser(description="Run the WGBS pipeline to generate pat & beta files out of an input alignment file")).parse_args(argv)
+    if not os.path.isdir(a.out_dir):
+        raise IllegalArgumentError(f"Invalid output dir: {a.out_dir}")
     if not 0 < a.np_thresh < 1:
-        raise ValueError("Invalid np_thresh range: must be in range (0,1)")
+        raise IllegalArgumentError("Invalid np_thresh range: must be in range (0,1)")
+    if a.blueprint:
+        raise IllegalArgumentError("--blueprint (legacy bisulfite-conversion filter) is not supported")
     ref = GenomeRef(a.genome)
+    gr = GenomicRegion(ref, region=a.region, sites=a.sites)
+    # black/white lists (bam2pat.py:287-304): a bare flag means the genome's own list
+    lists = None
+    for flag, fname, excl in ((a.blacklist, "blacklist.bed", True), (a.whitelist, "whitelist.bed", False)):
+        if flag:
+            path = os.path.join(ref.dir, fname) if flag is True else flag
+            if not os.path.isfile(path):
+                raise IllegalArgumentError(f"Invalid file: {path}")
+            lists = (load_bed_intervals(path), excl)
+    empty_iv = (np.zeros(0, np.int64), np.zeros(0, np.int64))
     with Context(0) as ctx:
         for path in a.bam:
+            print(f"[wt bam2pat] bam: {path}", file=sys.stderr)
+            if path != "-" and not os.path.isfile(path):
+                print(f"[wt bam2pat] Invalid bam: {path}\n[wt bam2pat] Skipping {path}", file=sys.stderr)
+                continue
             name = "stdin" if path == "-" else os.path.splitext(os.path.basename(path))[0]
-            pat_path = os.path.join(a.out_dir, name + ".pat.gz")
+            pat_path = os.path.join(a.out_dir, name + (f".{a.read_group}" if a.read_group else "") + ".pat.gz")   # bam2pat.py:406-407
             if os.path.exists(pat_path) and not a.force:
                 print(f"File {pat_path} already exists. Skipping it. Use -f to overwrite", file=sys.stderr)
                 continue
-            ex = FLAGS_FILTER_NANOPORE if a.nanopore else a.exclude_flags
-            bam = None
-            if path.endswith(".bam"):
-                from .bamio import BamFile
-                bam = BamFile(path, a.threads)
-                by_chrom = {c: None for c in bam.refs if bam.nrecords(c)}
+            src = _Source(path, a.threads)
+            if not is_sorted_header(src.header):
+                print(f"[wt bam2pat] WARNING: based on the @HD, bam file is not sorted: {path}\n[wt bam2pat] Skipping {path}", file=sys.stderr)
+                src.close(); continue
+            first = src.head(1)
+            if not first.strip():
+                print("[wt bam2pat] Empty bam file", file=sys.stderr)
+                src.close(); continue
+            paired = bool(int(first.split(b"\t", 2)[1]) & 1)                    # is_pair_end (bam2pat.py:262-267)
+            nanopore = a.nanopore
+            if not nanopore and detect_nanopore(src):
+                print("[wt bam2pat] Auto-detected modification-aware BAM — enabling --nanopore mode", file=sys.stderr)
+                nanopore = True
+            run = argparse.Namespace(**vars(a)); run.nanopore = nanopore
+            ex = FLAGS_FILTER_NANOPORE if nanopore else a.exclude_flags
+            mapq = 0 if nanopore else a.mapq
+            inc = a.include_flags if a.include_flags is not None else (3 if paired else None)
+            feq = strand_flags(paired, a.top_strand, a.bottom_strand)
+            if gr.region_str:
+                regions = [gr.region_str]
             else:
-                sam = sys.stdin.buffer.read() if path == "-" else open(path, "rb").read()
-                by_chrom = split_sam_by_chrom(sam)
+                regions = [c for c in ref.chroms if c in src.chroms]              # intersect, in chromosome_order (bam2pat.py:68-80)
+                if not regions:
+                    print("[wt bam2pat] Failed retrieving valid chromosome names. Perhaps you are using a wrong genome reference.", file=sys.stderr)
+                    raise IllegalArgumentError("Failed")
             mc = None if a.no_beta else ctx.alloc(ref.nr_sites * 8)
             if mc is not None:
                 ctx.pat2beta(ctx.pats_from_text(b""), 1, ref.nr_sites + 1, meth_cov=mc, zero_first=True)
             parts = []
             mb_total = None
-            for chrom in [c for c in ref.chroms if c in by_chrom]:           # chromosome_order (init_genome.py:263-275)
-                if bam is not None:
-                    head = bam.view(chrom, beg=1, end=1 << 29)[:4096]         # is_pair_end: FLAG of the first read (bam2pat.py:262-267)
-                    first_flag = int(head.split(b"\t", 2)[1]) if head else 0
-                    inc = a.include_flags if a.include_flags is not None else (3 if first_flag & 1 else None)
-                    s = bam.view(chrom, 0 if a.nanopore else a.mapq, ex, inc or 0)
-                else:
-                    s = by_chrom[chrom]
-                    first_flag = int(s.split(b"\t", 2)[1])
-                    inc = a.include_flags if a.include_flags is not None else (3 if first_flag & 1 else None)
-                    s = filter_sam(s, 0 if a.nanopore else a.mapq, ex, inc)
+            for region in regions:
+                chrom = region.split(":")[0]
+                kw = dict(mapq=mapq, exclude_flags=ex, include_flags=inc, read_group=a.read_group)
+                if lists is not None:
+                    kw.update(intervals=lists[0].get(chrom, empty_iv), exclude_intervals=lists[1])
+                s = b"" if feq is None else src.view(region, flag_eq=feq, **kw)
                 if not s:
+                    if a.verbose:
+                        print(f"[wt bam2pat] Skipping region {region}, no reads found", file=sys.stderr)
                     continue
-                txt, st = proc_chr(ctx, ref, chrom, s, a, mc)
+                txt, st = proc_chr(ctx, ref, region, s, run, mc)
                 if a.mbias and "mbias" in st:
                     mb_total = st["mbias"].astype(np.int64) if mb_total is None else mb_total + st["mbias"]   # mbias_merge (bam2pat.py:375-395)
                 if txt:
                     parts.append(bgzf_compress(txt, a.threads))
+            src.close()
             if not parts:
                 print("[wt bam2pat] No reads found. No pat file is generated", file=sys.stderr)
+                if mc is not None:
+                    mc.free()
                 continue
             with open(pat_path, "wb") as f:
                 f.write(b"".join(parts))                                       # `cat parts` (bam2pat.py:408)
@@ -142,7 +255,7 @@ def main(argv=None):
                             f.write(f"{t[0, 0]}\t{t[0, 1]}\t{t[1, 0]}\t{t[1, 1]}\n")
             if mc is not None:
                 beta = ctx.trim(mc, ref.nr_sites, 16 if a.lbeta else 8)
-                bp = os.path.join(a.out_dir, name + (".lbeta" if a.lbeta else ".beta"))
+                bp = pat_path[:-len(".pat.gz")] + (".lbeta" if a.lbeta else ".beta")
                 beta.tofile(bp)
                 print(f"[wt bam2pat] generated {bp}", file=sys.stderr)
                 mc.free()

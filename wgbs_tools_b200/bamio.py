@@ -10,7 +10,7 @@ import struct
 
 import numpy as np
 
-from ._lib import check, lib
+from ._lib import ViewOpts, check, lib
 from .patio import bgzf_compress
 
 
@@ -28,10 +28,30 @@ class BamFile:
     def nrecords(self, chrom: str | None = None) -> int:
         return int(lib.wgbs_bam_nrecords(self.h, -1 if chrom is None else self.refs.index(chrom)))
 
-    def view(self, chrom: str | None = None, mapq: int = 0, exclude_flags: int = 0, include_flags: int = 0, beg: int = 0, end: int = 0) -> bytes:
+    def view(self, chrom: str | None = None, mapq: int = 0, exclude_flags: int = 0, include_flags: int = 0, beg: int = 0, end: int = 0,
+             flag_eq=(), read_group: str | None = None, intervals=None, exclude_intervals: bool = False, max_records: int = 0) -> bytes:
+        """`samtools view BAM chrom[:beg-end] -q mapq -F exclude_flags [-f include_flags] [-r read_group]`, optionally
+        `| awk '$2 == flag_eq[0] || ...'`, `-M -L bed` (intervals = (starts, ends) 0-based half-open, sorted, merged) or
+        `bedtools intersect -v` (exclude_intervals), `| head -max_records`."""
+        vo = ViewOpts()
+        vo.refid = -1 if chrom is None else self.refs.index(chrom)
+        vo.min_mapq, vo.exclude_flags, vo.include_flags, vo.beg, vo.end = mapq, exclude_flags, include_flags or 0, beg, end
+        vo.n_flag_eq = len(flag_eq)
+        for i, f in enumerate(flag_eq):
+            vo.flag_eq[i] = f
+        vo.read_group = read_group.encode() if read_group else None
+        keep = None
+        if intervals is not None:
+            keep = (np.ascontiguousarray(intervals[0], np.int64), np.ascontiguousarray(intervals[1], np.int64))
+            vo.iv_beg, vo.iv_end, vo.n_iv = keep[0].ctypes.data, keep[1].ctypes.data, keep[0].size
+            vo.iv_exclude = int(exclude_intervals)
+            if keep[0].size == 0:                       # samtools -L with no interval on this reference prints nothing
+                if not exclude_intervals:
+                    return b""
+                vo.n_iv = 0
+        vo.max_records = max_records
         ptr = C.c_void_p(); n = C.c_size_t(); nr = C.c_uint64()
-        rid = -1 if chrom is None else self.refs.index(chrom)
-        check(lib.wgbs_bam_view(self.h, rid, mapq, exclude_flags, include_flags or 0, beg, end, C.byref(ptr), C.byref(n), C.byref(nr)))
+        check(lib.wgbs_bam_view_ex(self.h, C.byref(vo), C.byref(ptr), C.byref(n), C.byref(nr)))
         try:
             return C.string_at(ptr, n.value)
         finally:

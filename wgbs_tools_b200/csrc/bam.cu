@@ -237,32 +237,82 @@ extern "C" uint64_t wgbs_bam_nrecords(const wgbs_bam *B, int refid) {
     return refid < (int)B->ref_names.size() ? B->ref_last[refid] - B->ref_first[refid] : 0;
 }
 
-// SAM text of the records of reference `refid` (-1: every record) that pass `-q min_mapq -F exclude -f include`
-// [and overlap the 1-based closed interval beg..end when end > 0].  *text is malloc'ed: release with wgbs_host_free.
-extern "C" int wgbs_bam_view(const wgbs_bam *B, int refid, int min_mapq, int exclude_flags, int include_flags, int64_t beg, int64_t end,
-                             char **text, size_t *nbytes, uint64_t *nrecords) {
-    if (!B || !text || !nbytes) return wgbs_set_err("wgbs_bam_view: null argument");
+namespace {
+// value of a Z-typed tag (e.g. "RG"), or nullptr
+const char *find_z_tag(const uint8_t *t, const uint8_t *end, char a, char b, size_t *len) {
+    while (t + 3 <= end) {
+        const char ty = (char)t[2]; const bool hit = (char)t[0] == a && (char)t[1] == b; t += 3;
+        switch (ty) {
+            case 'A': case 'c': case 'C': t += 1; break;
+            case 's': case 'S': t += 2; break;
+            case 'i': case 'I': case 'f': t += 4; break;
+            case 'Z': case 'H': { const char *z = (const char *)t; size_t l = strnlen(z, end - t); if (hit && ty == 'Z') { *len = l; return z; } t += l + 1; break; }
+            case 'B': {
+                if (t + 5 > end) return nullptr;
+                const char sub = (char)t[0]; const uint32_t cnt = rd32(t + 1); t += 5;
+                const size_t w = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : (sub == 'i' || sub == 'I' || sub == 'f') ? 4 : 0;
+                if (!w) return nullptr;
+                t += (size_t)cnt * w; break;
+            }
+            default: return nullptr;
+        }
+    }
+    return nullptr;
+}
+}  // namespace
+
+// SAM text of the records that pass the filters of `o` (see wgbs_view_opts in the header).  *text is malloc'ed: release
+// with wgbs_host_free.
+extern "C" int wgbs_bam_view_ex(const wgbs_bam *B, const wgbs_view_opts *vo, char **text, size_t *nbytes, uint64_t *nrecords) {
+    if (!B || !vo || !text || !nbytes) return wgbs_set_err("wgbs_bam_view: null argument");
+    if (vo->n_flag_eq < 0 || vo->n_flag_eq > 4) return wgbs_set_err("wgbs_bam_view: n_flag_eq must be 0..4");
+    if (vo->n_iv && (!vo->iv_beg || !vo->iv_end)) return wgbs_set_err("wgbs_bam_view: interval list is null");
+    for (size_t k = 0; k + 1 < vo->n_iv; k++)
+        if (vo->iv_beg[k + 1] < vo->iv_end[k] || vo->iv_end[k] < vo->iv_beg[k]) return wgbs_set_err("wgbs_bam_view: intervals must be sorted and non-overlapping");
+    const int refid = vo->refid, min_mapq = vo->min_mapq, exclude_flags = vo->exclude_flags, include_flags = vo->include_flags;
+    const int64_t beg = vo->beg, end = vo->end;
+    const size_t rg_len = vo->read_group ? strlen(vo->read_group) : 0;
     uint64_t r0 = 0, r1 = B->rec_off.size();
     if (refid >= 0) { if (refid >= (int)B->ref_names.size()) return wgbs_set_err("wgbs_bam_view: no such reference"); r0 = B->ref_first[refid]; r1 = B->ref_last[refid]; }
-    const int nt = (int)std::max<uint64_t>(1, std::min<uint64_t>(B->threads, (r1 - r0) / 2048 + 1));
+    const bool need_span = end > 0 || vo->n_iv;
+    // head -N: a sequential walk (the caller wants the FIRST max_records passing records)
+    const int nt = vo->max_records ? 1 : (int)std::max<uint64_t>(1, std::min<uint64_t>(B->threads, (r1 - r0) / 2048 + 1));
     std::vector<OutBuf> parts(nt); std::vector<uint64_t> cnt(nt, 0); std::atomic<int> oom(0);
     auto work = [&](int t) {
         const uint64_t a = r0 + (r1 - r0) * t / nt, b = r0 + (r1 - r0) * (t + 1) / nt;
         OutBuf &o = parts[t];
-        if (!o.reserve((b - a) * 384 + 4096)) { oom.store(1); return; }
+        if (!o.reserve((vo->max_records ? std::min<uint64_t>(b - a, vo->max_records) : (b - a)) * 384 + 4096)) { oom.store(1); return; }
         for (uint64_t i = a; i < b; i++) {
             const uint8_t *r = B->data.data() + B->rec_off[i];
             const uint16_t flag = rd16(r + 4 + 14); const uint8_t mapq = r[4 + 9];
             if (mapq < min_mapq || (flag & exclude_flags) || (include_flags && (flag & include_flags) != include_flags)) continue;
-            if (end > 0) {
-                const int64_t pos = (int64_t)rdi32(r + 8) + 1; const uint16_t n_cig = rd16(r + 4 + 12); const uint8_t l_name = r[4 + 8];
+            if (vo->n_flag_eq) {                                     // awk '($2 == A || $2 == B)' (bam2pat.py:135-144)
+                bool ok = false;
+                for (int k = 0; k < vo->n_flag_eq; k++) ok |= (int)flag == vo->flag_eq[k];
+                if (!ok) continue;
+            }
+            const uint16_t n_cig = rd16(r + 4 + 12); const uint8_t l_name = r[4 + 8];
+            if (need_span) {
+                const int64_t pos0 = (int64_t)rdi32(r + 8);          // 0-based
                 int64_t span = 0; const uint8_t *cig = r + 36 + l_name;
                 for (uint16_t k = 0; k < n_cig; k++) { uint32_t c = rd32(cig + 4 * k); uint32_t op = c & 15; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += c >> 4; }
                 if (span < 1) span = 1;
-                if (pos > end || pos + span - 1 < beg) continue;
+                if (end > 0 && (pos0 + 1 > end || pos0 + span < beg)) continue;
+                if (vo->n_iv) {                                      // [pos0, pos0+span) against sorted disjoint [iv_beg, iv_end)
+                    const int64_t *e = std::upper_bound(vo->iv_end, vo->iv_end + vo->n_iv, pos0);     // first interval ending after pos0
+                    const bool hit = e != vo->iv_end + vo->n_iv && vo->iv_beg[e - vo->iv_end] < pos0 + span;
+                    if (hit == (vo->iv_exclude != 0)) continue;
+                }
+            }
+            if (rg_len || vo->read_group) {                          // samtools view -r RG
+                const uint32_t bs = rd32(r); const int32_t l_seq = rdi32(r + 4 + 16);
+                const uint8_t *tags = r + 36 + l_name + 4 * (size_t)n_cig + (size_t)((l_seq + 1) / 2) + (size_t)(l_seq > 0 ? l_seq : 0);
+                size_t zl = 0; const char *z = find_z_tag(tags, r + 4 + bs, 'R', 'G', &zl);
+                if (!z || zl != rg_len || memcmp(z, vo->read_group, zl)) continue;
             }
             if (!format_record(B, r, o)) { oom.store(1); return; }
             cnt[t]++;
+            if (vo->max_records && cnt[t] >= vo->max_records) break;
         }
     };
     {
@@ -285,6 +335,15 @@ extern "C" int wgbs_bam_view(const wgbs_bam *B, int refid, int min_mapq, int exc
     }
     *text = buf; *nbytes = tot; if (nrecords) *nrecords = nr;
     return 0;
+}
+
+// SAM text of the records of reference `refid` (-1: every record) that pass `-q min_mapq -F exclude -f include`
+// [and overlap the 1-based closed interval beg..end when end > 0].
+extern "C" int wgbs_bam_view(const wgbs_bam *B, int refid, int min_mapq, int exclude_flags, int include_flags, int64_t beg, int64_t end,
+                             char **text, size_t *nbytes, uint64_t *nrecords) {
+    wgbs_view_opts vo; memset(&vo, 0, sizeof vo);
+    vo.refid = refid; vo.min_mapq = min_mapq; vo.exclude_flags = exclude_flags; vo.include_flags = include_flags; vo.beg = beg; vo.end = end;
+    return wgbs_bam_view_ex(B, &vo, text, nbytes, nrecords);
 }
 
 extern "C" void wgbs_host_free(void *p) { free(p); }

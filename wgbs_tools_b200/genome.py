@@ -6,6 +6,7 @@ from __future__ import annotations
 
 import gzip
 import os
+import re
 
 import numpy as np
 
@@ -35,6 +36,7 @@ class GenomeRef:
         self.first = np.concatenate([[1], 1 + np.cumsum(self.sizes)])      # first CpG index per chromosome (+ sentinel)
         self.nr_sites = int(self.sizes.sum())
         self._loci = None
+        self._lengths = None
 
     def all_loci(self) -> np.ndarray:
         """uint32[nr_sites] locus of CpG i+1 (all chromosomes, index order)"""
@@ -70,22 +72,113 @@ class GenomeRef:
         return int(self.all_loci()[site - 1])
 
 
+    def chrom_length(self, chrom: str) -> int:
+        """bp length from chrome.size (falls back to the last CpG locus + 1 when the file is absent)"""
+        if self._lengths is None:
+            self._lengths = {}
+            path = os.path.join(self.dir, "chrome.size")
+            if os.path.isfile(path):
+                for l in open(path):
+                    c, n = l.split()
+                    self._lengths[c] = int(n)
+        if chrom in self._lengths:
+            return self._lengths[chrom]
+        loci, _ = self.chrom_loci(chrom)
+        return int(loci[-1]) + 1 if loci.size else 0
+
+
+_CHR = r"(chr)?([\d]+|[XYM]|(MT))"
+
+
+class GenomicRegion:
+    """`-s/--sites START-END` (CpG indices, end exclusive) or `-r/--region chr[:from[-to]]`, resolved against the CpG
+    dictionary the way the reference does (genomic_region.py:76-176): `sites` = (s1, s2), `region_str`, `bp_tuple`.
+    A site whose locus equals the region's end is NOT part of the region (genomic_region.py:139-144)."""
+
+    def __init__(self, ref: GenomeRef, region: str | None = None, sites: str | None = None):
+        self.ref = ref
+        self.chrom = None; self.sites = None; self.region_str = None; self.bp_tuple = None
+        if sites:
+            self._parse_sites(sites)
+        elif region:
+            self._parse_region(region)
+        self.nr_sites = None if self.sites is None else self.sites[1] - self.sites[0]
+
+    def is_whole(self) -> bool:
+        return self.sites is None
+
+    def _sites_tuple(self, sites_str: str) -> tuple[int, int]:
+        if not sites_str:
+            raise IllegalArgumentError(f"Empty sites string: {sites_str}")
+        sites_str = sites_str.replace(",", "")
+        m = re.match(r"([\d]+)-([\d]+)", sites_str)
+        if m:
+            s1, s2 = int(m.group(1)), int(m.group(2))
+        elif "-" not in sites_str and sites_str.isdigit():
+            s1 = int(sites_str); s2 = s1 + 1
+        else:
+            raise IllegalArgumentError(f'sites must be of format: "start-end" or "site" .\nGot: {sites_str}')
+        n = self.ref.nr_sites
+        if not n + 1 >= s2 >= s1 >= 1:
+            raise IllegalArgumentError(f"sites violate the constraints: {n + 1} >= {s2} > {s1} >= 1")
+        if s1 == s2:
+            s2 += 1
+        return s1, s2
+
+    def _parse_sites(self, sites_str: str):
+        s1, s2 = self._sites_tuple(sites_str)
+        self.chrom = self.ref.chrom_of_site(s1)
+        if self.chrom != self.ref.chrom_of_site(s2 - 1):
+            raise IllegalArgumentError("Invalid sites input")               # range crosses chromosomes
+        lo, hi = self.ref.locus_of_site(s1), self.ref.locus_of_site(s2 - 1) + 1   # include the whole last site (C and G)
+        self.sites = (s1, s2); self.region_str = f"{self.chrom}:{lo}-{hi}"; self.bp_tuple = (lo, hi)
+
+    def _parse_region(self, region: str):
+        region = region.replace(",", "")
+        if re.match(rf"^{_CHR}$", region):
+            if region not in self.ref.chroms:
+                raise IllegalArgumentError(f"Unknown chromosome: {region}")
+            self.chrom = region
+            lo, hi = 1, self.ref.chrom_length(region)
+        else:
+            m = re.match(rf"^{_CHR}:([\d]+)$", region)
+            if m:
+                region += f"-{int(m.group(4)) + 1}"
+            m = re.match(rf"^({_CHR}):([\d]+)-([\d]+)$", region)
+            if not m:
+                raise IllegalArgumentError(f"Invalid genomic region: {region}")
+            self.chrom = m.group(1)
+            if self.chrom not in self.ref.chroms:
+                raise IllegalArgumentError(f"Unknown chromosome: {region}")
+            lo, hi = int(m.group(5)), int(m.group(6))
+        if hi <= lo:
+            raise IllegalArgumentError(f"Invalid genomic region: {region}. end before start")
+        if hi > self.ref.chrom_length(self.chrom) or lo < 1:
+            raise IllegalArgumentError(f"Invalid genomic region: {region}. Out of range")
+        loci, first = self.ref.chrom_loci(self.chrom)
+        a = int(np.searchsorted(loci, lo, side="left")); b = int(np.searchsorted(loci, hi, side="left"))
+        # tabix returns loci in [lo, hi]; the reference then drops a last site sitting exactly on `hi`, and calls the
+        # range empty when that leaves a single index (genomic_region.py:139-149)
+        b_incl = int(np.searchsorted(loci, hi, side="right"))
+        if b_incl <= a or b <= a:
+            raise IllegalArgumentError(f"Invalid genomic region: {region}. No CpGs in range")
+        self.region_str = region; self.bp_tuple = (lo, hi); self.sites = (first + a, first + b)
+
+
+def extend_region(region: str, by: int = 1000) -> str:
+    """bam2pat.py:31-38: the dictionary patter loads covers the region +- MAX_READ_SIZE"""
+    if ":" not in region:
+        return region
+    chrom, r = region.split(":")
+    start, end = map(int, r.split("-"))
+    return f"{chrom}:{max(1, start - by)}-{end + by}"
+
+
 def parse_region(ref: GenomeRef, args):
     """-s START-END (CpG indices), -r chr:start-end, -L bed with startCpG/endCpG columns, or the whole genome: list of
     (startCpG, endCpG) (reference genomic_region.py / segment.py:94-122)."""
-    if getattr(args, "sites", None):
-        a, b = args.sites.split("-")
-        return [(int(a), int(b))]
-    if getattr(args, "region", None):
-        r = args.region
-        if ":" not in r:
-            return [ref.chrom_range(r)]
-        c, se = r.split(":"); s, e = (int(x.replace(",", "")) for x in se.split("-"))
-        loci, first = ref.chrom_loci(c)
-        a = int(np.searchsorted(loci, s, side="left")); b = int(np.searchsorted(loci, e, side="right"))
-        if b <= a:
-            raise IllegalArgumentError(f"Invalid genomic region: {r}. No CpGs in range")
-        return [(first + a, first + b)]
+    if getattr(args, "sites", None) or getattr(args, "region", None):
+        return [GenomicRegion(ref, region=getattr(args, "region", None), sites=getattr(args, "sites", None)).sites]
     if getattr(args, "bed_file", None):
         out = []
         for l in open(args.bed_file):
