@@ -136,6 +136,14 @@ int wgbs_collapse(wgbs_ctx *, wgbs_pats *);
  * wgbs_pats_format_long writes "chrom \t idx \t pattern \t 1 \t qname \n".  Needs opts.keep_names. */
 int wgbs_collapse_long(wgbs_ctx *, wgbs_pats *);
 int wgbs_pats_format_long(wgbs_ctx *, const wgbs_pats *, const char *chrom, char *out, size_t cap, size_t *nbytes);
+/* the collapse with its variants spelled out.  DOTTED: patterns may begin/end with '.' (cview output without --strip):
+ * "C" sorts before "C." as `sort -k3,3` has it.  ADJACENT: no sort, only neighbouring identical records merge -- what
+ * reference src/collapse_pat.pl does to the unsorted stream of a whole-file `wgbstools view` (cview.py:29-51). */
+#define WGBS_COLLAPSE_SORTED 0
+#define WGBS_COLLAPSE_LONG 1
+#define WGBS_COLLAPSE_DOTTED 2
+#define WGBS_COLLAPSE_ADJACENT 3
+int wgbs_collapse_ex(wgbs_ctx *, wgbs_pats *, int mode);
 /* "chrom \t idx \t pattern \t count \n" per record, record order.  out NULL: only *nbytes. out: host or device. */
 int wgbs_pats_format(wgbs_ctx *, const wgbs_pats *, const char *chrom, char *out, size_t cap, size_t *nbytes);
 /* utility: stable radix sort of (key, value) uint32 pairs, device pointers */
@@ -156,6 +164,27 @@ typedef struct wgbs_chunk { uint32_t start, n; } wgbs_chunk;
 int wgbs_segment(wgbs_ctx *, const uint8_t *const *betas, int K, const uint32_t *dists, size_t nsites,
                  const wgbs_chunk *chunks, int nchunks, int max_cpg, uint32_t max_bp, float pseudo,
                  int32_t *borders, int32_t *nborders);
+/* ---------------------------------------------------------------------------------------------------------------
+ * Consumers next to the hot path
+ * ------------------------------------------------------------------------------------------------------------- */
+/* cview (reference src/cview/cview.cpp:87-167; argv `--sites "s\te"` / `--blocks_path F [--strict] [--strip] [--no_gaps]
+ * [--min_cpgs N]`): the records of `in` (in file order = sorted by start) that overlap the blocks [bstart, bend) (CpG
+ * indices, end exclusive, sorted by start the way cview's `sort -k1,1n` leaves them; host or device int32), unchanged
+ * or -- with strict -- cut into one piece per overlapped block (blocks must then be disjoint: the reference aborts on
+ * overlapping ones).  strip removes leading/trailing '.', no_gaps drops pieces containing '.', min_cpgs drops pieces
+ * shorter than that.  pre_lo/pre_hi (npre closed ranges of START indices, sorted, disjoint; npre 0 = none) restate the
+ * `tabix pat chr:lo-hi` pre-selection in front of cview (cview.py:40, :88-96).  *out: new records (count copied), in the
+ * reference's output order; follow with wgbs_collapse_ex + wgbs_pats_format for the `| sort | collapse_pat.pl` tail. */
+int wgbs_cview(wgbs_ctx *, const wgbs_pats *in, const int32_t *bstart, const int32_t *bend, size_t nblocks,
+               const int32_t *pre_lo, const int32_t *pre_hi, size_t npre, int strict, int strip, int no_gaps, int min_cpgs,
+               wgbs_pats **out);
+/* beta_to_blocks (reference src/python/beta_to_blocks.py:101-126 + utils_wgbs.py:277-290): for every block the sums of
+ * (meth, cover) over rows startCpG-1 .. endCpG-2 of a beta file (uint8 pairs: in_bits 8; .lbeta uint16 pairs: 16),
+ * clamped to the file like a numpy slice; an empty / NA block (bend <= bstart) gives (0, 0).  out_sums: int64[nblocks,2]
+ * (optional); out_trimmed: the `.bin` / `.lbeta` rows (trim_to_uint8 of the sums; out_bits 8 or 16; optional). Host or device. */
+int wgbs_beta_to_blocks(wgbs_ctx *, const void *beta, int in_bits, size_t nsites, const int32_t *bstart, const int32_t *bend,
+                        size_t nblocks, int out_bits, void *out_trimmed, int64_t *out_sums);
+
 /* numerics self-test: log2f(p[i]) and log2(1.0 - (double)p[i]) exactly as glibc 2.39 (FMA build) computes them */
 int wgbs_glibc_log2_probe(wgbs_ctx *, const float *p, size_t n, float *out_log2f, double *out_log2_1mp);
 

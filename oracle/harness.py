@@ -219,3 +219,52 @@ def port_segment(betas, dists: np.ndarray, max_cpg: int, max_bp: int, pseudo: fl
     nb = L.port_segment(ptrs, ctypes.c_int(K), d.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(n), ctypes.c_int(max_cpg),
                         ctypes.c_uint32(max_bp), ctypes.c_float(pseudo), out.ctypes.data_as(ctypes.c_void_p))
     return out[:nb].astype(np.int64)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# cview (reference src/cview/cview.cpp) + the `| sort -k2,2n -k3,3 | collapse_pat.pl -` tail of cview.py
+# ------------------------------------------------------------------------------------------------------------
+def have_cview() -> bool:
+    return os.access(os.path.join(REF, "cview"), os.X_OK)
+
+
+def ref_cview(pat: bytes, *, sites: tuple[int, int] | None = None, blocks_path: str | None = None, strict=False, strip=False,
+              no_gaps=False, min_cpgs: int = 1) -> bytes:
+    """`cview --sites "s\\te" | --blocks_path F [--strict] [--strip] [--no_gaps] [--min_cpgs N]` on pat text"""
+    cmd = [tool("cview")]
+    cmd += ["--sites", f"{sites[0]}\t{sites[1]}"] if sites is not None else ["--blocks_path", blocks_path]
+    cmd += ["--strict"] * bool(strict) + ["--strip"] * bool(strip) + ["--no_gaps"] * bool(no_gaps)
+    if min_cpgs != 1:
+        cmd += ["--min_cpgs", str(min_cpgs)]
+    return subprocess.run(cmd, input=pat, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=_env()).stdout
+
+
+def port_collapse_pat(text: bytes) -> bytes:
+    """restatement of reference src/collapse_pat.pl: adjacent lines equal in every column but the 4th are merged,
+    their counts summed (lines whose summed count is 0 vanish)"""
+    out = []; prev = None; count = 0
+    for line in text.splitlines():
+        w = line.split(b"\t")
+        if prev is not None and len(w) <= len(prev) and all(w[i] == prev[i] for i in range(len(w)) if i != 3):
+            count += int(w[3])
+        else:
+            if prev is not None and count > 0:
+                prev[3] = b"%d" % count; out.append(b"\t".join(prev))
+            count = int(w[3])
+        prev = w
+    if prev is not None and count > 0:
+        prev[3] = b"%d" % count; out.append(b"\t".join(prev))
+    return b"".join(l + b"\n" for l in out)
+
+
+def ref_collapse_pat(text: bytes) -> bytes | None:
+    """the reference's own perl script, where /root/reference is mounted (this container only)"""
+    script = "/root/reference/src/collapse_pat.pl"
+    if not os.path.isfile(script):
+        return None
+    f = write_tmp(text, ".pat")
+    return subprocess.run(["perl", script, f], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=_env()).stdout
+
+
+def sort_pat(text: bytes) -> bytes:
+    return subprocess.run(["sort", "-k2,2n", "-k3,3"], input=text, stdout=subprocess.PIPE, env=_env()).stdout

@@ -113,3 +113,78 @@ def test_segment_cli_blocks(world):
     for r in rows[:50] + rows[-50:]:
         s, e = int(r[3]), int(r[4])
         assert r[0] == ("chr1" if s <= n1 else "chr2") and int(r[1]) == loci[s - 1] and int(r[2]) == loci[e - 2] + 1
+
+
+def test_view_cli_region_sites_bed_and_whole_file(world, tmp_path):
+    """`wgbstools view X.pat.gz [-r|-s|-L] [--strict --strip --no_gaps --min_len]` against
+    [tabix |] cview | [sort |] collapse_pat.pl with the reference cview executable (tabix's selection restated)"""
+    from wgbs_tools_b200 import view
+    w = world; H = w["H"]
+    if not H.have_cview():
+        pytest.skip("reference cview not built")
+    pat = w["pat"]; N = w["N"]; g1, g2 = w["g1"], w["g2"]
+    pg = w["dir"] / "v.pat.gz"; pg.write_bytes(gzip.compress(pat))
+    lines = pat.splitlines(keepends=True)
+    idx = np.array([int(l.split(b"\t")[1]) for l in lines]); chrom = np.array([l.split(b"\t")[0] for l in lines])
+
+    def run(*argv):
+        o = tmp_path / "view.out"
+        view.main([str(pg), "--genome", w["refdir"], "-o", str(o), *argv])
+        return o.read_bytes()
+
+    flagsets = [([], {}), (["--strict"], dict(strict=True)), (["--strict", "--strip", "--min_len", "3"], dict(strict=True, strip=True, min_cpgs=3)),
+                (["--no_gaps", "--strip"], dict(no_gaps=True, strip=True))]
+    # whole file: gunzip -c | cview --sites "1\tN+1" | collapse_pat.pl (no sort)
+    for argv, kw in flagsets:
+        assert run(*argv) == H.port_collapse_pat(H.ref_cview(pat, sites=(1, N + 1), **kw)), argv
+    # -r on chr2 and -s: tabix pat chr:(s-150)-(e-1) | cview --sites | sort | collapse
+    lo, hi = int(g2.loci[2000]), int(g2.loci[2300])
+    s = g2.first_idx + 2000; e = g2.first_idx + 2300                     # the CpG sitting on `hi` is excluded
+    for sel in (["-r", f"chr2:{lo}-{hi}"], ["-s", f"{s}-{e}"]):
+        m = (chrom == b"chr2") & (idx >= max(1, s - 150, g2.first_idx)) & (idx <= e - 1)
+        sub = b"".join(l for l, k in zip(lines, m) if k)
+        for argv, kw in flagsets:
+            exp = H.port_collapse_pat(H.sort_pat(H.ref_cview(sub, sites=(s, e), **kw)))
+            assert exp and run(*sel, *argv) == exp, (sel, argv)
+        assert run(*sel, "--no_sort", "--strip") == H.port_collapse_pat(H.ref_cview(sub, sites=(s, e), strip=True))
+    # a region at the very start of chr2 must not pull chr1 reads (tabix is per chromosome)
+    s0 = g2.first_idx; m = (chrom == b"chr2") & (idx <= s0 + 49)
+    sub = b"".join(l for l, k in zip(lines, m) if k)
+    assert run("-s", f"{s0}-{s0 + 50}") == H.port_collapse_pat(H.sort_pat(H.ref_cview(sub, sites=(s0, s0 + 50))))
+    # -L: blocks on both chromosomes; tabix -R over the blocks extended by 100 sites
+    rng = np.random.default_rng(8)
+    cuts = np.sort(rng.choice(np.arange(2, N), size=400, replace=False)); bl = list(zip(cuts[0::2].tolist(), cuts[1::2].tolist()))
+    loci = np.concatenate([g1.loci, g2.loci])
+    bed = tmp_path / "view_blocks.bed"
+    bed.write_text("#chr\tstart\tend\tstartCpG\tendCpG\n" + "".join(
+        f"{'chr1' if a <= g1.n_cpg else 'chr2'}\t{loci[a - 1]}\t{loci[b - 2] + 1}\t{a}\t{b}\n" for a, b in bl) + "chr2\t5\t6\tNA\tNA\n")
+    keep = np.zeros(len(lines), bool)
+    for a, b in bl:
+        keep |= (idx >= max(1, a - 100)) & (idx <= b)
+    sub = b"".join(l for l, k in zip(lines, keep) if k)
+    for argv, kw in flagsets:
+        exp = H.port_collapse_pat(H.sort_pat(H.ref_cview(sub, blocks_path=str(bed), **kw)))
+        assert len(exp) > 1000 and run("-L", str(bed), *argv) == exp, argv
+
+
+def test_view_cli_beta_and_beta_to_blocks_cli(world, tmp_path):
+    from wgbs_tools_b200 import beta_to_blocks, view
+    w = world; H = w["H"]; N = w["N"]
+    beta = synth.make_betas(5, 1, N)[0]
+    bp = tmp_path / "t.beta"; beta.tofile(bp)
+    o = tmp_path / "b.txt"
+    view.main([str(bp), "--genome", w["refdir"], "-s", "100-104", "-o", str(o)])
+    loci = np.concatenate([w["g1"].loci, w["g2"].loci])
+    assert o.read_bytes() == b"".join(b"chr1\t%d\t%d\t%d\t%d\n" % (loci[i] - 1, loci[i] + 1, beta[i, 0], beta[i, 1]) for i in range(99, 103))
+    blocks = synth.make_blocks(3, 1, N, mean_len=12.0)
+    bed = tmp_path / "bl.bed"
+    bed.write_bytes(b"chr\tstart\tend\tstartCpG\tendCpG\n" + synth.blocks_text("chr1", blocks, loci) + b"chr2\t1\t2\tNA\tNA\n")
+    out = tmp_path / "o"; out.mkdir()
+    beta_to_blocks.main([str(bp), "-b", str(bed), "-o", str(out), "--bedGraph"])
+    beta_to_blocks.main([str(bp), "-b", str(bed), "-o", str(out), "-l"])
+    sums = np.array([beta[s - 1:e - 1].sum(axis=0, dtype=np.int64) for s, e in blocks.tolist()] + [[0, 0]])
+    assert (out / "t.bin").read_bytes() == H.ref_trim(sums).tobytes()
+    assert (out / "t.lbeta").read_bytes() == H.ref_trim(sums, lbeta=True).tobytes()
+    bg = (out / "t.bedGraph").read_text().splitlines()
+    assert len(bg) == sums.shape[0] and bg[-1].endswith("\t-1\t0")
+    t = bg[0].split("\t"); assert t[3] == "%.2f" % (sums[0, 0] / sums[0, 1]) and int(t[4]) == sums[0, 1]

@@ -62,6 +62,9 @@ def _load():
         "wgbs_pileup_sam_mbias": (C.c_int, [vp, vp, vp, sz, vp, C.POINTER(vp), vp, vp]),
         "wgbs_collapse": (C.c_int, [vp, vp]),
         "wgbs_collapse_long": (C.c_int, [vp, vp]),
+        "wgbs_collapse_ex": (C.c_int, [vp, vp, C.c_int]),
+        "wgbs_cview": (C.c_int, [vp, vp, vp, vp, sz, vp, vp, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+        "wgbs_beta_to_blocks": (C.c_int, [vp, vp, C.c_int, sz, vp, vp, sz, C.c_int, vp, vp]),
         "wgbs_pats_format_long": (C.c_int, [vp, vp, C.c_char_p, vp, sz, C.POINTER(sz)]),
         "wgbs_pats_format": (C.c_int, [vp, vp, C.c_char_p, vp, sz, C.POINTER(sz)]),
         "wgbs_sort_pairs_u32": (C.c_int, [vp, vp, vp, sz]),

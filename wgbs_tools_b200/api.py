@@ -86,10 +86,27 @@ class Pats:
             out.append(lut[sym].tobytes())
         return out
 
-    def collapse(self, long: bool = False) -> "Pats":
-        """sort -k2,2n -k3,3 | uniq -c (in place); long=True: only sort (by idx, pattern, read name), no uniq (--long)"""
-        check((lib.wgbs_collapse_long if long else lib.wgbs_collapse)(self.ctx.h, self.h))
+    def collapse(self, long: bool = False, mode: int | None = None) -> "Pats":
+        """sort -k2,2n -k3,3 | uniq -c (in place); long=True: only sort (by idx, pattern, read name), no uniq (--long).
+        mode: WGBS_COLLAPSE_* (2 = patterns may end in '.', 3 = merge adjacent identical records only, no sort)."""
+        if mode is not None:
+            check(lib.wgbs_collapse_ex(self.ctx.h, self.h, int(mode)))
+        else:
+            check((lib.wgbs_collapse_long if long else lib.wgbs_collapse)(self.ctx.h, self.h))
         return self
+
+    def cview(self, bstart, bend, strict: bool = False, strip: bool = False, no_gaps: bool = False, min_cpgs: int = 1, pre=None) -> "Pats":
+        """`cview --blocks_path/--sites ... [--strict] [--strip] [--no_gaps] [--min_cpgs N]` on these records (file order).
+        bstart/bend: blocks [startCpG, endCpG) sorted by start.  pre: optional (lo[], hi[]) closed ranges of start indices
+        (the `tabix` pre-selection).  Returns new Pats, not yet sorted / collapsed."""
+        bs = np.ascontiguousarray(bstart, np.int32); be = np.ascontiguousarray(bend, np.int32)
+        pl = ph = None; npre = 0
+        if pre is not None:
+            pl = np.ascontiguousarray(pre[0], np.int32); ph = np.ascontiguousarray(pre[1], np.int32); npre = pl.size
+        h = C.c_void_p()
+        check(lib.wgbs_cview(self.ctx.h, self.h, bs.ctypes.data, be.ctypes.data, bs.size, pl.ctypes.data if npre else None,
+                             ph.ctypes.data if npre else None, npre, int(strict), int(strip), int(no_gaps), int(min_cpgs), C.byref(h)))
+        return Pats(self.ctx, h.value)
 
     def to_text(self, chrom: str, out=None, long: bool = False):
         """pat text.  out: optional preallocated host uint8 array or DevBuf (then the number of bytes is returned).
@@ -273,6 +290,20 @@ class Context:
         check(lib.wgbs_pat2beta_text(self.h, a.ctypes.data, a.size, start, end, nbits, out.ctypes.data,
                                      mc.ctypes.data if mc is not None else None))
         return (out, mc) if want_counts else out
+
+    def beta_to_blocks(self, beta: np.ndarray, bstart, bend, out_bits: int | None = 8, want_sums: bool = False):
+        """per-block (meth, cover) sums of a beta array (uint8[N,2] or uint16[N,2]); returns the trimmed `.bin`/`.lbeta`
+        rows (out_bits 8 / 16), the raw int64 sums (want_sums), or both (reference beta_to_blocks.py:101-150)."""
+        b = np.ascontiguousarray(beta)
+        if b.dtype not in (np.uint8, np.uint16) or b.ndim != 2 or b.shape[1] != 2:
+            raise ValueError("beta must be uint8[N,2] or uint16[N,2]")
+        bs = np.ascontiguousarray(bstart, np.int32); be = np.ascontiguousarray(bend, np.int32)
+        out = np.zeros((bs.size, 2), np.uint8 if out_bits == 8 else np.uint16) if out_bits else None
+        sums = np.zeros((bs.size, 2), np.int64) if want_sums else None
+        check(lib.wgbs_beta_to_blocks(self.h, b.ctypes.data, 8 * b.dtype.itemsize, b.shape[0], bs.ctypes.data, be.ctypes.data, bs.size,
+                                      int(out_bits or 0), out.ctypes.data if out is not None else None,
+                                      sums.ctypes.data if sums is not None else None))
+        return (out, sums) if (out is not None and want_sums) else (sums if want_sums else out)
 
     def homog(self, pats: Pats, blocks: np.ndarray, rng, min_cpgs: int, inclusive: bool = False) -> np.ndarray:
         bs = np.ascontiguousarray(blocks[:, 0], np.int32); be = np.ascontiguousarray(blocks[:, 1], np.int32)

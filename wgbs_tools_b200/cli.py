@@ -3,7 +3,7 @@ for the four hot-path commands (+ init_genome, which builds the CpG dictionary t
 import importlib
 import sys
 
-COMMANDS = ("bam2pat", "pat2beta", "homog", "segment", "init_genome")
+COMMANDS = ("bam2pat", "pat2beta", "homog", "segment", "init_genome", "view", "cview", "beta_to_blocks")
 
 
 def main():
@@ -11,7 +11,7 @@ def main():
         print("Usage: wgbstools_b200 <command> [<args>]\nCommands: " + ", ".join(COMMANDS), file=sys.stderr)
         sys.exit(1 if len(sys.argv) < 2 or sys.argv[1] not in ("-h", "--help") else 0)
     try:
-        importlib.import_module("wgbs_tools_b200." + sys.argv[1]).main(sys.argv[2:])
+        importlib.import_module("wgbs_tools_b200." + {"cview": "view"}.get(sys.argv[1], sys.argv[1])).main(sys.argv[2:])
     except ValueError as e:                                         # IllegalArgumentError (utils_wgbs.py:47-51)
         print(f"Invalid input argument\n{e}", file=sys.stderr)
         sys.exit(1)

@@ -53,6 +53,8 @@ __device__ __forceinline__ int name_cmp(const PatsView &P, uint32_t a, uint32_t 
     for (uint32_t k = 0; k < m; k++) if (x[k] != y[k]) return x[k] < y[k] ? -1 : 1;
     return la < lb ? -1 : (la > lb ? 1 : 0);
 }
+// mode 0: patterns never end in '.', zero padding orders them; 1 (--long): ties go to the read name; 2 (cview output: a clipped
+// pattern may end in '.'): equal zero-padded words are ordered shorter first, as `sort -k3,3` orders "C" before "C."
 __global__ void __launch_bounds__(128) fix_ties_k(PatsView P, uint32_t *__restrict__ perm, const uint32_t *__restrict__ key /*sorted*/, uint32_t nsym, int by_name) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
@@ -65,12 +67,17 @@ __global__ void __launch_bounds__(128) fix_ties_k(PatsView P, uint32_t *__restri
         const uint32_t v = perm[k]; size_t q = k;
         while (q > i) {
             int c = pat_cmp(P, perm[q - 1], v);
-            if (c == 0 && by_name) c = name_cmp(P, perm[q - 1], v);
+            if (c == 0 && by_name == 1) c = name_cmp(P, perm[q - 1], v);
+            if (c == 0 && by_name == 2) c = P.len[perm[q - 1]] < P.len[v] ? -1 : (P.len[perm[q - 1]] > P.len[v] ? 1 : 0);
             if (c <= 0) break;
             perm[q] = perm[q - 1]; q--;
         }
         perm[q] = v;
     }
+}
+__global__ void __launch_bounds__(256) iota_k(uint32_t *__restrict__ p, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (uint32_t)i;
 }
 __global__ void __launch_bounds__(256) permute_long_k(PatsView P, const uint32_t *__restrict__ perm, uint32_t *__restrict__ o_idx, uint32_t *__restrict__ o_len,
                                                        uint32_t *__restrict__ o_off, uint32_t *__restrict__ o_cnt, uint32_t *__restrict__ o_noff,
@@ -172,7 +179,9 @@ __global__ void __launch_bounds__(256) line_write_long_k(PatsView P, const char 
 
 }  // namespace
 
-static int collapse_impl(wgbs_ctx *ctx, wgbs_pats *P, bool long_mode) {
+// mode: WGBS_COLLAPSE_* (include/wgbs_b200.h)
+static int collapse_impl(wgbs_ctx *ctx, wgbs_pats *P, int mode) {
+    const bool long_mode = mode == WGBS_COLLAPSE_LONG;
     RC_TRY(wgbs_ctx_activate(ctx));
     if (!P) return wgbs_set_err("null pats");
     if (long_mode && P->n && !P->names) return wgbs_set_err("wgbs_collapse_long: records carry no read names (set opts.keep_names in the pileup)");
@@ -192,9 +201,13 @@ static int collapse_impl(wgbs_ctx *ctx, wgbs_pats *P, bool long_mode) {
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     uint32_t range = mm[1] - mm[0], ibits = 0; while (ibits < 32 && (range >> ibits)) ibits++;
     const uint32_t nsym = (32 - ibits) / 2 > 16 ? 16 : (32 - ibits) / 2;
-    LAUNCH(ctx, make_key_k, grid_for(n, 256), 256, 0, pv, mm[0], nsym, k, v);
-    RC_TRY(radix_sort_pairs(ctx, &k, &v, &ka, &va, n));
-    LAUNCH(ctx, fix_ties_k, grid_for(n, 128), 128, 0, pv, v, k, nsym, long_mode ? 1 : 0);   // longer patterns (and names): order inside equal-key runs
+    if (mode == WGBS_COLLAPSE_ADJACENT) {
+        LAUNCH(ctx, iota_k, grid_for(n, 256), 256, 0, v, n);          // no sort: only adjacent equal records merge (collapse_pat.pl on unsorted input)
+    } else {
+        LAUNCH(ctx, make_key_k, grid_for(n, 256), 256, 0, pv, mm[0], nsym, k, v);
+        RC_TRY(radix_sort_pairs(ctx, &k, &v, &ka, &va, n));
+        LAUNCH(ctx, fix_ties_k, grid_for(n, 128), 128, 0, pv, v, k, nsym, long_mode ? 1 : (mode == WGBS_COLLAPSE_DOTTED ? 2 : 0));   // longer patterns (and names): order inside equal-key runs
+    }
     if (long_mode) {
         // no uniq in --long: the records are only re-ordered
         uint32_t *o_idx, *o_len, *o_off, *o_cnt, *o_noff, *o_nlen;
@@ -228,8 +241,12 @@ static int collapse_impl(wgbs_ctx *ctx, wgbs_pats *P, bool long_mode) {
     return 0;
 }
 
-extern "C" int wgbs_collapse(wgbs_ctx *ctx, wgbs_pats *P) { return collapse_impl(ctx, P, false); }
-extern "C" int wgbs_collapse_long(wgbs_ctx *ctx, wgbs_pats *P) { return collapse_impl(ctx, P, true); }
+extern "C" int wgbs_collapse(wgbs_ctx *ctx, wgbs_pats *P) { return collapse_impl(ctx, P, WGBS_COLLAPSE_SORTED); }
+extern "C" int wgbs_collapse_long(wgbs_ctx *ctx, wgbs_pats *P) { return collapse_impl(ctx, P, WGBS_COLLAPSE_LONG); }
+extern "C" int wgbs_collapse_ex(wgbs_ctx *ctx, wgbs_pats *P, int mode) {
+    if (mode < WGBS_COLLAPSE_SORTED || mode > WGBS_COLLAPSE_ADJACENT) return wgbs_set_err("wgbs_collapse_ex: unknown mode %d", mode);
+    return collapse_impl(ctx, P, mode);
+}
 
 // Write "chrom \t idx \t pattern \t count \n" per record, in record order (reference docs/pat_format.md:3-47).
 // out == NULL: only *nbytes is computed.  out may be host or device.
