@@ -53,6 +53,11 @@ int wgbs_prof_report(wgbs_ctx *, char *buf, size_t cap);
 int wgbs_dev_alloc(wgbs_ctx *, size_t nbytes, void **dptr);
 int wgbs_dev_free(wgbs_ctx *, void *dptr);
 int wgbs_memcpy(wgbs_ctx *, void *dst, const void *src, size_t nbytes); /* any host/device combination */
+/* streaming inputs: begin the host->device copy of the NEXT batch (pinned host memory) on the context's copy stream while
+ * the current batch is being processed; wgbs_prefetch_wait orders the following calls on this context after that copy.
+ * (The reference streams chromosome after chromosome through its pipes, bam2pat.py:319-346; this is the same overlap.) */
+int wgbs_prefetch(wgbs_ctx *, void *dev_dst, const void *host_src, size_t nbytes);
+int wgbs_prefetch_wait(wgbs_ctx *);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * pat records  (on-disk format: reference docs/pat_format.md:3-47  "chr \t idx \t pattern \t count")

@@ -48,6 +48,8 @@ def _load():
         "wgbs_dev_alloc": (C.c_int, [vp, sz, C.POINTER(vp)]),
         "wgbs_dev_free": (C.c_int, [vp, vp]),
         "wgbs_memcpy": (C.c_int, [vp, vp, vp, sz]),
+        "wgbs_prefetch": (C.c_int, [vp, vp, vp, sz]),
+        "wgbs_prefetch_wait": (C.c_int, [vp]),
         "wgbs_pats_from_text": (C.c_int, [vp, vp, sz, C.POINTER(vp)]),
         "wgbs_pats_count": (C.c_int, [vp, C.POINTER(u64), C.POINTER(u64)]),
         "wgbs_pats_download": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),

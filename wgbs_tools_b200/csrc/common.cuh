@@ -37,6 +37,9 @@ struct wgbs_ctx {
     // pinned staging buffers (grown on demand)
     void *pin[2] = {nullptr, nullptr};
     size_t pin_cap[2] = {0, 0};
+    // second stream for wgbs_prefetch: host->device copies that overlap the kernels of the previous batch
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy = nullptr, ev_comp = nullptr;
     // small device scratch for flags / counters
     uint32_t *d_flags = nullptr;  // 64 words
     // optional per-kernel timing (wgbs_prof_enable): one event pair per launch, aggregated by kernel name

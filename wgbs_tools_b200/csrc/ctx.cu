@@ -64,6 +64,9 @@ extern "C" void wgbs_destroy(wgbs_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 2; i++) if (ctx->pin[i]) cudaFreeHost(ctx->pin[i]);
     if (ctx->d_flags) cudaFree(ctx->d_flags);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+    if (ctx->ev_comp) cudaEventDestroy(ctx->ev_comp);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -71,6 +74,32 @@ extern "C" void wgbs_destroy(wgbs_ctx *ctx) {
 extern "C" int wgbs_sync(wgbs_ctx *ctx) {
     RC_TRY(wgbs_ctx_activate(ctx));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// Streaming inputs: start the host->device copy of the NEXT batch on the context's copy stream while the kernels of the
+// current batch run (PCIe is the bottleneck of the end-to-end path: 357 MB of SAM text per 1M reads).  The copy is ordered
+// after everything already enqueued on the compute stream (the destination buffer may still be in use by it);
+// wgbs_prefetch_wait makes the compute stream wait for the last prefetch.  host_src should be pinned memory
+// (cudaHostAlloc / torch pin_memory): a pageable source makes cudaMemcpyAsync synchronous.
+extern "C" int wgbs_prefetch(wgbs_ctx *ctx, void *dev_dst, const void *host_src, size_t nbytes) {
+    RC_TRY(wgbs_ctx_activate(ctx));
+    if (!dev_dst || !host_src) return wgbs_set_err("wgbs_prefetch: null argument");
+    if (!is_device_ptr(dev_dst) || is_device_ptr(host_src)) return wgbs_set_err("wgbs_prefetch: dst must be device memory, src host memory");
+    if (!ctx->copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_comp, cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventRecord(ctx->ev_comp, ctx->stream));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_comp, 0));
+    CUDA_TRY(cudaMemcpyAsync(dev_dst, host_src, nbytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CUDA_TRY(cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+    return 0;
+}
+extern "C" int wgbs_prefetch_wait(wgbs_ctx *ctx) {
+    RC_TRY(wgbs_ctx_activate(ctx));
+    if (ctx->ev_copy) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
     return 0;
 }
 
