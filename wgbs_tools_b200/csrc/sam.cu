@@ -9,6 +9,12 @@
 #include "lines.cuh"
 #include "reads.cuh"
 
+#ifndef WGBS_NLSCAN_DEFAULT_WARP
+#define WGBS_NLSCAN_DEFAULT_WARP 0
+#endif
+#ifndef WGBS_LINES_PF_DEFAULT
+#define WGBS_LINES_PF_DEFAULT 1
+#endif
 #ifndef WGBS_TOKENIZER_DEFAULT_FUSED
 #define WGBS_TOKENIZER_DEFAULT_FUSED 0
 #endif
@@ -147,6 +153,81 @@ __global__ void __launch_bounds__(NLS_T) nl_scan_k(const char *__restrict__ text
     }
 }
 
+// Variant of nl_scan_k without block-wide barriers: every WARP is its own 8 KiB tile with its own ticket and its own
+// look-back, so no warp ever waits for the look-back of another one (the barrier stall was the top stall reason of the
+// CTA-wide version).  Selected with WGBS_NLSCAN=warp|cta.
+constexpr int NLW_T = 128, NLW_TILE = 32 * NLS_ROUNDS * 16;            // 8 KiB per warp
+__global__ void __launch_bounds__(NLW_T) nl_scan_warp_k(const char *__restrict__ text, size_t n, uint32_t cap,
+                                                         unsigned long long *__restrict__ status, unsigned int *__restrict__ ticket,
+                                                         uint32_t *__restrict__ nlpos, uint32_t *__restrict__ total) {
+    __shared__ __align__(16) uint16_t sm_mask[(NLW_T / 32) * 32 * NLS_ROUNDS];
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned tile = 0;
+    if (lane == 0) tile = atomicAdd(ticket, 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    const size_t warp0 = (size_t)tile * NLW_TILE;
+    if (warp0 >= n) return;                                          // whole warp: grid is rounded up to full CTAs
+    uint16_t *mym = sm_mask + w * (32 * NLS_ROUNDS);
+#pragma unroll
+    for (int h = 0; h < NLS_ROUNDS; h += 8) {                        // 8 independent 16-byte loads in flight per lane
+        uint4 v[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const size_t p = warp0 + (size_t)((h + c) * 32 + lane) * 16;
+            v[c] = make_uint4(0, 0, 0, 0);
+            if (p < n) v[c] = (p + 16 <= n) ? *reinterpret_cast<const uint4 *>(text + p) : load16_guard(text, p, n);
+        }
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const size_t p = warp0 + (size_t)((h + c) * 32 + lane) * 16;
+            uint32_t nm = 0;
+            if (p < n) { nm = eq_mask16(v[c], '\n'); if (n - p < 16) nm &= (1u << (n - p)) - 1; }
+            mym[(h + c) * 32 + lane] = (uint16_t)nm;
+        }
+    }
+    __syncwarp();
+    const uint4 q0 = *reinterpret_cast<const uint4 *>(&mym[lane * 16]);
+    const uint4 q1 = *reinterpret_cast<const uint4 *>(&mym[lane * 16 + 8]);
+    const uint32_t mk[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) cnt += __popc(mk[i]);
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (unsigned)d) inc += t; }
+    const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+    volatile unsigned long long *st = status;
+    uint64_t base = 0;
+    if (tile == 0) { if (lane == 0) st[0] = NS_INC | tot; }
+    else {
+        if (lane == 0) st[tile] = NS_AGG | tot;
+        long long top = (long long)tile - 1;
+        while (true) {
+            const long long j = top - lane;
+            unsigned long long x = NS_INC;
+            if (j >= 0) x = st[j];
+            while (__any_sync(0xffffffffu, (x >> 62) == 0)) { if ((x >> 62) == 0) x = st[j]; }
+            const unsigned incm = __ballot_sync(0xffffffffu, (x >> 62) == 2);
+            uint64_t val = x & NS_VAL;
+            if (incm) { const int L = __ffs(incm) - 1; if ((int)lane > L) val = 0; }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+            base += val;
+            if (incm) break;
+            top -= 32;
+        }
+        if (lane == 0) st[tile] = NS_INC | ((base + tot) & NS_VAL);
+    }
+    if (lane == 0 && warp0 + NLW_TILE >= n) *total = (uint32_t)(base + tot);
+    uint32_t o = (uint32_t)base + inc - cnt;
+    const size_t p0 = warp0 + (size_t)lane * 256;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t m = mk[i];
+        while (m) { const int b = __ffs(m) - 1; m &= m - 1; if (o < cap) nlpos[o] = (uint32_t)(p0 + (size_t)i * 32 + b); o++; }
+    }
+}
+
 // per-(byte, position) mixing summed over the name: independent of alignment
 __device__ __forceinline__ uint64_t name_byte_mix(uint32_t byte, uint32_t pos) {
     uint64_t x = ((uint64_t)(byte | (pos << 8)) + 1) * 0x9e3779b97f4a7c15ULL;
@@ -154,6 +235,8 @@ __device__ __forceinline__ uint64_t name_byte_mix(uint32_t byte, uint32_t pos) {
     return x;
 }
 
+// PF: 16-byte chunks fetched together (independent loads in flight per thread) before they are examined one by one
+template <int PF>
 __global__ void __launch_bounds__(128) sam_lines_k(const char *__restrict__ text, uint32_t n, const uint32_t *__restrict__ nlpos, uint32_t n_nl,
                                                     uint32_t n_lines, int want_tags, ReadBatch rb) {
     const uint32_t line = blockIdx.x * blockDim.x + threadIdx.x;
@@ -162,8 +245,27 @@ __global__ void __launch_bounds__(128) sam_lines_k(const char *__restrict__ text
     const uint32_t e = line < n_nl ? nlpos[line] : n;
     uint32_t tb[10];
     uint32_t ntab = 0, mm_off = 0, ml_off = 0;
-    for (uint32_t base = s & ~15u; base < e; base += 16) {
-        const uint4 v = (base + 16 <= n) ? *reinterpret_cast<const uint4 *>(text + base) : load16_guard(text, base, n);
+    uint4 buf[PF];
+    for (uint32_t base = s & ~15u, k = PF; base < e; base += 16, k++) {
+        if (PF > 1) {
+            if (k >= PF) {                                           // refill: PF loads issued back to back
+#pragma unroll
+                for (int j = 0; j < PF; j++) {
+                    const uint32_t b2 = base + 16 * j;
+                    buf[j] = make_uint4(0, 0, 0, 0);
+                    if (b2 < e) buf[j] = (b2 + 16 <= n) ? *reinterpret_cast<const uint4 *>(text + b2) : load16_guard(text, b2, n);
+                }
+                k = 0;
+            }
+        }
+        uint4 v;
+        if (PF > 1) {
+            v = buf[0];
+#pragma unroll
+            for (int j = 1; j < PF; j++) if (k == j) v = buf[j];
+        } else {
+            v = (base + 16 <= n) ? *reinterpret_cast<const uint4 *>(text + base) : load16_guard(text, base, n);
+        }
         uint32_t m = eq_mask16(v, '\t');
         if (base < s) m &= 0xffffu << (s - base);
         if (e - base < 16) m &= (1u << (e - base)) - 1;
@@ -524,7 +626,10 @@ int sam_tokenize(wgbs_ctx *ctx, const char *dtext, size_t nbytes, int want_tags 
     rb.text = dtext; rb.nbytes = (uint32_t)nbytes;
     uint32_t *nlpos = nullptr, *totals = ctx->d_flags + 8;
     unsigned long long *status = nullptr;
-    if (ntiles) RC_TRY(T.alloc(&status, (size_t)ntiles + 1));
+    static const int warp_scan = [] { const char *e = getenv("WGBS_NLSCAN"); return (e && !strcmp(e, "warp")) ? 1 : (e && !strcmp(e, "cta")) ? 0 : WGBS_NLSCAN_DEFAULT_WARP; }();
+    static const int lines_pf = [] { const char *e = getenv("WGBS_LINES_PF"); return e ? atoi(e) : WGBS_LINES_PF_DEFAULT; }();
+    const uint32_t wtiles = (uint32_t)((nbytes + NLW_TILE - 1) / NLW_TILE);
+    if (ntiles) RC_TRY(T.alloc(&status, (size_t)(warp_scan ? wtiles : ntiles) + 1));
     uint32_t cap = (uint32_t)(nbytes / 64 + 1024);            // optimistic: average line >= 64 bytes (a 50 bp SAM record is ~130)
     uint32_t n_nl = 0, first_mm = 0; char last = '\n';
     // first_line (patter.cpp:337-338): does the first non-empty line carry an MM tag?  Decided on the host from the head of the
@@ -533,8 +638,9 @@ int sam_tokenize(wgbs_ctx *ctx, const char *dtext, size_t nbytes, int want_tags 
     for (int attempt = 0; attempt < 2 && ntiles; attempt++) {
         if (nlpos) { T.keep(nlpos); dfree(ctx, nlpos); }
         RC_TRY(T.alloc(&nlpos, cap));
-        CUDA_TRY(cudaMemsetAsync(status, 0, ((size_t)ntiles + 1) * 8, ctx->stream));
-        LAUNCH(ctx, nl_scan_k, ntiles, NLS_T, 0, dtext, nbytes, cap, status, (unsigned int *)(status + ntiles), nlpos, totals);
+        CUDA_TRY(cudaMemsetAsync(status, 0, ((size_t)(warp_scan ? wtiles : ntiles) + 1) * 8, ctx->stream));
+        if (warp_scan) LAUNCH(ctx, nl_scan_warp_k, (wtiles + NLW_T / 32 - 1) / (NLW_T / 32), NLW_T, 0, dtext, nbytes, cap, status, (unsigned int *)(status + wtiles), nlpos, totals);
+        else LAUNCH(ctx, nl_scan_k, ntiles, NLS_T, 0, dtext, nbytes, cap, status, (unsigned int *)(status + ntiles), nlpos, totals);
         CUDA_TRY(cudaMemcpyAsync(&n_nl, totals, 4, cudaMemcpyDeviceToHost, ctx->stream));
         if (attempt == 0 && !head.empty()) CUDA_TRY(cudaMemcpyAsync(head.data(), dtext, head.size(), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(&last, dtext + nbytes - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
@@ -576,7 +682,9 @@ int sam_tokenize(wgbs_ctx *ctx, const char *dtext, size_t nbytes, int want_tags 
         RC_TRY(T.alloc(&rb.ml_off, n_lines)); RC_TRY(T.alloc(&rb.ml_len, n_lines));
     }
     if (n_lines) {
-        LAUNCH(ctx, sam_lines_k, grid_for(n_lines, 128), 128, 0, dtext, (uint32_t)nbytes, nlpos, n_nl, n_lines, tags ? 1 : 0, rb);
+        if (lines_pf >= 4) LAUNCH(ctx, sam_lines_k<4>, grid_for(n_lines, 128), 128, 0, dtext, (uint32_t)nbytes, nlpos, n_nl, n_lines, tags ? 1 : 0, rb);
+        else if (lines_pf >= 2) LAUNCH(ctx, sam_lines_k<2>, grid_for(n_lines, 128), 128, 0, dtext, (uint32_t)nbytes, nlpos, n_nl, n_lines, tags ? 1 : 0, rb);
+        else LAUNCH(ctx, sam_lines_k<1>, grid_for(n_lines, 128), 128, 0, dtext, (uint32_t)nbytes, nlpos, n_nl, n_lines, tags ? 1 : 0, rb);
         LAUNCH_CHECK();
     }
     *out = rb;
