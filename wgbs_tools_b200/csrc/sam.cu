@@ -13,7 +13,7 @@
 #define WGBS_NLSCAN_DEFAULT_WARP 0
 #endif
 #ifndef WGBS_LINES_PF_DEFAULT
-#define WGBS_LINES_PF_DEFAULT 1
+#define WGBS_LINES_PF_DEFAULT 2
 #endif
 #ifndef WGBS_TOKENIZER_DEFAULT_FUSED
 #define WGBS_TOKENIZER_DEFAULT_FUSED 0
