@@ -55,3 +55,59 @@ def test_two_rank_reduce_then_trim(oracle, tmp_path):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok").exists()
+
+
+def test_shard_lines_partitions_at_line_boundaries():
+    txt = b"".join(b"l%d\t%s\n" % (i, b"x" * (i % 17)) for i in range(1000)) + b"last-without-newline"
+    for world in (1, 2, 3, 8, 50):
+        parts = [wd.shard_lines(txt, r, world) for r in range(world)]
+        assert b"".join(parts) == txt
+        assert all(p.endswith(b"\n") for p in parts[:-1] if p)
+    assert wd.shard_lines(b"", 0, 4) == b"" and [wd.shard_lines(b"a\n", r, 4) for r in range(4)].count(b"a\n") == 1
+
+
+def _worker2(rank, world, port, tmp):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import harness as H
+    from wgbs_tools_b200 import segment as sg
+    # homog: records sharded by line ranges, every rank sees all blocks, ONE reduce of the bins
+    N = 5000
+    idx, pats, cnt = synth.make_pat_records(11, 15_000, N, mean_len=6)
+    txt = synth.pat_text("chr1", idx, pats, cnt)
+    blocks = synth.make_blocks(4, 1, N, mean_len=9.0)[:-40]                 # records past the last block exist: the cut-off rule is per record
+    edges = np.array([0, 0.334, 0.667, 1], np.float32)
+    mine = H.port_homog(wd.shard_lines(txt, rank, world), blocks, edges, 3)
+    tot = wd.reduce_np(mine.astype(np.int32), 0)
+    # segment: the DPs of a round dealt round-robin, all borders on all ranks, identical stitching everywhere
+    betas = synth.make_betas(9, 3, 3000)
+    loci = synth.make_genome(2, "chr1", 600_000, with_bases=False).loci[:3000].astype(np.int64)
+    calls = []
+
+    def solve(sites):
+        calls.append(len(sites))
+        return [H.port_segment([b[s - 1:e - 1] for b in betas], loci[s - 1:e - 1], 100, 1500, 15) + s for s, e in sites]
+    got = sg.segment_regions([(1, 1501), (1501, 3001)], wd.DistSolver(solve), 400)
+    every = [None] * world
+    dist.all_gather_object(every, got.tolist())
+    if rank == 0:
+        assert np.array_equal(tot, H.port_homog(txt, blocks, edges, 3)) and tot.sum() > 1000
+        ref_calls = []
+
+        def solve1(sites):
+            ref_calls.append(len(sites))
+            return [H.port_segment([b[s - 1:e - 1] for b in betas], loci[s - 1:e - 1], 100, 1500, 15) + s for s, e in sites]
+        exp = sg.segment_regions([(1, 1501), (1501, 3001)], solve1, 400)
+        assert np.array_equal(got, exp) and all(e == exp.tolist() for e in every)
+        assert sum(calls) < sum(ref_calls)                                   # this rank solved only its share
+        open(os.path.join(tmp, "ok2"), "w").write("1")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_homog_reduce_and_segment_round_robin(oracle, tmp_path):
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_worker2, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok2").exists()

@@ -94,6 +94,12 @@ class _Source:
             return self.bam.view(chrom, beg=beg, end=end, **kw)
         return filter_sam(self.sam.get(chrom, b""), chrom=chrom, beg=beg, end=end, **kw)
 
+    def weight(self, chrom: str) -> int:
+        """how much work a chromosome is (records in a .bam, bytes of SAM text): the LPT weights of the multi-GPU split"""
+        if self.bam is not None:
+            return self.bam.nrecords(chrom) if chrom in self.bam.refs else 0
+        return len(self.sam.get(chrom, b""))
+
     def close(self):
         if self.bam is not None:
             self.bam.close()
@@ -179,9 +185,14 @@ def main(argv=None):
                 raise IllegalArgumentError(f"Invalid file: {path}")
             lists = (load_bed_intervals(path), excl)
     empty_iv = (np.zeros(0, np.int64), np.zeros(0, np.int64))
-    with Context(0) as ctx:
+    # under torchrun the chromosomes are dealt to the ranks (one GPU each) the way the reference deals them to its worker
+    # pool (bam2pat.py:319-346); pat parts come back in chromosome order, the beta counts through ONE reduce
+    from . import dist as wd
+    rank, world, local = wd.init_from_env()
+    with Context(local) as ctx:
         for path in a.bam:
-            print(f"[wt bam2pat] bam: {path}", file=sys.stderr)
+            if rank == 0:
+                print(f"[wt bam2pat] bam: {path}", file=sys.stderr)
             if path != "-" and not os.path.isfile(path):
                 print(f"[wt bam2pat] Invalid bam: {path}\n[wt bam2pat] Skipping {path}", file=sys.stderr)
                 continue
@@ -215,12 +226,23 @@ def main(argv=None):
                 if not regions:
                     print("[wt bam2pat] Failed retrieving valid chromosome names. Perhaps you are using a wrong genome reference.", file=sys.stderr)
                     raise IllegalArgumentError("Failed")
-            mc = None if a.no_beta else ctx.alloc(ref.nr_sites * 8)
-            if mc is not None:
+            mine = set(range(len(regions)))
+            if world > 1:
+                weights = [src.weight(r.split(":")[0]) for r in regions]
+                mine = set(wd.lpt_assign(weights, world)[rank])
+            if a.no_beta:
+                mc = None
+            elif world > 1:
+                import torch
+                mc = torch.zeros((ref.nr_sites, 2), dtype=torch.int32, device=f"cuda:{local}")     # NCCL reduces it in place
+            else:
+                mc = ctx.alloc(ref.nr_sites * 8)
                 ctx.pat2beta(ctx.pats_from_text(b""), 1, ref.nr_sites + 1, meth_cov=mc, zero_first=True)
             parts = []
             mb_total = None
-            for region in regions:
+            for ri, region in enumerate(regions):
+                if ri not in mine:
+                    continue
                 chrom = region.split(":")[0]
                 kw = dict(mapq=mapq, exclude_flags=ex, include_flags=inc, read_group=a.read_group)
                 if lists is not None:
@@ -234,11 +256,21 @@ def main(argv=None):
                 if a.mbias and "mbias" in st:
                     mb_total = st["mbias"].astype(np.int64) if mb_total is None else mb_total + st["mbias"]   # mbias_merge (bam2pat.py:375-395)
                 if txt:
-                    parts.append(bgzf_compress(txt, a.threads))
+                    parts.append((ri, bgzf_compress(txt, a.threads)))
             src.close()
+            if world > 1:
+                ctx.sync()
+                if mc is not None:
+                    wd.reduce_counts(mc, 0)
+                if a.mbias:
+                    mb_total = wd.reduce_np(np.zeros((2, 2, 1000, 2), np.int64) if mb_total is None else mb_total, 0)
+                parts = [p for lst in wd.gather_parts(parts, 0) or [] for p in lst]
+                if rank != 0:
+                    continue
+            parts = [b for _, b in sorted(parts, key=lambda t: t[0])]
             if not parts:
                 print("[wt bam2pat] No reads found. No pat file is generated", file=sys.stderr)
-                if mc is not None:
+                if mc is not None and hasattr(mc, "free"):
                     mc.free()
                 continue
             with open(pat_path, "wb") as f:
@@ -258,7 +290,8 @@ def main(argv=None):
                 bp = pat_path[:-len(".pat.gz")] + (".lbeta" if a.lbeta else ".beta")
                 beta.tofile(bp)
                 print(f"[wt bam2pat] generated {bp}", file=sys.stderr)
-                mc.free()
+                if hasattr(mc, "free"):
+                    mc.free()
 
 
 if __name__ == "__main__":

@@ -130,7 +130,9 @@ def main(argv=None):
     lines, cols = load_blocks(args.blocks_file)
     outdir = os.path.dirname(args.prefix) if args.prefix else (args.out_dir or ".")
     os.makedirs(outdir or ".", exist_ok=True)
-    with Context(0) as ctx:
+    from . import dist as wd
+    rank, world, local = wd.init_from_env()                            # under torchrun: records sharded over the ranks, ONE reduce of the bins
+    with Context(local) as ctx:
         for pat in sorted(args.input_files):
             name = os.path.basename(pat)
             for suf in (".pat.gz", ".pat"):
@@ -141,9 +143,12 @@ def main(argv=None):
             if os.path.exists(opath) and not args.force:
                 print(f"[ wt homog ] skipping {name}. Use -f to overwrite", file=sys.stderr)
                 continue
-            P = ctx.pats_from_text(read_pat_text(pat))
+            P = ctx.pats_from_text(wd.shard_lines(read_pat_text(pat), rank, world))
             counts = homog_counts(ctx, P, lines, cols, edges, args.rlen, args.inclusive)
             P.free()
+            counts = wd.reduce_np(counts, 0)                           # bins are sums over records: exact under any record split
+            if rank != 0:
+                continue
             if args.binary:
                 trim_uxm_to_uint8(counts, args.nr_bits).tofile(opath)
             else:

@@ -13,8 +13,17 @@ def pat2beta(ctx, pat_path: str, out_dir: str, nr_sites: int, lbeta: bool = Fals
     if os.path.exists(out_beta) and not force:                     # delete_or_skip (utils_wgbs.py:435-454)
         print(f"File {out_beta} already exists. Skipping it. Use -f to overwrite", file=sys.stderr)
         return None
-    text = read_pat_text(pat_path)
-    beta = ctx.pat2beta_text(text, 1, nr_sites + 1, 16 if lbeta else 8)   # `stdin2beta 1 N+1` + trim_to_uint8 (pat2beta.py:32-37)
+    from . import dist as wd
+    rank, world = wd.world()
+    text = wd.shard_lines(read_pat_text(pat_path), rank, world)
+    if world == 1:
+        beta = ctx.pat2beta_text(text, 1, nr_sites + 1, 16 if lbeta else 8)   # `stdin2beta 1 N+1` + trim_to_uint8 (pat2beta.py:32-37)
+    else:                                                           # record-sharded: ONE reduce of the int32 counts, trim afterwards (it is non-linear)
+        _, mc = ctx.pat2beta_text(text, 1, nr_sites + 1, 8, want_counts=True)
+        mc = wd.reduce_np(mc, 0)
+        if rank != 0:
+            return None
+        beta = ctx.trim(mc, nr_sites, 16 if lbeta else 8)
     beta.tofile(out_beta)
     return out_beta
 
@@ -28,7 +37,9 @@ def main(argv=None):
     p.add_argument("--genome"); p.add_argument("-@", "--threads", type=int, default=1)
     a = p.parse_args(argv)
     ref = GenomeRef(a.genome)
-    with Context(0) as ctx:
+    from . import dist as wd
+    _, _, local = wd.init_from_env()
+    with Context(local) as ctx:
         for pat in a.pat_paths:
             pat2beta(ctx, pat, a.out_dir, ref.nr_sites, a.lbeta, a.force)
 

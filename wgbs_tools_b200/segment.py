@@ -204,10 +204,14 @@ def main(argv=None):
         if a.shape[0] != n:
             raise IllegalArgumentError(f"[wt segment] ERROR: current genome reference ({ref.name}) does not match the input beta file ({b}).")
         arrs.append(a)
-    with Context(0) as ctx:
+    from . import dist as wd
+    rank, world, local = wd.init_from_env()                            # under torchrun: the DPs of every round are dealt round-robin to the GPUs
+    with Context(local) as ctx:
         solver = GpuSolver(ctx, arrs, ref.all_loci(), max_cpg, args.max_bp, args.pcount)
-        blocks = filter_min_cpg(segment_regions(regions, solver, args.chunk_size), args.min_cpg)
+        blocks = filter_min_cpg(segment_regions(regions, wd.DistSolver(solver) if world > 1 else solver, args.chunk_size), args.min_cpg)
         solver.close()
+    if rank != 0:
+        return
     print(f"[wt segment] found {blocks.shape[0]:,} blocks", file=sys.stderr)
     lines = add_loci(blocks, ref.chrom_of_site, ref.locus_of_site)
     out = sys.stdout.buffer if args.out_path in (None, "-") else open(args.out_path, "wb")
