@@ -52,6 +52,13 @@ def test_bam2pat_cli_writes_reference_identical_pat_and_beta(world):
     beta = np.fromfile(out / "sample.beta", np.uint8).reshape(-1, 2)
     ref_counts = H.ref_stdin2beta(w["pat"], 1, w["N"] + 1) if H.have_ref() else H.port_pat2beta(w["pat"], 1, w["N"] + 1)
     assert beta.tobytes() == H.ref_trim(ref_counts).tobytes()
+    # the CSI index written next to it (Indxer, bam2pat.py:415): region reads through it == a scan of the text
+    from wgbs_tools_b200 import csi
+    ix = csi.CsiIndex.load(str(out / "sample.pat.gz.csi"))
+    assert ix.names == ["chr1", "chr2"]
+    lo, hi = w["g1"].n_cpg + 500, w["g1"].n_cpg + 900
+    exp = b"".join(l for l in w["pat"].splitlines(keepends=True) if l.startswith(b"chr2\t") and lo <= int(l.split(b"\t")[1]) <= hi)
+    assert exp and csi.read_region(str(out / "sample.pat.gz"), "chr2", lo, hi, ix) == exp
     w["out"] = out
 
 
@@ -147,6 +154,13 @@ def test_view_cli_region_sites_bed_and_whole_file(world, tmp_path):
             exp = H.port_collapse_pat(H.sort_pat(H.ref_cview(sub, sites=(s, e), **kw)))
             assert exp and run(*sel, *argv) == exp, (sel, argv)
         assert run(*sel, "--no_sort", "--strip") == H.port_collapse_pat(H.ref_cview(sub, sites=(s, e), strip=True))
+    # the same region read through a CSI index (BGZF pat + `wgbstools index`): only the indexed blocks are inflated
+    from wgbs_tools_b200 import index as windex
+    from wgbs_tools_b200.patio import bgzf_compress
+    pz = tmp_path / "vi.pat.gz"; pz.write_bytes(bgzf_compress(pat, 2)); windex.main([str(pz)])
+    o2 = tmp_path / "view2.out"
+    view.main([str(pz), "--genome", w["refdir"], "-o", str(o2), "-s", f"{s}-{e}", "--strict"])
+    assert o2.read_bytes() == run("-s", f"{s}-{e}", "--strict")
     # a region at the very start of chr2 must not pull chr1 reads (tabix is per chromosome)
     s0 = g2.first_idx; m = (chrom == b"chr2") & (idx <= s0 + 49)
     sub = b"".join(l for l, k in zip(lines, m) if k)

@@ -275,6 +275,8 @@ def main(argv=None):
                 continue
             with open(pat_path, "wb") as f:
                 f.write(b"".join(parts))                                       # `cat parts` (bam2pat.py:408)
+            from .csi import index_pat
+            index_pat(pat_path)                                                # Indxer(pat_path).run(): X.pat.gz.csi (bam2pat.py:415)
             print(f"[wt bam2pat] generated {pat_path}", file=sys.stderr)
             if a.mbias and mb_total is not None:
                 mdir = os.path.join(a.out_dir, name) + ".mbias"

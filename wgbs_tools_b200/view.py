@@ -163,7 +163,13 @@ def main(argv=None):
         s, e = (1, data.shape[0] + 1) if gr.is_whole() else gr.sites
         txt = b"".join(b"%d\t%d\n" % (m, v) for m, v in data[s - 1:e - 1].tolist())
     elif f.endswith(".pat.gz") or f.endswith(".pat"):
-        text = read_pat_text(f)
+        import os
+        if not gr.is_whole() and not a.bed_file and os.path.isfile(f + ".csi"):
+            from .csi import read_region                           # tabix pat chrom:ms-(e-1): only the indexed blocks are inflated
+            first, _ = ref.chrom_range(gr.chrom)
+            text = read_region(f, gr.chrom, max(1, gr.sites[0] - (100000 if a.nanopore else MAX_PAT_LEN), first), gr.sites[1] - 1)
+        else:
+            text = read_pat_text(f)
         with Context(0) as ctx:
             if a.bed_file:
                 bl = load_cview_blocks(a.bed_file)
