@@ -1,0 +1,172 @@
+// TEST INFRASTRUCTURE: builds wgbs_tools_b200/csrc/{inflate_core,bam_core}.cuh -- the per-block / per-record logic the
+// kernels of bamdev.cu run -- as plain host C++ (g++ -std=c++20), so tests/test_bamdev_core.py can pin it against zlib,
+// printf and the original SAM text without a GPU.  Not part of libwgbs_b200.so.
+//
+//   bamdev_core_check inflate FILE.bgzf [emu_blocks]   every BGZF block through Inflater<OneLane> vs zlib; the first
+//                                                      emu_blocks blocks also through a 32-lane lock-step emulation
+//   bamdev_core_check view FILE.bam SEG DEPTH          inflate, find the records with the segment guess / walk / repair
+//                                                      scheme (segment size SEG bytes), print the SAM text; stderr: stats
+//   bamdev_core_check fmtg N SEED                      fmt_g vs snprintf("%g") on N random floats + edge cases
+#include <zlib.h>
+
+#include <barrier>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../wgbs_tools_b200/csrc/bam_core.cuh"
+
+using namespace dflate;
+
+// ---- 32 lanes in lock step: one std::thread per lane, every collective is a barrier -----------------------------------
+struct EmuShared {
+    std::barrier<> bar{32};
+    uint32_t slot[32];
+};
+struct EmuLanes {
+    static constexpr int N = 32;
+    int lane; EmuShared *sh;
+    int id() const { return lane; }
+    void sync() const { sh->bar.arrive_and_wait(); }
+    uint32_t shfl(uint32_t v, int src) const { sh->slot[lane] = v; sh->bar.arrive_and_wait(); uint32_t r = sh->slot[src]; sh->bar.arrive_and_wait(); return r; }
+    uint32_t ballot(bool p) const {
+        sh->slot[lane] = p ? 1u : 0u; sh->bar.arrive_and_wait();
+        uint32_t m = 0; for (int i = 0; i < 32; i++) m |= sh->slot[i] << i;
+        sh->bar.arrive_and_wait(); return m;
+    }
+    uint32_t exscan(uint32_t v, uint32_t *total, uint32_t) const {
+        sh->slot[lane] = v; sh->bar.arrive_and_wait();
+        uint32_t pre = 0, tot = 0; for (int i = 0; i < 32; i++) { if (i < lane) pre += sh->slot[i]; tot += sh->slot[i]; }
+        sh->bar.arrive_and_wait(); *total = tot; return pre;
+    }
+};
+
+static std::vector<uint8_t> slurp(const char *path) {
+    FILE *f = fopen(path, "rb"); if (!f) { perror(path); exit(2); }
+    fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET);
+    std::vector<uint8_t> v((size_t)n + 16, 0);
+    if (n && fread(v.data(), 1, (size_t)n, f) != (size_t)n) { perror("read"); exit(2); }
+    fclose(f); v.resize((size_t)n);
+    return v;
+}
+struct Blk { uint64_t coff; uint32_t csize, xlen, usize; uint64_t uoff; };
+static std::vector<Blk> scan_blocks(const std::vector<uint8_t> &f, uint64_t *utotal) {
+    std::vector<Blk> b; uint64_t off = 0, uoff = 0;
+    while (off + 28 <= f.size()) {
+        uint32_t xlen = 0; const uint32_t bs = bgzf_block_size(f.data() + off, f.size() - off, &xlen);
+        if (!bs || off + bs > f.size()) { fprintf(stderr, "bad BGZF block at %llu\n", (unsigned long long)off); exit(3); }
+        Blk k; k.coff = off; k.csize = bs; k.xlen = xlen; k.usize = bamcore::ld32(f.data() + off + bs - 4); k.uoff = uoff;
+        b.push_back(k); off += bs; uoff += k.usize;
+    }
+    *utotal = uoff;
+    return b;
+}
+static int zlib_inflate(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usize) {
+    z_stream zs; memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, -15) != Z_OK) return -1;
+    zs.next_in = const_cast<Bytef *>(src); zs.avail_in = n; zs.next_out = dst; zs.avail_out = usize;
+    int rc = usize ? inflate(&zs, Z_FINISH) : Z_STREAM_END;
+    inflateEnd(&zs);
+    return (rc == Z_STREAM_END && zs.avail_out == 0) ? 0 : -1;
+}
+static int one_lane(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usize) {
+    Scratch S; Inflater<OneLane> I; I.S = &S; I.dst = dst; I.dst_len = usize;
+    return I.run(src, n);
+}
+static int emu_warp(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usize) {
+    static EmuShared sh; Scratch S; int rcs[32];
+    std::vector<std::thread> th;
+    for (int l = 0; l < 32; l++) th.emplace_back([&, l]() { Inflater<EmuLanes> I; I.lanes = EmuLanes{l, &sh}; I.S = &S; I.dst = dst; I.dst_len = usize; rcs[l] = I.run(src, n); });
+    for (auto &t : th) t.join();
+    for (int l = 1; l < 32; l++) if (rcs[l] != rcs[0]) { fprintf(stderr, "lanes disagree on rc\n"); exit(4); }
+    return rcs[0];
+}
+
+static int cmd_inflate(const char *path, int emu_blocks) {
+    auto f = slurp(path); uint64_t ut; auto blocks = scan_blocks(f, &ut);
+    size_t nbad = 0, nemu = 0; uint64_t bytes = 0;
+    for (size_t i = 0; i < blocks.size(); i++) {
+        const Blk &b = blocks[i];
+        const uint8_t *src = f.data() + b.coff + 12 + b.xlen; const uint32_t n = b.csize - 12 - b.xlen - 8;
+        std::vector<uint8_t> a(b.usize + 1), c(b.usize + 1), e(b.usize + 1);
+        const int rz = zlib_inflate(src, n, a.data(), b.usize);
+        const int r1 = one_lane(src, n, c.data(), b.usize);
+        bool ok = (rz == 0) == (r1 == 0) && (rz != 0 || !memcmp(a.data(), c.data(), b.usize));
+        if ((int)i < emu_blocks) { const int r2 = emu_warp(src, n, e.data(), b.usize); ok = ok && r2 == r1 && (r1 != 0 || !memcmp(a.data(), e.data(), b.usize)); nemu++; }
+        if (!ok) { nbad++; fprintf(stderr, "block %zu: zlib %d core %d\n", i, rz, r1); }
+        bytes += b.usize;
+    }
+    printf("blocks %zu emu %zu bytes %llu mismatches %zu\n", blocks.size(), nemu, (unsigned long long)bytes, nbad);
+    return nbad ? 1 : 0;
+}
+
+static int cmd_view(const char *path, uint64_t SEG, int depth) {
+    auto f = slurp(path); uint64_t n; auto blocks = scan_blocks(f, &n);
+    std::vector<uint8_t> d(n + 16, 0);
+    for (const Blk &b : blocks) if (one_lane(f.data() + b.coff + 12 + b.xlen, b.csize - 12 - b.xlen - 8, d.data() + b.uoff, b.usize)) { fprintf(stderr, "inflate failed\n"); return 3; }
+    using namespace bamcore;
+    if (n < 12 || memcmp(d.data(), "BAM\1", 4)) { fprintf(stderr, "not a BAM\n"); return 3; }
+    uint64_t p = 8ull + ld32(d.data() + 4); const int32_t n_ref = ldi32(d.data() + p); p += 4;
+    std::vector<uint32_t> name_off{0}; std::string names; std::vector<int32_t> lens;
+    for (int32_t i = 0; i < n_ref; i++) { const uint32_t l = ld32(d.data() + p); p += 4; names.append((const char *)d.data() + p, l ? l - 1 : 0); name_off.push_back((uint32_t)names.size()); p += l; lens.push_back(ldi32(d.data() + p)); p += 4; }
+    Refs F{n_ref, name_off.data(), names.data(), lens.data()};
+    // segments over [p, n): entry[s] = first record start >= p + s*SEG
+    const uint64_t p0 = p, nseg = n > p0 ? (n - p0 + SEG - 1) / SEG : 0;
+    std::vector<uint64_t> entry(nseg + 1), exit_(nseg), bad(nseg, ~0ull); std::vector<uint32_t> cnt(nseg);
+    OneLane one;
+    size_t wrong_guesses = 0, rounds = 0;
+    for (uint64_t s = 0; s < nseg; s++) entry[s] = s == 0 ? p0 : guess_entry(one, d.data(), n, p0 + s * SEG, n_ref, depth);
+    std::vector<char> dirty(nseg, 1);
+    for (bool changed = true; changed;) {
+        changed = false; rounds++;
+        for (uint64_t s = 0; s < nseg; s++) if (dirty[s]) { bad[s] = ~0ull; exit_[s] = walk_chain(d.data(), n, entry[s], p0 + (s + 1) * SEG, &cnt[s], nullptr, &bad[s]); dirty[s] = 0; }
+        for (uint64_t s = 0; s + 1 < nseg; s++) if (bad[s] == ~0ull && entry[s + 1] != exit_[s]) { entry[s + 1] = exit_[s]; dirty[s + 1] = 1; changed = true; wrong_guesses++; }
+    }
+    for (uint64_t s = 0; s < nseg; s++) if (bad[s] != ~0ull) { fprintf(stderr, "corrupt BAM record at %llu\n", (unsigned long long)bad[s]); return 3; }
+    std::vector<uint64_t> rec;
+    for (uint64_t s = 0; s < nseg; s++) { std::vector<uint64_t> o(cnt[s]); uint32_t c; uint64_t b = ~0ull; walk_chain(d.data(), n, entry[s], p0 + (s + 1) * SEG, &c, o.data(), &b); rec.insert(rec.end(), o.begin(), o.end()); }
+    std::string out;
+    for (uint64_t o : rec) {
+        Rec R; R.load(d.data() + o);
+        if (!R.consistent()) { fprintf(stderr, "inconsistent record at %llu\n", (unsigned long long)o); return 3; }
+        CountSink cs; format_record(R, F, cs);
+        const size_t at = out.size(); out.resize(at + cs.n);
+        WriteSink<OneLane> ws; ws.o = &out[at]; format_record(R, F, ws);
+        if (ws.n != cs.n) { fprintf(stderr, "count/write disagree\n"); return 4; }
+    }
+    fwrite(out.data(), 1, out.size(), stdout);
+    fprintf(stderr, "records %zu segments %llu wrong_guesses %zu rounds %zu\n", rec.size(), (unsigned long long)nseg, wrong_guesses, rounds);
+    return 0;
+}
+
+static int cmd_fmtg(long N, unsigned seed) {
+    std::mt19937_64 rng(seed); size_t bad = 0;
+    auto test = [&](uint32_t u) {
+        float f; memcpy(&f, &u, 4);
+        char a[40], b[40]; snprintf(a, sizeof a, "%g", f);
+        const int k = bamcore::fmt_g(f, b); b[k] = 0;
+        if (strcmp(a, b)) { if (bad < 20) fprintf(stderr, "%08x: printf '%s' core '%s'\n", u, a, b); bad++; }
+    };
+    const float edge[] = {0.f, -0.f, 1.f, -1.f, 0.5f, 0.1f, 100000.f, 999999.f, 999999.5f, 1000000.f, 1e-4f, 9.9999e-5f, 1e-5f, 123456.5f, 1234565.f, 0.25f, 2.f, 1.5f,
+                          3.4028235e38f, 1.17549435e-38f, 1e-45f, 16777216.f, 8388608.5f, 0.000123456789f, 1e10f, 1e-10f, INFINITY, -INFINITY, NAN, 2.5f, 0.3f, 1e6f, 1e5f, 99999.95f, 0.00001f};
+    for (float e : edge) { uint32_t u; memcpy(&u, &e, 4); test(u); }
+    for (long i = 0; i < N; i++) test((uint32_t)rng());
+    // values near the style switches and with short decimal expansions (tags are usually like 0.25 or 12.5)
+    for (long i = 0; i < N / 4; i++) { const float v = (float)((double)(rng() % 20000000) / 16.0); uint32_t u; memcpy(&u, &v, 4); test(u); }
+    for (long i = 0; i < N / 4; i++) { const float v = (float)((double)(rng() % 100000) / 1e3); uint32_t u; memcpy(&u, &v, 4); test(u); }
+    printf("fmtg mismatches %zu\n", bad);
+    return bad ? 1 : 0;
+}
+
+int main(int argc, char **argv) {
+    if (argc >= 3 && !strcmp(argv[1], "inflate")) return cmd_inflate(argv[2], argc > 3 ? atoi(argv[3]) : 0);
+    if (argc >= 5 && !strcmp(argv[1], "view")) return cmd_view(argv[2], strtoull(argv[3], nullptr, 10), atoi(argv[4]));
+    if (argc >= 4 && !strcmp(argv[1], "fmtg")) return cmd_fmtg(atol(argv[2]), (unsigned)atoi(argv[3]));
+    fprintf(stderr, "usage: see the header of tests/bamdev_core_check.cpp\n");
+    return 2;
+}

@@ -1,0 +1,335 @@
+// inflate_core.cuh -- raw DEFLATE (RFC 1951) decoder for ONE BGZF block, written for a warp: lane 0 walks the Huffman
+// stream and queues up to one symbol per lane; then the whole warp materialises the queue (literals in parallel, LZ77
+// matches in stream order, each copied cooperatively).  The output buffer is the LZ77 window: a BGZF block is an
+// independent deflate stream of <= 64 KiB (SAM spec 4.1), so distances never leave the block's own output.
+//
+// The same code compiles as plain host C++ with a one-lane policy (tests/bamdev_core_check.cpp pins it against zlib
+// without a GPU); the device policy is the 32 lanes of a warp.  Replaces the zlib inflate samtools/htslib run on the
+// host for the reference's `samtools view` stage (reference src/python/bam2pat.py:165).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define WGBS_HD __host__ __device__ __forceinline__
+#else
+#define WGBS_HD inline
+#endif
+
+namespace dflate {
+
+constexpr int LBITS = 10;   // literal/length codes up to this length decode with one table probe
+constexpr int DBITS = 8;    // distance codes
+
+enum : int { OK = 0, E_INPUT = -1 /* ran out of input */, E_BTYPE = -2, E_STORED = -3, E_CODES = -4 /* bad code lengths */,
+             E_SYMBOL = -5 /* invalid code / symbol */, E_DIST = -6 /* distance before the start of the block */,
+             E_OUTPUT = -7 /* more output than ISIZE */, E_SHORT = -8 /* stream ended before ISIZE bytes */ };
+
+// per-warp working set (shared memory on the device): 3.7 KB
+struct Scratch {
+    uint16_t lt[1 << LBITS];     // fast tables: symbol | code length << 9 (0: longer than the table, or unassigned)
+    uint16_t dt[1 << DBITS];
+    uint16_t lsym[288], dsym[32];   // symbols in canonical order + per-length counts, for the long codes
+    uint16_t lcnt[16], dcnt[16];
+    uint32_t q[32];              // decoded symbols: literal byte, or 0x80000000 | (dist-1) << 9 | length
+    uint8_t lens[320];
+};
+
+// ---- lane policies ---------------------------------------------------------------------------------------------------
+struct OneLane {
+    static constexpr int N = 1;
+    WGBS_HD int id() const { return 0; }
+    WGBS_HD void sync() const {}
+    WGBS_HD uint32_t shfl(uint32_t v, int) const { return v; }
+    WGBS_HD uint32_t ballot(bool p) const { return p ? 1u : 0u; }
+    WGBS_HD uint32_t exscan(uint32_t, uint32_t *total, uint32_t v_total) const { *total = v_total; return 0; }
+};
+#if defined(__CUDACC__)
+struct WarpLanes {
+    static constexpr int N = 32;
+    __device__ __forceinline__ int id() const { return (int)(threadIdx.x & 31); }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+    __device__ __forceinline__ uint32_t shfl(uint32_t v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+    __device__ __forceinline__ uint32_t ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
+    // exclusive prefix sum of v over the lanes; *total = sum
+    __device__ __forceinline__ uint32_t exscan(uint32_t v, uint32_t *total, uint32_t) const {
+        uint32_t x = v;
+        const int l = id();
+        for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (l >= d) x += y; }
+        *total = __shfl_sync(0xffffffffu, x, 31);
+        return x - v;
+    }
+};
+#endif
+
+// ---- canonical Huffman tables ----------------------------------------------------------------------------------------
+WGBS_HD uint32_t bitrev(uint32_t c, int n) { uint32_t r = 0; for (int i = 0; i < n; i++) { r = (r << 1) | (c & 1); c >>= 1; } return r; }
+
+// lens[0..n) -> cnt[16], sym[] (canonical order), fast[1<<fbits].  Over-subscribed sets are rejected; incomplete sets are
+// rejected too, except (single_ok: literal/length and distance sets, not the code-length code) when no code is longer
+// than one bit -- the cases zlib's inftrees.c accepts; an unused slot decodes to "invalid code" if the stream reaches it.
+WGBS_HD int build_table(const uint8_t *lens, int n, uint16_t *cnt, uint16_t *sym, uint16_t *fast, int fbits, bool single_ok) {
+    for (int i = 0; i < 16; i++) cnt[i] = 0;
+    for (int i = 0; i < n; i++) cnt[lens[i]]++;
+    for (int i = 0; i < (1 << fbits); i++) fast[i] = 0;
+    int left = 1, maxlen = 0;
+    for (int l = 1; l <= 15; l++) { left <<= 1; left -= cnt[l]; if (left < 0) return E_CODES; if (cnt[l]) maxlen = l; }
+    if (left > 0 && (maxlen > 1 || !single_ok)) return E_CODES;
+    uint16_t offs[16], code[16];
+    offs[1] = 0; code[1] = 0;
+    for (int l = 1; l < 15; l++) { offs[l + 1] = (uint16_t)(offs[l] + cnt[l]); code[l + 1] = (uint16_t)((code[l] + cnt[l]) << 1); }
+    for (int s = 0; s < n; s++) {
+        const int l = lens[s];
+        if (!l) continue;
+        const uint32_t c = code[l]++;
+        sym[offs[l]++] = (uint16_t)s;
+        if (l <= fbits) {
+            const uint16_t e = (uint16_t)(s | (l << 9));
+            for (uint32_t k = bitrev(c, l); k < (1u << fbits); k += (1u << l)) fast[k] = e;
+        }
+    }
+    return OK;
+}
+
+// one bit at a time (codes longer than the fast table): returns the symbol or -1; *nbits = code length
+WGBS_HD int slow_decode(uint64_t bb, const uint16_t *cnt, const uint16_t *sym, int *nbits) {
+    int code = 0, first = 0, index = 0;
+    for (int len = 1; len <= 15; len++) {
+        code |= (int)((bb >> (len - 1)) & 1);
+        const int count = cnt[len];
+        if (code - count < first) { *nbits = len; return sym[index + (code - first)]; }
+        index += count; first += count; first <<= 1; code <<= 1;
+    }
+    return -1;
+}
+
+// ---- bit reader (lane 0 only) ------------------------------------------------------------------------------------------
+struct Bits {
+    const uint8_t *src; uint32_t p, end;
+    uint64_t bb; int bc;
+    WGBS_HD void init(const uint8_t *s, uint32_t n) { src = s; p = 0; end = n; bb = 0; bc = 0; }
+    // at least 32 valid bits afterwards unless the input is exhausted (then the missing bits read as 0 and `take` notices)
+    WGBS_HD void refill() {
+        if (bc > 32) return;
+        if (((uintptr_t)(src + p) & 3) == 0 && p + 4 <= end) {
+            const uint32_t w = *(const uint32_t *)(src + p);
+            bb |= (uint64_t)w << bc; bc += 32; p += 4;
+        } else {
+            while (bc <= 56 && p < end) { bb |= (uint64_t)src[p++] << bc; bc += 8; }
+        }
+    }
+    WGBS_HD bool take(int n, uint32_t *v) {        // n <= 32
+        if (bc < n) return false;
+        *v = (uint32_t)(bb & ((1ull << n) - 1)); bb >>= n; bc -= n;
+        return true;
+    }
+    WGBS_HD bool drop(int n) { if (bc < n) return false; bb >>= n; bc -= n; return true; }
+};
+
+template <class L>
+struct Inflater {
+    L lanes;
+    Scratch *S;
+    uint8_t *dst; uint32_t dst_len;
+
+    // fixed code of RFC 1951 3.2.6
+    WGBS_HD int fixed_tables() {
+        uint8_t *l = S->lens;
+        for (int i = 0; i < 144; i++) l[i] = 8;
+        for (int i = 144; i < 256; i++) l[i] = 9;
+        for (int i = 256; i < 280; i++) l[i] = 7;
+        for (int i = 280; i < 288; i++) l[i] = 8;
+        int rc = build_table(l, 288, S->lcnt, S->lsym, S->lt, LBITS, true);
+        if (rc) return rc;
+        for (int i = 0; i < 30; i++) l[i] = 5;
+        // 30 five-bit codes leave two slots unused: incomplete by construction, accepted like zlib's fixed table
+        for (int i = 0; i < 16; i++) S->dcnt[i] = 0;
+        S->dcnt[5] = 30;
+        for (int i = 0; i < (1 << DBITS); i++) S->dt[i] = 0;
+        for (int s = 0; s < 30; s++) {
+            S->dsym[s] = (uint16_t)s;
+            for (uint32_t k = bitrev((uint32_t)s, 5); k < (1u << DBITS); k += 32) S->dt[k] = (uint16_t)(s | (5 << 9));
+        }
+        return OK;
+    }
+
+    // dynamic code of RFC 1951 3.2.7
+    WGBS_HD int dynamic_tables(Bits &B) {
+        uint32_t v;
+        B.refill();
+        if (!B.take(14, &v)) return E_INPUT;
+        const int nlen = (int)(v & 31) + 257, ndist = (int)((v >> 5) & 31) + 1, ncode = (int)((v >> 10) & 15) + 4;
+        if (nlen > 286 || ndist > 30) return E_CODES;
+        const char *order = "\x10\x11\x12\x00\x08\x07\x09\x06\x0a\x05\x0b\x04\x0c\x03\x0d\x02\x0e\x01\x0f";
+        uint8_t *l = S->lens;
+        for (int i = 0; i < 19; i++) l[i] = 0;
+        for (int i = 0; i < ncode; i++) { B.refill(); if (!B.take(3, &v)) return E_INPUT; l[(int)order[i]] = (uint8_t)v; }
+        // the code-length code borrows the distance tables (7-bit codes fit the 8-bit fast table)
+        int rc = build_table(l, 19, S->dcnt, S->dsym, S->dt, 7, false);
+        if (rc) return rc;
+        uint16_t clt[128], ccnt[16], csym[19];
+        for (int i = 0; i < 128; i++) clt[i] = S->dt[i];
+        for (int i = 0; i < 16; i++) ccnt[i] = S->dcnt[i];
+        for (int i = 0; i < 19; i++) csym[i] = S->dsym[i];
+        int idx = 0;
+        while (idx < nlen + ndist) {
+            B.refill();
+            const uint16_t e = clt[B.bb & 127];
+            int s, nb = e >> 9;
+            if (nb) s = e & 511; else { s = slow_decode(B.bb, ccnt, csym, &nb); if (s < 0) return E_SYMBOL; }
+            if (!B.drop(nb)) return E_INPUT;
+            if (s < 16) { l[idx++] = (uint8_t)s; continue; }
+            int rep; uint8_t val = 0;
+            if (s == 16) { if (idx == 0) return E_CODES; val = l[idx - 1]; if (!B.take(2, &v)) return E_INPUT; rep = 3 + (int)v; }
+            else if (s == 17) { if (!B.take(3, &v)) return E_INPUT; rep = 3 + (int)v; }
+            else { if (!B.take(7, &v)) return E_INPUT; rep = 11 + (int)v; }
+            if (idx + rep > nlen + ndist) return E_CODES;
+            while (rep--) l[idx++] = val;
+        }
+        if (l[256] == 0) return E_CODES;                 // no end-of-block code
+        rc = build_table(l, nlen, S->lcnt, S->lsym, S->lt, LBITS, true);
+        if (rc) return rc;
+        return build_table(l + nlen, ndist, S->dcnt, S->dsym, S->dt, DBITS, true);
+    }
+
+    // lane 0: decode up to `room` symbols of the current Huffman block into S->q.  *eob is set at the end-of-block code.
+    WGBS_HD int decode_some(Bits &B, int room, int *nq, bool *eob) {
+        int n = 0;
+        while (n < room) {
+            B.refill();
+            uint16_t e = S->lt[B.bb & ((1u << LBITS) - 1)];
+            int s, nb = e >> 9;
+            if (nb) s = e & 511; else { s = slow_decode(B.bb, S->lcnt, S->lsym, &nb); if (s < 0) return E_SYMBOL; }
+            if (!B.drop(nb)) return E_INPUT;
+            if (s < 256) { S->q[n++] = (uint32_t)s; continue; }
+            if (s == 256) { *eob = true; break; }
+            if (s > 285) return E_SYMBOL;
+            uint32_t len, v;
+            if (s < 265) len = (uint32_t)(s - 254);
+            else if (s == 285) len = 258;
+            else { const int eb = ((s - 265) >> 2) + 1; if (!B.take(eb, &v)) return E_INPUT; len = 3 + ((4u + (uint32_t)((s - 265) & 3)) << eb) + v; }
+            B.refill();
+            e = S->dt[B.bb & ((1u << DBITS) - 1)];
+            nb = e >> 9;
+            if (nb) s = e & 511; else { s = slow_decode(B.bb, S->dcnt, S->dsym, &nb); if (s < 0) return E_SYMBOL; }
+            if (!B.drop(nb)) return E_INPUT;
+            if (s > 29) return E_SYMBOL;
+            uint32_t dist;
+            if (s < 4) dist = (uint32_t)s + 1;
+            else { const int eb = (s >> 1) - 1; if (!B.take(eb, &v)) return E_INPUT; dist = 1 + ((2u + (uint32_t)(s & 1)) << eb) + v; }
+            S->q[n++] = 0x80000000u | ((dist - 1) << 9) | len;
+        }
+        *nq = n;
+        return OK;
+    }
+
+    // all lanes: write the queued symbols at *opos.  Literals first (independent), then the matches in stream order:
+    // everything a match reads lies before its own output position, i.e. was produced by an earlier symbol.
+    WGBS_HD int emit(int nq, uint32_t *opos) {
+        const int l = lanes.id();
+        const uint32_t e = l < nq ? S->q[l] : 0;
+        const bool live = l < nq, is_match = live && (e >> 31);
+        const uint32_t mylen = !live ? 0u : (is_match ? (e & 511u) : 1u);
+        uint32_t total;
+        const uint32_t at = *opos + lanes.exscan(mylen, &total, mylen);
+        if (*opos + total > dst_len) return E_OUTPUT;
+        if (live && !is_match) dst[at] = (uint8_t)e;
+        uint32_t m = lanes.ballot(is_match);
+        int bad = 0;
+        lanes.sync();
+        while (m) {
+            int i = 0; while (!((m >> i) & 1)) i++;
+            m &= m - 1;
+            const uint32_t ee = lanes.shfl(e, i), p = lanes.shfl(at, i);
+            const uint32_t len = ee & 511u, dist = ((ee >> 9) & 0xffffu) + 1;
+            if (dist > p) { bad = 1; break; }
+            const uint8_t *from = dst + p - dist;
+            if (dist >= len) { for (uint32_t k = (uint32_t)l; k < len; k += L::N) dst[p + k] = from[k]; }
+            else { for (uint32_t k = (uint32_t)l; k < len; k += L::N) dst[p + k] = from[k % dist]; }
+            lanes.sync();
+        }
+        if (bad) return E_DIST;
+        *opos += total;
+        return OK;
+    }
+
+    // Inflate `src[0..src_len)` into `dst[0..dst_len)`; the stream must produce exactly dst_len bytes (the block's ISIZE).
+    WGBS_HD int run(const uint8_t *src, uint32_t src_len) {
+        Bits B; B.init(src, src_len);
+        uint32_t opos = 0;
+        const bool lead = lanes.id() == 0;
+        int rc = OK;
+        bool last = false;
+        while (!last && rc == OK) {
+            // ---- block header (lane 0), broadcast: type, final flag, stored length / source offset
+            uint32_t hdr = 0, slen = 0, sfrom = 0;
+            if (lead) {
+                uint32_t v;
+                B.refill();
+                if (!B.take(3, &v)) rc = E_INPUT;
+                else {
+                    hdr = v;
+                    const uint32_t type = v >> 1;
+                    if (type == 0) {
+                        B.drop(B.bc & 7);                                   // to the byte boundary
+                        B.refill();
+                        if (!B.take(32, &v)) rc = E_INPUT;
+                        else if ((v & 0xffffu) != ((~v >> 16) & 0xffffu)) rc = E_STORED;
+                        else {
+                            slen = v & 0xffffu;
+                            sfrom = B.p - (uint32_t)(B.bc >> 3);            // bytes still parked in the bit buffer belong to the payload
+                            if (sfrom + slen > B.end) rc = E_INPUT;
+                            else { B.p = sfrom + slen; B.bb = 0; B.bc = 0; }
+                        }
+                    } else if (type == 1) rc = fixed_tables();
+                    else if (type == 2) rc = dynamic_tables(B);
+                    else rc = E_BTYPE;
+                }
+            }
+            rc = (int)lanes.shfl((uint32_t)rc, 0);
+            if (rc != OK) break;
+            hdr = lanes.shfl(hdr, 0);
+            last = hdr & 1;
+            if ((hdr >> 1) == 0) {
+                slen = lanes.shfl(slen, 0); sfrom = lanes.shfl(sfrom, 0);
+                if (opos + slen > dst_len) { rc = E_OUTPUT; break; }
+                for (uint32_t k = (uint32_t)lanes.id(); k < slen; k += L::N) dst[opos + k] = src[sfrom + k];
+                opos += slen;
+                lanes.sync();
+                continue;
+            }
+            lanes.sync();                                                   // tables visible (only lane 0 reads them; cheap)
+            bool eob = false;
+            while (!eob && rc == OK) {
+                int nq = 0;
+                if (lead) rc = decode_some(B, L::N, &nq, &eob);
+                lanes.sync();
+                rc = (int)lanes.shfl((uint32_t)rc, 0);
+                if (rc != OK) break;
+                nq = (int)lanes.shfl((uint32_t)nq, 0);
+                eob = lanes.shfl(eob ? 1u : 0u, 0) != 0;
+                if (nq) rc = emit(nq, &opos);
+                lanes.sync();
+            }
+        }
+        if (rc == OK && opos != dst_len) rc = E_SHORT;
+        return rc;
+    }
+};
+
+// ---- BGZF block framing (SAM spec 4.1) -----------------------------------------------------------------------------------
+// header: 1f 8b 08 04 | mtime(4) xfl os | xlen(2) | subfields ... 'B' 'C' 02 00 bsize-1(2) ... | deflate | crc32(4) isize(4)
+// returns the total block size (0: not a BGZF block header); *xlen_out = length of the extra field
+WGBS_HD uint32_t bgzf_block_size(const uint8_t *h, uint64_t avail, uint32_t *xlen_out) {
+    if (avail < 18 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return 0;
+    const uint32_t xlen = (uint32_t)h[10] | ((uint32_t)h[11] << 8);
+    if (12ull + xlen > avail) return 0;
+    for (uint32_t x = 0; x + 4 <= xlen;) {
+        const uint8_t *sf = h + 12 + x;
+        const uint32_t sl = (uint32_t)sf[2] | ((uint32_t)sf[3] << 8);
+        if (sf[0] == 'B' && sf[1] == 'C' && sl == 2 && x + 6 <= xlen) { *xlen_out = xlen; return ((uint32_t)sf[4] | ((uint32_t)sf[5] << 8)) + 1u; }
+        x += 4 + sl;
+    }
+    return 0;
+}
+
+}  // namespace dflate
