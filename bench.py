@@ -271,6 +271,66 @@ def extras(ctx, torch, peak, sam_for_bam=b""):
     return out
 
 
+def bam_device_leg(ctx, torch, stream, ix, g, bam_bytes, n_rec, sam_bytes, h_text, h_beta, mc, ref_text, ref_beta, peak, steps=8, warmup=3):
+    """The same batch end to end from the COMPRESSED BAM bytes in pinned host memory (no SAM-text detour over
+    PCIe): upload + one-warp-per-block BGZF inflate + record table + view + pileup + pat2beta + collapse + pat text and .beta
+    read back.  Outputs are compared with the SAM-text path's."""
+    import ctypes as C
+    from wgbs_tools_b200._lib import PileupOpts, ViewOpts, check, lib
+    h_bam = torch.frombuffer(bytearray(bam_bytes), dtype=torch.uint8).pin_memory()
+    out_n = {}
+
+    def step():
+        B = C.c_void_p()
+        check(lib.wgbs_dbam_open(ctx.h, h_bam.data_ptr(), h_bam.numel(), C.byref(B)))
+        vo = ViewOpts(); vo.refid = 0
+        o = PileupOpts(1, 0, -1, 0, 0, 0.67, b"C")
+        h = C.c_void_p(); st = (C.c_uint64 * 8)()
+        check(lib.wgbs_pileup_dbam(ctx.h, ix.h, B, C.byref(vo), C.addressof(o), C.byref(h), C.addressof(st), None))
+        lib.wgbs_dbam_close(ctx.h, B)
+        check(lib.wgbs_pat2beta(ctx.h, h, 1, g.n_cpg + 1, mc.data_ptr(), 1))
+        check(lib.wgbs_collapse(ctx.h, h))
+        n = C.c_size_t()
+        check(lib.wgbs_pats_format(ctx.h, h, CHR.encode(), h_text.data_ptr(), h_text.numel(), C.byref(n)))
+        check(lib.wgbs_trim(ctx.h, mc.data_ptr(), g.n_cpg, 8, h_beta.data_ptr()))
+        lib.wgbs_pats_free(ctx.h, h)
+        out_n.update(n=n.value, lines=int(st[0]))
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    same = bytes(h_text[:out_n["n"]].numpy().tobytes()) == ref_text and h_beta.numpy().tobytes() == ref_beta
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    ctx.prof(True)
+    for _ in range(2):
+        step()
+    rep = ctx.prof_report()
+    ctx.prof(False)
+    top = sorted(rep.items(), key=lambda kv: -kv[1][1])
+    infl = rep.get("bgzf_inflate_k")
+    res = {"records": n_rec, "lines_seen": out_n["lines"], "ms_per_step": ms, "reads_per_sec": n_rec / (ms / 1e3), "h2d_bytes_per_step": len(bam_bytes),
+           "d2h_bytes_per_step": out_n["n"] + 2 * g.n_cpg, "sam_text_bytes_equivalent": sam_bytes, "identical_to_sam_text_path": bool(same),
+           "breakdown_ms_per_step": {k: round(v[1] / 2, 4) for k, v in top[:12]},
+           "mode": "serial: upload, inflate, view, pileup, read back, one batch after the other; wgbs_dbam_open + wgbs_pileup_dbam from pinned host bytes"}
+    if infl:
+        sec = infl[1] / infl[0] / 1e3
+        # algorithmic bytes of the inflate: compressed bytes read + inflated bytes written
+        inflated = sam_bytes  # lower bound stand-in replaced below when the library reports it
+        B = C.c_void_p(); check(lib.wgbs_dbam_open(ctx.h, h_bam.data_ptr(), h_bam.numel(), C.byref(B)))
+        inflated = int(lib.wgbs_dbam_inflated_bytes(B)); lib.wgbs_dbam_close(ctx.h, B)
+        ab = len(bam_bytes) + inflated
+        res["roofline"] = {"kernel": "bgzf_inflate_k", "bound": "latency (serial Huffman decode per block), reported against hbm", "achieved": ab / sec / 1e9, "peak": peak,
+                           "unit": "GB/s", "frac": ab / sec / 1e9 / peak, "algorithmic_bytes": ab, "avg_launch_ms": sec * 1e3, "inflated_bytes": inflated}
+    log(f"[bench] bam_device: {ms:.3f} ms/step, {res['reads_per_sec'] / 1e6:.1f} M reads/s, identical={same}")
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -313,6 +373,18 @@ def main():
         return
 
     # ------------------------------------------------------------------------------------------------------------------
+    g = genome()
+    sam = make_batch(args.reads, 1000 + rank)
+    bam_bytes = None
+    if rank == 0 and args.gpus == 1 and not args.no_extras:
+        # the same batch as a BAM file, for the device-decode leg (forked workers: before CUDA is initialised here)
+        try:
+            from wgbs_tools_b200 import bamio
+            t0 = time.time()
+            bam_bytes = bamio.sam_to_bam(sam, [(CHR, CHR_LEN)], procs=max(1, min(host_threads(), 32)))
+            log(f"[bench] BAM of the batch: {len(bam_bytes) / 1e6:.1f} MB ({time.time() - t0:.1f}s)")
+        except Exception as e:
+            log(f"[bench] BAM build failed: {e!r}")
     import torch
     import torch.distributed as dist
     from wgbs_tools_b200.api import Context
@@ -334,8 +406,6 @@ def main():
             sys.stdout.flush()
             os.dup2(keep, 1)
             os.close(keep)
-    g = genome()
-    sam = make_batch(args.reads, 1000 + rank)
     n_rec = sam.count(10)
     text_bytes = len(sam)
     # a real (non-default) torch stream is made current and handed to the library, so that torch's CUDA events, the NCCL
@@ -508,6 +578,15 @@ def main():
         except Exception as e:
             log(f"[bench] extras failed: {e!r}")
             extra = {"error": repr(e)}
+        if bam_bytes is not None:
+            try:
+                run_step(True)
+                ref_text = bytes(h_text[:last["text_bytes"]].numpy().tobytes()); ref_beta = h_beta.numpy().tobytes()
+                extra["bam_device"] = bam_device_leg(ctx, torch, stream, ix, g, bam_bytes, n_rec, text_bytes, h_text, h_beta, mc, ref_text, ref_beta,
+                                                     roof["peak"] if roof else 6650.0)
+            except Exception as e:
+                log(f"[bench] bam_device leg failed: {e!r}")
+                extra["bam_device"] = {"error": repr(e)}
 
     if rank == 0:
         out = {

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define WGBS_B200_ABI_VERSION 3
+#define WGBS_B200_ABI_VERSION 4
 
 typedef struct wgbs_ctx wgbs_ctx;
 typedef struct wgbs_pats wgbs_pats;   /* device-resident pat records: (idx, len, count, 2-bit symbol pool) */
@@ -229,6 +229,31 @@ typedef struct wgbs_view_opts {
 } wgbs_view_opts;
 int wgbs_bam_view_ex(const wgbs_bam *, const wgbs_view_opts *, char **text, size_t *nbytes, uint64_t *nrecords);
 void wgbs_host_free(void *);
+
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * BAM ingest ON THE DEVICE (the `samtools view` stage of reference bam2pat.py:126-165 "without a SAM-text
+ * detour" over PCIe).  The COMPRESSED bytes of a coordinate-sorted .bam file are uploaded (about 55 B per 150 bp read
+ * instead of ~360 B of SAM text); one warp per BGZF block inflates it in HBM, the BAM records are located in the inflated
+ * stream (guess + verified chain walk: exact for any record / block alignment), and views with the same filters as
+ * wgbs_bam_view_ex are formatted to SAM text in HBM, ready for wgbs_pileup_sam.  Same results, byte for byte, as the host
+ * reader above.  The whole inflated stream stays resident: a file whose inflated size exceeds free device memory is refused.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct wgbs_dbam wgbs_dbam;
+/* bgzf: the bytes of a whole .bam file in HOST memory (pinned memory makes the upload a single DMA) */
+int wgbs_dbam_open(wgbs_ctx *, const void *bgzf, size_t nbytes, wgbs_dbam **out);
+int wgbs_dbam_open_file(wgbs_ctx *, const char *path, wgbs_dbam **out);
+void wgbs_dbam_close(wgbs_ctx *, wgbs_dbam *);
+int wgbs_dbam_nref(const wgbs_dbam *);
+const char *wgbs_dbam_ref_name(const wgbs_dbam *, int i);
+const char *wgbs_dbam_header(const wgbs_dbam *);
+uint64_t wgbs_dbam_nrecords(const wgbs_dbam *, int refid);
+uint64_t wgbs_dbam_inflated_bytes(const wgbs_dbam *);
+/* *dev_text: DEVICE buffer holding the SAM text of the passing records (release with wgbs_dev_free) */
+int wgbs_dbam_view(wgbs_ctx *, const wgbs_dbam *, const wgbs_view_opts *, char **dev_text, size_t *nbytes, uint64_t *nrecords);
+/* wgbs_dbam_view + wgbs_pileup_sam_mbias without leaving the device (mbias may be NULL) */
+int wgbs_pileup_dbam(wgbs_ctx *, const wgbs_index *, const wgbs_dbam *, const wgbs_view_opts *, const wgbs_pileup_opts *,
+                     wgbs_pats **out, uint64_t *stats, int32_t *mbias);
 
 #ifdef __cplusplus
 }

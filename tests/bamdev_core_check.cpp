@@ -4,8 +4,11 @@
 //
 //   bamdev_core_check inflate FILE.bgzf [emu_blocks]   every BGZF block through Inflater<OneLane> vs zlib; the first
 //                                                      emu_blocks blocks also through a 32-lane lock-step emulation
-//   bamdev_core_check view FILE.bam SEG DEPTH          inflate, find the records with the segment guess / walk / repair
-//                                                      scheme (segment size SEG bytes), print the SAM text; stderr: stats
+//   bamdev_core_check view FILE.bam SEG DEPTH [REFID MAPQ EXCL INCL BEG END FLAGEQ RG IVFILE IVEXCL MAXREC]
+//                                                      inflate, find the records with the segment guess / walk / repair
+//                                                      scheme (segment size SEG bytes), apply the `samtools view` filters
+//                                                      (FLAGEQ: comma list or '-', RG: read group or '-', IVFILE: "beg end"
+//                                                      lines or '-'), print the SAM text; stderr: stats
 //   bamdev_core_check fmtg N SEED                      fmt_g vs snprintf("%g") on N random floats + edge cases
 #include <zlib.h>
 
@@ -105,7 +108,7 @@ static int cmd_inflate(const char *path, int emu_blocks) {
     return nbad ? 1 : 0;
 }
 
-static int cmd_view(const char *path, uint64_t SEG, int depth) {
+static int cmd_view(const char *path, uint64_t SEG, int depth, int argc, char **argv) {
     auto f = slurp(path); uint64_t n; auto blocks = scan_blocks(f, &n);
     std::vector<uint8_t> d(n + 16, 0);
     for (const Blk &b : blocks) if (one_lane(f.data() + b.coff + 12 + b.xlen, b.csize - 12 - b.xlen - 8, d.data() + b.uoff, b.usize)) { fprintf(stderr, "inflate failed\n"); return 3; }
@@ -130,10 +133,24 @@ static int cmd_view(const char *path, uint64_t SEG, int depth) {
     for (uint64_t s = 0; s < nseg; s++) if (bad[s] != ~0ull) { fprintf(stderr, "corrupt BAM record at %llu\n", (unsigned long long)bad[s]); return 3; }
     std::vector<uint64_t> rec;
     for (uint64_t s = 0; s < nseg; s++) { std::vector<uint64_t> o(cnt[s]); uint32_t c; uint64_t b = ~0ull; walk_chain(d.data(), n, entry[s], p0 + (s + 1) * SEG, &c, o.data(), &b); rec.insert(rec.end(), o.begin(), o.end()); }
+    ViewParams V; memset(&V, 0, sizeof V); V.refid = -1;
+    std::vector<int64_t> ivb, ive; std::string rg; uint64_t max_rec = 0, npass = 0;
+    if (argc >= 11) {
+        V.refid = atoi(argv[0]); V.min_mapq = atoi(argv[1]); V.exclude_flags = atoi(argv[2]); V.include_flags = atoi(argv[3]);
+        V.beg = atoll(argv[4]); V.end = atoll(argv[5]);
+        if (strcmp(argv[6], "-")) { char *t = strdup(argv[6]); for (char *q = strtok(t, ","); q; q = strtok(nullptr, ",")) V.flag_eq[V.n_flag_eq++] = atoi(q); free(t); }
+        if (strcmp(argv[7], "-")) { rg = argv[7]; V.rg = rg.c_str(); V.rg_len = (uint32_t)rg.size(); V.have_rg = 1; }
+        if (strcmp(argv[8], "-")) { FILE *fi = fopen(argv[8], "r"); long long a, b; while (fi && fscanf(fi, "%lld %lld", &a, &b) == 2) { ivb.push_back(a); ive.push_back(b); } if (fi) fclose(fi); }
+        V.iv_beg = ivb.data(); V.iv_end = ive.data(); V.n_iv = ivb.size(); V.iv_exclude = atoi(argv[9]);
+        max_rec = strtoull(argv[10], nullptr, 10);
+    }
     std::string out;
     for (uint64_t o : rec) {
         Rec R; R.load(d.data() + o);
         if (!R.consistent()) { fprintf(stderr, "inconsistent record at %llu\n", (unsigned long long)o); return 3; }
+        if (!passes(R, V)) continue;
+        if (max_rec && npass >= max_rec) break;
+        npass++;
         CountSink cs; format_record(R, F, cs);
         const size_t at = out.size(); out.resize(at + cs.n);
         WriteSink<OneLane> ws; ws.o = &out[at]; format_record(R, F, ws);
@@ -165,7 +182,7 @@ static int cmd_fmtg(long N, unsigned seed) {
 
 int main(int argc, char **argv) {
     if (argc >= 3 && !strcmp(argv[1], "inflate")) return cmd_inflate(argv[2], argc > 3 ? atoi(argv[3]) : 0);
-    if (argc >= 5 && !strcmp(argv[1], "view")) return cmd_view(argv[2], strtoull(argv[3], nullptr, 10), atoi(argv[4]));
+    if (argc >= 5 && !strcmp(argv[1], "view")) return cmd_view(argv[2], strtoull(argv[3], nullptr, 10), atoi(argv[4]), argc - 5, argv + 5);
     if (argc >= 4 && !strcmp(argv[1], "fmtg")) return cmd_fmtg(atol(argv[2]), (unsigned)atoi(argv[3]));
     fprintf(stderr, "usage: see the header of tests/bamdev_core_check.cpp\n");
     return 2;

@@ -1,0 +1,189 @@
+"""Device BAM front end (csrc/bamdev.cu), the part that can be pinned WITHOUT a GPU: inflate_core.cuh / bam_core.cuh are
+host + device code, so tests/bamdev_core_check.cpp compiles them with g++ and this file checks them against zlib, printf,
+the source SAM text and the library's host BAM reader (csrc/bam.cu, itself round-trip tested in test_bam_ingest.py).
+The warp-cooperative part of the inflater runs here under a 32-lane lock-step emulation (one thread per lane, every
+shuffle / ballot / __syncwarp a barrier)."""
+import os
+import struct
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+from wgbs_tools_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def check(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("bamdev") / "bamdev_core_check")
+    r = subprocess.run(["g++", "-std=c++20", "-O2", "-o", exe, os.path.join(ROOT, "tests", "bamdev_core_check.cpp"), "-lz", "-lpthread"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    return exe
+
+
+def frame(comp: bytes, data: bytes) -> bytes:
+    assert len(comp) + 26 <= 65536
+    return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(comp) + 25) + comp
+            + struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data)))
+
+
+def block(data: bytes, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, mem=8) -> bytes:
+    co = zlib.compressobj(level, zlib.DEFLATED, -15, mem, strategy)
+    return frame(co.compress(data) + co.flush(), data)
+
+
+@pytest.fixture(scope="module")
+def sam():
+    g = synth.make_genome(7, "chrT", 300_000)
+    return g, synth.make_sam(g, 6000, 3, paired=True)
+
+
+def test_inflate_core_matches_zlib_on_every_block_type(check, sam, tmp_path):
+    """stored / fixed / dynamic blocks, long codes, overlapping matches (dist < len), several deflate blocks per BGZF block,
+    empty blocks; every block through the one-lane build, a sample through the emulated warp"""
+    from wgbs_tools_b200.patio import BGZF_EOF
+    _, s = sam
+    rng = np.random.default_rng(1)
+    datas = [s[:60000], s[60000:125000], b"", b"a", b"ab" * 30000, b"\0" * 65000, rng.integers(0, 256, 50000, dtype=np.uint8).tobytes(),
+             rng.integers(0, 4, 65000, dtype=np.uint8).tobytes(), bytes(range(256)) * 200, s[200000:260000]]
+    parts = []
+    for d in datas:
+        for lvl in (0, 1, 6, 9):
+            if lvl == 0 and len(d) > 65000:
+                continue
+            parts.append(block(d, lvl))
+        parts += [block(d, 6, zlib.Z_FIXED), block(d, 6, zlib.Z_HUFFMAN_ONLY), block(d, 6, zlib.Z_RLE), block(d, 9, zlib.Z_DEFAULT_STRATEGY, 1)]
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    d = s[300000:340000]
+    parts.append(frame(co.compress(d[:10000]) + co.flush(zlib.Z_SYNC_FLUSH) + co.compress(d[10000:]) + co.flush(zlib.Z_FULL_FLUSH) + co.flush(), d))
+    # the emulated warp is slow (thread barriers): put one block of every kind first
+    order = [0, 4, 5, 6, len(parts) - 1, 36, 12, 20] + [i for i in range(len(parts)) if i not in (0, 4, 5, 6, len(parts) - 1, 36, 12, 20)]
+    p = tmp_path / "mix.bgzf"
+    p.write_bytes(b"".join(parts[i] for i in order) + BGZF_EOF)
+    r = subprocess.run([check, "inflate", str(p), "8"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert f"blocks {len(parts) + 1} emu 8 " in r.stdout and r.stdout.strip().endswith("mismatches 0")
+
+
+def test_inflate_core_rejects_what_zlib_rejects(check, sam, tmp_path):
+    """corrupt payloads: the verdict (ok / error) must agree with zlib block by block; never a crash"""
+    _, s = sam
+    rng = np.random.default_rng(3)
+    good = block(s[:30000])
+    parts = []
+    for k in range(40):
+        b = bytearray(good)
+        pos = int(rng.integers(18, len(b) - 8))
+        b[pos] ^= 1 << int(rng.integers(0, 8))
+        parts.append(bytes(b))
+    short = bytearray(good); short[-4:] = struct.pack("<I", 29999)            # ISIZE smaller than the stream
+    longer = bytearray(good); longer[-4:] = struct.pack("<I", 30001)
+    parts += [bytes(short), bytes(longer)]
+    p = tmp_path / "bad.bgzf"
+    p.write_bytes(b"".join(parts))
+    r = subprocess.run([check, "inflate", str(p), "2"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr                            # 0 = no DISAGREEMENT with zlib
+    assert r.stdout.strip().endswith("mismatches 0")
+
+
+def test_fmt_g_matches_printf(check):
+    r = subprocess.run([check, "fmtg", "400000", "7"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip() == "fmtg mismatches 0", r.stdout + r.stderr
+
+
+EXTRA = (b"x1\t0\tchrT\t500\t7\t10M2I5M3D20M4S\t*\t0\t0\t" + b"ACGTN" * 8 + b"A\t*\tXA:A:q\tXB:i:-5\tXC:i:300\tXD:i:70000\tXE:f:1.5"
+         b"\tXF:Z:hello world\tXG:H:1AE3\tML:B:C,1,2,255\tXH:B:s,-3,400\tXI:B:f,0.25,2,1e-07,3.14159\tMM:Z:C+m?,0,1;\tRG:Z:grp1\n")
+UNMAPPED = b"x2\t4\t*\t0\t0\t*\t*\t0\t0\t*\t*\n"
+
+
+@pytest.mark.parametrize("seg,depth", [(64, 4), (1000, 4), (16384, 4), (1 << 20, 4), (50, 0)])
+def test_record_boundaries_and_sam_text_round_trip(check, sam, tmp_path, built_lib, seg, depth):
+    """SAM -> BAM (records spanning BGZF blocks) -> inflate core -> segment guess / walk / repair -> format core == SAM.
+    depth 0 makes every guess wrong (entry = segment base): the repair loop alone must still find every record."""
+    from wgbs_tools_b200 import bamio
+    g, s = sam
+    if depth == 0:
+        s = s[: s.index(b"\n", 40000) + 1]
+    full = EXTRA + s + UNMAPPED
+    p = tmp_path / "t.bam"
+    p.write_bytes(bamio.sam_to_bam(full, [("chrM", 16571), ("chrT", g.length)]))
+    r = subprocess.run([check, "view", str(p), str(seg), str(depth)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    assert r.returncode == 0, r.stderr.decode()
+    assert r.stdout == full
+    stats = dict(zip(r.stderr.decode().split()[::2], r.stderr.decode().split()[1::2]))
+    assert int(stats["records"]) == full.count(b"\n")
+    if depth:
+        assert int(stats["wrong_guesses"]) == 0 and int(stats["rounds"]) == 1
+    else:
+        assert int(stats["wrong_guesses"]) > 0
+
+
+def test_long_records_spanning_many_segments(check, tmp_path, built_lib):
+    """ONT-sized records (tens of KB, ML arrays of thousands of values): most segments hold no record start at all"""
+    from wgbs_tools_b200 import bamio
+    rng = np.random.default_rng(11)
+    lines = []
+    pos = 100
+    for i in range(40):
+        n = int(rng.integers(200, 60000))
+        seq = bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), n))
+        qual = bytes(rng.integers(33, 74, n, dtype=np.uint8))
+        nm = int(seq.count(b"C") // 3)
+        mm = b"MM:Z:C+m?" + b"".join(b",%d" % int(x) for x in rng.integers(0, 3, nm)) + b";"
+        ml = b"ML:B:C" + b"".join(b",%d" % int(x) for x in rng.integers(0, 256, nm))
+        lines.append(b"read%d\t%d\tchrT\t%d\t60\t%dM\t*\t0\t0\t%s\t%s\t%s\t%s\tqs:f:%s\n" % (i, 16 * (i & 1), pos, n, seq, qual, mm, ml, repr(float(np.float32(rng.random() * 40))).encode()))
+        pos += int(rng.integers(1, 3000))
+    full = b"".join(lines)
+    p = tmp_path / "ont.bam"
+    p.write_bytes(bamio.sam_to_bam(full, [("chrT", 10_000_000)]))
+    with bamio.BamFile(str(p), threads=2) as b:
+        host = b.view()
+    r = subprocess.run([check, "view", str(p), "16384", "4"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    assert r.returncode == 0, r.stderr.decode()
+    assert r.stdout == host                               # float tags print as %g on both sides
+
+
+def test_filters_match_the_host_reader(check, sam, tmp_path, built_lib):
+    """-q / -F / -f / region / FLAG equality / -r RG / -L / bedtools -v / head -N: core (bam_core.cuh passes()) == bam.cu"""
+    from wgbs_tools_b200 import bamio
+    g, s = sam
+    rng = np.random.default_rng(5)
+    # read groups on a third of the records, mapq varied
+    lines = s.splitlines()
+    for i in range(0, len(lines), 3):
+        lines[i] += b"\tRG:Z:grp1" if i % 2 == 0 else b"\tXX:i:5\tRG:Z:other"
+    for i in range(0, len(lines), 7):
+        t = lines[i].split(b"\t"); t[4] = b"3"; lines[i] = b"\t".join(t)
+    full = EXTRA + b"\n".join(lines) + b"\n" + UNMAPPED
+    p = tmp_path / "f.bam"
+    p.write_bytes(bamio.sam_to_bam(full, [("chrM", 16571), ("chrT", g.length)]))
+    starts = np.sort(rng.integers(0, g.length - 2000, 40)); ends = starts + rng.integers(1, 1500, 40)
+    keep = np.concatenate([[True], starts[1:] >= ends[:-1]]); starts, ends = starts[keep], ends[keep]
+    iv = tmp_path / "iv.txt"
+    iv.write_text("".join(f"{a} {b}\n" for a, b in zip(starts, ends)))
+    cases = [
+        dict(chrom="chrT", mapq=10, exclude_flags=1796, include_flags=3),
+        dict(chrom="chrT", beg=20_000, end=21_000),
+        dict(chrom="chrT", flag_eq=(99, 147)),
+        dict(chrom="chrT", read_group="grp1"),
+        dict(chrom="chrT", intervals=(starts, ends)),
+        dict(chrom="chrT", intervals=(starts, ends), exclude_intervals=True, mapq=5),
+        dict(chrom=None, max_records=200),
+        dict(chrom="chrM"),
+        dict(chrom=None, read_group="nosuch"),
+    ]
+    with bamio.BamFile(str(p), threads=2) as b:
+        for kw in cases:
+            exp = b.view(**kw)
+            argv = [str(-1 if kw.get("chrom") is None else b.refs.index(kw["chrom"])), str(kw.get("mapq", 0)), str(kw.get("exclude_flags", 0)),
+                    str(kw.get("include_flags", 0)), str(kw.get("beg", 0)), str(kw.get("end", 0)),
+                    ",".join(map(str, kw["flag_eq"])) if kw.get("flag_eq") else "-", kw.get("read_group") or "-",
+                    str(iv) if "intervals" in kw else "-", str(int(kw.get("exclude_intervals", False))), str(kw.get("max_records", 0))]
+            r = subprocess.run([check, "view", str(p), "16384", "4"] + argv, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+            assert r.returncode == 0, r.stderr.decode()
+            assert r.stdout == exp, kw
+            assert kw.get("chrom") == "chrM" or kw.get("read_group") == "nosuch" or exp

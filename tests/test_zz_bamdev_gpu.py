@@ -1,0 +1,202 @@
+"""BAM ingest on the device (csrc/bamdev.cu): warp-per-block BGZF inflate, record table, `samtools view` filters and SAM
+formatting in HBM.  Everything is compared byte for byte with the host reader (csrc/bam.cu, zlib on host threads), which is
+itself pinned by SAM -> BAM -> SAM round trips (test_bam_ingest.py); the per-block / per-record logic these kernels run is
+additionally pinned without a GPU in test_bamdev_core.py.  (File name: runs after the other GPU suites.)"""
+import gzip
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+from wgbs_tools_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+EXTRA = (b"x1\t0\tchrT\t500\t7\t10M2I5M3D20M4S\t*\t0\t0\t" + b"ACGTN" * 8 + b"A\t*\tXA:A:q\tXB:i:-5\tXC:i:300\tXD:i:70000\tXE:f:1.5"
+         b"\tXF:Z:hello world\tXG:H:1AE3\tML:B:C,1,2,255\tXH:B:s,-3,400\tXI:B:f,0.25,2,1e-07,3.14159\tMM:Z:C+m?,0,1;\tRG:Z:grp1\n")
+UNMAPPED = b"x2\t4\t*\t0\t0\t*\t*\t0\t0\t*\t*\n"
+
+
+@pytest.fixture(scope="module")
+def bamio(built_lib):
+    from wgbs_tools_b200 import bamio
+    return bamio
+
+
+@pytest.fixture(scope="module")
+def sample(bamio, tmp_path_factory):
+    g = synth.make_genome(7, "chrT", 300_000)
+    lines = synth.make_sam(g, 30_000, 3, paired=True).splitlines()
+    for i in range(0, len(lines), 3):
+        lines[i] += b"\tRG:Z:grp1" if i % 2 == 0 else b"\tXX:i:5\tRG:Z:other"
+    for i in range(0, len(lines), 7):
+        t = lines[i].split(b"\t"); t[4] = b"3"; lines[i] = b"\t".join(t)
+    full = EXTRA + b"\n".join(lines) + b"\n" + UNMAPPED
+    p = tmp_path_factory.mktemp("dbam") / "f.bam"
+    p.write_bytes(bamio.sam_to_bam(full, [("chrM", 16571), ("chrT", g.length)]))
+    return g, full, str(p)
+
+
+def test_device_views_equal_host_views(ctx, bamio, sample):
+    g, full, path = sample
+    rng = np.random.default_rng(5)
+    starts = np.sort(rng.integers(0, g.length - 2000, 40)); ends = starts + rng.integers(1, 1500, 40)
+    keep = np.concatenate([[True], starts[1:] >= ends[:-1]]); starts, ends = starts[keep], ends[keep]
+    cases = [
+        dict(chrom=None),
+        dict(chrom="chrT"),
+        dict(chrom="chrT", mapq=10, exclude_flags=1796, include_flags=3),
+        dict(chrom="chrT", beg=20_000, end=21_000),
+        dict(chrom="chrT", flag_eq=(99, 147)),
+        dict(chrom="chrT", read_group="grp1"),
+        dict(chrom="chrT", intervals=(starts, ends)),
+        dict(chrom="chrT", intervals=(starts, ends), exclude_intervals=True, mapq=5),
+        dict(chrom=None, max_records=1),
+        dict(chrom=None, max_records=200),
+        dict(chrom="chrT", mapq=10, max_records=77),
+        dict(chrom="chrM"),
+        dict(chrom=None, read_group="nosuch"),
+    ]
+    with bamio.BamFile(path, threads=4) as hb, bamio.DeviceBam(ctx, path) as db:
+        assert db.refs == hb.refs and db.header == hb.header
+        assert db.nrecords() == hb.nrecords() == full.count(b"\n")
+        assert [db.nrecords(c) for c in db.refs] == [hb.nrecords(c) for c in hb.refs]
+        assert db.view() == full
+        for kw in cases:
+            assert db.view(**kw) == hb.view(**kw), kw
+    # from bytes already in memory (what bench.py times): same object
+    with bamio.DeviceBam.from_bytes(ctx, open(path, "rb").read()) as db:
+        assert db.view("chrT", mapq=10, exclude_flags=1796, include_flags=3) == b"".join(
+            l + b"\n" for l in full.splitlines() if l.split(b"\t")[2] == b"chrT" and int(l.split(b"\t")[4]) >= 10 and int(l.split(b"\t")[1]) & 3 == 3
+            and not int(l.split(b"\t")[1]) & 1796)
+
+
+def test_every_deflate_block_type_and_records_across_blocks(ctx, bamio, tmp_path):
+    """the BAM stream cut into BGZF blocks of odd sizes, compressed as stored / fixed / dynamic / RLE / huffman-only blocks:
+    records straddle block boundaries everywhere"""
+    from wgbs_tools_b200.patio import BGZF_EOF
+    g = synth.make_genome(9, "chrT", 200_000)
+    sam = synth.make_sam(g, 6000, 5, paired=True)
+    raw = b"".join(zlib.decompress(b, 31) for b in _members(bamio.sam_to_bam(sam, [("chrT", g.length)])))
+    rng = np.random.default_rng(2)
+    parts = []; off = 0; k = 0
+    while off < len(raw):
+        n = int(rng.integers(1, 60_000)); d = raw[off:off + n]; off += n
+        level, strat = [(0, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_FIXED), (9, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_RLE), (6, zlib.Z_HUFFMAN_ONLY)][k % 6]; k += 1
+        co = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strat)
+        comp = co.compress(d) + co.flush()
+        parts.append(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(comp) + 25) + comp + struct.pack("<II", zlib.crc32(d), len(d)))
+        if k % 5 == 0:
+            parts.append(BGZF_EOF)                                    # empty blocks in the middle of the file are legal
+    data = b"".join(parts) + BGZF_EOF
+    with bamio.DeviceBam.from_bytes(ctx, data) as db:
+        assert db.inflated_bytes == len(raw)
+        assert db.view() == sam
+
+
+def _members(bgzf: bytes):
+    off = 0
+    while off < len(bgzf):
+        bs = struct.unpack_from("<H", bgzf, off + 16)[0] + 1
+        yield bgzf[off:off + bs]
+        off += bs
+
+
+def test_long_records(ctx, bamio, tmp_path):
+    """ONT-sized records: tens of KB each, ML arrays of thousands of values, float tags (printed like printf %g)"""
+    rng = np.random.default_rng(11)
+    lines = []; pos = 100
+    for i in range(60):
+        n = int(rng.integers(200, 90_000))
+        seq = bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), n))
+        qual = bytes(rng.integers(33, 74, n, dtype=np.uint8))
+        nm = int(seq.count(b"C") // 3)
+        mm = b"MM:Z:C+m?" + b"".join(b",%d" % int(x) for x in rng.integers(0, 3, nm)) + b";"
+        ml = b"ML:B:C" + b"".join(b",%d" % int(x) for x in rng.integers(0, 256, nm))
+        lines.append(b"read%d\t%d\tchrT\t%d\t60\t%dM\t*\t0\t0\t%s\t%s\t%s\t%s\tqs:f:%s\n" % (i, 16 * (i & 1), pos, n, seq, qual, mm, ml, repr(float(np.float32(rng.random() * 40))).encode()))
+        pos += int(rng.integers(1, 3000))
+    p = tmp_path / "ont.bam"
+    p.write_bytes(bamio.sam_to_bam(b"".join(lines), [("chrT", 10_000_000)]))
+    with bamio.BamFile(str(p), threads=2) as hb, bamio.DeviceBam(ctx, str(p)) as db:
+        assert db.view() == hb.view()
+        assert db.view("chrT", exclude_flags=16) == hb.view("chrT", exclude_flags=16)
+
+
+def test_corrupt_inputs_fail_loudly(ctx, bamio, sample, tmp_path):
+    from wgbs_tools_b200._lib import WgbsError
+    _, _, path = sample
+    good = open(path, "rb").read()
+    with pytest.raises(WgbsError, match="not a BGZF"):
+        bamio.DeviceBam.from_bytes(ctx, b"not a bam file at all........................")
+    bs0 = struct.unpack_from("<H", good, 16)[0] + 1                    # first BGZF block: wrong ISIZE
+    bad = bytearray(good); bad[bs0 - 4:bs0] = struct.pack("<I", struct.unpack_from("<I", good, bs0 - 4)[0] + 1)
+    with pytest.raises(WgbsError, match="inflate failed in BGZF block 0"):
+        bamio.DeviceBam.from_bytes(ctx, bytes(bad))
+    bad = bytearray(good); bad[bs0 + 18] |= 0x07                        # second block: BFINAL=1, BTYPE=3 (reserved)
+    with pytest.raises(WgbsError, match="inflate failed in BGZF block 1 .invalid deflate block type"):
+        bamio.DeviceBam.from_bytes(ctx, bytes(bad))
+    with pytest.raises(WgbsError, match="trailing bytes|corrupt BGZF"):
+        bamio.DeviceBam.from_bytes(ctx, good[:-40])
+    sam = b"a\t0\tchr2\t5\t60\t4M\t*\t0\t0\tACGT\t*\nb\t0\tchr1\t5\t60\t4M\t*\t0\t0\tACGT\t*\nc\t0\tchr2\t9\t60\t4M\t*\t0\t0\tACGT\t*\n"
+    with pytest.raises(WgbsError, match="not sorted"):
+        bamio.DeviceBam.from_bytes(ctx, bamio.sam_to_bam(sam, [("chr1", 100), ("chr2", 100)]))
+    with pytest.raises(WgbsError, match="not a BAM"):
+        from wgbs_tools_b200.patio import bgzf_compress
+        bamio.DeviceBam.from_bytes(ctx, bgzf_compress(b"chr1\t5\tCC\t1\n" * 100))
+    with pytest.raises(WgbsError, match="cannot open"):
+        bamio.DeviceBam(ctx, str(tmp_path / "missing.bam"))
+    # the context is still usable after every failure
+    with bamio.DeviceBam(ctx, path) as db:
+        assert db.nrecords() > 0
+
+
+def test_pileup_from_device_text_equals_pileup_from_host_text(ctx, bamio, oracle, tmp_path):
+    """compressed BAM -> device inflate -> device view -> pileup (nothing but the compressed bytes crosses PCIe) gives the
+    pat text of the oracle pipeline on the same filtered SAM"""
+    H = oracle
+    g = synth.make_genome(41, "chr1", 500_000)
+    sam = synth.make_sam(g, 20_000, 9, paired=True)
+    lines = sam.splitlines(keepends=True)
+    for i in range(0, len(lines), 37):
+        t = lines[i].split(b"\t"); t[4] = b"3"; lines[i] = b"\t".join(t)
+    sam = b"".join(lines)
+    kept = b"".join(l for l in lines if int(l.split(b"\t")[4]) >= 10 and not int(l.split(b"\t")[1]) & 1796 and int(l.split(b"\t")[1]) & 3 == 3)
+    ix = ctx.load_index(g.loci, 1)
+    with bamio.DeviceBam.from_bytes(ctx, bamio.sam_to_bam(sam, [("chr1", g.length)])) as db:
+        d = db.view_dev("chr1", mapq=10, exclude_flags=1796, include_flags=3)
+        assert len(d) == len(kept)
+        P, st = ctx.pileup_sam(ix, d)
+        d.free()
+    P.collapse()
+    txt = P.to_text("chr1"); P.free(); ix.free()
+    pout, pst = H.port_patter(H.port_match_maker(kept), g.loci, g.idx())
+    assert txt == H.port_collapse(pout)
+    assert [st[k] for k in ("lines", "pairs", "empty", "short", "invalid", "paired")] == pst
+
+
+def test_bam2pat_cli_device_decode_equals_host_decode(ctx, bamio, tmp_path):
+    from wgbs_tools_b200 import bam2pat
+    g1 = synth.make_genome(31, "chr1", 400_000, first_idx=1)
+    g2 = synth.make_genome(32, "chr2", 300_000, first_idx=1 + g1.n_cpg)
+    refdir = tmp_path / "ref"; refdir.mkdir()
+    with gzip.open(refdir / "CpG.bed.gz", "wb") as f:
+        f.write(g1.dict_text() + g2.dict_text())
+    (refdir / "CpG.chrome.size").write_text(f"chr1\t{g1.n_cpg}\nchr2\t{g2.n_cpg}\n")
+    (refdir / "chrome.size").write_text(f"chr1\t{g1.length}\nchr2\t{g2.length}\n")
+    sam = synth.make_sam(g1, 9000, 1, paired=True, name_prefix="a") + synth.make_sam(g2, 7000, 2, paired=True, name_prefix="b")
+    bam = tmp_path / "s.bam"; bam.write_bytes(bamio.sam_to_bam(sam, [("chr1", g1.length), ("chr2", g2.length)]))
+    for argv in ([], ["-r", "chr1:100000-180000", "--top_strand"], ["--long", "--no_beta"], ["--mbias"]):
+        outs = []
+        for mode in ("host", "device"):
+            out = tmp_path / f"out_{mode}_{len(outs)}_{abs(hash(tuple(argv)))}"; out.mkdir()
+            bam2pat.main([str(bam), "--genome", str(refdir), "-o", str(out), "--bam_decode", mode] + argv)
+            outs.append(out)
+        a, b = outs
+        assert gzip.decompress((a / "s.pat.gz").read_bytes()) == gzip.decompress((b / "s.pat.gz").read_bytes()), argv
+        assert len(gzip.decompress((a / "s.pat.gz").read_bytes())) > 1000
+        if "--no_beta" not in argv:
+            assert (a / "s.beta").read_bytes() == (b / "s.beta").read_bytes(), argv
+        if "--mbias" in argv:
+            for x in ("OT", "OB"):
+                assert (a / "s.mbias" / f"s.mbias.{x}.txt").read_bytes() == (b / "s.mbias" / f"s.mbias.{x}.txt").read_bytes()

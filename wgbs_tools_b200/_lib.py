@@ -81,6 +81,16 @@ def _load():
         "wgbs_bam_view": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.POINTER(vp), C.POINTER(sz), C.POINTER(u64)]),
         "wgbs_bam_view_ex": (C.c_int, [vp, C.POINTER(ViewOpts), C.POINTER(vp), C.POINTER(sz), C.POINTER(u64)]),
         "wgbs_host_free": (None, [vp]),
+        "wgbs_dbam_open": (C.c_int, [vp, vp, sz, C.POINTER(vp)]),
+        "wgbs_dbam_open_file": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
+        "wgbs_dbam_close": (None, [vp, vp]),
+        "wgbs_dbam_nref": (C.c_int, [vp]),
+        "wgbs_dbam_ref_name": (C.c_char_p, [vp, C.c_int]),
+        "wgbs_dbam_header": (C.c_char_p, [vp]),
+        "wgbs_dbam_nrecords": (u64, [vp, C.c_int]),
+        "wgbs_dbam_inflated_bytes": (u64, [vp]),
+        "wgbs_dbam_view": (C.c_int, [vp, vp, C.POINTER(ViewOpts), C.POINTER(vp), C.POINTER(sz), C.POINTER(u64)]),
+        "wgbs_pileup_dbam": (C.c_int, [vp, vp, vp, C.POINTER(ViewOpts), vp, C.POINTER(vp), vp, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)

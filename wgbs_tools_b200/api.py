@@ -39,6 +39,16 @@ class DevBuf:
         check(lib.wgbs_dev_alloc(ctx.h, self.nbytes, C.byref(p)))
         self.ptr = p.value
 
+    @classmethod
+    def adopt(cls, ctx: "Context", ptr: int, nbytes: int) -> "DevBuf":
+        """take ownership of a device buffer the library allocated (released with wgbs_dev_free)"""
+        b = cls.__new__(cls)
+        b.ctx, b.nbytes, b.ptr = ctx, int(nbytes), ptr
+        return b
+
+    def __len__(self):
+        return self.nbytes
+
     def free(self):
         if self.ptr:
             lib.wgbs_dev_free(self.ctx.h, self.ptr)

@@ -62,11 +62,13 @@ def proc_chr(ctx, ref, region: str, sam: bytes, args, mc_buf):
 class _Source:
     """the alignments of one input: a .bam (native reader) or SAM text (what `samtools view -h BAM` prints)"""
 
-    def __init__(self, path: str, threads: int):
-        self.bam = None; self.sam = None
+    def __init__(self, path: str, threads: int, ctx=None, decode: str = "host"):
+        self.bam = None; self.sam = None; self.on_device = False
         if path.endswith(".bam"):
-            from .bamio import BamFile
-            self.bam = BamFile(path, threads)
+            from .bamio import BamFile, DeviceBam
+            self.on_device = decode == "device"
+            # device: the compressed bytes cross PCIe, BGZF inflate + record filtering + SAM formatting run in HBM (csrc/bamdev.cu)
+            self.bam = DeviceBam(ctx, path) if self.on_device else BamFile(path, threads)
             self.header = self.bam.header
             self.chroms = set(self.bam.refs)                 # `samtools idxstats | cut -f1` lists every @SQ (bam2pat.py:59)
         elif path.endswith(".cram"):
@@ -86,11 +88,14 @@ class _Source:
             return self._first
         return filter_sam(b"".join(self.sam.values()), max_records=n)
 
-    def view(self, region: str, **kw) -> bytes:
+    def view(self, region: str, **kw):
+        """SAM text of one region: bytes, or -- device decode -- a DevBuf the caller frees (len() == number of bytes)"""
         chrom, beg, end = parse_region_str(region)
         if self.bam is not None:
             if chrom not in self.bam.refs:
                 return b""
+            if self.on_device:
+                return self.bam.view_dev(chrom, beg=beg, end=end, **kw)
             return self.bam.view(chrom, beg=beg, end=end, **kw)
         return filter_sam(self.sam.get(chrom, b""), chrom=chrom, beg=beg, end=end, **kw)
 
@@ -148,6 +153,8 @@ def add_args(p):
     p.add_argument("--clip", type=int, default=0, help="Clip for each read the first and last CLIP characters [0]")
     p.add_argument("--long", action="store_true", help="Use long format for pat file (add read name to each line)")
     p.add_argument("-@", "--threads", type=int, default=8, help="host threads for BGZF inflate/deflate")
+    p.add_argument("--bam_decode", choices=["host", "device"], default=os.environ.get("WGBS_BAM_DECODE", "host"),
+                   help="where the .bam is decoded: host threads (zlib), or on the GPU (compressed bytes over PCIe, one warp per BGZF block) [host]")
     p.add_argument("--no_beta", action="store_true", help="Do not generate a beta file")
     p.add_argument("-l", "--lbeta", action="store_true", help="Use lbeta file (uint16) instead of beta (uint8)")
     p.add_argument("-T", "--temp_dir", help="accepted for CLI compatibility (the collapse is a device sort: no temp files)")
@@ -201,7 +208,7 @@ def main(argv=None):
             if os.path.exists(pat_path) and not a.force:
                 print(f"File {pat_path} already exists. Skipping it. Use -f to overwrite", file=sys.stderr)
                 continue
-            src = _Source(path, a.threads)
+            src = _Source(path, a.threads, ctx, a.bam_decode)
             if not is_sorted_header(src.header):
                 print(f"[wt bam2pat] WARNING: based on the @HD, bam file is not sorted: {path}\n[wt bam2pat] Skipping {path}", file=sys.stderr)
                 src.close(); continue
@@ -248,11 +255,15 @@ def main(argv=None):
                 if lists is not None:
                     kw.update(intervals=lists[0].get(chrom, empty_iv), exclude_intervals=lists[1])
                 s = b"" if feq is None else src.view(region, flag_eq=feq, **kw)
-                if not s:
+                if s is None or len(s) == 0:
+                    if hasattr(s, "free"):
+                        s.free()
                     if a.verbose:
                         print(f"[wt bam2pat] Skipping region {region}, no reads found", file=sys.stderr)
                     continue
                 txt, st = proc_chr(ctx, ref, region, s, run, mc)
+                if hasattr(s, "free"):
+                    s.free()
                 if a.mbias and "mbias" in st:
                     mb_total = st["mbias"].astype(np.int64) if mb_total is None else mb_total + st["mbias"]   # mbias_merge (bam2pat.py:375-395)
                 if txt:

@@ -14,6 +14,29 @@ from ._lib import ViewOpts, check, lib
 from .patio import bgzf_compress
 
 
+def view_opts(refs, chrom: str | None = None, mapq: int = 0, exclude_flags: int = 0, include_flags: int = 0, beg: int = 0, end: int = 0,
+              flag_eq=(), read_group: str | None = None, intervals=None, exclude_intervals: bool = False, max_records: int = 0):
+    """wgbs_view_opts for one `samtools view` stage; returns (opts, arrays to keep alive) or (None, None) when nothing can pass"""
+    vo = ViewOpts()
+    vo.refid = -1 if chrom is None else refs.index(chrom)
+    vo.min_mapq, vo.exclude_flags, vo.include_flags, vo.beg, vo.end = mapq, exclude_flags, include_flags or 0, beg, end
+    vo.n_flag_eq = len(flag_eq)
+    for i, f in enumerate(flag_eq):
+        vo.flag_eq[i] = f
+    vo.read_group = read_group.encode() if read_group else None
+    keep = None
+    if intervals is not None:
+        keep = (np.ascontiguousarray(intervals[0], np.int64), np.ascontiguousarray(intervals[1], np.int64))
+        vo.iv_beg, vo.iv_end, vo.n_iv = keep[0].ctypes.data, keep[1].ctypes.data, keep[0].size
+        vo.iv_exclude = int(exclude_intervals)
+        if keep[0].size == 0:                       # samtools -L with no interval on this reference prints nothing
+            if not exclude_intervals:
+                return None, None
+            vo.n_iv = 0
+    vo.max_records = max_records
+    return vo, keep
+
+
 class BamFile:
     def __init__(self, path: str, threads: int = 0):
         h = C.c_void_p()
@@ -28,28 +51,13 @@ class BamFile:
     def nrecords(self, chrom: str | None = None) -> int:
         return int(lib.wgbs_bam_nrecords(self.h, -1 if chrom is None else self.refs.index(chrom)))
 
-    def view(self, chrom: str | None = None, mapq: int = 0, exclude_flags: int = 0, include_flags: int = 0, beg: int = 0, end: int = 0,
-             flag_eq=(), read_group: str | None = None, intervals=None, exclude_intervals: bool = False, max_records: int = 0) -> bytes:
+    def view(self, chrom: str | None = None, **kw) -> bytes:
         """`samtools view BAM chrom[:beg-end] -q mapq -F exclude_flags [-f include_flags] [-r read_group]`, optionally
         `| awk '$2 == flag_eq[0] || ...'`, `-M -L bed` (intervals = (starts, ends) 0-based half-open, sorted, merged) or
         `bedtools intersect -v` (exclude_intervals), `| head -max_records`."""
-        vo = ViewOpts()
-        vo.refid = -1 if chrom is None else self.refs.index(chrom)
-        vo.min_mapq, vo.exclude_flags, vo.include_flags, vo.beg, vo.end = mapq, exclude_flags, include_flags or 0, beg, end
-        vo.n_flag_eq = len(flag_eq)
-        for i, f in enumerate(flag_eq):
-            vo.flag_eq[i] = f
-        vo.read_group = read_group.encode() if read_group else None
-        keep = None
-        if intervals is not None:
-            keep = (np.ascontiguousarray(intervals[0], np.int64), np.ascontiguousarray(intervals[1], np.int64))
-            vo.iv_beg, vo.iv_end, vo.n_iv = keep[0].ctypes.data, keep[1].ctypes.data, keep[0].size
-            vo.iv_exclude = int(exclude_intervals)
-            if keep[0].size == 0:                       # samtools -L with no interval on this reference prints nothing
-                if not exclude_intervals:
-                    return b""
-                vo.n_iv = 0
-        vo.max_records = max_records
+        vo, keep = view_opts(self.refs, chrom, **kw)
+        if vo is None:
+            return b""
         ptr = C.c_void_p(); n = C.c_size_t(); nr = C.c_uint64()
         check(lib.wgbs_bam_view_ex(self.h, C.byref(vo), C.byref(ptr), C.byref(n), C.byref(nr)))
         try:
@@ -60,6 +68,70 @@ class BamFile:
     def close(self):
         if self.h:
             lib.wgbs_bam_close(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class DeviceBam:
+    """A .bam decoded ON THE GPU (csrc/bamdev.cu): the compressed bytes are uploaded, BGZF blocks inflated by one warp each,
+    records located and filtered in HBM.  Same interface and byte-identical views as BamFile; `view_dev` keeps the SAM
+    text in device memory for Context.pileup_sam."""
+
+    def __init__(self, ctx, path: str):
+        h = C.c_void_p()
+        check(lib.wgbs_dbam_open_file(ctx.h, path.encode(), C.byref(h)))
+        self.ctx, self.h = ctx, h.value
+        self.refs = [lib.wgbs_dbam_ref_name(self.h, i).decode() for i in range(lib.wgbs_dbam_nref(self.h))]
+
+    @classmethod
+    def from_bytes(cls, ctx, data) -> "DeviceBam":
+        """data: the bytes of a .bam file (bytes / numpy uint8 / anything with the buffer protocol; pinned memory uploads fastest)"""
+        a = np.frombuffer(data, np.uint8)
+        h = C.c_void_p()
+        check(lib.wgbs_dbam_open(ctx.h, a.ctypes.data, a.size, C.byref(h)))
+        b = cls.__new__(cls)
+        b.ctx, b.h = ctx, h.value
+        b.refs = [lib.wgbs_dbam_ref_name(b.h, i).decode() for i in range(lib.wgbs_dbam_nref(b.h))]
+        return b
+
+    @property
+    def header(self) -> str:
+        return lib.wgbs_dbam_header(self.h).decode(errors="replace")
+
+    @property
+    def inflated_bytes(self) -> int:
+        return int(lib.wgbs_dbam_inflated_bytes(self.h))
+
+    def nrecords(self, chrom: str | None = None) -> int:
+        return int(lib.wgbs_dbam_nrecords(self.h, -1 if chrom is None else self.refs.index(chrom)))
+
+    def view_dev(self, chrom: str | None = None, **kw):
+        """SAM text in device memory (a DevBuf; len() == number of bytes), or None when nothing can pass"""
+        from .api import DevBuf
+        vo, keep = view_opts(self.refs, chrom, **kw)
+        if vo is None:
+            return None
+        ptr = C.c_void_p(); n = C.c_size_t(); nr = C.c_uint64()
+        check(lib.wgbs_dbam_view(self.ctx.h, self.h, C.byref(vo), C.byref(ptr), C.byref(n), C.byref(nr)))
+        return DevBuf.adopt(self.ctx, ptr.value, n.value)
+
+    def view(self, chrom: str | None = None, **kw) -> bytes:
+        d = self.view_dev(chrom, **kw)
+        if d is None:
+            return b""
+        try:
+            return d.to_host().tobytes() if d.nbytes else b""
+        finally:
+            d.free()
+
+    def close(self):
+        if self.h:
+            lib.wgbs_dbam_close(self.ctx.h, self.h)
             self.h = None
 
     def __enter__(self):
@@ -97,14 +169,9 @@ def _tag_bytes(tag: bytes) -> bytes:
     raise ValueError(tag)
 
 
-def sam_to_bam(sam: bytes, refs: list[tuple[str, int]], header_text: str | None = None) -> bytes:
-    """SAM records (no header lines needed) + reference list -> BGZF-compressed BAM bytes"""
-    if header_text is None:
-        header_text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l in refs)
-    rid = {n: i for i, (n, _) in enumerate(refs)}
-    out = [b"BAM\1", struct.pack("<i", len(header_text)), header_text.encode(), struct.pack("<i", len(refs))]
-    for n, l in refs:
-        out += [struct.pack("<i", len(n) + 1), n.encode() + b"\0", struct.pack("<i", l)]
+def _records(sam: bytes, rid: dict) -> bytes:
+    """BAM records (SAM spec 4.2) of the alignment lines of `sam`"""
+    out = []
     for line in sam.splitlines():
         if not line or line.startswith(b"@"):
             continue
@@ -113,18 +180,51 @@ def sam_to_bam(sam: bytes, refs: list[tuple[str, int]], header_text: str | None 
         ops = re.findall(rb"(\d+)([MIDNSHP=X])", cigar) if cigar != b"*" else []
         cig = b"".join(struct.pack("<I", int(n) << 4 | _CIG[o.decode()]) for n, o in ops)
         l_seq = 0 if seq == b"*" else len(seq)
-        sq = bytearray((l_seq + 1) // 2)
-        for i in range(l_seq):
-            sq[i >> 1] |= _SEQ[chr(seq[i])] << (4 if i % 2 == 0 else 0)
-        ql = (b"\xff" * l_seq) if qual == b"*" else bytes(c - 33 for c in qual)
+        if l_seq:
+            codes = _SEQ_LUT[np.frombuffer(seq, np.uint8)]
+            if l_seq & 1:
+                codes = np.append(codes, np.uint8(0))
+            sq = ((codes[0::2] << 4) | codes[1::2]).astype(np.uint8).tobytes()
+        else:
+            sq = b""
+        ql = (b"\xff" * l_seq) if qual == b"*" else (np.frombuffer(qual, np.uint8) - 33).astype(np.uint8).tobytes()
         r = rid.get(rname.decode(), -1)
         nr = r if rnext == b"=" else rid.get(rnext.decode(), -1)
         end = int(pos) - 1 + sum(int(n) for n, o in ops if o in b"MDN=X") if ops else int(pos)
         bin_ = _reg2bin(int(pos) - 1, max(end, int(pos)))
         core = struct.pack("<iiBBHHHiiii", r, int(pos) - 1, len(name) + 1, int(mapq), bin_, len(ops), int(flag), l_seq, nr, int(pnext) - 1, int(tlen))
-        body = core + name + b"\0" + cig + bytes(sq) + ql + b"".join(_tag_bytes(x) for x in t[11:])
+        body = core + name + b"\0" + cig + sq + ql + b"".join(_tag_bytes(x) for x in t[11:])
         out.append(struct.pack("<i", len(body)) + body)
-    return bgzf_compress(b"".join(out))
+    return b"".join(out)
+
+
+_SEQ_LUT = np.zeros(256, np.uint8)
+for _c, _i in _SEQ.items():
+    _SEQ_LUT[ord(_c)] = _i
+
+
+def sam_to_bam(sam: bytes, refs: list[tuple[str, int]], header_text: str | None = None, procs: int = 1) -> bytes:
+    """SAM records (no header lines needed) + reference list -> BGZF-compressed BAM bytes.  procs > 1: the records are
+    built by that many forked worker processes (call it before CUDA is initialised in this process)."""
+    if header_text is None:
+        header_text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l in refs)
+    rid = {n: i for i, (n, _) in enumerate(refs)}
+    out = [b"BAM\1", struct.pack("<i", len(header_text)), header_text.encode(), struct.pack("<i", len(refs))]
+    for n, l in refs:
+        out += [struct.pack("<i", len(n) + 1), n.encode() + b"\0", struct.pack("<i", l)]
+    if procs > 1 and len(sam) > (1 << 20):
+        import multiprocessing as mp
+        cuts = [0]
+        for k in range(1, procs * 4):
+            c = sam.find(b"\n", len(sam) * k // (procs * 4)) + 1
+            if c > cuts[-1]:
+                cuts.append(c)
+        cuts.append(len(sam))
+        with mp.get_context("fork").Pool(procs) as pool:
+            out += pool.starmap(_records, [(sam[a:b], rid) for a, b in zip(cuts[:-1], cuts[1:])])
+    else:
+        out.append(_records(sam, rid))
+    return bgzf_compress(b"".join(out), threads=max(8, procs))
 
 
 def _reg2bin(beg: int, end: int) -> int:

@@ -1,0 +1,386 @@
+// bamdev.cu -- BAM ingest ON THE DEVICE: the compressed .bam bytes are what crosses PCIe (~55 B per
+// 150 bp read instead of ~360 B of SAM text); BGZF blocks are inflated by one warp each, BAM records are located in the
+// inflated stream, filtered like `samtools view` and written out as the SAM text the pileup front end (wgbs_pileup_sam)
+// consumes -- all in HBM.  Stands in for `samtools view BAM region -q Q -F X [-f Y] ...` of reference
+// src/python/bam2pat.py:126-165.  The per-block / per-record logic lives in inflate_core.cuh / bam_core.cuh (host + device,
+// pinned on the CPU by tests/test_bamdev_core.py); this file is the kernels around it and the C ABI.
+//
+//   bgzf_inflate_k   warp per BGZF block: lane 0 decodes Huffman symbols, the warp writes literals / copies matches
+//   bam_guess_k      warp per 16 KiB segment of the inflated stream: first plausible record start (a guess)
+//   bam_walk_k       thread per segment: follow the block_size chain from the segment's entry -> record count, exit
+//   bam_check_k      entry[s+1] must equal exit[s]; repaired and re-walked until nothing changes (exact, whatever the guesses)
+//   bam_fill_k       record offsets; bam_runs_k: per-reference record ranges + sortedness + record sanity
+//   bam_measure_k    thread per record: filters + SAM line length;  bam_format_k: warp per record: the line
+#include <string>
+#include <vector>
+
+#include "bam_core.cuh"
+#include "common.cuh"
+
+using namespace bamcore;
+
+struct wgbs_dbam {
+    uint8_t *data = nullptr;       // inflated BAM stream (device), padded by 16 bytes
+    uint64_t n = 0;
+    uint64_t *rec_off = nullptr;   // offset of every record's block_size field (device)
+    uint64_t nrec = 0;
+    std::string header_text;
+    std::vector<std::string> ref_names;
+    std::vector<int32_t> ref_lens;
+    std::vector<uint64_t> ref_first, ref_last;   // record index range per refID (+ one slot for unplaced records)
+    uint32_t *d_name_off = nullptr; char *d_names = nullptr; int32_t *d_ref_lens = nullptr;
+    uint64_t comp_bytes = 0, n_blocks = 0;
+};
+
+namespace {
+
+constexpr uint64_t SEG = 16384;     // bytes of inflated stream per boundary-search segment
+constexpr int GUESS_DEPTH = 4;      // consecutive plausible records required by a guess
+constexpr int INFL_WARPS = 4;       // warps (= BGZF blocks) per CTA of bgzf_inflate_k
+
+struct BgzfBlock { uint64_t coff /* first byte of the deflate payload */, uoff; uint32_t clen, usize; };
+
+__global__ void __launch_bounds__(INFL_WARPS * 32) bgzf_inflate_k(const uint8_t *__restrict__ comp, const BgzfBlock *__restrict__ blocks, uint32_t nblocks,
+                                                                    uint8_t *out, unsigned long long *__restrict__ err) {
+    __shared__ dflate::Scratch S[INFL_WARPS];
+    const uint32_t w = threadIdx.x >> 5, b = blockIdx.x * INFL_WARPS + w;
+    if (b >= nblocks) return;                       // whole warps leave together
+    const BgzfBlock B = blocks[b];
+    dflate::Inflater<dflate::WarpLanes> I;
+    I.S = &S[w]; I.dst = out + B.uoff; I.dst_len = B.usize;
+    const int rc = I.run(comp + B.coff, B.clen);
+    if (rc != dflate::OK && (threadIdx.x & 31) == 0) atomicMin(err, ((unsigned long long)b << 8) | (unsigned long long)(uint8_t)(-rc));
+}
+
+__global__ void __launch_bounds__(128) bam_guess_k(const uint8_t *__restrict__ data, uint64_t n, uint64_t p0, uint64_t nseg, int32_t n_ref,
+                                                    uint64_t *__restrict__ entry) {
+    const uint64_t s = (uint64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (s >= nseg) return;
+    dflate::WarpLanes lanes;
+    const uint64_t e = s == 0 ? p0 : guess_entry(lanes, data, n, p0 + s * SEG, n_ref, GUESS_DEPTH);
+    if ((threadIdx.x & 31) == 0) entry[s] = e;
+}
+
+__global__ void __launch_bounds__(128) bam_walk_k(const uint8_t *__restrict__ data, uint64_t n, uint64_t p0, uint64_t nseg,
+                                                   const uint64_t *__restrict__ entry, uint8_t *__restrict__ dirty, uint64_t *__restrict__ exit_,
+                                                   uint32_t *__restrict__ cnt, uint64_t *__restrict__ bad) {
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg || !dirty[s]) return;
+    uint32_t c = 0; uint64_t b = ~0ull;
+    exit_[s] = walk_chain(data, n, entry[s], p0 + (s + 1) * SEG, &c, nullptr, &b);
+    cnt[s] = c; bad[s] = b; dirty[s] = 0;
+}
+
+// thread s repairs the entry of segment s+1 (nobody else writes it)
+__global__ void __launch_bounds__(256) bam_check_k(uint64_t nseg, uint64_t *__restrict__ entry, const uint64_t *__restrict__ exit_,
+                                                    const uint64_t *__restrict__ bad, uint8_t *__restrict__ dirty, uint32_t *__restrict__ changed) {
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s + 1 >= nseg) return;
+    if (bad[s] == ~0ull && entry[s + 1] != exit_[s]) { entry[s + 1] = exit_[s]; dirty[s + 1] = 1; atomicAdd(changed, 1u); }
+}
+
+// first corrupt record in stream order (segments are in stream order; a bad segment stops the chain)
+__global__ void __launch_bounds__(256) bam_first_bad_k(uint64_t nseg, const uint64_t *__restrict__ bad, unsigned long long *__restrict__ out) {
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < nseg && bad[s] != ~0ull) atomicMin(out, (unsigned long long)bad[s]);
+}
+
+__global__ void __launch_bounds__(128) bam_fill_k(const uint8_t *__restrict__ data, uint64_t n, uint64_t p0, uint64_t nseg,
+                                                   const uint64_t *__restrict__ entry, const uint64_t *__restrict__ base, uint64_t *__restrict__ rec_off) {
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    uint32_t c; uint64_t b;
+    walk_chain(data, n, entry[s], p0 + (s + 1) * SEG, &c, rec_off + base[s], &b);
+}
+
+// per-reference runs of a coordinate-sorted file: first / last record index and the number of separate runs per slot
+// (slot n_ref: unplaced or out-of-range refID).  Also the record sanity check the per-record kernels rely on.
+__global__ void __launch_bounds__(256) bam_runs_k(const uint8_t *__restrict__ data, const uint64_t *__restrict__ rec_off, uint64_t nrec, int32_t n_ref,
+                                                   unsigned long long *__restrict__ first, unsigned long long *__restrict__ last, uint32_t *__restrict__ runs,
+                                                   unsigned long long *__restrict__ bad_rec) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrec) return;
+    Rec R; R.load(data + rec_off[i]);
+    if (!R.consistent()) atomicMin(bad_rec, (unsigned long long)rec_off[i]);
+    const int32_t me = R.refid;
+    const uint32_t slot = (me >= 0 && me < n_ref) ? (uint32_t)me : (uint32_t)n_ref;
+    const int32_t prev = i ? ldi32(data + rec_off[i - 1] + 4) : 0, next = i + 1 < nrec ? ldi32(data + rec_off[i + 1] + 4) : 0;
+    if (i == 0 || prev != me) { atomicAdd(&runs[slot], 1u); first[slot] = i; }
+    if (i + 1 == nrec || next != me) last[slot] = i + 1;
+}
+
+struct DevRefs { int32_t n; const uint32_t *name_off; const char *names; const int32_t *lens; };
+
+__global__ void __launch_bounds__(256) bam_measure_k(const uint8_t *__restrict__ data, const uint64_t *__restrict__ rec_off, uint64_t nr, DevRefs F, ViewParams V,
+                                                      uint32_t *__restrict__ len, uint32_t *__restrict__ pass, unsigned long long *__restrict__ too_long) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nr) return;
+    Rec R; R.load(data + rec_off[i]);
+    uint32_t l = 0, ok = 0;
+    if (passes(R, V)) {
+        const Refs RF{F.n, F.name_off, F.names, F.lens};
+        CountSink cs; format_record(R, RF, cs);
+        if (cs.n > 0xffffffffull) atomicMin(too_long, (unsigned long long)i); else { l = (uint32_t)cs.n; ok = 1; }
+    }
+    len[i] = l;
+    if (pass) pass[i] = ok;
+}
+
+// head -N: only the first max_records passing records keep their line
+__global__ void __launch_bounds__(256) bam_head_k(uint64_t nr, const uint32_t *__restrict__ rank, uint32_t max_records, uint32_t *__restrict__ len) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nr && rank[i] >= max_records) len[i] = 0;
+}
+
+__global__ void __launch_bounds__(256) bam_format_k(const uint8_t *__restrict__ data, const uint64_t *__restrict__ rec_off, uint64_t nr, DevRefs F,
+                                                     const uint32_t *__restrict__ len, const uint64_t *__restrict__ off, char *__restrict__ text) {
+    const uint64_t i = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= nr || len[i] == 0) return;
+    Rec R; R.load(data + rec_off[i]);
+    const Refs RF{F.n, F.name_off, F.names, F.lens};
+    WriteSink<dflate::WarpLanes> ws; ws.o = text + off[i];
+    format_record(R, RF, ws);
+}
+
+int fail_free(wgbs_ctx *ctx, wgbs_dbam *B, int rc) {
+    if (B) { dfree(ctx, B->data); dfree(ctx, B->rec_off); dfree(ctx, B->d_name_off); dfree(ctx, B->d_names); dfree(ctx, B->d_ref_lens); delete B; }
+    return rc;
+}
+
+const char *inflate_msg(int code) {
+    switch (code) {
+        case dflate::E_INPUT: return "deflate stream ends early";
+        case dflate::E_BTYPE: return "invalid deflate block type";
+        case dflate::E_STORED: return "invalid stored block length";
+        case dflate::E_CODES: return "invalid code lengths";
+        case dflate::E_SYMBOL: return "invalid code";
+        case dflate::E_DIST: return "distance too far back";
+        case dflate::E_OUTPUT: return "more data than ISIZE";
+        case dflate::E_SHORT: return "less data than ISIZE";
+        default: return "inflate error";
+    }
+}
+
+}  // namespace
+
+// bgzf: the bytes of a whole .bam file in HOST memory (pinned memory makes the upload one DMA).
+extern "C" int wgbs_dbam_open(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, wgbs_dbam **out) {
+    RC_TRY(wgbs_ctx_activate(ctx));
+    if (!bgzf || !out) return wgbs_set_err("wgbs_dbam_open: null argument");
+    *out = nullptr;
+    if (is_device_ptr(bgzf)) return wgbs_set_err("wgbs_dbam_open: the compressed bytes must be in host memory (the block table is read on the host)");
+    const uint8_t *f = (const uint8_t *)bgzf;
+    // 1. BGZF block table: one hop per block over the headers
+    std::vector<BgzfBlock> blocks; uint64_t off = 0, uoff = 0;
+    while (off + 28 <= nbytes) {
+        uint32_t xlen = 0; const uint32_t bs = dflate::bgzf_block_size(f + off, nbytes - off, &xlen);
+        if (!bs) return wgbs_set_err("wgbs_dbam_open: not a BGZF file (bad block header at %llu)", (unsigned long long)off);
+        if (off + bs > nbytes || bs < 12 + xlen + 8) return wgbs_set_err("wgbs_dbam_open: corrupt BGZF block at %llu", (unsigned long long)off);
+        BgzfBlock b; b.coff = off + 12 + xlen; b.clen = bs - 12 - xlen - 8; b.usize = ld32(f + off + bs - 4); b.uoff = uoff;
+        if (b.usize > 65536) return wgbs_set_err("wgbs_dbam_open: corrupt BGZF block at %llu (ISIZE %u)", (unsigned long long)off, b.usize);
+        blocks.push_back(b); off += bs; uoff += b.usize;
+    }
+    if (off != nbytes) return wgbs_set_err("wgbs_dbam_open: %llu trailing bytes after the last BGZF block", (unsigned long long)(nbytes - off));
+    if (blocks.size() >= 0xffffffffull) return wgbs_set_err("wgbs_dbam_open: too many BGZF blocks");
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    if ((double)uoff * 1.25 + (double)nbytes > (double)free_b)
+        return wgbs_set_err("wgbs_dbam_open: the inflated stream (%.1f GB) does not fit in device memory (%.1f GB free); open the file in parts", uoff / 1e9, free_b / 1e9);
+
+    wgbs_dbam *B = new wgbs_dbam();
+    B->n = uoff; B->comp_bytes = nbytes; B->n_blocks = blocks.size();
+    Temps T(ctx);
+    uint8_t *d_comp; BgzfBlock *d_blocks; unsigned long long *d_err;
+    int rc;
+    if ((rc = T.alloc(&d_comp, nbytes + 16)) < 0 || (rc = T.alloc(&d_blocks, blocks.size())) < 0 || (rc = T.alloc(&d_err, 4)) < 0 ||
+        (rc = dalloc(ctx, &B->data, uoff + 16)) < 0) return fail_free(ctx, B, rc);
+    if ((rc = copy_any(ctx, d_comp, f, nbytes)) < 0 || (rc = copy_any(ctx, d_blocks, blocks.data(), blocks.size() * sizeof(BgzfBlock))) < 0) return fail_free(ctx, B, rc);
+    CUDA_TRY(cudaMemsetAsync(d_err, 0xff, 4 * 8, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(B->data + uoff, 0, 16, ctx->stream));
+    // 2. inflate: one warp per block
+    if (!blocks.empty()) LAUNCH(ctx, bgzf_inflate_k, grid_for(blocks.size(), INFL_WARPS), INFL_WARPS * 32, 0, d_comp, d_blocks, (uint32_t)blocks.size(), B->data, d_err);
+    unsigned long long herr[4];
+    CUDA_TRY(cudaMemcpyAsync(herr, d_err, sizeof herr, cudaMemcpyDeviceToHost, ctx->stream));
+    // 3. header: "BAM\1" l_text text n_ref { l_name name l_ref }   (SAM spec 4.2)
+    std::vector<uint8_t> head(std::min<uint64_t>(uoff, 1u << 16));
+    if (!head.empty()) CUDA_TRY(cudaMemcpyAsync(head.data(), B->data, head.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    LAUNCH_CHECK();
+    if (herr[0] != ~0ull) return fail_free(ctx, B, wgbs_set_err("wgbs_dbam_open: inflate failed in BGZF block %llu (%s)", herr[0] >> 8, inflate_msg(-(int)(herr[0] & 0xff))));
+    auto need = [&](uint64_t upto) -> int {       // make head[0..upto) available
+        if (upto > uoff) return wgbs_set_err("wgbs_dbam_open: truncated BAM header");
+        if (upto <= head.size()) return 0;
+        const size_t old = head.size(); head.resize(std::min<uint64_t>(uoff, std::max<uint64_t>(upto, 2 * old)));
+        CUDA_TRY(cudaMemcpyAsync(head.data() + old, B->data + old, head.size() - old, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    };
+    if ((rc = need(12)) < 0 || memcmp(head.data(), "BAM\1", 4)) return fail_free(ctx, B, rc < 0 ? rc : wgbs_set_err("wgbs_dbam_open: not a BAM file"));
+    const uint32_t l_text = ld32(head.data() + 4);
+    if ((rc = need(8ull + l_text + 4)) < 0) return fail_free(ctx, B, rc);
+    B->header_text.assign((const char *)head.data() + 8, strnlen((const char *)head.data() + 8, l_text));
+    uint64_t p = 8ull + l_text; const uint32_t n_ref = ld32(head.data() + p); p += 4;
+    if (n_ref > 0x7ffffffeu) return fail_free(ctx, B, wgbs_set_err("wgbs_dbam_open: corrupt BAM header"));
+    std::vector<uint32_t> name_off{0}; std::string names;
+    for (uint32_t i = 0; i < n_ref; i++) {
+        if ((rc = need(p + 4)) < 0) return fail_free(ctx, B, rc);
+        const uint32_t l = ld32(head.data() + p); p += 4;
+        if ((rc = need(p + l + 4)) < 0) return fail_free(ctx, B, rc);
+        B->ref_names.emplace_back((const char *)head.data() + p, l ? strnlen((const char *)head.data() + p, l - 1) : 0); p += l;
+        B->ref_lens.push_back(ldi32(head.data() + p)); p += 4;
+        names += B->ref_names.back(); name_off.push_back((uint32_t)names.size());
+    }
+    if ((rc = dalloc(ctx, &B->d_name_off, name_off.size())) < 0 || (rc = dalloc(ctx, &B->d_names, names.size())) < 0 || (rc = dalloc(ctx, &B->d_ref_lens, (size_t)n_ref)) < 0 ||
+        (rc = copy_any(ctx, B->d_name_off, name_off.data(), name_off.size() * 4)) < 0 || (rc = copy_any(ctx, B->d_names, names.data(), names.size())) < 0 ||
+        (rc = copy_any(ctx, B->d_ref_lens, B->ref_lens.data(), (size_t)n_ref * 4)) < 0) return fail_free(ctx, B, rc);
+    // 4. record table: guess the first record of every segment, walk, repair until every entry equals its predecessor's exit
+    const uint64_t p0 = p, n = uoff, nseg = n > p0 ? (n - p0 + SEG - 1) / SEG : 0;
+    B->ref_first.assign(n_ref + 1, 0); B->ref_last.assign(n_ref + 1, 0);
+    if (nseg) {
+        uint64_t *entry, *exit_, *bad, *base; uint32_t *cnt, *changed; uint8_t *dirty; unsigned long long *d_first, *d_last; uint32_t *d_runs;
+        if ((rc = T.alloc(&entry, nseg)) < 0 || (rc = T.alloc(&exit_, nseg)) < 0 || (rc = T.alloc(&bad, nseg)) < 0 || (rc = T.alloc(&base, nseg + 1)) < 0 ||
+            (rc = T.alloc(&cnt, nseg)) < 0 || (rc = T.alloc(&changed, 1)) < 0 || (rc = T.alloc(&dirty, nseg)) < 0) return fail_free(ctx, B, rc);
+        CUDA_TRY(cudaMemsetAsync(dirty, 1, nseg, ctx->stream));
+        LAUNCH(ctx, bam_guess_k, grid_for(nseg, 4), 128, 0, B->data, n, p0, nseg, (int32_t)n_ref, entry);
+        for (uint64_t round = 0;; round++) {
+            CUDA_TRY(cudaMemsetAsync(changed, 0, 4, ctx->stream));
+            LAUNCH(ctx, bam_walk_k, grid_for(nseg, 128), 128, 0, B->data, n, p0, nseg, entry, dirty, exit_, cnt, bad);
+            LAUNCH(ctx, bam_check_k, grid_for(nseg, 256), 256, 0, nseg, entry, exit_, bad, dirty, changed);
+            uint32_t h = 0;
+            CUDA_TRY(cudaMemcpyAsync(&h, changed, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            if (!h) break;
+            if (round > nseg) return fail_free(ctx, B, wgbs_set_err("wgbs_dbam_open: record table did not converge"));
+        }
+        CUDA_TRY(cudaMemsetAsync(d_err, 0xff, 4 * 8, ctx->stream));
+        LAUNCH(ctx, bam_first_bad_k, grid_for(nseg, 256), 256, 0, nseg, bad, d_err);
+        if ((rc = scan_u32_u64(ctx, cnt, base, nseg)) < 0) return fail_free(ctx, B, rc);
+        uint64_t nrec = 0;
+        CUDA_TRY(cudaMemcpyAsync(&nrec, base + nseg, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(herr, d_err, sizeof herr, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (herr[0] != ~0ull) return fail_free(ctx, B, wgbs_set_err("wgbs_dbam_open: corrupt BAM record at uncompressed offset %llu", herr[0]));
+        B->nrec = nrec;
+        if ((rc = dalloc(ctx, &B->rec_off, (size_t)nrec)) < 0) return fail_free(ctx, B, rc);
+        LAUNCH(ctx, bam_fill_k, grid_for(nseg, 128), 128, 0, B->data, n, p0, nseg, entry, base, B->rec_off);
+        if (nrec) {
+            if ((rc = T.alloc(&d_first, (size_t)n_ref + 1)) < 0 || (rc = T.alloc(&d_last, (size_t)n_ref + 1)) < 0 || (rc = T.alloc(&d_runs, (size_t)n_ref + 1)) < 0) return fail_free(ctx, B, rc);
+            CUDA_TRY(cudaMemsetAsync(d_first, 0, ((size_t)n_ref + 1) * 8, ctx->stream)); CUDA_TRY(cudaMemsetAsync(d_last, 0, ((size_t)n_ref + 1) * 8, ctx->stream));
+            CUDA_TRY(cudaMemsetAsync(d_runs, 0, ((size_t)n_ref + 1) * 4, ctx->stream));
+            LAUNCH(ctx, bam_runs_k, grid_for(nrec, 256), 256, 0, B->data, B->rec_off, nrec, (int32_t)n_ref, d_first, d_last, d_runs, d_err + 1);
+            std::vector<uint32_t> runs(n_ref + 1);
+            static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "");
+            CUDA_TRY(cudaMemcpyAsync(B->ref_first.data(), d_first, ((size_t)n_ref + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(B->ref_last.data(), d_last, ((size_t)n_ref + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(runs.data(), d_runs, ((size_t)n_ref + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(herr, d_err, sizeof herr, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            if (herr[1] != ~0ull) return fail_free(ctx, B, wgbs_set_err("wgbs_dbam_open: corrupt BAM record at uncompressed offset %llu", herr[1]));
+            for (uint32_t i = 0; i <= n_ref; i++)
+                if (runs[i] > 1) return fail_free(ctx, B, wgbs_set_err("the BAM is not sorted by coordinate (reference %d appears in two separate runs)", i < n_ref ? (int)i : -1));
+        }
+    }
+    LAUNCH_CHECK();
+    *out = B;
+    return 0;
+}
+
+extern "C" int wgbs_dbam_open_file(wgbs_ctx *ctx, const char *path, wgbs_dbam **out) {
+    RC_TRY(wgbs_ctx_activate(ctx));
+    if (!path || !out) return wgbs_set_err("wgbs_dbam_open_file: null argument");
+    FILE *f = fopen(path, "rb");
+    if (!f) return wgbs_set_err("wgbs_dbam_open_file: cannot open %s", path);
+    fseek(f, 0, SEEK_END); const long fsz = ftell(f); fseek(f, 0, SEEK_SET);
+    void *pin = nullptr;
+    if (cudaMallocHost(&pin, (size_t)fsz + 16) != cudaSuccess) { fclose(f); cudaGetLastError(); return wgbs_set_err("wgbs_dbam_open_file: cannot pin %ld bytes", fsz); }
+    const size_t got = fsz ? fread(pin, 1, (size_t)fsz, f) : 0;
+    fclose(f);
+    int rc = got == (size_t)fsz ? wgbs_dbam_open(ctx, pin, (size_t)fsz, out) : wgbs_set_err("wgbs_dbam_open_file: short read on %s", path);
+    cudaFreeHost(pin);
+    if (rc < 0) { std::string m = g_wgbs_err; return wgbs_set_err("%s: %s", path, m.c_str()); }
+    return rc;
+}
+
+extern "C" void wgbs_dbam_close(wgbs_ctx *ctx, wgbs_dbam *B) {
+    if (!ctx || !B) return;
+    cudaSetDevice(ctx->device);
+    fail_free(ctx, B, 0);
+}
+extern "C" int wgbs_dbam_nref(const wgbs_dbam *B) { return B ? (int)B->ref_names.size() : -1; }
+extern "C" const char *wgbs_dbam_ref_name(const wgbs_dbam *B, int i) { return (B && i >= 0 && i < (int)B->ref_names.size()) ? B->ref_names[i].c_str() : nullptr; }
+extern "C" const char *wgbs_dbam_header(const wgbs_dbam *B) { return B ? B->header_text.c_str() : nullptr; }
+extern "C" uint64_t wgbs_dbam_nrecords(const wgbs_dbam *B, int refid) {
+    if (!B) return 0;
+    if (refid < 0) return B->nrec;
+    return refid < (int)B->ref_names.size() ? B->ref_last[refid] - B->ref_first[refid] : 0;
+}
+extern "C" uint64_t wgbs_dbam_inflated_bytes(const wgbs_dbam *B) { return B ? B->n : 0; }
+
+// SAM text (DEVICE memory, release with wgbs_dev_free) of the records that pass the filters: wgbs_bam_view_ex on the device.
+extern "C" int wgbs_dbam_view(wgbs_ctx *ctx, const wgbs_dbam *B, const wgbs_view_opts *vo, char **dev_text, size_t *nbytes, uint64_t *nrecords) {
+    RC_TRY(wgbs_ctx_activate(ctx));
+    if (!B || !vo || !dev_text || !nbytes) return wgbs_set_err("wgbs_dbam_view: null argument");
+    *dev_text = nullptr; *nbytes = 0;
+    if (vo->n_flag_eq < 0 || vo->n_flag_eq > 4) return wgbs_set_err("wgbs_dbam_view: n_flag_eq must be 0..4");
+    if (vo->n_iv && (!vo->iv_beg || !vo->iv_end)) return wgbs_set_err("wgbs_dbam_view: interval list is null");
+    if (vo->n_iv && (is_device_ptr(vo->iv_beg) || is_device_ptr(vo->iv_end))) return wgbs_set_err("wgbs_dbam_view: interval lists must be host arrays");
+    for (size_t k = 0; k + 1 < vo->n_iv; k++)
+        if (vo->iv_beg[k + 1] < vo->iv_end[k] || vo->iv_end[k] < vo->iv_beg[k]) return wgbs_set_err("wgbs_dbam_view: intervals must be sorted and non-overlapping");
+    if (vo->max_records > 0xffffffffull) return wgbs_set_err("wgbs_dbam_view: max_records too large");
+    uint64_t r0 = 0, r1 = B->nrec;
+    if (vo->refid >= 0) { if (vo->refid >= (int)B->ref_names.size()) return wgbs_set_err("wgbs_dbam_view: no such reference"); r0 = B->ref_first[vo->refid]; r1 = B->ref_last[vo->refid]; }
+    const uint64_t nr = r1 - r0;
+    if (nr >= 0xffffffffull) return wgbs_set_err("wgbs_dbam_view: too many records in one call");
+    Temps T(ctx);
+    ViewParams V; memset(&V, 0, sizeof V);
+    V.refid = vo->refid; V.min_mapq = vo->min_mapq; V.exclude_flags = vo->exclude_flags; V.include_flags = vo->include_flags; V.beg = vo->beg; V.end = vo->end;
+    V.n_flag_eq = vo->n_flag_eq; for (int k = 0; k < 4; k++) V.flag_eq[k] = vo->flag_eq[k];
+    V.n_iv = vo->n_iv; V.iv_exclude = vo->iv_exclude;
+    if (vo->n_iv) {
+        int64_t *a, *b;
+        RC_TRY(T.alloc(&a, vo->n_iv)); RC_TRY(T.alloc(&b, vo->n_iv));
+        RC_TRY(copy_any(ctx, a, vo->iv_beg, vo->n_iv * 8)); RC_TRY(copy_any(ctx, b, vo->iv_end, vo->n_iv * 8));
+        V.iv_beg = a; V.iv_end = b;
+    }
+    if (vo->read_group) {
+        V.have_rg = 1; V.rg_len = (uint32_t)strlen(vo->read_group);
+        char *g; RC_TRY(T.alloc(&g, (size_t)V.rg_len + 1)); RC_TRY(copy_any(ctx, g, vo->read_group, (size_t)V.rg_len + 1));
+        V.rg = g;
+    }
+    const DevRefs F{(int32_t)B->ref_names.size(), B->d_name_off, B->d_names, B->d_ref_lens};
+    uint32_t *len, *pass; uint64_t *off; unsigned long long *too_long;
+    RC_TRY(T.alloc(&len, nr)); RC_TRY(T.alloc(&pass, nr + 1)); RC_TRY(T.alloc(&off, nr + 1)); RC_TRY(T.alloc(&too_long, 1));
+    CUDA_TRY(cudaMemsetAsync(too_long, 0xff, 8, ctx->stream));
+    uint64_t npass = 0, tot = 0;
+    if (nr) {
+        LAUNCH(ctx, bam_measure_k, grid_for(nr, 256), 256, 0, B->data, B->rec_off + r0, nr, F, V, len, pass, too_long);
+        uint32_t *rank; RC_TRY(T.alloc(&rank, nr + 1));
+        RC_TRY(scan_u32_u32(ctx, pass, rank, nr));
+        if (vo->max_records) LAUNCH(ctx, bam_head_k, grid_for(nr, 256), 256, 0, nr, rank, (uint32_t)vo->max_records, len);
+        RC_TRY(scan_u32_u64(ctx, len, off, nr));
+        uint32_t np32 = 0; unsigned long long tl = 0;
+        CUDA_TRY(cudaMemcpyAsync(&np32, rank + nr, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(&tot, off + nr, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(&tl, too_long, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (tl != ~0ull) return wgbs_set_err("wgbs_dbam_view: record %llu formats to more than 4 GiB of text", tl + r0);
+        npass = vo->max_records ? std::min<uint64_t>(np32, vo->max_records) : np32;
+    }
+    char *text = nullptr;
+    RC_TRY(dalloc(ctx, &text, (size_t)tot + 16));
+    if (tot) LAUNCH(ctx, bam_format_k, grid_for(nr, 8), 256, 0, B->data, B->rec_off + r0, nr, F, len, off, text);
+    LAUNCH_CHECK();
+    *dev_text = text; *nbytes = (size_t)tot; if (nrecords) *nrecords = npass;
+    return 0;
+}
+
+// `samtools view ... | [match_maker |] patter ...` without leaving the device: wgbs_dbam_view + wgbs_pileup_sam_mbias
+extern "C" int wgbs_pileup_dbam(wgbs_ctx *ctx, const wgbs_index *ix, const wgbs_dbam *B, const wgbs_view_opts *vo, const wgbs_pileup_opts *opts,
+                                wgbs_pats **out, uint64_t *stats, int32_t *mbias) {
+    char *text = nullptr; size_t nb = 0;
+    RC_TRY(wgbs_dbam_view(ctx, B, vo, &text, &nb, nullptr));
+    if (nb >= 0xffffffffull) { dfree(ctx, text); return wgbs_set_err("wgbs_pileup_dbam: %zu bytes of SAM text in one call (limit 4 GiB): restrict the region", nb); }
+    const int rc = wgbs_pileup_sam_mbias(ctx, ix, text, nb, opts, out, stats, mbias);
+    dfree(ctx, text);
+    return rc;
+}
