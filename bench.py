@@ -271,35 +271,49 @@ def extras(ctx, torch, peak, sam_for_bam=b""):
     return out
 
 
-def bam_device_leg(ctx, torch, stream, ix, g, bam_bytes, n_rec, sam_bytes, h_text, h_beta, mc, ref_text, ref_beta, peak, steps=8, warmup=3):
-    """The same batch end to end from the COMPRESSED BAM bytes in pinned host memory (no SAM-text detour over
-    PCIe): upload + one-warp-per-block BGZF inflate + record table + view + pileup + pat2beta + collapse + pat text and .beta
-    read back.  Outputs are compared with the SAM-text path's."""
+def bam_device_leg(tmp: str, n_rec: int, sam_bytes: int, peak: float, steps=8, warmup=3):
+    """(child process of the bench) The same batch end to end from the COMPRESSED BAM bytes in pinned host memory (SURVEY 8f-1:
+    no SAM-text detour over PCIe): upload + one-warp-per-block BGZF inflate + record table + view + pileup + pat2beta + collapse
+    + pat text and .beta read back.  Outputs are compared with the SAM-text path's (files written by the parent)."""
     import ctypes as C
+    import torch
     from wgbs_tools_b200._lib import PileupOpts, ViewOpts, check, lib
+    from wgbs_tools_b200.api import Context
+    bam_bytes = open(os.path.join(tmp, "batch.bam"), "rb").read()
+    ref_text = open(os.path.join(tmp, "ref.pat"), "rb").read(); ref_beta = open(os.path.join(tmp, "ref.beta"), "rb").read()
+    loci = np.load(os.path.join(tmp, "loci.npy"))
+    n_cpg = int(loci.size)
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+    ctx = Context(0, stream=stream.cuda_stream)
+    ix = ctx.load_index(loci, 1)
     h_bam = torch.frombuffer(bytearray(bam_bytes), dtype=torch.uint8).pin_memory()
+    h_text = torch.empty(max(len(ref_text) * 2, 1 << 20), dtype=torch.uint8).pin_memory()
+    h_beta = torch.empty((n_cpg, 2), dtype=torch.uint8).pin_memory()
+    mc = torch.zeros((n_cpg, 2), dtype=torch.int32, device="cuda")
     out_n = {}
 
     def step():
         B = C.c_void_p()
         check(lib.wgbs_dbam_open(ctx.h, h_bam.data_ptr(), h_bam.numel(), C.byref(B)))
+        out_n["inflated"] = int(lib.wgbs_dbam_inflated_bytes(B))
         vo = ViewOpts(); vo.refid = 0
         o = PileupOpts(1, 0, -1, 0, 0, 0.67, b"C")
         h = C.c_void_p(); st = (C.c_uint64 * 8)()
         check(lib.wgbs_pileup_dbam(ctx.h, ix.h, B, C.byref(vo), C.addressof(o), C.byref(h), C.addressof(st), None))
         lib.wgbs_dbam_close(ctx.h, B)
-        check(lib.wgbs_pat2beta(ctx.h, h, 1, g.n_cpg + 1, mc.data_ptr(), 1))
+        check(lib.wgbs_pat2beta(ctx.h, h, 1, n_cpg + 1, mc.data_ptr(), 1))
         check(lib.wgbs_collapse(ctx.h, h))
         n = C.c_size_t()
         check(lib.wgbs_pats_format(ctx.h, h, CHR.encode(), h_text.data_ptr(), h_text.numel(), C.byref(n)))
-        check(lib.wgbs_trim(ctx.h, mc.data_ptr(), g.n_cpg, 8, h_beta.data_ptr()))
+        check(lib.wgbs_trim(ctx.h, mc.data_ptr(), n_cpg, 8, h_beta.data_ptr()))
         lib.wgbs_pats_free(ctx.h, h)
         out_n.update(n=n.value, lines=int(st[0]))
 
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
-    same = bytes(h_text[:out_n["n"]].numpy().tobytes()) == ref_text and h_beta.numpy().tobytes() == ref_beta
+    same = h_text[:out_n["n"]].numpy().tobytes() == ref_text and h_beta.numpy().tobytes() == ref_beta
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(steps):
@@ -313,22 +327,18 @@ def bam_device_leg(ctx, torch, stream, ix, g, bam_bytes, n_rec, sam_bytes, h_tex
     rep = ctx.prof_report()
     ctx.prof(False)
     top = sorted(rep.items(), key=lambda kv: -kv[1][1])
-    infl = rep.get("bgzf_inflate_k")
     res = {"records": n_rec, "lines_seen": out_n["lines"], "ms_per_step": ms, "reads_per_sec": n_rec / (ms / 1e3), "h2d_bytes_per_step": len(bam_bytes),
-           "d2h_bytes_per_step": out_n["n"] + 2 * g.n_cpg, "sam_text_bytes_equivalent": sam_bytes, "identical_to_sam_text_path": bool(same),
-           "breakdown_ms_per_step": {k: round(v[1] / 2, 4) for k, v in top[:12]},
+           "d2h_bytes_per_step": out_n["n"] + 2 * n_cpg, "sam_text_bytes_equivalent": sam_bytes, "inflated_bytes": out_n["inflated"],
+           "identical_to_sam_text_path": bool(same), "breakdown_ms_per_step": {k: round(v[1] / 2, 4) for k, v in top[:12]},
            "mode": "serial: upload, inflate, view, pileup, read back, one batch after the other; wgbs_dbam_open + wgbs_pileup_dbam from pinned host bytes"}
+    infl = rep.get("bgzf_inflate_k")
     if infl:
         sec = infl[1] / infl[0] / 1e3
-        # algorithmic bytes of the inflate: compressed bytes read + inflated bytes written
-        inflated = sam_bytes  # lower bound stand-in replaced below when the library reports it
-        B = C.c_void_p(); check(lib.wgbs_dbam_open(ctx.h, h_bam.data_ptr(), h_bam.numel(), C.byref(B)))
-        inflated = int(lib.wgbs_dbam_inflated_bytes(B)); lib.wgbs_dbam_close(ctx.h, B)
-        ab = len(bam_bytes) + inflated
-        res["roofline"] = {"kernel": "bgzf_inflate_k", "bound": "latency (serial Huffman decode per block), reported against hbm", "achieved": ab / sec / 1e9, "peak": peak,
-                           "unit": "GB/s", "frac": ab / sec / 1e9 / peak, "algorithmic_bytes": ab, "avg_launch_ms": sec * 1e3, "inflated_bytes": inflated}
+        ab = len(bam_bytes) + out_n["inflated"]          # algorithmic bytes: compressed bytes read + inflated bytes written
+        res["roofline"] = {"kernel": "bgzf_inflate_k", "bound": "latency of the serial Huffman walk per block; reported against hbm", "achieved": ab / sec / 1e9,
+                           "peak": peak, "unit": "GB/s", "frac": ab / sec / 1e9 / peak, "algorithmic_bytes": ab, "avg_launch_ms": sec * 1e3}
     log(f"[bench] bam_device: {ms:.3f} ms/step, {res['reads_per_sec'] / 1e6:.1f} M reads/s, identical={same}")
-    return res
+    print(json.dumps(res), flush=True)
 
 
 def main():
@@ -339,7 +349,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=1_000_000)
     ap.add_argument("--no-extras", dest="no_extras", action="store_true", help="skip the pat2beta / homog / segment side measurements")
+    ap.add_argument("--bam-leg", dest="bam_leg", help=argparse.SUPPRESS)       # internal: child process of the device-BAM leg
+    ap.add_argument("--sam-bytes", dest="sam_bytes", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--peak", type=float, default=6650.0, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.bam_leg:
+        return bam_device_leg(args.bam_leg, args.reads, args.sam_bytes, args.peak)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     workload = f"bam2pat synthetic 150bp PE WGBS, {args.reads:,} records per GPU, {CHR} index ({N_CPG:,} CpGs)"
@@ -579,14 +594,25 @@ def main():
             log(f"[bench] extras failed: {e!r}")
             extra = {"error": repr(e)}
         if bam_bytes is not None:
+            # in a child process with a time limit: a fault in this (newest) leg can then neither poison this process's CUDA
+            # context nor hold up the bench line
+            tmp = tempfile.mkdtemp(prefix="wgbsbam_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
             try:
                 run_step(True)
-                ref_text = bytes(h_text[:last["text_bytes"]].numpy().tobytes()); ref_beta = h_beta.numpy().tobytes()
-                extra["bam_device"] = bam_device_leg(ctx, torch, stream, ix, g, bam_bytes, n_rec, text_bytes, h_text, h_beta, mc, ref_text, ref_beta,
-                                                     roof["peak"] if roof else 6650.0)
+                torch.cuda.synchronize()
+                open(os.path.join(tmp, "ref.pat"), "wb").write(h_text[:last["text_bytes"]].numpy().tobytes())
+                open(os.path.join(tmp, "ref.beta"), "wb").write(h_beta.numpy().tobytes())
+                open(os.path.join(tmp, "batch.bam"), "wb").write(bam_bytes)
+                np.save(os.path.join(tmp, "loci.npy"), g.loci)
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--bam-leg", tmp, "--reads", str(n_rec), "--sam-bytes", str(text_bytes),
+                                    "--peak", str(roof["peak"] if roof else 6650.0)], stdout=subprocess.PIPE, timeout=300)
+                line = [l for l in r.stdout.decode(errors="replace").splitlines() if l.startswith("{")]
+                extra["bam_device"] = json.loads(line[-1]) if line else {"error": f"child exited {r.returncode} without a result"}
             except Exception as e:
                 log(f"[bench] bam_device leg failed: {e!r}")
                 extra["bam_device"] = {"error": repr(e)}
+            finally:
+                subprocess.run(["rm", "-rf", tmp])
 
     if rank == 0:
         out = {

@@ -239,6 +239,11 @@ void wgbs_host_free(void *);
  * wgbs_bam_view_ex are formatted to SAM text in HBM, ready for wgbs_pileup_sam.  Same results, byte for byte, as the host
  * reader above.  The whole inflated stream stays resident: a file whose inflated size exceeds free device memory is refused.
  * ------------------------------------------------------------------------------------------------------------- */
+/* BGZF inflate on the device (htslib's bgzf reader: deflate + ISIZE + CRC32 checks): bgzf = the bytes of any BGZF file
+ * (.bam, .pat.gz, CpG.bed.gz) in HOST memory; *dev_out = DEVICE buffer with the inflated bytes (wgbs_dev_free).  E.g. a
+ * .pat.gz goes from disk to wgbs_pats_from_text with only its compressed bytes crossing PCIe (`gunzip -c` of reference
+ * pat2beta.py:17-22 / homog.py:66). */
+int wgbs_bgzf_inflate(wgbs_ctx *, const void *bgzf, size_t nbytes, void **dev_out, size_t *out_bytes);
 typedef struct wgbs_dbam wgbs_dbam;
 /* bgzf: the bytes of a whole .bam file in HOST memory (pinned memory makes the upload a single DMA) */
 int wgbs_dbam_open(wgbs_ctx *, const void *bgzf, size_t nbytes, wgbs_dbam **out);

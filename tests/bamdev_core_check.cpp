@@ -77,14 +77,20 @@ static int zlib_inflate(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t u
     inflateEnd(&zs);
     return (rc == Z_STREAM_END && zs.avail_out == 0) ? 0 : -1;
 }
-static int one_lane(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usize) {
+static uint32_t g_crc_table[256];
+static int one_lane(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usize, uint32_t want_crc = 0, bool check_crc = false) {
     Scratch S; Inflater<OneLane> I; I.S = &S; I.dst = dst; I.dst_len = usize;
-    return I.run(src, n);
+    int rc = I.run(src, n);
+    if (rc == OK && check_crc && crc32_block(OneLane(), dst, usize, g_crc_table) != want_crc) rc = E_CRC;
+    return rc;
 }
-static int emu_warp(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usize) {
+static int emu_warp(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usize, uint32_t want_crc) {
     static EmuShared sh; Scratch S; int rcs[32];
     std::vector<std::thread> th;
-    for (int l = 0; l < 32; l++) th.emplace_back([&, l]() { Inflater<EmuLanes> I; I.lanes = EmuLanes{l, &sh}; I.S = &S; I.dst = dst; I.dst_len = usize; rcs[l] = I.run(src, n); });
+    for (int l = 0; l < 32; l++) th.emplace_back([&, l]() {
+        Inflater<EmuLanes> I; I.lanes = EmuLanes{l, &sh}; I.S = &S; I.dst = dst; I.dst_len = usize; rcs[l] = I.run(src, n);
+        if (rcs[l] == OK) { I.lanes.sync(); if (crc32_block(I.lanes, dst, usize, g_crc_table) != want_crc) rcs[l] = E_CRC; }
+    });
     for (auto &t : th) t.join();
     for (int l = 1; l < 32; l++) if (rcs[l] != rcs[0]) { fprintf(stderr, "lanes disagree on rc\n"); exit(4); }
     return rcs[0];
@@ -97,10 +103,12 @@ static int cmd_inflate(const char *path, int emu_blocks) {
         const Blk &b = blocks[i];
         const uint8_t *src = f.data() + b.coff + 12 + b.xlen; const uint32_t n = b.csize - 12 - b.xlen - 8;
         std::vector<uint8_t> a(b.usize + 1), c(b.usize + 1), e(b.usize + 1);
-        const int rz = zlib_inflate(src, n, a.data(), b.usize);
-        const int r1 = one_lane(src, n, c.data(), b.usize);
+        const uint32_t want = bamcore::ld32(f.data() + b.coff + b.csize - 8);
+        int rz = zlib_inflate(src, n, a.data(), b.usize);
+        if (rz == 0 && (uint32_t)crc32(crc32(0L, Z_NULL, 0), a.data(), b.usize) != want) rz = -1;       // what htslib's bgzf reader checks
+        const int r1 = one_lane(src, n, c.data(), b.usize, want, true);
         bool ok = (rz == 0) == (r1 == 0) && (rz != 0 || !memcmp(a.data(), c.data(), b.usize));
-        if ((int)i < emu_blocks) { const int r2 = emu_warp(src, n, e.data(), b.usize); ok = ok && r2 == r1 && (r1 != 0 || !memcmp(a.data(), e.data(), b.usize)); nemu++; }
+        if ((int)i < emu_blocks) { const int r2 = emu_warp(src, n, e.data(), b.usize, want); ok = ok && r2 == r1 && (r1 != 0 || !memcmp(a.data(), e.data(), b.usize)); nemu++; }
         if (!ok) { nbad++; fprintf(stderr, "block %zu: zlib %d core %d\n", i, rz, r1); }
         bytes += b.usize;
     }
@@ -181,6 +189,7 @@ static int cmd_fmtg(long N, unsigned seed) {
 }
 
 int main(int argc, char **argv) {
+    for (uint32_t i = 0; i < 256; i++) g_crc_table[i] = crc_table_entry(i);
     if (argc >= 3 && !strcmp(argv[1], "inflate")) return cmd_inflate(argv[2], argc > 3 ? atoi(argv[3]) : 0);
     if (argc >= 5 && !strcmp(argv[1], "view")) return cmd_view(argv[2], strtoull(argv[3], nullptr, 10), atoi(argv[4]), argc - 5, argv + 5);
     if (argc >= 4 && !strcmp(argv[1], "fmtg")) return cmd_fmtg(atol(argv[2]), (unsigned)atoi(argv[3]));

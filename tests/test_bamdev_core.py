@@ -69,7 +69,7 @@ def test_inflate_core_matches_zlib_on_every_block_type(check, sam, tmp_path):
     assert f"blocks {len(parts) + 1} emu 8 " in r.stdout and r.stdout.strip().endswith("mismatches 0")
 
 
-def test_inflate_core_rejects_what_zlib_rejects(check, sam, tmp_path):
+def test_inflate_core_rejects_what_zlib_rejects(check, sam, tmp_path, built_lib):
     """corrupt payloads: the verdict (ok / error) must agree with zlib block by block; never a crash"""
     _, s = sam
     rng = np.random.default_rng(3)
@@ -82,12 +82,21 @@ def test_inflate_core_rejects_what_zlib_rejects(check, sam, tmp_path):
         parts.append(bytes(b))
     short = bytearray(good); short[-4:] = struct.pack("<I", 29999)            # ISIZE smaller than the stream
     longer = bytearray(good); longer[-4:] = struct.pack("<I", 30001)
-    parts += [bytes(short), bytes(longer)]
+    badcrc = bytearray(good); badcrc[-8] ^= 1                                  # the gzip trailer's CRC32 (htslib checks it)
+    parts += [bytes(short), bytes(longer), bytes(badcrc)]
     p = tmp_path / "bad.bgzf"
     p.write_bytes(b"".join(parts))
     r = subprocess.run([check, "inflate", str(p), "2"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout + r.stderr                            # 0 = no DISAGREEMENT with zlib
+    assert r.returncode == 0, r.stdout + r.stderr                            # 0 = no DISAGREEMENT with zlib (+ CRC32 check)
     assert r.stdout.strip().endswith("mismatches 0")
+    # and the verdict on the last three is "reject"
+    p2 = tmp_path / "bad3.bgzf"; p2.write_bytes(b"".join(parts[-3:]))
+    for i in range(3):
+        q = tmp_path / f"one{i}.bgzf"; q.write_bytes(parts[-3 + i] + good)
+        from wgbs_tools_b200 import bamio
+        from wgbs_tools_b200._lib import WgbsError
+        with pytest.raises(WgbsError, match="inflate failed"):
+            bamio.BamFile(str(q), threads=1)                                 # the host reader (zlib + crc32) rejects them too
 
 
 def test_fmt_g_matches_printf(check):

@@ -38,6 +38,61 @@ def sample(bamio, tmp_path_factory):
     return g, full, str(p)
 
 
+def _block(data: bytes, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, mem=8) -> bytes:
+    co = zlib.compressobj(level, zlib.DEFLATED, -15, mem, strategy)
+    comp = co.compress(data) + co.flush()
+    return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(comp) + 25) + comp
+            + struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data)))
+
+
+def test_bgzf_inflate_kernel_matches_zlib(ctx, sample):
+    """bgzf_inflate_k alone (wgbs_bgzf_inflate): stored / fixed / dynamic blocks, long codes, overlapping matches, several
+    deflate blocks per BGZF block, empty blocks, incompressible bytes -- output == zlib's, byte for byte"""
+    from wgbs_tools_b200.patio import BGZF_EOF, bgzf_compress
+    _, s, _ = sample
+    rng = np.random.default_rng(1)
+    datas = [s[:60000], s[60000:125000], b"", b"a", b"ab" * 30000, b"\0" * 65000, rng.integers(0, 256, 50000, dtype=np.uint8).tobytes(),
+             rng.integers(0, 4, 65000, dtype=np.uint8).tobytes(), bytes(range(256)) * 200, s[200000:260000]]
+    parts, plain = [], []
+    for d in datas:
+        for lvl in (0, 1, 6, 9):
+            if lvl == 0 and len(d) > 65000:
+                continue
+            parts.append(_block(d, lvl)); plain.append(d)
+        for lvl, st, mem in ((6, zlib.Z_FIXED, 8), (6, zlib.Z_HUFFMAN_ONLY, 8), (6, zlib.Z_RLE, 8), (9, zlib.Z_DEFAULT_STRATEGY, 1)):
+            parts.append(_block(d, lvl, st, mem)); plain.append(d)
+    for k, (blk, d) in enumerate(zip(parts, plain)):                   # one at a time first: a failure names the block kind
+        out = ctx.bgzf_inflate(blk)
+        got = out.to_host().tobytes() if out.nbytes else b""
+        out.free()
+        assert got == d, f"block {k}: {len(d)} bytes"
+    out = ctx.bgzf_inflate(b"".join(parts) + BGZF_EOF)
+    assert out.to_host().tobytes() == b"".join(plain)
+    out.free()
+    big = s * 3                                                        # a few thousand blocks in one launch
+    out = ctx.bgzf_inflate(bgzf_compress(big))
+    assert out.nbytes == len(big) and out.to_host().tobytes() == big
+    out.free()
+    out = ctx.bgzf_inflate(BGZF_EOF)
+    assert out.nbytes == 0
+    out.free()
+
+
+def test_pat2beta_cli_device_inflate(ctx, tmp_path):
+    """X.pat.gz (BGZF) inflated in HBM and parsed there: same .beta as the host gunzip path"""
+    from wgbs_tools_b200 import pat2beta as p2b
+    from wgbs_tools_b200.patio import bgzf_compress
+    N = 50_000
+    idx, pats, cnt = synth.make_pat_records(1, 40_000, N)
+    txt = synth.pat_text("chr1", idx, pats, cnt)
+    (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir()
+    pg = tmp_path / "x.pat.gz"; pg.write_bytes(bgzf_compress(txt))
+    p2b.pat2beta(ctx, str(pg), str(tmp_path / "a"), N, decode="host")
+    p2b.pat2beta(ctx, str(pg), str(tmp_path / "b"), N, decode="device")
+    a = (tmp_path / "a" / "x.beta").read_bytes(); b = (tmp_path / "b" / "x.beta").read_bytes()
+    assert len(a) == 2 * N and a == b and any(a)
+
+
 def test_device_views_equal_host_views(ctx, bamio, sample):
     g, full, path = sample
     rng = np.random.default_rng(5)
@@ -135,6 +190,9 @@ def test_corrupt_inputs_fail_loudly(ctx, bamio, sample, tmp_path):
         bamio.DeviceBam.from_bytes(ctx, bytes(bad))
     bad = bytearray(good); bad[bs0 + 18] |= 0x07                        # second block: BFINAL=1, BTYPE=3 (reserved)
     with pytest.raises(WgbsError, match="inflate failed in BGZF block 1 .invalid deflate block type"):
+        bamio.DeviceBam.from_bytes(ctx, bytes(bad))
+    bad = bytearray(good); bad[bs0 - 8] ^= 1                            # first block: CRC32 of the trailer
+    with pytest.raises(WgbsError, match="inflate failed in BGZF block 0 .CRC32 mismatch"):
         bamio.DeviceBam.from_bytes(ctx, bytes(bad))
     with pytest.raises(WgbsError, match="trailing bytes|corrupt BGZF"):
         bamio.DeviceBam.from_bytes(ctx, good[:-40])

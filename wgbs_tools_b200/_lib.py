@@ -81,6 +81,7 @@ def _load():
         "wgbs_bam_view": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.POINTER(vp), C.POINTER(sz), C.POINTER(u64)]),
         "wgbs_bam_view_ex": (C.c_int, [vp, C.POINTER(ViewOpts), C.POINTER(vp), C.POINTER(sz), C.POINTER(u64)]),
         "wgbs_host_free": (None, [vp]),
+        "wgbs_bgzf_inflate": (C.c_int, [vp, vp, sz, C.POINTER(vp), C.POINTER(sz)]),
         "wgbs_dbam_open": (C.c_int, [vp, vp, sz, C.POINTER(vp)]),
         "wgbs_dbam_open_file": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
         "wgbs_dbam_close": (None, [vp, vp]),

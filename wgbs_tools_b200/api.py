@@ -210,6 +210,14 @@ class Context:
         check(lib.wgbs_memcpy(self.h, b.ptr, a.ctypes.data, a.nbytes))
         return b
 
+    def bgzf_inflate(self, data) -> DevBuf:
+        """the bytes of a BGZF file (host) -> its inflated bytes in device memory (one warp per BGZF block; deflate, ISIZE and
+        CRC32 are verified)"""
+        a = np.frombuffer(data, np.uint8)
+        p = C.c_void_p(); n = C.c_size_t()
+        check(lib.wgbs_bgzf_inflate(self.h, a.ctypes.data, a.size, C.byref(p), C.byref(n)))
+        return DevBuf.adopt(self, p.value, n.value)
+
     # ---- pileup -------------------------------------------------------------------------------------------------
     def load_index(self, loci, first_idx: int = 1) -> "Index":
         return Index(self, loci, first_idx)

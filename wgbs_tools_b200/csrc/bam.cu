@@ -35,7 +35,7 @@ inline uint16_t rd16(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v;
 struct Block { uint64_t coff; uint32_t csize, usize; uint64_t uoff; };
 
 int inflate_block(const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t usize) {
-    if (usize == 0) return 0;
+    if (usize == 0) return rd32(src + csize - 8) == 0 ? 0 : -1;
     z_stream zs; memset(&zs, 0, sizeof zs);
     if (inflateInit2(&zs, -15) != Z_OK) return -1;
     const uint16_t xlen = rd16(src + 10);
@@ -43,7 +43,8 @@ int inflate_block(const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t usi
     zs.next_out = dst; zs.avail_out = usize;
     int rc = inflate(&zs, Z_FINISH);
     inflateEnd(&zs);
-    return (rc == Z_STREAM_END && zs.avail_out == 0) ? 0 : -1;
+    if (!(rc == Z_STREAM_END && zs.avail_out == 0)) return -1;
+    return (uint32_t)crc32(crc32(0L, Z_NULL, 0), dst, usize) == rd32(src + csize - 8) ? 0 : -1;   // gzip trailer: CRC32, ISIZE
 }
 
 // ---- formatting: raw pointer writes into a per-thread buffer that is grown per record, no per-char container calls ----
@@ -192,7 +193,7 @@ extern "C" int wgbs_bam_open(const char *path, int threads, wgbs_bam **out) {
         for (auto &t : th) t.join();
     }
     lap("inflate");
-    if (bad.load()) { delete B; return wgbs_set_err("%s: inflate failed (corrupt BGZF block)", path); }
+    if (bad.load()) { delete B; return wgbs_set_err("%s: inflate failed (corrupt BGZF block or CRC32 mismatch)", path); }
     // 3. header
     const uint8_t *d = B->data.data(); const uint64_t n = B->data.size();
     if (n < 12 || memcmp(d, "BAM\1", 4)) { delete B; return wgbs_set_err("%s: not a BAM file", path); }

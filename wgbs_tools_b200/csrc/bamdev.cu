@@ -38,17 +38,24 @@ constexpr uint64_t SEG = 16384;     // bytes of inflated stream per boundary-sea
 constexpr int GUESS_DEPTH = 4;      // consecutive plausible records required by a guess
 constexpr int INFL_WARPS = 4;       // warps (= BGZF blocks) per CTA of bgzf_inflate_k
 
-struct BgzfBlock { uint64_t coff /* first byte of the deflate payload */, uoff; uint32_t clen, usize; };
+struct BgzfBlock { uint64_t coff /* first byte of the deflate payload */, uoff; uint32_t clen, usize, crc, pad; };
 
 __global__ void __launch_bounds__(INFL_WARPS * 32) bgzf_inflate_k(const uint8_t *__restrict__ comp, const BgzfBlock *__restrict__ blocks, uint32_t nblocks,
                                                                     uint8_t *out, unsigned long long *__restrict__ err) {
     __shared__ dflate::Scratch S[INFL_WARPS];
+    __shared__ uint32_t crc_table[256];
+    for (uint32_t i = threadIdx.x; i < 256; i += INFL_WARPS * 32) crc_table[i] = dflate::crc_table_entry(i);
+    __syncthreads();
     const uint32_t w = threadIdx.x >> 5, b = blockIdx.x * INFL_WARPS + w;
-    if (b >= nblocks) return;                       // whole warps leave together
+    if (b >= nblocks) return;                       // whole warps leave together (no block-wide barrier below)
     const BgzfBlock B = blocks[b];
     dflate::Inflater<dflate::WarpLanes> I;
     I.S = &S[w]; I.dst = out + B.uoff; I.dst_len = B.usize;
-    const int rc = I.run(comp + B.coff, B.clen);
+    int rc = I.run(comp + B.coff, B.clen);
+    if (rc == dflate::OK) {
+        __syncwarp();
+        if (dflate::crc32_block(dflate::WarpLanes(), out + B.uoff, B.usize, crc_table) != B.crc) rc = dflate::E_CRC;
+    }
     if (rc != dflate::OK && (threadIdx.x & 31) == 0) atomicMin(err, ((unsigned long long)b << 8) | (unsigned long long)(uint8_t)(-rc));
 }
 
@@ -157,8 +164,46 @@ const char *inflate_msg(int code) {
         case dflate::E_DIST: return "distance too far back";
         case dflate::E_OUTPUT: return "more data than ISIZE";
         case dflate::E_SHORT: return "less data than ISIZE";
+        case dflate::E_CRC: return "CRC32 mismatch";
         default: return "inflate error";
     }
+}
+
+// Inflate a whole BGZF file (host bytes) into a fresh device buffer (padded by 16 zero bytes).  Synchronises the stream:
+// errors (framing, deflate, ISIZE, CRC32) are reported here.
+int bgzf_inflate_device(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, const char *who, uint8_t **d_out, uint64_t *n_out, uint64_t *n_blocks) {
+    const uint8_t *f = (const uint8_t *)bgzf;
+    std::vector<BgzfBlock> blocks; uint64_t off = 0, uoff = 0;
+    while (off + 28 <= nbytes) {                       // one hop per block over the headers
+        uint32_t xlen = 0; const uint32_t bs = dflate::bgzf_block_size(f + off, nbytes - off, &xlen);
+        if (!bs) return wgbs_set_err("%s: not a BGZF file (bad block header at %llu)", who, (unsigned long long)off);
+        if (off + bs > nbytes || bs < 12 + xlen + 8) return wgbs_set_err("%s: corrupt BGZF block at %llu", who, (unsigned long long)off);
+        BgzfBlock b; b.coff = off + 12 + xlen; b.clen = bs - 12 - xlen - 8; b.usize = ld32(f + off + bs - 4); b.crc = ld32(f + off + bs - 8); b.uoff = uoff; b.pad = 0;
+        if (b.usize > 65536) return wgbs_set_err("%s: corrupt BGZF block at %llu (ISIZE %u)", who, (unsigned long long)off, b.usize);
+        blocks.push_back(b); off += bs; uoff += b.usize;
+    }
+    if (off != nbytes) return wgbs_set_err("%s: %llu trailing bytes after the last BGZF block", who, (unsigned long long)(nbytes - off));
+    if (blocks.size() >= 0xffffffffull) return wgbs_set_err("%s: too many BGZF blocks", who);
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    if ((double)uoff * 1.25 + (double)nbytes > (double)free_b)
+        return wgbs_set_err("%s: the inflated stream (%.1f GB) does not fit in device memory (%.1f GB free); process the file in parts", who, uoff / 1e9, free_b / 1e9);
+    Temps T(ctx);
+    uint8_t *d_comp, *data = nullptr; BgzfBlock *d_blocks; unsigned long long *d_err;
+    RC_TRY(T.alloc(&d_comp, nbytes + 16)); RC_TRY(T.alloc(&d_blocks, blocks.size())); RC_TRY(T.alloc(&d_err, 1));
+    RC_TRY(dalloc(ctx, &data, uoff + 16));
+    int rc;
+    if ((rc = copy_any(ctx, d_comp, f, nbytes)) < 0 || (rc = copy_any(ctx, d_blocks, blocks.data(), blocks.size() * sizeof(BgzfBlock))) < 0) { dfree(ctx, data); return rc; }
+    unsigned long long herr = 0;
+    cudaError_t e = cudaMemsetAsync(d_err, 0xff, 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(data + uoff, 0, 16, ctx->stream);
+    if (e == cudaSuccess && !blocks.empty()) { LAUNCH(ctx, bgzf_inflate_k, grid_for(blocks.size(), INFL_WARPS), INFL_WARPS * 32, 0, d_comp, d_blocks, (uint32_t)blocks.size(), data, d_err); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&herr, d_err, 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { dfree(ctx, data); return wgbs_set_err("%s: %s", who, cudaGetErrorString(e)); }
+    if (herr != ~0ull) { dfree(ctx, data); return wgbs_set_err("%s: inflate failed in BGZF block %llu (%s)", who, herr >> 8, inflate_msg(-(int)(herr & 0xff))); }
+    *d_out = data; *n_out = uoff; if (n_blocks) *n_blocks = blocks.size();
+    return 0;
 }
 
 }  // namespace
@@ -169,44 +214,20 @@ extern "C" int wgbs_dbam_open(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, wg
     if (!bgzf || !out) return wgbs_set_err("wgbs_dbam_open: null argument");
     *out = nullptr;
     if (is_device_ptr(bgzf)) return wgbs_set_err("wgbs_dbam_open: the compressed bytes must be in host memory (the block table is read on the host)");
-    const uint8_t *f = (const uint8_t *)bgzf;
-    // 1. BGZF block table: one hop per block over the headers
-    std::vector<BgzfBlock> blocks; uint64_t off = 0, uoff = 0;
-    while (off + 28 <= nbytes) {
-        uint32_t xlen = 0; const uint32_t bs = dflate::bgzf_block_size(f + off, nbytes - off, &xlen);
-        if (!bs) return wgbs_set_err("wgbs_dbam_open: not a BGZF file (bad block header at %llu)", (unsigned long long)off);
-        if (off + bs > nbytes || bs < 12 + xlen + 8) return wgbs_set_err("wgbs_dbam_open: corrupt BGZF block at %llu", (unsigned long long)off);
-        BgzfBlock b; b.coff = off + 12 + xlen; b.clen = bs - 12 - xlen - 8; b.usize = ld32(f + off + bs - 4); b.uoff = uoff;
-        if (b.usize > 65536) return wgbs_set_err("wgbs_dbam_open: corrupt BGZF block at %llu (ISIZE %u)", (unsigned long long)off, b.usize);
-        blocks.push_back(b); off += bs; uoff += b.usize;
-    }
-    if (off != nbytes) return wgbs_set_err("wgbs_dbam_open: %llu trailing bytes after the last BGZF block", (unsigned long long)(nbytes - off));
-    if (blocks.size() >= 0xffffffffull) return wgbs_set_err("wgbs_dbam_open: too many BGZF blocks");
-    size_t free_b = 0, total_b = 0;
-    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-    if ((double)uoff * 1.25 + (double)nbytes > (double)free_b)
-        return wgbs_set_err("wgbs_dbam_open: the inflated stream (%.1f GB) does not fit in device memory (%.1f GB free); open the file in parts", uoff / 1e9, free_b / 1e9);
-
     wgbs_dbam *B = new wgbs_dbam();
-    B->n = uoff; B->comp_bytes = nbytes; B->n_blocks = blocks.size();
     Temps T(ctx);
-    uint8_t *d_comp; BgzfBlock *d_blocks; unsigned long long *d_err;
     int rc;
-    if ((rc = T.alloc(&d_comp, nbytes + 16)) < 0 || (rc = T.alloc(&d_blocks, blocks.size())) < 0 || (rc = T.alloc(&d_err, 4)) < 0 ||
-        (rc = dalloc(ctx, &B->data, uoff + 16)) < 0) return fail_free(ctx, B, rc);
-    if ((rc = copy_any(ctx, d_comp, f, nbytes)) < 0 || (rc = copy_any(ctx, d_blocks, blocks.data(), blocks.size() * sizeof(BgzfBlock))) < 0) return fail_free(ctx, B, rc);
-    CUDA_TRY(cudaMemsetAsync(d_err, 0xff, 4 * 8, ctx->stream));
-    CUDA_TRY(cudaMemsetAsync(B->data + uoff, 0, 16, ctx->stream));
-    // 2. inflate: one warp per block
-    if (!blocks.empty()) LAUNCH(ctx, bgzf_inflate_k, grid_for(blocks.size(), INFL_WARPS), INFL_WARPS * 32, 0, d_comp, d_blocks, (uint32_t)blocks.size(), B->data, d_err);
+    unsigned long long *d_err;
+    if ((rc = T.alloc(&d_err, 4)) < 0) return fail_free(ctx, B, rc);
+    // 1 + 2. BGZF block table (host) and inflate (one warp per block)
+    { uint64_t nb = 0; if ((rc = bgzf_inflate_device(ctx, bgzf, nbytes, "wgbs_dbam_open", &B->data, &B->n, &nb)) < 0) return fail_free(ctx, B, rc); B->n_blocks = nb; }
+    B->comp_bytes = nbytes;
+    const uint64_t uoff = B->n;
     unsigned long long herr[4];
-    CUDA_TRY(cudaMemcpyAsync(herr, d_err, sizeof herr, cudaMemcpyDeviceToHost, ctx->stream));
     // 3. header: "BAM\1" l_text text n_ref { l_name name l_ref }   (SAM spec 4.2)
     std::vector<uint8_t> head(std::min<uint64_t>(uoff, 1u << 16));
     if (!head.empty()) CUDA_TRY(cudaMemcpyAsync(head.data(), B->data, head.size(), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    LAUNCH_CHECK();
-    if (herr[0] != ~0ull) return fail_free(ctx, B, wgbs_set_err("wgbs_dbam_open: inflate failed in BGZF block %llu (%s)", herr[0] >> 8, inflate_msg(-(int)(herr[0] & 0xff))));
     auto need = [&](uint64_t upto) -> int {       // make head[0..upto) available
         if (upto > uoff) return wgbs_set_err("wgbs_dbam_open: truncated BAM header");
         if (upto <= head.size()) return 0;
@@ -282,6 +303,18 @@ extern "C" int wgbs_dbam_open(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, wg
     }
     LAUNCH_CHECK();
     *out = B;
+    return 0;
+}
+
+// General BGZF inflate on the device: bgzf = the bytes of a BGZF file (.bam, .pat.gz, CpG.bed.gz ...) in HOST memory;
+// *dev_out = DEVICE buffer with the inflated bytes (release with wgbs_dev_free).
+extern "C" int wgbs_bgzf_inflate(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, void **dev_out, size_t *out_bytes) {
+    RC_TRY(wgbs_ctx_activate(ctx));
+    if ((!bgzf && nbytes) || !dev_out || !out_bytes) return wgbs_set_err("wgbs_bgzf_inflate: null argument");
+    if (is_device_ptr(bgzf)) return wgbs_set_err("wgbs_bgzf_inflate: the compressed bytes must be in host memory (the block table is read on the host)");
+    uint8_t *d = nullptr; uint64_t n = 0;
+    RC_TRY(bgzf_inflate_device(ctx, bgzf, nbytes, "wgbs_bgzf_inflate", &d, &n, nullptr));
+    *dev_out = d; *out_bytes = (size_t)n;
     return 0;
 }
 

@@ -22,7 +22,8 @@ constexpr int DBITS = 8;    // distance codes
 
 enum : int { OK = 0, E_INPUT = -1 /* ran out of input */, E_BTYPE = -2, E_STORED = -3, E_CODES = -4 /* bad code lengths */,
              E_SYMBOL = -5 /* invalid code / symbol */, E_DIST = -6 /* distance before the start of the block */,
-             E_OUTPUT = -7 /* more output than ISIZE */, E_SHORT = -8 /* stream ended before ISIZE bytes */ };
+             E_OUTPUT = -7 /* more output than ISIZE */, E_SHORT = -8 /* stream ended before ISIZE bytes */,
+             E_CRC = -9 /* CRC32 of the inflated bytes differs from the block trailer */ };
 
 // per-warp working set (shared memory on the device): 3.7 KB
 struct Scratch {
@@ -315,6 +316,49 @@ struct Inflater {
         return rc;
     }
 };
+
+// ---- CRC-32 of a block's output (gzip trailer; htslib checks it in bgzf_read_block -> check_header/inflate_block) -----------
+// Reflected CRC-32 (polynomial 0xEDB88320).  Every lane runs the byte-wise table update over its own contiguous slice from a
+// zero register; the slices are then chained: register(A||B) = register(A) * x^(8|B|) mod P  xor  register_0(B).
+constexpr uint32_t CRC_POLY = 0xEDB88320u;
+WGBS_HD uint32_t crc_table_entry(uint32_t i) { uint32_t c = i; for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ CRC_POLY : c >> 1; return c; }
+// a(x) * b(x) mod P in the reflected representation (bit 31 = x^0)
+WGBS_HD uint32_t crc_mulmod(uint32_t a, uint32_t b) {
+    uint32_t p = 0;
+    for (uint32_t m = 1u << 31; m; m >>= 1) {
+        if (a & m) p ^= b;
+        b = (b & 1) ? (b >> 1) ^ CRC_POLY : b >> 1;
+    }
+    return p;
+}
+// x^(8n) mod P
+WGBS_HD uint32_t crc_x8n(uint32_t n) {
+    uint32_t r = 1u << 31, base = 1u << 30;       // x^0, x^1
+    for (uint64_t e = 8ull * n; e; e >>= 1) { if (e & 1) r = crc_mulmod(r, base); base = crc_mulmod(base, base); }
+    return r;
+}
+template <class L>
+WGBS_HD uint32_t crc32_block(L lanes, const uint8_t *d, uint32_t n, const uint32_t *table /* 256 entries */) {
+    const uint32_t per = (n + L::N - 1) / L::N;
+    const uint32_t l = (uint32_t)lanes.id();
+    const uint32_t a = l * per < n ? l * per : n, b = a + per < n ? a + per : n;
+    uint32_t c = 0;
+    for (uint32_t i = a; i < b; i++) c = table[(c ^ d[i]) & 0xff] ^ (c >> 8);
+    // operators for a full slice and for the (shorter) last one: computed by lanes 0 / 1, broadcast
+    const uint32_t nfull = per ? n / per : 0, rem = per ? n - nfull * per : 0;
+    uint32_t op = 0;
+    if (l == 0) op = crc_x8n(per);
+    if (L::N > 1 && l == 1) op = crc_x8n(rem);
+    const uint32_t x_full = lanes.shfl(op, 0), x_rem = L::N > 1 ? lanes.shfl(op, 1) : crc_x8n(rem);
+    uint32_t t = 0xffffffffu;
+    for (int i = 0; i < L::N; i++) {
+        const uint32_t ci = lanes.shfl(c, i);
+        const uint32_t len_i = (uint32_t)i < nfull ? per : ((uint32_t)i == nfull ? rem : 0);
+        if (len_i == 0) continue;
+        t = crc_mulmod(t, len_i == per ? x_full : x_rem) ^ ci;
+    }
+    return t ^ 0xffffffffu;
+}
 
 // ---- BGZF block framing (SAM spec 4.1) -----------------------------------------------------------------------------------
 // header: 1f 8b 08 04 | mtime(4) xfl os | xlen(2) | subfields ... 'B' 'C' 02 00 bsize-1(2) ... | deflate | crc32(4) isize(4)

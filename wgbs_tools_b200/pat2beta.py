@@ -6,7 +6,7 @@ import os
 import sys
 
 
-def pat2beta(ctx, pat_path: str, out_dir: str, nr_sites: int, lbeta: bool = False, force: bool = True):
+def pat2beta(ctx, pat_path: str, out_dir: str, nr_sites: int, lbeta: bool = False, force: bool = True, decode: str = "host"):
     from .patio import read_pat_text, splitextgz
     suff = ".lbeta" if lbeta else ".beta"
     out_beta = os.path.join(out_dir, splitextgz(os.path.basename(pat_path)) + suff)
@@ -15,6 +15,17 @@ def pat2beta(ctx, pat_path: str, out_dir: str, nr_sites: int, lbeta: bool = Fals
         return None
     from . import dist as wd
     rank, world = wd.world()
+    dtext = None
+    if world == 1 and decode == "device":
+        from .patio import read_pat_device
+        dtext = read_pat_device(ctx, pat_path)                     # BGZF inflated in HBM; None: not a BGZF file
+    if dtext is not None:
+        P = ctx.pats_from_text(dtext)
+        mc = ctx.pat2beta(P, 1, nr_sites + 1)
+        beta = ctx.trim(mc, nr_sites, 16 if lbeta else 8)
+        P.free(); mc.free(); dtext.free()
+        beta.tofile(out_beta)
+        return out_beta
     text = wd.shard_lines(read_pat_text(pat_path), rank, world)
     if world == 1:
         beta = ctx.pat2beta_text(text, 1, nr_sites + 1, 16 if lbeta else 8)   # `stdin2beta 1 N+1` + trim_to_uint8 (pat2beta.py:32-37)
@@ -35,13 +46,15 @@ def main(argv=None):
     p.add_argument("pat_paths", nargs="+"); p.add_argument("-f", "--force", action="store_true")
     p.add_argument("-o", "--out_dir", default="."); p.add_argument("-l", "--lbeta", action="store_true")
     p.add_argument("--genome"); p.add_argument("-@", "--threads", type=int, default=1)
+    p.add_argument("--pat_decode", choices=["host", "device"], default=os.environ.get("WGBS_PAT_DECODE", "host"),
+                   help="where X.pat.gz is inflated: host (gzip), or on the GPU (compressed bytes over PCIe, one warp per BGZF block) [host]")
     a = p.parse_args(argv)
     ref = GenomeRef(a.genome)
     from . import dist as wd
     _, _, local = wd.init_from_env()
     with Context(local) as ctx:
         for pat in a.pat_paths:
-            pat2beta(ctx, pat, a.out_dir, ref.nr_sites, a.lbeta, a.force)
+            pat2beta(ctx, pat, a.out_dir, ref.nr_sites, a.lbeta, a.force, a.pat_decode)
 
 
 if __name__ == "__main__":

@@ -44,6 +44,23 @@ def read_pat_text(path: str) -> bytes:
     raise ValueError(f"Invalid pat suffix: {path}")
 
 
+def is_bgzf(head: bytes) -> bool:
+    """gzip member with the 'BC' extra subfield first (what bgzip writes; SAM spec 4.1)"""
+    return len(head) >= 18 and head[:4] == b"\x1f\x8b\x08\x04" and head[12:14] == b"BC"
+
+
+def read_pat_device(ctx, path: str):
+    """the pat text of a bgzip-compressed X.pat.gz as a device buffer (DevBuf): only the compressed bytes cross PCIe, the BGZF
+    blocks are inflated in HBM (csrc/bamdev.cu).  Returns None when the file is not BGZF (plain gzip / uncompressed)."""
+    if not path.endswith(".pat.gz"):
+        return None
+    with open(path, "rb") as f:
+        raw = f.read()
+    if not is_bgzf(raw[:18]):
+        return None
+    return ctx.bgzf_inflate(raw)
+
+
 def splitextgz(name: str) -> str:
     for suf in (".pat.gz", ".pat"):
         if name.endswith(suf):
