@@ -349,6 +349,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=1_000_000)
     ap.add_argument("--no-extras", dest="no_extras", action="store_true", help="skip the pat2beta / homog / segment side measurements")
+    ap.add_argument("--only-bam-extra", dest="only_bam", action="store_true", help="of the side measurements run only the device-BAM leg")
     ap.add_argument("--bam-leg", dest="bam_leg", help=argparse.SUPPRESS)       # internal: child process of the device-BAM leg
     ap.add_argument("--sam-bytes", dest="sam_bytes", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--peak", type=float, default=6650.0, help=argparse.SUPPRESS)
@@ -589,7 +590,7 @@ def main():
     extra = None
     if rank == 0 and args.gpus == 1 and not args.no_extras:
         try:
-            extra = extras(ctx, torch, roof["peak"] if roof else 6650.0, sam)
+            extra = {} if args.only_bam else extras(ctx, torch, roof["peak"] if roof else 6650.0, sam)
         except Exception as e:
             log(f"[bench] extras failed: {e!r}")
             extra = {"error": repr(e)}
