@@ -12,6 +12,7 @@
 //   bamdev_core_check fmtg N SEED                      fmt_g vs snprintf("%g") on N random floats + edge cases
 #include <zlib.h>
 
+#include <algorithm>
 #include <barrier>
 #include <cmath>
 #include <cstdio>
@@ -131,12 +132,19 @@ static int cmd_view(const char *path, uint64_t SEG, int depth, int argc, char **
     std::vector<uint64_t> entry(nseg + 1), exit_(nseg), bad(nseg, ~0ull); std::vector<uint32_t> cnt(nseg);
     OneLane one;
     size_t wrong_guesses = 0, rounds = 0;
-    for (uint64_t s = 0; s < nseg; s++) entry[s] = s == 0 ? p0 : guess_entry(one, d.data(), n, p0 + s * SEG, n_ref, depth);
+    // depth < 0: real guesses (depth 4), but every (-depth)-th one is replaced by a wrong one (a few bytes into a record or,
+    // every other time, far ahead): isolated wrong guesses must be repaired in one round without disturbing their neighbours
+    for (uint64_t s = 0; s < nseg; s++) {
+        entry[s] = s == 0 ? p0 : guess_entry(one, d.data(), n, p0 + s * SEG, n_ref, depth < 0 ? 4 : depth);
+        if (depth < 0 && s && s % (uint64_t)(-depth) == 0) entry[s] = (s / (uint64_t)(-depth)) & 1 ? std::min<uint64_t>(n, entry[s] + 7) : std::min<uint64_t>(n, entry[s] + 5 * SEG + 3);
+    }
     std::vector<char> dirty(nseg, 1);
     for (bool changed = true; changed;) {
         changed = false; rounds++;
         for (uint64_t s = 0; s < nseg; s++) if (dirty[s]) { bad[s] = ~0ull; exit_[s] = walk_chain(d.data(), n, entry[s], p0 + (s + 1) * SEG, &cnt[s], nullptr, &bad[s]); dirty[s] = 0; }
-        for (uint64_t s = 0; s + 1 < nseg; s++) if (bad[s] == ~0ull && entry[s + 1] != exit_[s]) { entry[s + 1] = exit_[s]; dirty[s + 1] = 1; changed = true; wrong_guesses++; }
+        std::vector<uint64_t> next(entry);                                   // the kernel reads the old entries and writes new ones
+        for (uint64_t s = 0; s + 1 < nseg; s++) { bool ch = false; next[s + 1] = repaired_entry(entry.data(), exit_.data(), bad.data(), s, &ch); if (ch) { dirty[s + 1] = 1; changed = true; wrong_guesses++; } }
+        entry.swap(next);
     }
     for (uint64_t s = 0; s < nseg; s++) if (bad[s] != ~0ull) { fprintf(stderr, "corrupt BAM record at %llu\n", (unsigned long long)bad[s]); return 3; }
     std::vector<uint64_t> rec;

@@ -109,10 +109,11 @@ EXTRA = (b"x1\t0\tchrT\t500\t7\t10M2I5M3D20M4S\t*\t0\t0\t" + b"ACGTN" * 8 + b"A\
 UNMAPPED = b"x2\t4\t*\t0\t0\t*\t*\t0\t0\t*\t*\n"
 
 
-@pytest.mark.parametrize("seg,depth", [(64, 4), (1000, 4), (16384, 4), (1 << 20, 4), (50, 0)])
+@pytest.mark.parametrize("seg,depth", [(64, 4), (1000, 4), (16384, 4), (1 << 20, 4), (50, 0), (1000, -3), (16384, -4)])
 def test_record_boundaries_and_sam_text_round_trip(check, sam, tmp_path, built_lib, seg, depth):
     """SAM -> BAM (records spanning BGZF blocks) -> inflate core -> segment guess / walk / repair -> format core == SAM.
-    depth 0 makes every guess wrong (entry = segment base): the repair loop alone must still find every record."""
+    depth 0 makes every guess wrong (entry = segment base): the repair loop alone must still find every record.
+    depth < 0 injects isolated wrong guesses into otherwise good ones."""
     from wgbs_tools_b200 import bamio
     g, s = sam
     if depth == 0:
@@ -125,8 +126,10 @@ def test_record_boundaries_and_sam_text_round_trip(check, sam, tmp_path, built_l
     assert r.stdout == full
     stats = dict(zip(r.stderr.decode().split()[::2], r.stderr.decode().split()[1::2]))
     assert int(stats["records"]) == full.count(b"\n")
-    if depth:
+    if depth > 0:
         assert int(stats["wrong_guesses"]) == 0 and int(stats["rounds"]) == 1
+    elif depth < 0:                                       # every |depth|-th guess deliberately wrong (near and far): one repair round,
+        assert int(stats["wrong_guesses"]) > 0 and int(stats["rounds"]) == 2      # the wrong ones cannot spread to their neighbours
     else:
         assert int(stats["wrong_guesses"]) > 0
 

@@ -57,7 +57,7 @@ WGBS_HD bool plausible_at(const uint8_t *data, uint64_t n, uint64_t o, int32_t n
     const int32_t refid = ldi32(p + 4), pos = ldi32(p + 8), nref = ldi32(p + 24), npos = ldi32(p + 28), l_seq = ldi32(p + 20);
     if (refid < -1 || refid >= n_ref || nref < -1 || nref >= n_ref || pos < -1 || npos < -1 || l_seq < 0) return false;
     const uint32_t l_name = p[12], n_cig = ld16(p + 16);
-    if (l_name < 1) return false;
+    if (l_name < 2) return false;                   // at least one character + NUL (SAM spec 1.4: [!-?A-~]{1,254})
     if (32ull + l_name + 4ull * n_cig + (uint64_t)((l_seq + 1) / 2) + (uint64_t)l_seq > bs) return false;
     if (p[36 + l_name - 1] != 0) return false;
     for (uint32_t k = 0; k + 1 < l_name; k++) { const uint8_t c = p[36 + k]; if (c < 33 || c > 126) return false; }
@@ -99,6 +99,16 @@ WGBS_HD uint64_t walk_chain(const uint8_t *data, uint64_t n, uint64_t from, uint
     }
     *count = c;
     return o;
+}
+
+// Repair step of the boundary search.  Invariant wanted: entry[s+1] == exit[s] for every s (entry[0] is exact).  Segment s
+// may overrule the entry of its successor only if its own entry agrees with ITS predecessor's exit ("supported"): a wrong
+// guess is inconsistent with the segment before it, so whatever it walked into cannot spread; isolated wrong guesses are
+// repaired in one round, a run of k wrong guesses in k rounds.  Returns the new entry of segment s+1.
+WGBS_HD uint64_t repaired_entry(const uint64_t *entry, const uint64_t *exit_, const uint64_t *bad, uint64_t s, bool *changed) {
+    const uint64_t cur = entry[s + 1];
+    if (bad[s] == ~0ull && cur != exit_[s] && (s == 0 || entry[s] == exit_[s - 1])) { *changed = true; return exit_[s]; }
+    return cur;
 }
 
 // ---- filters (`samtools view` options of bam2pat.py:126-159; same semantics as wgbs_bam_view_ex in bam.cu) --------------

@@ -37,6 +37,7 @@ namespace {
 constexpr uint64_t SEG = 16384;     // bytes of inflated stream per boundary-search segment
 constexpr int GUESS_DEPTH = 4;      // consecutive plausible records required by a guess
 constexpr int INFL_WARPS = 4;       // warps (= BGZF blocks) per CTA of bgzf_inflate_k
+constexpr int FMT_G = 8;            // lanes per record in bam_format_k
 
 struct BgzfBlock { uint64_t coff /* first byte of the deflate payload */, uoff; uint32_t clen, usize, crc, pad; };
 
@@ -78,12 +79,16 @@ __global__ void __launch_bounds__(128) bam_walk_k(const uint8_t *__restrict__ da
     cnt[s] = c; bad[s] = b; dirty[s] = 0;
 }
 
-// thread s repairs the entry of segment s+1 (nobody else writes it)
-__global__ void __launch_bounds__(256) bam_check_k(uint64_t nseg, uint64_t *__restrict__ entry, const uint64_t *__restrict__ exit_,
-                                                    const uint64_t *__restrict__ bad, uint8_t *__restrict__ dirty, uint32_t *__restrict__ changed) {
+// thread s decides the entry of segment s+1 from the OLD entries (bam_core.cuh repaired_entry) and writes it to the new array
+__global__ void __launch_bounds__(256) bam_check_k(uint64_t nseg, const uint64_t *__restrict__ entry, uint64_t *__restrict__ entry_new,
+                                                    const uint64_t *__restrict__ exit_, const uint64_t *__restrict__ bad, uint8_t *__restrict__ dirty,
+                                                    uint32_t *__restrict__ changed) {
     const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s == 0) entry_new[0] = entry[0];
     if (s + 1 >= nseg) return;
-    if (bad[s] == ~0ull && entry[s + 1] != exit_[s]) { entry[s + 1] = exit_[s]; dirty[s + 1] = 1; atomicAdd(changed, 1u); }
+    bool ch = false;
+    entry_new[s + 1] = repaired_entry(entry, exit_, bad, s, &ch);
+    if (ch) { dirty[s + 1] = 1; atomicAdd(changed, 1u); }
 }
 
 // first corrupt record in stream order (segments are in stream order; a bad segment stops the chain)
@@ -141,11 +146,13 @@ __global__ void __launch_bounds__(256) bam_head_k(uint64_t nr, const uint32_t *_
 
 __global__ void __launch_bounds__(256) bam_format_k(const uint8_t *__restrict__ data, const uint64_t *__restrict__ rec_off, uint64_t nr, DevRefs F,
                                                      const uint32_t *__restrict__ len, const uint64_t *__restrict__ off, char *__restrict__ text) {
-    const uint64_t i = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    // FMT_G lanes per record: the scalar fields are written by the group's first lane, SEQ and QUAL by all of them; four
+    // records per warp share one instruction stream (a whole warp per record spent 32 lanes on scalar work: 1.96 ms / 1M records)
+    const uint64_t i = ((uint64_t)blockIdx.x * 256 + threadIdx.x) / FMT_G;
     if (i >= nr || len[i] == 0) return;
     Rec R; R.load(data + rec_off[i]);
     const Refs RF{F.n, F.name_off, F.names, F.lens};
-    WriteSink<dflate::WarpLanes> ws; ws.o = text + off[i];
+    WriteSink<dflate::LaneGroup<FMT_G>> ws; ws.o = text + off[i];
     format_record(R, RF, ws);
 }
 
@@ -258,15 +265,16 @@ extern "C" int wgbs_dbam_open(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, wg
     const uint64_t p0 = p, n = uoff, nseg = n > p0 ? (n - p0 + SEG - 1) / SEG : 0;
     B->ref_first.assign(n_ref + 1, 0); B->ref_last.assign(n_ref + 1, 0);
     if (nseg) {
-        uint64_t *entry, *exit_, *bad, *base; uint32_t *cnt, *changed; uint8_t *dirty; unsigned long long *d_first, *d_last; uint32_t *d_runs;
-        if ((rc = T.alloc(&entry, nseg)) < 0 || (rc = T.alloc(&exit_, nseg)) < 0 || (rc = T.alloc(&bad, nseg)) < 0 || (rc = T.alloc(&base, nseg + 1)) < 0 ||
+        uint64_t *entry, *entry2, *exit_, *bad, *base; uint32_t *cnt, *changed; uint8_t *dirty; unsigned long long *d_first, *d_last; uint32_t *d_runs;
+        if ((rc = T.alloc(&entry, nseg)) < 0 || (rc = T.alloc(&entry2, nseg)) < 0 || (rc = T.alloc(&exit_, nseg)) < 0 || (rc = T.alloc(&bad, nseg)) < 0 || (rc = T.alloc(&base, nseg + 1)) < 0 ||
             (rc = T.alloc(&cnt, nseg)) < 0 || (rc = T.alloc(&changed, 1)) < 0 || (rc = T.alloc(&dirty, nseg)) < 0) return fail_free(ctx, B, rc);
         CUDA_TRY(cudaMemsetAsync(dirty, 1, nseg, ctx->stream));
         LAUNCH(ctx, bam_guess_k, grid_for(nseg, 4), 128, 0, B->data, n, p0, nseg, (int32_t)n_ref, entry);
         for (uint64_t round = 0;; round++) {
             CUDA_TRY(cudaMemsetAsync(changed, 0, 4, ctx->stream));
             LAUNCH(ctx, bam_walk_k, grid_for(nseg, 128), 128, 0, B->data, n, p0, nseg, entry, dirty, exit_, cnt, bad);
-            LAUNCH(ctx, bam_check_k, grid_for(nseg, 256), 256, 0, nseg, entry, exit_, bad, dirty, changed);
+            LAUNCH(ctx, bam_check_k, grid_for(nseg, 256), 256, 0, nseg, entry, entry2, exit_, bad, dirty, changed);
+            std::swap(entry, entry2);
             uint32_t h = 0;
             CUDA_TRY(cudaMemcpyAsync(&h, changed, 4, cudaMemcpyDeviceToHost, ctx->stream));
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -401,7 +409,7 @@ extern "C" int wgbs_dbam_view(wgbs_ctx *ctx, const wgbs_dbam *B, const wgbs_view
     }
     char *text = nullptr;
     RC_TRY(dalloc(ctx, &text, (size_t)tot + 16));
-    if (tot) LAUNCH(ctx, bam_format_k, grid_for(nr, 8), 256, 0, B->data, B->rec_off + r0, nr, F, len, off, text);
+    if (tot) LAUNCH(ctx, bam_format_k, grid_for(nr, 256 / FMT_G), 256, 0, B->data, B->rec_off + r0, nr, F, len, off, text);
     LAUNCH_CHECK();
     *dev_text = text; *nbytes = (size_t)tot; if (nrecords) *nrecords = npass;
     return 0;

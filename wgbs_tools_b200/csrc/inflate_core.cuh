@@ -60,6 +60,12 @@ struct WarpLanes {
         return x - v;
     }
 };
+// G consecutive lanes working on one item (no collectives: only id() / N are meaningful)
+template <int G>
+struct LaneGroup {
+    static constexpr int N = G;
+    __device__ __forceinline__ int id() const { return (int)(threadIdx.x & (G - 1)); }
+};
 #endif
 
 // ---- canonical Huffman tables ----------------------------------------------------------------------------------------
