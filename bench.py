@@ -605,10 +605,11 @@ def main():
                 open(os.path.join(tmp, "ref.beta"), "wb").write(h_beta.numpy().tobytes())
                 open(os.path.join(tmp, "batch.bam"), "wb").write(bam_bytes)
                 np.save(os.path.join(tmp, "loci.npy"), g.loci)
-                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--bam-leg", tmp, "--reads", str(n_rec), "--sam-bytes", str(text_bytes),
-                                    "--peak", str(roof["peak"] if roof else 6650.0)], stdout=subprocess.PIPE, timeout=300)
-                line = [l for l in r.stdout.decode(errors="replace").splitlines() if l.startswith("{")]
-                extra["bam_device"] = json.loads(line[-1]) if line else {"error": f"child exited {r.returncode} without a result"}
+                for key, env_add in [("bam_device", {})] + ([(f"bam_device_inflate{v}", {"WGBS_INFLATE": v}) for v in os.environ.get("WGBS_BENCH_INFLATE_VARIANTS", "").split(",") if v]):
+                    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--bam-leg", tmp, "--reads", str(n_rec), "--sam-bytes", str(text_bytes),
+                                        "--peak", str(roof["peak"] if roof else 6650.0)], stdout=subprocess.PIPE, timeout=300, env={**os.environ, **env_add})
+                    line = [l for l in r.stdout.decode(errors="replace").splitlines() if l.startswith("{")]
+                    extra[key] = json.loads(line[-1]) if line else {"error": f"child exited {r.returncode} without a result"}
             except Exception as e:
                 log(f"[bench] bam_device leg failed: {e!r}")
                 extra["bam_device"] = {"error": repr(e)}

@@ -85,6 +85,12 @@ static int one_lane(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usize
     if (rc == OK && check_crc && crc32_block(OneLane(), dst, usize, g_crc_table) != want_crc) rc = E_CRC;
     return rc;
 }
+static int one_lane2(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usize, uint32_t want_crc) {
+    Scratch S; Ring R; Inflater2<OneLane> I; I.S = &S; I.R = &R; I.dst = dst; I.dst_len = usize;
+    int rc = I.run(src, n);
+    if (rc == OK && crc32_block(OneLane(), dst, usize, g_crc_table) != want_crc) rc = E_CRC;
+    return rc;
+}
 static int emu_warp(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usize, uint32_t want_crc) {
     static EmuShared sh; Scratch S; int rcs[32];
     std::vector<std::thread> th;
@@ -94,6 +100,17 @@ static int emu_warp(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usize
     });
     for (auto &t : th) t.join();
     for (int l = 1; l < 32; l++) if (rcs[l] != rcs[0]) { fprintf(stderr, "lanes disagree on rc\n"); exit(4); }
+    return rcs[0];
+}
+static int emu_warp2(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usize, uint32_t want_crc) {
+    static EmuShared sh; Scratch S; Ring R; int rcs[32];
+    std::vector<std::thread> th;
+    for (int l = 0; l < 32; l++) th.emplace_back([&, l]() {
+        Inflater2<EmuLanes> I; I.lanes = EmuLanes{l, &sh}; I.S = &S; I.R = &R; I.dst = dst; I.dst_len = usize; rcs[l] = I.run(src, n);
+        if (rcs[l] == OK) { I.lanes.sync(); if (crc32_block(I.lanes, dst, usize, g_crc_table) != want_crc) rcs[l] = E_CRC; }
+    });
+    for (auto &t : th) t.join();
+    for (int l = 1; l < 32; l++) if (rcs[l] != rcs[0]) { fprintf(stderr, "lanes disagree on rc (v2)\n"); exit(4); }
     return rcs[0];
 }
 
@@ -109,7 +126,11 @@ static int cmd_inflate(const char *path, int emu_blocks) {
         if (rz == 0 && (uint32_t)crc32(crc32(0L, Z_NULL, 0), a.data(), b.usize) != want) rz = -1;       // what htslib's bgzf reader checks
         const int r1 = one_lane(src, n, c.data(), b.usize, want, true);
         bool ok = (rz == 0) == (r1 == 0) && (rz != 0 || !memcmp(a.data(), c.data(), b.usize));
-        if ((int)i < emu_blocks) { const int r2 = emu_warp(src, n, e.data(), b.usize, want); ok = ok && r2 == r1 && (r1 != 0 || !memcmp(a.data(), e.data(), b.usize)); nemu++; }
+        { std::vector<uint8_t> c2(b.usize + 1); const int r3 = one_lane2(src, n, c2.data(), b.usize, want); ok = ok && (rz == 0) == (r3 == 0) && (rz != 0 || !memcmp(a.data(), c2.data(), b.usize)); }
+        if ((int)i < emu_blocks) {
+            const int r2 = emu_warp(src, n, e.data(), b.usize, want); ok = ok && r2 == r1 && (r1 != 0 || !memcmp(a.data(), e.data(), b.usize)); nemu++;
+            std::vector<uint8_t> e2(b.usize + 1); const int r4 = emu_warp2(src, n, e2.data(), b.usize, want); ok = ok && (rz == 0) == (r4 == 0) && (rz != 0 || !memcmp(a.data(), e2.data(), b.usize));
+        }
         if (!ok) { nbad++; fprintf(stderr, "block %zu: zlib %d core %d\n", i, rz, r1); }
         bytes += b.usize;
     }

@@ -38,21 +38,34 @@ constexpr uint64_t SEG = 16384;     // bytes of inflated stream per boundary-sea
 constexpr int GUESS_DEPTH = 4;      // consecutive plausible records required by a guess
 constexpr int INFL_WARPS = 4;       // warps (= BGZF blocks) per CTA of bgzf_inflate_k
 constexpr int FMT_G = 8;            // lanes per record in bam_format_k
+#ifndef WGBS_INFLATE_DEFAULT
+#define WGBS_INFLATE_DEFAULT 1      // WGBS_INFLATE=1|2 selects the decoder at run time
+#endif
 
 struct BgzfBlock { uint64_t coff /* first byte of the deflate payload */, uoff; uint32_t clen, usize, crc, pad; };
 
-__global__ void __launch_bounds__(INFL_WARPS * 32) bgzf_inflate_k(const uint8_t *__restrict__ comp, const BgzfBlock *__restrict__ blocks, uint32_t nblocks,
+// V = 1: one decoding lane per warp (Inflater); V = 2: uniform execution, input staged in a shared-memory ring (Inflater2)
+template <int V>
+__global__ void __launch_bounds__(INFL_WARPS * 32, V == 2 ? 8 : 6) bgzf_inflate_k(const uint8_t *__restrict__ comp, const BgzfBlock *__restrict__ blocks, uint32_t nblocks,
                                                                     uint8_t *out, unsigned long long *__restrict__ err) {
     __shared__ dflate::Scratch S[INFL_WARPS];
+    __shared__ dflate::Ring RG[V == 2 ? INFL_WARPS : 1];
     __shared__ uint32_t crc_table[256];
     for (uint32_t i = threadIdx.x; i < 256; i += INFL_WARPS * 32) crc_table[i] = dflate::crc_table_entry(i);
     __syncthreads();
     const uint32_t w = threadIdx.x >> 5, b = blockIdx.x * INFL_WARPS + w;
     if (b >= nblocks) return;                       // whole warps leave together (no block-wide barrier below)
     const BgzfBlock B = blocks[b];
-    dflate::Inflater<dflate::WarpLanes> I;
-    I.S = &S[w]; I.dst = out + B.uoff; I.dst_len = B.usize;
-    int rc = I.run(comp + B.coff, B.clen);
+    int rc;
+    if (V == 2) {
+        dflate::Inflater2<dflate::WarpLanes> I;
+        I.S = &S[w]; I.R = &RG[V == 2 ? w : 0]; I.dst = out + B.uoff; I.dst_len = B.usize;
+        rc = I.run(comp + B.coff, B.clen);
+    } else {
+        dflate::Inflater<dflate::WarpLanes> I;
+        I.S = &S[w]; I.dst = out + B.uoff; I.dst_len = B.usize;
+        rc = I.run(comp + B.coff, B.clen);
+    }
     if (rc == dflate::OK) {
         __syncwarp();
         if (dflate::crc32_block(dflate::WarpLanes(), out + B.uoff, B.usize, crc_table) != B.crc) rc = dflate::E_CRC;
@@ -204,7 +217,12 @@ int bgzf_inflate_device(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, const ch
     unsigned long long herr = 0;
     cudaError_t e = cudaMemsetAsync(d_err, 0xff, 8, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(data + uoff, 0, 16, ctx->stream);
-    if (e == cudaSuccess && !blocks.empty()) { LAUNCH(ctx, bgzf_inflate_k, grid_for(blocks.size(), INFL_WARPS), INFL_WARPS * 32, 0, d_comp, d_blocks, (uint32_t)blocks.size(), data, d_err); e = cudaGetLastError(); }
+    static const int variant = [] { const char *v = getenv("WGBS_INFLATE"); return (v && v[0] == '1') ? 1 : (v && v[0] == '2') ? 2 : WGBS_INFLATE_DEFAULT; }();
+    if (e == cudaSuccess && !blocks.empty()) {
+        if (variant == 2) LAUNCH(ctx, bgzf_inflate_k<2>, grid_for(blocks.size(), INFL_WARPS), INFL_WARPS * 32, 0, d_comp, d_blocks, (uint32_t)blocks.size(), data, d_err);
+        else LAUNCH(ctx, bgzf_inflate_k<1>, grid_for(blocks.size(), INFL_WARPS), INFL_WARPS * 32, 0, d_comp, d_blocks, (uint32_t)blocks.size(), data, d_err);
+        e = cudaGetLastError();
+    }
     if (e == cudaSuccess) e = cudaMemcpyAsync(&herr, d_err, 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { dfree(ctx, data); return wgbs_set_err("%s: %s", who, cudaGetErrorString(e)); }

@@ -323,6 +323,239 @@ struct Inflater {
     }
 };
 
+// ---- second decoder: every lane runs the SAME instruction stream ------------------------------------------------------------
+// The first decoder spends one lane on the Huffman walk inside a divergent region (convergence barriers, a 64-bit bit
+// buffer refilled from global memory, a shared-memory symbol queue): ~46 warp-instructions per symbol, and the kernel is
+// issue-bound (measured: 10.3 ms for the 3 000 blocks of a 1M-read batch).  Here
+//   * the compressed bytes are staged in a shared-memory ring by coalesced loads (a word index, no refill branches),
+//   * a symbol costs two ring words + one funnel shift + one table probe, executed identically by all lanes (loads are
+//     broadcasts, control flow is uniform: no convergence barriers),
+//   * symbol i of a batch stays in lane i's register -- no queue in shared memory;
+// the emit step (literals in parallel, matches in stream order) is the same.
+constexpr uint32_t RING_WORDS = 512;            // 2 KiB of compressed stream per warp
+constexpr uint32_t RING_KEEP = 480;             // words loaded ahead of the read position by a refill
+struct Ring { uint32_t w[RING_WORDS + 1]; };    // slot RING_WORDS mirrors slot 0: the word after any slot is at +1, no wrap
+
+WGBS_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> (sh & 31));
+#endif
+}
+
+template <class L>
+struct Inflater2 {
+    L lanes;
+    Scratch *S;
+    Ring *R;
+    uint8_t *dst; uint32_t dst_len;
+    // compressed stream: 32-bit words at gw[0 .. nwords), first payload bit = bit0, one past the last payload bit = end_bit
+    const uint32_t *gw; uint32_t nwords, end_bit;
+    uint32_t hi_w;                                  // ring holds words [.., hi_w)
+    uint32_t bitpos;
+
+    // make the ring hold at least `ahead` words from the current position on (uniform; ends with a warp barrier)
+    WGBS_HD void refill(uint32_t ahead) {
+        const uint32_t cur = bitpos >> 5;
+        if (hi_w >= cur + ahead) return;
+        if (hi_w < cur) hi_w = cur;                  // jumped over everything staged (stored block)
+        const uint32_t target = cur + RING_KEEP;
+        lanes.sync();                                // nobody still reads the slots about to be overwritten
+        for (uint32_t w = hi_w + (uint32_t)lanes.id(); w < target; w += L::N) {
+            const uint32_t x = w < nwords ? gw[w] : 0u, slot = w & (RING_WORDS - 1);
+            R->w[slot] = x;
+            if (slot == 0) R->w[RING_WORDS] = x;
+        }
+        hi_w = target;
+        lanes.sync();
+    }
+    WGBS_HD uint32_t peek() const {                  // the next 32 bits of the stream
+        const uint32_t *p = R->w + ((bitpos >> 5) & (RING_WORDS - 1));
+        return funnel_r(p[0], p[1], bitpos & 31);
+    }
+
+    WGBS_HD int fixed_tables() {
+        uint8_t *l = S->lens;
+        for (int i = 0; i < 144; i++) l[i] = 8;
+        for (int i = 144; i < 256; i++) l[i] = 9;
+        for (int i = 256; i < 280; i++) l[i] = 7;
+        for (int i = 280; i < 288; i++) l[i] = 8;
+        int rc = build_table(l, 288, S->lcnt, S->lsym, S->lt, LBITS, true);
+        if (rc) return rc;
+        for (int i = 0; i < 16; i++) S->dcnt[i] = 0;
+        S->dcnt[5] = 30;
+        for (int i = 0; i < (1 << DBITS); i++) S->dt[i] = 0;
+        for (int s = 0; s < 30; s++) {
+            S->dsym[s] = (uint16_t)s;
+            for (uint32_t k = bitrev((uint32_t)s, 5); k < (1u << DBITS); k += 32) S->dt[k] = (uint16_t)(s | (5 << 9));
+        }
+        return OK;
+    }
+
+    // one lane: code lengths of a dynamic block (the ring holds >= 300 words ahead: the longest header is < 600 bytes)
+    WGBS_HD int dynamic_tables(uint32_t *bp) {
+        uint32_t b = *bp;
+        auto window = [&](uint32_t at) { const uint32_t *p = R->w + ((at >> 5) & (RING_WORDS - 1)); return funnel_r(p[0], p[1], at & 31); };
+        uint32_t v = window(b); b += 14;
+        const int nlen = (int)(v & 31) + 257, ndist = (int)((v >> 5) & 31) + 1, ncode = (int)((v >> 10) & 15) + 4;
+        if (nlen > 286 || ndist > 30) return E_CODES;
+        const char *order = "\x10\x11\x12\x00\x08\x07\x09\x06\x0a\x05\x0b\x04\x0c\x03\x0d\x02\x0e\x01\x0f";
+        uint8_t *l = S->lens;
+        for (int i = 0; i < 19; i++) l[i] = 0;
+        for (int i = 0; i < ncode; i++) { l[(int)order[i]] = (uint8_t)(window(b) & 7); b += 3; }
+        int rc = build_table(l, 19, S->dcnt, S->dsym, S->dt, 7, false);
+        if (rc) return rc;
+        uint16_t clt[128], ccnt[16], csym[19];
+        for (int i = 0; i < 128; i++) clt[i] = S->dt[i];
+        for (int i = 0; i < 16; i++) ccnt[i] = S->dcnt[i];
+        for (int i = 0; i < 19; i++) csym[i] = S->dsym[i];
+        int idx = 0;
+        while (idx < nlen + ndist) {
+            if (b > end_bit) return E_INPUT;
+            v = window(b);
+            const uint16_t e = clt[v & 127];
+            int s, nb = e >> 9;
+            if (nb) s = e & 511; else { s = slow_decode(v, ccnt, csym, &nb); if (s < 0) return E_SYMBOL; }
+            b += (uint32_t)nb; v >>= nb;
+            if (s < 16) { l[idx++] = (uint8_t)s; continue; }
+            int rep; uint8_t val = 0;
+            if (s == 16) { if (idx == 0) return E_CODES; val = l[idx - 1]; rep = 3 + (int)(v & 3); b += 2; }
+            else if (s == 17) { rep = 3 + (int)(v & 7); b += 3; }
+            else { rep = 11 + (int)(v & 127); b += 7; }
+            if (idx + rep > nlen + ndist) return E_CODES;
+            while (rep--) l[idx++] = val;
+        }
+        if (b > end_bit) return E_INPUT;
+        if (l[256] == 0) return E_CODES;
+        rc = build_table(l, nlen, S->lcnt, S->lsym, S->lt, LBITS, true);
+        if (rc) return rc;
+        *bp = b;
+        return build_table(l + nlen, ndist, S->dcnt, S->dsym, S->dt, DBITS, true);
+    }
+
+    // all lanes, same path: decode up to L::N symbols; lane i keeps symbol i in *mine.  Needs >= 64 ring words ahead.
+    WGBS_HD int decode_batch(uint32_t *mine, int *nq, bool *eob) {
+        int n = 0; uint32_t my = 0;
+        const int me = lanes.id();
+        while (n < L::N) {
+            uint32_t v = peek();
+            uint32_t e = S->lt[v & ((1u << LBITS) - 1)];
+            int s, nb = (int)(e >> 9);
+            if (nb) s = (int)(e & 511); else { s = slow_decode(v, S->lcnt, S->lsym, &nb); if (s < 0) return E_SYMBOL; }
+            bitpos += (uint32_t)nb;
+            if (s < 256) { if (me == n) my = (uint32_t)s; n++; continue; }
+            if (s == 256) { *eob = true; break; }
+            if (s > 285) return E_SYMBOL;
+            v >>= nb;                                                   // code <= 15 bits + extra <= 5 bits: still inside the window
+            uint32_t len;
+            if (s < 265) len = (uint32_t)(s - 254);
+            else if (s == 285) len = 258;
+            else { const int eb = ((s - 265) >> 2) + 1; len = 3 + ((4u + (uint32_t)((s - 265) & 3)) << eb) + (v & ((1u << eb) - 1)); bitpos += (uint32_t)eb; }
+            v = peek();
+            e = S->dt[v & ((1u << DBITS) - 1)];
+            nb = (int)(e >> 9);
+            if (nb) s = (int)(e & 511); else { s = slow_decode(v, S->dcnt, S->dsym, &nb); if (s < 0) return E_SYMBOL; }
+            if (s > 29) return E_SYMBOL;
+            bitpos += (uint32_t)nb; v >>= nb;
+            uint32_t dist;
+            if (s < 4) dist = (uint32_t)s + 1;
+            else { const int eb = (s >> 1) - 1; dist = 1 + ((2u + (uint32_t)(s & 1)) << eb) + (v & ((1u << eb) - 1)); bitpos += (uint32_t)eb; }
+            if (me == n) my = 0x80000000u | ((dist - 1) << 9) | len;
+            n++;
+        }
+        if (bitpos > end_bit) return E_INPUT;                          // some symbol of this batch read past the payload
+        *mine = my; *nq = n;
+        return OK;
+    }
+
+    // Write the batch at *opos.  Half of the symbols of a BAM stream are matches (measured: 4 000 literals + 4 000 matches of
+    // ~15 bytes per 64 KiB block), so copying them one after the other -- a dependent L2 round trip each -- is what the
+    // first decoder spends most of its time on.  Here a match whose source lies entirely BEFORE this batch's output
+    // (93 % of them) is copied by its own lane, all lanes at once; only matches that read what this very batch produces
+    // (short distances, runs) go through the in-order cooperative loop afterwards.
+    WGBS_HD int emit(uint32_t e, int nq, uint32_t *opos) {
+        const int l = lanes.id();
+        const uint32_t base = *opos;
+        const bool live = l < nq, is_match = live && (e >> 31);
+        const uint32_t len = e & 511u, dist = ((e >> 9) & 0xffffu) + 1;
+        const uint32_t mylen = !live ? 0u : (is_match ? len : 1u);
+        uint32_t total;
+        const uint32_t at = base + lanes.exscan(mylen, &total, mylen);
+        if (base + total > dst_len) return E_OUTPUT;
+        if (lanes.ballot(is_match && dist > at)) return E_DIST;
+        const bool dep = is_match && (at - dist + len > base);
+        lanes.sync();                                                   // everything written by earlier batches is visible
+        if (live && !is_match) dst[at] = (uint8_t)e;
+        if (is_match && !dep) { const uint8_t *from = dst + at - dist; for (uint32_t k = 0; k < len; k++) dst[at + k] = from[k]; }
+        uint32_t m = lanes.ballot(dep);
+        if (m) {
+            lanes.sync();
+            while (m) {
+                int i = 0; while (!((m >> i) & 1)) i++;
+                m &= m - 1;
+                const uint32_t ee = lanes.shfl(e, i), p = lanes.shfl(at, i);
+                const uint32_t ln = ee & 511u, ds = ((ee >> 9) & 0xffffu) + 1;
+                const uint8_t *from = dst + p - ds;
+                if (ds >= ln) { for (uint32_t k = (uint32_t)l; k < ln; k += L::N) dst[p + k] = from[k]; }
+                else { for (uint32_t k = (uint32_t)l; k < ln; k += L::N) dst[p + k] = from[k % ds]; }
+                lanes.sync();
+            }
+        }
+        *opos += total;
+        return OK;
+    }
+
+    // src / src_len: the deflate payload; the words around it must be readable (the caller pads the buffer)
+    WGBS_HD int run(const uint8_t *src, uint32_t src_len) {
+        const uint32_t mis = (uint32_t)((uintptr_t)src & 3);
+        gw = (const uint32_t *)(src - mis);
+        bitpos = 8 * mis; end_bit = 8 * (mis + src_len); nwords = (mis + src_len + 3) >> 2;
+        hi_w = 0;
+        uint32_t opos = 0;
+        int rc = OK;
+        bool last = false;
+        while (!last && rc == OK) {
+            refill(300);
+            if (bitpos + 3 > end_bit) { rc = E_INPUT; break; }
+            const uint32_t hdr = peek() & 7; bitpos += 3;
+            last = hdr & 1;
+            const uint32_t type = hdr >> 1;
+            if (type == 0) {
+                bitpos = (bitpos + 7) & ~7u;
+                if (bitpos + 32 > end_bit) { rc = E_INPUT; break; }
+                const uint32_t v = peek(); bitpos += 32;
+                if ((v & 0xffffu) != ((~v >> 16) & 0xffffu)) { rc = E_STORED; break; }
+                const uint32_t slen = v & 0xffffu, from = (bitpos >> 3) - mis;
+                if (from + slen > src_len) { rc = E_INPUT; break; }
+                if (opos + slen > dst_len) { rc = E_OUTPUT; break; }
+                for (uint32_t k = (uint32_t)lanes.id(); k < slen; k += L::N) dst[opos + k] = src[from + k];
+                opos += slen; bitpos += 8 * slen;
+                lanes.sync();
+                continue;
+            }
+            if (type == 3) { rc = E_BTYPE; break; }
+            // tables: one lane builds them (a few thousand instructions per deflate block), the position is broadcast
+            uint32_t bp = bitpos;
+            if (lanes.id() == 0) rc = type == 1 ? fixed_tables() : dynamic_tables(&bp);
+            lanes.sync();
+            rc = (int)lanes.shfl((uint32_t)rc, 0);
+            if (rc != OK) break;
+            bitpos = lanes.shfl(bp, 0);
+            bool eob = false;
+            while (!eob) {
+                refill(64);
+                uint32_t mine = 0; int nq = 0;
+                rc = decode_batch(&mine, &nq, &eob);
+                if (rc != OK) break;
+                if (nq) { rc = emit(mine, nq, &opos); if (rc != OK) break; }
+            }
+        }
+        if (rc == OK && opos != dst_len) rc = E_SHORT;
+        return rc;
+    }
+};
+
 // ---- CRC-32 of a block's output (gzip trailer; htslib checks it in bgzf_read_block -> check_header/inflate_block) -----------
 // Reflected CRC-32 (polynomial 0xEDB88320).  Every lane runs the byte-wise table update over its own contiguous slice from a
 // zero register; the slices are then chained: register(A||B) = register(A) * x^(8|B|) mod P  xor  register_0(B).
