@@ -4,8 +4,8 @@ becomes ONE wgbs_pileup_sam + wgbs_collapse + wgbs_pats_format per chromosome sh
 threads and concatenated in chromosome order (bam2pat.py:398-422), and the beta file comes from the same device-resident
 templates (no second pass over the pat text).
 
-Input: a coordinate-sorted .bam (decoded by the library's own BGZF/BAM reader, csrc/bam.cu -- samtools is not needed) or
-SAM text (.sam, or '-' for stdin: what `samtools view BAM` prints)."""
+Input: a coordinate-sorted .bam (decoded by the library's own BGZF/BAM readers -- on the device, csrc/bamdev.cu, or on host
+threads, csrc/bam.cu; samtools is not needed) or SAM text (.sam, or '-' for stdin: what `samtools view BAM` prints)."""
 from __future__ import annotations
 
 import argparse
@@ -66,9 +66,20 @@ class _Source:
         self.bam = None; self.sam = None; self.on_device = False
         if path.endswith(".bam"):
             from .bamio import BamFile, DeviceBam
-            self.on_device = decode == "device"
-            # device: the compressed bytes cross PCIe, BGZF inflate + record filtering + SAM formatting run in HBM (csrc/bamdev.cu)
-            self.bam = DeviceBam(ctx, path) if self.on_device else BamFile(path, threads)
+            # device: the compressed bytes cross PCIe, BGZF inflate + record filtering + SAM formatting run in HBM (csrc/bamdev.cu);
+            # auto: device unless the inflated file does not fit in device memory (then the host reader decodes it)
+            self.on_device = decode in ("device", "auto")
+            if self.on_device:
+                from ._lib import WgbsError
+                try:
+                    self.bam = DeviceBam(ctx, path)
+                except WgbsError as e:
+                    if decode != "auto" or "does not fit in device memory" not in str(e):
+                        raise
+                    print(f"[wt bam2pat] {e}; decoding on the host", file=sys.stderr)
+                    self.on_device = False
+            if not self.on_device:
+                self.bam = BamFile(path, threads)
             self.header = self.bam.header
             self.chroms = set(self.bam.refs)                 # `samtools idxstats | cut -f1` lists every @SQ (bam2pat.py:59)
         elif path.endswith(".cram"):
@@ -153,8 +164,9 @@ def add_args(p):
     p.add_argument("--clip", type=int, default=0, help="Clip for each read the first and last CLIP characters [0]")
     p.add_argument("--long", action="store_true", help="Use long format for pat file (add read name to each line)")
     p.add_argument("-@", "--threads", type=int, default=8, help="host threads for BGZF inflate/deflate")
-    p.add_argument("--bam_decode", choices=["host", "device"], default=os.environ.get("WGBS_BAM_DECODE", "host"),
-                   help="where the .bam is decoded: host threads (zlib), or on the GPU (compressed bytes over PCIe, one warp per BGZF block) [host]")
+    p.add_argument("--bam_decode", choices=["auto", "host", "device"], default=os.environ.get("WGBS_BAM_DECODE", "auto"),
+                   help="where the .bam is decoded: on the GPU (compressed bytes over PCIe, one warp per BGZF block), on host threads (zlib), "
+                        "or auto = GPU unless the inflated file does not fit in device memory [auto]")
     p.add_argument("--no_beta", action="store_true", help="Do not generate a beta file")
     p.add_argument("-l", "--lbeta", action="store_true", help="Use lbeta file (uint16) instead of beta (uint8)")
     p.add_argument("-T", "--temp_dir", help="accepted for CLI compatibility (the collapse is a device sort: no temp files)")

@@ -39,7 +39,7 @@ constexpr int GUESS_DEPTH = 4;      // consecutive plausible records required by
 constexpr int INFL_WARPS = 4;       // warps (= BGZF blocks) per CTA of bgzf_inflate_k
 constexpr int FMT_G = 8;            // lanes per record in bam_format_k
 #ifndef WGBS_INFLATE_DEFAULT
-#define WGBS_INFLATE_DEFAULT 1      // WGBS_INFLATE=1|2 selects the decoder at run time
+#define WGBS_INFLATE_DEFAULT 2      // WGBS_INFLATE=1|2 selects the decoder at run time (measured on the 1M-read batch: 10.4 ms / 4.7 ms)
 #endif
 
 struct BgzfBlock { uint64_t coff /* first byte of the deflate payload */, uoff; uint32_t clen, usize, crc, pad; };

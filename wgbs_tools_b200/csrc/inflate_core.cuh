@@ -31,6 +31,7 @@ struct Scratch {
     uint16_t dt[1 << DBITS];
     uint16_t lsym[288], dsym[32];   // symbols in canonical order + per-length counts, for the long codes
     uint16_t lcnt[16], dcnt[16];
+    uint16_t lfirst[16], loffs[16], dfirst[16], doffs[16];   // first canonical code / first index in *sym per code length
     uint32_t q[32];              // decoded symbols: literal byte, or 0x80000000 | (dist-1) << 9 | length
     uint8_t lens[320];
 };
@@ -68,13 +69,31 @@ struct LaneGroup {
 };
 #endif
 
+WGBS_HD int lowest_bit(uint32_t m) {             // index of the lowest set bit (m != 0)
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)m) - 1;
+#else
+    return __builtin_ctz(m);
+#endif
+}
+WGBS_HD uint32_t brev32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __brev(v);
+#else
+    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1); v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+    v = ((v >> 4) & 0x0f0f0f0fu) | ((v & 0x0f0f0f0fu) << 4); v = ((v >> 8) & 0x00ff00ffu) | ((v & 0x00ff00ffu) << 8);
+    return (v >> 16) | (v << 16);
+#endif
+}
+
 // ---- canonical Huffman tables ----------------------------------------------------------------------------------------
 WGBS_HD uint32_t bitrev(uint32_t c, int n) { uint32_t r = 0; for (int i = 0; i < n; i++) { r = (r << 1) | (c & 1); c >>= 1; } return r; }
 
 // lens[0..n) -> cnt[16], sym[] (canonical order), fast[1<<fbits].  Over-subscribed sets are rejected; incomplete sets are
 // rejected too, except (single_ok: literal/length and distance sets, not the code-length code) when no code is longer
 // than one bit -- the cases zlib's inftrees.c accepts; an unused slot decodes to "invalid code" if the stream reaches it.
-WGBS_HD int build_table(const uint8_t *lens, int n, uint16_t *cnt, uint16_t *sym, uint16_t *fast, int fbits, bool single_ok) {
+WGBS_HD int build_table(const uint8_t *lens, int n, uint16_t *cnt, uint16_t *sym, uint16_t *fast, int fbits, bool single_ok,
+                        uint16_t *first_out = nullptr, uint16_t *offs_out = nullptr) {
     for (int i = 0; i < 16; i++) cnt[i] = 0;
     for (int i = 0; i < n; i++) cnt[lens[i]]++;
     for (int i = 0; i < (1 << fbits); i++) fast[i] = 0;
@@ -84,6 +103,7 @@ WGBS_HD int build_table(const uint8_t *lens, int n, uint16_t *cnt, uint16_t *sym
     uint16_t offs[16], code[16];
     offs[1] = 0; code[1] = 0;
     for (int l = 1; l < 15; l++) { offs[l + 1] = (uint16_t)(offs[l] + cnt[l]); code[l + 1] = (uint16_t)((code[l] + cnt[l]) << 1); }
+    if (first_out) for (int l = 1; l <= 15; l++) { first_out[l] = code[l]; offs_out[l] = offs[l]; }
     for (int s = 0; s < n; s++) {
         const int l = lens[s];
         if (!l) continue;
@@ -105,6 +125,18 @@ WGBS_HD int slow_decode(uint64_t bb, const uint16_t *cnt, const uint16_t *sym, i
         const int count = cnt[len];
         if (code - count < first) { *nbits = len; return sym[index + (code - first)]; }
         index += count; first += count; first <<= 1; code <<= 1;
+    }
+    return -1;
+}
+
+// The same for codes longer than the fast table, without the bit-by-bit walk: the codes of length L are the numbers
+// first[L] .. first[L]+cnt[L]-1, and the L-bit prefix of any longer code is larger than all of them, so the first L for
+// which the (bit-reversed) next L stream bits fall into that range is the code length.  v: next 32 stream bits, LSB first.
+WGBS_HD int long_decode(uint32_t v, const uint16_t *cnt, const uint16_t *first, const uint16_t *offs, const uint16_t *sym, int fbits, int *nbits) {
+    const uint32_t r = brev32(v);
+    for (int L = fbits + 1; L <= 15; L++) {
+        const uint32_t d = (r >> (32 - L)) - first[L];
+        if (d < cnt[L]) { *nbits = L; return sym[offs[L] + d]; }
     }
     return -1;
 }
@@ -334,6 +366,7 @@ struct Inflater {
 // the emit step (literals in parallel, matches in stream order) is the same.
 constexpr uint32_t RING_WORDS = 512;            // 2 KiB of compressed stream per warp
 constexpr uint32_t RING_KEEP = 480;             // words loaded ahead of the read position by a refill
+constexpr uint32_t OWN_MAX = 16;                // matches up to this length are copied by the lane that decoded them
 struct Ring { uint32_t w[RING_WORDS + 1]; };    // slot RING_WORDS mirrors slot 0: the word after any slot is at +1, no wrap
 
 WGBS_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
@@ -381,10 +414,11 @@ struct Inflater2 {
         for (int i = 144; i < 256; i++) l[i] = 9;
         for (int i = 256; i < 280; i++) l[i] = 7;
         for (int i = 280; i < 288; i++) l[i] = 8;
-        int rc = build_table(l, 288, S->lcnt, S->lsym, S->lt, LBITS, true);
+        int rc = build_table(l, 288, S->lcnt, S->lsym, S->lt, LBITS, true, S->lfirst, S->loffs);
         if (rc) return rc;
         for (int i = 0; i < 16; i++) S->dcnt[i] = 0;
         S->dcnt[5] = 30;
+        for (int i = 0; i < 16; i++) { S->dfirst[i] = 0; S->doffs[i] = 0; }
         for (int i = 0; i < (1 << DBITS); i++) S->dt[i] = 0;
         for (int s = 0; s < 30; s++) {
             S->dsym[s] = (uint16_t)s;
@@ -428,25 +462,26 @@ struct Inflater2 {
         }
         if (b > end_bit) return E_INPUT;
         if (l[256] == 0) return E_CODES;
-        rc = build_table(l, nlen, S->lcnt, S->lsym, S->lt, LBITS, true);
+        rc = build_table(l, nlen, S->lcnt, S->lsym, S->lt, LBITS, true, S->lfirst, S->loffs);
         if (rc) return rc;
         *bp = b;
-        return build_table(l + nlen, ndist, S->dcnt, S->dsym, S->dt, DBITS, true);
+        return build_table(l + nlen, ndist, S->dcnt, S->dsym, S->dt, DBITS, true, S->dfirst, S->doffs);
     }
 
     // all lanes, same path: decode up to L::N symbols; lane i keeps symbol i in *mine.  Needs >= 64 ring words ahead.
     WGBS_HD int decode_batch(uint32_t *mine, int *nq, bool *eob) {
         int n = 0; uint32_t my = 0;
         const int me = lanes.id();
-        while (n < L::N) {
+        bool bad = false;                                                // invalid code / symbol: noted, reported after the batch
+        while (n < L::N) {                                               // (no early exits in the loop: one uniform path)
             uint32_t v = peek();
             uint32_t e = S->lt[v & ((1u << LBITS) - 1)];
             int s, nb = (int)(e >> 9);
-            if (nb) s = (int)(e & 511); else { s = slow_decode(v, S->lcnt, S->lsym, &nb); if (s < 0) return E_SYMBOL; }
+            if (nb) s = (int)(e & 511); else { s = long_decode(v, S->lcnt, S->lfirst, S->loffs, S->lsym, LBITS, &nb); if (s < 0) { bad = true; s = 256; nb = 0; } }
             bitpos += (uint32_t)nb;
             if (s < 256) { if (me == n) my = (uint32_t)s; n++; continue; }
             if (s == 256) { *eob = true; break; }
-            if (s > 285) return E_SYMBOL;
+            if (s > 285) { bad = true; *eob = true; break; }
             v >>= nb;                                                   // code <= 15 bits + extra <= 5 bits: still inside the window
             uint32_t len;
             if (s < 265) len = (uint32_t)(s - 254);
@@ -455,8 +490,8 @@ struct Inflater2 {
             v = peek();
             e = S->dt[v & ((1u << DBITS) - 1)];
             nb = (int)(e >> 9);
-            if (nb) s = (int)(e & 511); else { s = slow_decode(v, S->dcnt, S->dsym, &nb); if (s < 0) return E_SYMBOL; }
-            if (s > 29) return E_SYMBOL;
+            if (nb) s = (int)(e & 511); else { s = long_decode(v, S->dcnt, S->dfirst, S->doffs, S->dsym, DBITS, &nb); if (s < 0) { bad = true; s = 0; nb = 0; } }
+            if (s > 29) { bad = true; s = 0; }
             bitpos += (uint32_t)nb; v >>= nb;
             uint32_t dist;
             if (s < 4) dist = (uint32_t)s + 1;
@@ -464,6 +499,7 @@ struct Inflater2 {
             if (me == n) my = 0x80000000u | ((dist - 1) << 9) | len;
             n++;
         }
+        if (bad) return E_SYMBOL;
         if (bitpos > end_bit) return E_INPUT;                          // some symbol of this batch read past the payload
         *mine = my; *nq = n;
         return OK;
@@ -473,7 +509,7 @@ struct Inflater2 {
     // ~15 bytes per 64 KiB block), so copying them one after the other -- a dependent L2 round trip each -- is what the
     // first decoder spends most of its time on.  Here a match whose source lies entirely BEFORE this batch's output
     // (93 % of them) is copied by its own lane, all lanes at once; only matches that read what this very batch produces
-    // (short distances, runs) go through the in-order cooperative loop afterwards.
+    // (short distances, runs) and long ones go through the in-order cooperative loop afterwards.
     WGBS_HD int emit(uint32_t e, int nq, uint32_t *opos) {
         const int l = lanes.id();
         const uint32_t base = *opos;
@@ -484,15 +520,17 @@ struct Inflater2 {
         const uint32_t at = base + lanes.exscan(mylen, &total, mylen);
         if (base + total > dst_len) return E_OUTPUT;
         if (lanes.ballot(is_match && dist > at)) return E_DIST;
-        const bool dep = is_match && (at - dist + len > base);
+        // own: source entirely before this batch AND short (6 % of the matches are 80..258 bytes long and carry two thirds of
+        // the bytes: one lane copying such a match byte by byte stalls the other 31, so long ones are copied by the whole warp)
+        const bool own = is_match && (at - dist + len <= base) && len <= OWN_MAX;
         lanes.sync();                                                   // everything written by earlier batches is visible
         if (live && !is_match) dst[at] = (uint8_t)e;
-        if (is_match && !dep) { const uint8_t *from = dst + at - dist; for (uint32_t k = 0; k < len; k++) dst[at + k] = from[k]; }
-        uint32_t m = lanes.ballot(dep);
+        if (own) { const uint8_t *from = dst + at - dist; for (uint32_t k = 0; k < len; k++) dst[at + k] = from[k]; }
+        uint32_t m = lanes.ballot(is_match && !own);
         if (m) {
             lanes.sync();
             while (m) {
-                int i = 0; while (!((m >> i) & 1)) i++;
+                const int i = lowest_bit(m);
                 m &= m - 1;
                 const uint32_t ee = lanes.shfl(e, i), p = lanes.shfl(at, i);
                 const uint32_t ln = ee & 511u, ds = ((ee >> 9) & 0xffffu) + 1;
