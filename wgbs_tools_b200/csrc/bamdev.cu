@@ -11,6 +11,7 @@
 //   bam_check_k      entry[s+1] must equal exit[s]; repaired and re-walked until nothing changes (exact, whatever the guesses)
 //   bam_fill_k       record offsets; bam_runs_k: per-reference record ranges + sortedness + record sanity
 //   bam_measure_k    thread per record: filters + SAM line length;  bam_format_k: warp per record: the line
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -204,15 +205,17 @@ int bgzf_inflate_device(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, const ch
     }
     if (off != nbytes) return wgbs_set_err("%s: %llu trailing bytes after the last BGZF block", who, (unsigned long long)(nbytes - off));
     if (blocks.size() >= 0xffffffffull) return wgbs_set_err("%s: too many BGZF blocks", who);
-    size_t free_b = 0, total_b = 0;
-    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-    if ((double)uoff * 1.25 + (double)nbytes > (double)free_b)
-        return wgbs_set_err("%s: the inflated stream (%.1f GB) does not fit in device memory (%.1f GB free); process the file in parts", who, uoff / 1e9, free_b / 1e9);
     Temps T(ctx);
     uint8_t *d_comp, *data = nullptr; BgzfBlock *d_blocks; unsigned long long *d_err;
-    RC_TRY(T.alloc(&d_comp, nbytes + 16)); RC_TRY(T.alloc(&d_blocks, blocks.size())); RC_TRY(T.alloc(&d_err, 1));
-    RC_TRY(dalloc(ctx, &data, uoff + 16));
     int rc;
+    if ((rc = T.alloc(&d_comp, nbytes + 16)) < 0 || (rc = T.alloc(&d_blocks, blocks.size())) < 0 || (rc = T.alloc(&d_err, 1)) < 0 || (rc = dalloc(ctx, &data, uoff + 16)) < 0) {
+        // (cudaMemGetInfo costs a fraction of a millisecond: asked only to word the error)
+        cudaGetLastError();
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        return wgbs_set_err("%s: the inflated stream (%.1f GB + %.1f GB compressed) does not fit in device memory (%.1f GB free); process the file in parts",
+                            who, uoff / 1e9, nbytes / 1e9, free_b / 1e9);
+    }
     if ((rc = copy_any(ctx, d_comp, f, nbytes)) < 0 || (rc = copy_any(ctx, d_blocks, blocks.data(), blocks.size() * sizeof(BgzfBlock))) < 0) { dfree(ctx, data); return rc; }
     unsigned long long herr = 0;
     cudaError_t e = cudaMemsetAsync(d_err, 0xff, 8, ctx->stream);
@@ -243,10 +246,19 @@ extern "C" int wgbs_dbam_open(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, wg
     Temps T(ctx);
     int rc;
     unsigned long long *d_err;
+    static const bool dbg = getenv("WGBS_BAM_DEBUG") != nullptr;          // host-side phase times on stderr
+    auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!dbg) return;
+        cudaStreamSynchronize(ctx->stream);
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[dbam] %-12s %.3f ms\n", what, std::chrono::duration<double, std::milli>(t - T0).count()); T0 = t;
+    };
     if ((rc = T.alloc(&d_err, 4)) < 0) return fail_free(ctx, B, rc);
     // 1 + 2. BGZF block table (host) and inflate (one warp per block)
     { uint64_t nb = 0; if ((rc = bgzf_inflate_device(ctx, bgzf, nbytes, "wgbs_dbam_open", &B->data, &B->n, &nb)) < 0) return fail_free(ctx, B, rc); B->n_blocks = nb; }
     B->comp_bytes = nbytes;
+    lap("scan+inflate");
     const uint64_t uoff = B->n;
     unsigned long long herr[4];
     // 3. header: "BAM\1" l_text text n_ref { l_name name l_ref }   (SAM spec 4.2)
@@ -279,6 +291,7 @@ extern "C" int wgbs_dbam_open(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, wg
     if ((rc = dalloc(ctx, &B->d_name_off, name_off.size())) < 0 || (rc = dalloc(ctx, &B->d_names, names.size())) < 0 || (rc = dalloc(ctx, &B->d_ref_lens, (size_t)n_ref)) < 0 ||
         (rc = copy_any(ctx, B->d_name_off, name_off.data(), name_off.size() * 4)) < 0 || (rc = copy_any(ctx, B->d_names, names.data(), names.size())) < 0 ||
         (rc = copy_any(ctx, B->d_ref_lens, B->ref_lens.data(), (size_t)n_ref * 4)) < 0) return fail_free(ctx, B, rc);
+    lap("header");
     // 4. record table: guess the first record of every segment, walk, repair until every entry equals its predecessor's exit
     const uint64_t p0 = p, n = uoff, nseg = n > p0 ? (n - p0 + SEG - 1) / SEG : 0;
     B->ref_first.assign(n_ref + 1, 0); B->ref_last.assign(n_ref + 1, 0);
@@ -299,6 +312,7 @@ extern "C" int wgbs_dbam_open(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, wg
             if (!h) break;
             if (round > nseg) return fail_free(ctx, B, wgbs_set_err("wgbs_dbam_open: record table did not converge"));
         }
+        lap("guess+walk");
         CUDA_TRY(cudaMemsetAsync(d_err, 0xff, 4 * 8, ctx->stream));
         LAUNCH(ctx, bam_first_bad_k, grid_for(nseg, 256), 256, 0, nseg, bad, d_err);
         if ((rc = scan_u32_u64(ctx, cnt, base, nseg)) < 0) return fail_free(ctx, B, rc);
@@ -327,6 +341,7 @@ extern "C" int wgbs_dbam_open(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, wg
                 if (runs[i] > 1) return fail_free(ctx, B, wgbs_set_err("the BAM is not sorted by coordinate (reference %d appears in two separate runs)", i < n_ref ? (int)i : -1));
         }
     }
+    lap("table+runs");
     LAUNCH_CHECK();
     *out = B;
     return 0;
