@@ -109,6 +109,8 @@ def parse_args(argv=None):
     p.add_argument("--verbose", "-v", action="store_true"); p.add_argument("--binary", action="store_true")
     p.add_argument("--genome"); p.add_argument("--nr_bits", type=int, default=8)
     p.add_argument("--thresholds", "-t"); p.add_argument("--rlen", "-l", type=int, default=3); p.add_argument("--debug", "-d", action="store_true")
+    p.add_argument("--pat_decode", choices=["auto", "host", "device"], default=os.environ.get("WGBS_PAT_DECODE", "auto"),
+                   help="where X.pat.gz is inflated: on the GPU when it is BGZF (one warp per block), or on the host (gzip) [auto]")
     return p.parse_args(argv)
 
 
@@ -143,9 +145,15 @@ def main(argv=None):
             if os.path.exists(opath) and not args.force:
                 print(f"[ wt homog ] skipping {name}. Use -f to overwrite", file=sys.stderr)
                 continue
-            P = ctx.pats_from_text(wd.shard_lines(read_pat_text(pat), rank, world))
+            dtext = None
+            if world == 1 and args.pat_decode in ("auto", "device"):
+                from .patio import read_pat_device
+                dtext = read_pat_device(ctx, pat)                  # BGZF: only the compressed bytes cross PCIe; None: plain gzip / text
+            P = ctx.pats_from_text(dtext if dtext is not None else wd.shard_lines(read_pat_text(pat), rank, world))
             counts = homog_counts(ctx, P, lines, cols, edges, args.rlen, args.inclusive)
             P.free()
+            if dtext is not None:
+                dtext.free()
             counts = wd.reduce_np(counts, 0)                           # bins are sums over records: exact under any record split
             if rank != 0:
                 continue

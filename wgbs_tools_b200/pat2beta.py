@@ -6,7 +6,7 @@ import os
 import sys
 
 
-def pat2beta(ctx, pat_path: str, out_dir: str, nr_sites: int, lbeta: bool = False, force: bool = True, decode: str = "host"):
+def pat2beta(ctx, pat_path: str, out_dir: str, nr_sites: int, lbeta: bool = False, force: bool = True, decode: str = "auto"):
     from .patio import read_pat_text, splitextgz
     suff = ".lbeta" if lbeta else ".beta"
     out_beta = os.path.join(out_dir, splitextgz(os.path.basename(pat_path)) + suff)
@@ -16,7 +16,7 @@ def pat2beta(ctx, pat_path: str, out_dir: str, nr_sites: int, lbeta: bool = Fals
     from . import dist as wd
     rank, world = wd.world()
     dtext = None
-    if world == 1 and decode == "device":
+    if world == 1 and decode in ("auto", "device"):
         from .patio import read_pat_device
         dtext = read_pat_device(ctx, pat_path)                     # BGZF inflated in HBM; None: not a BGZF file
     if dtext is not None:
@@ -46,8 +46,8 @@ def main(argv=None):
     p.add_argument("pat_paths", nargs="+"); p.add_argument("-f", "--force", action="store_true")
     p.add_argument("-o", "--out_dir", default="."); p.add_argument("-l", "--lbeta", action="store_true")
     p.add_argument("--genome"); p.add_argument("-@", "--threads", type=int, default=1)
-    p.add_argument("--pat_decode", choices=["host", "device"], default=os.environ.get("WGBS_PAT_DECODE", "host"),
-                   help="where X.pat.gz is inflated: host (gzip), or on the GPU (compressed bytes over PCIe, one warp per BGZF block) [host]")
+    p.add_argument("--pat_decode", choices=["auto", "host", "device"], default=os.environ.get("WGBS_PAT_DECODE", "auto"),
+                   help="where X.pat.gz is inflated: on the GPU when it is BGZF (compressed bytes over PCIe, one warp per block), or on the host (gzip) [auto]")
     a = p.parse_args(argv)
     ref = GenomeRef(a.genome)
     from . import dist as wd
