@@ -258,3 +258,91 @@ def test_bam2pat_cli_device_decode_equals_host_decode(ctx, bamio, tmp_path):
         if "--mbias" in argv:
             for x in ("OT", "OB"):
                 assert (a / "s.mbias" / f"s.mbias.{x}.txt").read_bytes() == (b / "s.mbias" / f"s.mbias.{x}.txt").read_bytes()
+
+
+# ---- the direct route: BAM records feed the pileup kernels as they are (no SAM text formatted / tokenized) --------------------------
+def _both_routes(ctx, db, ix, chrom, monkeypatch, **kw):
+    res = []
+    for direct in ("0", "1"):
+        monkeypatch.setenv("WGBS_DBAM_DIRECT", direct)
+        P, st = db.pileup(ix, chrom, **kw)
+        long = bool(kw.get("keep_names"))
+        raw = P.to_text(chrom, long=long) if not long else None
+        P.collapse(long=long)
+        txt = P.to_text(chrom, long=long)
+        P.free()
+        mb = st.pop("mbias", None)
+        res.append((raw, txt, st, None if mb is None else mb.tobytes()))
+    assert res[0] == res[1], kw
+    return res[1]
+
+
+def test_direct_route_equals_text_route_and_oracle(ctx, bamio, oracle, monkeypatch):
+    H = oracle
+    g = synth.make_genome(7, "chrT", 1_000_000)
+    ix = ctx.load_index(g.loci, g.first_idx)
+    refs = [("chrT", g.length)]
+    # 1. paired-end reads with I/D/S events and singletons, plus supplementary copies (3-record QNAME groups: whole-line ordering)
+    lines = synth.make_sam(g, 6_000, 5, paired=True, single_frac=0.05).splitlines()
+    extra = []
+    for l in lines[::97]:
+        t = l.split(b"\t"); t[1] = b"%d" % (int(t[1]) | 2048); t[3] = b"%d" % (int(t[3]) + 5000); extra.append(b"\t".join(t))
+    sam = b"\n".join(sorted(lines + extra, key=lambda l: int(l.split(b"\t")[3]))) + b"\n"
+    with bamio.DeviceBam.from_bytes(ctx, bamio.sam_to_bam(sam, refs)) as db:
+        for kw in (dict(), dict(clip=7, min_cpg=2), dict(keep_names=True), dict(mbias=True), dict(view=dict(mapq=10, exclude_flags=1796, include_flags=3)),
+                   dict(view=dict(beg=200_000, end=400_000)), dict(view=dict(max_records=1001))):
+            raw, txt, st, _ = _both_routes(ctx, db, ix, "chrT", monkeypatch, **kw)
+            if not kw:
+                pout, pst = H.port_patter(H.port_match_maker(sam), g.loci, g.idx())
+                assert txt == H.port_collapse(pout)
+                assert [st[k] for k in ("lines", "pairs", "empty", "short", "invalid", "paired")] == pst and st["pairs"] > 2000
+    # 2. single-end reads with every CIGAR op, invalid CIGARs, SEQ '*', CIGAR '*', reads beyond the last CpG
+    rng = np.random.default_rng(4)
+    recs = []; pos = 1000
+    for i in range(3000):
+        pos += int(rng.integers(1, 300))
+        ops = []; qlen = 0
+        for _ in range(int(rng.integers(1, 7))):
+            op = "MIDSNH=XP"[int(rng.integers(0, 9))]; k = int(rng.integers(1, 40))
+            ops.append(f"{k}{op}")
+            if op in "MIS=X":
+                qlen += k
+        seq = bytes(rng.choice(list(b"ACGTN"), size=max(qlen + int(rng.integers(-2, 3)), 1), p=[.2, .3, .25, .2, .05]).tolist())
+        cig = "".join(ops).encode() if i % 50 else b"*"
+        recs.append(b"r%d\t%d\tchrT\t%d\t60\t%s\t*\t0\t0\t%s\t*" % (i, 16 * int(rng.integers(0, 2)), pos, cig, seq if i % 41 else b"*"))
+    p = int(g.loci[-1]) - 5
+    recs.append(b"z\t0\tchrT\t%d\t60\t60M\t*\t0\t0\t%s\t*" % (p, g.bases[p:p + 60].tobytes()))
+    sam = b"\n".join(recs) + b"\n"
+    with bamio.DeviceBam.from_bytes(ctx, bamio.sam_to_bam(sam, refs)) as db:
+        raw, txt, st, _ = _both_routes(ctx, db, ix, "chrT", monkeypatch)
+        pout, pst = H.port_patter(sam, g.loci, g.idx())
+        assert txt == H.port_collapse(pout)
+        assert [st[k] for k in ("lines", "pairs", "empty", "short", "invalid", "paired")] == pst and st["invalid"] > 100
+        _both_routes(ctx, db, ix, "chrT", monkeypatch, clip=3, mbias=True)
+    # 3. MM/ML data takes the text route by itself (first record carries an MM tag): same result under either setting
+    sam = synth.make_sam(g, 800, 9, paired=False, np_mode=True) if "np_mode" in synth.make_sam.__code__.co_varnames else None
+    if sam:
+        with bamio.DeviceBam.from_bytes(ctx, bamio.sam_to_bam(sam, refs)) as db:
+            raw, txt, st, _ = _both_routes(ctx, db, ix, "chrT", monkeypatch)
+            assert st["nanopore"] == 1 and txt
+    ix.free()
+
+
+def test_bam2pat_cli_direct_route(ctx, bamio, tmp_path, monkeypatch):
+    from wgbs_tools_b200 import bam2pat
+    g1 = synth.make_genome(31, "chr1", 400_000, first_idx=1)
+    refdir = tmp_path / "ref"; refdir.mkdir()
+    with gzip.open(refdir / "CpG.bed.gz", "wb") as f:
+        f.write(g1.dict_text())
+    (refdir / "CpG.chrome.size").write_text(f"chr1\t{g1.n_cpg}\n"); (refdir / "chrome.size").write_text(f"chr1\t{g1.length}\n")
+    sam = synth.make_sam(g1, 9000, 1, paired=True)
+    bam = tmp_path / "s.bam"; bam.write_bytes(bamio.sam_to_bam(sam, [("chr1", g1.length)]))
+    outs = {}
+    for mode, direct in (("host", "0"), ("device", "0"), ("device", "1")):
+        monkeypatch.setenv("WGBS_DBAM_DIRECT", direct)
+        out = tmp_path / f"out_{mode}_{direct}"; out.mkdir()
+        bam2pat.main([str(bam), "--genome", str(refdir), "-o", str(out), "--bam_decode", mode, "--mbias"])
+        outs[(mode, direct)] = (gzip.decompress((out / "s.pat.gz").read_bytes()), (out / "s.beta").read_bytes(),
+                                (out / "s.mbias" / "s.mbias.OT.txt").read_bytes())
+    assert outs[("host", "0")] == outs[("device", "0")] == outs[("device", "1")]
+    assert len(outs[("host", "0")][0]) > 1000

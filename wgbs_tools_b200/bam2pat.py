@@ -33,18 +33,25 @@ def split_sam_by_chrom(sam: bytes) -> dict[str, bytes]:
     return {c: b"".join(v) for c, v in out.items()}
 
 
-def proc_chr(ctx, ref, region: str, sam: bytes, args, mc_buf):
+def proc_chr(ctx, ref, region: str, sam, args, mc_buf):
     """one chromosome / region: returns (pat text bytes, stats); adds its beta counts into mc_buf (device).  patter is
-    given the dictionary of the region extended by MAX_READ_SIZE (bam2pat.py:190): CpGs outside it are not called."""
+    given the dictionary of the region extended by MAX_READ_SIZE (bam2pat.py:190): CpGs outside it are not called.
+    sam: the SAM text of the region (bytes / DevBuf), or a callable(index, **pileup options) -> (Pats, stats) that views and piles up
+    on the device (device-decoded .bam: wgbs_pileup_dbam); it returns Pats None when the region holds no reads."""
     chrom, beg, end = parse_region_str(extend_region(region))
     loci, first = ref.chrom_loci(chrom)
     if end > 0:
         lo = int(np.searchsorted(loci, beg, side="left")); hi = int(np.searchsorted(loci, end, side="right"))
         loci, first = loci[lo:hi], first + lo
     ix = ctx.load_index(loci, first)
-    P, st = ctx.pileup_sam(ix, sam, min_cpg=args.min_cpg, clip=args.clip, paired=-1, nanopore=args.nanopore,
-                           np_thresh=args.np_thresh, cpc_call=args.cpc_call, combine_mods=args.combine_mods, mbias=args.mbias,
-                           keep_names=args.long)
+    kw = dict(min_cpg=args.min_cpg, clip=args.clip, paired=-1, nanopore=args.nanopore, np_thresh=args.np_thresh, cpc_call=args.cpc_call,
+              combine_mods=args.combine_mods, mbias=args.mbias, keep_names=args.long)
+    P, st = sam(ix, **kw) if callable(sam) else ctx.pileup_sam(ix, sam, **kw)
+    if P is None or (callable(sam) and st["lines"] == 0):
+        if P is not None:
+            P.free()
+        ix.free()
+        return None, st
     if mc_buf is not None:
         ctx.pat2beta(P, 1, ref.nr_sites + 1, meth_cov=mc_buf, zero_first=False)
     P.collapse(long=args.long)                          # --long: `sort | awk '{print $1,$2,$3,1,$4}'`, no uniq (bam2pat.py:102-103)
@@ -109,6 +116,13 @@ class _Source:
                 return self.bam.view_dev(chrom, beg=beg, end=end, **kw)
             return self.bam.view(chrom, beg=beg, end=end, **kw)
         return filter_sam(self.sam.get(chrom, b""), chrom=chrom, beg=beg, end=end, **kw)
+
+    def piler(self, region: str, **view_kw):
+        """device-decoded .bam: callable(index, **pileup options) -> (Pats | None, stats) for the reads of `region`"""
+        chrom, beg, end = parse_region_str(region)
+        if chrom not in self.bam.refs:
+            return lambda ix, **kw: (None, {"lines": 0})
+        return lambda ix, **kw: self.bam.pileup(ix, chrom, view=dict(beg=beg, end=end, **view_kw), **kw)
 
     def weight(self, chrom: str) -> int:
         """how much work a chromosome is (records in a .bam, bytes of SAM text): the LPT weights of the multi-GPU split"""
@@ -266,16 +280,19 @@ def main(argv=None):
                 kw = dict(mapq=mapq, exclude_flags=ex, include_flags=inc, read_group=a.read_group)
                 if lists is not None:
                     kw.update(intervals=lists[0].get(chrom, empty_iv), exclude_intervals=lists[1])
-                s = b"" if feq is None else src.view(region, flag_eq=feq, **kw)
-                if s is None or len(s) == 0:
-                    if hasattr(s, "free"):
-                        s.free()
+                txt = None
+                if feq is None:
+                    pass
+                elif src.on_device:                                            # view + pileup in one device call (wgbs_pileup_dbam)
+                    txt, st = proc_chr(ctx, ref, region, src.piler(region, flag_eq=feq, **kw), run, mc)
+                else:
+                    s = src.view(region, flag_eq=feq, **kw)
+                    if s:
+                        txt, st = proc_chr(ctx, ref, region, s, run, mc)
+                if txt is None:
                     if a.verbose:
                         print(f"[wt bam2pat] Skipping region {region}, no reads found", file=sys.stderr)
                     continue
-                txt, st = proc_chr(ctx, ref, region, s, run, mc)
-                if hasattr(s, "free"):
-                    s.free()
                 if a.mbias and "mbias" in st:
                     mb_total = st["mbias"].astype(np.int64) if mb_total is None else mb_total + st["mbias"]   # mbias_merge (bam2pat.py:375-395)
                 if txt:

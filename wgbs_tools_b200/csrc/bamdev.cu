@@ -17,6 +17,7 @@
 
 #include "bam_core.cuh"
 #include "common.cuh"
+#include "reads.cuh"
 
 using namespace bamcore;
 
@@ -168,6 +169,64 @@ __global__ void __launch_bounds__(256) bam_format_k(const uint8_t *__restrict__ 
     const Refs RF{F.n, F.name_off, F.names, F.lens};
     WriteSink<dflate::LaneGroup<FMT_G>> ws; ws.o = text + off[i];
     format_record(R, RF, ws);
+}
+
+// ---- BAM records -> pileup descriptors, no SAM text (BAM flavour of ReadBatch, reads.cuh) ---------------------------------------
+__global__ void __launch_bounds__(256) bam_pass_k(const uint8_t *__restrict__ data, const uint64_t *__restrict__ rec_off, uint64_t nr, ViewParams V,
+                                                   uint32_t *__restrict__ pass) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nr) return;
+    Rec R; R.load(data + rec_off[i]);
+    pass[i] = passes(R, V) ? 1u : 0u;
+}
+
+// has_mm[0] = 1 iff the FIRST passing record carries an MM:Z: / Mm:Z: tag (patter.cpp:337-338 looks at the first line only)
+__global__ void __launch_bounds__(256) bam_records_k(const uint8_t *__restrict__ data, const uint64_t *__restrict__ rec_off, uint64_t nr,
+                                                      const uint32_t *__restrict__ pass, const uint32_t *__restrict__ rank, uint32_t max_records,
+                                                      uint64_t base, ReadBatch rb, uint64_t *__restrict__ rec_abs, uint32_t *__restrict__ has_mm) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nr || !pass[i]) return;
+    const uint32_t k = rank[i];
+    if (max_records && k >= max_records) return;
+    const uint64_t o = rec_off[i];
+    Rec R; R.load(data + o);
+    const uint8_t *nm = R.name();
+    uint32_t ql = 0; while (ql < R.l_name && nm[ql]) ql++;                 // l_read_name counts the NUL
+    uint64_t h = 0;
+    for (uint32_t p = 0; p < ql; p++) h += name_byte_mix(nm[p], p);
+    h = fmix64(h ^ (uint64_t)ql);
+    rb.line_off[k] = (uint32_t)(o + 36 - base); rb.line_len[k] = 0; rb.qn_len[k] = ql;
+    rb.flag[k] = (int32_t)R.flag; rb.pos[k] = (int32_t)((int64_t)R.pos + 1); rb.pos_hi[k] = 0;
+    rb.cig_off[k] = (uint32_t)(R.cigar() - data - base); rb.cig_len[k] = R.n_cig;
+    if (R.l_seq > 0) { rb.seq_off[k] = (uint32_t)(R.seq() - data - base); rb.seq_len[k] = (uint32_t)R.l_seq; }
+    else { rb.seq_off[k] = SEQ_STAR; rb.seq_len[k] = 1; }
+    rb.hash_lo[k] = (uint32_t)h; rb.hash_hi[k] = (uint32_t)(h >> 32);
+    rb.status[k] = REC_OK;
+    rec_abs[k] = o;
+    if (k == 0) {
+        uint32_t zl = 0;
+        has_mm[0] = (find_z_tag(R.tags(), R.end(), 'M', 'M', &zl) || find_z_tag(R.tags(), R.end(), 'M', 'm', &zl)) ? 1u : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(128) side_len_k(BamSide S, const uint32_t *__restrict__ ids, uint32_t m, uint32_t *__restrict__ len) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    Rec R; R.load(S.data + S.rec[ids[j]]);
+    const Refs RF{S.n_ref, S.name_off, S.names, S.ref_lens};
+    CountSink cs; format_record(R, RF, cs);
+    len[j] = cs.n > 0xffffffffull ? 0xffffffffu : (uint32_t)cs.n;
+}
+__global__ void __launch_bounds__(128) side_write_k(BamSide S, const uint32_t *__restrict__ ids, uint32_t m, const uint32_t *__restrict__ len,
+                                                     const uint64_t *__restrict__ off, char *__restrict__ text, uint32_t *__restrict__ line_off,
+                                                     uint32_t *__restrict__ line_len) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    Rec R; R.load(S.data + S.rec[ids[j]]);
+    const Refs RF{S.n_ref, S.name_off, S.names, S.ref_lens};
+    WriteSink<dflate::OneLane> ws; ws.o = text + off[j];
+    format_record(R, RF, ws);
+    line_off[ids[j]] = (uint32_t)off[j]; line_len[ids[j]] = len[j] - 1;           // without the newline, like the tokenizer's lines
 }
 
 int fail_free(wgbs_ctx *ctx, wgbs_dbam *B, int rc) {
@@ -448,9 +507,111 @@ extern "C" int wgbs_dbam_view(wgbs_ctx *ctx, const wgbs_dbam *B, const wgbs_view
     return 0;
 }
 
-// `samtools view ... | [match_maker |] patter ...` without leaving the device: wgbs_dbam_view + wgbs_pileup_sam_mbias
+int bam_side_lines(wgbs_ctx *ctx, const BamSide &S, const uint32_t *ids, uint32_t m, uint32_t n, Temps &T, char **text, uint32_t **line_off,
+                   uint32_t **line_len) {
+    uint32_t *len; uint64_t *off;
+    RC_TRY(T.alloc(&len, (size_t)m + 1)); RC_TRY(T.alloc(&off, (size_t)m + 1)); RC_TRY(T.alloc(line_off, n)); RC_TRY(T.alloc(line_len, n));
+    LAUNCH(ctx, side_len_k, grid_for(m, 128), 128, 0, S, ids, m, len);
+    RC_TRY(scan_u32_u64(ctx, len, off, m));
+    uint64_t tot = 0;
+    CUDA_TRY(cudaMemcpyAsync(&tot, off + m, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (tot >= 0xffffffffull) return wgbs_set_err("bam_side_lines: %llu bytes of SAM text for the multi-record QNAME groups", (unsigned long long)tot);
+    RC_TRY(T.alloc(text, (size_t)tot + 16));
+    LAUNCH(ctx, side_write_k, grid_for(m, 128), 128, 0, S, ids, m, len, off, *text, *line_off, *line_len);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int pileup_records(wgbs_ctx *ctx, const wgbs_index *ix, const ReadBatch &rb, const wgbs_pileup_opts *opts, Temps &T, wgbs_pats **out,
+                   uint64_t *stats_out, int32_t *mbias_out);      // pileup.cu
+
+// The direct route: filters -> descriptors of the passing records (no SAM text is formatted or tokenized); the pileup kernels
+// read binary CIGARs and 4-bit bases in place.  Returns 1 when the batch needs the text route (MM/ML mode), 0 when done.
+static int pileup_dbam_direct(wgbs_ctx *ctx, const wgbs_index *ix, const wgbs_dbam *B, const wgbs_view_opts *vo, const wgbs_pileup_opts *opts,
+                              wgbs_pats **out, uint64_t *stats, int32_t *mbias) {
+    if (opts->nanopore) return 1;
+    if (vo->n_flag_eq < 0 || vo->n_flag_eq > 4) return wgbs_set_err("wgbs_pileup_dbam: n_flag_eq must be 0..4");
+    if (vo->n_iv && (!vo->iv_beg || !vo->iv_end)) return wgbs_set_err("wgbs_pileup_dbam: interval list is null");
+    if (vo->n_iv && (is_device_ptr(vo->iv_beg) || is_device_ptr(vo->iv_end))) return wgbs_set_err("wgbs_pileup_dbam: interval lists must be host arrays");
+    for (size_t k = 0; k + 1 < vo->n_iv; k++)
+        if (vo->iv_beg[k + 1] < vo->iv_end[k] || vo->iv_end[k] < vo->iv_beg[k]) return wgbs_set_err("wgbs_pileup_dbam: intervals must be sorted and non-overlapping");
+    if (vo->max_records > 0xffffffffull) return wgbs_set_err("wgbs_pileup_dbam: max_records too large");
+    uint64_t r0 = 0, r1 = B->nrec;
+    if (vo->refid >= 0) { if (vo->refid >= (int)B->ref_names.size()) return wgbs_set_err("wgbs_pileup_dbam: no such reference"); r0 = B->ref_first[vo->refid]; r1 = B->ref_last[vo->refid]; }
+    const uint64_t nr = r1 - r0;
+    if (nr >= 0xffffffffull) return wgbs_set_err("wgbs_pileup_dbam: too many records in one call");
+    Temps T(ctx);
+    ViewParams V; memset(&V, 0, sizeof V);
+    V.refid = vo->refid; V.min_mapq = vo->min_mapq; V.exclude_flags = vo->exclude_flags; V.include_flags = vo->include_flags; V.beg = vo->beg; V.end = vo->end;
+    V.n_flag_eq = vo->n_flag_eq; for (int k = 0; k < 4; k++) V.flag_eq[k] = vo->flag_eq[k];
+    V.n_iv = vo->n_iv; V.iv_exclude = vo->iv_exclude;
+    if (vo->n_iv) {
+        int64_t *a, *b;
+        RC_TRY(T.alloc(&a, vo->n_iv)); RC_TRY(T.alloc(&b, vo->n_iv));
+        RC_TRY(copy_any(ctx, a, vo->iv_beg, vo->n_iv * 8)); RC_TRY(copy_any(ctx, b, vo->iv_end, vo->n_iv * 8));
+        V.iv_beg = a; V.iv_end = b;
+    }
+    if (vo->read_group) {
+        V.have_rg = 1; V.rg_len = (uint32_t)strlen(vo->read_group);
+        char *g; RC_TRY(T.alloc(&g, (size_t)V.rg_len + 1)); RC_TRY(copy_any(ctx, g, vo->read_group, (size_t)V.rg_len + 1));
+        V.rg = g;
+    }
+    uint32_t *pass, *rank, *has_mm = ctx->d_flags + 24;
+    RC_TRY(T.alloc(&pass, nr + 1)); RC_TRY(T.alloc(&rank, nr + 1));
+    CUDA_TRY(cudaMemsetAsync(has_mm, 0, 4, ctx->stream));
+    uint32_t np32 = 0; uint64_t span[2] = {0, 0};
+    if (nr) {
+        LAUNCH(ctx, bam_pass_k, grid_for(nr, 256), 256, 0, B->data, B->rec_off + r0, nr, V, pass);
+        RC_TRY(scan_u32_u32(ctx, pass, rank, nr));
+        CUDA_TRY(cudaMemcpyAsync(&np32, rank + nr, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(&span[0], B->rec_off + r0, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        span[1] = r1 < B->nrec ? 0 : B->n;                       // end of the window: start of the record after the range, or the stream's end
+        if (r1 < B->nrec) { CUDA_TRY(cudaMemcpyAsync(&span[1], B->rec_off + r1, 8, cudaMemcpyDeviceToHost, ctx->stream)); CUDA_TRY(cudaStreamSynchronize(ctx->stream)); }
+    }
+    const uint32_t n = vo->max_records ? (uint32_t)std::min<uint64_t>(np32, vo->max_records) : np32;
+    const uint64_t base = span[0];
+    if (span[1] - base >= 0xfffffff0ull)
+        return wgbs_set_err("wgbs_pileup_dbam: the records of this view span %.1f GB of the BAM stream (limit 4 GiB per call): restrict the region", (span[1] - base) / 1e9);
+    ReadBatch rb;
+    rb.text = (const char *)B->data + base; rb.nbytes = (uint32_t)(span[1] - base); rb.n = n; rb.bam = 1;
+    RC_TRY(T.alloc(&rb.line_off, n)); RC_TRY(T.alloc(&rb.line_len, n)); RC_TRY(T.alloc(&rb.qn_len, n));
+    RC_TRY(T.alloc(&rb.flag, n)); RC_TRY(T.alloc(&rb.pos, n)); RC_TRY(T.alloc(&rb.pos_hi, n));
+    RC_TRY(T.alloc(&rb.cig_off, n)); RC_TRY(T.alloc(&rb.cig_len, n)); RC_TRY(T.alloc(&rb.seq_off, n)); RC_TRY(T.alloc(&rb.seq_len, n));
+    RC_TRY(T.alloc(&rb.hash_lo, n)); RC_TRY(T.alloc(&rb.hash_hi, n)); RC_TRY(T.alloc(&rb.status, n));
+    uint64_t *rec_abs; RC_TRY(T.alloc(&rec_abs, n));
+    uint32_t mm = 0;
+    if (n) {
+        LAUNCH(ctx, bam_records_k, grid_for(nr, 256), 256, 0, B->data, B->rec_off + r0, nr, pass, rank, (uint32_t)vo->max_records, base, rb, rec_abs, has_mm);
+        CUDA_TRY(cudaMemcpyAsync(&mm, has_mm, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        LAUNCH_CHECK();
+    }
+    if (mm) return 1;                                            // first record has an MM tag: MM/ML mode, text route
+    BamSide side{B->data, rec_abs, (int32_t)B->ref_names.size(), B->d_name_off, B->d_names, B->d_ref_lens};
+    rb.side = &side;
+    RC_TRY(pileup_records(ctx, ix, rb, opts, T, out, stats, mbias));
+    return 0;
+}
+
+// `samtools view ... | [match_maker |] patter ...` without leaving the device.  Direct route (WGBS_DBAM_DIRECT=1, or the
+// default below): BAM records feed the pileup kernels as they are.  Text route: wgbs_dbam_view + wgbs_pileup_sam_mbias (always
+// used for MM/ML data, whose tag parsing is textual).
+#ifndef WGBS_DBAM_DIRECT_DEFAULT
+#define WGBS_DBAM_DIRECT_DEFAULT 0
+#endif
 extern "C" int wgbs_pileup_dbam(wgbs_ctx *ctx, const wgbs_index *ix, const wgbs_dbam *B, const wgbs_view_opts *vo, const wgbs_pileup_opts *opts,
                                 wgbs_pats **out, uint64_t *stats, int32_t *mbias) {
+    RC_TRY(wgbs_ctx_activate(ctx));
+    if (!ix || !B || !vo || !opts || !out) return wgbs_set_err("wgbs_pileup_dbam: null argument");
+    *out = nullptr;
+    const char *e = getenv("WGBS_DBAM_DIRECT");                  // read per call: tests switch routes inside one process
+    const int direct = e ? (e[0] == '1') : (WGBS_DBAM_DIRECT_DEFAULT != 0);
+    if (direct) {
+        const int rc = pileup_dbam_direct(ctx, ix, B, vo, opts, out, stats, mbias);
+        if (rc <= 0) return rc;                                  // done, or failed; 1: the batch needs the text route
+    }
     char *text = nullptr; size_t nb = 0;
     RC_TRY(wgbs_dbam_view(ctx, B, vo, &text, &nb, nullptr));
     if (nb >= 0xffffffffull) { dfree(ctx, text); return wgbs_set_err("wgbs_pileup_dbam: %zu bytes of SAM text in one call (limit 4 GiB): restrict the region", nb); }

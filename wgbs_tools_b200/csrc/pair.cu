@@ -148,7 +148,15 @@ int build_mates(wgbs_ctx *ctx, const ReadBatch &rb, bool paired, Temps &T, uint3
         RC_TRY(T.alloc(&ka, m)); RC_TRY(T.alloc(&va, m));
         uint32_t *k = slow_key, *v = slow_id;
         RC_TRY(radix_sort_pairs(ctx, &k, &v, &ka, &va, m));
-        LAUNCH(ctx, pair_runs_k, grid_for(m, 256), 256, 0, view_of(rb), v, k, m, mate, d_stats);
+        ReadBatchView vw = view_of(rb);
+        if (rb.bam) {
+            // BAM batch: the whole-line order is the order of the SAM lines samtools would print; format just these few records
+            if (!rb.side) return wgbs_set_err("build_mates: BAM batch without its record table");
+            char *stext; uint32_t *soff, *slen;
+            RC_TRY(bam_side_lines(ctx, *rb.side, v, m, n, T, &stext, &soff, &slen));      // v: the m ids (sorted by slot)
+            vw.text = stext; vw.line_off = soff; vw.line_len = slen;          // QNAME starts the line: name_eq keeps working
+        }
+        LAUNCH(ctx, pair_runs_k, grid_for(m, 256), 256, 0, vw, v, k, m, mate, d_stats);
     }
     LAUNCH_CHECK();
     return 0;

@@ -13,6 +13,8 @@
 #include "pileup_dev.cuh"
 
 int build_mates(wgbs_ctx *ctx, const ReadBatch &rb, bool paired, Temps &T, uint32_t **mate_out, unsigned long long *d_stats);
+int pileup_records(wgbs_ctx *ctx, const wgbs_index *ix, const ReadBatch &rb, const wgbs_pileup_opts *opts, Temps &T, wgbs_pats **out,
+                   uint64_t *stats_out, int32_t *mbias_out);
 // np.cu (MM/ML mode)
 int np_measure(wgbs_ctx *ctx, const ReadBatch &rb, const uint32_t *loci, uint32_t nloci, PileupOpts o, uint32_t *r_lo, uint32_t *r_ncand,
                uint32_t *words, unsigned long long *d_stats);
@@ -34,7 +36,7 @@ __global__ void __launch_bounds__(256) pileup_measure_k(ReadBatchView rb, const 
         if (st == REC_INVALID || st == REC_BADINT) inval = 1;
         else if (st == REC_OK) {
             int64_t span = 0;
-            bool ok = cig_validate(rb.text, rb.cig_off[r], rb.cig_off[r] + rb.cig_len[r], rb.seq_len[r], &span);
+            bool ok = rec_cig_validate(rb, r, &span);
             if (!ok) inval = 1;
             else {
                 int64_t pos = rb.pos[r];
@@ -77,9 +79,9 @@ __global__ void __launch_bounds__(256) pileup_call_k(ReadBatchView rb, const uin
         const int64_t pos = rb.pos[r];
         const int flag = rb.flag[r];
         const bool bottom = is_bottom(flag, o.paired);
-        int64_t span; cig_validate(rb.text, rb.cig_off[r], rb.cig_off[r] + rb.cig_len[r], rb.seq_len[r], &span);
-        CigCursor cc; cc.init(rb.text, rb.cig_off[r], rb.cig_len[r]);
-        const char *seq = rb.text + rb.seq_off[r];
+        int64_t span; rec_cig_validate(rb, r, &span);
+        CigCursor cc; cc.init(rb, r);
+        const uint32_t seq_off = rb.seq_off[r];
         uint32_t *wp = pool + off[r];
         int32_t first = -1, last = -1;      // candidate ordinals of the first / last called ('C'/'T') site
         uint32_t w = 0; int32_t nsym = 0;   // symbols emitted since `first`
@@ -99,8 +101,8 @@ __global__ void __launch_bounds__(256) pileup_call_k(ReadBatchView rb, const uin
             const int64_t i = (int64_t)loci[lo + j] - pos;     // offset of the CpG's C in the reference-projected read
             // adj[i] and adj[i+1]
             char c0 = 0, c1 = 0;
-            if (cc.seek(i)) c0 = cc.op == 'M' ? seq[cc.q0 + (i - cc.r0)] : 'N';
-            if (i + 1 < span && cc.seek(i + 1)) c1 = cc.op == 'M' ? seq[cc.q0 + (i + 1 - cc.r0)] : 'N';
+            if (cc.seek(i)) c0 = cc.op == 'M' ? rec_base(rb, seq_off, cc.q0 + (i - cc.r0)) : 'N';
+            if (i + 1 < span && cc.seek(i + 1)) c1 = cc.op == 'M' ? rec_base(rb, seq_off, cc.q0 + (i + 1 - cc.r0)) : 'N';
             uint32_t code = SYM_DOT;
             int64_t jx;
             if (!bottom) {      // OT: C/T at the C position, G must follow (patter.cpp:96-103 is_cpg, shift 0)
@@ -255,6 +257,12 @@ extern "C" int wgbs_pileup_sam_mbias(wgbs_ctx *ctx, const wgbs_index *ix, const 
     // carries an MM tag (the tokenizer checks that and only then records tag spans).
     ReadBatch rb;
     RC_TRY(sam_tokenize(ctx, dtext, nbytes, opts->nanopore ? 1 : -1, T, &rb));
+    return pileup_records(ctx, ix, rb, opts, T, out, stats_out, mbias_out);
+}
+
+// everything after the records exist: mates, calls, merge, filter.  rb: a tokenized SAM text, or a BAM batch (bamdev.cu)
+int pileup_records(wgbs_ctx *ctx, const wgbs_index *ix, const ReadBatch &rb, const wgbs_pileup_opts *opts, Temps &T, wgbs_pats **out,
+                   uint64_t *stats_out, int32_t *mbias_out) {
     const uint32_t n = rb.n;
     unsigned long long *d_stats;
     RC_TRY(T.alloc(&d_stats, ST_N));

@@ -41,11 +41,52 @@ static __device__ bool cig_validate(const char *__restrict__ t, uint32_t p, uint
     return ok;
 }
 
+// ---- BAM flavour (reads.cuh): binary CIGAR = n little-endian words (length << 4 | op), ops "MIDNSHP=X" = 0..8 -----------------
+__device__ __forceinline__ uint32_t bam_ld32(const char *__restrict__ t, uint32_t off) {
+    const uint8_t *p = (const uint8_t *)t + off;
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+// the verdict clean_CIGAR reaches on the TEXT of this CIGAR: no ops ("*") and ops other than M I D N S H = X (P, B, reserved) throw
+static __device__ bool cig_validate_bam(const char *__restrict__ t, uint32_t off, uint32_t n_ops, uint32_t seq_len, int64_t *span_out) {
+    int64_t span = 0, q = 0;
+    bool ok = n_ops != 0;
+    for (uint32_t k = 0; k < n_ops; k++) {
+        const uint32_t v = bam_ld32(t, off + 4 * k), op = v & 15; const int64_t num = (int64_t)(v >> 4);
+        if (op == 0 || op == 7 || op == 8 || op == 1 || op == 4) {
+            if (num > (int64_t)seq_len - q) ok = false;
+            q += num;
+            if (op != 1 && op != 4) span += num;
+        } else if (op == 2 || op == 3) span += num;
+        else if (op == 5) {}
+        else ok = false;
+    }
+    *span_out = span;
+    return ok;
+}
+// one base of SEQ as the character SAM text shows ("=ACMGRSVTWYHKDBN"; SEQ "*" is the one character '*')
+__device__ __forceinline__ char bam_base(const char *__restrict__ t, uint32_t seq_off, int64_t q) {
+    if (seq_off == SEQ_STAR) return '*';
+    const uint32_t b = ((const uint8_t *)t)[seq_off + (uint32_t)(q >> 1)];
+    return "=ACMGRSVTWYHKDBN"[(q & 1) ? (b & 15) : (b >> 4)];
+}
+// per-record front ends used by the kernels: pick the flavour (uniform over the whole grid)
+static __device__ __forceinline__ bool rec_cig_validate(const ReadBatchView &rb, uint32_t r, int64_t *span) {
+    return rb.bam ? cig_validate_bam(rb.text, rb.cig_off[r], rb.cig_len[r], rb.seq_len[r], span)
+                  : cig_validate(rb.text, rb.cig_off[r], rb.cig_off[r] + rb.cig_len[r], rb.seq_len[r], span);
+}
+__device__ __forceinline__ char rec_base(const ReadBatchView &rb, uint32_t seq_off, int64_t q) {
+    return rb.bam ? bam_base(rb.text, seq_off, q) : rb.text[seq_off + q];
+}
+
 struct CigCursor {
     const char *t; uint32_t p, e;
     int64_t r0, q0, len;   // current ref-consuming op covers ref offsets [r0, r0+len); its first read base is q0 (op 'M')
     char op;               // 'M' (M,=,X) or 'D' (D,N); 0 before the first op
-    __device__ void init(const char *text, uint32_t off, uint32_t n) { t = text; p = off; e = off + n; r0 = 0; q0 = 0; len = 0; op = 0; }
+    bool bin;              // BAM flavour: p / e count bytes of 4-byte op words
+    __device__ void init(const char *text, uint32_t off, uint32_t n) { t = text; p = off; e = off + n; r0 = 0; q0 = 0; len = 0; op = 0; bin = false; }
+    __device__ void init(const ReadBatchView &rb, uint32_t r) {
+        t = rb.text; p = rb.cig_off[r]; bin = rb.bam != 0; e = p + (bin ? 4 * rb.cig_len[r] : rb.cig_len[r]); r0 = 0; q0 = 0; len = 0; op = 0;
+    }
     // position on the op covering ref offset x (x must be non-decreasing across calls); false past the end
     __device__ bool seek(int64_t x) {
         while (true) {
@@ -55,7 +96,14 @@ struct CigCursor {
             len = 0; op = 0;
             // next op
             bool found = false;
-            while (p < e) {
+            while (bin && p < e) {
+                const uint32_t v = bam_ld32(t, p), o4 = v & 15; const int64_t num = (int64_t)(v >> 4);
+                p += 4;
+                if (o4 == 0 || o4 == 7 || o4 == 8) { op = 'M'; len = num; found = true; break; }
+                if (o4 == 2 || o4 == 3) { op = 'D'; len = num; found = true; break; }
+                if (o4 == 1 || o4 == 4) q0 += num;
+            }
+            while (!bin && p < e) {
                 int64_t num = 0;
                 while (p < e && t[p] >= '0' && t[p] <= '9') { num = num * 10 + (t[p] - '0'); p++; }
                 if (p >= e) break;

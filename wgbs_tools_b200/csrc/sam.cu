@@ -23,11 +23,6 @@ namespace {
 
 constexpr int NTAB = 11;   // tab ordinals 0..10 delimit the 11 mandatory fields
 
-__device__ __forceinline__ uint64_t fmix64(uint64_t k) {
-    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
-    return k;
-}
-
 // std::stoi semantics on text[s,e): optional blanks, sign, >=1 digit, int range; trailing junk ignored
 __device__ __forceinline__ bool parse_i32(const char *__restrict__ t, uint32_t s, uint32_t e, int32_t *out) {
     while (s < e && (t[s] == ' ' || (t[s] >= 9 && t[s] <= 13))) s++;
@@ -226,13 +221,6 @@ __global__ void __launch_bounds__(NLW_T) nl_scan_warp_k(const char *__restrict__
         uint32_t m = mk[i];
         while (m) { const int b = __ffs(m) - 1; m &= m - 1; if (o < cap) nlpos[o] = (uint32_t)(p0 + (size_t)i * 32 + b); o++; }
     }
-}
-
-// per-(byte, position) mixing summed over the name: independent of alignment
-__device__ __forceinline__ uint64_t name_byte_mix(uint32_t byte, uint32_t pos) {
-    uint64_t x = ((uint64_t)(byte | (pos << 8)) + 1) * 0x9e3779b97f4a7c15ULL;
-    x ^= x >> 29; x *= 0xbf58476d1ce4e5b9ULL; x ^= x >> 32;
-    return x;
 }
 
 // PF: 16-byte chunks fetched together (independent loads in flight per thread) before they are examined one by one
