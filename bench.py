@@ -329,13 +329,15 @@ def bam_device_leg(tmp: str, n_rec: int, sam_bytes: int, peak: float, steps=8, w
     top = sorted(rep.items(), key=lambda kv: -kv[1][1])
     res = {"records": n_rec, "lines_seen": out_n["lines"], "ms_per_step": ms, "reads_per_sec": n_rec / (ms / 1e3), "h2d_bytes_per_step": len(bam_bytes),
            "d2h_bytes_per_step": out_n["n"] + 2 * n_cpg, "sam_text_bytes_equivalent": sam_bytes, "inflated_bytes": out_n["inflated"],
+           "route": "direct (BAM records -> pileup kernels, no SAM text)" if os.environ.get("WGBS_DBAM_DIRECT") == "1" else "text (view -> SAM text -> tokenizer)",
            "identical_to_sam_text_path": bool(same), "breakdown_ms_per_step": {k: round(v[1] / 2, 4) for k, v in top[:12]},
            "mode": "serial: upload, inflate, view, pileup, read back, one batch after the other; wgbs_dbam_open + wgbs_pileup_dbam from pinned host bytes"}
-    infl = rep.get("bgzf_inflate_k")
+    infl_name = next((k for k in rep if k.startswith("bgzf_inflate")), None)      # bgzf_inflate_k<2>, bgzf_inflate_team_k<G>
+    infl = rep.get(infl_name)
     if infl:
         sec = infl[1] / infl[0] / 1e3
         ab = len(bam_bytes) + out_n["inflated"]          # algorithmic bytes: compressed bytes read + inflated bytes written
-        res["roofline"] = {"kernel": "bgzf_inflate_k", "bound": "latency of the serial Huffman walk per block; reported against hbm", "achieved": ab / sec / 1e9,
+        res["roofline"] = {"kernel": infl_name, "bound": "latency of the serial Huffman walk per block; reported against hbm", "achieved": ab / sec / 1e9,
                            "peak": peak, "unit": "GB/s", "frac": ab / sec / 1e9 / peak, "algorithmic_bytes": ab, "avg_launch_ms": sec * 1e3}
     log(f"[bench] bam_device: {ms:.3f} ms/step, {res['reads_per_sec'] / 1e6:.1f} M reads/s, identical={same}")
     print(json.dumps(res), flush=True)
@@ -605,11 +607,20 @@ def main():
                 open(os.path.join(tmp, "ref.beta"), "wb").write(h_beta.numpy().tobytes())
                 open(os.path.join(tmp, "batch.bam"), "wb").write(bam_bytes)
                 np.save(os.path.join(tmp, "loci.npy"), g.loci)
-                for key, env_add in [("bam_device", {})] + ([(f"bam_device_inflate{v}", {"WGBS_INFLATE": v}) for v in os.environ.get("WGBS_BENCH_INFLATE_VARIANTS", "").split(",") if v]):
-                    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--bam-leg", tmp, "--reads", str(n_rec), "--sam-bytes", str(text_bytes),
-                                        "--peak", str(roof["peak"] if roof else 6650.0)], stdout=subprocess.PIPE, timeout=300, env={**os.environ, **env_add})
-                    line = [l for l in r.stdout.decode(errors="replace").splitlines() if l.startswith("{")]
-                    extra[key] = json.loads(line[-1]) if line else {"error": f"child exited {r.returncode} without a result"}
+                # text route (view -> SAM text -> tokenizer) and direct route (BAM records feed the pileup kernels in place)
+                legs = [("bam_device", {"WGBS_DBAM_DIRECT": "0"}), ("bam_device_direct", {"WGBS_DBAM_DIRECT": "1"})]
+                # decoder variants (teams of G lanes per BGZF block instead of a whole warp), on the direct route
+                variants = os.environ.get("WGBS_BENCH_INFLATE_VARIANTS", "g8,g16").split(",")
+                legs += [(f"bam_device_direct_inflate_{v}", {"WGBS_DBAM_DIRECT": "1", "WGBS_INFLATE": v}) for v in variants if v]
+                for key, env_add in legs:
+                    try:                                     # one leg failing (or running into its time limit) must not cost the others
+                        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--bam-leg", tmp, "--reads", str(n_rec), "--sam-bytes", str(text_bytes),
+                                            "--peak", str(roof["peak"] if roof else 6650.0)], stdout=subprocess.PIPE, timeout=150, env={**os.environ, **env_add})
+                        line = [l for l in r.stdout.decode(errors="replace").splitlines() if l.startswith("{")]
+                        extra[key] = json.loads(line[-1]) if line else {"error": f"child exited {r.returncode} without a result"}
+                    except Exception as e:
+                        log(f"[bench] {key} leg failed: {e!r}")
+                        extra[key] = {"error": repr(e)}
             except Exception as e:
                 log(f"[bench] bam_device leg failed: {e!r}")
                 extra["bam_device"] = {"error": repr(e)}

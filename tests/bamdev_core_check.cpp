@@ -27,28 +27,33 @@
 
 using namespace dflate;
 
-// ---- 32 lanes in lock step: one std::thread per lane, every collective is a barrier -----------------------------------
-struct EmuShared {
-    std::barrier<> bar{32};
-    uint32_t slot[32];
+// ---- NL lanes in lock step: one std::thread per lane, every collective is a barrier ------------------------------------
+// NL = 32: a warp (dflate::WarpLanes); NL = 4, 8, 16: a team of a warp's lanes (dflate::SubWarp<NL>)
+template <int NL>
+struct EmuSharedN {
+    std::barrier<> bar{NL};
+    uint32_t slot[NL];
 };
-struct EmuLanes {
-    static constexpr int N = 32;
-    int lane; EmuShared *sh;
+template <int NL>
+struct EmuLanesN {
+    static constexpr int N = NL;
+    int lane; EmuSharedN<NL> *sh;
     int id() const { return lane; }
     void sync() const { sh->bar.arrive_and_wait(); }
     uint32_t shfl(uint32_t v, int src) const { sh->slot[lane] = v; sh->bar.arrive_and_wait(); uint32_t r = sh->slot[src]; sh->bar.arrive_and_wait(); return r; }
     uint32_t ballot(bool p) const {
         sh->slot[lane] = p ? 1u : 0u; sh->bar.arrive_and_wait();
-        uint32_t m = 0; for (int i = 0; i < 32; i++) m |= sh->slot[i] << i;
+        uint32_t m = 0; for (int i = 0; i < NL; i++) m |= sh->slot[i] << i;
         sh->bar.arrive_and_wait(); return m;
     }
     uint32_t exscan(uint32_t v, uint32_t *total, uint32_t) const {
         sh->slot[lane] = v; sh->bar.arrive_and_wait();
-        uint32_t pre = 0, tot = 0; for (int i = 0; i < 32; i++) { if (i < lane) pre += sh->slot[i]; tot += sh->slot[i]; }
+        uint32_t pre = 0, tot = 0; for (int i = 0; i < NL; i++) { if (i < lane) pre += sh->slot[i]; tot += sh->slot[i]; }
         sh->bar.arrive_and_wait(); *total = tot; return pre;
     }
 };
+using EmuShared = EmuSharedN<32>;
+using EmuLanes = EmuLanesN<32>;
 
 static std::vector<uint8_t> slurp(const char *path) {
     FILE *f = fopen(path, "rb"); if (!f) { perror(path); exit(2); }
@@ -102,17 +107,19 @@ static int emu_warp(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usize
     for (int l = 1; l < 32; l++) if (rcs[l] != rcs[0]) { fprintf(stderr, "lanes disagree on rc\n"); exit(4); }
     return rcs[0];
 }
-static int emu_warp2(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usize, uint32_t want_crc) {
-    static EmuShared sh; Scratch S; Ring R; int rcs[32];
+template <int NL>
+static int emu_team2(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usize, uint32_t want_crc) {
+    static EmuSharedN<NL> sh; Scratch S; Ring R; int rcs[NL];
     std::vector<std::thread> th;
-    for (int l = 0; l < 32; l++) th.emplace_back([&, l]() {
-        Inflater2<EmuLanes> I; I.lanes = EmuLanes{l, &sh}; I.S = &S; I.R = &R; I.dst = dst; I.dst_len = usize; rcs[l] = I.run(src, n);
+    for (int l = 0; l < NL; l++) th.emplace_back([&, l]() {
+        Inflater2<EmuLanesN<NL>> I; I.lanes = EmuLanesN<NL>{l, &sh}; I.S = &S; I.R = &R; I.dst = dst; I.dst_len = usize; rcs[l] = I.run(src, n);
         if (rcs[l] == OK) { I.lanes.sync(); if (crc32_block(I.lanes, dst, usize, g_crc_table) != want_crc) rcs[l] = E_CRC; }
     });
     for (auto &t : th) t.join();
-    for (int l = 1; l < 32; l++) if (rcs[l] != rcs[0]) { fprintf(stderr, "lanes disagree on rc (v2)\n"); exit(4); }
+    for (int l = 1; l < NL; l++) if (rcs[l] != rcs[0]) { fprintf(stderr, "lanes disagree on rc (v2, %d lanes)\n", NL); exit(4); }
     return rcs[0];
 }
+static int emu_warp2(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usize, uint32_t want_crc) { return emu_team2<32>(src, n, dst, usize, want_crc); }
 
 static int cmd_inflate(const char *path, int emu_blocks) {
     auto f = slurp(path); uint64_t ut; auto blocks = scan_blocks(f, &ut);
@@ -130,6 +137,14 @@ static int cmd_inflate(const char *path, int emu_blocks) {
         if ((int)i < emu_blocks) {
             const int r2 = emu_warp(src, n, e.data(), b.usize, want); ok = ok && r2 == r1 && (r1 != 0 || !memcmp(a.data(), e.data(), b.usize)); nemu++;
             std::vector<uint8_t> e2(b.usize + 1); const int r4 = emu_warp2(src, n, e2.data(), b.usize, want); ok = ok && (rz == 0) == (r4 == 0) && (rz != 0 || !memcmp(a.data(), e2.data(), b.usize));
+            // the team decoders (bgzf_inflate_team_k<G>): the same Inflater2 with batches of 4 / 8 / 16 symbols
+            for (int g : {4, 8, 16}) {
+                std::vector<uint8_t> eg(b.usize + 1);
+                const int rg = g == 4 ? emu_team2<4>(src, n, eg.data(), b.usize, want) : g == 8 ? emu_team2<8>(src, n, eg.data(), b.usize, want) : emu_team2<16>(src, n, eg.data(), b.usize, want);
+                const bool okg = rg == r4 && (rz != 0 || !memcmp(a.data(), eg.data(), b.usize));
+                if (!okg) fprintf(stderr, "block %zu: team of %d lanes: rc %d (warp %d)\n", i, g, rg, r4);
+                ok = ok && okg;
+            }
         }
         if (!ok) { nbad++; fprintf(stderr, "block %zu: zlib %d core %d\n", i, rz, r1); }
         bytes += b.usize;

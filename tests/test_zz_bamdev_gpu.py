@@ -48,8 +48,24 @@ def _block(data: bytes, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, mem=8) -> byt
 def test_bgzf_inflate_kernel_matches_zlib(ctx, sample):
     """bgzf_inflate_k alone (wgbs_bgzf_inflate): stored / fixed / dynamic blocks, long codes, overlapping matches, several
     deflate blocks per BGZF block, empty blocks, incompressible bytes -- output == zlib's, byte for byte"""
+    _inflate_checks(ctx, sample[1])
+
+
+@pytest.mark.staged
+@pytest.mark.parametrize("variant", ["g16", "g8", "g4"])
+def test_bgzf_inflate_team_kernels_match_zlib(ctx, sample, monkeypatch, variant):
+    """bgzf_inflate_team_k<G> (teams of G lanes per BGZF block, WGBS_INFLATE=gG): the same checks; a corrupt block is reported
+    with its number like the warp-per-block kernel does"""
+    monkeypatch.setenv("WGBS_INFLATE", variant)
+    _inflate_checks(ctx, sample[1])
+    from wgbs_tools_b200.patio import bgzf_compress
+    bad = bytearray(bgzf_compress(sample[1][:200_000])); bad[18 + 100] ^= 0x55          # inside the first block's deflate payload
+    with pytest.raises(Exception, match="inflate failed in BGZF block 0"):
+        ctx.bgzf_inflate(bytes(bad)).free()
+
+
+def _inflate_checks(ctx, s):
     from wgbs_tools_b200.patio import BGZF_EOF, bgzf_compress
-    _, s, _ = sample
     rng = np.random.default_rng(1)
     datas = [s[:60000], s[60000:125000], b"", b"a", b"ab" * 30000, b"\0" * 65000, rng.integers(0, 256, 50000, dtype=np.uint8).tobytes(),
              rng.integers(0, 4, 65000, dtype=np.uint8).tobytes(), bytes(range(256)) * 200, s[200000:260000]]

@@ -75,6 +75,39 @@ __global__ void __launch_bounds__(INFL_WARPS * 32, V == 2 ? 8 : 6) bgzf_inflate_
     if (rc != dflate::OK && (threadIdx.x & 31) == 0) atomicMin(err, ((unsigned long long)b << 8) | (unsigned long long)(uint8_t)(-rc));
 }
 
+// Teams of G lanes per BGZF block (dflate::SubWarp): 32 / G blocks share one warp's instruction stream.  The warp-per-block
+// kernel above is bound by instruction issue (ncu: issue slots 65 % busy with 28 warps per SM, every warp executing the
+// same ~40 instructions per symbol for its own block on 32 lanes that all compute the same thing); here the same
+// instructions serve 32 / G blocks at once wherever the teams of a warp run in step, and a batch is G symbols.
+// Per team: Scratch + Ring in dynamic shared memory (5.9 KB), so an SM holds the same ~32 blocks in flight with a quarter
+// (G = 8) of the warps.  Selected with WGBS_INFLATE=g4|g8|g16.
+constexpr int TEAM_THREADS = 64;
+template <int G>
+__global__ void __launch_bounds__(TEAM_THREADS) bgzf_inflate_team_k(const uint8_t *__restrict__ comp, const BgzfBlock *__restrict__ blocks, uint32_t nblocks,
+                                                                     uint8_t *out, unsigned long long *__restrict__ err) {
+    constexpr int TEAMS = TEAM_THREADS / G;
+    extern __shared__ __align__(16) unsigned char team_smem[];
+    dflate::Scratch *S = reinterpret_cast<dflate::Scratch *>(team_smem);
+    dflate::Ring *RG = reinterpret_cast<dflate::Ring *>(team_smem + TEAMS * sizeof(dflate::Scratch));
+    uint32_t *crc_table = reinterpret_cast<uint32_t *>(team_smem + TEAMS * (sizeof(dflate::Scratch) + sizeof(dflate::Ring)));
+    for (uint32_t i = threadIdx.x; i < 256; i += TEAM_THREADS) crc_table[i] = dflate::crc_table_entry(i);
+    __syncthreads();
+    const uint32_t t = threadIdx.x / G, b = blockIdx.x * TEAMS + t;
+    if (b >= nblocks) return;                       // whole teams leave together (every barrier below is team-wide only)
+    const BgzfBlock B = blocks[b];
+    dflate::Inflater2<dflate::SubWarp<G>> I;
+    I.S = &S[t]; I.R = &RG[t]; I.dst = out + B.uoff; I.dst_len = B.usize;
+    int rc = I.run(comp + B.coff, B.clen);
+    if (rc == dflate::OK) {
+        I.lanes.sync();
+        if (dflate::crc32_block(dflate::SubWarp<G>(), out + B.uoff, B.usize, crc_table) != B.crc) rc = dflate::E_CRC;
+    }
+    if (rc != dflate::OK && (threadIdx.x & (G - 1)) == 0) atomicMin(err, ((unsigned long long)b << 8) | (unsigned long long)(uint8_t)(-rc));
+}
+template <int G>
+static size_t team_smem_bytes() { return (size_t)(TEAM_THREADS / G) * (sizeof(dflate::Scratch) + sizeof(dflate::Ring)) + 256 * sizeof(uint32_t); }
+static_assert(sizeof(dflate::Scratch) % 4 == 0 && sizeof(dflate::Ring) % 4 == 0, "team shared-memory layout");
+
 __global__ void __launch_bounds__(128) bam_guess_k(const uint8_t *__restrict__ data, uint64_t n, uint64_t p0, uint64_t nseg, int32_t n_ref,
                                                     uint64_t *__restrict__ entry) {
     const uint64_t s = (uint64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -279,11 +312,24 @@ int bgzf_inflate_device(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, const ch
     unsigned long long herr = 0;
     cudaError_t e = cudaMemsetAsync(d_err, 0xff, 8, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(data + uoff, 0, 16, ctx->stream);
-    static const int variant = [] { const char *v = getenv("WGBS_INFLATE"); return (v && v[0] == '1') ? 1 : (v && v[0] == '2') ? 2 : WGBS_INFLATE_DEFAULT; }();
+    // read per call (a getenv is nothing next to an inflate): tests and bench legs switch decoders inside one process
+    const char *ev = getenv("WGBS_INFLATE");
+    const int variant = !ev ? WGBS_INFLATE_DEFAULT : ev[0] == '1' ? 1 : ev[0] == '2' ? 2 : (ev[0] == 'g' && atoi(ev + 1) > 0) ? -atoi(ev + 1) : WGBS_INFLATE_DEFAULT;
+    if (variant < 0 && variant != -4 && variant != -8 && variant != -16) { dfree(ctx, data); return wgbs_set_err("%s: WGBS_INFLATE=%s (teams of 4, 8 or 16 lanes: g4 | g8 | g16)", who, ev); }
     if (e == cudaSuccess && !blocks.empty()) {
-        if (variant == 2) LAUNCH(ctx, bgzf_inflate_k<2>, grid_for(blocks.size(), INFL_WARPS), INFL_WARPS * 32, 0, d_comp, d_blocks, (uint32_t)blocks.size(), data, d_err);
-        else LAUNCH(ctx, bgzf_inflate_k<1>, grid_for(blocks.size(), INFL_WARPS), INFL_WARPS * 32, 0, d_comp, d_blocks, (uint32_t)blocks.size(), data, d_err);
-        e = cudaGetLastError();
+        const uint32_t nb = (uint32_t)blocks.size();
+        if (variant == 2) LAUNCH(ctx, bgzf_inflate_k<2>, grid_for(nb, INFL_WARPS), INFL_WARPS * 32, 0, d_comp, d_blocks, nb, data, d_err);
+        else if (variant == 1) LAUNCH(ctx, bgzf_inflate_k<1>, grid_for(nb, INFL_WARPS), INFL_WARPS * 32, 0, d_comp, d_blocks, nb, data, d_err);
+        else {
+#define TEAM_LAUNCH(G)                                                                                                                             \
+            do {                                                                                                                                       \
+                e = cudaFuncSetAttribute(bgzf_inflate_team_k<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)team_smem_bytes<G>());              \
+                if (e == cudaSuccess) LAUNCH(ctx, bgzf_inflate_team_k<G>, grid_for(nb, TEAM_THREADS / G), TEAM_THREADS, team_smem_bytes<G>(), d_comp, d_blocks, nb, data, d_err); \
+            } while (0)
+            if (variant == -4) TEAM_LAUNCH(4); else if (variant == -8) TEAM_LAUNCH(8); else TEAM_LAUNCH(16);
+#undef TEAM_LAUNCH
+        }
+        if (e == cudaSuccess) e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(&herr, d_err, 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

@@ -61,6 +61,32 @@ struct WarpLanes {
         return x - v;
     }
 };
+// G consecutive lanes of a warp (G = 4, 8, 16) as an independent team WITH collectives: 32 / G teams share one warp's
+// instruction stream, each on its own item.  Every collective names only the team's own lanes in its mask, so teams may sit
+// at different points of the program (independent thread scheduling); where they happen to be at the same point, one
+// issued instruction serves all of them -- that is the point: the decoder's per-symbol work is uniform over the lanes of a
+// team, so a whole warp per BGZF block spends 32 lanes on what G do just as well.
+template <int G>
+struct SubWarp {
+    static_assert(G == 4 || G == 8 || G == 16 || G == 32, "team size");
+    static constexpr int N = G;
+    __device__ __forceinline__ unsigned lane() const { return threadIdx.x & 31u; }
+    __device__ __forceinline__ unsigned shift() const { return lane() & ~(unsigned)(G - 1); }
+    __device__ __forceinline__ unsigned mask() const { return (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u)) << shift(); }
+    __device__ __forceinline__ int id() const { return (int)(threadIdx.x & (G - 1)); }
+    __device__ __forceinline__ void sync() const { __syncwarp(mask()); }
+    __device__ __forceinline__ uint32_t shfl(uint32_t v, int src) const { return __shfl_sync(mask(), v, src, G); }
+    __device__ __forceinline__ uint32_t ballot(bool p) const { return (__ballot_sync(mask(), p) >> shift()) & (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u)); }
+    __device__ __forceinline__ uint32_t exscan(uint32_t v, uint32_t *total, uint32_t) const {
+        uint32_t x = v;
+        const int l = id();
+        const unsigned m = mask();
+#pragma unroll
+        for (int d = 1; d < G; d <<= 1) { uint32_t y = __shfl_up_sync(m, x, d, G); if (l >= d) x += y; }
+        *total = __shfl_sync(m, x, G - 1, G);
+        return x - v;
+    }
+};
 // G consecutive lanes working on one item (no collectives: only id() / N are meaningful)
 template <int G>
 struct LaneGroup {
