@@ -343,6 +343,82 @@ def bam_device_leg(tmp: str, n_rec: int, sam_bytes: int, peak: float, steps=8, w
     print(json.dumps(res), flush=True)
 
 
+def stream_leg(tmp: str, n_rec: int, steps=12, warmup=3):
+    """(child process of the bench) The device-resident step of the main line, with S batches in flight on S streams: one
+    Context (own stream, own scratch) per host thread, the way bam2pat has several chromosomes in flight on one GPU.  A single
+    stream leaves the GPU idle while the host reads back sizes between kernels (~10 round trips per step) and runs kernels of
+    one wave or less back to back; a second stream fills those gaps.  S = 1 repeats the main line's `value` as the control.
+    Timed on the device: a start event every worker stream waits for, an end event that waits for every worker stream."""
+    import ctypes as C
+    import torch
+    from wgbs_tools_b200._lib import PileupOpts, check, lib
+    from wgbs_tools_b200.api import Context
+    sam = open(os.path.join(tmp, "batch.sam"), "rb").read()
+    ref_text = open(os.path.join(tmp, "ref.pat"), "rb").read(); ref_beta = open(os.path.join(tmp, "ref.beta"), "rb").read()
+    loci = np.load(os.path.join(tmp, "loci.npy"))
+    n_cpg = int(loci.size); text_bytes = len(sam)
+    torch.cuda.set_device(0)
+    main_stream = torch.cuda.Stream(); torch.cuda.set_stream(main_stream)
+    ctx0 = Context(0, stream=main_stream.cuda_stream)
+    ix = ctx0.load_index(loci, 1)
+    d_sam = torch.frombuffer(bytearray(sam), dtype=torch.uint8).cuda()
+    torch.cuda.synchronize()
+    out = {"records": n_rec, "steps": steps, "by_streams": {}}
+    for S in (1, 2, 3, 4):
+        streams = [torch.cuda.Stream() for _ in range(S)]
+        ctxs = [Context(0, stream=st.cuda_stream) for st in streams]
+        mcs = [torch.zeros((n_cpg, 2), dtype=torch.int32, device="cuda") for _ in range(S)]
+        texts = [torch.empty(text_bytes // 4, dtype=torch.uint8, device="cuda") for _ in range(S)]
+        betas = [torch.empty((n_cpg, 2), dtype=torch.uint8, device="cuda") for _ in range(S)]
+        sizes = [0] * S; errs = []
+
+        def work(w: int, k: int):
+            try:
+                torch.cuda.set_device(0)
+                ctx = ctxs[w]
+                for _ in range(k):
+                    o = PileupOpts(1, 0, -1, 0, 0, 0.67, b"C")
+                    h = C.c_void_p(); st = (C.c_uint64 * 8)()
+                    check(lib.wgbs_pileup_sam(ctx.h, ix.h, d_sam.data_ptr(), text_bytes, C.addressof(o), C.byref(h), C.addressof(st)))
+                    check(lib.wgbs_pat2beta(ctx.h, h, 1, n_cpg + 1, mcs[w].data_ptr(), 1))
+                    check(lib.wgbs_collapse(ctx.h, h))
+                    n = C.c_size_t()
+                    check(lib.wgbs_pats_format(ctx.h, h, CHR.encode(), texts[w].data_ptr(), texts[w].numel(), C.byref(n)))
+                    check(lib.wgbs_trim(ctx.h, mcs[w].data_ptr(), n_cpg, 8, betas[w].data_ptr()))
+                    lib.wgbs_pats_free(ctx.h, h)
+                    sizes[w] = n.value
+            except Exception as e:                      # surfaces in the parent thread
+                errs.append(repr(e))
+
+        def run(total_steps: int):
+            share = [total_steps // S + (1 if w < total_steps % S else 0) for w in range(S)]
+            th = [threading.Thread(target=work, args=(w, share[w])) for w in range(S)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+
+        run(warmup * S)
+        torch.cuda.synchronize()
+        same = all(texts[w][:sizes[w]].cpu().numpy().tobytes() == ref_text and betas[w].cpu().numpy().tobytes() == ref_beta for w in range(S)) and not errs
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main_stream)
+        for st in streams:
+            st.wait_event(e0)
+        run(steps)
+        for st in streams:
+            ev = torch.cuda.Event(); ev.record(st); main_stream.wait_event(ev)
+        e1.record(main_stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out["by_streams"][str(S)] = {"ms_per_step": ms, "reads_per_sec": n_rec / (ms / 1e3), "identical_outputs": bool(same), "errors": errs[:3]}
+        log(f"[bench] streams={S}: {ms:.3f} ms/step, {n_rec / (ms / 1e3) / 1e6:.1f} M reads/s, identical={same}")
+        for c in ctxs:
+            c.close()
+        del mcs, texts, betas
+    print(json.dumps(out), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -353,11 +429,14 @@ def main():
     ap.add_argument("--no-extras", dest="no_extras", action="store_true", help="skip the pat2beta / homog / segment side measurements")
     ap.add_argument("--only-bam-extra", dest="only_bam", action="store_true", help="of the side measurements run only the device-BAM leg")
     ap.add_argument("--bam-leg", dest="bam_leg", help=argparse.SUPPRESS)       # internal: child process of the device-BAM leg
+    ap.add_argument("--stream-leg", dest="stream_leg", help=argparse.SUPPRESS)  # internal: child process of the batches-in-flight leg
     ap.add_argument("--sam-bytes", dest="sam_bytes", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--peak", type=float, default=6650.0, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.bam_leg:
         return bam_device_leg(args.bam_leg, args.reads, args.sam_bytes, args.peak)
+    if args.stream_leg:
+        return stream_leg(args.stream_leg, args.reads)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     workload = f"bam2pat synthetic 150bp PE WGBS, {args.reads:,} records per GPU, {CHR} index ({N_CPG:,} CpGs)"
@@ -607,6 +686,14 @@ def main():
                 open(os.path.join(tmp, "ref.beta"), "wb").write(h_beta.numpy().tobytes())
                 open(os.path.join(tmp, "batch.bam"), "wb").write(bam_bytes)
                 np.save(os.path.join(tmp, "loci.npy"), g.loci)
+                open(os.path.join(tmp, "batch.sam"), "wb").write(sam)
+                try:                                         # S batches in flight on S streams (device-resident step)
+                    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--stream-leg", tmp, "--reads", str(n_rec)], stdout=subprocess.PIPE, timeout=150)
+                    line = [l for l in r.stdout.decode(errors="replace").splitlines() if l.startswith("{")]
+                    extra["batches_in_flight"] = json.loads(line[-1]) if line else {"error": f"child exited {r.returncode} without a result"}
+                except Exception as e:
+                    log(f"[bench] batches_in_flight leg failed: {e!r}")
+                    extra["batches_in_flight"] = {"error": repr(e)}
                 # text route (view -> SAM text -> tokenizer) and direct route (BAM records feed the pileup kernels in place)
                 legs = [("bam_device", {"WGBS_DBAM_DIRECT": "0"}), ("bam_device_direct", {"WGBS_DBAM_DIRECT": "1"})]
                 # decoder variants (teams of G lanes per BGZF block instead of a whole warp), on the direct route
