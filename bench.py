@@ -271,10 +271,13 @@ def extras(ctx, torch, peak, sam_for_bam=b""):
     return out
 
 
-def bam_device_leg(tmp: str, n_rec: int, sam_bytes: int, peak: float, steps=8, warmup=3):
+def bam_device_leg(tmp: str, n_rec: int, sam_bytes: int, peak: float, configs: str, steps=8, warmup=3):
     """(child process of the bench) The same batch end to end from the COMPRESSED BAM bytes in pinned host memory (SURVEY 8f-1:
-    no SAM-text detour over PCIe): upload + one-warp-per-block BGZF inflate + record table + view + pileup + pat2beta + collapse
-    + pat text and .beta read back.  Outputs are compared with the SAM-text path's (files written by the parent)."""
+    no SAM-text detour over PCIe): upload + BGZF inflate + record table + view + pileup + pat2beta + collapse + pat text and .beta
+    read back.  Outputs are compared with the SAM-text path's (files written by the parent).
+    configs: "key:direct:inflate:streams,..." -- route (WGBS_DBAM_DIRECT), decoder (WGBS_INFLATE, empty = default) and the number of
+    batches in flight (S Contexts with their own streams on S host threads: the upload of one batch overlaps the kernels of
+    another); one JSON line per configuration, printed as soon as it is measured."""
     import ctypes as C
     import torch
     from wgbs_tools_b200._lib import PileupOpts, ViewOpts, check, lib
@@ -284,63 +287,114 @@ def bam_device_leg(tmp: str, n_rec: int, sam_bytes: int, peak: float, steps=8, w
     loci = np.load(os.path.join(tmp, "loci.npy"))
     n_cpg = int(loci.size)
     torch.cuda.set_device(0)
-    stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
-    ctx = Context(0, stream=stream.cuda_stream)
-    ix = ctx.load_index(loci, 1)
+    main_stream = torch.cuda.Stream(); torch.cuda.set_stream(main_stream)
+    ctx0 = Context(0, stream=main_stream.cuda_stream)
+    ix = ctx0.load_index(loci, 1)
     h_bam = torch.frombuffer(bytearray(bam_bytes), dtype=torch.uint8).pin_memory()
-    h_text = torch.empty(max(len(ref_text) * 2, 1 << 20), dtype=torch.uint8).pin_memory()
-    h_beta = torch.empty((n_cpg, 2), dtype=torch.uint8).pin_memory()
-    mc = torch.zeros((n_cpg, 2), dtype=torch.int32, device="cuda")
-    out_n = {}
-
-    def step():
-        B = C.c_void_p()
-        check(lib.wgbs_dbam_open(ctx.h, h_bam.data_ptr(), h_bam.numel(), C.byref(B)))
-        out_n["inflated"] = int(lib.wgbs_dbam_inflated_bytes(B))
-        vo = ViewOpts(); vo.refid = 0
-        o = PileupOpts(1, 0, -1, 0, 0, 0.67, b"C")
-        h = C.c_void_p(); st = (C.c_uint64 * 8)()
-        check(lib.wgbs_pileup_dbam(ctx.h, ix.h, B, C.byref(vo), C.addressof(o), C.byref(h), C.addressof(st), None))
-        lib.wgbs_dbam_close(ctx.h, B)
-        check(lib.wgbs_pat2beta(ctx.h, h, 1, n_cpg + 1, mc.data_ptr(), 1))
-        check(lib.wgbs_collapse(ctx.h, h))
-        n = C.c_size_t()
-        check(lib.wgbs_pats_format(ctx.h, h, CHR.encode(), h_text.data_ptr(), h_text.numel(), C.byref(n)))
-        check(lib.wgbs_trim(ctx.h, mc.data_ptr(), n_cpg, 8, h_beta.data_ptr()))
-        lib.wgbs_pats_free(ctx.h, h)
-        out_n.update(n=n.value, lines=int(st[0]))
-
-    for _ in range(warmup):
-        step()
     torch.cuda.synchronize()
-    same = h_text[:out_n["n"]].numpy().tobytes() == ref_text and h_beta.numpy().tobytes() == ref_beta
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(steps):
-        step()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    ctx.prof(True)
-    for _ in range(2):
-        step()
-    rep = ctx.prof_report()
-    ctx.prof(False)
-    top = sorted(rep.items(), key=lambda kv: -kv[1][1])
-    res = {"records": n_rec, "lines_seen": out_n["lines"], "ms_per_step": ms, "reads_per_sec": n_rec / (ms / 1e3), "h2d_bytes_per_step": len(bam_bytes),
-           "d2h_bytes_per_step": out_n["n"] + 2 * n_cpg, "sam_text_bytes_equivalent": sam_bytes, "inflated_bytes": out_n["inflated"],
-           "route": "direct (BAM records -> pileup kernels, no SAM text)" if os.environ.get("WGBS_DBAM_DIRECT") == "1" else "text (view -> SAM text -> tokenizer)",
-           "identical_to_sam_text_path": bool(same), "breakdown_ms_per_step": {k: round(v[1] / 2, 4) for k, v in top[:12]},
-           "mode": "serial: upload, inflate, view, pileup, read back, one batch after the other; wgbs_dbam_open + wgbs_pileup_dbam from pinned host bytes"}
-    infl_name = next((k for k in rep if k.startswith("bgzf_inflate")), None)      # bgzf_inflate_k<2>, bgzf_inflate_team_k<G>
-    infl = rep.get(infl_name)
-    if infl:
-        sec = infl[1] / infl[0] / 1e3
-        ab = len(bam_bytes) + out_n["inflated"]          # algorithmic bytes: compressed bytes read + inflated bytes written
-        res["roofline"] = {"kernel": infl_name, "bound": "latency of the serial Huffman walk per block; reported against hbm", "achieved": ab / sec / 1e9,
-                           "peak": peak, "unit": "GB/s", "frac": ab / sec / 1e9 / peak, "algorithmic_bytes": ab, "avg_launch_ms": sec * 1e3}
-    log(f"[bench] bam_device: {ms:.3f} ms/step, {res['reads_per_sec'] / 1e6:.1f} M reads/s, identical={same}")
-    print(json.dumps(res), flush=True)
+
+    def run_config(S: int) -> dict:
+        streams = [main_stream] if S == 1 else [torch.cuda.Stream() for _ in range(S)]
+        ctxs = [ctx0] if S == 1 else [Context(0, stream=st.cuda_stream) for st in streams]
+        h_text = [torch.empty(max(len(ref_text) * 2, 1 << 20), dtype=torch.uint8).pin_memory() for _ in range(S)]
+        h_beta = [torch.empty((n_cpg, 2), dtype=torch.uint8).pin_memory() for _ in range(S)]
+        mc = [torch.zeros((n_cpg, 2), dtype=torch.int32, device="cuda") for _ in range(S)]
+        out_n = [{} for _ in range(S)]; errs = []
+        torch.cuda.synchronize()
+
+        def step(w: int):
+            ctx = ctxs[w]
+            B = C.c_void_p()
+            check(lib.wgbs_dbam_open(ctx.h, h_bam.data_ptr(), h_bam.numel(), C.byref(B)))
+            out_n[w]["inflated"] = int(lib.wgbs_dbam_inflated_bytes(B))
+            vo = ViewOpts(); vo.refid = 0
+            o = PileupOpts(1, 0, -1, 0, 0, 0.67, b"C")
+            h = C.c_void_p(); st = (C.c_uint64 * 8)()
+            check(lib.wgbs_pileup_dbam(ctx.h, ix.h, B, C.byref(vo), C.addressof(o), C.byref(h), C.addressof(st), None))
+            lib.wgbs_dbam_close(ctx.h, B)
+            check(lib.wgbs_pat2beta(ctx.h, h, 1, n_cpg + 1, mc[w].data_ptr(), 1))
+            check(lib.wgbs_collapse(ctx.h, h))
+            n = C.c_size_t()
+            check(lib.wgbs_pats_format(ctx.h, h, CHR.encode(), h_text[w].data_ptr(), h_text[w].numel(), C.byref(n)))
+            check(lib.wgbs_trim(ctx.h, mc[w].data_ptr(), n_cpg, 8, h_beta[w].data_ptr()))
+            lib.wgbs_pats_free(ctx.h, h)
+            out_n[w].update(n=n.value, lines=int(st[0]))
+
+        def work(w: int, k: int):
+            try:
+                torch.cuda.set_device(0)
+                for _ in range(k):
+                    step(w)
+            except Exception as e:
+                errs.append(repr(e))
+
+        def run(total: int):
+            if S == 1:
+                return work(0, total)
+            th = [threading.Thread(target=work, args=(w, total // S + (1 if w < total % S else 0))) for w in range(S)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+
+        run(warmup * S)
+        torch.cuda.synchronize()
+        if errs:
+            return {"error": errs[0]}
+        same = all(h_text[w][:out_n[w]["n"]].numpy().tobytes() == ref_text and h_beta[w].numpy().tobytes() == ref_beta for w in range(S))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main_stream)
+        for st in streams:
+            if st is not main_stream:
+                st.wait_event(e0)
+        run(steps)
+        for st in streams:
+            if st is not main_stream:
+                ev = torch.cuda.Event(); ev.record(st); main_stream.wait_event(ev)
+        e1.record(main_stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        ctxs[0].prof(True)
+        for _ in range(2):
+            step(0)
+        rep = ctxs[0].prof_report()
+        ctxs[0].prof(False)
+        top = sorted(rep.items(), key=lambda kv: -kv[1][1])
+        res = {"records": n_rec, "lines_seen": out_n[0]["lines"], "ms_per_step": ms, "reads_per_sec": n_rec / (ms / 1e3), "h2d_bytes_per_step": len(bam_bytes),
+               "d2h_bytes_per_step": out_n[0]["n"] + 2 * n_cpg, "sam_text_bytes_equivalent": sam_bytes, "inflated_bytes": out_n[0]["inflated"],
+               "route": "direct (BAM records -> pileup kernels, no SAM text)" if os.environ.get("WGBS_DBAM_DIRECT") == "1" else "text (view -> SAM text -> tokenizer)",
+               "inflate": os.environ.get("WGBS_INFLATE") or "default (warp per BGZF block)", "batches_in_flight": S,
+               "identical_to_sam_text_path": bool(same) and not errs, "errors": errs[:3],
+               "breakdown_ms_per_step": {k: round(v[1] / 2, 4) for k, v in top[:12]},
+               "mode": ("serial: upload, inflate, view, pileup, read back, one batch after the other" if S == 1 else
+                        f"{S} batches in flight on {S} streams (one Context per host thread): uploads overlap the kernels of the other batches")
+                       + "; wgbs_dbam_open + wgbs_pileup_dbam from pinned host bytes"}
+        infl_name = next((k for k in rep if k.startswith("bgzf_inflate")), None)      # bgzf_inflate_k<2>, bgzf_inflate_team_k<G>
+        infl = rep.get(infl_name)
+        if infl:
+            sec = infl[1] / infl[0] / 1e3
+            ab = len(bam_bytes) + out_n[0]["inflated"]          # algorithmic bytes: compressed bytes read + inflated bytes written
+            res["roofline"] = {"kernel": infl_name, "bound": "instruction issue of the serial Huffman walk per block; reported against hbm", "achieved": ab / sec / 1e9,
+                               "peak": peak, "unit": "GB/s", "frac": ab / sec / 1e9 / peak, "algorithmic_bytes": ab, "avg_launch_ms": sec * 1e3}
+        if S > 1:
+            for c in ctxs:
+                c.close()
+        return res
+
+    for cfg in configs.split(","):
+        key, direct, inflate, S = cfg.split(":")
+        os.environ["WGBS_DBAM_DIRECT"] = direct
+        if inflate:
+            os.environ["WGBS_INFLATE"] = inflate
+        else:
+            os.environ.pop("WGBS_INFLATE", None)
+        try:
+            res = run_config(int(S))
+        except Exception as e:
+            res = {"error": repr(e)}
+        res["key"] = key
+        log(f"[bench] {key}: {res.get('ms_per_step', float('nan')):.3f} ms/step, {res.get('reads_per_sec', 0) / 1e6:.1f} M reads/s, identical={res.get('identical_to_sam_text_path')}")
+        print(json.dumps(res), flush=True)
 
 
 def stream_leg(tmp: str, n_rec: int, steps=12, warmup=3):
@@ -429,12 +483,13 @@ def main():
     ap.add_argument("--no-extras", dest="no_extras", action="store_true", help="skip the pat2beta / homog / segment side measurements")
     ap.add_argument("--only-bam-extra", dest="only_bam", action="store_true", help="of the side measurements run only the device-BAM leg")
     ap.add_argument("--bam-leg", dest="bam_leg", help=argparse.SUPPRESS)       # internal: child process of the device-BAM leg
+    ap.add_argument("--bam-configs", dest="bam_configs", default="bam_device:0::1", help=argparse.SUPPRESS)
     ap.add_argument("--stream-leg", dest="stream_leg", help=argparse.SUPPRESS)  # internal: child process of the batches-in-flight leg
     ap.add_argument("--sam-bytes", dest="sam_bytes", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--peak", type=float, default=6650.0, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.bam_leg:
-        return bam_device_leg(args.bam_leg, args.reads, args.sam_bytes, args.peak)
+        return bam_device_leg(args.bam_leg, args.reads, args.sam_bytes, args.peak, args.bam_configs)
     if args.stream_leg:
         return stream_leg(args.stream_leg, args.reads)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -694,20 +749,30 @@ def main():
                 except Exception as e:
                     log(f"[bench] batches_in_flight leg failed: {e!r}")
                     extra["batches_in_flight"] = {"error": repr(e)}
-                # text route (view -> SAM text -> tokenizer) and direct route (BAM records feed the pileup kernels in place)
-                legs = [("bam_device", {"WGBS_DBAM_DIRECT": "0"}), ("bam_device_direct", {"WGBS_DBAM_DIRECT": "1"})]
-                # decoder variants (teams of G lanes per BGZF block instead of a whole warp), on the direct route
-                variants = os.environ.get("WGBS_BENCH_INFLATE_VARIANTS", "g8,g16").split(",")
-                legs += [(f"bam_device_direct_inflate_{v}", {"WGBS_DBAM_DIRECT": "1", "WGBS_INFLATE": v}) for v in variants if v]
-                for key, env_add in legs:
-                    try:                                     # one leg failing (or running into its time limit) must not cost the others
-                        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--bam-leg", tmp, "--reads", str(n_rec), "--sam-bytes", str(text_bytes),
-                                            "--peak", str(roof["peak"] if roof else 6650.0)], stdout=subprocess.PIPE, timeout=150, env={**os.environ, **env_add})
-                        line = [l for l in r.stdout.decode(errors="replace").splitlines() if l.startswith("{")]
-                        extra[key] = json.loads(line[-1]) if line else {"error": f"child exited {r.returncode} without a result"}
+                # children, verified code first: text route (view -> SAM text -> tokenizer), direct route (BAM records feed the pileup
+                # kernels in place); then ONE child for the staged configurations (two batches in flight; teams of G lanes per BGZF
+                # block), which prints a line per configuration as it goes -- what it measured before a fault or its time limit is kept
+                staged = os.environ.get("WGBS_BENCH_BAM_STAGED", "bam_device_direct_2streams:1::2,bam_device_direct_inflate_g8:1:g8:1,"
+                                        "bam_device_direct_inflate_g16:1:g16:1,bam_device_direct_inflate_g8_2streams:1:g8:2")
+                for cfgs, limit in [("bam_device:0::1", 150), ("bam_device_direct:1::1", 150)] + ([(staged, 200)] if staged else []):
+                    stdout = b""
+                    try:
+                        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--bam-leg", tmp, "--bam-configs", cfgs, "--reads", str(n_rec), "--sam-bytes", str(text_bytes),
+                                            "--peak", str(roof["peak"] if roof else 6650.0)], stdout=subprocess.PIPE, timeout=limit)
+                        stdout = r.stdout
+                        note = None if r.returncode == 0 else f"child exited {r.returncode}"
+                    except subprocess.TimeoutExpired as e:
+                        stdout, note = e.stdout or b"", f"child ran into its {limit} s limit"
                     except Exception as e:
-                        log(f"[bench] {key} leg failed: {e!r}")
-                        extra[key] = {"error": repr(e)}
+                        note = repr(e)
+                    seen = set()
+                    for l in stdout.decode(errors="replace").splitlines():
+                        if l.startswith("{"):
+                            d = json.loads(l); seen.add(d.get("key")); extra[d.pop("key", "bam_device")] = d
+                    for c in cfgs.split(","):
+                        if c.split(":")[0] not in seen:
+                            extra[c.split(":")[0]] = {"error": note or "no result"}
+                            log(f"[bench] {c.split(':')[0]}: {note or 'no result'}")
             except Exception as e:
                 log(f"[bench] bam_device leg failed: {e!r}")
                 extra["bam_device"] = {"error": repr(e)}
