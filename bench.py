@@ -473,6 +473,45 @@ def stream_leg(tmp: str, n_rec: int, steps=12, warmup=3):
     print(json.dumps(out), flush=True)
 
 
+def segment_leg():
+    """(child process of the bench) segment at a scale where the per-call structure shows: many 60 000-site chunks per call (the DP
+    is one warp per chunk, so few chunks = few busy warps), K = 10 and K = 200, with the worst-case wave plan (default) and the
+    exact one (WGBS_SEG_PLAN=exact, staged); per-kernel times from the library's profiler; borders compared between the plans."""
+    import torch
+    from wgbs_tools_b200 import synth
+    from wgbs_tools_b200.api import Context
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+    ctx = Context(0, stream=stream.cuda_stream)
+    out = {}
+    for key, K, nch in (("K10_x64_chunks", 10, 64), ("K200_x8_chunks", 200, 8)):
+        S = nch * 60_000
+        betas = synth.make_betas(9, K, S)
+        loci = synth.make_genome(2, "chr1", S * 110, with_bases=False).loci[:S]
+        dbet = [ctx.upload(b) for b in betas]; dd = ctx.upload(loci)
+        chunks = [(s, 60_000) for s in range(0, S, 60_000)]
+        res = {}
+        ref = None
+        for plan in ("worst", "exact"):
+            os.environ["WGBS_SEG_PLAN"] = plan
+            try:
+                ctx.segment(dbet, dd, chunks, 1000, 2000, 15); torch.cuda.synchronize()            # warm-up
+                t0 = time.time(); r = ctx.segment(dbet, dd, chunks, 1000, 2000, 15); torch.cuda.synchronize(); sec = time.time() - t0
+                ctx.prof(True); ctx.segment(dbet, dd, chunks, 1000, 2000, 15); rep = ctx.prof_report(); ctx.prof(False)
+                same = ref is None or all(np.array_equal(a, b) for a, b in zip(ref, r))
+                ref = ref or r
+                res[plan] = {"ms": sec * 1e3, "sites_per_sec": S / sec, "blocks": int(sum(len(x) - 1 for x in r)), "same_borders_as_worst_plan": bool(same),
+                             "kernels_ms": {k: round(v[1], 3) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])[:6]},
+                             "launches": {k: v[0] for k, v in rep.items() if k.startswith("seg_dp") or k.startswith("seg_cost")}}
+            except Exception as e:
+                res[plan] = {"error": repr(e)}
+            log(f"[bench] segment {key} plan={plan}: {res[plan]}")
+        out[key] = {"K": K, "sites": S, "chunks": nch, "timing": "host wall clock around the C-ABI call (betas resident in HBM, borders read back)", **res}
+        for b in dbet + [dd]:
+            b.free()
+    print(json.dumps(out), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -484,6 +523,7 @@ def main():
     ap.add_argument("--only-bam-extra", dest="only_bam", action="store_true", help="of the side measurements run only the device-BAM leg")
     ap.add_argument("--bam-leg", dest="bam_leg", help=argparse.SUPPRESS)       # internal: child process of the device-BAM leg
     ap.add_argument("--bam-configs", dest="bam_configs", default="bam_device:0::1", help=argparse.SUPPRESS)
+    ap.add_argument("--segment-leg", dest="segment_leg", action="store_true", help=argparse.SUPPRESS)   # internal: child process, segment at scale
     ap.add_argument("--stream-leg", dest="stream_leg", help=argparse.SUPPRESS)  # internal: child process of the batches-in-flight leg
     ap.add_argument("--sam-bytes", dest="sam_bytes", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--peak", type=float, default=6650.0, help=argparse.SUPPRESS)
@@ -492,6 +532,8 @@ def main():
         return bam_device_leg(args.bam_leg, args.reads, args.sam_bytes, args.peak, args.bam_configs)
     if args.stream_leg:
         return stream_leg(args.stream_leg, args.reads)
+    if args.segment_leg:
+        return segment_leg()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     workload = f"bam2pat synthetic 150bp PE WGBS, {args.reads:,} records per GPU, {CHR} index ({N_CPG:,} CpGs)"
@@ -749,6 +791,13 @@ def main():
                 except Exception as e:
                     log(f"[bench] batches_in_flight leg failed: {e!r}")
                     extra["batches_in_flight"] = {"error": repr(e)}
+                try:                                         # segment with many chunks per call, both wave plans
+                    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--segment-leg"], stdout=subprocess.PIPE, timeout=200)
+                    line = [l for l in r.stdout.decode(errors="replace").splitlines() if l.startswith("{")]
+                    extra["segment_at_scale"] = json.loads(line[-1]) if line else {"error": f"child exited {r.returncode} without a result"}
+                except Exception as e:
+                    log(f"[bench] segment_at_scale leg failed: {e!r}")
+                    extra["segment_at_scale"] = {"error": repr(e)}
                 # children, verified code first: text route (view -> SAM text -> tokenizer), direct route (BAM records feed the pileup
                 # kernels in place); then ONE child for the staged configurations (two batches in flight; teams of G lanes per BGZF
                 # block), which prints a line per configuration as it goes -- what it measured before a fault or its time limit is kept

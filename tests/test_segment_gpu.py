@@ -75,3 +75,18 @@ def test_segment_rejects_bad_beta(ctx):
     b[1][100] = (9, 3)                                   # meth > cover
     with pytest.raises(WgbsError, match="meth > cover"):
         ctx.segment(b, np.arange(500, dtype=np.uint32) * 50, [(0, 500)], 100, 2000, 15)
+
+
+@pytest.mark.staged
+def test_segment_exact_wave_plan_gives_the_same_borders(ctx, oracle, monkeypatch):
+    """WGBS_SEG_PLAN=exact packs waves by the real number of cost cells (seg_chunk_cells_k): many more chunks per wave, same borders"""
+    K, n, nch = 4, 3000, 40
+    betas = synth.make_betas(3, K, n * nch)
+    loci = synth.make_genome(2, "chr1", n * nch * 120, with_bases=False).loci[:n * nch]
+    chunks = [(s, n) for s in range(0, n * nch, n)]
+    monkeypatch.setenv("WGBS_SEG_PLAN", "worst")
+    a = ctx.segment(betas, loci, chunks, 1000, 2000, 15)
+    monkeypatch.setenv("WGBS_SEG_PLAN", "exact")
+    b = ctx.segment(betas, loci, chunks, 1000, 2000, 15)
+    assert len(a) == len(b) == nch and all(np.array_equal(x, y) for x, y in zip(a, b))
+    np.testing.assert_array_equal(b[7], oracle.port_segment([x[7 * n:8 * n] for x in betas], loci[7 * n:8 * n], 1000, 2000, 15))

@@ -16,6 +16,10 @@
 //   seg_dp_k       one WARP per chunk: sequential over e, parallel max over the admissible block lengths, M in a
 //                  shared-memory ring, next step's cells prefetched.  End-major layout: the candidates of step e are contiguous.
 //   seg_trace_k    traceback (segmentor.cpp:50-58)
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 #include "glibc_log2.cuh"
 
@@ -209,6 +213,30 @@ __global__ void seg_chunk_of_k(const Chunk *__restrict__ chunks, uint32_t nchunk
     for (uint32_t s = threadIdx.x; s < ch.n; s += blockDim.x) chunk_of[ch.start + s] = c;
 }
 
+// cells of every chunk of the call (what seg_window_k will find, summed per chunk): lets the host pack waves by the real scratch
+// need instead of the worst case n * max_cpg -- with max_bp limiting blocks to a few dozen sites that is ~40x more chunks
+// (= concurrent DP warps) per wave.  One CTA per chunk; chunks are absolute here.
+__global__ void __launch_bounds__(256) seg_chunk_cells_k(const uint32_t *__restrict__ dists, const Chunk *__restrict__ chunks, uint32_t max_cpg,
+                                                          uint32_t max_bp, unsigned long long *__restrict__ cells) {
+    const Chunk c = chunks[blockIdx.x];
+    unsigned long long sum = 0;
+    for (uint32_t k = threadIdx.x; k < c.n; k += blockDim.x) {
+        const uint32_t e = c.start + k;
+        uint32_t lo = c.start;
+        if (e + 1 - c.start > max_cpg) lo = e + 1 - max_cpg;
+        const uint32_t de = dists[e];
+        uint32_t a = lo, b = e;
+        while (a < b) { uint32_t m = (a + b) >> 1; if (de - dists[m] > max_bp) a = m + 1; else b = m; }
+        sum += e - a + 1;
+    }
+    __shared__ unsigned long long ws[8];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned long long t = 0; for (int i = 0; i < 8; i++) t += ws[i]; cells[blockIdx.x] = t; }
+}
+
 __global__ void __launch_bounds__(256) glibc_log2_probe_k(const float *__restrict__ p, size_t n, float *__restrict__ l2f, double *__restrict__ l2) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -271,6 +299,18 @@ extern "C" int wgbs_segment(wgbs_ctx *ctx, const uint8_t *const *betas, int K, c
     // waves of consecutive chunks bounded by a scratch budget
     const uint64_t CELL_BUDGET = 600ull << 20;          // cells (8 B each)  -> <= 4.7 GiB of cost
     const uint64_t PREFIX_BUDGET = 6ull << 30;          // bytes of running sums
+    // WGBS_SEG_PLAN=exact: budget the cells of a chunk by what its windows really hold (one small kernel + one read-back per
+    // call) instead of n * min(max_cpg, n); staged -- the default stays the worst-case plan until this has run on a B200
+    std::vector<unsigned long long> exact_cells;
+    if (const char *e = getenv("WGBS_SEG_PLAN"); e && !strcmp(e, "exact") && nchunks > 1) {
+        Chunk *dall; unsigned long long *dcells;
+        RC_TRY(T.alloc(&dall, (size_t)nchunks)); RC_TRY(T.alloc(&dcells, (size_t)nchunks));
+        RC_TRY(copy_any(ctx, dall, hc.data(), (size_t)nchunks * sizeof(wgbs_chunk)));
+        LAUNCH(ctx, seg_chunk_cells_k, (unsigned)nchunks, 256, 0, ddists, dall, (uint32_t)max_cpg, max_bp, dcells);
+        LAUNCH_CHECK();
+        exact_cells.resize(nchunks);
+        RC_TRY(copy_any(ctx, exact_cells.data(), dcells, (size_t)nchunks * 8));
+    }
     int c0 = 0;
     while (c0 < nchunks) {
         // a wave must cover a contiguous site range: extend while chunks are adjacent/ascending and budgets hold
@@ -279,7 +319,7 @@ extern "C" int wgbs_segment(wgbs_ctx *ctx, const uint8_t *const *betas, int K, c
         while (c1 < nchunks) {
             if (c1 > c0 && hc[c1].start < s_end) break;                       // overlapping / unordered: new wave
             uint64_t ns_new = (uint64_t)hc[c1].start + hc[c1].n - s_begin;
-            uint64_t cells_new = worst_cells + (uint64_t)hc[c1].n * (uint64_t)std::min<uint64_t>(max_cpg, hc[c1].n);
+            uint64_t cells_new = worst_cells + (exact_cells.empty() ? (uint64_t)hc[c1].n * (uint64_t)std::min<uint64_t>(max_cpg, hc[c1].n) : (uint64_t)exact_cells[c1]);
             if (c1 > c0 && (ns_new * 8ull * K > PREFIX_BUDGET || cells_new > CELL_BUDGET)) break;
             sites = ns_new; worst_cells = cells_new; s_end = hc[c1].start + hc[c1].n; c1++;
         }
