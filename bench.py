@@ -418,7 +418,7 @@ def stream_leg(tmp: str, n_rec: int, steps=12, warmup=3):
     d_sam = torch.frombuffer(bytearray(sam), dtype=torch.uint8).cuda()
     torch.cuda.synchronize()
     out = {"records": n_rec, "steps": steps, "by_streams": {}}
-    for S in (1, 2, 3, 4):
+    for S in (1, 2, 4):
         streams = [torch.cuda.Stream() for _ in range(S)]
         ctxs = [Context(0, stream=st.cuda_stream) for st in streams]
         mcs = [torch.zeros((n_cpg, 2), dtype=torch.int32, device="cuda") for _ in range(S)]
@@ -484,7 +484,7 @@ def segment_leg():
     stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
     ctx = Context(0, stream=stream.cuda_stream)
     out = {}
-    for key, K, nch in (("K10_x64_chunks", 10, 64), ("K200_x8_chunks", 200, 8)):
+    for key, K, nch in (("K10_x64_chunks", 10, 64), ("K200_x4_chunks", 200, 4)):
         S = nch * 60_000
         betas = synth.make_betas(9, K, S)
         loci = synth.make_genome(2, "chr1", S * 110, with_bases=False).loci[:S]
