@@ -509,7 +509,40 @@ def segment_leg():
         out[key] = {"K": K, "sites": S, "chunks": nch, "timing": "host wall clock around the C-ABI call (betas resident in HBM, borders read back)", **res}
         for b in dbet + [dd]:
             b.free()
-    print(json.dumps(out), flush=True)
+    print(json.dumps({"key": "segment_at_scale", **out}), flush=True)
+    # ---- pat text parser: default (4 byte-wise passes) vs the two-pass tile parser (WGBS_PATPARSE=tiles, staged)
+    try:
+        R, N = 8_000_000, N_CPG
+        txt = synth.make_pat_text_fast(3, R, N, chrom=CHR)
+        d_txt = ctx.upload(txt)
+        res = {"records": R, "text_bytes": len(txt)}
+        ref = None
+        for mode in ("default", "tiles"):
+            os.environ["WGBS_PATPARSE"] = mode
+            try:
+                for _ in range(2):
+                    ctx.pats_from_text(d_txt).free()
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                for _ in range(5):
+                    ctx.pats_from_text(d_txt).free()
+                b.record(stream)
+                torch.cuda.synchronize()
+                ms = a.elapsed_time(b) / 5
+                P = ctx.pats_from_text(d_txt)
+                arrs = tuple(x.tobytes() for x in P.download())
+                P.free()
+                same = ref is None or arrs == ref
+                ref = ref or arrs
+                res[mode] = {"ms": ms, "text_gb_per_s": len(txt) / ms / 1e6, "records_per_sec": R / (ms / 1e3), "same_records_as_default": bool(same)}
+            except Exception as e:
+                res[mode] = {"error": repr(e)}
+            log(f"[bench] pat parse {mode}: {res[mode]}")
+        d_txt.free()
+        print(json.dumps({"key": "pat_parse", **res}), flush=True)
+    except Exception as e:
+        print(json.dumps({"key": "pat_parse", "error": repr(e)}), flush=True)
 
 
 def main():
@@ -791,13 +824,19 @@ def main():
                 except Exception as e:
                     log(f"[bench] batches_in_flight leg failed: {e!r}")
                     extra["batches_in_flight"] = {"error": repr(e)}
-                try:                                         # segment with many chunks per call, both wave plans
-                    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--segment-leg"], stdout=subprocess.PIPE, timeout=200)
-                    line = [l for l in r.stdout.decode(errors="replace").splitlines() if l.startswith("{")]
-                    extra["segment_at_scale"] = json.loads(line[-1]) if line else {"error": f"child exited {r.returncode} without a result"}
+                stdout = b""
+                try:                                         # segment with many chunks per call (both wave plans); pat text parsers
+                    stdout = subprocess.run([sys.executable, os.path.abspath(__file__), "--segment-leg"], stdout=subprocess.PIPE, timeout=200).stdout
+                except subprocess.TimeoutExpired as e:
+                    stdout = e.stdout or b""
+                    log("[bench] segment / pat-parse leg ran into its time limit")
                 except Exception as e:
-                    log(f"[bench] segment_at_scale leg failed: {e!r}")
-                    extra["segment_at_scale"] = {"error": repr(e)}
+                    log(f"[bench] segment / pat-parse leg failed: {e!r}")
+                for l in stdout.decode(errors="replace").splitlines():
+                    if l.startswith("{"):
+                        d = json.loads(l); extra[d.pop("key", "staged")] = d
+                for k in ("segment_at_scale", "pat_parse"):
+                    extra.setdefault(k, {"error": "no result"})
                 # children, verified code first: text route (view -> SAM text -> tokenizer), direct route (BAM records feed the pileup
                 # kernels in place); then ONE child for the staged configurations (two batches in flight; teams of G lanes per BGZF
                 # block), which prints a line per configuration as it goes -- what it measured before a fault or its time limit is kept
