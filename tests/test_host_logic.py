@@ -169,3 +169,9 @@ def test_csi_index_round_trip_region_queries(tmp_path):
     # an empty pat file still gives a loadable index
     q = tmp_path / "e.pat.gz"; q.write_bytes(bgzf_compress(b"", 1))
     assert csi.CsiIndex.load(csi.index_pat(str(q))).names == []
+
+
+def test_pat_tile_parser_algorithm_model():
+    """the staged two-pass tile parser (pat_tiles_k): its algorithm, modelled in Python, equals a straightforward parser"""
+    import pat_tiles_model
+    assert pat_tiles_model.run(iters=1200, seed=3) == 0
