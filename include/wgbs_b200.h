@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define WGBS_B200_ABI_VERSION 4
+#define WGBS_B200_ABI_VERSION 5
 
 typedef struct wgbs_ctx wgbs_ctx;
 typedef struct wgbs_pats wgbs_pats;   /* device-resident pat records: (idx, len, count, 2-bit symbol pool) */
@@ -226,6 +226,13 @@ typedef struct wgbs_view_opts {
     size_t n_iv;                /* 0: no interval filter */
     int iv_exclude;             /* 0: keep records overlapping an interval (-L); 1: keep records overlapping none (bedtools -v) */
     uint64_t max_records;       /* 0: all; else only the first max_records passing records (is_pair_end / detect_nanopore peeks) */
+    /* Template window (key_end <= 0: none): keep the records whose TEMPLATE KEY lies in the 0-based half-open window
+     * [key_beg, key_end).  key = POS, or max(POS, PNEXT) for a paired record whose mate is mapped to the same reference -- so
+     * both mates of a pair carry the same key and a chromosome can be piled up in windows (a 30x chromosome is far more than
+     * the 4 GiB of SAM text / BAM stream one call takes) without ever separating mates: the windows partition the records.
+     * This is match_maker's own rule for what may still find its mate (PNEXT against the last position seen,
+     * reference match_maker.cpp:77-88), applied at window granularity. */
+    int64_t key_beg, key_end;
 } wgbs_view_opts;
 int wgbs_bam_view_ex(const wgbs_bam *, const wgbs_view_opts *, char **text, size_t *nbytes, uint64_t *nrecords);
 void wgbs_host_free(void *);

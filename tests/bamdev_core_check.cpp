@@ -4,7 +4,7 @@
 //
 //   bamdev_core_check inflate FILE.bgzf [emu_blocks]   every BGZF block through Inflater<OneLane> vs zlib; the first
 //                                                      emu_blocks blocks also through a 32-lane lock-step emulation
-//   bamdev_core_check view FILE.bam SEG DEPTH [REFID MAPQ EXCL INCL BEG END FLAGEQ RG IVFILE IVEXCL MAXREC]
+//   bamdev_core_check view FILE.bam SEG DEPTH [REFID MAPQ EXCL INCL BEG END FLAGEQ RG IVFILE IVEXCL MAXREC [KEYBEG KEYEND]]
 //                                                      inflate, find the records with the segment guess / walk / repair
 //                                                      scheme (segment size SEG bytes), apply the `samtools view` filters
 //                                                      (FLAGEQ: comma list or '-', RG: read group or '-', IVFILE: "beg end"
@@ -195,6 +195,7 @@ static int cmd_view(const char *path, uint64_t SEG, int depth, int argc, char **
         if (strcmp(argv[8], "-")) { FILE *fi = fopen(argv[8], "r"); long long a, b; while (fi && fscanf(fi, "%lld %lld", &a, &b) == 2) { ivb.push_back(a); ive.push_back(b); } if (fi) fclose(fi); }
         V.iv_beg = ivb.data(); V.iv_end = ive.data(); V.n_iv = ivb.size(); V.iv_exclude = atoi(argv[9]);
         max_rec = strtoull(argv[10], nullptr, 10);
+        if (argc >= 13) { V.key_beg = atoll(argv[11]); V.key_end = atoll(argv[12]); }     // template window (wgbs_view_opts.key_beg / key_end)
     }
     std::string out;
     for (uint64_t o : rec) {

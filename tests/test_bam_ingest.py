@@ -256,3 +256,32 @@ def test_bam2pat_cli_region_strand_readgroup_and_lists(ctx, oracle, bamio, tmp_p
     reg = f"chr1:{g.loci[999]}-{g.loci[1198] + 1}"
     assert gzip.decompress((out / "s.pat.gz").read_bytes()) == expect(reg)
     assert not (out / "s.beta").exists()
+
+
+def test_template_windows_partition_the_records_and_keep_mates_together(built_lib, tmp_path):
+    """wgbs_view_opts.key_beg / key_end (bam2pat piles a large chromosome up in windows): the windows partition the view, no
+    QNAME is split over two windows, and the SAM-text filter (filter_sam) selects the same records as the BAM reader"""
+    from wgbs_tools_b200 import bamio
+    from wgbs_tools_b200.samfilter import filter_sam
+    g = synth.make_genome(7, "chrT", 300_000)
+    sam = synth.make_sam(g, 20_000, 3, paired=True, single_frac=0.05)
+    p = tmp_path / "w.bam"
+    p.write_bytes(bamio.sam_to_bam(sam, [("chrT", g.length)]))
+    edges = [0, 40_000, 40_300, 41_000, 150_000, 150_001, 299_000, 1 << 40]        # narrow windows: many pairs straddle an edge
+    kw = dict(mapq=10, exclude_flags=1796, include_flags=3)
+    with bamio.BamFile(str(p), threads=3) as b:
+        whole = b.view("chrT", **kw)
+        parts = [b.view("chrT", key_window=(lo, hi), **kw) for lo, hi in zip(edges[:-1], edges[1:])]
+    assert sorted(whole.splitlines()) == sorted(l for t in parts for l in t.splitlines())
+    assert sum(t.count(b"\n") for t in parts) == whole.count(b"\n")
+    where = {}
+    for k, t in enumerate(parts):
+        for l in t.splitlines():
+            assert where.setdefault(l.split(b"\t", 1)[0], k) == k                 # every record of a QNAME in ONE window
+    assert len([t for t in parts if t]) >= 5
+    for (lo, hi), t in zip(zip(edges[:-1], edges[1:]), parts):
+        assert filter_sam(sam, chrom="chrT", key_window=(lo, hi), **kw) == t
+    # every window is still in coordinate order (what the pairing and the pileup expect of a batch)
+    for t in parts:
+        pos = [int(l.split(b"\t")[3]) for l in t.splitlines()]
+        assert pos == sorted(pos)

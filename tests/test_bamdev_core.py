@@ -187,6 +187,9 @@ def test_filters_match_the_host_reader(check, sam, tmp_path, built_lib):
         dict(chrom=None, max_records=200),
         dict(chrom="chrM"),
         dict(chrom=None, read_group="nosuch"),
+        dict(chrom="chrT", key_window=(100_000, 200_000)),
+        dict(chrom="chrT", key_window=(0, 100_000), mapq=10, exclude_flags=1796, include_flags=3),
+        dict(chrom="chrT", key_window=(200_000, 1 << 40), flag_eq=(99, 147)),
     ]
     with bamio.BamFile(str(p), threads=2) as b:
         for kw in cases:
@@ -195,6 +198,8 @@ def test_filters_match_the_host_reader(check, sam, tmp_path, built_lib):
                     str(kw.get("include_flags", 0)), str(kw.get("beg", 0)), str(kw.get("end", 0)),
                     ",".join(map(str, kw["flag_eq"])) if kw.get("flag_eq") else "-", kw.get("read_group") or "-",
                     str(iv) if "intervals" in kw else "-", str(int(kw.get("exclude_intervals", False))), str(kw.get("max_records", 0))]
+            if "key_window" in kw:
+                argv += [str(kw["key_window"][0]), str(kw["key_window"][1])]
             r = subprocess.run([check, "view", str(p), "16384", "4"] + argv, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
             assert r.returncode == 0, r.stderr.decode()
             assert r.stdout == exp, kw

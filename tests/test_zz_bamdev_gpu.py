@@ -362,3 +362,25 @@ def test_bam2pat_cli_direct_route(ctx, bamio, tmp_path, monkeypatch):
                                 (out / "s.mbias" / "s.mbias.OT.txt").read_bytes())
     assert outs[("host", "0")] == outs[("device", "0")] == outs[("device", "1")]
     assert len(outs[("host", "0")][0]) > 1000
+
+
+@pytest.mark.parametrize("decode,direct", [("host", "0"), ("device", "0"), ("device", "1")])
+def test_bam2pat_cli_template_windows(ctx, bamio, tmp_path, monkeypatch, decode, direct):
+    """a chromosome piled up in template windows (wgbs_view_opts.key_beg / key_end; what bam2pat does when a chromosome is too
+    large for one call) == the chromosome in one call: same .pat.gz text, same .beta, for every decoder / route"""
+    from wgbs_tools_b200 import bam2pat
+    g1 = synth.make_genome(31, "chr1", 400_000, first_idx=1)
+    refdir = tmp_path / "ref"; refdir.mkdir()
+    with gzip.open(refdir / "CpG.bed.gz", "wb") as f:
+        f.write(g1.dict_text())
+    (refdir / "CpG.chrome.size").write_text(f"chr1\t{g1.n_cpg}\n"); (refdir / "chrome.size").write_text(f"chr1\t{g1.length}\n")
+    sam = synth.make_sam(g1, 12_000, 4, paired=True, single_frac=0.03)
+    bam = tmp_path / "s.bam"; bam.write_bytes(bamio.sam_to_bam(sam, [("chr1", g1.length)]))
+    monkeypatch.setenv("WGBS_DBAM_DIRECT", direct)
+    outs = []
+    for tag, limit in (("whole", "0"), ("windows", "1700")):
+        monkeypatch.setenv("WGBS_CHUNK_RECORDS", limit)
+        out = tmp_path / tag; out.mkdir()
+        bam2pat.main([str(bam), "--genome", str(refdir), "-o", str(out), "--bam_decode", decode])
+        outs.append((gzip.decompress((out / "s.pat.gz").read_bytes()), (out / "s.beta").read_bytes()))
+    assert outs[0] == outs[1] and len(outs[0][0]) > 1000

@@ -22,7 +22,7 @@ class ViewOpts(C.Structure):
     _fields_ = [("refid", C.c_int), ("min_mapq", C.c_int), ("exclude_flags", C.c_int), ("include_flags", C.c_int),
                 ("beg", C.c_int64), ("end", C.c_int64), ("n_flag_eq", C.c_int), ("flag_eq", C.c_int * 4),
                 ("read_group", C.c_char_p), ("iv_beg", C.c_void_p), ("iv_end", C.c_void_p), ("n_iv", C.c_size_t),
-                ("iv_exclude", C.c_int), ("max_records", C.c_uint64)]
+                ("iv_exclude", C.c_int), ("max_records", C.c_uint64), ("key_beg", C.c_int64), ("key_end", C.c_int64)]
 
 
 class WgbsError(RuntimeError):

@@ -33,11 +33,39 @@ def split_sam_by_chrom(sam: bytes) -> dict[str, bytes]:
     return {c: b"".join(v) for c, v in out.items()}
 
 
-def proc_chr(ctx, ref, region: str, sam, args, mc_buf):
+def template_windows(weight: int, limit: int, lo: int, hi: int):
+    """None when one call takes the whole region; else 0-based half-open windows on the template key max(POS, PNEXT)
+    (wgbs_view_opts.key_beg / key_end) that partition its records into ~equal shares of at most `limit` units (records of a
+    .bam, bytes of SAM text): a 30x chromosome is tens of GB of SAM text, one call takes < 4 GiB.  The first window starts at
+    0 and the last one is open-ended, so every record falls into exactly one window."""
+    if limit <= 0 or weight <= limit or hi <= lo:
+        return None
+    k = -(-weight // limit)
+    edges = sorted({lo + (hi - lo) * i // k for i in range(1, k)} - {lo, hi})
+    bounds = [0] + [e for e in edges if e > 0] + [1 << 40]
+    return list(zip(bounds[:-1], bounds[1:]))
+
+
+def merge_pat_texts(ctx, chrom: str, texts: list[bytes], long: bool) -> bytes:
+    """the collapsed pat texts of the windows of one chromosome -> one sorted, collapsed text (`sort -k2,2n -k3,3 | uniq -c`
+    over their union: counts of identical (index, pattern) add up)"""
+    if long:                                             # no uniq in --long: a merge by (index, pattern, read name)
+        lines = [l for t in texts for l in t.splitlines(keepends=True)]
+        lines.sort(key=lambda l: (lambda f: (int(f[1]), f[2], f[4]))(l.rstrip(b"\n").split(b"\t")))
+        return b"".join(lines)
+    P = ctx.pats_from_text(b"".join(texts))
+    P.collapse()
+    txt = P.to_text(chrom)
+    P.free()
+    return txt
+
+
+def proc_chr(ctx, ref, region: str, get, args, mc_buf, windows=None):
     """one chromosome / region: returns (pat text bytes, stats); adds its beta counts into mc_buf (device).  patter is
     given the dictionary of the region extended by MAX_READ_SIZE (bam2pat.py:190): CpGs outside it are not called.
-    sam: the SAM text of the region (bytes / DevBuf), or a callable(index, **pileup options) -> (Pats, stats) that views and piles up
-    on the device (device-decoded .bam: wgbs_pileup_dbam); it returns Pats None when the region holds no reads."""
+    get(window): the alignments of the region [restricted to a template window] as SAM text (bytes), or a
+    callable(index, **pileup options) -> (Pats | None, stats) that views and piles up on the device (device-decoded .bam:
+    wgbs_pileup_dbam).  windows: template_windows() of the region, or None for one call."""
     chrom, beg, end = parse_region_str(extend_region(region))
     loci, first = ref.chrom_loci(chrom)
     if end > 0:
@@ -46,17 +74,33 @@ def proc_chr(ctx, ref, region: str, sam, args, mc_buf):
     ix = ctx.load_index(loci, first)
     kw = dict(min_cpg=args.min_cpg, clip=args.clip, paired=-1, nanopore=args.nanopore, np_thresh=args.np_thresh, cpc_call=args.cpc_call,
               combine_mods=args.combine_mods, mbias=args.mbias, keep_names=args.long)
-    P, st = sam(ix, **kw) if callable(sam) else ctx.pileup_sam(ix, sam, **kw)
-    if P is None or (callable(sam) and st["lines"] == 0):
-        if P is not None:
-            P.free()
-        ix.free()
-        return None, st
-    if mc_buf is not None:
-        ctx.pat2beta(P, 1, ref.nr_sites + 1, meth_cov=mc_buf, zero_first=False)
-    P.collapse(long=args.long)                          # --long: `sort | awk '{print $1,$2,$3,1,$4}'`, no uniq (bam2pat.py:102-103)
-    txt = P.to_text(chrom, long=args.long)
-    P.free(); ix.free()
+    texts = []; st = None
+    for w in (windows or [None]):
+        s = get(w)
+        if not callable(s) and not s:
+            continue
+        P, st_w = s(ix, **kw) if callable(s) else ctx.pileup_sam(ix, s, **kw)
+        if P is None or st_w["lines"] == 0:
+            if P is not None:
+                P.free()
+            continue
+        if mc_buf is not None:
+            ctx.pat2beta(P, 1, ref.nr_sites + 1, meth_cov=mc_buf, zero_first=False)
+        P.collapse(long=args.long)                      # --long: `sort | awk '{print $1,$2,$3,1,$4}'`, no uniq (bam2pat.py:102-103)
+        texts.append(P.to_text(chrom, long=args.long))
+        P.free()
+        if st is None:
+            st = st_w
+            # patter decides paired / MM-ML mode from the FIRST line of the chromosome (patter.cpp:324-350): later windows inherit it
+            kw.update(paired=st["paired"], nanopore=bool(st["nanopore"]))
+        else:
+            for k, v in st_w.items():
+                if k not in ("paired", "nanopore"):
+                    st[k] = st[k] + v                   # counters and the M-bias tables add up
+    ix.free()
+    if st is None:
+        return None, {"lines": 0}
+    txt = texts[0] if len(texts) == 1 else merge_pat_texts(ctx, chrom, texts, args.long)
     pe = f"({st['pairs']:,} pairs). " if st["paired"] else ""
     good = st["lines"] - st["empty"] - st["invalid"]
     succ = int((1.0 - st["invalid"] / st["lines"]) * 100.0) if st["lines"] else 0
@@ -117,12 +161,21 @@ class _Source:
             return self.bam.view(chrom, beg=beg, end=end, **kw)
         return filter_sam(self.sam.get(chrom, b""), chrom=chrom, beg=beg, end=end, **kw)
 
-    def piler(self, region: str, **view_kw):
-        """device-decoded .bam: callable(index, **pileup options) -> (Pats | None, stats) for the reads of `region`"""
+    def getter(self, region: str, **view_kw):
+        """get(window) for proc_chr: the alignments of `region` that pass the `samtools view` filters, optionally restricted to a
+        template window -- SAM text (bytes), or for a device-decoded .bam a callable(index, **pileup options) -> (Pats | None,
+        stats) that views and piles up without leaving the device"""
         chrom, beg, end = parse_region_str(region)
-        if chrom not in self.bam.refs:
-            return lambda ix, **kw: (None, {"lines": 0})
-        return lambda ix, **kw: self.bam.pileup(ix, chrom, view=dict(beg=beg, end=end, **view_kw), **kw)
+
+        def get(window):
+            if self.bam is not None:
+                if chrom not in self.bam.refs:
+                    return b""
+                if self.on_device:
+                    return lambda ix, **kw: self.bam.pileup(ix, chrom, view=dict(beg=beg, end=end, key_window=window, **view_kw), **kw)
+                return self.bam.view(chrom, beg=beg, end=end, key_window=window, **view_kw)
+            return filter_sam(self.sam.get(chrom, b""), chrom=chrom, beg=beg, end=end, key_window=window, **view_kw)
+        return get
 
     def weight(self, chrom: str) -> int:
         """how much work a chromosome is (records in a .bam, bytes of SAM text): the LPT weights of the multi-GPU split"""
@@ -281,14 +334,14 @@ def main(argv=None):
                 if lists is not None:
                     kw.update(intervals=lists[0].get(chrom, empty_iv), exclude_intervals=lists[1])
                 txt = None
-                if feq is None:
-                    pass
-                elif src.on_device:                                            # view + pileup in one device call (wgbs_pileup_dbam)
-                    txt, st = proc_chr(ctx, ref, region, src.piler(region, flag_eq=feq, **kw), run, mc)
-                else:
-                    s = src.view(region, flag_eq=feq, **kw)
-                    if s:
-                        txt, st = proc_chr(ctx, ref, region, s, run, mc)
+                if feq is not None:
+                    # a chromosome too large for one call (< 4 GiB of SAM text / BAM stream) is piled up in template windows
+                    _, rb, re_ = parse_region_str(extend_region(region)) if ":" in region else (chrom, 0, 0)
+                    limit = int(os.environ.get("WGBS_CHUNK_RECORDS", 6_000_000)) if src.bam is not None else int(os.environ.get("WGBS_CHUNK_BYTES", 2 << 30))
+                    wins = template_windows(src.weight(chrom), limit, max(rb - 1, 0) if re_ > 0 else 0, re_ if re_ > 0 else ref.chrom_length(chrom))
+                    if wins and a.verbose:
+                        print(f"[wt bam2pat] {region}: {len(wins)} template windows", file=sys.stderr)
+                    txt, st = proc_chr(ctx, ref, region, src.getter(region, flag_eq=feq, **kw), run, mc, wins)
                 if txt is None:
                     if a.verbose:
                         print(f"[wt bam2pat] Skipping region {region}, no reads found", file=sys.stderr)

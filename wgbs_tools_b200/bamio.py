@@ -15,8 +15,10 @@ from .patio import bgzf_compress
 
 
 def view_opts(refs, chrom: str | None = None, mapq: int = 0, exclude_flags: int = 0, include_flags: int = 0, beg: int = 0, end: int = 0,
-              flag_eq=(), read_group: str | None = None, intervals=None, exclude_intervals: bool = False, max_records: int = 0):
-    """wgbs_view_opts for one `samtools view` stage; returns (opts, arrays to keep alive) or (None, None) when nothing can pass"""
+              flag_eq=(), read_group: str | None = None, intervals=None, exclude_intervals: bool = False, max_records: int = 0,
+              key_window: tuple[int, int] | None = None):
+    """wgbs_view_opts for one `samtools view` stage; returns (opts, arrays to keep alive) or (None, None) when nothing can pass.
+    key_window: 0-based half-open window on the template key max(POS, PNEXT) (see wgbs_view_opts in include/wgbs_b200.h)"""
     vo = ViewOpts()
     vo.refid = -1 if chrom is None else refs.index(chrom)
     vo.min_mapq, vo.exclude_flags, vo.include_flags, vo.beg, vo.end = mapq, exclude_flags, include_flags or 0, beg, end
@@ -34,6 +36,10 @@ def view_opts(refs, chrom: str | None = None, mapq: int = 0, exclude_flags: int 
                 return None, None
             vo.n_iv = 0
     vo.max_records = max_records
+    if key_window is not None:
+        vo.key_beg, vo.key_end = int(key_window[0]), int(key_window[1])
+        if vo.key_end <= 0:
+            return None, None
     return vo, keep
 
 

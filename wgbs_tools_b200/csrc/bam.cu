@@ -292,6 +292,11 @@ extern "C" int wgbs_bam_view_ex(const wgbs_bam *B, const wgbs_view_opts *vo, cha
                 for (int k = 0; k < vo->n_flag_eq; k++) ok |= (int)flag == vo->flag_eq[k];
                 if (!ok) continue;
             }
+            if (vo->key_end > 0) {                                   // template window: max(POS, PNEXT) of a pair on one reference (wgbs_b200.h)
+                const int32_t rid = rdi32(r + 4), pos0 = rdi32(r + 8), nref = rdi32(r + 24), npos = rdi32(r + 28);
+                const int64_t key = ((flag & 1) && !(flag & 8) && nref == rid && npos > pos0) ? npos : pos0;
+                if (key < vo->key_beg || key >= vo->key_end) continue;
+            }
             const uint16_t n_cig = rd16(r + 4 + 12); const uint8_t l_name = r[4 + 8];
             if (need_span) {
                 const int64_t pos0 = (int64_t)rdi32(r + 8);          // 0-based

@@ -119,7 +119,14 @@ struct ViewParams {
     int32_t n_flag_eq; int32_t flag_eq[4];
     const int64_t *iv_beg, *iv_end; uint64_t n_iv; int32_t iv_exclude;   // sorted disjoint 0-based half-open intervals
     const char *rg; uint32_t rg_len; int32_t have_rg;
+    int64_t key_beg, key_end;      // template window on max(POS, PNEXT) (0-based half-open), key_end <= 0: none (wgbs_b200.h)
 };
+
+// the position a record's TEMPLATE is filed under: both mates of a pair on one reference share it (0-based)
+WGBS_HD int64_t template_key(int32_t flag, int32_t refid, int32_t pos, int32_t nref, int32_t npos) {
+    if ((flag & 1) && !(flag & 8) && nref == refid && npos > pos) return npos;
+    return pos;
+}
 
 // value of the first Z-typed tag `ab`, or nullptr (malformed tag area: nullptr)
 WGBS_HD const uint8_t *find_z_tag(const uint8_t *t, const uint8_t *end, char a, char b, uint32_t *len) {
@@ -149,6 +156,7 @@ WGBS_HD bool passes(const Rec &R, const ViewParams &V) {
     if ((int32_t)R.mapq < V.min_mapq || ((int32_t)R.flag & V.exclude_flags)) return false;
     if (V.include_flags && ((int32_t)R.flag & V.include_flags) != V.include_flags) return false;
     if (V.n_flag_eq) { bool ok = false; for (int k = 0; k < V.n_flag_eq; k++) ok |= (int32_t)R.flag == V.flag_eq[k]; if (!ok) return false; }
+    if (V.key_end > 0) { const int64_t key = template_key((int32_t)R.flag, R.refid, R.pos, R.nref, R.npos); if (key < V.key_beg || key >= V.key_end) return false; }
     if (V.end > 0 || V.n_iv) {
         const int64_t pos0 = R.pos;
         int64_t span = 0; const uint8_t *cig = R.cigar();

@@ -213,6 +213,12 @@ __global__ void __launch_bounds__(256) bam_pass_k(const uint8_t *__restrict__ da
     pass[i] = passes(R, V) ? 1u : 0u;
 }
 
+// first / last passing record of a view (only asked for when the whole record range is too wide for 32-bit offsets)
+__global__ void __launch_bounds__(256) pass_range_k(const uint32_t *__restrict__ pass, uint64_t nr, uint32_t *__restrict__ first_last) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nr && pass[i]) { atomicMin(&first_last[0], (uint32_t)i); atomicMax(&first_last[1], (uint32_t)i); }
+}
+
 // has_mm[0] = 1 iff the FIRST passing record carries an MM:Z: / Mm:Z: tag (patter.cpp:337-338 looks at the first line only)
 __global__ void __launch_bounds__(256) bam_records_k(const uint8_t *__restrict__ data, const uint64_t *__restrict__ rec_off, uint64_t nr,
                                                       const uint32_t *__restrict__ pass, const uint32_t *__restrict__ rank, uint32_t max_records,
@@ -514,7 +520,7 @@ extern "C" int wgbs_dbam_view(wgbs_ctx *ctx, const wgbs_dbam *B, const wgbs_view
     ViewParams V; memset(&V, 0, sizeof V);
     V.refid = vo->refid; V.min_mapq = vo->min_mapq; V.exclude_flags = vo->exclude_flags; V.include_flags = vo->include_flags; V.beg = vo->beg; V.end = vo->end;
     V.n_flag_eq = vo->n_flag_eq; for (int k = 0; k < 4; k++) V.flag_eq[k] = vo->flag_eq[k];
-    V.n_iv = vo->n_iv; V.iv_exclude = vo->iv_exclude;
+    V.n_iv = vo->n_iv; V.iv_exclude = vo->iv_exclude; V.key_beg = vo->key_beg; V.key_end = vo->key_end;
     if (vo->n_iv) {
         int64_t *a, *b;
         RC_TRY(T.alloc(&a, vo->n_iv)); RC_TRY(T.alloc(&b, vo->n_iv));
@@ -591,7 +597,7 @@ static int pileup_dbam_direct(wgbs_ctx *ctx, const wgbs_index *ix, const wgbs_db
     ViewParams V; memset(&V, 0, sizeof V);
     V.refid = vo->refid; V.min_mapq = vo->min_mapq; V.exclude_flags = vo->exclude_flags; V.include_flags = vo->include_flags; V.beg = vo->beg; V.end = vo->end;
     V.n_flag_eq = vo->n_flag_eq; for (int k = 0; k < 4; k++) V.flag_eq[k] = vo->flag_eq[k];
-    V.n_iv = vo->n_iv; V.iv_exclude = vo->iv_exclude;
+    V.n_iv = vo->n_iv; V.iv_exclude = vo->iv_exclude; V.key_beg = vo->key_beg; V.key_end = vo->key_end;
     if (vo->n_iv) {
         int64_t *a, *b;
         RC_TRY(T.alloc(&a, vo->n_iv)); RC_TRY(T.alloc(&b, vo->n_iv));
@@ -617,9 +623,21 @@ static int pileup_dbam_direct(wgbs_ctx *ctx, const wgbs_index *ix, const wgbs_db
         if (r1 < B->nrec) { CUDA_TRY(cudaMemcpyAsync(&span[1], B->rec_off + r1, 8, cudaMemcpyDeviceToHost, ctx->stream)); CUDA_TRY(cudaStreamSynchronize(ctx->stream)); }
     }
     const uint32_t n = vo->max_records ? (uint32_t)std::min<uint64_t>(np32, vo->max_records) : np32;
+    if (span[1] - span[0] >= 0xfffffff0ull && np32) {
+        // a large chromosome seen through a template window (bam2pat piles it up in windows): the passing records lie close
+        // together, so the window of the stream the 32-bit descriptors index is narrowed to them
+        uint32_t *fl = ctx->d_flags + 26; const uint32_t init[2] = {0xffffffffu, 0u}; uint32_t hfl[2] = {0, 0};
+        CUDA_TRY(cudaMemcpyAsync(fl, init, 8, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(ctx, pass_range_k, grid_for(nr, 256), 256, 0, pass, nr, fl);
+        CUDA_TRY(cudaMemcpyAsync(hfl, fl, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(&span[0], B->rec_off + r0 + hfl[0], 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (r0 + hfl[1] + 1 < B->nrec) CUDA_TRY(cudaMemcpyAsync(&span[1], B->rec_off + r0 + hfl[1] + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        else span[1] = B->n;
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
     const uint64_t base = span[0];
-    if (span[1] - base >= 0xfffffff0ull)
-        return wgbs_set_err("wgbs_pileup_dbam: the records of this view span %.1f GB of the BAM stream (limit 4 GiB per call): restrict the region", (span[1] - base) / 1e9);
+    if (span[1] - base >= 0xfffffff0ull) return 1;                // still too wide: the text route formats only the passing records
     ReadBatch rb;
     rb.text = (const char *)B->data + base; rb.nbytes = (uint32_t)(span[1] - base); rb.n = n; rb.bam = 1;
     RC_TRY(T.alloc(&rb.line_off, n)); RC_TRY(T.alloc(&rb.line_len, n)); RC_TRY(T.alloc(&rb.qn_len, n));

@@ -65,7 +65,7 @@ def parse_region_str(region: str | None):
 
 def filter_sam(sam: bytes, mapq: int = 0, exclude_flags: int = 0, include_flags: int | None = None, *, chrom: str | None = None,
                beg: int = 0, end: int = 0, flag_eq=(), read_group: str | None = None, intervals=None, exclude_intervals: bool = False,
-               max_records: int = 0) -> bytes:
+               max_records: int = 0, key_window: tuple[int, int] | None = None) -> bytes:
     """same filters as BamFile.view, on SAM text (header lines dropped)"""
     keep = []
     rg = (b"RG:Z:" + read_group.encode()) if read_group else None
@@ -83,6 +83,12 @@ def filter_sam(sam: bytes, mapq: int = 0, exclude_flags: int = 0, include_flags:
             continue
         if flag_eq and f not in flag_eq:
             continue
+        if key_window is not None:                                  # template window: max(POS, PNEXT) of a pair on one reference
+            pos0 = int(t[3]) - 1; key = pos0
+            if (f & 1) and not (f & 8) and len(t) > 7 and t[6] in (b"=", t[2]) and int(t[7]) - 1 > pos0:
+                key = int(t[7]) - 1
+            if not key_window[0] <= key < key_window[1]:
+                continue
         if end > 0 or intervals is not None:
             pos0 = int(t[3]) - 1; span = ref_span(t[5])
             if end > 0 and (pos0 + 1 > end or pos0 + span < beg):
