@@ -237,6 +237,22 @@ typedef struct wgbs_view_opts {
 int wgbs_bam_view_ex(const wgbs_bam *, const wgbs_view_opts *, char **text, size_t *nbytes, uint64_t *nrecords);
 void wgbs_host_free(void *);
 
+/* A .bam that does not fit in memory as a whole is read as a sequence of PARTS (bam2pat --bam_decode stream; samtools streams
+ * the file the same way, reference bam2pat.py:165).  bgzf = the bytes of consecutive WHOLE BGZF blocks of the file.
+ * has_header != 0: the part begins with the BAM header (the first part of a file); else the reference list is passed in
+ * (n_ref names / lengths, from the first part) and records are indexed from inflated offset first_record on.  The last record
+ * may be cut off by the end of the part: *tail = inflated offset of the first byte that is not part of a complete record (the
+ * next part starts at the block holding it, or earlier: wgbs_bam_first_key).  A part is viewed like a file; combined with the
+ * template window of wgbs_view_opts the parts of a file give exactly the templates of the whole file, each once. */
+int wgbs_bam_open_part(const void *bgzf, size_t nbytes, int n_ref, const char *const *ref_names, const int32_t *ref_lens,
+                       int has_header, uint64_t first_record, int threads, wgbs_bam **out, uint64_t *tail);
+/* (refid, 0-based POS) of the last complete record; *refid = -2 when there is none */
+int wgbs_bam_last_record(const wgbs_bam *, int *refid, int64_t *pos);
+/* inflated offset of the first record of reference refid that passes the filters (key window ignored) and whose template key is
+ * >= key; *found = 0 when there is none */
+int wgbs_bam_first_key(const wgbs_bam *, const wgbs_view_opts *, int refid, int64_t key, uint64_t *offset, int *found);
+uint64_t wgbs_bam_inflated_bytes(const wgbs_bam *);
+
 
 /* ---------------------------------------------------------------------------------------------------------------
  * BAM ingest ON THE DEVICE (the `samtools view` stage of reference bam2pat.py:126-165 "without a SAM-text

@@ -122,10 +122,10 @@ def world(tmp_path, oracle, monkeypatch, built_lib):
     return tmp_path, str(refdir)
 
 
-def _run(tmp, refdir, inp, tag, extra=()):
+def _run(tmp, refdir, inp, tag, extra=(), decode="host"):
     from wgbs_tools_b200 import bam2pat
     out = tmp / tag; out.mkdir()
-    bam2pat.main([str(tmp / inp), "--genome", refdir, "-o", str(out), "--bam_decode", "host", *extra])
+    bam2pat.main([str(tmp / inp), "--genome", refdir, "-o", str(out), "--bam_decode", decode, *extra])
     name = inp.split(".")[0]
     pat = gzip.decompress((out / f"{name}.pat.gz").read_bytes())
     beta = (out / f"{name}.beta").read_bytes() if (out / f"{name}.beta").exists() else None
@@ -151,3 +151,15 @@ def test_template_windows_cover_everything():
     w = template_windows(10**9, 6_000_000, 99_000, 301_000)
     assert w[0][0] == 0 and w[-1][1] == 1 << 40 and all(a[1] == b[0] and a[0] < a[1] for a, b in zip(w, w[1:]))
     assert template_windows(10, 3, 5, 6) in (None, [(0, 1 << 40)])                                       # nothing to cut
+
+
+@pytest.mark.parametrize("extra", [(), ("-r", "chr2:50000-200000"), ("--top_strand",), ("--long", "--no_beta")])
+@pytest.mark.parametrize("budget", ["150000", "700000"])
+def test_streamed_bam_gives_the_same_outputs(world, monkeypatch, extra, budget):
+    """--bam_decode stream: the file read as parts of WGBS_STREAM_BYTES inflated bytes (records cut off at part ends, templates
+    deferred until both mates are in) == the file decoded as a whole"""
+    tmp, refdir = world
+    monkeypatch.setenv("WGBS_CHUNK_RECORDS", "0")
+    whole = _run(tmp, refdir, "s.bam", "whole", extra)
+    monkeypatch.setenv("WGBS_STREAM_BYTES", budget)
+    assert _run(tmp, refdir, "s.bam", "stream", extra, decode="stream") == whole

@@ -285,3 +285,34 @@ def test_template_windows_partition_the_records_and_keep_mates_together(built_li
     for t in parts:
         pos = [int(l.split(b"\t")[3]) for l in t.splitlines()]
         assert pos == sorted(pos)
+
+
+@pytest.mark.parametrize("budget", [60_000, 200_000, 1_500_000, 1 << 40])
+def test_streamed_parts_give_every_template_once(built_lib, tmp_path, budget):
+    """stream_parts (a .bam read as windows of BGZF blocks, records cut off at window ends, templates deferred until both mates
+    are in): the union of the yielded (part, chromosome, key window) views == the whole-file views, and no QNAME is split"""
+    from wgbs_tools_b200 import bamio
+    g1 = synth.make_genome(7, "chrA", 200_000); g2 = synth.make_genome(8, "chrB", 120_000); g3 = synth.make_genome(9, "chrC", 50_000)
+    sam = (synth.make_sam(g1, 9_000, 3, paired=True, single_frac=0.05, name_prefix="a") + synth.make_sam(g2, 5_000, 4, paired=True, name_prefix="b")
+           + synth.make_sam(g3, 1_500, 5, paired=False, name_prefix="c") + b"u1\t4\t*\t0\t0\t*\t*\t0\t0\tACGT\t*\n" * 3)
+    p = tmp_path / "s.bam"
+    p.write_bytes(bamio.sam_to_bam(sam, [("chrA", g1.length), ("chrB", g2.length), ("chrC", g3.length), ("chrD", 1000)]))
+    kw = dict(mapq=10, exclude_flags=1796)
+    with bamio.BamFile(str(p), threads=2) as b:
+        whole = {c: b.view(c, **kw) for c in b.refs}
+    got = {c: [] for c in whole}; seen_done = set(); items = 0; where = {}
+    opener = lambda data, refs, lens, first: bamio.BamPart(data, refs, lens, first, threads=2)
+    for part, chrom, win, done in bamio.stream_parts(str(p), opener, lambda c: kw, budget):
+        assert chrom not in seen_done
+        t = part.view(chrom, key_window=win, **kw)
+        for l in t.splitlines():
+            q = l.split(b"\t", 1)[0]
+            assert where.setdefault(q, items) == items, q                # every record of a QNAME in ONE item
+        got[chrom].append(t); items += 1
+        if done:
+            seen_done.add(chrom)
+    for c in whole:
+        assert sorted(b"".join(got[c]).splitlines()) == sorted(whole[c].splitlines()), c
+    assert seen_done >= {"chrA", "chrB", "chrC"}
+    if budget < 1_000_000:
+        assert items > 5                                                  # really streamed

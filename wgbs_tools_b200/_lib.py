@@ -81,6 +81,10 @@ def _load():
         "wgbs_bam_view": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.POINTER(vp), C.POINTER(sz), C.POINTER(u64)]),
         "wgbs_bam_view_ex": (C.c_int, [vp, C.POINTER(ViewOpts), C.POINTER(vp), C.POINTER(sz), C.POINTER(u64)]),
         "wgbs_host_free": (None, [vp]),
+        "wgbs_bam_open_part": (C.c_int, [vp, sz, C.c_int, vp, vp, C.c_int, u64, C.c_int, C.POINTER(vp), C.POINTER(u64)]),
+        "wgbs_bam_last_record": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
+        "wgbs_bam_first_key": (C.c_int, [vp, C.POINTER(ViewOpts), C.c_int, C.c_int64, C.POINTER(u64), C.POINTER(C.c_int)]),
+        "wgbs_bam_inflated_bytes": (u64, [vp]),
         "wgbs_bgzf_inflate": (C.c_int, [vp, vp, sz, C.POINTER(vp), C.POINTER(sz)]),
         "wgbs_dbam_open": (C.c_int, [vp, vp, sz, C.POINTER(vp)]),
         "wgbs_dbam_open_file": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),

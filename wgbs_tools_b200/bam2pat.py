@@ -60,61 +60,93 @@ def merge_pat_texts(ctx, chrom: str, texts: list[bytes], long: bool) -> bytes:
     return txt
 
 
-def proc_chr(ctx, ref, region: str, get, args, mc_buf, windows=None):
-    """one chromosome / region: returns (pat text bytes, stats); adds its beta counts into mc_buf (device).  patter is
-    given the dictionary of the region extended by MAX_READ_SIZE (bam2pat.py:190): CpGs outside it are not called.
-    get(window): the alignments of the region [restricted to a template window] as SAM text (bytes), or a
-    callable(index, **pileup options) -> (Pats | None, stats) that views and piles up on the device (device-decoded .bam:
-    wgbs_pileup_dbam).  windows: template_windows() of the region, or None for one call."""
-    chrom, beg, end = parse_region_str(extend_region(region))
-    loci, first = ref.chrom_loci(chrom)
-    if end > 0:
-        lo = int(np.searchsorted(loci, beg, side="left")); hi = int(np.searchsorted(loci, end, side="right"))
-        loci, first = loci[lo:hi], first + lo
-    ix = ctx.load_index(loci, first)
-    kw = dict(min_cpg=args.min_cpg, clip=args.clip, paired=-1, nanopore=args.nanopore, np_thresh=args.np_thresh, cpc_call=args.cpc_call,
-              combine_mods=args.combine_mods, mbias=args.mbias, keep_names=args.long)
-    texts = []; st = None
-    for w in (windows or [None]):
-        s = get(w)
+class ChromPile:
+    """one chromosome / region being piled up: every add() is one pileup call (the whole region, a template window of it, or
+    the share of it found in one part of a streamed file); beta counts go into mc_buf (device) as they come, the collapsed pat
+    texts are merged in finish().  patter is given the dictionary of the region extended by MAX_READ_SIZE (bam2pat.py:190):
+    CpGs outside it are not called."""
+
+    def __init__(self, ctx, ref, region: str, args, mc_buf):
+        self.ctx, self.ref, self.args, self.mc_buf = ctx, ref, args, mc_buf
+        self.chrom, beg, end = parse_region_str(extend_region(region))
+        loci, first = ref.chrom_loci(self.chrom)
+        if end > 0:
+            lo = int(np.searchsorted(loci, beg, side="left")); hi = int(np.searchsorted(loci, end, side="right"))
+            loci, first = loci[lo:hi], first + lo
+        self.ix = ctx.load_index(loci, first)
+        self.kw = dict(min_cpg=args.min_cpg, clip=args.clip, paired=-1, nanopore=args.nanopore, np_thresh=args.np_thresh, cpc_call=args.cpc_call,
+                       combine_mods=args.combine_mods, mbias=args.mbias, keep_names=args.long)
+        self.texts = []; self.st = None
+
+    def add(self, s):
+        """s: SAM text (bytes), or a callable(index, **pileup options) -> (Pats | None, stats) that views and piles up on the
+        device (device-decoded .bam: wgbs_pileup_dbam)"""
         if not callable(s) and not s:
-            continue
-        P, st_w = s(ix, **kw) if callable(s) else ctx.pileup_sam(ix, s, **kw)
+            return
+        args = self.args
+        P, st_w = s(self.ix, **self.kw) if callable(s) else self.ctx.pileup_sam(self.ix, s, **self.kw)
         if P is None or st_w["lines"] == 0:
             if P is not None:
                 P.free()
-            continue
-        if mc_buf is not None:
-            ctx.pat2beta(P, 1, ref.nr_sites + 1, meth_cov=mc_buf, zero_first=False)
+            return
+        if self.mc_buf is not None:
+            self.ctx.pat2beta(P, 1, self.ref.nr_sites + 1, meth_cov=self.mc_buf, zero_first=False)
         P.collapse(long=args.long)                      # --long: `sort | awk '{print $1,$2,$3,1,$4}'`, no uniq (bam2pat.py:102-103)
-        texts.append(P.to_text(chrom, long=args.long))
+        self.texts.append(P.to_text(self.chrom, long=args.long))
         P.free()
-        if st is None:
-            st = st_w
-            # patter decides paired / MM-ML mode from the FIRST line of the chromosome (patter.cpp:324-350): later windows inherit it
-            kw.update(paired=st["paired"], nanopore=bool(st["nanopore"]))
+        if self.st is None:
+            self.st = st_w
+            # patter decides paired / MM-ML mode from the FIRST line of the chromosome (patter.cpp:324-350): later calls inherit it
+            self.kw.update(paired=st_w["paired"], nanopore=bool(st_w["nanopore"]))
         else:
             for k, v in st_w.items():
                 if k not in ("paired", "nanopore"):
-                    st[k] = st[k] + v                   # counters and the M-bias tables add up
-    ix.free()
-    if st is None:
-        return None, {"lines": 0}
-    txt = texts[0] if len(texts) == 1 else merge_pat_texts(ctx, chrom, texts, args.long)
-    pe = f"({st['pairs']:,} pairs). " if st["paired"] else ""
-    good = st["lines"] - st["empty"] - st["invalid"]
-    succ = int((1.0 - st["invalid"] / st["lines"]) * 100.0) if st["lines"] else 0
-    short = f"{st['short']:,} with too few CpGs. " if args.min_cpg > 1 else ""
-    print(f"[ patter ] [ {chrom} ] finished {st['lines']:,} lines. {pe}{good:,} good, {st['empty']:,} empty, {short}"
-          f"{st['invalid']:,} invalid. (success {succ}%)", file=sys.stderr)          # patter.cpp:298-316
-    return txt, st
+                    self.st[k] = self.st[k] + v         # counters and the M-bias tables add up
+
+    def finish(self):
+        """(pat text | None, stats)"""
+        self.ix.free()
+        st, args, chrom = self.st, self.args, self.chrom
+        if st is None:
+            return None, {"lines": 0}
+        txt = self.texts[0] if len(self.texts) == 1 else merge_pat_texts(self.ctx, chrom, self.texts, args.long)
+        self.texts = []
+        pe = f"({st['pairs']:,} pairs). " if st["paired"] else ""
+        good = st["lines"] - st["empty"] - st["invalid"]
+        succ = int((1.0 - st["invalid"] / st["lines"]) * 100.0) if st["lines"] else 0
+        short = f"{st['short']:,} with too few CpGs. " if args.min_cpg > 1 else ""
+        print(f"[ patter ] [ {chrom} ] finished {st['lines']:,} lines. {pe}{good:,} good, {st['empty']:,} empty, {short}"
+              f"{st['invalid']:,} invalid. (success {succ}%)", file=sys.stderr)          # patter.cpp:298-316
+        return txt, st
+
+
+def proc_chr(ctx, ref, region: str, get, args, mc_buf, windows=None):
+    """one chromosome / region: returns (pat text bytes | None, stats); adds its beta counts into mc_buf (device).
+    get(window): the alignments of the region [restricted to a template window] as SAM text (bytes), or a
+    callable(index, **pileup options) -> (Pats | None, stats).  windows: template_windows() of the region, or None for one call."""
+    pile = ChromPile(ctx, ref, region, args, mc_buf)
+    for w in (windows or [None]):
+        pile.add(get(w))
+    return pile.finish()
 
 
 class _Source:
     """the alignments of one input: a .bam (native reader) or SAM text (what `samtools view -h BAM` prints)"""
 
     def __init__(self, path: str, threads: int, ctx=None, decode: str = "host"):
-        self.bam = None; self.sam = None; self.on_device = False
+        self.bam = None; self.sam = None; self.on_device = False; self.stream = None
+        if path.endswith(".bam") and decode == "stream":
+            # a file too large to hold inflated (host or device): read as a sequence of parts (bamio.stream_parts).  The head of
+            # the file (header, reference list, the first records for the paired-end / MM-tag peeks) comes from its first blocks.
+            from .bamio import BamPart, bgzf_block_table
+            coff, csize, usize = bgzf_block_table(path)
+            k = int(np.searchsorted(np.cumsum(usize), 4 << 20)) + 1
+            with open(path, "rb") as f:
+                self.bam = BamPart(f.read(int(coff[:k][-1] + csize[:k][-1])), threads=threads)
+            self.stream = dict(path=path, threads=threads, budget=int(os.environ.get("WGBS_STREAM_BYTES", 2 << 30)))   # inflated bytes per part: its SAM text stays < 4 GiB
+            self.header = self.bam.header
+            self.chroms = set(self.bam.refs)
+            return
         if path.endswith(".bam"):
             from .bamio import BamFile, DeviceBam
             # device: the compressed bytes cross PCIe, BGZF inflate + record filtering + SAM formatting run in HBM (csrc/bamdev.cu);
@@ -127,8 +159,9 @@ class _Source:
                 except WgbsError as e:
                     if decode != "auto" or "does not fit in device memory" not in str(e):
                         raise
-                    print(f"[wt bam2pat] {e}; decoding on the host", file=sys.stderr)
-                    self.on_device = False
+                    print(f"[wt bam2pat] {e}; reading the file in parts (--bam_decode stream)", file=sys.stderr)
+                    self.__init__(path, threads, ctx, "stream")
+                    return
             if not self.on_device:
                 self.bam = BamFile(path, threads)
             self.header = self.bam.header
@@ -179,6 +212,8 @@ class _Source:
 
     def weight(self, chrom: str) -> int:
         """how much work a chromosome is (records in a .bam, bytes of SAM text): the LPT weights of the multi-GPU split"""
+        if self.stream is not None:                          # not known without reading the file: its length stands in
+            return int(self.bam.ref_len(chrom)) if hasattr(self.bam, "ref_len") else 1
         if self.bam is not None:
             return self.bam.nrecords(chrom) if chrom in self.bam.refs else 0
         return len(self.sam.get(chrom, b""))
@@ -231,9 +266,10 @@ def add_args(p):
     p.add_argument("--clip", type=int, default=0, help="Clip for each read the first and last CLIP characters [0]")
     p.add_argument("--long", action="store_true", help="Use long format for pat file (add read name to each line)")
     p.add_argument("-@", "--threads", type=int, default=8, help="host threads for BGZF inflate/deflate")
-    p.add_argument("--bam_decode", choices=["auto", "host", "device"], default=os.environ.get("WGBS_BAM_DECODE", "auto"),
+    p.add_argument("--bam_decode", choices=["auto", "host", "device", "stream"], default=os.environ.get("WGBS_BAM_DECODE", "auto"),
                    help="where the .bam is decoded: on the GPU (compressed bytes over PCIe, one warp per BGZF block), on host threads (zlib), "
-                        "or auto = GPU unless the inflated file does not fit in device memory [auto]")
+                        "auto = GPU unless the inflated file does not fit in device memory, or stream = read the file as a sequence of "
+                        "parts of WGBS_STREAM_BYTES inflated bytes (files larger than memory) [auto]")
     p.add_argument("--no_beta", action="store_true", help="Do not generate a beta file")
     p.add_argument("-l", "--lbeta", action="store_true", help="Use lbeta file (uint16) instead of beta (uint8)")
     p.add_argument("-T", "--temp_dir", help="accepted for CLI compatibility (the collapse is a device sort: no temp files)")
@@ -326,6 +362,36 @@ def main(argv=None):
                 ctx.pat2beta(ctx.pats_from_text(b""), 1, ref.nr_sites + 1, meth_cov=mc, zero_first=True)
             parts = []
             mb_total = None
+
+            def view_kw(chrom: str) -> dict:
+                kw = dict(mapq=mapq, exclude_flags=ex, include_flags=inc, read_group=a.read_group)
+                if lists is not None:
+                    kw.update(intervals=lists[0].get(chrom, empty_iv), exclude_intervals=lists[1])
+                return kw
+
+            if src.stream is not None and feq is not None:
+                # one pass over the file, part by part; a chromosome's ChromPile lives from its first part to its last
+                from .bamio import BamPart, stream_parts
+                by_chrom = {r.split(":")[0]: (ri, r) for ri, r in enumerate(regions) if ri in mine}
+                piles: dict[str, ChromPile] = {}
+                opener = lambda data, refs, lens, first: BamPart(data, refs, lens, first, threads=src.stream["threads"])
+                for part, chrom, win, done in stream_parts(path, opener, lambda c: dict(flag_eq=feq, **view_kw(c)), src.stream["budget"]):
+                    if chrom not in by_chrom:
+                        continue
+                    ri, region = by_chrom[chrom]
+                    _, beg, end = parse_region_str(region)
+                    if chrom not in piles:
+                        piles[chrom] = ChromPile(ctx, ref, region, run, mc)
+                    piles[chrom].add(part.view(chrom, beg=beg, end=end, key_window=win, flag_eq=feq, **view_kw(chrom)))
+                    if done:
+                        txt, st = piles.pop(chrom).finish()
+                        if txt is None:
+                            continue
+                        if a.mbias and "mbias" in st:
+                            mb_total = st["mbias"].astype(np.int64) if mb_total is None else mb_total + st["mbias"]
+                        if txt:
+                            parts.append((ri, bgzf_compress(txt, a.threads)))
+                regions = []                                                   # all done above
             for ri, region in enumerate(regions):
                 if ri not in mine:
                     continue

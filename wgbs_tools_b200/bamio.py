@@ -83,6 +83,138 @@ class BamFile:
         self.close()
 
 
+def _part_args(refs, ref_lens):
+    names = (C.c_char_p * max(len(refs), 1))(*[r.encode() for r in refs])
+    lens = (C.c_int32 * max(len(refs), 1))(*[int(x) for x in ref_lens])
+    return names, lens
+
+
+class BamPart(BamFile):
+    """A window of a .bam (consecutive whole BGZF blocks) decoded on host threads: viewed like a BamFile.  `tail` = inflated
+    offset of the first byte that is not part of a complete record (wgbs_bam_open_part)."""
+
+    def __init__(self, data, refs=None, ref_lens=None, first_record: int = 0, threads: int = 0):
+        a = np.frombuffer(data, np.uint8)
+        h = C.c_void_p(); tail = C.c_uint64()
+        if refs is None:
+            check(lib.wgbs_bam_open_part(a.ctypes.data, a.size, 0, None, None, 1, 0, threads, C.byref(h), C.byref(tail)))
+        else:
+            names, lens = _part_args(refs, ref_lens)
+            check(lib.wgbs_bam_open_part(a.ctypes.data, a.size, len(refs), names, lens, 0, int(first_record), threads, C.byref(h), C.byref(tail)))
+        self.h, self.tail = h.value, int(tail.value)
+        self.refs = [lib.wgbs_bam_ref_name(self.h, i).decode() for i in range(lib.wgbs_bam_nref(self.h))]
+        self.ref_lens = list(ref_lens) if ref_lens is not None else None
+        self.inflated_bytes = int(lib.wgbs_bam_inflated_bytes(self.h))
+
+    def last_record(self):
+        """(refid, 0-based POS) of the last complete record; refid -2: no record"""
+        r = C.c_int(); p = C.c_int64()
+        check(lib.wgbs_bam_last_record(self.h, C.byref(r), C.byref(p)))
+        return r.value, p.value
+
+    def first_key(self, refid: int, key: int, **view_kw):
+        """inflated offset of the first record of `refid` that passes the view filters and has template key >= key, or None"""
+        vo, keep = view_opts(self.refs, None, **view_kw)
+        if vo is None:
+            return None
+        off = C.c_uint64(); found = C.c_int()
+        check(lib.wgbs_bam_first_key(self.h, C.byref(vo), refid, int(key), C.byref(off), C.byref(found)))
+        return int(off.value) if found.value else None
+
+
+def bgzf_block_table(path: str):
+    """(coff, csize, usize) int64 arrays of every BGZF block of a file, by hopping over the block headers (18 bytes + the 4-byte
+    ISIZE at the end of each block are read; nothing is inflated)"""
+    import struct
+    coff, csize, usize = [], [], []
+    with open(path, "rb") as f:
+        f.seek(0, 2); fsz = f.tell(); off = 0
+        while off + 28 <= fsz:
+            f.seek(off); h = f.read(18)
+            if len(h) < 18 or h[:4] != b"\x1f\x8b\x08\x04":
+                raise ValueError(f"{path}: not a BGZF file (bad block header at {off})")
+            xlen = struct.unpack_from("<H", h, 10)[0]
+            if h[12:14] == b"BC" and xlen == 6:
+                bs = struct.unpack_from("<H", h, 16)[0] + 1
+            else:                                                   # other extra subfields first: walk them
+                f.seek(off + 12); x = f.read(xlen); bs = 0; k = 0
+                while k + 4 <= xlen:
+                    sl = struct.unpack_from("<H", x, k + 2)[0]
+                    if x[k:k + 2] == b"BC" and sl == 2:
+                        bs = struct.unpack_from("<H", x, k + 4)[0] + 1; break
+                    k += 4 + sl
+            if bs < 28 or off + bs > fsz:
+                raise ValueError(f"{path}: corrupt BGZF block at {off}")
+            f.seek(off + bs - 4); us = struct.unpack("<I", f.read(4))[0]
+            coff.append(off); csize.append(bs); usize.append(us); off += bs
+        if off != fsz:
+            raise ValueError(f"{path}: {fsz - off} trailing bytes after the last BGZF block")
+    return np.array(coff, np.int64), np.array(csize, np.int64), np.array(usize, np.int64)
+
+
+def stream_parts(path: str, open_part, view_kw_for, budget: int):
+    """Read a coordinate-sorted .bam that does not fit in memory as a sequence of parts and yield
+        (part, chrom, key_window, chrom_done)
+    such that piling up, for every yielded item, the records of `chrom` in `part` that pass the view filters AND whose template
+    key (max(POS, PNEXT), wgbs_view_opts) lies in key_window, gives every template of the file exactly once with all its
+    records in one part.  chrom_done: no later item carries this chromosome.  The part is closed after its items are consumed.
+        open_part(bytes, refs, ref_lens, first_record) -> part object (BamPart / DeviceBamPart): refs is None for the first part
+        view_kw_for(chrom) -> the view filters (keyword arguments of view_opts) the caller applies to that chromosome
+        budget: inflated bytes per part (a part is at least one block; it grows when a single pile of deferred templates does not
+        fit -- deferred are the templates whose key is not yet below the POS of the part's last record)
+    Why it is exact: the file is sorted, so when a part ends inside chromosome c at POS P, every record with POS < P is in this
+    part or an earlier one.  Templates with key < P are complete (both mates have POS <= key); the others are deferred, and the
+    next part starts at the block holding the first deferred record (or the cut-off record), found by first_key()."""
+    coff, csize, usize = bgzf_block_table(path)
+    nb = coff.size
+    uoff = np.concatenate([[0], np.cumsum(usize)])
+    refs = ref_lens = None
+    b = 0; first_record = 0; prev_hi: dict[int, int] = {}
+    grow = 1; at_start = True
+    with open(path, "rb") as f:
+        while b < nb:
+            e = int(np.searchsorted(uoff, uoff[b] + budget * grow, side="right")) - 1
+            e = min(max(e, b + 1), nb)
+            f.seek(int(coff[b])); data = f.read(int(coff[e - 1] + csize[e - 1] - coff[b]))
+            part = open_part(data, None if at_start else refs, ref_lens, first_record)     # the first part carries the BAM header
+            del data
+            if refs is None:
+                refs, ref_lens = list(part.refs), [0] * len(part.refs)
+            final = e == nb
+            L, P = part.last_record()
+            try:
+                present = [c for c in range(len(refs)) if part.nrecords(refs[c]) > 0]
+                restart = part.tail
+                if not final and L >= 0:
+                    r = part.first_key(L, P, **view_kw_for(refs[L]))
+                    if r is not None:
+                        restart = min(restart, r)
+                if not final:
+                    nblk = int(np.searchsorted(uoff, uoff[b] + restart, side="right")) - 1       # the block holding that offset
+                    if nblk <= b and restart < part.inflated_bytes:
+                        # the deferred templates reach back into the first block of this part: nothing would be gained -- take more
+                        if e == nb:
+                            final = True
+                        else:
+                            grow *= 2
+                            continue
+                for c in present:
+                    done = final or c != L
+                    hi = (1 << 40) if done else P
+                    lo = prev_hi.pop(c, 0)
+                    if not done:
+                        prev_hi[c] = hi
+                    if hi > lo:
+                        yield part, refs[c], (lo, hi), done
+            finally:
+                part.close()
+            if final:
+                break
+            grow = 1; at_start = False
+            first_record = int(uoff[b] + restart - uoff[nblk])
+            b = nblk
+
+
 class DeviceBam:
     """A .bam decoded ON THE GPU (csrc/bamdev.cu): the compressed bytes are uploaded, BGZF blocks inflated by one warp each,
     records located and filtered in HBM.  Same interface and byte-identical views as BamFile; `view_dev` keeps the SAM

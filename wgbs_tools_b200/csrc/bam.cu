@@ -147,23 +147,20 @@ bool format_record(const wgbs_bam *B, const uint8_t *r, OutBuf &ob) {
 
 }  // namespace
 
-extern "C" int wgbs_bam_open(const char *path, int threads, wgbs_bam **out) {
-    if (!path || !out) return wgbs_set_err("wgbs_bam_open: null argument");
-    *out = nullptr;
+namespace {
+// comp[0..fsz): consecutive whole BGZF blocks.  part == false: a whole file (BAM header first, every record complete).
+// part == true: a window of a file -- the reference list comes from the caller, records are indexed from inflated offset
+// `first_record` on, and the last record may be cut off by the end of the window: *tail = inflated offset of the first byte
+// that is not part of a complete record.
+int open_stream(const char *who, const uint8_t *comp, uint64_t fsz, int threads, bool part, int n_ref_in, const char *const *ref_names,
+                const int32_t *ref_lens, uint64_t first_record, wgbs_bam **out, uint64_t *tail) {
     const bool dbg = getenv("WGBS_BAM_DEBUG") != nullptr; auto T0 = std::chrono::steady_clock::now();
     auto lap = [&](const char *what) { if (dbg) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "[bam] %-10s %.3f s\n", what, std::chrono::duration<double>(t - T0).count()); T0 = t; } };
-    FILE *f = fopen(path, "rb");
-    if (!f) return wgbs_set_err("wgbs_bam_open: cannot open %s", path);
-    fseek(f, 0, SEEK_END); const long fsz = ftell(f); fseek(f, 0, SEEK_SET);
-    std::vector<uint8_t> comp((size_t)fsz);
-    if (fsz && fread(comp.data(), 1, (size_t)fsz, f) != (size_t)fsz) { fclose(f); return wgbs_set_err("wgbs_bam_open: short read on %s", path); }
-    fclose(f);
-    lap("read");
     // 1. BGZF block table
     std::vector<Block> blocks; uint64_t off = 0, uoff = 0;
-    while (off + 28 <= (uint64_t)fsz) {
-        const uint8_t *h = comp.data() + off;
-        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return wgbs_set_err("%s: not a BGZF file (bad block header at %llu)", path, (unsigned long long)off);
+    while (off + 28 <= fsz) {
+        const uint8_t *h = comp + off;
+        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return wgbs_set_err("%s: not a BGZF file (bad block header at %llu)", who, (unsigned long long)off);
         const uint16_t xlen = rd16(h + 10);
         uint32_t bsize = 0; bool found = false;
         for (uint32_t x = 0; x + 4 <= xlen;) {
@@ -171,10 +168,11 @@ extern "C" int wgbs_bam_open(const char *path, int threads, wgbs_bam **out) {
             if (sf[0] == 'B' && sf[1] == 'C' && sl == 2) { bsize = rd16(sf + 4) + 1u; found = true; break; }
             x += 4 + sl;
         }
-        if (!found || off + bsize > (uint64_t)fsz) return wgbs_set_err("%s: corrupt BGZF block at %llu", path, (unsigned long long)off);
+        if (!found || off + bsize > fsz) return wgbs_set_err("%s: corrupt BGZF block at %llu", who, (unsigned long long)off);
         Block b; b.coff = off; b.csize = bsize; b.usize = rd32(h + bsize - 4); b.uoff = uoff;
         blocks.push_back(b); off += bsize; uoff += b.usize;
     }
+    if (part && off != fsz) return wgbs_set_err("%s: a part must consist of whole BGZF blocks (%llu trailing bytes)", who, (unsigned long long)(fsz - off));
     wgbs_bam *B = new wgbs_bam();
     B->threads = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
     lap("blocks");
@@ -184,7 +182,7 @@ extern "C" int wgbs_bam_open(const char *path, int threads, wgbs_bam **out) {
     std::atomic<size_t> next(0); std::atomic<int> bad(0);
     auto work = [&]() {
         for (size_t i; (i = next.fetch_add(1)) < blocks.size();)
-            if (inflate_block(comp.data() + blocks[i].coff, blocks[i].csize, B->data.data() + blocks[i].uoff, blocks[i].usize)) bad.store(1);
+            if (inflate_block(comp + blocks[i].coff, blocks[i].csize, B->data.data() + blocks[i].uoff, blocks[i].usize)) bad.store(1);
     };
     {
         std::vector<std::thread> th; int nt = std::min<int>(B->threads, (int)std::max<size_t>(1, blocks.size() / 4));
@@ -193,40 +191,124 @@ extern "C" int wgbs_bam_open(const char *path, int threads, wgbs_bam **out) {
         for (auto &t : th) t.join();
     }
     lap("inflate");
-    if (bad.load()) { delete B; return wgbs_set_err("%s: inflate failed (corrupt BGZF block or CRC32 mismatch)", path); }
+    if (bad.load()) { delete B; return wgbs_set_err("%s: inflate failed (corrupt BGZF block or CRC32 mismatch)", who); }
     // 3. header
     const uint8_t *d = B->data.data(); const uint64_t n = B->data.size();
-    if (n < 12 || memcmp(d, "BAM\1", 4)) { delete B; return wgbs_set_err("%s: not a BAM file", path); }
-    const uint32_t l_text = rd32(d + 4);
-    if (8ull + l_text + 4 > n) { delete B; return wgbs_set_err("%s: truncated BAM header", path); }
-    B->header_text.assign((const char *)d + 8, strnlen((const char *)d + 8, l_text));
-    uint64_t p = 8ull + l_text; const uint32_t n_ref = rd32(d + p); p += 4;
-    for (uint32_t i = 0; i < n_ref; i++) {
-        if (p + 4 > n) { delete B; return wgbs_set_err("%s: truncated reference list", path); }
-        const uint32_t l = rd32(d + p); p += 4;
-        if (p + l + 4 > n) { delete B; return wgbs_set_err("%s: truncated reference list", path); }
-        B->ref_names.emplace_back((const char *)d + p, l ? l - 1 : 0); p += l;
-        B->ref_lens.push_back(rdi32(d + p)); p += 4;
+    uint64_t p = 0; uint32_t n_ref = 0;
+    if (!part) {
+        if (n < 12 || memcmp(d, "BAM\1", 4)) { delete B; return wgbs_set_err("%s: not a BAM file", who); }
+        const uint32_t l_text = rd32(d + 4);
+        if (8ull + l_text + 4 > n) { delete B; return wgbs_set_err("%s: truncated BAM header", who); }
+        B->header_text.assign((const char *)d + 8, strnlen((const char *)d + 8, l_text));
+        p = 8ull + l_text; n_ref = rd32(d + p); p += 4;
+        for (uint32_t i = 0; i < n_ref; i++) {
+            if (p + 4 > n) { delete B; return wgbs_set_err("%s: truncated reference list", who); }
+            const uint32_t l = rd32(d + p); p += 4;
+            if (p + l + 4 > n) { delete B; return wgbs_set_err("%s: truncated reference list", who); }
+            B->ref_names.emplace_back((const char *)d + p, l ? l - 1 : 0); p += l;
+            B->ref_lens.push_back(rdi32(d + p)); p += 4;
+        }
+    } else {
+        n_ref = (uint32_t)n_ref_in;
+        for (uint32_t i = 0; i < n_ref; i++) { B->ref_names.emplace_back(ref_names[i]); B->ref_lens.push_back(ref_lens ? ref_lens[i] : 0); }
+        p = first_record;
+        if (p > n) { delete B; return wgbs_set_err("%s: first record offset %llu beyond the part (%llu inflated bytes)", who, (unsigned long long)p, (unsigned long long)n); }
     }
     // 4. record table (records are length-prefixed: a sequential walk) + per-reference ranges
     B->ref_first.assign(n_ref + 1, 0); B->ref_last.assign(n_ref + 1, 0);
     int32_t cur = -2; uint64_t idx = 0;
     while (p + 4 <= n) {
         const uint32_t bs = rd32(d + p);
-        if (bs < 32 || p + 4 + bs > n) { delete B; return wgbs_set_err("%s: corrupt BAM record at uncompressed offset %llu", path, (unsigned long long)p); }
+        if (part && bs >= 32 && p + 4 + bs > n) break;                     // cut off by the end of the window: the next part starts here
+        if (bs < 32 || p + 4 + bs > n) { delete B; return wgbs_set_err("%s: corrupt BAM record at uncompressed offset %llu", who, (unsigned long long)p); }
         const int32_t refid = rdi32(d + p + 4);
         const uint32_t slot = (refid >= 0 && (uint32_t)refid < n_ref) ? (uint32_t)refid : n_ref;
         if (refid != cur) {
-            if (B->ref_last[slot] != 0) { delete B; return wgbs_set_err("%s is not sorted by coordinate (reference %d appears in two separate runs)", path, refid); }
+            if (B->ref_last[slot] != 0) { delete B; return wgbs_set_err("%s is not sorted by coordinate (reference %d appears in two separate runs)", who, refid); }
             B->ref_first[slot] = idx; cur = refid;
         }
         B->ref_last[slot] = idx + 1;
         B->rec_off.push_back(p); p += 4 + bs; idx++;
     }
     lap("walk");
+    if (tail) *tail = p;
     *out = B;
     return 0;
 }
+}  // namespace
+
+extern "C" int wgbs_bam_open(const char *path, int threads, wgbs_bam **out) {
+    if (!path || !out) return wgbs_set_err("wgbs_bam_open: null argument");
+    *out = nullptr;
+    FILE *f = fopen(path, "rb");
+    if (!f) return wgbs_set_err("wgbs_bam_open: cannot open %s", path);
+    fseek(f, 0, SEEK_END); const long fsz = ftell(f); fseek(f, 0, SEEK_SET);
+    std::vector<uint8_t> comp((size_t)fsz);
+    if (fsz && fread(comp.data(), 1, (size_t)fsz, f) != (size_t)fsz) { fclose(f); return wgbs_set_err("wgbs_bam_open: short read on %s", path); }
+    fclose(f);
+    return open_stream(path, comp.data(), (uint64_t)fsz, threads, false, 0, nullptr, nullptr, 0, out, nullptr);
+}
+
+// A window of a .bam that does not fit in memory as a whole (bam2pat streams such files): see wgbs_b200.h
+extern "C" int wgbs_bam_open_part(const void *bgzf, size_t nbytes, int n_ref, const char *const *ref_names, const int32_t *ref_lens,
+                                  int has_header, uint64_t first_record, int threads, wgbs_bam **out, uint64_t *tail) {
+    if (!bgzf || !out || !tail || (!has_header && n_ref > 0 && !ref_names)) return wgbs_set_err("wgbs_bam_open_part: null argument");
+    *out = nullptr;
+    if (has_header) {
+        // the first window of a file: header, then records; its last record may be cut off like any other window's
+        wgbs_bam *H = nullptr;
+        // parse the header with the whole-file walker disabled: open as a part at the offset right behind the reference list
+        // (found by a header-only pass over the first inflated bytes)
+        std::vector<const char *> names; std::vector<int32_t> lens; std::vector<std::string> keep; uint64_t first = 0; std::string text;
+        {
+            // inflate just enough leading blocks to hold the header
+            const uint8_t *c = (const uint8_t *)bgzf; uint64_t off = 0; std::vector<uint8_t> head;
+            auto need = [&](uint64_t upto) -> bool {
+                while (head.size() < upto && off + 28 <= nbytes) {
+                    const uint8_t *h = c + off;
+                    if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return false;
+                    const uint16_t xlen = rd16(h + 10); uint32_t bsize = 0;
+                    for (uint32_t x = 0; x + 4 <= xlen;) { const uint8_t *sf = h + 12 + x; const uint16_t sl = rd16(sf + 2); if (sf[0] == 'B' && sf[1] == 'C' && sl == 2) { bsize = rd16(sf + 4) + 1u; break; } x += 4 + sl; }
+                    if (!bsize || off + bsize > nbytes) return false;
+                    const uint32_t usize = rd32(h + bsize - 4); const size_t at = head.size();
+                    head.resize(at + usize);
+                    if (inflate_block(h, bsize, head.data() + at, usize)) return false;
+                    off += bsize;
+                }
+                return head.size() >= upto;
+            };
+            if (!need(12) || memcmp(head.data(), "BAM\1", 4)) return wgbs_set_err("wgbs_bam_open_part: not a BAM file");
+            const uint32_t l_text = rd32(head.data() + 4);
+            if (!need(8ull + l_text + 4)) return wgbs_set_err("wgbs_bam_open_part: truncated BAM header");
+            text.assign((const char *)head.data() + 8, strnlen((const char *)head.data() + 8, l_text));
+            uint64_t p = 8ull + l_text; const uint32_t nr = rd32(head.data() + p); p += 4;
+            for (uint32_t i = 0; i < nr; i++) {
+                if (!need(p + 4)) return wgbs_set_err("wgbs_bam_open_part: truncated reference list");
+                const uint32_t l = rd32(head.data() + p); p += 4;
+                if (!need(p + l + 4)) return wgbs_set_err("wgbs_bam_open_part: truncated reference list");
+                keep.emplace_back((const char *)head.data() + p, l ? strnlen((const char *)head.data() + p, l - 1) : 0); p += l;
+                lens.push_back(rdi32(head.data() + p)); p += 4;
+            }
+            first = p;
+        }
+        for (auto &k : keep) names.push_back(k.c_str());
+        int rc = open_stream("wgbs_bam_open_part", (const uint8_t *)bgzf, nbytes, threads, true, (int)names.size(), names.data(), lens.data(), first, &H, tail);
+        if (rc < 0) return rc;
+        H->header_text = text;
+        *out = H;
+        return 0;
+    }
+    return open_stream("wgbs_bam_open_part", (const uint8_t *)bgzf, nbytes, threads, true, n_ref, ref_names, ref_lens, first_record, out, tail);
+}
+
+// (refid, 0-based POS) of the last complete record of a file / part; *refid = -2 when there is no record
+extern "C" int wgbs_bam_last_record(const wgbs_bam *B, int *refid, int64_t *pos) {
+    if (!B || !refid || !pos) return wgbs_set_err("wgbs_bam_last_record: null argument");
+    *refid = -2; *pos = -1;
+    if (!B->rec_off.empty()) { const uint8_t *r = B->data.data() + B->rec_off.back(); *refid = rdi32(r + 4); *pos = rdi32(r + 8); }
+    return 0;
+}
+extern "C" uint64_t wgbs_bam_inflated_bytes(const wgbs_bam *B) { return B ? B->data.size() : 0; }
 
 extern "C" void wgbs_bam_close(wgbs_bam *B) { delete B; }
 extern "C" int wgbs_bam_nref(const wgbs_bam *B) { return B ? (int)B->ref_names.size() : -1; }
@@ -262,6 +344,45 @@ const char *find_z_tag(const uint8_t *t, const uint8_t *end, char a, char b, siz
 }
 }  // namespace
 
+// the `samtools view` filters of wgbs_view_opts on one record (r -> block_size)
+static bool rec_passes(const uint8_t *r, const wgbs_view_opts *vo, size_t rg_len) {
+    const int min_mapq = vo->min_mapq, exclude_flags = vo->exclude_flags, include_flags = vo->include_flags;
+    const int64_t beg = vo->beg, end = vo->end;
+    const bool need_span = end > 0 || vo->n_iv;
+    const uint16_t flag = rd16(r + 4 + 14); const uint8_t mapq = r[4 + 9];
+    if (mapq < min_mapq || (flag & exclude_flags) || (include_flags && (flag & include_flags) != include_flags)) return false;
+    if (vo->n_flag_eq) {                                     // awk '($2 == A || $2 == B)' (bam2pat.py:135-144)
+        bool ok = false;
+        for (int k = 0; k < vo->n_flag_eq; k++) ok |= (int)flag == vo->flag_eq[k];
+        if (!ok) return false;
+    }
+    if (vo->key_end > 0) {                                   // template window: max(POS, PNEXT) of a pair on one reference (wgbs_b200.h)
+        const int32_t rid = rdi32(r + 4), pos0 = rdi32(r + 8), nref = rdi32(r + 24), npos = rdi32(r + 28);
+        const int64_t key = ((flag & 1) && !(flag & 8) && nref == rid && npos > pos0) ? npos : pos0;
+        if (key < vo->key_beg || key >= vo->key_end) return false;
+    }
+    const uint16_t n_cig = rd16(r + 4 + 12); const uint8_t l_name = r[4 + 8];
+    if (need_span) {
+        const int64_t pos0 = (int64_t)rdi32(r + 8);          // 0-based
+        int64_t span = 0; const uint8_t *cig = r + 36 + l_name;
+        for (uint16_t k = 0; k < n_cig; k++) { uint32_t c = rd32(cig + 4 * k); uint32_t op = c & 15; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += c >> 4; }
+        if (span < 1) span = 1;
+        if (end > 0 && (pos0 + 1 > end || pos0 + span < beg)) return false;
+        if (vo->n_iv) {                                      // [pos0, pos0+span) against sorted disjoint [iv_beg, iv_end)
+            const int64_t *e = std::upper_bound(vo->iv_end, vo->iv_end + vo->n_iv, pos0);     // first interval ending after pos0
+            const bool hit = e != vo->iv_end + vo->n_iv && vo->iv_beg[e - vo->iv_end] < pos0 + span;
+            if (hit == (vo->iv_exclude != 0)) return false;
+        }
+    }
+    if (rg_len || vo->read_group) {                          // samtools view -r RG
+        const uint32_t bs = rd32(r); const int32_t l_seq = rdi32(r + 4 + 16);
+        const uint8_t *tags = r + 36 + l_name + 4 * (size_t)n_cig + (size_t)((l_seq + 1) / 2) + (size_t)(l_seq > 0 ? l_seq : 0);
+        size_t zl = 0; const char *z = find_z_tag(tags, r + 4 + bs, 'R', 'G', &zl);
+        if (!z || zl != rg_len || memcmp(z, vo->read_group, zl)) return false;
+    }
+    return true;
+}
+
 // SAM text of the records that pass the filters of `o` (see wgbs_view_opts in the header).  *text is malloc'ed: release
 // with wgbs_host_free.
 extern "C" int wgbs_bam_view_ex(const wgbs_bam *B, const wgbs_view_opts *vo, char **text, size_t *nbytes, uint64_t *nrecords) {
@@ -285,37 +406,7 @@ extern "C" int wgbs_bam_view_ex(const wgbs_bam *B, const wgbs_view_opts *vo, cha
         if (!o.reserve((vo->max_records ? std::min<uint64_t>(b - a, vo->max_records) : (b - a)) * 384 + 4096)) { oom.store(1); return; }
         for (uint64_t i = a; i < b; i++) {
             const uint8_t *r = B->data.data() + B->rec_off[i];
-            const uint16_t flag = rd16(r + 4 + 14); const uint8_t mapq = r[4 + 9];
-            if (mapq < min_mapq || (flag & exclude_flags) || (include_flags && (flag & include_flags) != include_flags)) continue;
-            if (vo->n_flag_eq) {                                     // awk '($2 == A || $2 == B)' (bam2pat.py:135-144)
-                bool ok = false;
-                for (int k = 0; k < vo->n_flag_eq; k++) ok |= (int)flag == vo->flag_eq[k];
-                if (!ok) continue;
-            }
-            if (vo->key_end > 0) {                                   // template window: max(POS, PNEXT) of a pair on one reference (wgbs_b200.h)
-                const int32_t rid = rdi32(r + 4), pos0 = rdi32(r + 8), nref = rdi32(r + 24), npos = rdi32(r + 28);
-                const int64_t key = ((flag & 1) && !(flag & 8) && nref == rid && npos > pos0) ? npos : pos0;
-                if (key < vo->key_beg || key >= vo->key_end) continue;
-            }
-            const uint16_t n_cig = rd16(r + 4 + 12); const uint8_t l_name = r[4 + 8];
-            if (need_span) {
-                const int64_t pos0 = (int64_t)rdi32(r + 8);          // 0-based
-                int64_t span = 0; const uint8_t *cig = r + 36 + l_name;
-                for (uint16_t k = 0; k < n_cig; k++) { uint32_t c = rd32(cig + 4 * k); uint32_t op = c & 15; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += c >> 4; }
-                if (span < 1) span = 1;
-                if (end > 0 && (pos0 + 1 > end || pos0 + span < beg)) continue;
-                if (vo->n_iv) {                                      // [pos0, pos0+span) against sorted disjoint [iv_beg, iv_end)
-                    const int64_t *e = std::upper_bound(vo->iv_end, vo->iv_end + vo->n_iv, pos0);     // first interval ending after pos0
-                    const bool hit = e != vo->iv_end + vo->n_iv && vo->iv_beg[e - vo->iv_end] < pos0 + span;
-                    if (hit == (vo->iv_exclude != 0)) continue;
-                }
-            }
-            if (rg_len || vo->read_group) {                          // samtools view -r RG
-                const uint32_t bs = rd32(r); const int32_t l_seq = rdi32(r + 4 + 16);
-                const uint8_t *tags = r + 36 + l_name + 4 * (size_t)n_cig + (size_t)((l_seq + 1) / 2) + (size_t)(l_seq > 0 ? l_seq : 0);
-                size_t zl = 0; const char *z = find_z_tag(tags, r + 4 + bs, 'R', 'G', &zl);
-                if (!z || zl != rg_len || memcmp(z, vo->read_group, zl)) continue;
-            }
+            if (!rec_passes(r, vo, rg_len)) continue;
             if (!format_record(B, r, o)) { oom.store(1); return; }
             cnt[t]++;
             if (vo->max_records && cnt[t] >= vo->max_records) break;
@@ -340,6 +431,25 @@ extern "C" int wgbs_bam_view_ex(const wgbs_bam *B, const wgbs_view_opts *vo, cha
         for (auto &t : th) t.join();
     }
     *text = buf; *nbytes = tot; if (nrecords) *nrecords = nr;
+    return 0;
+}
+
+// Inflated offset (in this file / part) of the first record of reference `refid` that passes the filters of `vo` (its key
+// window ignored) and whose template key is >= key; *found = 0 when there is none.  bam2pat's streaming reader restarts the
+// next window of the file there: everything a later template window needs lies at or behind that record.
+extern "C" int wgbs_bam_first_key(const wgbs_bam *B, const wgbs_view_opts *vo, int refid, int64_t key, uint64_t *offset, int *found) {
+    if (!B || !vo || !offset || !found) return wgbs_set_err("wgbs_bam_first_key: null argument");
+    *found = 0; *offset = 0;
+    if (refid < 0 || refid >= (int)B->ref_names.size()) return 0;
+    wgbs_view_opts v = *vo; v.key_beg = 0; v.key_end = 0; v.refid = refid;
+    const size_t rg_len = v.read_group ? strlen(v.read_group) : 0;
+    for (uint64_t i = B->ref_first[refid]; i < B->ref_last[refid]; i++) {
+        const uint8_t *r = B->data.data() + B->rec_off[i];
+        const uint16_t flag = rd16(r + 4 + 14);
+        const int32_t pos0 = rdi32(r + 8), nref = rdi32(r + 24), npos = rdi32(r + 28);
+        const int64_t k = ((flag & 1) && !(flag & 8) && nref == refid && npos > pos0) ? npos : pos0;
+        if (k >= key && rec_passes(r, &v, rg_len)) { *offset = B->rec_off[i]; *found = 1; return 0; }
+    }
     return 0;
 }
 
