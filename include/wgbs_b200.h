@@ -277,6 +277,12 @@ const char *wgbs_dbam_ref_name(const wgbs_dbam *, int i);
 const char *wgbs_dbam_header(const wgbs_dbam *);
 uint64_t wgbs_dbam_nrecords(const wgbs_dbam *, int refid);
 uint64_t wgbs_dbam_inflated_bytes(const wgbs_dbam *);
+/* parts of a file larger than device memory: wgbs_bam_open_part / wgbs_bam_last_record / wgbs_bam_first_key on the device (the
+ * bytes of the part are uploaded, inflated and indexed in HBM; same arguments, same results) */
+int wgbs_dbam_open_part(wgbs_ctx *, const void *bgzf, size_t nbytes, int n_ref, const char *const *ref_names, const int32_t *ref_lens,
+                        int has_header, uint64_t first_record, wgbs_dbam **out, uint64_t *tail);
+int wgbs_dbam_last_record(wgbs_ctx *, const wgbs_dbam *, int *refid, int64_t *pos);
+int wgbs_dbam_first_key(wgbs_ctx *, const wgbs_dbam *, const wgbs_view_opts *, int refid, int64_t key, uint64_t *offset, int *found);
 /* *dev_text: DEVICE buffer holding the SAM text of the passing records (release with wgbs_dev_free) */
 int wgbs_dbam_view(wgbs_ctx *, const wgbs_dbam *, const wgbs_view_opts *, char **dev_text, size_t *nbytes, uint64_t *nrecords);
 /* wgbs_dbam_view + wgbs_pileup_sam_mbias without leaving the device (mbias may be NULL) */

@@ -384,3 +384,30 @@ def test_bam2pat_cli_template_windows(ctx, bamio, tmp_path, monkeypatch, decode,
         bam2pat.main([str(bam), "--genome", str(refdir), "-o", str(out), "--bam_decode", decode])
         outs.append((gzip.decompress((out / "s.pat.gz").read_bytes()), (out / "s.beta").read_bytes()))
     assert outs[0] == outs[1] and len(outs[0][0]) > 1000
+
+
+@pytest.mark.staged
+def test_device_parts_equal_host_parts_and_streamed_cli(ctx, bamio, tmp_path, monkeypatch):
+    """wgbs_dbam_open_part / last_record / first_key: a file streamed as parts decoded on the device gives the same items (same
+    views, same tails) as the host part reader, and `bam2pat --bam_decode stream` with WGBS_STREAM_BACKEND=device the same files
+    as decoding the file as a whole"""
+    from wgbs_tools_b200 import bam2pat
+    g1 = synth.make_genome(31, "chr1", 300_000, first_idx=1); g2 = synth.make_genome(32, "chr2", 150_000, first_idx=1 + g1.n_cpg)
+    sam = synth.make_sam(g1, 9_000, 4, paired=True, single_frac=0.03, name_prefix="a") + synth.make_sam(g2, 4_000, 5, paired=True, name_prefix="b")
+    bam = tmp_path / "s.bam"; bam.write_bytes(bamio.sam_to_bam(sam, [("chr1", g1.length), ("chr2", g2.length)]))
+    kw = dict(mapq=10, exclude_flags=1796, include_flags=3)
+    items = {}
+    for name, opener in (("host", lambda d, r, l, f: bamio.BamPart(d, r, l, f, threads=2)), ("device", lambda d, r, l, f: bamio.DeviceBamPart(ctx, d, r, l, f))):
+        items[name] = [(chrom, win, done, part.tail, part.view(chrom, key_window=win, **kw)) for part, chrom, win, done in bamio.stream_parts(str(bam), opener, lambda c: kw, 200_000)]
+    assert items["host"] == items["device"] and len(items["host"]) > 6
+    refdir = tmp_path / "ref"; refdir.mkdir()
+    with gzip.open(refdir / "CpG.bed.gz", "wb") as f:
+        f.write(g1.dict_text() + g2.dict_text())
+    (refdir / "CpG.chrome.size").write_text(f"chr1\t{g1.n_cpg}\nchr2\t{g2.n_cpg}\n"); (refdir / "chrome.size").write_text(f"chr1\t{g1.length}\nchr2\t{g2.length}\n")
+    outs = []
+    for tag, decode, backend in (("whole", "host", "host"), ("stream_host", "stream", "host"), ("stream_dev", "stream", "device")):
+        monkeypatch.setenv("WGBS_STREAM_BACKEND", backend); monkeypatch.setenv("WGBS_STREAM_BYTES", "200000")
+        out = tmp_path / tag; out.mkdir()
+        bam2pat.main([str(bam), "--genome", str(refdir), "-o", str(out), "--bam_decode", decode])
+        outs.append((gzip.decompress((out / "s.pat.gz").read_bytes()), (out / "s.beta").read_bytes()))
+    assert outs[0] == outs[1] == outs[2] and len(outs[0][0]) > 1000

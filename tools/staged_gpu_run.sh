@@ -12,6 +12,7 @@ run suite 600 python -m pytest tests -m gpu -x -q -k "not staged" -p no:cachepro
 run inflate_teams 120 python -m pytest tests/test_zz_bamdev_gpu.py -m gpu -q -k "team_kernels"
 run pat_tiles 120 python -m pytest tests/test_pat_gpu.py -m gpu -q -k "tile_parser"
 run seg_plan 120 python -m pytest tests/test_segment_gpu.py -m gpu -q -k "exact_wave_plan"
+run dev_parts 180 python -m pytest tests/test_zz_bamdev_gpu.py -m gpu -q -k "device_parts"
 # 2. the bench with all child legs (direct route, team decoders, batches in flight, segment at scale, pat parsers)
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/staged_bench.json 2> gpurun_out/staged_bench.err; echo "bench rc=$?"
 python - <<'P'

@@ -89,6 +89,9 @@ def _load():
         "wgbs_dbam_open": (C.c_int, [vp, vp, sz, C.POINTER(vp)]),
         "wgbs_dbam_open_file": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
         "wgbs_dbam_close": (None, [vp, vp]),
+        "wgbs_dbam_open_part": (C.c_int, [vp, vp, sz, C.c_int, vp, vp, C.c_int, u64, C.POINTER(vp), C.POINTER(u64)]),
+        "wgbs_dbam_last_record": (C.c_int, [vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
+        "wgbs_dbam_first_key": (C.c_int, [vp, vp, C.POINTER(ViewOpts), C.c_int, C.c_int64, C.POINTER(u64), C.POINTER(C.c_int)]),
         "wgbs_dbam_nref": (C.c_int, [vp]),
         "wgbs_dbam_ref_name": (C.c_char_p, [vp, C.c_int]),
         "wgbs_dbam_header": (C.c_char_p, [vp]),

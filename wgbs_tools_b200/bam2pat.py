@@ -371,10 +371,15 @@ def main(argv=None):
 
             if src.stream is not None and feq is not None:
                 # one pass over the file, part by part; a chromosome's ChromPile lives from its first part to its last
-                from .bamio import BamPart, stream_parts
+                from .bamio import BamPart, DeviceBamPart, stream_parts
                 by_chrom = {r.split(":")[0]: (ri, r) for ri, r in enumerate(regions) if ri in mine}
                 piles: dict[str, ChromPile] = {}
-                opener = lambda data, refs, lens, first: BamPart(data, refs, lens, first, threads=src.stream["threads"])
+                # parts decoded on host threads, or (WGBS_STREAM_BACKEND=device; staged) uploaded compressed and decoded in HBM
+                on_dev = os.environ.get("WGBS_STREAM_BACKEND", "host") == "device"
+                if on_dev:
+                    opener = lambda data, refs, lens, first: DeviceBamPart(ctx, data, refs, lens, first)
+                else:
+                    opener = lambda data, refs, lens, first: BamPart(data, refs, lens, first, threads=src.stream["threads"])
                 for part, chrom, win, done in stream_parts(path, opener, lambda c: dict(flag_eq=feq, **view_kw(c)), src.stream["budget"]):
                     if chrom not in by_chrom:
                         continue
@@ -382,7 +387,11 @@ def main(argv=None):
                     _, beg, end = parse_region_str(region)
                     if chrom not in piles:
                         piles[chrom] = ChromPile(ctx, ref, region, run, mc)
-                    piles[chrom].add(part.view(chrom, beg=beg, end=end, key_window=win, flag_eq=feq, **view_kw(chrom)))
+                    vkw = dict(beg=beg, end=end, key_window=win, flag_eq=feq, **view_kw(chrom))
+                    if on_dev:
+                        piles[chrom].add(lambda ix, _p=part, _c=chrom, _v=vkw, **kw: _p.pileup(ix, _c, view=_v, **kw))
+                    else:
+                        piles[chrom].add(part.view(chrom, **vkw))
                     if done:
                         txt, st = piles.pop(chrom).finish()
                         if txt is None:

@@ -299,6 +299,35 @@ class DeviceBam:
         self.close()
 
 
+class DeviceBamPart(DeviceBam):
+    """A window of a .bam decoded on the GPU (wgbs_dbam_open_part): the part's bytes are uploaded, inflated and indexed in HBM;
+    used like a DeviceBam (view / view_dev / pileup), plus what bamio.stream_parts asks of a part"""
+
+    def __init__(self, ctx, data, refs=None, ref_lens=None, first_record: int = 0):
+        a = np.frombuffer(data, np.uint8)
+        h = C.c_void_p(); tail = C.c_uint64()
+        if refs is None:
+            check(lib.wgbs_dbam_open_part(ctx.h, a.ctypes.data, a.size, 0, None, None, 1, 0, C.byref(h), C.byref(tail)))
+        else:
+            names, lens = _part_args(refs, ref_lens)
+            check(lib.wgbs_dbam_open_part(ctx.h, a.ctypes.data, a.size, len(refs), names, lens, 0, int(first_record), C.byref(h), C.byref(tail)))
+        self.ctx, self.h, self.tail = ctx, h.value, int(tail.value)
+        self.refs = [lib.wgbs_dbam_ref_name(self.h, i).decode() for i in range(lib.wgbs_dbam_nref(self.h))]
+
+    def last_record(self):
+        r = C.c_int(); p = C.c_int64()
+        check(lib.wgbs_dbam_last_record(self.ctx.h, self.h, C.byref(r), C.byref(p)))
+        return r.value, p.value
+
+    def first_key(self, refid: int, key: int, **view_kw):
+        vo, keep = view_opts(self.refs, None, **view_kw)
+        if vo is None:
+            return None
+        off = C.c_uint64(); found = C.c_int()
+        check(lib.wgbs_dbam_first_key(self.ctx.h, self.h, C.byref(vo), refid, int(key), C.byref(off), C.byref(found)))
+        return int(off.value) if found.value else None
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # writer (test inputs): SAM text -> BAM bytes
 # ----------------------------------------------------------------------------------------------------------------------

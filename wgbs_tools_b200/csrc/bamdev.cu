@@ -348,7 +348,11 @@ int bgzf_inflate_device(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, const ch
 }  // namespace
 
 // bgzf: the bytes of a whole .bam file in HOST memory (pinned memory makes the upload one DMA).
-extern "C" int wgbs_dbam_open(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, wgbs_dbam **out) {
+// part: a window of a file (wgbs_dbam_open_part).  The stream then has no BAM header unless part->has_header (the first window of a
+// file), records are indexed from part->first_record on, and the last record may be cut off by the end of the window
+// (*part->tail = its offset; everything behind it is left unindexed).
+struct PartArgs { int has_header; int n_ref; const char *const *ref_names; const int32_t *ref_lens; uint64_t first_record; uint64_t *tail; };
+static int dbam_open_impl(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, const PartArgs *part, wgbs_dbam **out) {
     RC_TRY(wgbs_ctx_activate(ctx));
     if (!bgzf || !out) return wgbs_set_err("wgbs_dbam_open: null argument");
     *out = nullptr;
@@ -384,27 +388,39 @@ extern "C" int wgbs_dbam_open(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, wg
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         return 0;
     };
-    if ((rc = need(12)) < 0 || memcmp(head.data(), "BAM\1", 4)) return fail_free(ctx, B, rc < 0 ? rc : wgbs_set_err("wgbs_dbam_open: not a BAM file"));
-    const uint32_t l_text = ld32(head.data() + 4);
-    if ((rc = need(8ull + l_text + 4)) < 0) return fail_free(ctx, B, rc);
-    B->header_text.assign((const char *)head.data() + 8, strnlen((const char *)head.data() + 8, l_text));
-    uint64_t p = 8ull + l_text; const uint32_t n_ref = ld32(head.data() + p); p += 4;
-    if (n_ref > 0x7ffffffeu) return fail_free(ctx, B, wgbs_set_err("wgbs_dbam_open: corrupt BAM header"));
+    uint64_t p = 0; uint32_t n_ref = 0;
     std::vector<uint32_t> name_off{0}; std::string names;
-    for (uint32_t i = 0; i < n_ref; i++) {
-        if ((rc = need(p + 4)) < 0) return fail_free(ctx, B, rc);
-        const uint32_t l = ld32(head.data() + p); p += 4;
-        if ((rc = need(p + l + 4)) < 0) return fail_free(ctx, B, rc);
-        B->ref_names.emplace_back((const char *)head.data() + p, l ? strnlen((const char *)head.data() + p, l - 1) : 0); p += l;
-        B->ref_lens.push_back(ldi32(head.data() + p)); p += 4;
-        names += B->ref_names.back(); name_off.push_back((uint32_t)names.size());
+    if (!part || part->has_header) {
+        if ((rc = need(12)) < 0 || memcmp(head.data(), "BAM\1", 4)) return fail_free(ctx, B, rc < 0 ? rc : wgbs_set_err("wgbs_dbam_open: not a BAM file"));
+        const uint32_t l_text = ld32(head.data() + 4);
+        if ((rc = need(8ull + l_text + 4)) < 0) return fail_free(ctx, B, rc);
+        B->header_text.assign((const char *)head.data() + 8, strnlen((const char *)head.data() + 8, l_text));
+        p = 8ull + l_text; n_ref = ld32(head.data() + p); p += 4;
+        if (n_ref > 0x7ffffffeu) return fail_free(ctx, B, wgbs_set_err("wgbs_dbam_open: corrupt BAM header"));
+        for (uint32_t i = 0; i < n_ref; i++) {
+            if ((rc = need(p + 4)) < 0) return fail_free(ctx, B, rc);
+            const uint32_t l = ld32(head.data() + p); p += 4;
+            if ((rc = need(p + l + 4)) < 0) return fail_free(ctx, B, rc);
+            B->ref_names.emplace_back((const char *)head.data() + p, l ? strnlen((const char *)head.data() + p, l - 1) : 0); p += l;
+            B->ref_lens.push_back(ldi32(head.data() + p)); p += 4;
+            names += B->ref_names.back(); name_off.push_back((uint32_t)names.size());
+        }
+    } else {
+        n_ref = (uint32_t)part->n_ref;
+        for (uint32_t i = 0; i < n_ref; i++) {
+            B->ref_names.emplace_back(part->ref_names[i]); B->ref_lens.push_back(part->ref_lens ? part->ref_lens[i] : 0);
+            names += B->ref_names.back(); name_off.push_back((uint32_t)names.size());
+        }
+        p = part->first_record;
+        if (p > uoff) return fail_free(ctx, B, wgbs_set_err("wgbs_dbam_open_part: first record offset %llu beyond the part (%llu inflated bytes)", (unsigned long long)p, (unsigned long long)uoff));
     }
     if ((rc = dalloc(ctx, &B->d_name_off, name_off.size())) < 0 || (rc = dalloc(ctx, &B->d_names, names.size())) < 0 || (rc = dalloc(ctx, &B->d_ref_lens, (size_t)n_ref)) < 0 ||
         (rc = copy_any(ctx, B->d_name_off, name_off.data(), name_off.size() * 4)) < 0 || (rc = copy_any(ctx, B->d_names, names.data(), names.size())) < 0 ||
         (rc = copy_any(ctx, B->d_ref_lens, B->ref_lens.data(), (size_t)n_ref * 4)) < 0) return fail_free(ctx, B, rc);
     lap("header");
     // 4. record table: guess the first record of every segment, walk, repair until every entry equals its predecessor's exit
-    const uint64_t p0 = p, n = uoff, nseg = n > p0 ? (n - p0 + SEG - 1) / SEG : 0;
+    const uint64_t p0 = p, n = uoff; uint64_t nseg = n > p0 ? (n - p0 + SEG - 1) / SEG : 0;
+    if (part && part->tail) *part->tail = n > p0 ? n : p0;
     B->ref_first.assign(n_ref + 1, 0); B->ref_last.assign(n_ref + 1, 0);
     if (nseg) {
         uint64_t *entry, *entry2, *exit_, *bad, *base; uint32_t *cnt, *changed; uint8_t *dirty; unsigned long long *d_first, *d_last; uint32_t *d_runs;
@@ -426,6 +442,22 @@ extern "C" int wgbs_dbam_open(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, wg
         lap("guess+walk");
         CUDA_TRY(cudaMemsetAsync(d_err, 0xff, 4 * 8, ctx->stream));
         LAUNCH(ctx, bam_first_bad_k, grid_for(nseg, 256), 256, 0, nseg, bad, d_err);
+        if (part) {
+            // a window of a file may end inside a record: the first record that does not fit is where the chain of this part ends
+            // (its offset = the tail the caller restarts from); segments behind it hold no record of this part.  Anything else that
+            // cannot be a record is still an error.
+            CUDA_TRY(cudaMemcpyAsync(herr, d_err, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            if (herr[0] != ~0ull) {
+                const uint64_t o = herr[0]; uint32_t bs = 0;
+                if (o + 4 <= n) { uint8_t b4[4]; CUDA_TRY(cudaMemcpyAsync(b4, B->data + o, 4, cudaMemcpyDeviceToHost, ctx->stream)); CUDA_TRY(cudaStreamSynchronize(ctx->stream)); bs = ld32(b4); }
+                const bool cut = o + 4 > n || (bs >= 32 && o + 4 + (uint64_t)bs > n);
+                if (!cut) return fail_free(ctx, B, wgbs_set_err("wgbs_dbam_open_part: corrupt BAM record at uncompressed offset %llu", herr[0]));
+                if (part->tail) *part->tail = o;
+                nseg = o > p0 ? (o - p0) / SEG + 1 : 1;                       // the segment the cut-off record starts in is the last one
+                CUDA_TRY(cudaMemsetAsync(d_err, 0xff, 4 * 8, ctx->stream));
+            }
+        }
         if ((rc = scan_u32_u64(ctx, cnt, base, nseg)) < 0) return fail_free(ctx, B, rc);
         uint64_t nrec = 0;
         CUDA_TRY(cudaMemcpyAsync(&nrec, base + nseg, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -455,6 +487,77 @@ extern "C" int wgbs_dbam_open(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, wg
     lap("table+runs");
     LAUNCH_CHECK();
     *out = B;
+    return 0;
+}
+
+extern "C" int wgbs_dbam_open(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, wgbs_dbam **out) { return dbam_open_impl(ctx, bgzf, nbytes, nullptr, out); }
+
+// A window of a .bam on the device: see wgbs_bam_open_part (include/wgbs_b200.h)
+extern "C" int wgbs_dbam_open_part(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, int n_ref, const char *const *ref_names, const int32_t *ref_lens,
+                                   int has_header, uint64_t first_record, wgbs_dbam **out, uint64_t *tail) {
+    if (!tail || (!has_header && n_ref > 0 && !ref_names)) return wgbs_set_err("wgbs_dbam_open_part: null argument");
+    PartArgs pa{has_header, n_ref, ref_names, ref_lens, first_record, tail};
+    return dbam_open_impl(ctx, bgzf, nbytes, &pa, out);
+}
+
+__global__ void __launch_bounds__(256) bam_first_key_k(const uint8_t *__restrict__ data, const uint64_t *__restrict__ rec_off, uint64_t nr, ViewParams V,
+                                                        int64_t key, unsigned long long *__restrict__ first) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nr) return;
+    Rec R; R.load(data + rec_off[i]);
+    if (template_key((int32_t)R.flag, R.refid, R.pos, R.nref, R.npos) >= key && passes(R, V)) atomicMin(first, (unsigned long long)rec_off[i]);
+}
+
+// inflated offset of the first record of reference refid that passes the filters (key window ignored) and whose template key is
+// >= key; *found = 0 when there is none (wgbs_bam_first_key on the device)
+extern "C" int wgbs_dbam_first_key(wgbs_ctx *ctx, const wgbs_dbam *B, const wgbs_view_opts *vo, int refid, int64_t key, uint64_t *offset, int *found) {
+    RC_TRY(wgbs_ctx_activate(ctx));
+    if (!B || !vo || !offset || !found) return wgbs_set_err("wgbs_dbam_first_key: null argument");
+    *found = 0; *offset = 0;
+    if (refid < 0 || refid >= (int)B->ref_names.size()) return 0;
+    if (vo->n_flag_eq < 0 || vo->n_flag_eq > 4) return wgbs_set_err("wgbs_dbam_first_key: n_flag_eq must be 0..4");
+    if (vo->n_iv && (!vo->iv_beg || !vo->iv_end || is_device_ptr(vo->iv_beg) || is_device_ptr(vo->iv_end))) return wgbs_set_err("wgbs_dbam_first_key: interval lists must be host arrays");
+    const uint64_t r0 = B->ref_first[refid], r1 = B->ref_last[refid], nr = r1 - r0;
+    if (!nr) return 0;
+    Temps T(ctx);
+    ViewParams V; memset(&V, 0, sizeof V);
+    V.refid = refid; V.min_mapq = vo->min_mapq; V.exclude_flags = vo->exclude_flags; V.include_flags = vo->include_flags; V.beg = vo->beg; V.end = vo->end;
+    V.n_flag_eq = vo->n_flag_eq; for (int k = 0; k < 4; k++) V.flag_eq[k] = vo->flag_eq[k];
+    V.n_iv = vo->n_iv; V.iv_exclude = vo->iv_exclude;
+    if (vo->n_iv) {
+        int64_t *a, *b;
+        RC_TRY(T.alloc(&a, vo->n_iv)); RC_TRY(T.alloc(&b, vo->n_iv));
+        RC_TRY(copy_any(ctx, a, vo->iv_beg, vo->n_iv * 8)); RC_TRY(copy_any(ctx, b, vo->iv_end, vo->n_iv * 8));
+        V.iv_beg = a; V.iv_end = b;
+    }
+    if (vo->read_group) {
+        V.have_rg = 1; V.rg_len = (uint32_t)strlen(vo->read_group);
+        char *g; RC_TRY(T.alloc(&g, (size_t)V.rg_len + 1)); RC_TRY(copy_any(ctx, g, vo->read_group, (size_t)V.rg_len + 1));
+        V.rg = g;
+    }
+    unsigned long long *d_first, h = ~0ull;
+    RC_TRY(T.alloc(&d_first, 1));
+    CUDA_TRY(cudaMemsetAsync(d_first, 0xff, 8, ctx->stream));
+    LAUNCH(ctx, bam_first_key_k, grid_for(nr, 256), 256, 0, B->data, B->rec_off + r0, nr, V, (int64_t)key, d_first);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(&h, d_first, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (h != ~0ull) { *offset = h; *found = 1; }
+    return 0;
+}
+
+// (refid, 0-based POS) of the last complete record; *refid = -2 when there is none
+extern "C" int wgbs_dbam_last_record(wgbs_ctx *ctx, const wgbs_dbam *B, int *refid, int64_t *pos) {
+    RC_TRY(wgbs_ctx_activate(ctx));
+    if (!B || !refid || !pos) return wgbs_set_err("wgbs_dbam_last_record: null argument");
+    *refid = -2; *pos = -1;
+    if (!B->nrec) return 0;
+    uint64_t o = 0; uint8_t h[12];
+    CUDA_TRY(cudaMemcpyAsync(&o, B->rec_off + (B->nrec - 1), 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(h, B->data + o, 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *refid = ldi32(h + 4); *pos = ldi32(h + 8);
     return 0;
 }
 
