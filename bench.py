@@ -517,7 +517,7 @@ def segment_leg():
         d_txt = ctx.upload(txt)
         res = {"records": R, "text_bytes": len(txt)}
         ref = None
-        for mode in ("default", "tiles"):
+        for mode in ("default", "tiles", "tiles_tma"):
             os.environ["WGBS_PATPARSE"] = mode
             try:
                 for _ in range(2):

@@ -139,12 +139,13 @@ def test_homog_overlapping_blocks(ctx, oracle):
 
 @pytest.mark.staged
 def test_tile_parser_equals_default_parser(ctx, monkeypatch):
-    """WGBS_PATPARSE=tiles (pat_tiles_k, two passes over 16 KiB tiles) == the default parser: same records, same pool, same errors"""
+    """WGBS_PATPARSE=tiles / tiles_tma (pat_tiles_k, two passes over 16 KiB tiles; tiles fetched by LDG.128 or by one TMA bulk copy)
+    == the default parser: same records, same pool, same errors"""
     rng = np.random.default_rng(8)
 
     def both(txt):
         res = []
-        for mode in ("default", "tiles"):
+        for mode in ("default", "tiles", "tiles_tma"):
             monkeypatch.setenv("WGBS_PATPARSE", mode)
             try:
                 P = ctx.pats_from_text(txt)
@@ -152,7 +153,8 @@ def test_tile_parser_equals_default_parser(ctx, monkeypatch):
                 P.free()
             except Exception as e:
                 res.append(str(e))
-        assert res[0] == res[1], (len(txt), res[0][:80] if isinstance(res[0], str) else "arrays differ", res[1][:80] if isinstance(res[1], str) else "")
+        for k in (1, 2):
+            assert res[0] == res[k], (k, len(txt), res[0][:80] if isinstance(res[0], str) else "arrays differ", res[k][:80] if isinstance(res[k], str) else "")
         return res[1]
 
     idx, pats, cnt = synth.make_pat_records(2, 60_000, 200_000, mean_len=9, max_len=70)

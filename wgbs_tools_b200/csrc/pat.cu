@@ -135,24 +135,46 @@ __device__ __forceinline__ PatRec pat_line(const PatTile &T, uint32_t s, bool fu
     return r;
 }
 
-template <int PASS>
+// TMA = 1: a full, 16-byte aligned tile is fetched by ONE bulk asynchronous copy (cp.async.bulk: the TMA engine moves 16 KiB from
+// global to shared memory and signals an mbarrier with the byte count) instead of 1024 LDG.128 + STS pairs; every thread then waits
+// on the barrier's phase.  The last (partial) tile and unaligned texts take the LDG path.  WGBS_PATPARSE=tiles_tma.
+template <int PASS, int TMA>
 __global__ void __launch_bounds__(PS_T) pat_tiles_k(const char *__restrict__ text, uint32_t n, uint32_t *__restrict__ tile_lines,
                                                      uint32_t *__restrict__ tile_words, uint32_t *__restrict__ idx, uint32_t *__restrict__ len,
                                                      uint32_t *__restrict__ count, uint32_t *__restrict__ off, uint32_t *__restrict__ pool,
                                                      uint32_t *__restrict__ err) {
-    __shared__ __align__(16) unsigned char sm_text[PS_TILE];
+    __shared__ __align__(128) unsigned char sm_text[PS_TILE];
     __shared__ unsigned long long sm_nl[PS_T], sm_tab[PS_T];
     __shared__ uint32_t ws_l[PS_T / 32], ws_w[PS_T / 32];
+    __shared__ __align__(8) unsigned long long sm_bar;
     const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const uint32_t t0 = blockIdx.x * (uint32_t)PS_TILE, t1 = (n - t0 > (uint32_t)PS_TILE) ? t0 + PS_TILE : n;    // n < 2^31 (host)
+    const bool bulk = TMA && (t1 - t0 == (uint32_t)PS_TILE) && (((uintptr_t)(text + t0)) & 15) == 0;              // uniform over the CTA
+    if (bulk) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&sm_bar), dst = (uint32_t)__cvta_generic_to_shared(sm_text);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)PS_TILE) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(text + t0), "r"((uint32_t)PS_TILE), "r"(bar) : "memory");
+        }
+        uint32_t landed = 0;                                         // phase 0 of the barrier completes when the 16 KiB have arrived
+        while (!landed)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(landed) : "r"(bar), "r"(0u) : "memory");
+    } else {
 #pragma unroll
-    for (int c = 0; c < PS_SPAN / 16; c++) {                         // coalesced: one round covers 4 KiB
-        const uint32_t o = (uint32_t)(c * PS_T + tid) * 16, p = t0 + o;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (p < n) v = load16_guard(text, p, n);                     // bytes past the end read as 0: neither newline nor tab
-        *reinterpret_cast<uint4 *>(sm_text + o) = v;
+        for (int c = 0; c < PS_SPAN / 16; c++) {                     // coalesced: one round covers 4 KiB
+            const uint32_t o = (uint32_t)(c * PS_T + tid) * 16, p = t0 + o;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (p < n) v = load16_guard(text, p, n);                 // bytes past the end read as 0: neither newline nor tab
+            *reinterpret_cast<uint4 *>(sm_text + o) = v;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     unsigned long long nl = 0, tb = 0;
 #pragma unroll
     for (int c = 0; c < PS_SPAN / 16; c++) {
@@ -343,7 +365,7 @@ __global__ void set_u64_k(unsigned long long *p, unsigned long long v) { *p = v;
 // C ABI
 // ==================================================================================================================
 // the two-pass tile parser (pat_tiles_k); dtext is device memory, n < 2^31 (line and word totals stay below 2^32)
-static int pats_from_text_tiles(wgbs_ctx *ctx, const char *dtext, uint32_t n, wgbs_pats **out) {
+static int pats_from_text_tiles(wgbs_ctx *ctx, const char *dtext, uint32_t n, bool tma, wgbs_pats **out) {
     Temps T(ctx);
     const uint32_t ntiles = (n + PS_TILE - 1) / PS_TILE;
     uint32_t *tl, *tw, *tlo, *two, *err = ctx->d_flags;
@@ -351,7 +373,8 @@ static int pats_from_text_tiles(wgbs_ctx *ctx, const char *dtext, uint32_t n, wg
     CUDA_TRY(cudaMemsetAsync(err, 0, 4, ctx->stream));
     uint32_t tot[2] = {0, 0};
     if (ntiles) {
-        LAUNCH(ctx, pat_tiles_k<0>, ntiles, PS_T, 0, dtext, n, tl, tw, nullptr, nullptr, nullptr, nullptr, nullptr, err);
+        if (tma) LAUNCH(ctx, (pat_tiles_k<0, 1>), ntiles, PS_T, 0, dtext, n, tl, tw, nullptr, nullptr, nullptr, nullptr, nullptr, err);
+        else LAUNCH(ctx, (pat_tiles_k<0, 0>), ntiles, PS_T, 0, dtext, n, tl, tw, nullptr, nullptr, nullptr, nullptr, nullptr, err);
         RC_TRY(scan_u32_u32(ctx, tl, tlo, ntiles)); RC_TRY(scan_u32_u32(ctx, tw, two, ntiles));
         CUDA_TRY(cudaMemcpyAsync(&tot[0], tlo + ntiles, 4, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(&tot[1], two + ntiles, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -364,7 +387,8 @@ static int pats_from_text_tiles(wgbs_ctx *ctx, const char *dtext, uint32_t n, wg
         (rc = dalloc(ctx, &P->off, P->n + 1)) < 0 || (rc = dalloc(ctx, &P->pool, P->pool_words)) < 0) { wgbs_pats_free(ctx, P); return rc; }
     cudaError_t ce = cudaSuccess;
     if (ntiles) {
-        LAUNCH(ctx, pat_tiles_k<1>, ntiles, PS_T, 0, dtext, n, tlo, two, P->idx, P->len, P->count, P->off, P->pool, err);
+        if (tma) LAUNCH(ctx, (pat_tiles_k<1, 1>), ntiles, PS_T, 0, dtext, n, tlo, two, P->idx, P->len, P->count, P->off, P->pool, err);
+        else LAUNCH(ctx, (pat_tiles_k<1, 0>), ntiles, PS_T, 0, dtext, n, tlo, two, P->idx, P->len, P->count, P->off, P->pool, err);
         ce = cudaGetLastError();
         if (ce == cudaSuccess) ce = cudaMemcpyAsync(P->off + P->n, two + ntiles, 4, cudaMemcpyDeviceToDevice, ctx->stream);
     } else ce = cudaMemsetAsync(P->off, 0, 4, ctx->stream);
@@ -391,7 +415,7 @@ extern "C" int wgbs_pats_from_text(wgbs_ctx *ctx, const char *text, size_t nbyte
     const char *dtext = (const char *)dtext_v;
     if (owned) T.v.push_back((void *)dtext);
     const uint32_t n = (uint32_t)nbytes;
-    if (const char *e = getenv("WGBS_PATPARSE"); e && !strcmp(e, "tiles") && nbytes < 0x78000000ull) return pats_from_text_tiles(ctx, dtext, n, out);
+    if (const char *e = getenv("WGBS_PATPARSE"); e && !strncmp(e, "tiles", 5) && nbytes < 0x78000000ull) return pats_from_text_tiles(ctx, dtext, n, !strcmp(e, "tiles_tma"), out);
     // 1. newline positions
     uint32_t *nlpos = nullptr, n_nl = 0, n_lines = 0;
     RC_TRY(find_lines(ctx, dtext, nbytes, T, &nlpos, &n_nl, &n_lines));
