@@ -13,6 +13,11 @@ run inflate_teams 120 python -m pytest tests/test_zz_bamdev_gpu.py -m gpu -q -k 
 run pat_tiles 120 python -m pytest tests/test_pat_gpu.py -m gpu -q -k "tile_parser"
 run seg_plan 120 python -m pytest tests/test_segment_gpu.py -m gpu -q -k "exact_wave_plan"
 run dev_parts 180 python -m pytest tests/test_zz_bamdev_gpu.py -m gpu -q -k "device_parts"
+# newline-scan variants (the env var is read once per process: whole test files per variant, then a short bench for the kernel time)
+for v in batch8 batch16 tma; do
+  WGBS_NLSCAN=$v run nlscan_${v}_tests 300 python -m pytest tests/test_pileup_gpu.py -m gpu -x -q
+  WGBS_NLSCAN=$v timeout 300 python bench.py --steps 10 --warmup 3 --no-extras > gpurun_out/staged_bench_nlscan_$v.json 2> gpurun_out/staged_bench_nlscan_$v.err; echo "   bench nlscan=$v rc=$?"
+done
 # 2. the bench with all child legs (direct route, team decoders, batches in flight, segment at scale, pat parsers)
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/staged_bench.json 2> gpurun_out/staged_bench.err; echo "bench rc=$?"
 python - <<'P'

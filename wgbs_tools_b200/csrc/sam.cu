@@ -74,6 +74,11 @@ __device__ __forceinline__ int tag_kind(const char *__restrict__ t, uint32_t p, 
 constexpr int NLS_T = 256, NLS_ROUNDS = 16, NLS_TILE = NLS_T * NLS_ROUNDS * 16;   // 64 KiB per CTA
 constexpr unsigned long long NS_AGG = 1ull << 62, NS_INC = 2ull << 62, NS_VAL = (1ull << 62) - 1;
 
+// BATCH = 0: every 16-byte chunk is loaded, guarded and examined in turn (the SASS shows the 16 LDG.128 of a thread ~170
+// instructions apart, each behind the branches of its guard: ONE load in flight per thread).  BATCH = 4 / 8 / 16 (staged,
+// WGBS_NLSCAN=batch4|batch8|batch16): a tile that lies wholly inside an aligned text takes a branch-free path in which BATCH
+// loads are issued back to back before the first mask is computed -- BATCH x 16 bytes in flight per thread.
+template <int BATCH>
 __global__ void __launch_bounds__(NLS_T) nl_scan_k(const char *__restrict__ text, size_t n, uint32_t cap,
                                                     unsigned long long *__restrict__ status, unsigned int *__restrict__ ticket,
                                                     uint32_t *__restrict__ nlpos, uint32_t *__restrict__ total) {
@@ -86,6 +91,42 @@ __global__ void __launch_bounds__(NLS_T) nl_scan_k(const char *__restrict__ text
     __syncthreads();
     const unsigned tile = s_tile;
     const size_t warp0 = (size_t)tile * NLS_TILE + (size_t)w * (32 * NLS_ROUNDS * 16);
+    const bool whole = BATCH != 0 && (size_t)(tile + 1) * NLS_TILE <= n && (((uintptr_t)text) & 15) == 0;     // uniform over the CTA
+    if (BATCH < 0 && whole) {
+        // BATCH = -1 (WGBS_NLSCAN=tma): the 64 KiB tile is fetched by ONE bulk asynchronous copy (TMA engine, global -> shared,
+        // completion counted in bytes on an mbarrier); the threads then take their chunks from shared memory (conflict-free:
+        // consecutive lanes, consecutive 16 bytes).  64 KiB in flight per CTA whatever the compiler makes of the loop.
+        extern __shared__ __align__(128) unsigned char nl_tile[];
+        __shared__ __align__(8) unsigned long long nl_bar;
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&nl_bar), dst = (uint32_t)__cvta_generic_to_shared(nl_tile);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)NLS_TILE) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(text + (size_t)tile * NLS_TILE), "r"((uint32_t)NLS_TILE), "r"(bar) : "memory");
+        }
+        uint32_t landed = 0;
+        while (!landed)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(landed) : "r"(bar), "r"(0u) : "memory");
+        const uint4 *src = reinterpret_cast<const uint4 *>(nl_tile + (size_t)w * (32 * NLS_ROUNDS * 16)) + lane;
+#pragma unroll
+        for (int c = 0; c < NLS_ROUNDS; c++) sm_mask[w * 512 + c * 32 + lane] = (uint16_t)eq_mask16(src[c * 32], '\n');
+    } else if (whole) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(text + warp0) + lane;
+#pragma unroll
+        for (int h = 0; h < NLS_ROUNDS; h += (BATCH > 0 ? BATCH : 1)) {
+            uint4 v[BATCH > 0 ? BATCH : 1];
+#pragma unroll
+            for (int c = 0; c < (BATCH > 0 ? BATCH : 1); c++)      // volatile asm: ptxas keeps these loads together, ahead of the first use
+                asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[c].x), "=r"(v[c].y), "=r"(v[c].z), "=r"(v[c].w) : "l"(src + (h + c) * 32));
+#pragma unroll
+            for (int c = 0; c < (BATCH > 0 ? BATCH : 1); c++) sm_mask[w * 512 + (h + c) * 32 + lane] = (uint16_t)eq_mask16(v[c], '\n');
+        }
+    } else
 #pragma unroll
     for (int c = 0; c < NLS_ROUNDS; c++) {
         const size_t p = warp0 + (size_t)(c * 32 + lane) * 16;
@@ -614,10 +655,16 @@ int sam_tokenize(wgbs_ctx *ctx, const char *dtext, size_t nbytes, int want_tags 
     rb.text = dtext; rb.nbytes = (uint32_t)nbytes;
     uint32_t *nlpos = nullptr, *totals = ctx->d_flags + 8;
     unsigned long long *status = nullptr;
-    static const int warp_scan = [] { const char *e = getenv("WGBS_NLSCAN"); return (e && !strcmp(e, "warp")) ? 1 : (e && !strcmp(e, "cta")) ? 0 : WGBS_NLSCAN_DEFAULT_WARP; }();
+    // 1: warp tiles; 0: CTA tiles (default); -4 / -8 / -16: CTA tiles with batched loads; -1: CTA tiles fetched by TMA (staged)
+    static const int warp_scan = [] {
+        const char *e = getenv("WGBS_NLSCAN");
+        if (e && !strncmp(e, "batch", 5)) { const int b = atoi(e + 5); return (b == 4 || b == 8 || b == 16) ? -b : 0; }
+        if (e && !strcmp(e, "tma")) return -1;
+        return (e && !strcmp(e, "warp")) ? 1 : (e && !strcmp(e, "cta")) ? 0 : WGBS_NLSCAN_DEFAULT_WARP;
+    }();
     static const int lines_pf = [] { const char *e = getenv("WGBS_LINES_PF"); return e ? atoi(e) : WGBS_LINES_PF_DEFAULT; }();
     const uint32_t wtiles = (uint32_t)((nbytes + NLW_TILE - 1) / NLW_TILE);
-    if (ntiles) RC_TRY(T.alloc(&status, (size_t)(warp_scan ? wtiles : ntiles) + 1));
+    if (ntiles) RC_TRY(T.alloc(&status, (size_t)(warp_scan == 1 ? wtiles : ntiles) + 1));
     uint32_t cap = (uint32_t)(nbytes / 64 + 1024);            // optimistic: average line >= 64 bytes (a 50 bp SAM record is ~130)
     uint32_t n_nl = 0, first_mm = 0; char last = '\n';
     // first_line (patter.cpp:337-338): does the first non-empty line carry an MM tag?  Decided on the host from the head of the
@@ -626,9 +673,16 @@ int sam_tokenize(wgbs_ctx *ctx, const char *dtext, size_t nbytes, int want_tags 
     for (int attempt = 0; attempt < 2 && ntiles; attempt++) {
         if (nlpos) { T.keep(nlpos); dfree(ctx, nlpos); }
         RC_TRY(T.alloc(&nlpos, cap));
-        CUDA_TRY(cudaMemsetAsync(status, 0, ((size_t)(warp_scan ? wtiles : ntiles) + 1) * 8, ctx->stream));
-        if (warp_scan) LAUNCH(ctx, nl_scan_warp_k, (wtiles + NLW_T / 32 - 1) / (NLW_T / 32), NLW_T, 0, dtext, nbytes, cap, status, (unsigned int *)(status + wtiles), nlpos, totals);
-        else LAUNCH(ctx, nl_scan_k, ntiles, NLS_T, 0, dtext, nbytes, cap, status, (unsigned int *)(status + ntiles), nlpos, totals);
+        CUDA_TRY(cudaMemsetAsync(status, 0, ((size_t)(warp_scan == 1 ? wtiles : ntiles) + 1) * 8, ctx->stream));
+        if (warp_scan == 1) LAUNCH(ctx, nl_scan_warp_k, (wtiles + NLW_T / 32 - 1) / (NLW_T / 32), NLW_T, 0, dtext, nbytes, cap, status, (unsigned int *)(status + wtiles), nlpos, totals);
+        else if (warp_scan == -4) LAUNCH(ctx, nl_scan_k<4>, ntiles, NLS_T, 0, dtext, nbytes, cap, status, (unsigned int *)(status + ntiles), nlpos, totals);
+        else if (warp_scan == -8) LAUNCH(ctx, nl_scan_k<8>, ntiles, NLS_T, 0, dtext, nbytes, cap, status, (unsigned int *)(status + ntiles), nlpos, totals);
+        else if (warp_scan == -16) LAUNCH(ctx, nl_scan_k<16>, ntiles, NLS_T, 0, dtext, nbytes, cap, status, (unsigned int *)(status + ntiles), nlpos, totals);
+        else if (warp_scan == -1) {
+            CUDA_TRY(cudaFuncSetAttribute(nl_scan_k<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, NLS_TILE));
+            LAUNCH(ctx, nl_scan_k<-1>, ntiles, NLS_T, NLS_TILE, dtext, nbytes, cap, status, (unsigned int *)(status + ntiles), nlpos, totals);
+        }
+        else LAUNCH(ctx, nl_scan_k<0>, ntiles, NLS_T, 0, dtext, nbytes, cap, status, (unsigned int *)(status + ntiles), nlpos, totals);
         CUDA_TRY(cudaMemcpyAsync(&n_nl, totals, 4, cudaMemcpyDeviceToHost, ctx->stream));
         if (attempt == 0 && !head.empty()) CUDA_TRY(cudaMemcpyAsync(head.data(), dtext, head.size(), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(&last, dtext + nbytes - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
