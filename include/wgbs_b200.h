@@ -252,6 +252,10 @@ int wgbs_bam_last_record(const wgbs_bam *, int *refid, int64_t *pos);
  * >= key; *found = 0 when there is none */
 int wgbs_bam_first_key(const wgbs_bam *, const wgbs_view_opts *, int refid, int64_t key, uint64_t *offset, int *found);
 uint64_t wgbs_bam_inflated_bytes(const wgbs_bam *);
+/* bgzf: a few consecutive whole BGZF blocks from anywhere in a .bam.  *offset = inflated offset (within these blocks) of the first
+ * record that starts in them, with its refid / 0-based POS; *found = 0 when no record starts there (probe more blocks).  Lets a
+ * multi-GPU bam2pat give every rank its own block range of a streamed file without a .bai (binary search per chromosome). */
+int wgbs_bam_probe(const void *bgzf, size_t nbytes, int n_ref, uint64_t *offset, int *refid, int64_t *pos, int *found);
 
 
 /* ---------------------------------------------------------------------------------------------------------------

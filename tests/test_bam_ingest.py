@@ -316,3 +316,30 @@ def test_streamed_parts_give_every_template_once(built_lib, tmp_path, budget):
     assert seen_done >= {"chrA", "chrB", "chrC"}
     if budget < 1_000_000:
         assert items > 5                                                  # really streamed
+
+
+def test_chromosome_block_ranges_without_an_index(built_lib, tmp_path):
+    """chrom_first_blocks (binary search with wgbs_bam_probe) brackets every chromosome's records, and streaming only a
+    chromosome's block range gives exactly that chromosome's whole-file view"""
+    from wgbs_tools_b200 import bamio
+    gs = [synth.make_genome(7 + i, f"chr{c}", L) for i, (c, L) in enumerate((("A", 150_000), ("B", 90_000), ("C", 30_000), ("E", 60_000)))]
+    sam = b"".join(synth.make_sam(g, n, 3 + i, paired=True, name_prefix=f"{g.chrom}_") for i, (g, n) in enumerate(zip(gs, (7000, 4000, 300, 2500))))
+    sam += b"u1\t4\t*\t0\t0\t*\t*\t0\t0\tACGT\t*\n" * 5
+    refs = [("chrA", 150_000), ("chrB", 90_000), ("chrC", 30_000), ("chrD", 1000), ("chrE", 60_000)]          # chrD: no reads
+    p = tmp_path / "s.bam"
+    p.write_bytes(bamio.sam_to_bam(sam, refs))
+    table = bamio.bgzf_block_table(str(p))
+    first = bamio.chrom_first_blocks(str(p), table, len(refs))
+    assert first == sorted(first) and len(first) == len(refs) + 1 and first[0] == 0
+    kw = dict(mapq=10, exclude_flags=1796)
+    names = [r[0] for r in refs]
+    with bamio.BamFile(str(p), threads=2) as b:
+        whole = {c: b.view(c, **kw) for c in names}
+    opener = lambda data, r, l, f: bamio.BamPart(data, r, l, f, threads=2)
+    for ci, c in enumerate(names):
+        rng = (max(first[ci] - 1, 0), min(first[ci + 1] + 1, table[0].size))
+        got = []
+        for part, chrom, win, done in bamio.stream_parts(str(p), opener, lambda _c: kw, 150_000, blocks=rng, refs0=names):
+            if chrom == c:
+                got.append(part.view(chrom, key_window=win, **kw))
+        assert sorted(b"".join(got).splitlines()) == sorted(whole[c].splitlines()), c

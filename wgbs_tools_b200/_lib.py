@@ -85,6 +85,7 @@ def _load():
         "wgbs_bam_last_record": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
         "wgbs_bam_first_key": (C.c_int, [vp, C.POINTER(ViewOpts), C.c_int, C.c_int64, C.POINTER(u64), C.POINTER(C.c_int)]),
         "wgbs_bam_inflated_bytes": (u64, [vp]),
+        "wgbs_bam_probe": (C.c_int, [vp, sz, C.c_int, C.POINTER(u64), C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
         "wgbs_bgzf_inflate": (C.c_int, [vp, vp, sz, C.POINTER(vp), C.POINTER(sz)]),
         "wgbs_dbam_open": (C.c_int, [vp, vp, sz, C.POINTER(vp)]),
         "wgbs_dbam_open_file": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),

@@ -143,7 +143,8 @@ class _Source:
             k = int(np.searchsorted(np.cumsum(usize), 4 << 20)) + 1
             with open(path, "rb") as f:
                 self.bam = BamPart(f.read(int(coff[:k][-1] + csize[:k][-1])), threads=threads)
-            self.stream = dict(path=path, threads=threads, budget=int(os.environ.get("WGBS_STREAM_BYTES", 2 << 30)))   # inflated bytes per part: its SAM text stays < 4 GiB
+            self.stream = dict(path=path, threads=threads, budget=int(os.environ.get("WGBS_STREAM_BYTES", 2 << 30)),   # inflated bytes per part: its SAM text stays < 4 GiB
+                               table=(coff, csize, usize), first=None)
             self.header = self.bam.header
             self.chroms = set(self.bam.refs)
             return
@@ -212,11 +213,41 @@ class _Source:
 
     def weight(self, chrom: str) -> int:
         """how much work a chromosome is (records in a .bam, bytes of SAM text): the LPT weights of the multi-GPU split"""
-        if self.stream is not None:                          # not known without reading the file: its length stands in
-            return int(self.bam.ref_len(chrom)) if hasattr(self.bam, "ref_len") else 1
+        if self.stream is not None:                          # the compressed bytes between the chromosome's first block and the next one's
+            if chrom not in self.bam.refs:
+                return 0
+            first, coff = self.chrom_blocks(), self.stream["table"][0]
+            c = self.bam.refs.index(chrom); end = int(coff[-1]) + 1
+            return max((int(coff[first[c + 1]]) if first[c + 1] < coff.size else end) - (int(coff[first[c]]) if first[c] < coff.size else end), 0)
         if self.bam is not None:
             return self.bam.nrecords(chrom) if chrom in self.bam.refs else 0
         return len(self.sam.get(chrom, b""))
+
+    def chrom_blocks(self) -> list[int]:
+        """streamed .bam: first BGZF block of every reference (bamio.chrom_first_blocks), found once by probing"""
+        if self.stream["first"] is None:
+            from .bamio import chrom_first_blocks
+            self.stream["first"] = chrom_first_blocks(self.stream["path"], self.stream["table"], len(self.bam.refs))
+        return self.stream["first"]
+
+    def block_runs(self, chroms) -> list[tuple[int, int]] | None:
+        """streamed .bam: the BGZF block ranges that hold the records of `chroms` (merged where they touch), or None when that is
+        (nearly) the whole file anyway"""
+        refs = self.bam.refs; nb = self.stream["table"][0].size
+        want = sorted(refs.index(c) for c in chroms if c in refs)
+        if len(want) >= len(refs):
+            return None
+        first = self.chrom_blocks()
+        runs: list[list[int]] = []
+        for c in want:
+            lo, hi = max(first[c] - 1, 0), min(first[c + 1] + 1, nb)
+            if hi <= lo:
+                continue
+            if runs and lo <= runs[-1][1]:
+                runs[-1][1] = max(runs[-1][1], hi)
+            else:
+                runs.append([lo, hi])
+        return [(a, b) for a, b in runs]
 
     def close(self):
         if self.bam is not None:
@@ -373,15 +404,21 @@ def main(argv=None):
                 # one pass over the file, part by part; a chromosome's ChromPile lives from its first part to its last
                 from .bamio import BamPart, DeviceBamPart, stream_parts
                 by_chrom = {r.split(":")[0]: (ri, r) for ri, r in enumerate(regions) if ri in mine}
-                piles: dict[str, ChromPile] = {}
+                piles: dict[str, ChromPile] = {}; finished: set[str] = set()
                 # parts decoded on host threads, or (WGBS_STREAM_BACKEND=device; staged) uploaded compressed and decoded in HBM
                 on_dev = os.environ.get("WGBS_STREAM_BACKEND", "host") == "device"
                 if on_dev:
                     opener = lambda data, refs, lens, first: DeviceBamPart(ctx, data, refs, lens, first)
                 else:
                     opener = lambda data, refs, lens, first: BamPart(data, refs, lens, first, threads=src.stream["threads"])
-                for part, chrom, win, done in stream_parts(path, opener, lambda c: dict(flag_eq=feq, **view_kw(c)), src.stream["budget"]):
-                    if chrom not in by_chrom:
+                # only the block ranges of the chromosomes asked for are read (a region, or this rank's share of a multi-GPU run)
+                runs = src.block_runs(by_chrom) if by_chrom else []
+                import itertools
+                stream = itertools.chain.from_iterable(
+                    stream_parts(path, opener, lambda c: dict(flag_eq=feq, **view_kw(c)), src.stream["budget"], blocks=r, refs0=src.bam.refs)
+                    for r in ([None] if runs is None else runs))
+                for part, chrom, win, done in stream:
+                    if chrom not in by_chrom or (chrom not in piles and chrom in finished):
                         continue
                     ri, region = by_chrom[chrom]
                     _, beg, end = parse_region_str(region)
@@ -393,6 +430,7 @@ def main(argv=None):
                     else:
                         piles[chrom].add(part.view(chrom, **vkw))
                     if done:
+                        finished.add(chrom)
                         txt, st = piles.pop(chrom).finish()
                         if txt is None:
                             continue

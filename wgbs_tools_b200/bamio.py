@@ -152,7 +152,54 @@ def bgzf_block_table(path: str):
     return np.array(coff, np.int64), np.array(csize, np.int64), np.array(usize, np.int64)
 
 
-def stream_parts(path: str, open_part, view_kw_for, budget: int):
+def probe_block(f, table, b: int, n_ref: int, span: int = 3):
+    """(inflated offset within block b.., refid, pos) of the first record that starts at or after the beginning of BGZF block b
+    of the open file f, or None when no record starts in the rest of the file (wgbs_bam_probe on a few blocks; more when a
+    record is longer than that)"""
+    coff, csize, usize = table
+    nb = coff.size
+    while b < nb:
+        e = min(b + span, nb)
+        f.seek(int(coff[b])); data = f.read(int(coff[e - 1] + csize[e - 1] - coff[b]))
+        a = np.frombuffer(data, np.uint8)
+        off = C.c_uint64(); refid = C.c_int(); pos = C.c_int64(); found = C.c_int()
+        check(lib.wgbs_bam_probe(a.ctypes.data, a.size, n_ref, C.byref(off), C.byref(refid), C.byref(pos), C.byref(found)))
+        if found.value:
+            return int(off.value), refid.value, pos.value
+        if e == nb:
+            return None
+        span *= 4
+    return None
+
+
+def chrom_first_blocks(path: str, table, n_ref: int) -> list[int]:
+    """first[c] = the first BGZF block b of a coordinate-sorted .bam such that the first record starting in b.. belongs to
+    reference >= c (unmapped records count as beyond every reference); first[n_ref] = where the unmapped tail starts.  The
+    records of reference c lie in blocks [first[c] - 1, first[c + 1]]: binary search with wgbs_bam_probe, no .bai needed."""
+    nb = table[0].size
+    first = []
+    with open(path, "rb") as f:
+        memo = {}
+
+        def rid(b):
+            if b not in memo:
+                r = probe_block(f, table, b, n_ref)
+                memo[b] = (1 << 30) if r is None or r[1] < 0 else r[1]
+            return memo[b]
+        lo_all = 0
+        for c in range(n_ref + 1):
+            lo, hi = lo_all, nb                      # first b in [lo, nb] with rid(b) >= c   (rid(nb) = infinity)
+            while lo < hi:
+                m = (lo + hi) // 2
+                if rid(m) >= c:
+                    hi = m
+                else:
+                    lo = m + 1
+            first.append(lo); lo_all = lo
+    return first
+
+
+def stream_parts(path: str, open_part, view_kw_for, budget: int, blocks: tuple[int, int] | None = None, refs0=None):
     """Read a coordinate-sorted .bam that does not fit in memory as a sequence of parts and yield
         (part, chrom, key_window, chrom_done)
     such that piling up, for every yielded item, the records of `chrom` in `part` that pass the view filters AND whose template
@@ -164,13 +211,29 @@ def stream_parts(path: str, open_part, view_kw_for, budget: int):
         fit -- deferred are the templates whose key is not yet below the POS of the part's last record)
     Why it is exact: the file is sorted, so when a part ends inside chromosome c at POS P, every record with POS < P is in this
     part or an earlier one.  Templates with key < P are complete (both mates have POS <= key); the others are deferred, and the
-    next part starts at the block holding the first deferred record (or the cut-off record), found by first_key()."""
+    next part starts at the block holding the first deferred record (or the cut-off record), found by first_key().
+    blocks / refs0: restrict the pass to BGZF blocks [blocks[0], blocks[1]) (a chromosome that ENDS inside the range is complete;
+    the caller ignores chromosomes it did not ask for)."""
     coff, csize, usize = bgzf_block_table(path)
     nb = coff.size
     uoff = np.concatenate([[0], np.cumsum(usize)])
     refs = ref_lens = None
     b = 0; first_record = 0; prev_hi: dict[int, int] = {}
     grow = 1; at_start = True
+    if blocks is not None and blocks[0] > 0:
+        # only blocks [blocks[0], blocks[1]) of the file (one rank's share of a multi-GPU run; refs0 = the file's reference names):
+        # the first record that starts in the first block is found by a probe
+        refs, ref_lens = list(refs0), [0] * len(refs0)
+        with open(path, "rb") as f:
+            r = probe_block(f, (coff, csize, usize), blocks[0], len(refs))
+        if r is None:
+            return
+        b = blocks[0]; first_record = r[0]; at_start = False
+        while first_record >= usize[b] and b + 1 < nb:                # (the probe may have had to look beyond its first block)
+            first_record -= int(usize[b]); b += 1
+    if blocks is not None:
+        nb = min(nb, blocks[1])
+        coff, csize, usize, uoff = coff[:nb], csize[:nb], usize[:nb], uoff[:nb + 1]
     with open(path, "rb") as f:
         while b < nb:
             e = int(np.searchsorted(uoff, uoff[b] + budget * grow, side="right")) - 1

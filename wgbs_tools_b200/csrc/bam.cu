@@ -14,6 +14,7 @@
 #include <thread>
 #include <vector>
 
+#include "bam_core.cuh"
 #include "common.cuh"
 
 struct wgbs_bam {
@@ -299,6 +300,42 @@ extern "C" int wgbs_bam_open_part(const void *bgzf, size_t nbytes, int n_ref, co
         return 0;
     }
     return open_stream("wgbs_bam_open_part", (const uint8_t *)bgzf, nbytes, threads, true, n_ref, ref_names, ref_lens, first_record, out, tail);
+}
+
+// Where does a record start in the middle of a file?  bgzf: a few consecutive whole BGZF blocks from anywhere in a .bam.  Finds
+// the first offset of their inflated bytes from which the length-prefixed record chain runs plausibly (bam_core.cuh
+// plausible_at) all the way to the end of the probed bytes -- hundreds of records when the probe spans a few blocks, so a
+// chance hit inside sequence or quality bytes cannot survive -- and returns it with that record's refid / POS.  *found = 0:
+// no record starts inside the probed bytes (take more blocks).  bam2pat uses it to give every rank of a multi-GPU run its own
+// block range of a streamed file (binary search for the first block of each chromosome) without a .bai index.
+extern "C" int wgbs_bam_probe(const void *bgzf, size_t nbytes, int n_ref, uint64_t *offset, int *refid, int64_t *pos, int *found) {
+    if (!bgzf || !offset || !refid || !pos || !found) return wgbs_set_err("wgbs_bam_probe: null argument");
+    *found = 0; *offset = 0; *refid = -2; *pos = -1;
+    const uint8_t *c = (const uint8_t *)bgzf; uint64_t off = 0; std::vector<uint8_t> d;
+    while (off + 28 <= nbytes) {
+        const uint8_t *h = c + off;
+        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return wgbs_set_err("wgbs_bam_probe: not a BGZF block at %llu", (unsigned long long)off);
+        const uint16_t xlen = rd16(h + 10); uint32_t bsize = 0;
+        for (uint32_t x = 0; x + 4 <= xlen;) { const uint8_t *sf = h + 12 + x; const uint16_t sl = rd16(sf + 2); if (sf[0] == 'B' && sf[1] == 'C' && sl == 2) { bsize = rd16(sf + 4) + 1u; break; } x += 4 + sl; }
+        if (!bsize || off + bsize > nbytes) return wgbs_set_err("wgbs_bam_probe: corrupt BGZF block at %llu", (unsigned long long)off);
+        const uint32_t usize = rd32(h + bsize - 4); const size_t at = d.size();
+        d.resize(at + usize);
+        if (inflate_block(h, bsize, d.data() + at, usize)) return wgbs_set_err("wgbs_bam_probe: inflate failed");
+        off += bsize;
+    }
+    const uint64_t n = d.size();
+    for (uint64_t o = 0; o + 36 <= n; o++) {
+        if (!bamcore::plausible_at(d.data(), n, o, n_ref)) continue;
+        uint64_t q = o; int chain = 0; bool ok = true;
+        while (q + 4 <= n) {                                             // the whole chain to the end of the probe must hold
+            const uint32_t bs = rd32(d.data() + q);
+            if (bs >= 32 && q + 4 + (uint64_t)bs > n) break;             // cut off by the end of the probe: fine
+            if (!bamcore::plausible_at(d.data(), n, q, n_ref)) { ok = false; break; }
+            q += 4 + (uint64_t)bs; chain++;
+        }
+        if (ok && chain >= 2) { *found = 1; *offset = o; *refid = rdi32(d.data() + o + 4); *pos = rdi32(d.data() + o + 8); return 0; }
+    }
+    return 0;
 }
 
 // (refid, 0-based POS) of the last complete record of a file / part; *refid = -2 when there is no record
