@@ -85,7 +85,7 @@ class BamFile:
 
 def _part_args(refs, ref_lens):
     names = (C.c_char_p * max(len(refs), 1))(*[r.encode() for r in refs])
-    lens = (C.c_int32 * max(len(refs), 1))(*[int(x) for x in ref_lens])
+    lens = (C.c_int32 * max(len(refs), 1))(*[int(x) for x in (ref_lens if ref_lens is not None else [0] * len(refs))])
     return names, lens
 
 
