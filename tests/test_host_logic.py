@@ -175,3 +175,17 @@ def test_pat_tile_parser_algorithm_model():
     """the staged two-pass tile parser (pat_tiles_k): its algorithm, modelled in Python, equals a straightforward parser"""
     import pat_tiles_model
     assert pat_tiles_model.run(iters=1200, seed=3) == 0
+
+
+def test_pat_pieces_cut_at_line_ends():
+    """patio.pat_pieces (pat2beta / homog on pat files larger than one call): pieces end at line ends, cover the text, fit the limit"""
+    from wgbs_tools_b200.patio import pat_pieces
+    txt = synth.make_pat_text_fast(3, 20_000, 50_000)
+    assert list(pat_pieces(None, txt, 1 << 30)) == [txt]
+    for limit in (200, 4096, 100_000):
+        ps = [bytes(p) for p in pat_pieces(None, txt, limit)]
+        assert b"".join(ps) == txt and all(len(p) <= limit and p.endswith(b"\n") for p in ps) and len(ps) > 1
+    ps = [bytes(p) for p in pat_pieces(None, txt[:-1], 4096)]                  # no newline at the end of the text
+    assert b"".join(ps) == txt[:-1]
+    with pytest.raises(ValueError):
+        list(pat_pieces(None, b"chr1\t5\t" + b"C" * 500 + b"\t1\n" * 3, 100))

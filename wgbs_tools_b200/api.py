@@ -60,6 +60,16 @@ class DevBuf:
         return out
 
 
+class DevView:
+    """A byte range inside somebody else's device buffer (no ownership): what patio.pat_pieces yields for device-resident text"""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.ptr, self.nbytes = int(ptr), int(nbytes)
+
+    def __len__(self):
+        return self.nbytes
+
+
 class Pats:
     """Device-resident pat records (idx, len, count, 2-bit symbol pool)."""
 
@@ -277,8 +287,8 @@ class Context:
 
     # ---- pat ----------------------------------------------------------------------------------------------------
     def pats_from_text(self, text, nbytes: int | None = None) -> Pats:
-        """text: bytes (host) or DevBuf (device-resident pat text)."""
-        if isinstance(text, DevBuf):
+        """text: bytes (host), or DevBuf / DevView (device-resident pat text)."""
+        if isinstance(text, (DevBuf, DevView)):
             p, n = text.ptr, text.nbytes if nbytes is None else nbytes
         else:
             a = np.frombuffer(text, np.uint8)

@@ -149,9 +149,13 @@ def main(argv=None):
             if world == 1 and args.pat_decode in ("auto", "device"):
                 from .patio import read_pat_device
                 dtext = read_pat_device(ctx, pat)                  # BGZF: only the compressed bytes cross PCIe; None: plain gzip / text
-            P = ctx.pats_from_text(dtext if dtext is not None else wd.shard_lines(read_pat_text(pat), rank, world))
-            counts = homog_counts(ctx, P, lines, cols, edges, args.rlen, args.inclusive)
-            P.free()
+            from .patio import pat_pieces
+            counts = None                                              # bins are sums over records: a text of any size goes piece by piece
+            for piece in pat_pieces(ctx, dtext if dtext is not None else wd.shard_lines(read_pat_text(pat), rank, world)):
+                P = ctx.pats_from_text(piece)
+                c = homog_counts(ctx, P, lines, cols, edges, args.rlen, args.inclusive)
+                P.free()
+                counts = c if counts is None else counts + c
             if dtext is not None:
                 dtext.free()
             counts = wd.reduce_np(counts, 0)                           # bins are sums over records: exact under any record split

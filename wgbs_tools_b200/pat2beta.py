@@ -5,6 +5,8 @@ import argparse
 import os
 import sys
 
+import numpy as np
+
 
 def pat2beta(ctx, pat_path: str, out_dir: str, nr_sites: int, lbeta: bool = False, force: bool = True, decode: str = "auto"):
     from .patio import read_pat_text, splitextgz
@@ -19,18 +21,36 @@ def pat2beta(ctx, pat_path: str, out_dir: str, nr_sites: int, lbeta: bool = Fals
     if world == 1 and decode in ("auto", "device"):
         from .patio import read_pat_device
         dtext = read_pat_device(ctx, pat_path)                     # BGZF inflated in HBM; None: not a BGZF file
+    from .patio import pat_pieces
+
+    def counts(text):
+        """device int32[nr_sites, 2] of a pat text of any size (pieces of < 4 GiB, accumulated)"""
+        mc = None
+        for piece in pat_pieces(ctx, text):
+            P = ctx.pats_from_text(piece)
+            mc = ctx.pat2beta(P, 1, nr_sites + 1, meth_cov=mc, zero_first=mc is None)
+            P.free()
+        return mc
+
     if dtext is not None:
-        P = ctx.pats_from_text(dtext)
-        mc = ctx.pat2beta(P, 1, nr_sites + 1)
+        mc = counts(dtext)
         beta = ctx.trim(mc, nr_sites, 16 if lbeta else 8)
-        P.free(); mc.free(); dtext.free()
+        mc.free(); dtext.free()
         beta.tofile(out_beta)
         return out_beta
     text = wd.shard_lines(read_pat_text(pat_path), rank, world)
-    if world == 1:
+    big = len(text) > int(os.environ.get("WGBS_PAT_CHUNK_BYTES", 2 << 30))
+    if world == 1 and not big:
         beta = ctx.pat2beta_text(text, 1, nr_sites + 1, 16 if lbeta else 8)   # `stdin2beta 1 N+1` + trim_to_uint8 (pat2beta.py:32-37)
+    elif world == 1:
+        mc = counts(text)
+        beta = ctx.trim(mc, nr_sites, 16 if lbeta else 8)
+        mc.free()
     else:                                                           # record-sharded: ONE reduce of the int32 counts, trim afterwards (it is non-linear)
-        _, mc = ctx.pat2beta_text(text, 1, nr_sites + 1, 8, want_counts=True)
+        if big:
+            d = counts(text); mc = d.to_host(np.int32).reshape(-1, 2); d.free()
+        else:
+            _, mc = ctx.pat2beta_text(text, 1, nr_sites + 1, 8, want_counts=True)
         mc = wd.reduce_np(mc, 0)
         if rank != 0:
             return None

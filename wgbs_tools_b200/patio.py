@@ -61,6 +61,40 @@ def read_pat_device(ctx, path: str):
     return ctx.bgzf_inflate(raw)
 
 
+def pat_pieces(ctx, text, limit: int | None = None):
+    """A pat text (bytes, or a DevBuf of device-resident text) as pieces of at most `limit` bytes that end at line ends: one
+    wgbs_pats_from_text call takes < 4 GiB, a 30x pat file is more.  pat2beta and homog are sums over records, so the pieces are
+    simply processed one after the other.  Yields the text itself when it fits (the common case costs nothing)."""
+    import os
+    from .api import DevBuf, DevView
+    limit = limit or int(os.environ.get("WGBS_PAT_CHUNK_BYTES", 2 << 30))
+    n = len(text)
+    if n <= limit:
+        yield text
+        return
+    dev = isinstance(text, DevBuf)
+    mv = None if dev else memoryview(text)
+    lo = 0
+    while lo < n:
+        hi = min(lo + limit, n)
+        if hi < n:                                                   # back up to the last line end inside [lo, hi)
+            if dev:
+                import numpy as np
+                from ._lib import check, lib
+                w = min(hi - lo, 1 << 20)
+                tail = np.empty(w, np.uint8)
+                check(lib.wgbs_memcpy(ctx.h, tail.ctypes.data, text.ptr + hi - w, w))
+                k = tail.tobytes().rfind(b"\n")
+                cut = hi - w + k + 1 if k >= 0 else lo
+            else:
+                cut = text.rfind(b"\n", lo, hi) + 1
+            if cut <= lo:
+                raise ValueError("pat line longer than the chunk size (WGBS_PAT_CHUNK_BYTES)")
+            hi = cut
+        yield DevView(text.ptr + lo, hi - lo) if dev else mv[lo:hi]
+        lo = hi
+
+
 def splitextgz(name: str) -> str:
     for suf in (".pat.gz", ".pat"):
         if name.endswith(suf):
