@@ -189,3 +189,28 @@ def test_pat_pieces_cut_at_line_ends():
     assert b"".join(ps) == txt[:-1]
     with pytest.raises(ValueError):
         list(pat_pieces(None, b"chr1\t5\t" + b"C" * 500 + b"\t1\n" * 3, 100))
+
+
+def test_pat_tile_parser_core_on_the_cpu(tmp_path):
+    """csrc/pat_core.cuh (what pat_tiles_k runs per line) built with g++; the kernel's two passes emulated sequentially over
+    real texts == the default parser's algorithm: long patterns, lines across tile edges, blank lines, extra columns, errors"""
+    import subprocess
+    exe = str(tmp_path / "pat_core_check")
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(os.path.dirname(os.path.abspath(__file__)), "pat_core_check.cpp")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    rng = np.random.default_rng(8)
+    idx, pats, cnt = synth.make_pat_records(2, 30_000, 200_000, mean_len=9, max_len=70)
+    txt = synth.pat_text("chr7", idx, pats, cnt)
+    long_pat = bytes(rng.choice(list(b"CT.H"), size=40_000).tolist())
+    parts = [b"chr1\t7\t" + long_pat + b"\t3", b"", b"chr1\t9\tCCT\t1\tx\ty"]
+    for k in (16384 - 30, 16384 - 13, 16384, 32768 + 5):
+        parts += [b"chr1\t11\t" + b"T" * (k % 997 + 1) + b"\t1"] * 3
+    t2 = b"\n".join(parts + txt.splitlines()[:5000]) + b"\n"
+    cases = [txt, txt[:-1], b"", b"\n", b"\n\n\n", b"chr1\t5\tCT\t2", b"chr1\t5\tCT\t2\n", t2, synth.make_pat_text_fast(3, 150_000, 1_000_000)]
+    cases += [b"chr1\t1\t" + b"C" * pad + b"T\t1\n" + t2[:70_000] for pad in range(0, 40, 3)]
+    cases += [b"chr1\t5\tCT\n", txt[:txt.rindex(b"\n", 0, 5000) + 1] + b"chr1\tx\tCT\t1\n" + txt[5000:9000]]        # too few columns; non-numeric
+    for k, c in enumerate(cases):
+        p = tmp_path / f"c{k}.pat"; p.write_bytes(c)
+        r = subprocess.run([exe, str(p)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0 and r.stdout.strip().endswith("mismatches 0"), (k, r.stdout, r.stderr)
