@@ -250,6 +250,36 @@ def extras(ctx, torch, peak, sam_for_bam=b""):
             os.remove(p)
     for b in dbet + [dd, d_txt, mc, bs, be, d_rng, d_out]:
         b.free()
+    # ---- the MM/ML mode of the pileup (BASELINE config 5's flavour: single-end reads with MM:Z / ML:B:C tags, 5mC + 5hmC calls)
+    try:
+        n_np = 150_000
+        t0 = time.time(); npsam = synth.make_np_sam(genome(), n_np, 7)
+        log(f"[bench] MM/ML SAM batch: {n_np:,} records, {len(npsam) / 1e6:.1f} MB ({time.time() - t0:.1f}s)")
+        d_np = ctx.upload(npsam)
+        ix_np = ctx.load_index(genome().loci, 1)
+
+        def np_step():
+            Pn, _ = ctx.pileup_sam(ix_np, d_np)              # MM tag on the first line: MM/ML mode is auto-detected like patter does
+            Pn.collapse(); Pn.free()
+        sec_np = dev_time(np_step, reps=5, warm=2)
+        Pn, st_np = ctx.pileup_sam(ix_np, d_np)
+        Pn.collapse()
+        got = Pn.to_text(CHR); Pn.free()
+        out["pileup_mm_ml"] = {"records": n_np, "sam_bytes": len(npsam), "ms": sec_np * 1e3, "reads_per_sec": n_np / sec_np, "nanopore_mode": int(st_np["nanopore"]),
+                               "templates": int(st_np["templates"]), "what": "tokenize + MM/ML decode + calls + collapse, inputs resident in HBM"}
+        if H.have_ref():
+            sub = npsam[: npsam.index(b"\n", len(npsam) // 8) + 1]
+            dp = H.write_tmp(genome().dict_text(), ".CpG.bed")
+            t0 = time.time(); ro, _ = H.ref_patter(sub, dp, CHR, False, nanopore=True); c_np = time.time() - t0
+            os.remove(dp)
+            gsub, _ = ctx.pileup_sam(ix_np, sub)
+            gsub.collapse()
+            out["pileup_mm_ml"]["cpu_reference"] = {"reads_per_sec": sub.count(b"\n") / c_np, "cores": 1, "sample": f"{sub.count(10):,} records, patter --nanopore (incl. loading the dictionary)",
+                                                    "identical_pat": bool(gsub.to_text(CHR) == H.ref_collapse(ro))}
+            gsub.free()
+        d_np.free(); ix_np.free()
+    except Exception as e:
+        out["pileup_mm_ml"] = {"error": repr(e)}
     # ---- BAM ingest (host side: BGZF inflate + BAM -> SAM text on threads); what `samtools view` does in the reference pipeline
     try:
         from wgbs_tools_b200 import bamio
