@@ -142,8 +142,20 @@ def reference_run(sam: bytes, shards: int, steps: int, warmup: int, opt: bool = 
         if it >= warmup:
             times.append(dt)
     nlines = sum(1 for p in paths for _ in open(p + ".pat", "rb"))
+    # what one patter process spends before its first read: loading the CpG dictionary of the chromosome (patter.cpp:14-42; every
+    # chromosome worker of the reference pays it once, every shard pipeline here)
+    global REF_DICT_LOAD_S
+    one = os.path.join(tmp, "one.sam")
+    with open(one, "wb") as f:
+        f.writelines(lines[:2])
+    t0 = time.time()
+    subprocess.run(cmd.format(inp=one), shell=True, env=env, stderr=subprocess.DEVNULL)
+    REF_DICT_LOAD_S = time.time() - t0
     subprocess.run(["rm", "-rf", tmp])
     return float(np.mean(times)), len(paths), nlines
+
+
+REF_DICT_LOAD_S = None
 
 
 def host_threads() -> int:
@@ -630,7 +642,8 @@ def main():
             "dtype": "u8", "data": "synthetic", "config": config,
             "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": "reference",
                              "sample": f"whole batch ({n_rec:,} records) as {nsh} concurrent shard pipelines "
-                                       "(match_maker|patter|sort|uniq|awk, reference setup.py flags)"},
+                                       "(match_maker|patter|sort|uniq|awk, reference setup.py flags); every pipeline loads the chromosome's "
+                                       f"CpG dictionary first, as every chromosome worker of the reference does ({REF_DICT_LOAD_S:.1f} s of each step)"},
             "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -831,7 +844,9 @@ def main():
             sec, nsh, nlines = r
             cpu = {"value": n_rec / sec, "unit": "reads/s", "cores": cores, "kind": "reference",
                    "sample": f"whole batch ({n_rec:,} records) once, as {nsh} concurrent shard pipelines of the reference "
-                             "executables (match_maker|patter|sort|uniq|awk; reference setup.py flags, i.e. no -O)"}
+                             "executables (match_maker|patter|sort|uniq|awk; reference setup.py flags, i.e. no -O); every pipeline loads the "
+                             f"chromosome's CpG dictionary first, as every chromosome worker of the reference does ({REF_DICT_LOAD_S:.1f} s of the run)",
+                   "dictionary_load_s": REF_DICT_LOAD_S}
 
     extra = None
     if rank == 0 and args.gpus == 1 and not args.no_extras:
