@@ -628,7 +628,7 @@ def main():
         sam = make_batch(args.reads, 1000)
         n_rec = sam.count(10)
         cores = host_threads()
-        shards = max(1, min(cores // 4, 32))
+        shards = max(1, min(cores // 2, 64))                  # one pipeline = patter + 4 light helpers: half the cores as pipelines keeps every core busy
         r = reference_run(sam, shards, args.steps, args.warmup)
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref executables missing"}))
@@ -834,7 +834,7 @@ def main():
     cpu = None
     if rank == 0 and args.gpus == 1:
         cores = host_threads()
-        shards = max(1, min(cores // 4, 32))
+        shards = max(1, min(cores // 2, 64))                  # one pipeline = patter + 4 light helpers: half the cores as pipelines keeps every core busy
         try:
             r = reference_run(sam, shards, 1, 0)
         except Exception as e:  # the baseline must not kill the bench line
