@@ -252,8 +252,17 @@ def extras(ctx, torch, peak, sam_for_bam=b""):
     chunks = [(s, min(60_000, S - s)) for s in range(0, S, 60_000)]
     t0 = time.time(); res = ctx.segment(dbet, dd, chunks, 1000, 2000, 15); torch.cuda.synchronize(); warm = time.time() - t0
     t0 = time.time(); res = ctx.segment(dbet, dd, chunks, 1000, 2000, 15); torch.cuda.synchronize(); sec_s = time.time() - t0
+    # work of the DP: one cost cell per admissible (start, end) pair (max_cpg 1000, max_bp 2000, inside the chunk), K log-likelihood
+    # terms per cell (one fp32 divide + log2f + fp64 log2 each: SURVEY 8d -- segment is bound by that arithmetic, not by HBM)
+    l64 = loci.astype(np.int64); e_idx = np.arange(S)
+    lo_i = np.maximum(np.maximum((e_idx // 60_000) * 60_000, e_idx + 1 - 1000), np.searchsorted(l64, l64 - 2000, side="left"))
+    cells = int((e_idx - lo_i + 1).sum())
+    hbm_min = 2 * K * S + 8 * S
     out["segment"] = {"K": K, "sites": S, "chunks": len(chunks), "ms": sec_s * 1e3, "sites_per_sec": S / sec_s,
-                      "blocks": int(sum(len(r) - 1 for r in res)), "timing": "host wall clock around the C-ABI call (includes D2H of borders)"}
+                      "blocks": int(sum(len(r) - 1 for r in res)), "timing": "host wall clock around the C-ABI call (includes D2H of borders)",
+                      "cost_cells": cells, "cell_terms_per_sec": cells * K / sec_s,
+                      "roofline": {"bound": "arithmetic (fp32 divide + log2f + fp64 log2 per term) and the sequential DP chain per chunk; HBM minimum shown for scale",
+                                   "hbm_min_bytes": hbm_min, "achieved": hbm_min / sec_s / 1e9, "peak": peak, "unit": "GB/s", "frac": hbm_min / sec_s / 1e9 / peak}}
     if H.have_ref():
         paths = [H.write_tmp(b.tobytes(), f".{i}.beta") for i, b in enumerate(betas)]
         t0 = time.time(); r0 = H.ref_segmentor(paths, 0, 60_000, 1000, 2000, 15, loci[:60_000]); c3 = time.time() - t0
