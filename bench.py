@@ -548,8 +548,9 @@ def segment_leg():
         chunks = [(s, 60_000) for s in range(0, S, 60_000)]
         res = {}
         ref = None
-        for plan in ("worst", "exact"):
-            os.environ["WGBS_SEG_PLAN"] = plan
+        for plan in ("worst", "exact", "exact+redux"):
+            os.environ["WGBS_SEG_PLAN"] = plan.split("+")[0]
+            os.environ["WGBS_SEG_DP"] = "redux" if plan.endswith("redux") else "shuffle"
             try:
                 ctx.segment(dbet, dd, chunks, 1000, 2000, 15); torch.cuda.synchronize()            # warm-up
                 t0 = time.time(); r = ctx.segment(dbet, dd, chunks, 1000, 2000, 15); torch.cuda.synchronize(); sec = time.time() - t0

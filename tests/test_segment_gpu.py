@@ -90,3 +90,18 @@ def test_segment_exact_wave_plan_gives_the_same_borders(ctx, oracle, monkeypatch
     b = ctx.segment(betas, loci, chunks, 1000, 2000, 15)
     assert len(a) == len(b) == nch and all(np.array_equal(x, y) for x, y in zip(a, b))
     np.testing.assert_array_equal(b[7], oracle.port_segment([x[7 * n:8 * n] for x in betas], loci[7 * n:8 * n], 1000, 2000, 15))
+
+
+@pytest.mark.staged
+@pytest.mark.parametrize("K,n,max_cpg,max_bp,ps", [(6, 2500, 200, 2000, 15), (3, 4000, 1000, 5000, 1), (1, 800, 800, 10 ** 9, 15)])
+def test_segment_redux_argmax_gives_the_same_borders(ctx, oracle, monkeypatch, K, n, max_cpg, max_bp, ps):
+    """WGBS_SEG_DP=redux (argmax of a DP step by hardware warp reductions on order-preserving keys) == the shuffle version == oracle,
+    including windows wider than a warp (max_cpg 800 / 1000 with a huge max_bp)"""
+    betas = synth.make_betas(11, K, n)
+    loci = synth.make_genome(2, "chr1", n * 150, with_bases=False).loci[:n]
+    monkeypatch.delenv("WGBS_SEG_DP", raising=False)
+    a = ctx.segment(betas, loci, [(0, n)], max_cpg, max_bp, ps)[0]
+    monkeypatch.setenv("WGBS_SEG_DP", "redux")
+    b = ctx.segment(betas, loci, [(0, n)], max_cpg, max_bp, ps)[0]
+    np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(b, oracle.port_segment(betas, loci, max_cpg, max_bp, ps))

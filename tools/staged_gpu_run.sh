@@ -11,7 +11,7 @@ run() { local name=$1 limit=$2; shift 2; echo "== $name"; timeout "$limit" "$@" 
 run suite 600 python -m pytest tests -m gpu -x -q -k "not staged" -p no:cacheprovider
 run inflate_teams 120 python -m pytest tests/test_zz_bamdev_gpu.py -m gpu -q -k "team_kernels"
 run pat_tiles 120 python -m pytest tests/test_pat_gpu.py -m gpu -q -k "tile_parser"
-run seg_plan 120 python -m pytest tests/test_segment_gpu.py -m gpu -q -k "exact_wave_plan"
+run seg_plan 120 python -m pytest tests/test_segment_gpu.py -m gpu -q -k "exact_wave_plan or redux_argmax"
 run dev_parts 180 python -m pytest tests/test_zz_bamdev_gpu.py -m gpu -q -k "device_parts"
 # newline-scan variants (the env var is read once per process: whole test files per variant, then a short bench for the kernel time)
 for v in batch8 batch16 tma; do

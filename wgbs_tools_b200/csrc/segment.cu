@@ -152,6 +152,19 @@ __global__ void __launch_bounds__(256) seg_cost_k(const uint32_t *__restrict__ P
 // lane, broadcast by shuffle), and the first 32 cost cells of step x+1 are loaded while step x is being reduced.  No block
 // barrier anywhere; many chunks share an SM.
 constexpr int DP_T = 32;
+// REDUX = 1 (staged, WGBS_SEG_DP=redux): the argmax over the <= 32 candidates of a step by two hardware warp reductions instead of
+// five shuffle rounds of (double, index) pairs -- the reduction is what sits on the sequential chain.  A double is mapped to a
+// 64-bit unsigned key with the same order (sign flip / complement); REDUX.MAX over the high words, then over the low words of the
+// lanes that hold that high word, then the LARGEST j among the lanes that hold the maximum (lowest k wins ties, as above).  Costs
+// are finite or -inf and never -0.0 (seg_cost_k), so comparing keys == comparing doubles.
+__device__ __forceinline__ unsigned long long dbl_key(double v) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_dbl(unsigned long long k) {
+    return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+template <int REDUX>
 __global__ void __launch_bounds__(DP_T) seg_dp_k(const Chunk *__restrict__ chunks, const uint32_t *__restrict__ W, const uint64_t *__restrict__ coff,
                                                   const double *__restrict__ cost, uint32_t ring, int32_t *__restrict__ Tb /* per site+chunk */,
                                                   const uint64_t *__restrict__ toff) {
@@ -182,10 +195,20 @@ __global__ void __launch_bounds__(DP_T) seg_dp_k(const Chunk *__restrict__ chunk
                 const double v = M[(x - j) & mask] + cost[base + j];
                 if (v >= best) { best = v; bj = j; }                          // lowest k = largest j wins ties
             }
+            if (REDUX) {
+                const unsigned long long key = dbl_key(best);                  // lanes without a candidate hold -inf: the lowest key
+                const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+                const uint32_t mhi = __reduce_max_sync(0xffffffffu, hi);
+                const uint32_t mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+                const bool top = hi == mhi && lo == mlo;
+                const uint32_t mj = __reduce_max_sync(0xffffffffu, top ? bj : 0u);
+                best = key_dbl(((unsigned long long)mhi << 32) | mlo); bj = mj;
+            } else {
 #pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, best, d); const uint32_t oj = __shfl_xor_sync(0xffffffffu, bj, d);
-                if (ov > best || (ov == best && oj > bj)) { best = ov; bj = oj; }
+                for (int d = 16; d >= 1; d >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, best, d); const uint32_t oj = __shfl_xor_sync(0xffffffffu, bj, d);
+                    if (ov > best || (ov == best && oj > bj)) { best = ov; bj = oj; }
+                }
             }
             if (lane == 0) { M[(x + 1) & mask] = best; T[x + 1] = (int32_t)(x - bj); }
             __syncwarp();
@@ -294,7 +317,10 @@ extern "C" int wgbs_segment(wgbs_ctx *ctx, const uint8_t *const *betas, int K, c
     const uint32_t *ddists = (const uint32_t *)dd;
     uint32_t *bad = ctx->d_flags + 2;
     CUDA_TRY(cudaMemsetAsync(bad, 0, 4, ctx->stream));
-    CUDA_TRY(cudaFuncSetAttribute(seg_dp_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const char *dpv = getenv("WGBS_SEG_DP");
+    const bool dp_redux = dpv && !strcmp(dpv, "redux");
+    if (dp_redux) CUDA_TRY(cudaFuncSetAttribute(seg_dp_k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else CUDA_TRY(cudaFuncSetAttribute(seg_dp_k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     // waves of consecutive chunks bounded by a scratch budget
     const uint64_t CELL_BUDGET = 600ull << 20;          // cells (8 B each)  -> <= 4.7 GiB of cost
@@ -354,7 +380,8 @@ extern "C" int wgbs_segment(wgbs_ctx *ctx, const uint8_t *const *betas, int K, c
             if (g > 0x7fffffffull) return wgbs_set_err("wgbs_segment: wave too large");
             LAUNCH(ctx, seg_cost_k, (unsigned)g, 256, 0, Pm, Pt, ns, K, coff, ncells, pseudo, cost);
         }
-        LAUNCH(ctx, seg_dp_k, nw, DP_T, smem, dch, Wd, coff, cost, ring, Tb, dtoff);
+        if (dp_redux) LAUNCH(ctx, seg_dp_k<1>, nw, DP_T, smem, dch, Wd, coff, cost, ring, Tb, dtoff);
+        else LAUNCH(ctx, seg_dp_k<0>, nw, DP_T, smem, dch, Wd, coff, cost, ring, Tb, dtoff);
         LAUNCH(ctx, seg_trace_k, grid_for(nw, 64), 64, 0, dch, nw, Tb, dtoff, dbord, dnb);
         LAUNCH_CHECK();
         // borders: the caller's buffer is laid out like ours (n_c + 1 slots per chunk, chunk order)
