@@ -22,6 +22,16 @@ FLAGS_FILTER = 1796
 FLAGS_FILTER_NANOPORE = 3844
 
 
+def default_threads() -> int:
+    """the reference's default for -@ (utils_wgbs.py:250-260): SLURM_JOB_CPUS_PER_NODE, else all CPUs, else 8 -- capped, because
+    here the threads only (de)compress BGZF blocks"""
+    try:
+        n = int(os.environ["SLURM_JOB_CPUS_PER_NODE"]) if "SLURM_JOB_CPUS_PER_NODE" in os.environ else (len(os.sched_getaffinity(0)) or 8)
+    except Exception:
+        n = 8
+    return max(1, min(n, 64))
+
+
 def split_sam_by_chrom(sam: bytes) -> dict[str, bytes]:
     """contiguous runs of equal RNAME in a coordinate-sorted SAM (header lines dropped)"""
     out: dict[str, list[bytes]] = {}
@@ -296,7 +306,8 @@ def add_args(p):
     p.add_argument("--verbose", "-v", action="store_true")
     p.add_argument("--clip", type=int, default=0, help="Clip for each read the first and last CLIP characters [0]")
     p.add_argument("--long", action="store_true", help="Use long format for pat file (add read name to each line)")
-    p.add_argument("-@", "--threads", type=int, default=8, help="host threads for BGZF inflate/deflate")
+    p.add_argument("-@", "--threads", type=int, default=default_threads(),
+                   help="host threads for BGZF inflate/deflate (default: all available CPUs, capped at 64; utils_wgbs.py:250-260)")
     p.add_argument("--bam_decode", choices=["auto", "host", "device", "stream"], default=os.environ.get("WGBS_BAM_DECODE", "auto"),
                    help="where the .bam is decoded: on the GPU (compressed bytes over PCIe, one warp per BGZF block), on host threads (zlib), "
                         "auto = GPU unless the inflated file does not fit in device memory, or stream = read the file as a sequence of "
