@@ -319,7 +319,7 @@ def test_streamed_parts_give_every_template_once(built_lib, tmp_path, budget):
 
 
 def test_chromosome_block_ranges_without_an_index(built_lib, tmp_path):
-    """chrom_first_blocks (binary search with wgbs_bam_probe) brackets every chromosome's records, and streaming only a
+    """chrom_block_ranges (binary search with wgbs_bam_probe) brackets every chromosome's records, and streaming only a
     chromosome's block range gives exactly that chromosome's whole-file view"""
     from wgbs_tools_b200 import bamio
     gs = [synth.make_genome(7 + i, f"chr{c}", L) for i, (c, L) in enumerate((("A", 150_000), ("B", 90_000), ("C", 30_000), ("E", 60_000)))]
@@ -329,15 +329,15 @@ def test_chromosome_block_ranges_without_an_index(built_lib, tmp_path):
     p = tmp_path / "s.bam"
     p.write_bytes(bamio.sam_to_bam(sam, refs))
     table = bamio.bgzf_block_table(str(p))
-    first = bamio.chrom_first_blocks(str(p), table, len(refs))
-    assert first == sorted(first) and len(first) == len(refs) + 1 and first[0] == 0
+    ranges = bamio.chrom_block_ranges(str(p), table, len(refs))
+    assert len(ranges) == len(refs) and ranges[0][0] == 0 and all(lo <= hi for lo, hi in ranges)
     kw = dict(mapq=10, exclude_flags=1796)
     names = [r[0] for r in refs]
     with bamio.BamFile(str(p), threads=2) as b:
         whole = {c: b.view(c, **kw) for c in names}
     opener = lambda data, r, l, f: bamio.BamPart(data, r, l, f, threads=2)
     for ci, c in enumerate(names):
-        rng = (max(first[ci] - 1, 0), min(first[ci + 1] + 1, table[0].size))
+        rng = ranges[ci]
         got = []
         for part, chrom, win, done in bamio.stream_parts(str(p), opener, lambda _c: kw, 150_000, blocks=rng, refs0=names):
             if chrom == c:

@@ -226,18 +226,18 @@ class _Source:
         if self.stream is not None:                          # the compressed bytes between the chromosome's first block and the next one's
             if chrom not in self.bam.refs:
                 return 0
-            first, coff = self.chrom_blocks(), self.stream["table"][0]
-            c = self.bam.refs.index(chrom); end = int(coff[-1]) + 1
-            return max((int(coff[first[c + 1]]) if first[c + 1] < coff.size else end) - (int(coff[first[c]]) if first[c] < coff.size else end), 0)
+            coff, csize, _ = self.stream["table"]
+            lo, hi = self.chrom_blocks()[self.bam.refs.index(chrom)]
+            return int(coff[hi - 1] + csize[hi - 1] - coff[lo]) if hi > lo else 0
         if self.bam is not None:
             return self.bam.nrecords(chrom) if chrom in self.bam.refs else 0
         return len(self.sam.get(chrom, b""))
 
-    def chrom_blocks(self) -> list[int]:
-        """streamed .bam: first BGZF block of every reference (bamio.chrom_first_blocks), found once by probing"""
+    def chrom_blocks(self) -> list[tuple[int, int]]:
+        """streamed .bam: the BGZF block range of every reference (bamio.chrom_block_ranges), found once by probing"""
         if self.stream["first"] is None:
-            from .bamio import chrom_first_blocks
-            self.stream["first"] = chrom_first_blocks(self.stream["path"], self.stream["table"], len(self.bam.refs))
+            from .bamio import chrom_block_ranges
+            self.stream["first"] = chrom_block_ranges(self.stream["path"], self.stream["table"], len(self.bam.refs))
         return self.stream["first"]
 
     def block_runs(self, chroms) -> list[tuple[int, int]] | None:
@@ -247,10 +247,10 @@ class _Source:
         want = sorted(refs.index(c) for c in chroms if c in refs)
         if len(want) >= len(refs):
             return None
-        first = self.chrom_blocks()
+        ranges = self.chrom_blocks()
         runs: list[list[int]] = []
         for c in want:
-            lo, hi = max(first[c] - 1, 0), min(first[c + 1] + 1, nb)
+            lo, hi = ranges[c]
             if hi <= lo:
                 continue
             if runs and lo <= runs[-1][1]:

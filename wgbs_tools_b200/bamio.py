@@ -172,31 +172,39 @@ def probe_block(f, table, b: int, n_ref: int, span: int = 3):
     return None
 
 
-def chrom_first_blocks(path: str, table, n_ref: int) -> list[int]:
-    """first[c] = the first BGZF block b of a coordinate-sorted .bam such that the first record starting in b.. belongs to
-    reference >= c (unmapped records count as beyond every reference); first[n_ref] = where the unmapped tail starts.  The
-    records of reference c lie in blocks [first[c] - 1, first[c + 1]]: binary search with wgbs_bam_probe, no .bai needed."""
-    nb = table[0].size
-    first = []
+def chrom_block_ranges(path: str, table, n_ref: int) -> list[tuple[int, int]]:
+    """ranges[c] = (lo, hi): the BGZF blocks [lo, hi) of a coordinate-sorted .bam that hold every record of reference c, found
+    without a .bai by binary search with wgbs_bam_probe.  With first[c] = the first block b such that the first record STARTING
+    in b.. belongs to a reference >= c (unmapped records count as beyond every reference), the records of c start in blocks
+    >= first[c] - 1 and end before the block in which the first record of a later reference starts has ended -- that block, not
+    first[c + 1], is the upper end: a record may be longer than a block."""
+    coff, csize, usize = table
+    nb = coff.size
+    uoff = np.concatenate([[0], np.cumsum(usize)])
+    first, rec_block = [], []
     with open(path, "rb") as f:
         memo = {}
 
-        def rid(b):
+        def probe(b):
             if b not in memo:
-                r = probe_block(f, table, b, n_ref)
-                memo[b] = (1 << 30) if r is None or r[1] < 0 else r[1]
+                r = probe_block(f, table, b, n_ref) if b < nb else None
+                if r is None:
+                    memo[b] = ((1 << 30), nb)
+                else:
+                    at = int(uoff[b]) + r[0]                                     # inflated offset of that record in the file
+                    memo[b] = ((1 << 30) if r[1] < 0 else r[1], int(np.searchsorted(uoff, at, side="right")) - 1)
             return memo[b]
         lo_all = 0
         for c in range(n_ref + 1):
             lo, hi = lo_all, nb                      # first b in [lo, nb] with rid(b) >= c   (rid(nb) = infinity)
             while lo < hi:
                 m = (lo + hi) // 2
-                if rid(m) >= c:
+                if probe(m)[0] >= c:
                     hi = m
                 else:
                     lo = m + 1
-            first.append(lo); lo_all = lo
-    return first
+            first.append(lo); rec_block.append(probe(lo)[1] if lo < nb else nb); lo_all = lo
+    return [(max(first[c] - 1, 0), min(rec_block[c + 1] + 1, nb)) for c in range(n_ref)]
 
 
 def stream_parts(path: str, open_part, view_kw_for, budget: int, blocks: tuple[int, int] | None = None, refs0=None):
