@@ -10,6 +10,7 @@
 //                                                      (FLAGEQ: comma list or '-', RG: read group or '-', IVFILE: "beg end"
 //                                                      lines or '-'), print the SAM text; stderr: stats
 //   bamdev_core_check fmtg N SEED                      fmt_g vs snprintf("%g") on N random floats + edge cases
+//   bamdev_core_check part FILE.bam SEG DEPTH B0 NB FIRST REFS   blocks [B0, B0+NB) as a part of a streamed file (dbam_open_impl, part mode)
 #include <zlib.h>
 
 #include <algorithm>
@@ -214,6 +215,56 @@ static int cmd_view(const char *path, uint64_t SEG, int depth, int argc, char **
     return 0;
 }
 
+// A PART of a file (wgbs_dbam_open_part, bamdev.cu dbam_open_impl with part != nullptr): blocks [b0, b0 + nb) inflated, records
+// indexed from inflated offset `first` on with the segment guess / walk / repair scheme, the record cut off by the end of the part
+// ends the chain (tail), segments behind it hold no record of this part.  Prints "nrec tail" on stderr and the SAM text of the
+// records on stdout; refs: "name,name,..." (the reference list of the file).
+static int cmd_part(const char *path, uint64_t SEG, int depth, size_t b0, size_t nb, uint64_t first, const char *refs_csv) {
+    auto f = slurp(path); uint64_t ut; auto all = scan_blocks(f, &ut);
+    if (b0 + nb > all.size()) nb = all.size() - b0;
+    uint64_t n = 0; for (size_t i = b0; i < b0 + nb; i++) n += all[i].usize;
+    std::vector<uint8_t> d(n + 16, 0); uint64_t at = 0;
+    for (size_t i = b0; i < b0 + nb; i++) { const Blk &b = all[i]; if (one_lane(f.data() + b.coff + 12 + b.xlen, b.csize - 12 - b.xlen - 8, d.data() + at, b.usize)) { fprintf(stderr, "inflate failed\n"); return 3; } at += b.usize; }
+    using namespace bamcore;
+    std::vector<uint32_t> name_off{0}; std::string names; std::vector<int32_t> lens;
+    { std::string r(refs_csv); size_t p = 0; while (p <= r.size()) { size_t q = r.find(',', p); if (q == std::string::npos) q = r.size(); names.append(r, p, q - p); name_off.push_back((uint32_t)names.size()); lens.push_back(0); p = q + 1; } }
+    const int32_t n_ref = (int32_t)lens.size();
+    Refs F{n_ref, name_off.data(), names.data(), lens.data()};
+    const uint64_t p0 = first; uint64_t nseg = n > p0 ? (n - p0 + SEG - 1) / SEG : 0, tail = n > p0 ? n : p0;
+    std::vector<uint64_t> entry(nseg + 1), exit_(nseg), bad(nseg, ~0ull); std::vector<uint32_t> cnt(nseg);
+    OneLane one;
+    for (uint64_t s = 0; s < nseg; s++) entry[s] = s == 0 ? p0 : guess_entry(one, d.data(), n, p0 + s * SEG, n_ref, depth);
+    std::vector<char> dirty(nseg, 1);
+    for (bool changed = true; changed;) {
+        changed = false;
+        for (uint64_t s = 0; s < nseg; s++) if (dirty[s]) { bad[s] = ~0ull; exit_[s] = walk_chain(d.data(), n, entry[s], p0 + (s + 1) * SEG, &cnt[s], nullptr, &bad[s]); dirty[s] = 0; }
+        std::vector<uint64_t> next(entry);
+        for (uint64_t s = 0; s + 1 < nseg; s++) { bool ch = false; next[s + 1] = repaired_entry(entry.data(), exit_.data(), bad.data(), s, &ch); if (ch) { dirty[s + 1] = 1; changed = true; } }
+        entry.swap(next);
+    }
+    uint64_t first_bad = ~0ull;
+    for (uint64_t s = 0; s < nseg; s++) if (bad[s] < first_bad) first_bad = bad[s];
+    if (first_bad != ~0ull) {
+        const uint64_t o = first_bad; const uint32_t bs = o + 4 <= n ? ld32(d.data() + o) : 0;
+        const bool cut = o + 4 > n || (bs >= 32 && o + 4 + (uint64_t)bs > n);
+        if (!cut) { fprintf(stderr, "corrupt BAM record at %llu\n", (unsigned long long)o); return 3; }
+        tail = o; nseg = o > p0 ? (o - p0) / SEG + 1 : 1;
+    }
+    std::vector<uint64_t> rec;
+    for (uint64_t s = 0; s < nseg; s++) { std::vector<uint64_t> o(cnt[s]); uint32_t c; uint64_t b = ~0ull; walk_chain(d.data(), n, entry[s], p0 + (s + 1) * SEG, &c, o.data(), &b); rec.insert(rec.end(), o.begin(), o.end()); }
+    std::string out;
+    for (uint64_t o : rec) {
+        Rec R; R.load(d.data() + o);
+        if (!R.consistent()) { fprintf(stderr, "inconsistent record at %llu\n", (unsigned long long)o); return 3; }
+        CountSink cs; format_record(R, F, cs);
+        const size_t a2 = out.size(); out.resize(a2 + cs.n);
+        WriteSink<OneLane> ws; ws.o = &out[a2]; format_record(R, F, ws);
+    }
+    fwrite(out.data(), 1, out.size(), stdout);
+    fprintf(stderr, "nrec %zu tail %llu\n", rec.size(), (unsigned long long)tail);
+    return 0;
+}
+
 static int cmd_fmtg(long N, unsigned seed) {
     std::mt19937_64 rng(seed); size_t bad = 0;
     auto test = [&](uint32_t u) {
@@ -238,6 +289,7 @@ int main(int argc, char **argv) {
     if (argc >= 3 && !strcmp(argv[1], "inflate")) return cmd_inflate(argv[2], argc > 3 ? atoi(argv[3]) : 0);
     if (argc >= 5 && !strcmp(argv[1], "view")) return cmd_view(argv[2], strtoull(argv[3], nullptr, 10), atoi(argv[4]), argc - 5, argv + 5);
     if (argc >= 4 && !strcmp(argv[1], "fmtg")) return cmd_fmtg(atol(argv[2]), (unsigned)atoi(argv[3]));
+    if (argc >= 9 && !strcmp(argv[1], "part")) return cmd_part(argv[2], strtoull(argv[3], nullptr, 10), atoi(argv[4]), strtoull(argv[5], nullptr, 10), strtoull(argv[6], nullptr, 10), strtoull(argv[7], nullptr, 10), argv[8]);
     fprintf(stderr, "usage: see the header of tests/bamdev_core_check.cpp\n");
     return 2;
 }

@@ -204,3 +204,32 @@ def test_filters_match_the_host_reader(check, sam, tmp_path, built_lib):
             assert r.returncode == 0, r.stderr.decode()
             assert r.stdout == exp, kw
             assert kw.get("chrom") == "chrM" or kw.get("read_group") == "nosuch" or exp
+
+
+def test_part_record_table_equals_the_host_part_reader(check, sam, tmp_path, built_lib):
+    """the device's part mode (dbam_open_impl with a cut-off last record: first bad record = tail, segments behind it ignored),
+    emulated on the CPU, == wgbs_bam_open_part: same records, same tail, for parts starting at a probed record in mid-file"""
+    from wgbs_tools_b200 import bamio
+    g, s = sam
+    lines = s.splitlines()
+    # a few very long records so that cut-off records span several 16 KiB segments and whole BGZF blocks
+    big = b"L1\t0\tchrT\t150000\t60\t90000M\t*\t0\t0\t" + b"ACGT" * 22500 + b"\t" + b"F" * 90000
+    lines = sorted(lines + [big, big.replace(b"L1", b"L2").replace(b"150000", b"150700")], key=lambda l: int(l.split(b"\t")[3]))
+    full = b"\n".join(lines) + b"\n"
+    p = tmp_path / "p.bam"
+    p.write_bytes(bamio.sam_to_bam(full, [("chrT", g.length)]))
+    table = bamio.bgzf_block_table(str(p)); nb = table[0].size
+    raw = p.read_bytes()
+    with open(p, "rb") as f:
+        for b0, n in [(3, 2), (5, 1), (nb // 2, 3), (nb // 2 + 1, 7), (nb - 4, 4), (1, nb - 1)]:
+            pr = bamio.probe_block(f, table, b0, 1)
+            assert pr is not None
+            data = raw[int(table[0][b0]): int(table[0][b0 + n - 1] + table[1][b0 + n - 1])]
+            host = bamio.BamPart(data, ["chrT"], [g.length], pr[0], threads=2)
+            exp = host.view()
+            for seg in (4096, 16384):
+                r = subprocess.run([check, "part", str(p), str(seg), "4", str(b0), str(n), str(pr[0]), "chrT"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+                assert r.returncode == 0, r.stderr.decode()
+                assert r.stdout == exp, (b0, n, seg)
+                assert r.stderr.decode().strip().endswith(f"nrec {host.nrecords()} tail {host.tail}"), (r.stderr.decode(), host.tail)
+            host.close()
