@@ -168,7 +168,7 @@ class _Source:
                 try:
                     self.bam = DeviceBam(ctx, path)
                 except WgbsError as e:
-                    if decode != "auto" or "does not fit in device memory" not in str(e):
+                    if decode != "auto" or not ("does not fit in device memory" in str(e) or "out of memory" in str(e).lower()):
                         raise
                     print(f"[wt bam2pat] {e}; reading the file in parts (--bam_decode stream)", file=sys.stderr)
                     self.__init__(path, threads, ctx, "stream")
