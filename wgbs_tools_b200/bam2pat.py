@@ -163,12 +163,16 @@ class _Source:
             # device: the compressed bytes cross PCIe, BGZF inflate + record filtering + SAM formatting run in HBM (csrc/bamdev.cu);
             # auto: device unless the inflated file does not fit in device memory (then the host reader decodes it)
             self.on_device = decode in ("device", "auto")
+            # auto: a file whose inflated bytes (~5x the compressed ones) cannot fit beside the working set goes straight to streaming
+            if decode == "auto" and os.path.getsize(path) > int(os.environ.get("WGBS_DEVICE_BAM_MAX", 20 << 30)):
+                self.__init__(path, threads, ctx, "stream")
+                return
             if self.on_device:
                 from ._lib import WgbsError
                 try:
                     self.bam = DeviceBam(ctx, path)
                 except WgbsError as e:
-                    if decode != "auto" or not ("does not fit in device memory" in str(e) or "out of memory" in str(e).lower()):
+                    if decode != "auto" or not any(m in str(e).lower() for m in ("does not fit in device memory", "out of memory", "cannot pin")):
                         raise
                     print(f"[wt bam2pat] {e}; reading the file in parts (--bam_decode stream)", file=sys.stderr)
                     self.__init__(path, threads, ctx, "stream")
