@@ -430,7 +430,7 @@ def main(argv=None):
                 runs = src.block_runs(by_chrom) if by_chrom else []
                 import itertools
                 stream = itertools.chain.from_iterable(
-                    stream_parts(path, opener, lambda c: dict(flag_eq=feq, **view_kw(c)), src.stream["budget"], blocks=r, refs0=src.bam.refs)
+                    stream_parts(path, opener, lambda c: dict(flag_eq=feq, **view_kw(c)), src.stream["budget"], blocks=r, refs0=src.bam.refs, table=src.stream["table"])
                     for r in ([None] if runs is None else runs))
                 for part, chrom, win, done in stream:
                     if chrom not in by_chrom or (chrom not in piles and chrom in finished):

@@ -207,7 +207,7 @@ def chrom_block_ranges(path: str, table, n_ref: int) -> list[tuple[int, int]]:
     return [(max(first[c] - 1, 0), min(rec_block[c + 1] + 1, nb)) for c in range(n_ref)]
 
 
-def stream_parts(path: str, open_part, view_kw_for, budget: int, blocks: tuple[int, int] | None = None, refs0=None):
+def stream_parts(path: str, open_part, view_kw_for, budget: int, blocks: tuple[int, int] | None = None, refs0=None, table=None):
     """Read a coordinate-sorted .bam that does not fit in memory as a sequence of parts and yield
         (part, chrom, key_window, chrom_done)
     such that piling up, for every yielded item, the records of `chrom` in `part` that pass the view filters AND whose template
@@ -222,7 +222,7 @@ def stream_parts(path: str, open_part, view_kw_for, budget: int, blocks: tuple[i
     next part starts at the block holding the first deferred record (or the cut-off record), found by first_key().
     blocks / refs0: restrict the pass to BGZF blocks [blocks[0], blocks[1]) (a chromosome that ENDS inside the range is complete;
     the caller ignores chromosomes it did not ask for)."""
-    coff, csize, usize = bgzf_block_table(path)
+    coff, csize, usize = table if table is not None else bgzf_block_table(path)      # (the caller may have scanned the file already)
     nb = coff.size
     uoff = np.concatenate([[0], np.cumsum(usize)])
     refs = ref_lens = None
