@@ -428,12 +428,10 @@ extern "C" int wgbs_bam_view_ex(const wgbs_bam *B, const wgbs_view_opts *vo, cha
     if (vo->n_iv && (!vo->iv_beg || !vo->iv_end)) return wgbs_set_err("wgbs_bam_view: interval list is null");
     for (size_t k = 0; k + 1 < vo->n_iv; k++)
         if (vo->iv_beg[k + 1] < vo->iv_end[k] || vo->iv_end[k] < vo->iv_beg[k]) return wgbs_set_err("wgbs_bam_view: intervals must be sorted and non-overlapping");
-    const int refid = vo->refid, min_mapq = vo->min_mapq, exclude_flags = vo->exclude_flags, include_flags = vo->include_flags;
-    const int64_t beg = vo->beg, end = vo->end;
+    const int refid = vo->refid;
     const size_t rg_len = vo->read_group ? strlen(vo->read_group) : 0;
     uint64_t r0 = 0, r1 = B->rec_off.size();
     if (refid >= 0) { if (refid >= (int)B->ref_names.size()) return wgbs_set_err("wgbs_bam_view: no such reference"); r0 = B->ref_first[refid]; r1 = B->ref_last[refid]; }
-    const bool need_span = end > 0 || vo->n_iv;
     // head -N: a sequential walk (the caller wants the FIRST max_records passing records)
     const int nt = vo->max_records ? 1 : (int)std::max<uint64_t>(1, std::min<uint64_t>(B->threads, (r1 - r0) / 2048 + 1));
     std::vector<OutBuf> parts(nt); std::vector<uint64_t> cnt(nt, 0); std::atomic<int> oom(0);

@@ -21,8 +21,6 @@
 
 namespace {
 
-constexpr int NTAB = 11;   // tab ordinals 0..10 delimit the 11 mandatory fields
-
 // std::stoi semantics on text[s,e): optional blanks, sign, >=1 digit, int range; trailing junk ignored
 __device__ __forceinline__ bool parse_i32(const char *__restrict__ t, uint32_t s, uint32_t e, int32_t *out) {
     while (s < e && (t[s] == ' ' || (t[s] >= 9 && t[s] <= 13))) s++;
