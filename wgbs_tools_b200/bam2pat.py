@@ -432,6 +432,16 @@ def main(argv=None):
                 stream = itertools.chain.from_iterable(
                     stream_parts(path, opener, lambda c: dict(flag_eq=feq, **view_kw(c)), src.stream["budget"], blocks=r, refs0=src.bam.refs, table=src.stream["table"])
                     for r in ([None] if runs is None else runs))
+
+                def close_pile(chrom, mb):
+                    txt, st = piles.pop(chrom).finish()
+                    if txt is not None:
+                        if a.mbias and "mbias" in st:
+                            mb = st["mbias"].astype(np.int64) if mb is None else mb + st["mbias"]
+                        if txt:
+                            parts.append((by_chrom[chrom][0], bgzf_compress(txt, a.threads)))
+                    return mb
+
                 for part, chrom, win, done in stream:
                     if chrom not in by_chrom or (chrom not in piles and chrom in finished):
                         continue
@@ -446,13 +456,9 @@ def main(argv=None):
                         piles[chrom].add(part.view(chrom, **vkw))
                     if done:
                         finished.add(chrom)
-                        txt, st = piles.pop(chrom).finish()
-                        if txt is None:
-                            continue
-                        if a.mbias and "mbias" in st:
-                            mb_total = st["mbias"].astype(np.int64) if mb_total is None else mb_total + st["mbias"]
-                        if txt:
-                            parts.append((ri, bgzf_compress(txt, a.threads)))
+                        mb_total = close_pile(chrom, mb_total)
+                for chrom in list(piles):                                      # (a chromosome is always closed by its last part; belt and braces)
+                    mb_total = close_pile(chrom, mb_total)
                 regions = []                                                   # all done above
             for ri, region in enumerate(regions):
                 if ri not in mine:
