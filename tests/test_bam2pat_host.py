@@ -92,10 +92,17 @@ class PortContext:
         return _PortPats(H, lines, False), st
 
     def pats_from_text(self, text):
-        return _PortPats(self.H, text.splitlines(keepends=True), True)
+        return _PortPats(self.H, bytes(text).splitlines(keepends=True), True)
+
+    def pat2beta_text(self, text, start, end, nbits=8, want_counts=False):
+        mc = self.H.port_pat2beta(bytes(text), start, end)
+        beta = self.H.port_trim(mc, nbits)
+        return (beta, mc) if want_counts else beta
 
     def pat2beta(self, P, start, end, meth_cov=None, zero_first=True):
         mc = self.H.port_pat2beta(P.with_counts(), start, end) if P.lines else np.zeros((end - start, 2), np.int32)
+        if meth_cov is None:
+            meth_cov = _Buf((end - start) * 8)
         if zero_first:
             meth_cov.a[:] = 0
         meth_cov.a += mc.reshape(-1)
@@ -163,3 +170,23 @@ def test_streamed_bam_gives_the_same_outputs(world, monkeypatch, extra, budget):
     whole = _run(tmp, refdir, "s.bam", "whole", extra)
     monkeypatch.setenv("WGBS_STREAM_BYTES", budget)
     assert _run(tmp, refdir, "s.bam", "stream", extra, decode="stream") == whole
+
+
+def test_pat2beta_cli_on_a_pat_larger_than_one_call(tmp_path, oracle, monkeypatch, built_lib):
+    """pat2beta with the text cut into pieces (WGBS_PAT_CHUNK_BYTES) == in one call; gzip input (the host decode path)"""
+    from wgbs_tools_b200 import api
+    from wgbs_tools_b200 import pat2beta as p2b
+    monkeypatch.setattr(api, "Context", PortContext)
+    N = 40_000
+    txt = synth.make_pat_text_fast(5, 30_000, N, chrom="chr1")
+    pg = tmp_path / "x.pat.gz"
+    with gzip.open(pg, "wb") as f:
+        f.write(txt)
+    outs = []
+    for limit in (None, "50000", "7000"):
+        if limit:
+            monkeypatch.setenv("WGBS_PAT_CHUNK_BYTES", limit)
+        d = tmp_path / f"o{limit}"; d.mkdir()
+        p2b.pat2beta(PortContext(), str(pg), str(d), N, decode="host")
+        outs.append((d / "x.beta").read_bytes())
+    assert outs[0] == outs[1] == outs[2] == oracle.port_trim(oracle.port_pat2beta(txt, 1, N + 1)).tobytes()
