@@ -43,7 +43,8 @@ for it in range(12):
     (refdir / "CpG.chrome.size").write_text("".join(f"{g.chrom}\t{g.n_cpg}\n" for g in gs)); (refdir / "chrome.size").write_text("".join(f"{g.chrom}\t{g.length}\n" for g in gs))
     (tmp / "s.bam").write_bytes(bamio.sam_to_bam(sam, lens))
     outs = []
-    extra = random.choice([[], ["-F", "1796", "--include_flags", "1"], ["-r", "chr1"]])
+    extra = random.choice([[], ["-F", "1796", "--include_flags", "1"], ["-r", "chr1"], ["--long", "--no_beta"], ["--bottom_strand"], ["--top_strand"],
+                           ["--min_cpg", "2", "--clip", "3"], ["-r", "chr1:500-%d" % random.randint(600, 40_000)], ["-l"]])
     for tag, dec, env in (("w", "host", {}), ("s", "stream", {"WGBS_STREAM_BYTES": str(random.choice([1, 100_000, 400_000]))}), ("c", "host", {"WGBS_CHUNK_RECORDS": str(random.choice([50, 700]))})):
         os.environ.pop("WGBS_STREAM_BYTES", None); os.environ["WGBS_CHUNK_RECORDS"] = "0"
         os.environ.update(env)
