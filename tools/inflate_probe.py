@@ -18,6 +18,6 @@ with Context(0) as ctx:
         ctx.bgzf_inflate(raw).free()
     rep = ctx.prof_report()
     ctx.prof(False)
-    k, (c, ms) = next((k, v) for k, v in rep.items() if k.startswith("bgzf_inflate_k"))
+    k, (c, ms) = next((k, v) for k, v in rep.items() if k.startswith("bgzf_inflate"))
     print(json.dumps({"file": os.path.basename(path), "variant": os.environ.get("WGBS_INFLATE", "default"), "kernel": k, "compressed_bytes": len(raw),
                       "inflated_bytes": n, "ms_per_launch": ms / c, "inflated_GBps": n / (ms / c / 1e3) / 1e9}))
