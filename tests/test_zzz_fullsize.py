@@ -156,6 +156,37 @@ def test_config2_bam2pat_1m_reads_chr19_index(ctx, oracle):
 
 
 @pytest.mark.gpu
+def test_config4_segment_200_betas_chunk(ctx, oracle):
+    """configs[3]: K = 200 betas, the reference's 60 000-site chunk, max_cpg 5000 (effective min(max_cpg, max_bp // 2), segment.py:65),
+    pcount 15: borders identical to segmentor's; a chunk solved inside a many-chunk call == the same chunk solved alone"""
+    K, S, chunk = 200, 180_000, 60_000
+    betas = synth.make_betas(4, K, S)
+    loci = synth.make_genome(2, "chr1", 40_000_000, with_bases=False).loci[:S]
+    assert loci.size == S
+    max_bp = 2000; max_cpg = min(5000, max_bp // 2)
+    dbet = [ctx.upload(b) for b in betas]; dd = ctx.upload(loci)
+    chunks = [(s, chunk) for s in range(0, S, chunk)]
+    res = ctx.segment(dbet, dd, chunks, max_cpg, max_bp, 15)
+    alone = ctx.segment(dbet, dd, [chunks[1]], max_cpg, max_bp, 15)[0]
+    for b in dbet + [dd]:
+        b.free()
+    np.testing.assert_array_equal(res[1], alone)
+    for r in res:
+        assert r[0] == 0 and r[-1] == chunk and (np.diff(r) > 0).all() and (np.diff(r) <= max_cpg).all()
+    H = oracle
+    if H.have_ref():
+        paths = [H.write_tmp(b.tobytes(), f".{i}.beta") for i, b in enumerate(betas)]
+        try:
+            ref = H.ref_segmentor(paths, chunk, chunk, max_cpg, max_bp, 15, loci[chunk:2 * chunk])
+        finally:
+            for p in paths:
+                os.remove(p)
+    else:
+        ref = H.port_segment([b[chunk:2 * chunk] for b in betas], loci[chunk:2 * chunk], max_cpg, max_bp, 15)
+    np.testing.assert_array_equal(res[1], ref)
+
+
+@pytest.mark.gpu
 def test_config3_homog_and_pat2beta_hg38_index_100m_records(ctx, oracle):
     """configs[2]: U/X/M homog (and the pat2beta reduction) over a 28.2M-CpG index, 100M pat records, in batches the way a
     chromosome-sharded run feeds them; every batch: sum over two shards == whole, accumulated counts == sum of batches"""
@@ -189,34 +220,3 @@ def test_config3_homog_and_pat2beta_hg38_index_100m_records(ctx, oracle):
     got = E.homog(tail, blocks, rng, 3)[blocks.shape[0] - sub.shape[0]:]
     np.testing.assert_array_equal(got, oracle.port_homog(tail, sub, rng, 3))
     np.testing.assert_array_equal(E.p2b(tail, lo, N + 1), oracle.port_pat2beta(tail, lo, N + 1))
-
-
-@pytest.mark.gpu
-def test_config4_segment_200_betas_chunk(ctx, oracle):
-    """configs[3]: K = 200 betas, the reference's 60 000-site chunk, max_cpg 5000 (effective min(max_cpg, max_bp // 2), segment.py:65),
-    pcount 15: borders identical to segmentor's; a chunk solved inside a many-chunk call == the same chunk solved alone"""
-    K, S, chunk = 200, 180_000, 60_000
-    betas = synth.make_betas(4, K, S)
-    loci = synth.make_genome(2, "chr1", 40_000_000, with_bases=False).loci[:S]
-    assert loci.size == S
-    max_bp = 2000; max_cpg = min(5000, max_bp // 2)
-    dbet = [ctx.upload(b) for b in betas]; dd = ctx.upload(loci)
-    chunks = [(s, chunk) for s in range(0, S, chunk)]
-    res = ctx.segment(dbet, dd, chunks, max_cpg, max_bp, 15)
-    alone = ctx.segment(dbet, dd, [chunks[1]], max_cpg, max_bp, 15)[0]
-    for b in dbet + [dd]:
-        b.free()
-    np.testing.assert_array_equal(res[1], alone)
-    for r in res:
-        assert r[0] == 0 and r[-1] == chunk and (np.diff(r) > 0).all() and (np.diff(r) <= max_cpg).all()
-    H = oracle
-    if H.have_ref():
-        paths = [H.write_tmp(b.tobytes(), f".{i}.beta") for i, b in enumerate(betas)]
-        try:
-            ref = H.ref_segmentor(paths, chunk, chunk, max_cpg, max_bp, 15, loci[chunk:2 * chunk])
-        finally:
-            for p in paths:
-                os.remove(p)
-    else:
-        ref = H.port_segment([b[chunk:2 * chunk] for b in betas], loci[chunk:2 * chunk], max_cpg, max_bp, 15)
-    np.testing.assert_array_equal(res[1], ref)
