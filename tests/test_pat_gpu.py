@@ -137,15 +137,15 @@ def test_homog_overlapping_blocks(ctx, oracle):
     assert got[0, 2] == 2
 
 
-@pytest.mark.staged
-def test_tile_parser_equals_default_parser(ctx, monkeypatch):
+@pytest.mark.parametrize("variant", ["tiles", pytest.param("tiles_tma", marks=pytest.mark.staged)])     # (the TMA variant spins on an mbarrier: kept out of the default run)
+def test_tile_parser_equals_default_parser(ctx, monkeypatch, variant):
     """WGBS_PATPARSE=tiles / tiles_tma (pat_tiles_k, two passes over 16 KiB tiles; tiles fetched by LDG.128 or by one TMA bulk copy)
     == the default parser: same records, same pool, same errors"""
     rng = np.random.default_rng(8)
 
     def both(txt):
         res = []
-        for mode in ("default", "tiles", "tiles_tma"):
+        for mode in ("default", variant):
             monkeypatch.setenv("WGBS_PATPARSE", mode)
             try:
                 P = ctx.pats_from_text(txt)
@@ -153,8 +153,7 @@ def test_tile_parser_equals_default_parser(ctx, monkeypatch):
                 P.free()
             except Exception as e:
                 res.append(str(e))
-        for k in (1, 2):
-            assert res[0] == res[k], (k, len(txt), res[0][:80] if isinstance(res[0], str) else "arrays differ", res[k][:80] if isinstance(res[k], str) else "")
+        assert res[0] == res[1], (len(txt), res[0][:80] if isinstance(res[0], str) else "arrays differ", res[1][:80] if isinstance(res[1], str) else "")
         return res[1]
 
     idx, pats, cnt = synth.make_pat_records(2, 60_000, 200_000, mean_len=9, max_len=70)

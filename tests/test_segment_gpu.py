@@ -77,7 +77,6 @@ def test_segment_rejects_bad_beta(ctx):
         ctx.segment(b, np.arange(500, dtype=np.uint32) * 50, [(0, 500)], 100, 2000, 15)
 
 
-@pytest.mark.staged
 def test_segment_exact_wave_plan_gives_the_same_borders(ctx, oracle, monkeypatch):
     """WGBS_SEG_PLAN=exact packs waves by the real number of cost cells (seg_chunk_cells_k): many more chunks per wave, same borders"""
     K, n, nch = 4, 3000, 40
@@ -92,7 +91,6 @@ def test_segment_exact_wave_plan_gives_the_same_borders(ctx, oracle, monkeypatch
     np.testing.assert_array_equal(b[7], oracle.port_segment([x[7 * n:8 * n] for x in betas], loci[7 * n:8 * n], 1000, 2000, 15))
 
 
-@pytest.mark.staged
 @pytest.mark.parametrize("K,n,max_cpg,max_bp,ps", [(6, 2500, 200, 2000, 15), (3, 4000, 1000, 5000, 1), (1, 800, 800, 10 ** 9, 15)])
 def test_segment_redux_argmax_gives_the_same_borders(ctx, oracle, monkeypatch, K, n, max_cpg, max_bp, ps):
     """WGBS_SEG_DP=redux (argmax of a DP step by hardware warp reductions on order-preserving keys) == the shuffle version == oracle,
