@@ -214,3 +214,23 @@ def test_pat_tile_parser_core_on_the_cpu(tmp_path):
         p = tmp_path / f"c{k}.pat"; p.write_bytes(c)
         r = subprocess.run([exe, str(p)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         assert r.returncode == 0 and r.stdout.strip().endswith("mismatches 0"), (k, r.stdout, r.stderr)
+
+
+def test_bench_reference_arm_prints_the_contract_line(oracle):
+    """`bench.py --impl reference` (the reference's own executables on the host cores): ONE JSON line with the contract's keys"""
+    import subprocess
+    import sys
+    if not oracle.have_ref():
+        pytest.skip("reference executables not built")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--reads", "12000", "--steps", "1", "--warmup", "0"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "bam2pat_reads_per_sec" and d["unit"] == "reads/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1 and d["dtype"] == "u8" and d["data"] == "synthetic" and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"] and "dictionary" in d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
