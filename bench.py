@@ -168,7 +168,7 @@ def host_threads() -> int:
 # ----------------------------------------------------------------------------------------------------------------------
 # roofline bookkeeping: algorithmic bytes per launch of each hot kernel (DESIGN.md section "kernels")
 # ----------------------------------------------------------------------------------------------------------------------
-def algorithmic_bytes(kernel: str, n_rec: int, text_bytes: int, n_tmpl: int, seq_end_avg: float = 0.0):
+def algorithmic_bytes(kernel: str, n_rec: int, text_bytes: int, n_tmpl: int, seq_end_avg: float = 0.0, out_text_bytes: int = 0):
     """bytes one launch must move at minimum.  n for the sort kernels is not fixed (records when pairing,
     templates when collapsing): use the larger so the fraction is a lower bound."""
     return {
@@ -184,6 +184,14 @@ def algorithmic_bytes(kernel: str, n_rec: int, text_bytes: int, n_tmpl: int, seq
         # in place from the SAM text; 150 bp x N_CPG / CHR_LEN candidates per read)
         "pileup_call_k": int(n_rec * (44 + 32 + 32 * 150.0 * N_CPG / CHR_LEN)),
         "nl_count_k": text_bytes, "nl_write_k": text_bytes + 4 * n_rec,
+        # pairing: a 24-byte slot per table entry (2 x records rounded up to a power of two), hash words + slot index per record;
+        # the resolve step also compares the two QNAMEs of every pair (~10 bytes each, one 32-byte sector per name)
+        "slots_init_k": 24 * (1 << (2 * n_rec - 1).bit_length()),
+        "pair_insert_k": 12 * n_rec + 24 * n_rec,
+        "pair_resolve_k": 4 * n_rec + 24 * n_rec + 32 * n_rec + 4 * n_rec,
+        # mate overlay: per record idx / len / word offset in, per template idx / len / off / valid out + the pattern words of both mates
+        "merge_templates_k": 12 * n_rec + 16 * n_rec + 8 * n_rec,
+        "line_write_k": 16 * n_tmpl + 8 * n_tmpl + out_text_bytes,
     }.get(kernel)
 
 
@@ -198,6 +206,15 @@ def extras(ctx, torch, peak, sam_for_bam=b""):
     out = {}
     ev = lambda: torch.cuda.Event(enable_timing=True)
     stream = torch.cuda.current_stream()
+
+    def kernel_ms(fn, reps=2):
+        """per-kernel device time of one call of fn (the library's own profiler: an event pair around every launch)"""
+        ctx.prof(True)
+        for _ in range(reps):
+            fn()
+        rep = ctx.prof_report()
+        ctx.prof(False)
+        return {k: round(v[1] / reps, 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])[:8]}
 
     def dev_time(fn, reps=5, warm=2):
         for _ in range(warm):
@@ -224,6 +241,7 @@ def extras(ctx, torch, peak, sam_for_bam=b""):
     words = P.pool_words
     p2b_bytes = R * 16 + words * 4 + N * 8          # idx,len,count,off + symbol words + one int32 pair per site written
     out["pat2beta"] = {"records": R, "sites": N, "parse_text_ms": sec_parse * 1e3, "kernel_ms": sec_p2b * 1e3,
+                       "kernels_ms": {"parse": kernel_ms(lambda: ctx.pats_from_text(d_txt).free()), "accumulate": kernel_ms(lambda: ctx.pat2beta(P, 1, N + 1, meth_cov=mc))},
                        "sites_per_sec": N / (sec_parse + sec_p2b), "records_per_sec": R / (sec_parse + sec_p2b),
                        "roofline": {"kernel": "pat2beta_k", "bound": "hbm", "achieved": p2b_bytes / sec_p2b / 1e9, "peak": peak, "unit": "GB/s",
                                     "frac": p2b_bytes / sec_p2b / 1e9 / peak, "algorithmic_bytes": p2b_bytes}}
@@ -232,7 +250,8 @@ def extras(ctx, torch, peak, sam_for_bam=b""):
     bs = ctx.upload(np.ascontiguousarray(blocks[:, 0])); be = ctx.upload(np.ascontiguousarray(blocks[:, 1]))
     d_rng = ctx.upload(rng); d_out = ctx.alloc(blocks.shape[0] * 12)
     sec_h = dev_time(lambda: check(lib.wgbs_homog(ctx.h, P.h, bs.ptr, be.ptr, blocks.shape[0], d_rng.ptr, 3, 3, 0, d_out.ptr)))
-    out["homog"] = {"records": R, "blocks": int(blocks.shape[0]), "ms": sec_h * 1e3, "records_per_sec": R / sec_h, "sites_per_sec": N / sec_h}
+    out["homog"] = {"records": R, "blocks": int(blocks.shape[0]), "ms": sec_h * 1e3, "records_per_sec": R / sec_h, "sites_per_sec": N / sec_h,
+                    "kernels_ms": kernel_ms(lambda: check(lib.wgbs_homog(ctx.h, P.h, bs.ptr, be.ptr, blocks.shape[0], d_rng.ptr, 3, 3, 0, d_out.ptr)))}
     # reference CPU (single process, reference flags) on the same text
     if H.have_ref():
         sub = txt[: txt.index(b"\n", len(txt) // 8) + 1]          # bounded sample: first eighth of the records
@@ -287,7 +306,8 @@ def extras(ctx, torch, peak, sam_for_bam=b""):
         Pn.collapse()
         got = Pn.to_text(CHR); Pn.free()
         out["pileup_mm_ml"] = {"records": n_np, "sam_bytes": len(npsam), "ms": sec_np * 1e3, "reads_per_sec": n_np / sec_np, "nanopore_mode": int(st_np["nanopore"]),
-                               "templates": int(st_np["templates"]), "what": "tokenize + MM/ML decode + calls + collapse, inputs resident in HBM"}
+                               "templates": int(st_np["templates"]), "what": "tokenize + MM/ML decode + calls + collapse, inputs resident in HBM",
+                               "kernels_ms": kernel_ms(np_step)}
         if H.have_ref():
             sub = npsam[: npsam.index(b"\n", len(npsam) // 8) + 1]
             dp = H.write_tmp(genome().dict_text(), ".CpG.bed")
@@ -820,14 +840,14 @@ def main():
         dom, (dc, dms) = top[0]
         head = sam[:2_000_000].splitlines()[:5000]
         seq_end_avg = float(np.mean([len(b"\t".join(l.split(b"\t")[:10])) + 1 for l in head]))
-        ab = algorithmic_bytes(dom, n_rec, text_bytes, last["stats"][7], seq_end_avg)
+        ab = algorithmic_bytes(dom, n_rec, text_bytes, last["stats"][7], seq_end_avg, last["text_bytes"])
         traffic = None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.isfile(tp):
             traffic = json.load(open(tp)).get(dom)
         others = []
-        for k, (c, ms) in top[:8]:
-            b = algorithmic_bytes(k, n_rec, text_bytes, last["stats"][7], seq_end_avg)
+        for k, (c, ms) in top[:10]:
+            b = algorithmic_bytes(k, n_rec, text_bytes, last["stats"][7], seq_end_avg, last["text_bytes"])
             if b:
                 others.append({"kernel": k, "launches_per_step": c // psteps, "avg_launch_ms": ms / c, "achieved": b / (ms / c / 1e3) / 1e9,
                                "frac": b / (ms / c / 1e3) / 1e9 / peak, "share_of_step": ms / tot})
