@@ -171,6 +171,7 @@ def host_threads() -> int:
 def algorithmic_bytes(kernel: str, n_rec: int, text_bytes: int, n_tmpl: int, seq_end_avg: float = 0.0, out_text_bytes: int = 0):
     """bytes one launch must move at minimum.  n for the sort kernels is not fixed (records when pairing,
     templates when collapsing): use the larger so the fraction is a lower bound."""
+    kernel = kernel.strip("()").split("<")[0]            # the profiler reports template instances: nl_scan_k<0>, sam_lines_k<2>
     return {
         "nl_scan_k": text_bytes + 4 * n_rec,             # read the text ONCE; write one newline offset per line
         "sam_lines_k": int(seq_end_avg * n_rec) + 8 * n_rec + 49 * n_rec,   # read each line up to the end of SEQ (QUAL/tags are
@@ -844,7 +845,7 @@ def main():
         traffic = None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.isfile(tp):
-            traffic = json.load(open(tp)).get(dom)
+            traffic = json.load(open(tp)).get(dom.strip("()").split("<")[0])
         others = []
         for k, (c, ms) in top[:10]:
             b = algorithmic_bytes(k, n_rec, text_bytes, last["stats"][7], seq_end_avg, last["text_bytes"])
