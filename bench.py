@@ -196,6 +196,31 @@ def algorithmic_bytes(kernel: str, n_rec: int, text_bytes: int, n_tmpl: int, seq
     }.get(kernel)
 
 
+def build_roofline(rep: dict, psteps: int, n_rec: int, text_bytes: int, n_tmpl: int, seq_end_avg: float, out_text_bytes: int, peak: float, how: str) -> dict:
+    """the `roofline` object of the bench line from the library's per-kernel profile of `psteps` steps ({kernel: (launches, ms)}):
+    the dominant kernel = the one with the largest share of the step among those whose algorithmic bytes are defined"""
+    tot = sum(v[1] for v in rep.values())
+    top = sorted(rep.items(), key=lambda kv: -kv[1][1])
+    per = []
+    for k, (c, ms) in top[:10]:
+        b = algorithmic_bytes(k, n_rec, text_bytes, n_tmpl, seq_end_avg, out_text_bytes)
+        if b:
+            per.append({"kernel": k, "launches_per_step": c // psteps, "avg_launch_ms": ms / c, "achieved": b / (ms / c / 1e3) / 1e9,
+                        "frac": b / (ms / c / 1e3) / 1e9 / peak, "share_of_step": ms / tot, "algorithmic_bytes_per_launch": b})
+    breakdown = {k: round(v[1] / psteps, 4) for k, v in top[:10]}
+    if not per:
+        return {"bound": "hbm", "kernel": top[0][0] if top else None, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
+                "peak_source": how, "breakdown_ms_per_step": breakdown}
+    d = per[0]
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.isfile(tp):
+        traffic = json.load(open(tp)).get(d["kernel"].strip("()").split("<")[0])
+    return {"bound": "hbm", "kernel": d["kernel"], "achieved": d["achieved"], "peak": peak, "unit": "GB/s", "frac": d["frac"], "traffic": traffic,
+            "peak_source": how, "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"], "avg_launch_ms": d["avg_launch_ms"],
+            "share_of_step": d["share_of_step"], "per_kernel": per, "breakdown_ms_per_step": breakdown}
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # the other hot-path steps (BASELINE.json metric: "pat2beta CpG-sites/sec", homog, segment) -- reported under "extra"
 # ----------------------------------------------------------------------------------------------------------------------
@@ -838,29 +863,9 @@ def main():
             peak, how = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, how = 6650.0, "fallback (B200_PROFILING.md)"
-        dom, (dc, dms) = top[0]
         head = sam[:2_000_000].splitlines()[:5000]
         seq_end_avg = float(np.mean([len(b"\t".join(l.split(b"\t")[:10])) + 1 for l in head]))
-        ab = algorithmic_bytes(dom, n_rec, text_bytes, last["stats"][7], seq_end_avg, last["text_bytes"])
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.isfile(tp):
-            traffic = json.load(open(tp)).get(dom.strip("()").split("<")[0])
-        others = []
-        for k, (c, ms) in top[:10]:
-            b = algorithmic_bytes(k, n_rec, text_bytes, last["stats"][7], seq_end_avg, last["text_bytes"])
-            if b:
-                others.append({"kernel": k, "launches_per_step": c // psteps, "avg_launch_ms": ms / c, "achieved": b / (ms / c / 1e3) / 1e9,
-                               "frac": b / (ms / c / 1e3) / 1e9 / peak, "share_of_step": ms / tot})
-        if ab:
-            ach = ab / (dms / dc / 1e3) / 1e9
-            roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                    "peak_source": how, "algorithmic_bytes_per_launch": ab, "avg_launch_ms": dms / dc,
-                    "share_of_step": dms / tot, "per_kernel": others,
-                    "breakdown_ms_per_step": {k: round(v[1] / psteps, 4) for k, v in top[:10]}}
-        else:
-            roof = {"bound": "hbm", "kernel": dom, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": traffic,
-                    "peak_source": how, "breakdown_ms_per_step": {k: round(v[1] / psteps, 4) for k, v in top[:10]}}
+        roof = build_roofline(rep, psteps, n_rec, text_bytes, last["stats"][7], seq_end_avg, last["text_bytes"], peak, how)
 
     cpu = None
     if rank == 0 and args.gpus == 1:

@@ -234,3 +234,24 @@ def test_bench_reference_arm_prints_the_contract_line(oracle):
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"] and "dictionary" in d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+def test_bench_roofline_object_from_a_profile():
+    """bench.build_roofline: kernel names come from the library's profiler WITH template arguments (nl_scan_k<0>, sam_lines_k<2>); the
+    dominant kernel is the largest share of the step among those with defined algorithmic bytes"""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    rep = {"nl_scan_k<0>": (3, 0.388), "sam_lines_k<2>": (3, 0.336), "rs_onesweep_k": (12, 0.299), "pileup_call_k": (3, 0.283), "scan_lookback_k<OutT>": (12, 0.172),
+           "merge_templates_k": (3, 0.188), "pileup_measure_k": (3, 0.182), "pair_resolve_k": (3, 0.167), "line_write_k": (3, 0.163), "pat2beta_k": (3, 0.1), "tiny_k": (3, 0.01)}
+    r = bench.build_roofline(rep, 3, 994_890, 356_666_308, 494_264, 181.0, 10_200_000, 6554.9, "measured")
+    assert r["kernel"] == "nl_scan_k<0>" and r["bound"] == "hbm" and r["unit"] == "GB/s"
+    assert abs(r["achieved"] - (356_666_308 + 4 * 994_890) / (0.388 / 3 / 1e3) / 1e9) < 1e-6 and abs(r["frac"] - r["achieved"] / 6554.9) < 1e-12
+    assert r["traffic"] == 362886144                                        # profiles/ncu_traffic.json, keyed by the bare kernel name
+    names = [k["kernel"] for k in r["per_kernel"]]
+    assert "sam_lines_k<2>" in names and "merge_templates_k" in names and "scan_lookback_k<OutT>" not in names
+    assert abs(sum(k["share_of_step"] for k in r["per_kernel"]) - (sum(v[1] for k, v in rep.items() if k in names) / sum(v[1] for v in rep.values()))) < 1e-9
+    # a profile whose top kernel has no byte model: the next one with a model is reported
+    r2 = bench.build_roofline({"mystery_k": (3, 9.0), **rep}, 3, 994_890, 356_666_308, 494_264, 181.0, 10_200_000, 6554.9, "measured")
+    assert r2["kernel"] == "nl_scan_k<0>" and list(r2["breakdown_ms_per_step"])[0] == "mystery_k"
