@@ -198,6 +198,15 @@ static int cmd_view(const char *path, uint64_t SEG, int depth, int argc, char **
         max_rec = strtoull(argv[10], nullptr, 10);
         if (argc >= 13) { V.key_beg = atoll(argv[11]); V.key_end = atoll(argv[12]); }     // template window (wgbs_view_opts.key_beg / key_end)
     }
+    if (argc >= 15 && !strcmp(argv[13], "firstkey")) {
+        // bam_first_key_k (bamdev.cu): the first record of reference V.refid that passes the filters (key window ignored) with
+        // template key >= KEY; prints its offset, or -1
+        const long long key = atoll(argv[14]); ViewParams W = V; W.key_beg = 0; W.key_end = 0;
+        long long best = -1;
+        for (uint64_t o : rec) { Rec R; R.load(d.data() + o); if (template_key((int32_t)R.flag, R.refid, R.pos, R.nref, R.npos) >= key && passes(R, W)) { best = (long long)o; break; } }
+        printf("%lld\n", best);
+        return 0;
+    }
     std::string out;
     for (uint64_t o : rec) {
         Rec R; R.load(d.data() + o);

@@ -233,3 +233,21 @@ def test_part_record_table_equals_the_host_part_reader(check, sam, tmp_path, bui
                 assert r.stdout == exp, (b0, n, seg)
                 assert r.stderr.decode().strip().endswith(f"nrec {host.nrecords()} tail {host.tail}"), (r.stderr.decode(), host.tail)
             host.close()
+
+
+def test_first_key_core_equals_the_host_reader(check, sam, tmp_path, built_lib):
+    """bam_first_key_k's logic (shared record code: template_key + passes) == wgbs_bam_first_key of the host reader"""
+    from wgbs_tools_b200 import bamio
+    g, s = sam
+    p = tmp_path / "k.bam"
+    p.write_bytes(bamio.sam_to_bam(s, [("chrT", g.length)]))
+    part = bamio.BamPart(p.read_bytes(), threads=2)
+    for kw in (dict(), dict(mapq=10, exclude_flags=1796, include_flags=3), dict(flag_eq=(99, 147))):
+        for key in (0, 1000, 150_000, 299_000, 10**9):
+            exp = part.first_key(0, key, **kw)
+            argv = ["0", str(kw.get("mapq", 0)), str(kw.get("exclude_flags", 0)), str(kw.get("include_flags", 0)), "0", "0",
+                    ",".join(map(str, kw["flag_eq"])) if kw.get("flag_eq") else "-", "-", "-", "0", "0", "0", "0", "firstkey", str(key)]
+            r = subprocess.run([check, "view", str(p), "16384", "4"] + argv, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+            assert r.returncode == 0, r.stderr.decode()
+            assert int(r.stdout.decode().strip()) == (-1 if exp is None else exp), (kw, key)
+    part.close()
