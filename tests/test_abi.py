@@ -63,3 +63,34 @@ def test_product_never_touches_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not bad.search(txt), f"{f} reaches into oracle/"
+
+
+def test_bindings_and_library_agree_on_the_abi_version():
+    """a stale libwgbs_b200.so (older struct layouts) must not load silently"""
+    import re
+    from wgbs_tools_b200 import _lib
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "wgbs_b200.h")).read()
+    v = int(re.search(r"#define\s+WGBS_B200_ABI_VERSION\s+(\d+)", hdr).group(1))
+    assert v == _lib.ABI_VERSION == _lib.lib.wgbs_abi_version()
+
+
+def test_ctypes_structs_have_the_layout_of_the_header(tmp_path):
+    """ViewOpts / PileupOpts (wgbs_tools_b200/_lib.py) field by field against offsetof() in include/wgbs_b200.h (gcc)"""
+    import ctypes as C
+    from wgbs_tools_b200._lib import PileupOpts, ViewOpts
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    prog = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{root}/include/wgbs_b200.h"', 'int main(void) {']
+    for cname, T in (("wgbs_view_opts", ViewOpts), ("wgbs_pileup_opts", PileupOpts)):
+        prog.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for f, _ in T._fields_:
+            prog.append(f'printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    prog += ['return 0; }']
+    src = tmp_path / "layout.c"; src.write_text("\n".join(prog))
+    exe = str(tmp_path / "layout")
+    r = subprocess.run(["gcc", str(src), "-o", exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    got = dict(l.split() for l in subprocess.run([exe], stdout=subprocess.PIPE, text=True).stdout.splitlines())
+    for cname, T in (("wgbs_view_opts", ViewOpts), ("wgbs_pileup_opts", PileupOpts)):
+        assert int(got[cname]) == C.sizeof(T), cname
+        for f, _ in T._fields_:
+            assert int(got[f"{cname}.{f}"]) == getattr(T, f).offset, (cname, f)

@@ -109,6 +109,10 @@ def _load():
 
 
 lib, SIGNATURES = _load()
+ABI_VERSION = 5          # WGBS_B200_ABI_VERSION of include/wgbs_b200.h these bindings mirror (struct layouts, signatures)
+if lib.wgbs_abi_version() != ABI_VERSION:
+    raise ImportError(f"{LIB_PATH} has ABI version {lib.wgbs_abi_version()}, these bindings expect {ABI_VERSION}: rebuild it "
+                      "(python -m wgbs_tools_b200.build -f)")
 
 
 def check(rc: int) -> None:
