@@ -411,26 +411,3 @@ def test_device_parts_equal_host_parts_and_streamed_cli(ctx, bamio, tmp_path, mo
         bam2pat.main([str(bam), "--genome", str(refdir), "-o", str(out), "--bam_decode", decode])
         outs.append((gzip.decompress((out / "s.pat.gz").read_bytes()), (out / "s.beta").read_bytes()))
     assert outs[0] == outs[1] == outs[2] and len(outs[0][0]) > 1000
-
-
-def test_pat_files_larger_than_one_call_go_piece_by_piece(ctx, tmp_path, monkeypatch):
-    """pat2beta / homog on a pat text cut into pieces at line ends (WGBS_PAT_CHUNK_BYTES; a 30x pat file exceeds the 4 GiB one call
-    takes): same .beta / same U-X-M table as in one call, for host text and for text inflated on the device"""
-    from wgbs_tools_b200 import homog as hg
-    from wgbs_tools_b200 import pat2beta as p2b
-    from wgbs_tools_b200.patio import bgzf_compress
-    N = 60_000
-    txt = synth.make_pat_text_fast(5, 50_000, N, chrom="chr1")
-    pg = tmp_path / "x.pat.gz"; pg.write_bytes(bgzf_compress(txt))
-    blocks = synth.make_blocks(5, 1, N)
-    bed = tmp_path / "b.bed"; bed.write_bytes(synth.blocks_text("chr1", blocks))
-    out = {}
-    for limit in ("0", "70000"):
-        if limit != "0":
-            monkeypatch.setenv("WGBS_PAT_CHUNK_BYTES", limit)
-        for decode in ("host", "device"):
-            d = tmp_path / f"o_{limit}_{decode}"; d.mkdir()
-            p2b.pat2beta(ctx, str(pg), str(d), N, decode=decode)
-            hg.main([str(pg), "-b", str(bed), "-o", str(d), "--pat_decode", decode])
-            out[(limit, decode)] = ((d / "x.beta").read_bytes(), gzip.decompress((d / "x.uxm.bed.gz").read_bytes()))
-    assert len(set(out.values())) == 1 and any(out[("0", "host")][0])
