@@ -79,6 +79,7 @@ class PortContext:
     def pileup_sam(self, ix, sam, min_cpg=1, clip=0, paired=-1, nanopore=False, np_thresh=0.67, cpc_call="C", combine_mods=False,
                    mbias=False, keep_names=False, nbytes=None):
         H = self.H
+        sam = bytes(sam)                                     # (the host BAM reader hands over a uint8 array, not bytes)
         first = next((l for l in sam.splitlines() if l), b"")
         pe = bool(int(first.split(b"\t")[1]) & 1) if paired < 0 else bool(paired)
         # the port's patter prints `chr idx pattern`; --long adds the read name (patter --long): the port has no such switch, so

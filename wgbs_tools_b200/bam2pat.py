@@ -91,7 +91,7 @@ class ChromPile:
     def add(self, s):
         """s: SAM text (bytes), or a callable(index, **pileup options) -> (Pats | None, stats) that views and piles up on the
         device (device-decoded .bam: wgbs_pileup_dbam)"""
-        if not callable(s) and not s:
+        if not callable(s) and len(s) == 0:
             return
         args = self.args
         P, st_w = s(self.ix, **self.kw) if callable(s) else self.ctx.pileup_sam(self.ix, s, **self.kw)
@@ -221,7 +221,7 @@ class _Source:
                     return b""
                 if self.on_device:
                     return lambda ix, **kw: self.bam.pileup(ix, chrom, view=dict(beg=beg, end=end, key_window=window, **view_kw), **kw)
-                return self.bam.view(chrom, beg=beg, end=end, key_window=window, **view_kw)
+                return self.bam.view(chrom, beg=beg, end=end, key_window=window, as_array=True, **view_kw)
             return filter_sam(self.sam.get(chrom, b""), chrom=chrom, beg=beg, end=end, key_window=window, **view_kw)
         return get
 
@@ -453,7 +453,7 @@ def main(argv=None):
                     if on_dev:
                         piles[chrom].add(lambda ix, _p=part, _c=chrom, _v=vkw, **kw: _p.pileup(ix, _c, view=_v, **kw))
                     else:
-                        piles[chrom].add(part.view(chrom, **vkw))
+                        piles[chrom].add(part.view(chrom, as_array=True, **vkw))
                     if done:
                         finished.add(chrom)
                         mb_total = close_pile(chrom, mb_total)

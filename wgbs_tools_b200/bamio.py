@@ -8,6 +8,8 @@ import ctypes as C
 import re
 import struct
 
+import weakref
+
 import numpy as np
 
 from ._lib import ViewOpts, check, lib
@@ -57,15 +59,25 @@ class BamFile:
     def nrecords(self, chrom: str | None = None) -> int:
         return int(lib.wgbs_bam_nrecords(self.h, -1 if chrom is None else self.refs.index(chrom)))
 
-    def view(self, chrom: str | None = None, **kw) -> bytes:
-        """`samtools view BAM chrom[:beg-end] -q mapq -F exclude_flags [-f include_flags] [-r read_group]`, optionally
+    def view(self, chrom: str | None = None, **kw):
+        """(as_array=True: the text as a numpy uint8 array over the library's buffer instead of a bytes copy)
+        `samtools view BAM chrom[:beg-end] -q mapq -F exclude_flags [-f include_flags] [-r read_group]`, optionally
         `| awk '$2 == flag_eq[0] || ...'`, `-M -L bed` (intervals = (starts, ends) 0-based half-open, sorted, merged) or
         `bedtools intersect -v` (exclude_intervals), `| head -max_records`."""
+        as_array = kw.pop("as_array", False)
         vo, keep = view_opts(self.refs, chrom, **kw)
         if vo is None:
-            return b""
+            return np.zeros(0, np.uint8) if as_array else b""
         ptr = C.c_void_p(); n = C.c_size_t(); nr = C.c_uint64()
         check(lib.wgbs_bam_view_ex(self.h, C.byref(vo), C.byref(ptr), C.byref(n), C.byref(nr)))
+        if as_array:
+            # the library's own buffer as a uint8 array, released when the array is: no copy of gigabytes of text on one thread
+            if not n.value:
+                lib.wgbs_host_free(ptr)
+                return np.zeros(0, np.uint8)
+            a = np.ctypeslib.as_array((C.c_uint8 * n.value).from_address(ptr.value))
+            weakref.finalize(a, lib.wgbs_host_free, ptr.value)
+            return a
         try:
             return C.string_at(ptr, n.value)
         finally:
