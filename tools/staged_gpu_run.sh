@@ -1,14 +1,14 @@
 #!/bin/bash
 # First GPU call of the next round: run everything that was written without GPU access (see DESIGN.md "Staged"), each piece
 # under its own time limit so that a hang costs one limit, not the call.  Usage (from the repo root):
-#   gpurun --timeout 900 -- 'bash tools/staged_gpu_run.sh'
+#   gpurun --timeout 2400 -- 'bash tools/staged_gpu_run.sh'
 # Results land in gpurun_out/staged_*.log; the bench line (with every staged child leg) in gpurun_out/staged_bench.json.
 set -u
 mkdir -p gpurun_out
 export WGBS_STAGED=1
 run() { local name=$1 limit=$2; shift 2; echo "== $name"; timeout "$limit" "$@" > "gpurun_out/staged_$name.log" 2>&1; echo "   rc=$? $(tail -1 "gpurun_out/staged_$name.log")"; }
 # 1. the verified suite first (must stay green), then each staged test on its own
-run suite 600 python -m pytest tests -m gpu -x -q -k "not staged" -p no:cacheprovider
+run suite 1500 python -m pytest tests -m gpu -x -q -k "not staged" -p no:cacheprovider
 run inflate_teams 120 python -m pytest tests/test_zz_bamdev_gpu.py -m gpu -q -k "team_kernels"
 run pat_tiles 120 python -m pytest tests/test_pat_gpu.py -m gpu -q -k "tile_parser"
 run seg_plan 120 python -m pytest tests/test_segment_gpu.py -m gpu -q -k "exact_wave_plan or redux_argmax"
