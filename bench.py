@@ -655,6 +655,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=1_000_000)
+    ap.add_argument("--streams", type=int, default=1, help="batches in flight per GPU in the device-resident leg: S Contexts (own stream each) on S host "
+                                                             "threads, the way bam2pat keeps several chromosomes in flight [1]")
     ap.add_argument("--no-extras", dest="no_extras", action="store_true", help="skip the pat2beta / homog / segment side measurements")
     ap.add_argument("--only-bam-extra", dest="only_bam", action="store_true", help="of the side measurements run only the device-BAM leg")
     ap.add_argument("--bam-leg", dest="bam_leg", help=argparse.SUPPRESS)       # internal: child process of the device-BAM leg
@@ -676,6 +678,8 @@ def main():
     config = {"workload": workload, "records_per_gpu": args.reads, "read_len": 150, "paired": True, "n_cpg": N_CPG,
               "sharding": "reads (one batch per GPU), beta counts NCCL-reduced" if args.gpus > 1 else "single GPU",
               "l2": "inputs larger than L2 (SAM batch ~345 MB > 126 MB)"}
+    if args.streams > 1:
+        config["batches_in_flight"] = args.streams
 
     # ------------------------------------------------------------------------------------------------------------------
     if args.impl == "reference":
@@ -781,6 +785,47 @@ def main():
         last.update(text_bytes=n.value, stats=[int(x) for x in st])
         lib.wgbs_pats_free(ctx.h, h)
 
+    # --streams S: S - 1 more Contexts on their own streams; every worker runs whole device-resident steps (own outputs)
+    workers = []
+    for _ in range(max(args.streams, 1) - 1):
+        st_w = torch.cuda.Stream()
+        workers.append(dict(stream=st_w, ctx=Context(local, stream=st_w.cuda_stream), mc=torch.zeros_like(mc), text=torch.empty_like(d_text), beta=torch.empty_like(d_beta)))
+
+    def worker_steps(w: dict, k: int, errs: list):
+        try:
+            torch.cuda.set_device(local)
+            for _ in range(k):
+                o = PileupOpts(1, 0, -1, 0, 0, 0.67, b"C")
+                h = C.c_void_p(); st = (C.c_uint64 * 8)()
+                check(lib.wgbs_pileup_sam(w["ctx"].h, ix.h, d_sam.data_ptr(), text_bytes, C.addressof(o), C.byref(h), C.addressof(st)))
+                check(lib.wgbs_pat2beta(w["ctx"].h, h, start, end, w["mc"].data_ptr(), 1))
+                check(lib.wgbs_collapse(w["ctx"].h, h))
+                n = C.c_size_t()
+                check(lib.wgbs_pats_format(w["ctx"].h, h, CHR.encode(), w["text"].data_ptr(), w["text"].numel(), C.byref(n)))
+                check(lib.wgbs_trim(w["ctx"].h, w["mc"].data_ptr(), g.n_cpg, 8, w["beta"].data_ptr()))
+                lib.wgbs_pats_free(w["ctx"].h, h)
+        except Exception as e:
+            errs.append(repr(e))
+
+    def run_device_steps(k: int):
+        """k device-resident steps: on the main Context alone, or shared out over the main Context and the workers (single-GPU runs)"""
+        if not workers or world > 1:
+            for _ in range(k):
+                run_step(False)
+            return
+        S = len(workers) + 1
+        share = [k // S + (1 if i < k % S else 0) for i in range(S)]
+        errs: list = []
+        th = [threading.Thread(target=worker_steps, args=(w, share[i + 1], errs)) for i, w in enumerate(workers)]
+        for t in th:
+            t.start()
+        for _ in range(share[0]):
+            run_step(False)
+        for t in th:
+            t.join()
+        if errs:
+            raise SystemExit(f"worker stream failed: {errs[0]}")
+
     d_in = [torch.empty_like(d_sam), torch.empty_like(d_sam)]     # double-buffered device copies of the streamed input
 
     def run_stream(k: int):
@@ -796,6 +841,8 @@ def main():
     def timed(host: bool, steps: int, warmup: int, streamed: bool = False):
         if streamed:
             run_stream(warmup)
+        elif not host:
+            run_device_steps(warmup * (len(workers) + 1))
         else:
             for _ in range(warmup):
                 run_step(host)
@@ -803,14 +850,21 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        l0 = ctx.launches
+        all_launches = lambda: ctx.launches + sum(w["ctx"].launches for w in workers)
+        l0 = all_launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        for w in workers:                                    # (no workers unless --streams > 1)
+            w["stream"].wait_event(e0)
         if streamed:
             run_stream(steps)
+        elif not host:
+            run_device_steps(steps)
         else:
             for _ in range(steps):
                 run_step(host)
+        for w in workers:
+            ev = torch.cuda.Event(); ev.record(w["stream"]); stream.wait_event(ev)
         e1.record(stream)
         torch.cuda.synchronize()
         if world > 1:
@@ -820,7 +874,7 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), ctx.launches - l0
+        return float(t.item()), all_launches() - l0
 
     # nvidia-smi samples every 100 ms; one timed region lasts tens of ms, so the sampler spans both (warm-ups included:
     # the GPU is under the same load throughout)

@@ -18,6 +18,10 @@ for v in batch8 batch16 tma; do
   WGBS_NLSCAN=$v run nlscan_${v}_tests 300 python -m pytest tests/test_pileup_gpu.py -m gpu -x -q
   WGBS_NLSCAN=$v timeout 300 python bench.py --steps 10 --warmup 3 --no-extras > gpurun_out/staged_bench_nlscan_$v.json 2> gpurun_out/staged_bench_nlscan_$v.err; echo "   bench nlscan=$v rc=$?"
 done
+# the official-format line with 2 and 3 batches in flight on the device-resident leg
+for n in 2 3; do
+  timeout 300 python bench.py --steps 12 --warmup 3 --no-extras --streams $n > gpurun_out/staged_bench_streams_$n.json 2> gpurun_out/staged_bench_streams_$n.err; echo "   bench streams=$n rc=$?"
+done
 # 2. the bench with all child legs (direct route, team decoders, batches in flight, segment at scale, pat parsers)
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/staged_bench.json 2> gpurun_out/staged_bench.err; echo "bench rc=$?"
 python - <<'P'
