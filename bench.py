@@ -502,7 +502,7 @@ def bam_device_leg(tmp: str, n_rec: int, sam_bytes: int, peak: float, configs: s
 def stream_leg(tmp: str, n_rec: int, steps=12, warmup=3):
     """(child process of the bench) The device-resident step of the main line, with S batches in flight on S streams: one
     Context (own stream, own scratch) per host thread -- chromosomes are independent units of work, so several can be in flight on
-    one GPU (the bam2pat CLI itself still walks them one after the other: a round-2 item if this leg pays).  A single
+    one GPU (`bam2pat --gpu_streams S` does the same in the CLI).  A single
     stream leaves the GPU idle while the host reads back sizes between kernels (~10 round trips per step) and runs kernels of
     one wave or less back to back; a second stream fills those gaps.  S = 1 repeats the main line's `value` as the control.
     Timed on the device: a start event every worker stream waits for, an end event that waits for every worker stream."""
@@ -657,7 +657,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=1_000_000)
     ap.add_argument("--streams", type=int, default=1, help="batches in flight per GPU in the device-resident leg: S Contexts (own stream each) on S host "
-                                                             "threads (chromosomes are independent units of work; the bam2pat CLI still walks them one by one) [1]")
+                                                             "threads (chromosomes are independent units of work: bam2pat --gpu_streams) [1]")
     ap.add_argument("--no-extras", dest="no_extras", action="store_true", help="skip the pat2beta / homog / segment side measurements")
     ap.add_argument("--only-bam-extra", dest="only_bam", action="store_true", help="of the side measurements run only the device-BAM leg")
     ap.add_argument("--bam-leg", dest="bam_leg", help=argparse.SUPPRESS)       # internal: child process of the device-BAM leg

@@ -5,11 +5,15 @@ piling a chromosome up in template windows (wgbs_view_opts.key_beg / key_end) ch
 for the host BAM reader, with region / strand filters, --long and --mbias-free runs."""
 import gzip
 import os
+import threading
 
 import numpy as np
 import pytest
 
 from wgbs_tools_b200 import synth
+
+
+_LOCK = threading.Lock()
 
 
 class _Buf:
@@ -66,6 +70,9 @@ class PortContext:
     def sync(self):
         pass
 
+    def close(self):
+        pass
+
     def alloc(self, n):
         return _Buf(n)
 
@@ -104,9 +111,10 @@ class PortContext:
         mc = self.H.port_pat2beta(P.with_counts(), start, end) if P.lines else np.zeros((end - start, 2), np.int32)
         if meth_cov is None:
             meth_cov = _Buf((end - start) * 8)
-        if zero_first:
-            meth_cov.a[:] = 0
-        meth_cov.a += mc.reshape(-1)
+        with _LOCK:                                         # (the device adds atomically; numpy does not)
+            if zero_first:
+                meth_cov.a[:] = 0
+            meth_cov.a += mc.reshape(-1)
         return meth_cov
 
     def trim(self, mc, n, nbits=8):
@@ -191,3 +199,14 @@ def test_pat2beta_cli_on_a_pat_larger_than_one_call(tmp_path, oracle, monkeypatc
         p2b.pat2beta(PortContext(), str(pg), str(d), N, decode="host")
         outs.append((d / "x.beta").read_bytes())
     assert outs[0] == outs[1] == outs[2] == oracle.port_trim(oracle.port_pat2beta(txt, 1, N + 1)).tobytes()
+
+
+@pytest.mark.parametrize("inp", ["s.sam", "s.bam"])
+def test_chromosomes_in_flight_give_the_same_outputs(world, monkeypatch, inp):
+    """--gpu_streams 2: two chromosomes at a time, each on its own Context / host thread, counts added into the one beta array"""
+    tmp, refdir = world
+    monkeypatch.setenv("WGBS_CHUNK_RECORDS", "0"); monkeypatch.setenv("WGBS_CHUNK_BYTES", "0")
+    one = _run(tmp, refdir, inp, "one")
+    assert _run(tmp, refdir, inp, "two", ("--gpu_streams", "2")) == one
+    monkeypatch.setenv("WGBS_CHUNK_RECORDS", "1500"); monkeypatch.setenv("WGBS_CHUNK_BYTES", "500000")
+    assert _run(tmp, refdir, inp, "two_windows", ("--gpu_streams", "2", "-v")) == one

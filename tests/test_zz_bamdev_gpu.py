@@ -411,3 +411,28 @@ def test_device_parts_equal_host_parts_and_streamed_cli(ctx, bamio, tmp_path, mo
         bam2pat.main([str(bam), "--genome", str(refdir), "-o", str(out), "--bam_decode", decode])
         outs.append((gzip.decompress((out / "s.pat.gz").read_bytes()), (out / "s.beta").read_bytes()))
     assert outs[0] == outs[1] == outs[2] and len(outs[0][0]) > 1000
+
+
+@pytest.mark.staged
+@pytest.mark.parametrize("decode", ["host", "device"])
+def test_bam2pat_cli_chromosomes_in_flight(ctx, bamio, tmp_path, monkeypatch, decode):
+    """--gpu_streams 2: two chromosomes at a time, each on its own Context (stream) and host thread, all adding into the one
+    device beta array; a device-decoded file is shared by the Contexts.  Same files as one chromosome after the other."""
+    from wgbs_tools_b200 import bam2pat
+    gs = [synth.make_genome(31 + k, f"chr{k + 1}", 250_000, first_idx=1) for k in range(3)]
+    first = 1
+    for g in gs:
+        g.first_idx = first; first += g.n_cpg
+    refdir = tmp_path / "ref"; refdir.mkdir()
+    with gzip.open(refdir / "CpG.bed.gz", "wb") as f:
+        f.write(b"".join(g.dict_text() for g in gs))
+    (refdir / "CpG.chrome.size").write_text("".join(f"{g.chrom}\t{g.n_cpg}\n" for g in gs)); (refdir / "chrome.size").write_text("".join(f"{g.chrom}\t{g.length}\n" for g in gs))
+    sam = b"".join(synth.make_sam(g, 6_000, 4 + k, paired=True, name_prefix=f"c{k}_") for k, g in enumerate(gs))
+    bam = tmp_path / "s.bam"; bam.write_bytes(bamio.sam_to_bam(sam, [(g.chrom, g.length) for g in gs]))
+    outs = []
+    for tag, extra in (("one", []), ("two", ["--gpu_streams", "2"]), ("three", ["--gpu_streams", "3", "--mbias"])):
+        out = tmp_path / tag; out.mkdir()
+        bam2pat.main([str(bam), "--genome", str(refdir), "-o", str(out), "--bam_decode", decode] + extra)
+        outs.append((gzip.decompress((out / "s.pat.gz").read_bytes()), (out / "s.beta").read_bytes()))
+    assert outs[0] == outs[1] == outs[2] and len(outs[0][0]) > 3000
+

@@ -13,6 +13,7 @@ run inflate_teams 120 python -m pytest tests/test_zz_bamdev_gpu.py -m gpu -q -k 
 run pat_tiles 120 python -m pytest tests/test_pat_gpu.py -m gpu -q -k "tile_parser"
 run seg_plan 120 python -m pytest tests/test_segment_gpu.py -m gpu -q -k "exact_wave_plan or redux_argmax"
 run dev_parts 180 python -m pytest tests/test_zz_bamdev_gpu.py -m gpu -q -k "device_parts"
+run cli_streams 180 python -m pytest tests/test_zz_bamdev_gpu.py -m gpu -q -k "chromosomes_in_flight"
 # newline-scan variants (the env var is read once per process: whole test files per variant, then a short bench for the kernel time)
 for v in batch8 batch16 tma; do
   WGBS_NLSCAN=$v run nlscan_${v}_tests 300 python -m pytest tests/test_pileup_gpu.py -m gpu -x -q

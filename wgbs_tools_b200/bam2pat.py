@@ -220,7 +220,7 @@ class _Source:
                 if chrom not in self.bam.refs:
                     return b""
                 if self.on_device:
-                    return lambda ix, **kw: self.bam.pileup(ix, chrom, view=dict(beg=beg, end=end, key_window=window, **view_kw), **kw)
+                    return lambda ix, **kw: self.bam.pileup(ix, chrom, view=dict(beg=beg, end=end, key_window=window, **view_kw), ctx=ix.ctx, **kw)
                 return self.bam.view(chrom, beg=beg, end=end, key_window=window, as_array=True, **view_kw)
             return filter_sam(self.sam.get(chrom, b""), chrom=chrom, beg=beg, end=end, key_window=window, **view_kw)
         return get
@@ -312,6 +312,7 @@ def add_args(p):
     p.add_argument("--long", action="store_true", help="Use long format for pat file (add read name to each line)")
     p.add_argument("-@", "--threads", type=int, default=default_threads(),
                    help="host threads for BGZF inflate/deflate (default: all available CPUs, capped at 64; utils_wgbs.py:250-260)")
+    p.add_argument("--gpu_streams", type=int, default=1, help="chromosomes in flight on the GPU (one Context / stream / host thread each) [1]")
     p.add_argument("--bam_decode", choices=["auto", "host", "device", "stream"], default=os.environ.get("WGBS_BAM_DECODE", "auto"),
                    help="where the .bam is decoded: on the GPU (compressed bytes over PCIe, one warp per BGZF block), on host threads (zlib), "
                         "auto = GPU unless the inflated file does not fit in device memory, or stream = read the file as a sequence of "
@@ -460,30 +461,51 @@ def main(argv=None):
                 for chrom in list(piles):                                      # (a chromosome is always closed by its last part; belt and braces)
                     mb_total = close_pile(chrom, mb_total)
                 regions = []                                                   # all done above
-            for ri, region in enumerate(regions):
-                if ri not in mine:
-                    continue
+            def do_region(cx, ri: int, region: str):
+                """one chromosome / region on Context cx: (ri, compressed part | None, stats | None)"""
                 chrom = region.split(":")[0]
-                kw = dict(mapq=mapq, exclude_flags=ex, include_flags=inc, read_group=a.read_group)
-                if lists is not None:
-                    kw.update(intervals=lists[0].get(chrom, empty_iv), exclude_intervals=lists[1])
-                txt = None
-                if feq is not None:
-                    # a chromosome too large for one call (< 4 GiB of SAM text / BAM stream) is piled up in template windows
-                    _, rb, re_ = parse_region_str(extend_region(region)) if ":" in region else (chrom, 0, 0)
-                    limit = int(os.environ.get("WGBS_CHUNK_RECORDS", 6_000_000)) if src.bam is not None else int(os.environ.get("WGBS_CHUNK_BYTES", 2 << 30))
-                    wins = template_windows(src.weight(chrom), limit, max(rb - 1, 0) if re_ > 0 else 0, re_ if re_ > 0 else ref.chrom_length(chrom))
-                    if wins and a.verbose:
-                        print(f"[wt bam2pat] {region}: {len(wins)} template windows", file=sys.stderr)
-                    txt, st = proc_chr(ctx, ref, region, src.getter(region, flag_eq=feq, **kw), run, mc, wins)
+                if feq is None:
+                    return ri, None, None
+                # a chromosome too large for one call (< 4 GiB of SAM text / BAM stream) is piled up in template windows
+                _, rb, re_ = parse_region_str(extend_region(region)) if ":" in region else (chrom, 0, 0)
+                limit = int(os.environ.get("WGBS_CHUNK_RECORDS", 6_000_000)) if src.bam is not None else int(os.environ.get("WGBS_CHUNK_BYTES", 2 << 30))
+                wins = template_windows(src.weight(chrom), limit, max(rb - 1, 0) if re_ > 0 else 0, re_ if re_ > 0 else ref.chrom_length(chrom))
+                if wins and a.verbose:
+                    print(f"[wt bam2pat] {region}: {len(wins)} template windows", file=sys.stderr)
+                txt, st = proc_chr(cx, ref, region, src.getter(region, flag_eq=feq, **view_kw(chrom)), run, mc, wins)
                 if txt is None:
+                    return ri, None, None
+                return ri, (bgzf_compress(txt, a.threads) if txt else None), st
+
+            todo = [(ri, region) for ri, region in enumerate(regions) if ri in mine]
+            S = max(1, min(int(os.environ.get("WGBS_GPU_STREAMS", a.gpu_streams)), len(todo) or 1))
+            if S == 1:
+                results = (do_region(ctx, ri, region) for ri, region in todo)
+            else:
+                # S chromosomes in flight on this GPU: one Context (own stream, own scratch) per worker thread, like the reference's
+                # pool of chromosome workers (bam2pat.py:343); the beta counts of all of them add into the one device array
+                import threading
+                from concurrent.futures import ThreadPoolExecutor
+                ctx.sync()                                                      # the zeroed counters are there before any worker adds to them
+                tls = threading.local(); made = []
+
+                def on_worker(item):
+                    if not hasattr(tls, "ctx"):
+                        tls.ctx = Context(local); made.append(tls.ctx)
+                    return do_region(tls.ctx, *item)
+                with ThreadPoolExecutor(S) as pool:
+                    results = list(pool.map(on_worker, todo))
+                for c in made:
+                    c.sync(); c.close()
+            for ri, part, st in results:
+                if st is None:
                     if a.verbose:
-                        print(f"[wt bam2pat] Skipping region {region}, no reads found", file=sys.stderr)
+                        print(f"[wt bam2pat] Skipping region {regions[ri]}, no reads found", file=sys.stderr)
                     continue
                 if a.mbias and "mbias" in st:
                     mb_total = st["mbias"].astype(np.int64) if mb_total is None else mb_total + st["mbias"]   # mbias_merge (bam2pat.py:375-395)
-                if txt:
-                    parts.append((ri, bgzf_compress(txt, a.threads)))
+                if part:
+                    parts.append((ri, part))
             src.close()
             if world > 1:
                 ctx.sync()

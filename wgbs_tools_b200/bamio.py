@@ -342,8 +342,11 @@ class DeviceBam:
         return DevBuf.adopt(self.ctx, ptr.value, n.value)
 
     def pileup(self, index, chrom: str | None = None, view=None, min_cpg: int = 1, clip: int = 0, paired: int = -1, nanopore: bool = False,
-               np_thresh: float = 0.67, cpc_call: str = "C", combine_mods: bool = False, mbias: bool = False, keep_names: bool = False):
-        """`samtools view BAM chrom ... | [match_maker |] patter ...` without leaving the device (wgbs_pileup_dbam): the records that
+               np_thresh: float = 0.67, cpc_call: str = "C", combine_mods: bool = False, mbias: bool = False, keep_names: bool = False,
+               ctx=None):
+        """(ctx: the Context to run on -- another stream of the same GPU may pile up from this file's resident records; default: the
+        one that opened the file)
+        `samtools view BAM chrom ... | [match_maker |] patter ...` without leaving the device (wgbs_pileup_dbam): the records that
         pass `view` (keyword arguments of view_opts) go to the pileup kernels.  Returns (Pats, stats) like Context.pileup_sam;
         (None, stats with lines == 0) when nothing can pass."""
         from ._lib import PileupOpts
@@ -355,11 +358,12 @@ class DeviceBam:
         o = PileupOpts(min_cpg, clip, paired, int(nanopore), int(combine_mods), np_thresh, cpc_call.encode(), int(keep_names))
         h = C.c_void_p(); st = (C.c_uint64 * 8)()
         mb = np.zeros((2, 2, 1000, 2), np.int32) if mbias else None
-        check(lib.wgbs_pileup_dbam(self.ctx.h, index.h, self.h, C.byref(vo), C.addressof(o), C.byref(h), C.addressof(st), mb.ctypes.data if mbias else None))
+        cx = ctx or self.ctx
+        check(lib.wgbs_pileup_dbam(cx.h, index.h, self.h, C.byref(vo), C.addressof(o), C.byref(h), C.addressof(st), mb.ctypes.data if mbias else None))
         stats = dict(zip(keys, [int(x) for x in st]))
         if mbias:
             stats["mbias"] = mb
-        return Pats(self.ctx, h.value), stats
+        return Pats(cx, h.value), stats
 
     def view(self, chrom: str | None = None, **kw) -> bytes:
         d = self.view_dev(chrom, **kw)
