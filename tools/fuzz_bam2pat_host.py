@@ -45,8 +45,8 @@ for it in range(12):
     outs = []
     extra = random.choice([[], ["-F", "1796", "--include_flags", "1"], ["-r", "chr1"], ["--long", "--no_beta"], ["--bottom_strand"], ["--top_strand"],
                            ["--min_cpg", "2", "--clip", "3"], ["-r", "chr1:500-%d" % random.randint(600, 40_000)], ["-l"]])
-    for tag, dec, env in (("w", "host", {}), ("s", "stream", {"WGBS_STREAM_BYTES": str(random.choice([1, 100_000, 400_000]))}), ("c", "host", {"WGBS_CHUNK_RECORDS": str(random.choice([50, 700]))})):
-        os.environ.pop("WGBS_STREAM_BYTES", None); os.environ["WGBS_CHUNK_RECORDS"] = "0"
+    for tag, dec, env in (("w", "host", {}), ("s", "stream", {"WGBS_STREAM_BYTES": str(random.choice([1, 100_000, 400_000]))}), ("c", "host", {"WGBS_CHUNK_RECORDS": str(random.choice([50, 700])), "WGBS_GPU_STREAMS": str(random.choice([1, 2, 3]))})):
+        os.environ.pop("WGBS_STREAM_BYTES", None); os.environ.pop("WGBS_GPU_STREAMS", None); os.environ["WGBS_CHUNK_RECORDS"] = "0"
         os.environ.update(env)
         o = tmp / tag; o.mkdir()
         try:
