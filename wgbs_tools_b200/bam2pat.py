@@ -164,7 +164,8 @@ class _Source:
             # auto: device unless the inflated file does not fit in device memory (then the host reader decodes it)
             self.on_device = decode in ("device", "auto")
             # auto: a file whose inflated bytes (~5x the compressed ones) cannot fit beside the working set goes straight to streaming
-            if decode == "auto" and os.path.getsize(path) > int(os.environ.get("WGBS_DEVICE_BAM_MAX", 20 << 30)):
+            # (under torchrun every rank would hold the whole file: the limit is shared out, and a streamed file is read by block range)
+            if decode == "auto" and os.path.getsize(path) > int(os.environ.get("WGBS_DEVICE_BAM_MAX", 20 << 30)) // max(int(os.environ.get("WORLD_SIZE", "1")), 1):
                 self.__init__(path, threads, ctx, "stream")
                 return
             if self.on_device:
