@@ -9,6 +9,7 @@
 //                                                      scheme (segment size SEG bytes), apply the `samtools view` filters
 //                                                      (FLAGEQ: comma list or '-', RG: read group or '-', IVFILE: "beg end"
 //                                                      lines or '-'), print the SAM text; stderr: stats
+//   bamdev_core_check tables N SEED                    two-level Huffman tables of the two-phase decoder vs a canonical-code walk
 //   bamdev_core_check fmtg N SEED                      fmt_g vs snprintf("%g") on N random floats + edge cases
 //   bamdev_core_check part FILE.bam SEG DEPTH B0 NB FIRST REFS   blocks [B0, B0+NB) as a part of a streamed file (dbam_open_impl, part mode)
 #include <zlib.h>
@@ -25,6 +26,7 @@
 #include <vector>
 
 #include "../wgbs_tools_b200/csrc/bam_core.cuh"
+#include "../wgbs_tools_b200/csrc/inflate2_core.cuh"
 
 using namespace dflate;
 
@@ -84,7 +86,7 @@ static int zlib_inflate(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t u
     inflateEnd(&zs);
     return (rc == Z_STREAM_END && zs.avail_out == 0) ? 0 : -1;
 }
-static uint32_t g_crc_table[256];
+static uint32_t g_crc_table[256], g_crc4[1024];
 static int one_lane(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usize, uint32_t want_crc = 0, bool check_crc = false) {
     Scratch S; Inflater<OneLane> I; I.S = &S; I.dst = dst; I.dst_len = usize;
     int rc = I.run(src, n);
@@ -122,9 +124,56 @@ static int emu_team2(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usiz
 }
 static int emu_warp2(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usize, uint32_t want_crc) { return emu_team2<32>(src, n, dst, usize, want_crc); }
 
+
+// ---- the two-phase decoder (inflate2_core.cuh) ----------------------------------------------------------------------------------
+// phase 1 = one lane per block: plain arrays (layout 0) or the warp's lane-interleaved arrays seen from lane `lane` (layout 5);
+// phase 2 = the token replay by one lane, or by 32 lanes in lock step.  *ntok_out / *nsym_out: statistics.
+static size_t g_fallbacks = 0;
+static int one_lane2(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usize, uint32_t want_crc);
+static int two_phase(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usize, uint32_t want_crc, int layout, bool emu, uint32_t *ntok_out = nullptr) {
+    std::vector<dflate2::Token> tok(dflate2::token_cap(usize));
+    int rc;
+    auto fallback = [&]() { g_fallbacks++; return one_lane2(src, n, dst, usize, want_crc); };      // what bgzf_warp_inflate_k does for such a block
+    if (layout == 0) {
+        static dflate2::HostLane H; dflate2::Decoder<0> D; D.init(H.mem(), src, n, dst, usize, tok.data()); rc = D.run();
+        if (ntok_out) *ntok_out = D.ntok;
+        if (rc == dflate2::E_FALLBACK) return fallback();
+        if (rc != OK) return rc;
+        if (!emu) rc = dflate2::resolve(OneLane(), tok.data(), D.ntok, dst, usize, src);
+        else {
+            static EmuShared sh; int rcs[32]; const uint32_t nt = D.ntok;
+            std::vector<std::thread> th;
+            for (int l = 0; l < 32; l++) th.emplace_back([&, l]() {
+                EmuLanes L{l, &sh};
+                rcs[l] = dflate2::resolve(L, tok.data(), nt, dst, usize, src);
+                L.sync();
+                if (rcs[l] == OK && dflate2::crc32_block4(L, dst, usize, g_crc4) != want_crc) rcs[l] = E_CRC;
+            });
+            for (auto &t : th) t.join();
+            for (int l = 1; l < 32; l++) if (rcs[l] != rcs[0]) { fprintf(stderr, "lanes disagree on rc (two-phase)\n"); exit(4); }
+            return rcs[0];
+        }
+    } else {
+        static std::vector<unsigned char> smem(32 * dflate2::LANE_BYTES + 16);
+        unsigned char *base = smem.data() + ((16 - ((uintptr_t)smem.data() & 15)) & 15);
+        const uint32_t lane = (uint32_t)(n % 32);
+        dflate2::Decoder<5> D; D.init(dflate2::warp_mem(base, lane), src, n, dst, usize, tok.data());
+        // the kernel's schedule: header / bounded runs of probes
+        int st = dflate2::ST_HDR;
+        while (st != dflate2::ST_DONE) { if (st == dflate2::ST_HDR) st = D.header(); else { D.ring_top_up(); st = D.decode_burst(); } }
+        rc = D.rc;
+        if (ntok_out) *ntok_out = D.ntok;
+        if (rc == dflate2::E_FALLBACK) return fallback();
+        if (rc != OK) return rc;
+        rc = dflate2::resolve(OneLane(), tok.data(), D.ntok, dst, usize, src);
+    }
+    if (rc == OK && dflate2::crc32_block4(OneLane(), dst, usize, g_crc4) != want_crc) rc = E_CRC;
+    return rc;
+}
+
 static int cmd_inflate(const char *path, int emu_blocks) {
     auto f = slurp(path); uint64_t ut; auto blocks = scan_blocks(f, &ut);
-    size_t nbad = 0, nemu = 0; uint64_t bytes = 0;
+    size_t nbad = 0, nemu = 0; uint64_t bytes = 0, tokens = 0;
     for (size_t i = 0; i < blocks.size(); i++) {
         const Blk &b = blocks[i];
         const uint8_t *src = f.data() + b.coff + 12 + b.xlen; const uint32_t n = b.csize - 12 - b.xlen - 8;
@@ -135,8 +184,18 @@ static int cmd_inflate(const char *path, int emu_blocks) {
         const int r1 = one_lane(src, n, c.data(), b.usize, want, true);
         bool ok = (rz == 0) == (r1 == 0) && (rz != 0 || !memcmp(a.data(), c.data(), b.usize));
         { std::vector<uint8_t> c2(b.usize + 1); const int r3 = one_lane2(src, n, c2.data(), b.usize, want); ok = ok && (rz == 0) == (r3 == 0) && (rz != 0 || !memcmp(a.data(), c2.data(), b.usize)); }
+        for (int layout : {0, 5}) {
+            std::vector<uint8_t> c3(b.usize + 1); uint32_t nt = 0; const int r5 = two_phase(src, n, c3.data(), b.usize, want, layout, false, &nt);
+            const bool ok3 = (rz == 0) == (r5 == 0) && (rz != 0 || !memcmp(a.data(), c3.data(), b.usize));
+            if (!ok3) fprintf(stderr, "block %zu: two-phase decoder (layout %d): rc %d (zlib %d)\n", i, layout, r5, rz);
+            ok = ok && ok3; if (layout == 0) tokens += nt;
+        }
         if ((int)i < emu_blocks) {
             const int r2 = emu_warp(src, n, e.data(), b.usize, want); ok = ok && r2 == r1 && (r1 != 0 || !memcmp(a.data(), e.data(), b.usize)); nemu++;
+            { std::vector<uint8_t> e3(b.usize + 1); const int r6 = two_phase(src, n, e3.data(), b.usize, want, 0, true);
+              const bool ok6 = (rz == 0) == (r6 == 0) && (rz != 0 || !memcmp(a.data(), e3.data(), b.usize));
+              if (!ok6) fprintf(stderr, "block %zu: two-phase decoder, 32-lane replay: rc %d (zlib %d)\n", i, r6, rz);
+              ok = ok && ok6; }
             std::vector<uint8_t> e2(b.usize + 1); const int r4 = emu_warp2(src, n, e2.data(), b.usize, want); ok = ok && (rz == 0) == (r4 == 0) && (rz != 0 || !memcmp(a.data(), e2.data(), b.usize));
             // the team decoders (bgzf_inflate_team_k<G>): the same Inflater2 with batches of 4 / 8 / 16 symbols
             for (int g : {4, 8, 16}) {
@@ -150,6 +209,7 @@ static int cmd_inflate(const char *path, int emu_blocks) {
         if (!ok) { nbad++; fprintf(stderr, "block %zu: zlib %d core %d\n", i, rz, r1); }
         bytes += b.usize;
     }
+    fprintf(stderr, "tokens %llu fallbacks %zu\n", (unsigned long long)tokens, g_fallbacks);
     printf("blocks %zu emu %zu bytes %llu mismatches %zu\n", blocks.size(), nemu, (unsigned long long)bytes, nbad);
     return nbad ? 1 : 0;
 }
@@ -274,6 +334,71 @@ static int cmd_part(const char *path, uint64_t SEG, int depth, size_t b0, size_t
     return 0;
 }
 
+
+// ---- table construction of the two-phase decoder against a plain canonical-code walk -----------------------------------------------
+// N random complete code-length sets (literal/length: up to 286 symbols, distance: up to 30, lengths up to 15 bits, skewed so that
+// long codes and large second-level tables occur): every symbol's code must decode to that symbol with that length through
+// Decoder::probe (root + second level), in both memory layouts.  Sets whose tables exceed the arena must say E_FALLBACK.
+static void random_lengths(std::mt19937_64 &rng, int n, int maxbits, uint8_t *out) {
+    // split a unit of Kraft weight: start with one code of length 0, repeatedly split a random leaf (biased to deep ones) until n leaves
+    std::vector<int> leaves{0};
+    while ((int)leaves.size() < n) {
+        size_t pick = rng() % leaves.size();
+        if (rng() % 3) { size_t p2 = rng() % leaves.size(); if (leaves[p2] > leaves[pick]) pick = p2; }       // prefer deeper leaves: skew
+        if (leaves[pick] >= maxbits) { bool any = false; for (size_t i = 0; i < leaves.size(); i++) if (leaves[i] < maxbits) { pick = i; any = true; break; } if (!any) break; }
+        const int l = leaves[pick] + 1; leaves[pick] = l; leaves.push_back(l);
+    }
+    std::shuffle(leaves.begin(), leaves.end(), rng);
+    for (int i = 0; i < n; i++) out[i] = i < (int)leaves.size() ? (uint8_t)leaves[i] : 0;
+}
+template <int SH>
+static int check_tables(dflate2::Decoder<SH> &D, const uint8_t *ln, int nlen, int ndist, size_t *fallbacks) {
+    const uint32_t S = (uint32_t)SH;
+    for (int i = 0; i < nlen + ndist; i++) D.m.ln[(uint32_t)i << S] = ln[i];
+    const int rc = D.both_tables(nlen, ndist);
+    if (rc == dflate2::E_FALLBACK) { (*fallbacks)++; return 0; }
+    if (rc != OK) { fprintf(stderr, "both_tables: rc %d on a complete code\n", rc); return 1; }
+    for (int which = 0; which < 2; which++) {
+        const int n = which ? ndist : nlen; const uint8_t *l = ln + (which ? nlen : 0);
+        // canonical codes (RFC 1951 3.2.2)
+        int cnt[16] = {0}, next[16] = {0};
+        for (int i = 0; i < n; i++) cnt[l[i]]++;
+        cnt[0] = 0; int code = 0;
+        for (int b = 1; b <= 15; b++) { code = (code + cnt[b - 1]) << 1; next[b] = code; }
+        for (int sy = 0; sy < n; sy++) {
+            if (!l[sy]) continue;
+            const uint32_t c = (uint32_t)next[l[sy]]++, rev = brev32(c) >> (32 - l[sy]);
+            for (uint32_t hi = 0; hi < 4; hi++) {                          // the bits behind the code must not matter
+                D.bb = (uint64_t)rev | ((uint64_t)(hi * 0x9e3779b9u) << l[sy]);
+                const uint32_t e = which ? D.probe(D.dt_off, dflate2::DB) : D.probe(0, dflate2::LB);
+                const uint32_t want = which ? dflate2::dist_entry((uint32_t)sy, l[sy]) : dflate2::litlen_entry((uint32_t)sy, l[sy]);
+                if (e != want) { fprintf(stderr, "table %d symbol %d len %d: entry %08x, want %08x\n", which, sy, l[sy], e, want); return 1; }
+            }
+        }
+    }
+    return 0;
+}
+static int cmd_tables(long N, unsigned seed) {
+    std::mt19937_64 rng(seed); size_t bad = 0, fallbacks = 0;
+    static dflate2::HostLane H;
+    static std::vector<unsigned char> smem(32 * dflate2::LANE_BYTES + 16);
+    unsigned char *base = smem.data() + ((16 - ((uintptr_t)smem.data() & 15)) & 15);
+    static uint8_t dummy[64] = {3, 0};
+    for (long t = 0; t < N; t++) {
+        uint8_t ln[320] = {0};
+        const int nlen = 257 + (int)(rng() % 30), ndist = 1 + (int)(rng() % 30);
+        const int maxl = 9 + (int)(rng() % 7), maxd = 5 + (int)(rng() % 11);
+        random_lengths(rng, nlen, maxl, ln);
+        if (ndist >= 2) random_lengths(rng, ndist, maxd, ln + nlen); else ln[nlen] = 1;
+        dflate2::Decoder<0> D0; D0.init(H.mem(), dummy, 2, dummy + 8, 0, nullptr);
+        bad += check_tables(D0, ln, nlen, ndist, &fallbacks);
+        dflate2::Decoder<5> D5; D5.init(dflate2::warp_mem(base, (uint32_t)(t % 32)), dummy, 2, dummy + 8, 0, nullptr);
+        size_t fb5 = 0; bad += check_tables(D5, ln, nlen, ndist, &fb5);
+    }
+    printf("tables %ld fallbacks %zu mismatches %zu\n", N, fallbacks, bad);
+    return bad ? 1 : 0;
+}
+
 static int cmd_fmtg(long N, unsigned seed) {
     std::mt19937_64 rng(seed); size_t bad = 0;
     auto test = [&](uint32_t u) {
@@ -295,9 +420,11 @@ static int cmd_fmtg(long N, unsigned seed) {
 
 int main(int argc, char **argv) {
     for (uint32_t i = 0; i < 256; i++) g_crc_table[i] = crc_table_entry(i);
+    for (uint32_t k = 0; k < 4; k++) for (uint32_t i = 0; i < 256; i++) g_crc4[k * 256 + i] = dflate2::crc_slice_entry(k, i);
     if (argc >= 3 && !strcmp(argv[1], "inflate")) return cmd_inflate(argv[2], argc > 3 ? atoi(argv[3]) : 0);
     if (argc >= 5 && !strcmp(argv[1], "view")) return cmd_view(argv[2], strtoull(argv[3], nullptr, 10), atoi(argv[4]), argc - 5, argv + 5);
     if (argc >= 4 && !strcmp(argv[1], "fmtg")) return cmd_fmtg(atol(argv[2]), (unsigned)atoi(argv[3]));
+    if (argc >= 4 && !strcmp(argv[1], "tables")) return cmd_tables(atol(argv[2]), (unsigned)atoi(argv[3]));
     if (argc >= 9 && !strcmp(argv[1], "part")) return cmd_part(argv[2], strtoull(argv[3], nullptr, 10), atoi(argv[4]), strtoull(argv[5], nullptr, 10), strtoull(argv[6], nullptr, 10), strtoull(argv[7], nullptr, 10), argv[8]);
     fprintf(stderr, "usage: see the header of tests/bamdev_core_check.cpp\n");
     return 2;

@@ -251,3 +251,80 @@ def test_first_key_core_equals_the_host_reader(check, sam, tmp_path, built_lib):
             assert r.returncode == 0, r.stderr.decode()
             assert int(r.stdout.decode().strip()) == (-1 if exp is None else exp), (kw, key)
     part.close()
+
+
+
+def deep_code_block(rng, data: bytes, maxbits: int = 15, lens=None) -> bytes:
+    """a BGZF block holding ONE dynamic-Huffman deflate block of literals only whose literal/length code is deliberately deep
+    (many codes longer than 10 bits: large second-level tables in the two-phase decoder; some sets exceed its arena and must take
+    the warp-per-block decoder).  Written bit by bit here -- zlib never emits such shapes."""
+    n = 257
+    leaves = [0]
+    while lens is None and len(leaves) < n:
+        i, j = int(rng.integers(len(leaves))), int(rng.integers(len(leaves)))
+        if leaves[j] > leaves[i] and rng.integers(3):
+            i = j                                                  # prefer deep leaves: a skewed tree
+        if leaves[i] >= maxbits:
+            i = next(k for k, l in enumerate(leaves) if l < maxbits)
+        leaves[i] += 1; leaves.append(leaves[i])
+    lens = [int(x) for x in rng.permutation(leaves if lens is None else lens)]
+    cnt = [0] * 17
+    for l in lens:
+        cnt[l] += 1
+    cnt[0] = 0; code = 0; nxt = [0] * 17
+    for b in range(1, 16):
+        code = (code + cnt[b - 1]) << 1; nxt[b] = code
+    codes = []
+    for l in lens:
+        codes.append(nxt[l]); nxt[l] += 1
+    out = bytearray(); acc = 0; nacc = 0
+
+    def put(v, nb):                                                # nb bits of v, least significant first (RFC 1951 3.1.1)
+        nonlocal acc, nacc
+        acc |= v << nacc; nacc += nb
+        while nacc >= 8:
+            out.append(acc & 0xFF); acc >>= 8; nacc -= 8
+
+    def put_code(c, l):                                            # Huffman codes are packed most significant bit first
+        put(int(format(c, f"0{l}b")[::-1], 2), l)
+    put(1, 1); put(2, 2)                                           # final block, dynamic Huffman
+    put(n - 257, 5); put(0, 5); put(19 - 4, 4)                     # HLIT, HDIST (one distance code), HCLEN (all 19 lengths)
+    for sym in (16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15):
+        put(0 if sym >= 16 else 4, 3)                              # code-length code: symbols 0..15 get 4 bits each (code = the symbol)
+    for l in lens + [1]:                                           # the literal/length lengths, then the single distance code
+        put_code(l, 4)
+    for b in data:
+        put_code(codes[b], lens[b])
+    put_code(codes[256], lens[256])
+    if nacc:
+        out.append(acc & 0xFF)
+    return frame(bytes(out), data)
+
+
+def test_two_phase_decoder_tables_and_fallback(check, tmp_path):
+    """(1) the two-level Huffman tables of the two-phase decoder on 4 000 random complete code sets, in both memory layouts: every
+    symbol decodes to itself through root + second level, sets that exceed the per-lane arena are handed back (E_FALLBACK);
+    (2) hand-written deflate blocks with deep literal codes: output == zlib's, and some of them do take the fallback decoder"""
+    from wgbs_tools_b200.patio import BGZF_EOF
+    r = subprocess.run([check, "tables", "4000", "7"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("mismatches 0"), r.stdout + r.stderr
+    rng = np.random.default_rng(5)
+    parts = []
+    for k in range(60):
+        data = rng.integers(0, 256, int(rng.integers(1, 3000)), dtype=np.uint8).tobytes()
+        blk = deep_code_block(rng, data, maxbits=int(rng.integers(11, 16)))
+        assert zlib.decompress(blk[18:-8], -15) == data            # the hand-written stream is a valid deflate stream
+        parts.append(blk)
+    # 250 codes of 14-15 bits fill 8 different 10-bit prefixes: 8 second-level tables of 32 entries do not fit next to the roots
+    wide = list(range(1, 8)) + [15] * 244 + [14] * 6
+    for k in range(3):
+        data = rng.integers(0, 256, 2000, dtype=np.uint8).tobytes()
+        blk = deep_code_block(rng, data, lens=wide)
+        assert zlib.decompress(blk[18:-8], -15) == data
+        parts.insert(5 * k + 1, blk)
+    p = tmp_path / "deep.bgzf"
+    p.write_bytes(b"".join(parts) + BGZF_EOF)
+    r = subprocess.run([check, "inflate", str(p), "6"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("mismatches 0"), r.stdout + r.stderr
+    fb = int(r.stderr.split("fallbacks")[1].split()[0])
+    assert fb > 0, "no block exceeded the arena: the fallback path was not exercised"

@@ -46,22 +46,39 @@ def _block(data: bytes, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, mem=8) -> byt
 
 
 def test_bgzf_inflate_kernel_matches_zlib(ctx, sample):
-    """bgzf_inflate_k alone (wgbs_bgzf_inflate): stored / fixed / dynamic blocks, long codes, overlapping matches, several
-    deflate blocks per BGZF block, empty blocks, incompressible bytes -- output == zlib's, byte for byte"""
-    _inflate_checks(ctx, sample[1])
-
-
-@pytest.mark.staged
-@pytest.mark.parametrize("variant", ["g16", "g8", "g4"])
-def test_bgzf_inflate_team_kernels_match_zlib(ctx, sample, monkeypatch, variant):
-    """bgzf_inflate_team_k<G> (teams of G lanes per BGZF block, WGBS_INFLATE=gG): the same checks; a corrupt block is reported
-    with its number like the warp-per-block kernel does"""
-    monkeypatch.setenv("WGBS_INFLATE", variant)
+    """the two-phase decoder (bgzf_decode_k + bgzf_resolve_k, wgbs_bgzf_inflate): stored / fixed / dynamic blocks, long codes,
+    overlapping matches, several deflate blocks per BGZF block, empty blocks, incompressible bytes -- output == zlib's, byte
+    for byte; a corrupt block is reported with its number"""
     _inflate_checks(ctx, sample[1])
     from wgbs_tools_b200.patio import bgzf_compress
     bad = bytearray(bgzf_compress(sample[1][:200_000])); bad[18 + 100] ^= 0x55          # inside the first block's deflate payload
     with pytest.raises(Exception, match="inflate failed in BGZF block 0"):
         ctx.bgzf_inflate(bytes(bad)).free()
+    bad = bytearray(bgzf_compress(sample[1][:200_000])); bad[-28 - 6] ^= 0x01           # CRC32 field of the last data block
+    with pytest.raises(Exception, match="CRC32 mismatch"):
+        ctx.bgzf_inflate(bytes(bad)).free()
+
+
+def test_bgzf_inflate_deep_codes_and_the_fallback_decoder(ctx):
+    """hand-written deflate blocks with deep literal codes (test_bamdev_core.deep_code_block): large second-level tables in
+    bgzf_decode_k, and blocks whose tables exceed a lane's arena (handed to bgzf_warp_inflate_k inside the same call) -- all == zlib"""
+    from test_bamdev_core import deep_code_block
+    from wgbs_tools_b200.patio import BGZF_EOF
+    rng = np.random.default_rng(11)
+    parts, plain = [], []
+    wide = list(range(1, 8)) + [15] * 244 + [14] * 6               # 8 second-level tables of 32 entries: more than the arena holds
+    for k in range(70):
+        data = rng.integers(0, 256, int(rng.integers(1, 4000)), dtype=np.uint8).tobytes()
+        parts.append(deep_code_block(rng, data, maxbits=int(rng.integers(11, 16)), lens=wide if k % 9 == 4 else None)); plain.append(data)
+    out = ctx.bgzf_inflate(b"".join(parts) + BGZF_EOF)
+    assert out.to_host().tobytes() == b"".join(plain)
+    out.free()
+
+
+def test_bgzf_inflate_round1_decoder_matches_zlib(ctx, sample, monkeypatch):
+    """bgzf_inflate_k (WGBS_INFLATE=2: one warp per block, the round-1 decoder kept as the yardstick of the bench): same checks"""
+    monkeypatch.setenv("WGBS_INFLATE", "2")
+    _inflate_checks(ctx, sample[1])
 
 
 def _inflate_checks(ctx, s):

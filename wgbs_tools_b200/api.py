@@ -23,8 +23,17 @@ def _addr(x):
         if not x.flags["C_CONTIGUOUS"]:
             raise ValueError("array must be C-contiguous")
         return x.ctypes.data
-    if isinstance(x, (bytes, bytearray, memoryview)):
-        return C.cast(C.c_char_p(bytes(x)) if not isinstance(x, bytes) else C.c_char_p(x), C.c_void_p).value
+    if isinstance(x, bytes):
+        return C.cast(C.c_char_p(x), C.c_void_p).value
+    if isinstance(x, (bytearray, memoryview)):
+        # the address of the caller's own buffer (never of a temporary copy): the caller keeps `x` alive for the call,
+        # and writes through the pointer land in `x`
+        mv = memoryview(x)
+        if not mv.contiguous:
+            raise ValueError("buffer must be contiguous")
+        if mv.nbytes == 0:
+            return None
+        return np.frombuffer(mv, np.uint8).ctypes.data
     if isinstance(x, int):
         return x
     raise TypeError(type(x))

@@ -405,6 +405,7 @@ def main(argv=None):
             elif world > 1:
                 import torch
                 mc = torch.zeros((ref.nr_sites, 2), dtype=torch.int32, device=f"cuda:{local}")     # NCCL reduces it in place
+                torch.cuda.current_stream(local).synchronize()       # the fill ran on torch's stream; the Context's stream adds into mc
             else:
                 mc = ctx.alloc(ref.nr_sites * 8)
                 ctx.pat2beta(ctx.pats_from_text(b""), 1, ref.nr_sites + 1, meth_cov=mc, zero_first=True)

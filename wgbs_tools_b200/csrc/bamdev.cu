@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "bam_core.cuh"
+#include "bgzf.cuh"
 #include "common.cuh"
 #include "reads.cuh"
 
@@ -38,76 +39,7 @@ namespace {
 
 constexpr uint64_t SEG = 16384;     // bytes of inflated stream per boundary-search segment
 constexpr int GUESS_DEPTH = 4;      // consecutive plausible records required by a guess
-constexpr int INFL_WARPS = 4;       // warps (= BGZF blocks) per CTA of bgzf_inflate_k
 constexpr int FMT_G = 8;            // lanes per record in bam_format_k
-#ifndef WGBS_INFLATE_DEFAULT
-#define WGBS_INFLATE_DEFAULT 2      // WGBS_INFLATE=1|2 selects the decoder at run time (measured on the 1M-read batch: 10.4 ms / 4.7 ms)
-#endif
-
-struct BgzfBlock { uint64_t coff /* first byte of the deflate payload */, uoff; uint32_t clen, usize, crc, pad; };
-
-// V = 1: one decoding lane per warp (Inflater); V = 2: uniform execution, input staged in a shared-memory ring (Inflater2)
-template <int V>
-__global__ void __launch_bounds__(INFL_WARPS * 32, V == 2 ? 8 : 6) bgzf_inflate_k(const uint8_t *__restrict__ comp, const BgzfBlock *__restrict__ blocks, uint32_t nblocks,
-                                                                    uint8_t *out, unsigned long long *__restrict__ err) {
-    __shared__ dflate::Scratch S[INFL_WARPS];
-    __shared__ dflate::Ring RG[V == 2 ? INFL_WARPS : 1];
-    __shared__ uint32_t crc_table[256];
-    for (uint32_t i = threadIdx.x; i < 256; i += INFL_WARPS * 32) crc_table[i] = dflate::crc_table_entry(i);
-    __syncthreads();
-    const uint32_t w = threadIdx.x >> 5, b = blockIdx.x * INFL_WARPS + w;
-    if (b >= nblocks) return;                       // whole warps leave together (no block-wide barrier below)
-    const BgzfBlock B = blocks[b];
-    int rc;
-    if (V == 2) {
-        dflate::Inflater2<dflate::WarpLanes> I;
-        I.S = &S[w]; I.R = &RG[V == 2 ? w : 0]; I.dst = out + B.uoff; I.dst_len = B.usize;
-        rc = I.run(comp + B.coff, B.clen);
-    } else {
-        dflate::Inflater<dflate::WarpLanes> I;
-        I.S = &S[w]; I.dst = out + B.uoff; I.dst_len = B.usize;
-        rc = I.run(comp + B.coff, B.clen);
-    }
-    if (rc == dflate::OK) {
-        __syncwarp();
-        if (dflate::crc32_block(dflate::WarpLanes(), out + B.uoff, B.usize, crc_table) != B.crc) rc = dflate::E_CRC;
-    }
-    if (rc != dflate::OK && (threadIdx.x & 31) == 0) atomicMin(err, ((unsigned long long)b << 8) | (unsigned long long)(uint8_t)(-rc));
-}
-
-// Teams of G lanes per BGZF block (dflate::SubWarp): 32 / G blocks share one warp's instruction stream.  The warp-per-block
-// kernel above is bound by instruction issue (ncu: issue slots 65 % busy with 28 warps per SM, every warp executing the
-// same ~40 instructions per symbol for its own block on 32 lanes that all compute the same thing); here the same
-// instructions serve 32 / G blocks at once wherever the teams of a warp run in step, and a batch is G symbols.
-// Per team: Scratch + Ring in dynamic shared memory (5.9 KB), so an SM holds the same ~32 blocks in flight with a quarter
-// (G = 8) of the warps.  Selected with WGBS_INFLATE=g4|g8|g16.
-constexpr int TEAM_THREADS = 64;
-template <int G>
-__global__ void __launch_bounds__(TEAM_THREADS) bgzf_inflate_team_k(const uint8_t *__restrict__ comp, const BgzfBlock *__restrict__ blocks, uint32_t nblocks,
-                                                                     uint8_t *out, unsigned long long *__restrict__ err) {
-    constexpr int TEAMS = TEAM_THREADS / G;
-    extern __shared__ __align__(16) unsigned char team_smem[];
-    dflate::Scratch *S = reinterpret_cast<dflate::Scratch *>(team_smem);
-    dflate::Ring *RG = reinterpret_cast<dflate::Ring *>(team_smem + TEAMS * sizeof(dflate::Scratch));
-    uint32_t *crc_table = reinterpret_cast<uint32_t *>(team_smem + TEAMS * (sizeof(dflate::Scratch) + sizeof(dflate::Ring)));
-    for (uint32_t i = threadIdx.x; i < 256; i += TEAM_THREADS) crc_table[i] = dflate::crc_table_entry(i);
-    __syncthreads();
-    const uint32_t t = threadIdx.x / G, b = blockIdx.x * TEAMS + t;
-    if (b >= nblocks) return;                       // whole teams leave together (every barrier below is team-wide only)
-    const BgzfBlock B = blocks[b];
-    dflate::Inflater2<dflate::SubWarp<G>> I;
-    I.S = &S[t]; I.R = &RG[t]; I.dst = out + B.uoff; I.dst_len = B.usize;
-    int rc = I.run(comp + B.coff, B.clen);
-    if (rc == dflate::OK) {
-        I.lanes.sync();
-        if (dflate::crc32_block(dflate::SubWarp<G>(), out + B.uoff, B.usize, crc_table) != B.crc) rc = dflate::E_CRC;
-    }
-    if (rc != dflate::OK && (threadIdx.x & (G - 1)) == 0) atomicMin(err, ((unsigned long long)b << 8) | (unsigned long long)(uint8_t)(-rc));
-}
-template <int G>
-static size_t team_smem_bytes() { return (size_t)(TEAM_THREADS / G) * (sizeof(dflate::Scratch) + sizeof(dflate::Ring)) + 256 * sizeof(uint32_t); }
-static_assert(sizeof(dflate::Scratch) % 4 == 0 && sizeof(dflate::Ring) % 4 == 0, "team shared-memory layout");
-
 __global__ void __launch_bounds__(128) bam_guess_k(const uint8_t *__restrict__ data, uint64_t n, uint64_t p0, uint64_t nseg, int32_t n_ref,
                                                     uint64_t *__restrict__ entry) {
     const uint64_t s = (uint64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -297,7 +229,7 @@ int bgzf_inflate_device(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, const ch
         uint32_t xlen = 0; const uint32_t bs = dflate::bgzf_block_size(f + off, nbytes - off, &xlen);
         if (!bs) return wgbs_set_err("%s: not a BGZF file (bad block header at %llu)", who, (unsigned long long)off);
         if (off + bs > nbytes || bs < 12 + xlen + 8) return wgbs_set_err("%s: corrupt BGZF block at %llu", who, (unsigned long long)off);
-        BgzfBlock b; b.coff = off + 12 + xlen; b.clen = bs - 12 - xlen - 8; b.usize = ld32(f + off + bs - 4); b.crc = ld32(f + off + bs - 8); b.uoff = uoff; b.pad = 0;
+        BgzfBlock b; b.coff = off + 12 + xlen; b.clen = bs - 12 - xlen - 8; b.usize = ld32(f + off + bs - 4); b.crc = ld32(f + off + bs - 8); b.uoff = uoff; b.tok = 0;
         if (b.usize > 65536) return wgbs_set_err("%s: corrupt BGZF block at %llu (ISIZE %u)", who, (unsigned long long)off, b.usize);
         blocks.push_back(b); off += bs; uoff += b.usize;
     }
@@ -306,7 +238,8 @@ int bgzf_inflate_device(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, const ch
     Temps T(ctx);
     uint8_t *d_comp, *data = nullptr; BgzfBlock *d_blocks; unsigned long long *d_err;
     int rc;
-    if ((rc = T.alloc(&d_comp, nbytes + 16)) < 0 || (rc = T.alloc(&d_blocks, blocks.size())) < 0 || (rc = T.alloc(&d_err, 1)) < 0 || (rc = dalloc(ctx, &data, uoff + 16)) < 0) {
+    const uint64_t token_slots = bgzf_inflate2_plan(blocks.data(), (uint32_t)blocks.size());
+    if ((rc = T.alloc(&d_comp, nbytes + 64)) < 0 || (rc = T.alloc(&d_blocks, blocks.size())) < 0 || (rc = T.alloc(&d_err, 1)) < 0 || (rc = dalloc(ctx, &data, uoff + 16)) < 0) {
         // (cudaMemGetInfo costs a fraction of a millisecond: asked only to word the error)
         cudaGetLastError();
         size_t free_b = 0, total_b = 0;
@@ -320,21 +253,11 @@ int bgzf_inflate_device(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, const ch
     if (e == cudaSuccess) e = cudaMemsetAsync(data + uoff, 0, 16, ctx->stream);
     // read per call (a getenv is nothing next to an inflate): tests and bench legs switch decoders inside one process
     const char *ev = getenv("WGBS_INFLATE");
-    const int variant = !ev ? WGBS_INFLATE_DEFAULT : ev[0] == '1' ? 1 : ev[0] == '2' ? 2 : (ev[0] == 'g' && atoi(ev + 1) > 0) ? -atoi(ev + 1) : WGBS_INFLATE_DEFAULT;
-    if (variant < 0 && variant != -4 && variant != -8 && variant != -16) { dfree(ctx, data); return wgbs_set_err("%s: WGBS_INFLATE=%s (teams of 4, 8 or 16 lanes: g4 | g8 | g16)", who, ev); }
+    const bool old_decoder = ev && ev[0] == '2';
     if (e == cudaSuccess && !blocks.empty()) {
         const uint32_t nb = (uint32_t)blocks.size();
-        if (variant == 2) LAUNCH(ctx, bgzf_inflate_k<2>, grid_for(nb, INFL_WARPS), INFL_WARPS * 32, 0, d_comp, d_blocks, nb, data, d_err);
-        else if (variant == 1) LAUNCH(ctx, bgzf_inflate_k<1>, grid_for(nb, INFL_WARPS), INFL_WARPS * 32, 0, d_comp, d_blocks, nb, data, d_err);
-        else {
-#define TEAM_LAUNCH(G)                                                                                                                             \
-            do {                                                                                                                                       \
-                e = cudaFuncSetAttribute(bgzf_inflate_team_k<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)team_smem_bytes<G>());              \
-                if (e == cudaSuccess) LAUNCH(ctx, bgzf_inflate_team_k<G>, grid_for(nb, TEAM_THREADS / G), TEAM_THREADS, team_smem_bytes<G>(), d_comp, d_blocks, nb, data, d_err); \
-            } while (0)
-            if (variant == -4) TEAM_LAUNCH(4); else if (variant == -8) TEAM_LAUNCH(8); else TEAM_LAUNCH(16);
-#undef TEAM_LAUNCH
-        }
+        if (old_decoder) { if ((rc = bgzf_inflate_warp_launch(ctx, d_comp, d_blocks, nb, data, d_err)) < 0) { dfree(ctx, data); return rc; } }
+        else if ((rc = bgzf_inflate2_launch(ctx, d_comp, d_blocks, nb, token_slots, data, d_err)) < 0) { dfree(ctx, data); return rc; }
         if (e == cudaSuccess) e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(&herr, d_err, 8, cudaMemcpyDeviceToHost, ctx->stream);

@@ -6,6 +6,8 @@
 // packed MSB-first and zero padding, that order is the numeric order of (idx, word0, word1, ...): patterns never end
 // in '.', so zero padding is unambiguous.  One stable 32-bit radix sort on (idx - idx_min, first few symbols) orders
 // everything except ties between longer patterns, which fix_ties_k settles run by run.
+#include <algorithm>
+
 #include "reads.cuh"
 #include "sort.cuh"
 
@@ -53,9 +55,21 @@ __device__ __forceinline__ int name_cmp(const PatsView &P, uint32_t a, uint32_t 
     for (uint32_t k = 0; k < m; k++) if (x[k] != y[k]) return x[k] < y[k] ? -1 : 1;
     return la < lb ? -1 : (la > lb ? 1 : 0);
 }
-// mode 0: patterns never end in '.', zero padding orders them; 1 (--long): ties go to the read name; 2 (cview output: a clipped
-// pattern may end in '.'): equal zero-padded words are ordered shorter first, as `sort -k3,3` orders "C" before "C."
-__global__ void __launch_bounds__(128) fix_ties_k(PatsView P, uint32_t *__restrict__ perm, const uint32_t *__restrict__ key /*sorted*/, uint32_t nsym, int by_name) {
+// full comparison of two records of one run.  mode 0: patterns never end in '.', zero padding orders them; 1 (--long): ties go to
+// the read name; 2 (cview output: a clipped pattern may end in '.'): equal zero-padded words are ordered shorter first, as
+// `sort -k3,3` orders "C" before "C."
+__device__ __forceinline__ int rec_cmp(const PatsView &P, uint32_t a, uint32_t b, int by_name) {
+    int c = pat_cmp(P, a, b);
+    if (c == 0 && by_name == 1) c = name_cmp(P, a, b);
+    if (c == 0 && by_name == 2) c = P.len[a] < P.len[b] ? -1 : (P.len[a] > P.len[b] ? 1 : 0);
+    return c;
+}
+// Runs up to this length are ordered by ONE thread (insertion sort: at 30x WGBS a run is the few templates that start at one CpG
+// with the same first calls); longer ones -- amplicon / targeted / RRBS data pile 1e5..1e6 templates onto one start CpG -- are
+// queued for fix_long_runs_k, which sorts each with a whole CTA in O(n log^2 n) like the reference's `sort` stays O(n log n).
+constexpr uint32_t TIES_SERIAL_MAX = 64;
+__global__ void __launch_bounds__(128) fix_ties_k(PatsView P, uint32_t *__restrict__ perm, const uint32_t *__restrict__ key /*sorted*/, uint32_t nsym, int by_name,
+                                                   uint2 *__restrict__ long_runs, uint32_t *__restrict__ n_long) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
     const uint32_t k0 = key[i];
@@ -63,16 +77,41 @@ __global__ void __launch_bounds__(128) fix_ties_k(PatsView P, uint32_t *__restri
     size_t j = i + 1; bool any_long = P.len[perm[i]] > nsym;
     while (j < P.n && key[j] == k0) { any_long |= P.len[perm[j]] > nsym; j++; }
     if ((!any_long && !by_name) || j - i < 2) return;
+    if (j - i > TIES_SERIAL_MAX) { long_runs[atomicAdd(n_long, 1u)] = make_uint2((uint32_t)i, (uint32_t)(j - i)); return; }
     for (size_t k = i + 1; k < j; k++) {
         const uint32_t v = perm[k]; size_t q = k;
         while (q > i) {
-            int c = pat_cmp(P, perm[q - 1], v);
-            if (c == 0 && by_name == 1) c = name_cmp(P, perm[q - 1], v);
-            if (c == 0 && by_name == 2) c = P.len[perm[q - 1]] < P.len[v] ? -1 : (P.len[perm[q - 1]] > P.len[v] ? 1 : 0);
-            if (c <= 0) break;
+            if (rec_cmp(P, perm[q - 1], v, by_name) <= 0) break;
             perm[q] = perm[q - 1]; q--;
         }
         perm[q] = v;
+    }
+}
+// One CTA per queued run (CTAs stride over the queue): bitonic sort of perm[start .. start + len) in global memory, positions past
+// the run's end acting as +infinity.  Not stable -- records that compare equal are identical in everything the output shows
+// (index, pattern, and in --long the name), so their order cannot be observed.
+__global__ void __launch_bounds__(1024) fix_long_runs_k(PatsView P, uint32_t *__restrict__ perm, int by_name, const uint2 *__restrict__ long_runs,
+                                                         const uint32_t *__restrict__ n_long) {
+    const uint32_t nq = *n_long;
+    for (uint32_t r = blockIdx.x; r < nq; r += gridDim.x) {
+        uint32_t *a = perm + long_runs[r].x; const uint32_t n = long_runs[r].y;
+        uint32_t np2 = 1; while (np2 < n) np2 <<= 1;
+        // the all-ascending form of the network: the first step of a merge stage pairs position p with its mirror inside the
+        // 2k-block (p ^ (k - 1)), the others pair p with p ^ j; virtual +infinity elements then never have to move
+        for (uint32_t k = 2; k <= np2; k <<= 1) {
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                const bool mirror = j == (k >> 1);
+                for (uint32_t t = threadIdx.x; t < np2 / 2; t += blockDim.x) {
+                    const uint32_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));                  // position without bit j
+                    const uint32_t hi = mirror ? (lo ^ (k - 1)) : (lo | j);
+                    if (hi >= n) continue;                                                       // partner is +infinity
+                    const uint32_t x = a[lo], y = a[hi];
+                    if (rec_cmp(P, x, y, by_name) > 0) { a[lo] = y; a[hi] = x; }
+                }
+                __syncthreads();
+            }
+        }
+        __syncthreads();
     }
 }
 __global__ void __launch_bounds__(256) iota_k(uint32_t *__restrict__ p, size_t n) {
@@ -206,7 +245,13 @@ static int collapse_impl(wgbs_ctx *ctx, wgbs_pats *P, int mode) {
     } else {
         LAUNCH(ctx, make_key_k, grid_for(n, 256), 256, 0, pv, mm[0], nsym, k, v);
         RC_TRY(radix_sort_pairs(ctx, &k, &v, &ka, &va, n));
-        LAUNCH(ctx, fix_ties_k, grid_for(n, 128), 128, 0, pv, v, k, nsym, long_mode ? 1 : (mode == WGBS_COLLAPSE_DOTTED ? 2 : 0));   // longer patterns (and names): order inside equal-key runs
+        // longer patterns (and names): order inside equal-key runs; runs too long for one thread are queued and sorted by whole CTAs
+        const int by = long_mode ? 1 : (mode == WGBS_COLLAPSE_DOTTED ? 2 : 0);
+        uint2 *long_runs; uint32_t *n_long = ctx->d_flags + 14;
+        RC_TRY(T.alloc(&long_runs, n / TIES_SERIAL_MAX + 1));
+        CUDA_TRY(cudaMemsetAsync(n_long, 0, 4, ctx->stream));
+        LAUNCH(ctx, fix_ties_k, grid_for(n, 128), 128, 0, pv, v, k, nsym, by, long_runs, n_long);
+        LAUNCH(ctx, fix_long_runs_k, (unsigned)std::min<size_t>(n / TIES_SERIAL_MAX + 1, (size_t)ctx->sm_count), 1024, 0, pv, v, by, long_runs, n_long);
     }
     if (long_mode) {
         // no uniq in --long: the records are only re-ordered

@@ -1,0 +1,135 @@
+// inflate2.cu -- the two kernels of the two-phase BGZF decoder (inflate2_core.cuh):
+//
+//   bgzf_decode_k        one THREAD per BGZF block, 4 warps x 8 decoding lanes (= 32 blocks) per CTA and SM: lane-interleaved
+//                        two-level Huffman tables in 220 KB of shared memory; literals go to their final place, matches to a
+//                        token list.  Lanes take the deflate-block headers of their blocks together (table construction is
+//                        the same instruction stream for all of them) and then run bursts of table probes.
+//   bgzf_resolve_k       one WARP per block: token replay (LZ77 copies), then ISIZE and CRC32 of the block.
+//   bgzf_warp_inflate_k  the round-1 decoder (one warp per block): blocks whose tables exceed a lane's arena, and the yardstick.
+//
+// Stands in for the zlib inflate inside `samtools view` (reference src/python/bam2pat.py:165).
+#include <algorithm>
+
+#include "bgzf.cuh"
+#include "inflate2_core.cuh"
+
+namespace {
+
+constexpr int DEC_WARPS = 4;            // warps per CTA of bgzf_decode_k, DEC_LANES decoding lanes each: 32 blocks per CTA (and SM)
+constexpr int DEC_LANES = 8;            // few lanes per warp: what one lane does rarely (second-level probe, ring word) stalls only 7 others
+constexpr int RES_WARPS = 8;            // warps (= blocks) per CTA of bgzf_resolve_k
+constexpr int OLD_WARPS = 4;            // warps (= blocks) per CTA of bgzf_warp_inflate_k
+constexpr uint32_t CHUNK_BLOCKS = 8192; // blocks per launch pair: bounds the token scratch (~175 KB per block) to 1.4 GB
+
+__global__ void __launch_bounds__(DEC_WARPS * 32, 1) bgzf_decode_k(const uint8_t *__restrict__ comp, const BgzfBlock *__restrict__ blocks, uint32_t nblocks,
+                                                                   uint8_t *__restrict__ out, dflate2::Token *__restrict__ tok, uint32_t *__restrict__ ntok,
+                                                                   int32_t *__restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr unsigned MASK = 0xffffffffu;                          // lanes >= DEC_LANES idle along (state DONE): whole-warp barriers stay valid
+    const uint32_t slot = warp * DEC_LANES + (lane & (DEC_LANES - 1));
+    for (uint32_t base = blockIdx.x * 32; base < nblocks; base += gridDim.x * 32) {
+        const uint32_t b = base + slot;
+        const bool active = lane < DEC_LANES && b < nblocks;
+        dflate2::Decoder<5> D;
+        int st = dflate2::ST_DONE;
+        if (active) {
+            const BgzfBlock B = blocks[b];
+            D.init(dflate2::warp_mem(smem, slot), comp + B.coff, B.clen, out + B.uoff, B.usize, tok + B.tok);
+            st = dflate2::ST_HDR;
+        }
+        __syncwarp(MASK);
+        while (__any_sync(MASK, st != dflate2::ST_DONE)) {
+            if (st == dflate2::ST_HDR) st = D.header();             // lanes at a deflate block header build their tables together
+            __syncwarp(MASK);
+            if (st == dflate2::ST_DEC) { D.ring_top_up(); st = D.decode_burst(); }
+            __syncwarp(MASK);
+        }
+        if (active) { ntok[b] = D.ntok; status[b] = D.rc; }
+        __syncwarp(MASK);
+    }
+}
+
+__global__ void __launch_bounds__(RES_WARPS * 32) bgzf_resolve_k(const uint8_t *__restrict__ comp, const BgzfBlock *__restrict__ blocks, uint32_t nblocks, uint32_t block0,
+                                                                  uint8_t *out, const dflate2::Token *__restrict__ tok, const uint32_t *__restrict__ ntok,
+                                                                  const int32_t *__restrict__ status, unsigned long long *__restrict__ err) {
+    __shared__ uint32_t T[1024];
+    for (uint32_t i = threadIdx.x; i < 1024; i += RES_WARPS * 32) T[i] = dflate2::crc_slice_entry(i >> 8, i & 255);
+    __syncthreads();
+    const uint32_t b = blockIdx.x * RES_WARPS + (threadIdx.x >> 5);
+    if (b >= nblocks) return;                       // whole warps leave together (no block-wide barrier below)
+    const BgzfBlock B = blocks[b];
+    int rc = status[b];
+    if (rc == dflate2::E_FALLBACK) return;          // bgzf_warp_inflate_k decodes this block
+    if (rc == dflate2::OK) {
+        rc = dflate2::resolve(dflate::WarpLanes(), tok + B.tok, ntok[b], out + B.uoff, B.usize, comp + B.coff);
+        __syncwarp();
+        if (rc == dflate2::OK && dflate2::crc32_block4(dflate::WarpLanes(), out + B.uoff, B.usize, T) != B.crc) rc = dflate2::E_CRC;
+    }
+    if (rc != dflate2::OK && (threadIdx.x & 31) == 0)
+        atomicMin(err, ((unsigned long long)(block0 + b) << 8) | (unsigned long long)(uint8_t)(-rc));
+}
+
+// One warp per BGZF block, every lane running the same Huffman walk (dflate::Inflater2, inflate_core.cuh): the round-1 decoder.
+// status != nullptr: only the blocks bgzf_decode_k handed back (E_FALLBACK: their Huffman tables exceed its per-lane arena);
+// status == nullptr: every block (WGBS_INFLATE=2: the yardstick the two-phase decoder is measured against).
+__global__ void __launch_bounds__(OLD_WARPS * 32, 8) bgzf_warp_inflate_k(const uint8_t *__restrict__ comp, const BgzfBlock *__restrict__ blocks, uint32_t nblocks, uint32_t block0,
+                                                                          uint8_t *out, const int32_t *__restrict__ status, unsigned long long *__restrict__ err) {
+    __shared__ dflate::Scratch S[OLD_WARPS];
+    __shared__ dflate::Ring RG[OLD_WARPS];
+    __shared__ uint32_t crc_table[256];
+    const uint32_t w = threadIdx.x >> 5, b = blockIdx.x * OLD_WARPS + w;
+    const bool mine = b < nblocks && (!status || status[b] == dflate2::E_FALLBACK);
+    if (!__syncthreads_or(mine)) return;            // the usual case of the fallback launch: nothing to do
+    for (uint32_t i = threadIdx.x; i < 256; i += OLD_WARPS * 32) crc_table[i] = dflate::crc_table_entry(i);
+    __syncthreads();
+    if (!mine) return;                              // whole warps leave together (no block-wide barrier below)
+    const BgzfBlock B = blocks[b];
+    dflate::Inflater2<dflate::WarpLanes> I;
+    I.S = &S[w]; I.R = &RG[w]; I.dst = out + B.uoff; I.dst_len = B.usize;
+    int rc = I.run(comp + B.coff, B.clen);
+    if (rc == dflate::OK) {
+        __syncwarp();
+        if (dflate::crc32_block(dflate::WarpLanes(), out + B.uoff, B.usize, crc_table) != B.crc) rc = dflate::E_CRC;
+    }
+    if (rc != dflate::OK && (threadIdx.x & 31) == 0) atomicMin(err, ((unsigned long long)(block0 + b) << 8) | (unsigned long long)(uint8_t)(-rc));
+}
+
+}  // namespace
+
+uint64_t bgzf_inflate2_plan(BgzfBlock *h_blocks, uint32_t nb) {
+    // token slots are numbered inside a chunk of blocks: the scratch is reused chunk after chunk (launches on one stream run in order)
+    uint64_t max_tok = 0;
+    for (uint32_t c0 = 0; c0 < nb; c0 += CHUNK_BLOCKS) {
+        uint64_t o = 0;
+        for (uint32_t i = c0; i < nb && i < c0 + CHUNK_BLOCKS; i++) { h_blocks[i].tok = (uint32_t)o; o += dflate2::token_cap(h_blocks[i].usize); }
+        if (o > max_tok) max_tok = o;
+    }
+    return max_tok;
+}
+
+int bgzf_inflate2_launch(wgbs_ctx *ctx, const uint8_t *d_comp, const BgzfBlock *d_blocks, uint32_t nb, uint64_t token_slots, uint8_t *out,
+                         unsigned long long *d_err) {
+    if (!nb) return 0;
+    static const size_t smem_bytes = 32 * dflate2::LANE_BYTES;
+    CUDA_TRY(cudaFuncSetAttribute(bgzf_decode_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    Temps T(ctx);
+    dflate2::Token *tok; uint32_t *ntok; int32_t *status;
+    RC_TRY(T.alloc(&tok, (size_t)token_slots)); RC_TRY(T.alloc(&ntok, nb)); RC_TRY(T.alloc(&status, nb));
+    for (uint32_t c0 = 0; c0 < nb; c0 += CHUNK_BLOCKS) {
+        const uint32_t n = nb - c0 < CHUNK_BLOCKS ? nb - c0 : CHUNK_BLOCKS;
+        const unsigned grid = (unsigned)std::min<uint32_t>((n + 31) / 32, (uint32_t)ctx->sm_count);
+        LAUNCH(ctx, bgzf_decode_k, grid, DEC_WARPS * 32, smem_bytes, d_comp, d_blocks + c0, n, out, tok, ntok + c0, status + c0);
+        LAUNCH(ctx, bgzf_resolve_k, grid_for(n, RES_WARPS), RES_WARPS * 32, 0, d_comp, d_blocks + c0, n, c0, out, tok, ntok + c0, status + c0, d_err);
+        LAUNCH(ctx, bgzf_warp_inflate_k, grid_for(n, OLD_WARPS), OLD_WARPS * 32, 0, d_comp, d_blocks + c0, n, c0, out, status + c0, d_err);
+    }
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int bgzf_inflate_warp_launch(wgbs_ctx *ctx, const uint8_t *d_comp, const BgzfBlock *d_blocks, uint32_t nb, uint8_t *out, unsigned long long *d_err) {
+    if (!nb) return 0;
+    LAUNCH(ctx, bgzf_warp_inflate_k, grid_for(nb, OLD_WARPS), OLD_WARPS * 32, 0, d_comp, d_blocks, nb, 0u, out, (const int32_t *)nullptr, d_err);
+    LAUNCH_CHECK();
+    return 0;
+}

@@ -6,6 +6,7 @@ from __future__ import annotations
 
 import gzip
 import os
+import threading
 import re
 
 import numpy as np
@@ -37,23 +38,29 @@ class GenomeRef:
         self.nr_sites = int(self.sizes.sum())
         self._loci = None
         self._lengths = None
+        self._lock = threading.Lock()      # the lazy caches below are filled once, whichever thread asks first
 
     def all_loci(self) -> np.ndarray:
         """uint32[nr_sites] locus of CpG i+1 (all chromosomes, index order)"""
-        if self._loci is None:
+        if self._loci is not None:
+            return self._loci
+        with self._lock:                                       # one thread parses the ~28M-line dictionary, the others wait for it
+            if self._loci is not None:
+                return self._loci
             cache = self.dict_path + ".loci.npy"
             if os.path.isfile(cache) and os.path.getmtime(cache) >= os.path.getmtime(self.dict_path):
-                self._loci = np.load(cache)
+                loci = np.load(cache)
             else:
                 op = gzip.open if open(self.dict_path, "rb").read(2) == b"\x1f\x8b" else open
                 with op(self.dict_path, "rb") as f:
-                    self._loci = np.array([int(l.split(b"\t", 2)[1]) for l in f], np.uint32)
+                    loci = np.array([int(l.split(b"\t", 2)[1]) for l in f], np.uint32)
                 try:
-                    np.save(cache, self._loci)
+                    np.save(cache, loci)
                 except OSError:
                     pass
-            if self._loci.size != self.nr_sites:
+            if loci.size != self.nr_sites:
                 raise IllegalArgumentError("CpG.bed.gz does not match CpG.chrome.size")
+            self._loci = loci                                  # published only when complete
         return self._loci
 
     def chrom_range(self, chrom: str) -> tuple[int, int]:
@@ -75,12 +82,15 @@ class GenomeRef:
     def chrom_length(self, chrom: str) -> int:
         """bp length from chrome.size (falls back to the last CpG locus + 1 when the file is absent)"""
         if self._lengths is None:
-            self._lengths = {}
-            path = os.path.join(self.dir, "chrome.size")
-            if os.path.isfile(path):
-                for l in open(path):
-                    c, n = l.split()
-                    self._lengths[c] = int(n)
+            with self._lock:                                   # bam2pat --gpu_streams calls this from several worker threads
+                if self._lengths is None:
+                    lengths = {}
+                    path = os.path.join(self.dir, "chrome.size")
+                    if os.path.isfile(path):
+                        for l in open(path):
+                            c, n = l.split()
+                            lengths[c] = int(n)
+                    self._lengths = lengths                    # published only when complete
         if chrom in self._lengths:
             return self._lengths[chrom]
         loci, _ = self.chrom_loci(chrom)

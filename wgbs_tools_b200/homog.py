@@ -146,12 +146,21 @@ def main(argv=None):
                 print(f"[ wt homog ] skipping {name}. Use -f to overwrite", file=sys.stderr)
                 continue
             dtext = None
-            if world == 1 and args.pat_decode in ("auto", "device"):
+            small = len(lines) <= 5000                                 # homog.py:107-110: few blocks -> `wgbstools cview pat -L blocks | homog`
+            if small:
+                # The reference then feeds homog with cview's output: the reads that start at most 100 CpGs before a block (extend_blocks.sh +
+                # tabix -R) and overlap one, whole (no --strict), sorted and collapsed.  A read that starts earlier and still reaches into
+                # a block is NOT counted on this path (it is with > 5000 blocks): mirrored, so both paths give the reference's numbers.
+                from .genome import GenomeRef
+                from .view import load_cview_blocks, view_pat
+                ref = GenomeRef(args.genome)
+                vtext = view_pat(ctx, ref, wd.shard_lines(read_pat_text(pat), rank, world), blocks=load_cview_blocks(args.blocks_file), prefilter=True)
+            if not small and world == 1 and args.pat_decode in ("auto", "device"):
                 from .patio import read_pat_device
                 dtext = read_pat_device(ctx, pat)                  # BGZF: only the compressed bytes cross PCIe; None: plain gzip / text
             from .patio import pat_pieces
             counts = None                                              # bins are sums over records: a text of any size goes piece by piece
-            for piece in pat_pieces(ctx, dtext if dtext is not None else wd.shard_lines(read_pat_text(pat), rank, world)):
+            for piece in pat_pieces(ctx, vtext if small else dtext if dtext is not None else wd.shard_lines(read_pat_text(pat), rank, world)):
                 P = ctx.pats_from_text(piece)
                 c = homog_counts(ctx, P, lines, cols, edges, args.rlen, args.inclusive)
                 P.free()
