@@ -171,6 +171,47 @@ static int two_phase(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usiz
     return rc;
 }
 
+
+// the schedule of bgzf_decode_k on the host: 32 decoding lanes share one lane-interleaved buffer; per round every lane at a header
+// takes it, then every lane inside a Huffman block tops its ring up and runs one burst.  Blocks are taken 32 at a time.
+static size_t group_check(const std::vector<uint8_t> &f, const std::vector<Blk> &blocks) {
+    static std::vector<unsigned char> smem(32 * dflate2::LANE_BYTES + 16);
+    unsigned char *base = smem.data() + ((16 - ((uintptr_t)smem.data() & 15)) & 15);
+    size_t bad = 0;
+    for (size_t g0 = 0; g0 < blocks.size(); g0 += 32) {
+        const size_t ng = std::min<size_t>(32, blocks.size() - g0);
+        std::vector<dflate2::Decoder<5>> D(ng); std::vector<int> st(ng, dflate2::ST_HDR);
+        std::vector<std::vector<uint8_t>> out(ng); std::vector<std::vector<dflate2::Token>> tok(ng);
+        for (size_t i = 0; i < ng; i++) {
+            const Blk &b = blocks[g0 + i];
+            out[i].assign(b.usize + 1, 0); tok[i].resize(dflate2::token_cap(b.usize));
+            D[i].init(dflate2::warp_mem(base, (uint32_t)i), f.data() + b.coff + 12 + b.xlen, b.csize - 12 - b.xlen - 8, out[i].data(), b.usize, tok[i].data());
+        }
+        for (bool any = true; any;) {
+            any = false;
+            for (size_t i = 0; i < ng; i++) if (st[i] == dflate2::ST_HDR) st[i] = D[i].header();
+            for (size_t i = 0; i < ng; i++) if (st[i] == dflate2::ST_DEC) D[i].ring_top_up();
+            for (size_t i = 0; i < ng; i++) if (st[i] == dflate2::ST_DEC) st[i] = D[i].decode_burst();
+            for (size_t i = 0; i < ng; i++) any = any || st[i] != dflate2::ST_DONE;
+        }
+        for (size_t i = 0; i < ng; i++) {
+            const Blk &b = blocks[g0 + i];
+            const uint8_t *src = f.data() + b.coff + 12 + b.xlen; const uint32_t n = b.csize - 12 - b.xlen - 8;
+            std::vector<uint8_t> a(b.usize + 1);
+            const uint32_t want = bamcore::ld32(f.data() + b.coff + b.csize - 8);
+            int rz = zlib_inflate(src, n, a.data(), b.usize);
+            if (rz == 0 && (uint32_t)crc32(crc32(0L, Z_NULL, 0), a.data(), b.usize) != want) rz = -1;
+            int rc = D[i].rc;
+            if (rc == dflate2::E_FALLBACK) continue;
+            if (rc == OK) rc = dflate2::resolve(OneLane(), tok[i].data(), D[i].ntok, out[i].data(), b.usize, src);
+            if (rc == OK && dflate2::crc32_block4(OneLane(), out[i].data(), b.usize, g_crc4) != want) rc = E_CRC;
+            const bool ok = (rz == 0) == (rc == 0) && (rz != 0 || !memcmp(a.data(), out[i].data(), b.usize));
+            if (!ok) { fprintf(stderr, "block %zu: 32-lane schedule: rc %d (zlib %d)\n", g0 + i, rc, rz); bad++; }
+        }
+    }
+    return bad;
+}
+
 static int cmd_inflate(const char *path, int emu_blocks) {
     auto f = slurp(path); uint64_t ut; auto blocks = scan_blocks(f, &ut);
     size_t nbad = 0, nemu = 0; uint64_t bytes = 0, tokens = 0;
@@ -209,6 +250,7 @@ static int cmd_inflate(const char *path, int emu_blocks) {
         if (!ok) { nbad++; fprintf(stderr, "block %zu: zlib %d core %d\n", i, rz, r1); }
         bytes += b.usize;
     }
+    nbad += group_check(f, blocks);
     fprintf(stderr, "tokens %llu fallbacks %zu\n", (unsigned long long)tokens, g_fallbacks);
     printf("blocks %zu emu %zu bytes %llu mismatches %zu\n", blocks.size(), nemu, (unsigned long long)bytes, nbad);
     return nbad ? 1 : 0;

@@ -31,6 +31,13 @@ def frame(comp: bytes, data: bytes) -> bytes:
             + struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data)))
 
 
+def frame_shifted(comp: bytes, data: bytes, k: int) -> bytes:
+    """the same BGZF block with a second extra subfield of k payload bytes in front of 'BC': moves the deflate payload by 4 + k bytes"""
+    xlen = 6 + 4 + k
+    return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff" + struct.pack("<H", xlen) + b"XX" + struct.pack("<H", k) + bytes(k) + b"BC\x02\x00"
+            + struct.pack("<H", len(comp) + 12 + xlen + 8 - 1) + comp + struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data)))
+
+
 def block(data: bytes, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, mem=8) -> bytes:
     co = zlib.compressobj(level, zlib.DEFLATED, -15, mem, strategy)
     return frame(co.compress(data) + co.flush(), data)
@@ -62,11 +69,21 @@ def test_inflate_core_matches_zlib_on_every_block_type(check, sam, tmp_path):
     parts.append(frame(co.compress(d[:10000]) + co.flush(zlib.Z_SYNC_FLUSH) + co.compress(d[10000:]) + co.flush(zlib.Z_FULL_FLUSH) + co.flush(), d))
     # the emulated warp is slow (thread barriers): put one block of every kind first
     order = [0, 4, 5, 6, len(parts) - 1, 36, 12, 20] + [i for i in range(len(parts)) if i not in (0, 4, 5, 6, len(parts) - 1, 36, 12, 20)]
+    # every alignment of the payload (the bit reader starts inside a 16-byte chunk; a fixed / stored block header leaves it
+    # with as few as 5 bits before the first probe)
+    shifted = []
+    for k in range(16):
+        for st in (zlib.Z_FIXED, zlib.Z_DEFAULT_STRATEGY):
+            d = s[1000 * k:1000 * k + 20000]
+            co = zlib.compressobj(6, zlib.DEFLATED, -15, 8, st)
+            shifted.append(frame_shifted(co.compress(d) + co.flush(), d, k))
+        shifted.append(frame_shifted(zlib.compressobj(0, zlib.DEFLATED, -15).compress(s[:3000]) + zlib.compressobj(0, zlib.DEFLATED, -15).flush(), s[:3000], k) if False else
+                       frame_shifted((lambda c: c.compress(s[:3000]) + c.flush())(zlib.compressobj(0, zlib.DEFLATED, -15)), s[:3000], k))
     p = tmp_path / "mix.bgzf"
-    p.write_bytes(b"".join(parts[i] for i in order) + BGZF_EOF)
+    p.write_bytes(b"".join(parts[i] for i in order) + b"".join(shifted) + BGZF_EOF)
     r = subprocess.run([check, "inflate", str(p), "8"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert f"blocks {len(parts) + 1} emu 8 " in r.stdout and r.stdout.strip().endswith("mismatches 0")
+    assert f"blocks {len(parts) + len(shifted) + 1} emu 8 " in r.stdout and r.stdout.strip().endswith("mismatches 0")
 
 
 def test_inflate_core_rejects_what_zlib_rejects(check, sam, tmp_path, built_lib):

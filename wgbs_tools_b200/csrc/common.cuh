@@ -42,6 +42,8 @@ struct wgbs_ctx {
     cudaEvent_t ev_copy = nullptr, ev_comp = nullptr;
     // small device scratch for flags / counters
     uint32_t *d_flags = nullptr;  // 64 words
+    // large device scratch that outlives a call (grown on demand, plain cudaMalloc): see ctx_scratch
+    void *scratch = nullptr; size_t scratch_cap = 0;
     // optional per-kernel timing (wgbs_prof_enable): one event pair per launch, aggregated by kernel name
     bool prof = false;
     struct ProfRec { const char *name; cudaEvent_t e0, e1; };
@@ -61,6 +63,9 @@ void prof_end(wgbs_ctx *ctx);
 #define LAUNCH_CHECK() CUDA_TRY(cudaGetLastError())
 
 int wgbs_ctx_activate(wgbs_ctx *ctx);
+// at least nbytes of device memory owned by the context, valid until the next ctx_scratch call on it (calls on one context are
+// serial and stream-ordered, so one call's kernels are done with it before the next call's kernels run)
+int ctx_scratch(wgbs_ctx *ctx, size_t nbytes, void **p);
 // stream-ordered allocation
 int dmalloc(wgbs_ctx *ctx, void **p, size_t nbytes);
 int dfree(wgbs_ctx *ctx, void *p);

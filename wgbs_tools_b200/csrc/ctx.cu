@@ -64,6 +64,7 @@ extern "C" void wgbs_destroy(wgbs_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 2; i++) if (ctx->pin[i]) cudaFreeHost(ctx->pin[i]);
     if (ctx->d_flags) cudaFree(ctx->d_flags);
+    if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
     if (ctx->ev_comp) cudaEventDestroy(ctx->ev_comp);
@@ -138,6 +139,18 @@ extern "C" int wgbs_prof_report(wgbs_ctx *ctx, char *buf, size_t cap) {
 }
 
 extern "C" uint64_t wgbs_launch_count(const wgbs_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int ctx_scratch(wgbs_ctx *ctx, size_t nbytes, void **p) {
+    if (nbytes > ctx->scratch_cap) {
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));              // kernels of earlier calls may still use the old block
+        if (ctx->scratch) { cudaFree(ctx->scratch); ctx->scratch = nullptr; ctx->scratch_cap = 0; }
+        const size_t cap = nbytes + nbytes / 8 + (1u << 20);
+        CUDA_TRY(cudaMalloc(&ctx->scratch, cap));
+        ctx->scratch_cap = cap;
+    }
+    *p = ctx->scratch;
+    return 0;
+}
 
 int dmalloc(wgbs_ctx *ctx, void **p, size_t nbytes) {
     *p = nullptr;

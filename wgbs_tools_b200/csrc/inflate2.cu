@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 1) bgzf_decode_k(const uint8_t
     }
 }
 
-__global__ void __launch_bounds__(RES_WARPS * 32) bgzf_resolve_k(const uint8_t *__restrict__ comp, const BgzfBlock *__restrict__ blocks, uint32_t nblocks, uint32_t block0,
+// (4 CTAs of 8 warps per SM = 64 registers per thread: the ~4 200 blocks of a 1M-read BAM must be ONE wave -- at 78 registers they were two)
+__global__ void __launch_bounds__(RES_WARPS * 32, 4) bgzf_resolve_k(const uint8_t *__restrict__ comp, const BgzfBlock *__restrict__ blocks, uint32_t nblocks, uint32_t block0,
                                                                   uint8_t *out, const dflate2::Token *__restrict__ tok, const uint32_t *__restrict__ ntok,
                                                                   const int32_t *__restrict__ status, unsigned long long *__restrict__ err) {
     __shared__ uint32_t T[1024];
@@ -115,7 +116,12 @@ int bgzf_inflate2_launch(wgbs_ctx *ctx, const uint8_t *d_comp, const BgzfBlock *
     CUDA_TRY(cudaFuncSetAttribute(bgzf_decode_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     Temps T(ctx);
     dflate2::Token *tok; uint32_t *ntok; int32_t *status;
-    RC_TRY(T.alloc(&tok, (size_t)token_slots)); RC_TRY(T.alloc(&ntok, nb)); RC_TRY(T.alloc(&status, nb));
+    // the token lists (~2.7 bytes per inflated byte in the worst case every block is sized for) live in the context's own scratch:
+    // hundreds of MB taken from and returned to the stream-ordered pool on every call made the pool remap memory (6 ms per call)
+    void *sc = nullptr;
+    RC_TRY(ctx_scratch(ctx, (size_t)token_slots * sizeof(dflate2::Token), &sc));
+    tok = (dflate2::Token *)sc;
+    RC_TRY(T.alloc(&ntok, nb)); RC_TRY(T.alloc(&status, nb));
     for (uint32_t c0 = 0; c0 < nb; c0 += CHUNK_BLOCKS) {
         const uint32_t n = nb - c0 < CHUNK_BLOCKS ? nb - c0 : CHUNK_BLOCKS;
         const unsigned grid = (unsigned)std::min<uint32_t>((n + 31) / 32, (uint32_t)ctx->sm_count);

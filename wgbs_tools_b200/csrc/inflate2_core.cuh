@@ -359,6 +359,7 @@ struct Decoder {
 
     // ---- one deflate block header: returns the next state ------------------------------------------------------------------
     WGBS_HD int header() {
+        ring_commit_wait();                    // chunks requested by the last top-up may still be in flight: a header reads on without pacing
         if (last) { if (opos != dst_len) rc = E_SHORT; else if (bitpos() > end_bit) rc = E_INPUT; return ST_DONE; }
         if (bitpos() + 3 > end_bit) { rc = E_INPUT; return ST_DONE; }
         const uint32_t hdr = take(3);
@@ -394,7 +395,11 @@ struct Decoder {
     // iteration i (stores, counters, checks), which then runs while the probe is in flight.  The bit buffer takes the next word by
     // an unconditional OR (stream bits above bc are simply there early; OR-ing them again is harmless), only the count is conditional.
     // The ring must hold BURST * 28 bits beyond the read position (ring_top_up before every call).
+    // (A lone warp issues one instruction every ~3.5 cycles -- each waits for the one before -- so a block takes as long as the
+    // instruction stream of its probes: ~80 instructions per probe here.  Splitting the burst into a lean walk that only records
+    // (entry, bit-buffer word) and an interpreting pass was measured: more instructions in total, 2.8 ms instead of 1.7 ms.)
     WGBS_HD int decode_burst() {
+        if (bc < 32) refill_careful();         // a header may leave fewer bits than one probe consumes (the loop below counts on >= 28)
         uint32_t want_dist = len != 0 ? 1u : 0u;
         bb |= (uint64_t)nw << bc;
         uint32_t e_next = tab_load(want_dist ? dt_off + ((uint32_t)bb & ((1u << DB) - 1)) : (uint32_t)bb & ((1u << LB) - 1));
@@ -448,13 +453,31 @@ constexpr uint32_t OWN_MAX = 16;      // matches up to this length are copied by
 
 // lanes: dflate::WarpLanes / dflate::OneLane / the test's lock-step emulation.  dst: the block's output (literals already in
 // place), payload: the block's deflate payload (stored blocks).  Every lane returns the same verdict.
+// bytes lane `lane` copies of one cooperative match: k = lane, lane + N, ... < ln -- at most 9 of them for the longest match (258)
+template <class L, uint32_t SLOTS>
+WGBS_HD void coop_copy(uint32_t lane, uint8_t *dst, uint32_t p, uint32_t ln, const uint8_t *from, bool wrap, uint32_t d) {
+    // every load before the first store: the bytes of one match make ONE memory round trip (a load-store-load-store loop makes one per 32 bytes)
+    constexpr uint32_t N = (uint32_t)L::N;
+    uint8_t c[SLOTS];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (uint32_t q = 0; q < SLOTS; q++) { const uint32_t k = lane + q * N; if (k < ln) c[q] = from[wrap ? k % d : k]; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (uint32_t q = 0; q < SLOTS; q++) { const uint32_t k = lane + q * N; if (k < ln) dst[p + k] = c[q]; }
+}
 template <class L>
 WGBS_HD int resolve(L lanes, const Token *tok, uint32_t ntok, uint8_t *dst, uint32_t dst_len, const uint8_t *payload) {
     const uint32_t lane = (uint32_t)lanes.id();
-    for (uint32_t t0 = 0; t0 < ntok; t0 += (uint32_t)L::N) {
+    constexpr uint32_t N = (uint32_t)L::N;
+    Token nxt; nxt.x = 0; nxt.y = 0;
+    if (lane < ntok) nxt = tok[lane];
+    for (uint32_t t0 = 0; t0 < ntok; t0 += N) {
         const bool valid = t0 + lane < ntok;
-        Token tk; tk.x = 0; tk.y = 0;
-        if (valid) tk = tok[t0 + lane];
+        const Token tk = nxt;
+        if (t0 + N + lane < ntok) nxt = tok[t0 + N + lane];          // the next batch's tokens travel while this batch is replayed
         const uint32_t at = tk.x & 0xffffu, len = tk.x >> 16;
         const bool stored = (tk.y & TOK_STORED) != 0;
         const uint32_t dist = tk.y & ~TOK_STORED;
@@ -496,19 +519,17 @@ WGBS_HD int resolve(L lanes, const Token *tok, uint32_t ntok, uint8_t *dst, uint
 #endif
                 for (uint32_t k = 0; k < 8; k++) if (k < len) dst[at + k] = b[k];
             }
+            // cooperative copies (long, overlapping, stored): the whole warp on one match at a time
             while (C) {
                 const int i = dflate::lowest_bit(C);
                 C &= C - 1;
                 const uint32_t x = lanes.shfl(tk.x, i), y = lanes.shfl(tk.y, i);
-                const uint32_t p = x & 0xffffu, ln = x >> 16;
-                if (y & TOK_STORED) {
-                    const uint8_t *from = payload + (y & ~TOK_STORED);
-                    for (uint32_t k = lane; k < ln; k += (uint32_t)L::N) dst[p + k] = from[k];
-                } else {
-                    const uint8_t *from = dst + p - y;
-                    if (y >= ln) { for (uint32_t k = lane; k < ln; k += (uint32_t)L::N) dst[p + k] = from[k]; }
-                    else { for (uint32_t k = lane; k < ln; k += (uint32_t)L::N) dst[p + k] = from[k % y]; }
-                }
+                const uint32_t p = x & 0xffffu, ln = x >> 16, d = y & ~TOK_STORED;
+                const bool st = (y & TOK_STORED) != 0, wrap = !st && d < ln;
+                const uint8_t *from = st ? payload + d : dst + p - d;
+                if (ln <= 3 * N) coop_copy<L, 3>(lane, dst, p, ln, from, wrap, d);
+                else if (ln <= 9 * N) coop_copy<L, 9>(lane, dst, p, ln, from, wrap, d);
+                else for (uint32_t k = lane; k < ln; k += N) dst[p + k] = from[wrap ? k % d : k];      // a stored block (or few lanes): plain loop
             }
             lanes.sync();                                            // this round's bytes are visible to the next round's loads
             pending &= ~R;
@@ -533,11 +554,22 @@ WGBS_HD uint32_t crc32_block4(L lanes, const uint8_t *d, uint32_t n, const uint3
     const uint32_t l = (uint32_t)lanes.id();
     const uint32_t a = l * per < n ? l * per : n, b = a + per < n ? a + per : n;
     uint32_t c = 0, i = a;
-    for (; i < b && ((uintptr_t)(d + i) & 3); i++) c = T[(c ^ d[i]) & 0xff] ^ (c >> 8);
-    for (; i + 4 <= b; i += 4) {
-        c ^= *(const uint32_t *)(d + i);
-        c = T[768 + (c & 0xff)] ^ T[512 + ((c >> 8) & 0xff)] ^ T[256 + ((c >> 16) & 0xff)] ^ T[c >> 24];
+    auto word = [&](uint32_t w) { c ^= w; c = T[768 + (c & 0xff)] ^ T[512 + ((c >> 8) & 0xff)] ^ T[256 + ((c >> 16) & 0xff)] ^ T[c >> 24]; };
+    for (; i < b && ((uintptr_t)(d + i) & 15); i++) c = T[(c ^ d[i]) & 0xff] ^ (c >> 8);
+    // 16 bytes per step, loaded one step ahead of the table walk that consumes them
+    if (i + 16 <= b) {
+        const uint32_t *p = (const uint32_t *)(d + i);
+        uint32_t w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3];
+        i += 16;
+        for (; i + 16 <= b; i += 16) {
+            const uint32_t *q = (const uint32_t *)(d + i);
+            const uint32_t v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3];
+            word(w0); word(w1); word(w2); word(w3);
+            w0 = v0; w1 = v1; w2 = v2; w3 = v3;
+        }
+        word(w0); word(w1); word(w2); word(w3);
     }
+    for (; i + 4 <= b; i += 4) word(*(const uint32_t *)(d + i));
     for (; i < b; i++) c = T[(c ^ d[i]) & 0xff] ^ (c >> 8);
     const uint32_t nfull = per ? n / per : 0, rem = per ? n - nfull * per : 0;
     uint32_t op = 0;
