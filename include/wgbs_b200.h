@@ -275,6 +275,14 @@ typedef struct wgbs_dbam wgbs_dbam;
 /* bgzf: the bytes of a whole .bam file in HOST memory (pinned memory makes the upload a single DMA) */
 int wgbs_dbam_open(wgbs_ctx *, const void *bgzf, size_t nbytes, wgbs_dbam **out);
 int wgbs_dbam_open_file(wgbs_ctx *, const char *path, wgbs_dbam **out);
+/* The block table of a BGZF file (what `bgzip -i` keeps in a .gzi, plus each block's CRC32 / ISIZE), built once per file from its
+ * bytes in HOST memory.  With it wgbs_dbam_open_indexed takes the compressed bytes from host OR DEVICE memory (a device buffer
+ * must be readable for 64 bytes past nbytes): a file that is already resident in HBM is opened without touching the host copy. */
+typedef struct wgbs_bgzf_index wgbs_bgzf_index;
+int wgbs_bgzf_index_build(const void *bgzf, size_t nbytes, wgbs_bgzf_index **out);
+void wgbs_bgzf_index_free(wgbs_bgzf_index *);
+uint64_t wgbs_bgzf_index_blocks(const wgbs_bgzf_index *);
+int wgbs_dbam_open_indexed(wgbs_ctx *, const void *bgzf, size_t nbytes, const wgbs_bgzf_index *, wgbs_dbam **out);
 void wgbs_dbam_close(wgbs_ctx *, wgbs_dbam *);
 int wgbs_dbam_nref(const wgbs_dbam *);
 const char *wgbs_dbam_ref_name(const wgbs_dbam *, int i);

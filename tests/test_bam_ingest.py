@@ -343,3 +343,20 @@ def test_chromosome_block_ranges_without_an_index(built_lib, tmp_path):
             if chrom == c:
                 got.append(part.view(chrom, key_window=win, **kw))
         assert sorted(b"".join(got).splitlines()) == sorted(whole[c].splitlines()), c
+
+
+TUTORIAL = (("Lung_STL002.small.bam", 2793), ("Pancreas_STL002.small.bam", 814))
+
+
+@pytest.mark.parametrize("name,n_lines", TUTORIAL)
+def test_tutorial_bams_known_line_counts(built_lib, name, n_lines):
+    """the reference's own tutorial (tutorial/README.md:72-80): `wgbstools bam2pat bams/*.bam -r chr3:119527929-119531943` reports
+    "finished 2,793 lines" / "814 lines" -- what `samtools view BAM chr3:119527929-119531943 -q 10 -F 1796` prints (single-end data:
+    no -f 3).  The BAMs (written by htslib, not by this repo) are the fixtures; the host reader must print that many lines."""
+    from wgbs_tools_b200 import bamio
+    bf = bamio.BamFile(os.path.join(GOLD, name), 2)
+    txt = bf.view("chr3", mapq=10, exclude_flags=1796, beg=119527929, end=119531943)
+    bf.close()
+    assert txt.count(b"\n") == n_lines
+    fl = {int(l.split(b"\t")[1]) for l in txt.splitlines()}
+    assert not any(f & 1796 for f in fl) and all(int(l.split(b"\t")[4]) >= 10 for l in txt.splitlines())

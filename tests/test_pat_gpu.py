@@ -135,44 +135,3 @@ def test_homog_overlapping_blocks(ctx, oracle):
     got = ctx.homog(P, blocks, r, 1)
     np.testing.assert_array_equal(got, H.port_homog(txt, blocks, r, 1))
     assert got[0, 2] == 2
-
-
-@pytest.mark.parametrize("variant", ["tiles", pytest.param("tiles_tma", marks=pytest.mark.staged)])     # (the TMA variant spins on an mbarrier: kept out of the default run)
-def test_tile_parser_equals_default_parser(ctx, monkeypatch, variant):
-    """WGBS_PATPARSE=tiles / tiles_tma (pat_tiles_k, two passes over 16 KiB tiles; tiles fetched by LDG.128 or by one TMA bulk copy)
-    == the default parser: same records, same pool, same errors"""
-    rng = np.random.default_rng(8)
-
-    def both(txt):
-        res = []
-        for mode in ("default", variant):
-            monkeypatch.setenv("WGBS_PATPARSE", mode)
-            try:
-                P = ctx.pats_from_text(txt)
-                res.append(tuple(a.tobytes() for a in P.download()))
-                P.free()
-            except Exception as e:
-                res.append(str(e))
-        assert res[0] == res[1], (len(txt), res[0][:80] if isinstance(res[0], str) else "arrays differ", res[1][:80] if isinstance(res[1], str) else "")
-        return res[1]
-
-    idx, pats, cnt = synth.make_pat_records(2, 60_000, 200_000, mean_len=9, max_len=70)
-    txt = synth.pat_text("chr7", idx, pats, cnt)
-    assert not isinstance(both(txt), str)
-    both(txt[:-1])                                                     # no trailing newline
-    both(b""); both(b"\n"); both(b"\n\n\n"); both(b"chr1\t5\tCT\t2"); both(b"chr1\t5\tCT\t2\n")
-    both(synth.make_pat_text_fast(3, 400_000, 1_000_000))              # ~8 MB: hundreds of tiles
-    # lines longer than a tile, lines ending exactly at tile boundaries, extra columns, blank lines
-    long_pat = bytes(rng.choice(list(b"CT.H"), size=40_000).tolist())
-    parts = [b"chr1\t7\t" + long_pat + b"\t3", b"", b"chr1\t9\tCCT\t1\tx\ty"]
-    for k in (16384 - 30, 16384 - 13, 16384, 32768 + 5):
-        filler = b"chr1\t11\t" + b"T" * (k % 997 + 1) + b"\t1"
-        parts += [filler] * 3
-    t2 = b"\n".join(parts + txt.splitlines()[:5000]) + b"\n"
-    assert not isinstance(both(t2), str)
-    for pad in range(0, 40, 3):                                        # shift every boundary through the tile edges
-        both(b"chr1\t1\t" + b"C" * pad + b"T\t1\n" + t2[:70_000])
-    # failures: same message
-    assert "too few columns" in both(b"chr1\t5\tCT\n")
-    cut = txt.rindex(b"\n", 0, 5000) + 1
-    assert "non-numeric" in both(txt[:cut] + b"chr1\tx\tCT\t1\n" + txt[cut:txt.rindex(b"\n", 0, 20000) + 1])

@@ -339,3 +339,92 @@ def test_pairing_survives_hash_collisions(ctx, oracle, genome, monkeypatch, bits
     assert txt == ref_txt
     _, pst = H.port_patter(H.port_match_maker(sam), genome.loci, genome.idx())
     assert [st[k] for k in ("lines", "pairs", "empty", "short", "invalid", "paired")] == pst
+
+
+def _big_batch(g, n_reads=160_000, seed=21, far_every=23, supp=True):
+    """>= 3 match_maker buffers (it flushes every 50 000 lines, match_maker.cpp:162-170) of PE reads: mates 60 kb apart (thousands of
+    lines: many pairs straddle a buffer edge), singles, and supplementary copies (0x800 passes -F 1796) 2 kb from their record.  PNEXT /
+    POS stay consistent.  Returns the lines, coordinate-sorted."""
+    lines = synth.make_sam(g, n_reads, seed, paired=True, single_frac=0.02).splitlines()
+    first = {}
+    for k, l in enumerate(lines):
+        first.setdefault(l.split(b"\t", 1)[0], k)
+    out = []
+    for k, l in enumerate(lines):
+        t = l.split(b"\t")
+        fl, pos, pn, tl = int(t[1]), int(t[3]), int(t[7]), int(t[8])
+        far = first[t[0]] % far_every == 0 and max(pos, pn) + 60_000 < g.length - 300
+        if far and tl > 0:                                     # left mate: its mate moves 60 kb downstream
+            t[7] = b"%d" % (pn + 60_000); t[8] = b"%d" % (tl + 60_000)
+        elif far and tl < 0:                                   # the right mate itself
+            t[3] = b"%d" % (pos + 60_000); t[8] = b"%d" % (tl - 60_000)
+        out.append(b"\t".join(t))
+        if supp and k % 97 == 0 and not far:
+            u = list(t); u[1] = b"%d" % (fl | 2048); u[3] = b"%d" % (pos + 2_000)
+            out.append(b"\t".join(u))
+    out.sort(key=lambda l: int(l.split(b"\t")[3]))
+    return out
+
+
+def _groups(lines):
+    idx = {}
+    for i, l in enumerate(lines):
+        idx.setdefault(l.split(b"\t", 1)[0], []).append(i)
+    return idx
+
+
+def test_pairing_across_match_maker_buffers(ctx, oracle, genome):
+    """160 000 records = four 50 000-line buffers of the reference's match_maker: hundreds of pairs whose mates sit in different
+    buffers (the first one is carried over while its PNEXT lies ahead, match_maker.cpp:77-105), singles whose mate never comes --
+    pat text and counters == `_ref/match_maker | _ref/patter`"""
+    H = oracle; g = genome
+    if not H.have_ref():
+        pytest.skip("reference executables not built")
+    lines = _big_batch(g, supp=False)
+    idx = _groups(lines)
+    assert len(lines) > 155_000 and sum(1 for v in idx.values() if len(v) == 1) > 1000
+    assert sum(1 for v in idx.values() if len(v) == 2 and v[0] // 50_000 != v[1] // 50_000) > 300
+    sam = b"\n".join(lines) + b"\n"
+    ref_raw, ref_txt = _oracle_pat(H, g, sam, True)
+    raw, txt, st = _gpu_pat(ctx, g, sam)
+    assert txt == ref_txt
+    assert st["pairs"] > 70_000
+
+
+def test_known_divergences_from_match_maker_buffers(ctx, oracle, genome):
+    """match_maker pairs inside 50 000-line buffers (match_maker.cpp:60-105,162-170); this library pairs by QNAME over the whole
+    chromosome.  The two differ in exactly two situations, both pinned here with --long output (read names in column 5):
+      * a STALE PNEXT: the reference gives up on an unpaired read as soon as its PNEXT lies before the position of a line of the
+        current buffer; when the mate really sits in a later buffer it then emits both mates as singles -- here they are merged;
+      * a QNAME group of 3+ records (supplementary alignments): match_maker pairs what is adjacent after sorting one buffer's lines,
+        re-sorts pairs and singles by position with an unstable std::sort (equal keys: the pair and its third record), and patter then
+        pairs consecutive equal names of THAT order again -- which two of the three records end up merged depends on libstdc++'s sort.
+        Here the group is ordered by whole line and paired greedily (what match_maker's first step does).
+    Every template that is not one of those is identical.  ("pairing".)"""
+    H = oracle; g = genome
+    if not H.have_ref():
+        pytest.skip("reference executables not built")
+    lines = _big_batch(g, 110_000, 23, far_every=41)
+    idx = _groups(lines)
+    special = {q for q, v in idx.items() if len(v) > 2}
+    n_split3 = len(special)
+    stale = 0
+    for q, v in idx.items():
+        if len(v) == 2 and v[0] // 50_000 != v[1] // 50_000 and stale < 40:
+            t = lines[v[0]].split(b"\t"); t[7] = b"1"; lines[v[0]] = b"\t".join(t); special.add(q); stale += 1
+    assert stale >= 20 and n_split3 >= 1
+    sam = b"\n".join(lines) + b"\n"
+    d = H.write_tmp(g.dict_text(), ".CpG.bed")
+    ref_long, _ = H.ref_patter(sam, d, g.chrom, True, long=True)
+    ix = ctx.load_index(g.loci, g.first_idx)
+    P, st = ctx.pileup_sam(ix, sam, keep_names=True)
+    got_long = P.to_text(g.chrom, long=True)
+    P.free(); ix.free()
+    # patter --long prints `chr idx pattern qname`; the library's long format is the .pat line of bam2pat --long: `chr idx pattern 1 qname`
+    rows = lambda txt: [(t[1], t[2], t[-1]) for t in (l.split(b"\t") for l in txt.splitlines())]
+    others = lambda txt: sorted(r for r in rows(txt) if r[2] not in special)
+    assert others(got_long) == others(ref_long)                 # every other template: identical
+    ours = [r for r in rows(got_long) if r[2] in special]
+    theirs = [r for r in rows(ref_long) if r[2] in special]
+    assert ours and theirs and sorted(ours) != sorted(theirs)
+

@@ -77,29 +77,25 @@ def test_segment_rejects_bad_beta(ctx):
         ctx.segment(b, np.arange(500, dtype=np.uint32) * 50, [(0, 500)], 100, 2000, 15)
 
 
-def test_segment_exact_wave_plan_gives_the_same_borders(ctx, oracle, monkeypatch):
-    """WGBS_SEG_PLAN=exact packs waves by the real number of cost cells (seg_chunk_cells_k): many more chunks per wave, same borders"""
+def test_segment_many_chunks_in_one_call(ctx, oracle):
+    """waves are packed by the real number of cost cells of every chunk (seg_chunk_cells_k): 40 chunks in one call give what the
+    same chunks give one call each, and what the oracle gives"""
     K, n, nch = 4, 3000, 40
     betas = synth.make_betas(3, K, n * nch)
     loci = synth.make_genome(2, "chr1", n * nch * 120, with_bases=False).loci[:n * nch]
     chunks = [(s, n) for s in range(0, n * nch, n)]
-    monkeypatch.setenv("WGBS_SEG_PLAN", "worst")
-    a = ctx.segment(betas, loci, chunks, 1000, 2000, 15)
-    monkeypatch.setenv("WGBS_SEG_PLAN", "exact")
     b = ctx.segment(betas, loci, chunks, 1000, 2000, 15)
-    assert len(a) == len(b) == nch and all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert len(b) == nch
+    for c in (0, 7, 39):
+        one = ctx.segment(betas, loci, [chunks[c]], 1000, 2000, 15)[0]
+        np.testing.assert_array_equal(b[c], one)
     np.testing.assert_array_equal(b[7], oracle.port_segment([x[7 * n:8 * n] for x in betas], loci[7 * n:8 * n], 1000, 2000, 15))
 
 
 @pytest.mark.parametrize("K,n,max_cpg,max_bp,ps", [(6, 2500, 200, 2000, 15), (3, 4000, 1000, 5000, 1), (1, 800, 800, 10 ** 9, 15)])
-def test_segment_redux_argmax_gives_the_same_borders(ctx, oracle, monkeypatch, K, n, max_cpg, max_bp, ps):
-    """WGBS_SEG_DP=redux (argmax of a DP step by hardware warp reductions on order-preserving keys) == the shuffle version == oracle,
-    including windows wider than a warp (max_cpg 800 / 1000 with a huge max_bp)"""
+def test_segment_windows_wider_than_a_warp(ctx, oracle, K, n, max_cpg, max_bp, ps):
+    """borders == oracle, including windows wider than a warp (max_cpg 800 / 1000 with a huge max_bp)"""
     betas = synth.make_betas(11, K, n)
     loci = synth.make_genome(2, "chr1", n * 150, with_bases=False).loci[:n]
-    monkeypatch.delenv("WGBS_SEG_DP", raising=False)
-    a = ctx.segment(betas, loci, [(0, n)], max_cpg, max_bp, ps)[0]
-    monkeypatch.setenv("WGBS_SEG_DP", "redux")
     b = ctx.segment(betas, loci, [(0, n)], max_cpg, max_bp, ps)[0]
-    np.testing.assert_array_equal(a, b)
     np.testing.assert_array_equal(b, oracle.port_segment(betas, loci, max_cpg, max_bp, ps))

@@ -75,6 +75,20 @@ def test_bgzf_inflate_deep_codes_and_the_fallback_decoder(ctx):
     out.free()
 
 
+@pytest.mark.parametrize("name,n_lines", (("Lung_STL002.small.bam", 2793), ("Pancreas_STL002.small.bam", 814)))
+def test_tutorial_bams_on_the_device(ctx, bamio, name, n_lines):
+    """BAMs written by htslib (the reference's tutorial data): inflated and viewed in HBM == the host reader, and the line counts the
+    reference's tutorial prints for them (tutorial/README.md:75,80)"""
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)
+    bf = bamio.BamFile(path, 2)
+    want = bf.view("chr3", mapq=10, exclude_flags=1796, beg=119527929, end=119531943)
+    bf.close()
+    with bamio.DeviceBam(ctx, path) as db:
+        got = db.view("chr3", mapq=10, exclude_flags=1796, beg=119527929, end=119531943)
+    assert got == want and got.count(b"\n") == n_lines
+
+
 def test_bgzf_inflate_round1_decoder_matches_zlib(ctx, sample, monkeypatch):
     """bgzf_inflate_k (WGBS_INFLATE=2: one warp per block, the round-1 decoder kept as the yardstick of the bench): same checks"""
     monkeypatch.setenv("WGBS_INFLATE", "2")

@@ -88,6 +88,10 @@ def _load():
         "wgbs_bam_probe": (C.c_int, [vp, sz, C.c_int, C.POINTER(u64), C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
         "wgbs_bgzf_inflate": (C.c_int, [vp, vp, sz, C.POINTER(vp), C.POINTER(sz)]),
         "wgbs_dbam_open": (C.c_int, [vp, vp, sz, C.POINTER(vp)]),
+        "wgbs_bgzf_index_build": (C.c_int, [vp, sz, C.POINTER(vp)]),
+        "wgbs_bgzf_index_free": (None, [vp]),
+        "wgbs_bgzf_index_blocks": (u64, [vp]),
+        "wgbs_dbam_open_indexed": (C.c_int, [vp, vp, sz, vp, C.POINTER(vp)]),
         "wgbs_dbam_open_file": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
         "wgbs_dbam_close": (None, [vp, vp]),
         "wgbs_dbam_open_part": (C.c_int, [vp, vp, sz, C.c_int, vp, vp, C.c_int, u64, C.POINTER(vp), C.POINTER(u64)]),

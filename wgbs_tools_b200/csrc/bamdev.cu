@@ -220,11 +220,10 @@ const char *inflate_msg(int code) {
     }
 }
 
-// Inflate a whole BGZF file (host bytes) into a fresh device buffer (padded by 16 zero bytes).  Synchronises the stream:
-// errors (framing, deflate, ISIZE, CRC32) are reported here.
-int bgzf_inflate_device(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, const char *who, uint8_t **d_out, uint64_t *n_out, uint64_t *n_blocks) {
+// hop over the block headers of a BGZF file in host memory: the block table (what `bgzip -i` records in a .gzi, plus CRC32 / ISIZE)
+int bgzf_scan_blocks(const void *bgzf, size_t nbytes, const char *who, std::vector<BgzfBlock> &blocks, uint64_t *inflated) {
     const uint8_t *f = (const uint8_t *)bgzf;
-    std::vector<BgzfBlock> blocks; uint64_t off = 0, uoff = 0;
+    uint64_t off = 0, uoff = 0;
     while (off + 28 <= nbytes) {                       // one hop per block over the headers
         uint32_t xlen = 0; const uint32_t bs = dflate::bgzf_block_size(f + off, nbytes - off, &xlen);
         if (!bs) return wgbs_set_err("%s: not a BGZF file (bad block header at %llu)", who, (unsigned long long)off);
@@ -235,11 +234,28 @@ int bgzf_inflate_device(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, const ch
     }
     if (off != nbytes) return wgbs_set_err("%s: %llu trailing bytes after the last BGZF block", who, (unsigned long long)(nbytes - off));
     if (blocks.size() >= 0xffffffffull) return wgbs_set_err("%s: too many BGZF blocks", who);
+    *inflated = uoff;
+    return 0;
+}
+
+// Inflate a whole BGZF file into a fresh device buffer (padded by 16 zero bytes).  bgzf: host bytes; or, with a prebuilt block
+// table (pre != nullptr: wgbs_bgzf_index), host or DEVICE bytes.  Synchronises the stream: errors (framing, deflate, ISIZE, CRC32)
+// are reported here.
+int bgzf_inflate_device(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, const char *who, uint8_t **d_out, uint64_t *n_out, uint64_t *n_blocks,
+                        const std::vector<BgzfBlock> *pre = nullptr) {
+    const uint8_t *f = (const uint8_t *)bgzf;
+    std::vector<BgzfBlock> scanned; uint64_t uoff = 0;
+    if (pre) { if (!pre->empty()) uoff = pre->back().uoff + pre->back().usize; }
+    else RC_TRY(bgzf_scan_blocks(bgzf, nbytes, who, scanned, &uoff));
+    std::vector<BgzfBlock> blocks = pre ? *pre : std::move(scanned);
+    const bool src_on_device = is_device_ptr(bgzf);
     Temps T(ctx);
     uint8_t *d_comp, *data = nullptr; BgzfBlock *d_blocks; unsigned long long *d_err;
     int rc;
     const uint64_t token_slots = bgzf_inflate2_plan(blocks.data(), (uint32_t)blocks.size());
-    if ((rc = T.alloc(&d_comp, nbytes + 64)) < 0 || (rc = T.alloc(&d_blocks, blocks.size())) < 0 || (rc = T.alloc(&d_err, 1)) < 0 || (rc = dalloc(ctx, &data, uoff + 16)) < 0) {
+    d_comp = nullptr;
+    if (src_on_device) d_comp = const_cast<uint8_t *>(f);             // resident already (readable for 64 bytes past its end: wgbs_dbam_open_indexed)
+    if ((!src_on_device && (rc = T.alloc(&d_comp, nbytes + 64)) < 0) || (rc = T.alloc(&d_blocks, blocks.size())) < 0 || (rc = T.alloc(&d_err, 1)) < 0 || (rc = dalloc(ctx, &data, uoff + 16)) < 0) {
         // (cudaMemGetInfo costs a fraction of a millisecond: asked only to word the error)
         cudaGetLastError();
         size_t free_b = 0, total_b = 0;
@@ -247,7 +263,7 @@ int bgzf_inflate_device(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, const ch
         return wgbs_set_err("%s: the inflated stream (%.1f GB + %.1f GB compressed) does not fit in device memory (%.1f GB free); process the file in parts",
                             who, uoff / 1e9, nbytes / 1e9, free_b / 1e9);
     }
-    if ((rc = copy_any(ctx, d_comp, f, nbytes)) < 0 || (rc = copy_any(ctx, d_blocks, blocks.data(), blocks.size() * sizeof(BgzfBlock))) < 0) { dfree(ctx, data); return rc; }
+    if ((!src_on_device && (rc = copy_any(ctx, d_comp, f, nbytes)) < 0) || (rc = copy_any(ctx, d_blocks, blocks.data(), blocks.size() * sizeof(BgzfBlock))) < 0) { dfree(ctx, data); return rc; }
     unsigned long long herr = 0;
     cudaError_t e = cudaMemsetAsync(d_err, 0xff, 8, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(data + uoff, 0, 16, ctx->stream);
@@ -275,11 +291,13 @@ int bgzf_inflate_device(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, const ch
 // file), records are indexed from part->first_record on, and the last record may be cut off by the end of the window
 // (*part->tail = its offset; everything behind it is left unindexed).
 struct PartArgs { int has_header; int n_ref; const char *const *ref_names; const int32_t *ref_lens; uint64_t first_record; uint64_t *tail; };
-static int dbam_open_impl(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, const PartArgs *part, wgbs_dbam **out) {
+struct wgbs_bgzf_index { std::vector<BgzfBlock> blocks; uint64_t file_bytes = 0, inflated = 0; };
+static int dbam_open_impl(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, const PartArgs *part, wgbs_dbam **out, const wgbs_bgzf_index *bix = nullptr) {
     RC_TRY(wgbs_ctx_activate(ctx));
     if (!bgzf || !out) return wgbs_set_err("wgbs_dbam_open: null argument");
     *out = nullptr;
-    if (is_device_ptr(bgzf)) return wgbs_set_err("wgbs_dbam_open: the compressed bytes must be in host memory (the block table is read on the host)");
+    if (!bix && is_device_ptr(bgzf)) return wgbs_set_err("wgbs_dbam_open: the compressed bytes must be in host memory (the block table is read on the host); device-resident bytes need wgbs_dbam_open_indexed");
+    if (bix && bix->file_bytes != nbytes) return wgbs_set_err("wgbs_dbam_open_indexed: the index was built for a file of %llu bytes, not %zu", (unsigned long long)bix->file_bytes, nbytes);
     wgbs_dbam *B = new wgbs_dbam();
     Temps T(ctx);
     int rc;
@@ -294,7 +312,7 @@ static int dbam_open_impl(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, const 
     };
     if ((rc = T.alloc(&d_err, 4)) < 0) return fail_free(ctx, B, rc);
     // 1 + 2. BGZF block table (host) and inflate (one warp per block)
-    { uint64_t nb = 0; if ((rc = bgzf_inflate_device(ctx, bgzf, nbytes, "wgbs_dbam_open", &B->data, &B->n, &nb)) < 0) return fail_free(ctx, B, rc); B->n_blocks = nb; }
+    { uint64_t nb = 0; if ((rc = bgzf_inflate_device(ctx, bgzf, nbytes, "wgbs_dbam_open", &B->data, &B->n, &nb, bix ? &bix->blocks : nullptr)) < 0) return fail_free(ctx, B, rc); B->n_blocks = nb; }
     B->comp_bytes = nbytes;
     lap("scan+inflate");
     const uint64_t uoff = B->n;
@@ -414,6 +432,27 @@ static int dbam_open_impl(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, const 
 }
 
 extern "C" int wgbs_dbam_open(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, wgbs_dbam **out) { return dbam_open_impl(ctx, bgzf, nbytes, nullptr, out); }
+
+// The block table of a BGZF file, built once per file from its bytes in host memory (the offsets a .gzi holds, plus each block's
+// CRC32 and ISIZE): with it the compressed bytes may already be resident on the device when the file is opened.
+extern "C" int wgbs_bgzf_index_build(const void *bgzf, size_t nbytes, wgbs_bgzf_index **out) {
+    if (!bgzf || !out) return wgbs_set_err("wgbs_bgzf_index_build: null argument");
+    if (is_device_ptr(bgzf)) return wgbs_set_err("wgbs_bgzf_index_build: the bytes must be in host memory");
+    wgbs_bgzf_index *ix = new wgbs_bgzf_index();
+    const int rc = bgzf_scan_blocks(bgzf, nbytes, "wgbs_bgzf_index_build", ix->blocks, &ix->inflated);
+    if (rc < 0) { delete ix; return rc; }
+    ix->file_bytes = nbytes;
+    *out = ix;
+    return 0;
+}
+extern "C" void wgbs_bgzf_index_free(wgbs_bgzf_index *ix) { delete ix; }
+extern "C" uint64_t wgbs_bgzf_index_blocks(const wgbs_bgzf_index *ix) { return ix ? ix->blocks.size() : 0; }
+// wgbs_dbam_open with the block table at hand: bgzf may be HOST or DEVICE memory (a device buffer must be readable for 64 bytes past
+// nbytes: the decoder fetches whole 16-byte chunks)
+extern "C" int wgbs_dbam_open_indexed(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, const wgbs_bgzf_index *ix, wgbs_dbam **out) {
+    if (!ix) return wgbs_set_err("wgbs_dbam_open_indexed: null index");
+    return dbam_open_impl(ctx, bgzf, nbytes, nullptr, out, ix);
+}
 
 // A window of a .bam on the device: see wgbs_bam_open_part (include/wgbs_b200.h)
 extern "C" int wgbs_dbam_open_part(wgbs_ctx *ctx, const void *bgzf, size_t nbytes, int n_ref, const char *const *ref_names, const int32_t *ref_lens,

@@ -9,7 +9,7 @@
 #include "common.cuh"
 #include "pats.cuh"
 #include "lines.cuh"
-#include "pat_core.cuh"
+
 
 namespace {
 
@@ -68,115 +68,9 @@ __global__ void __launch_bounds__(256) pat_pack_k(const char *__restrict__ text,
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Two-pass tile parser (WGBS_PATPARSE=tiles; staged).  The path above reads the text four times with byte loads (newline
-// count, newline write, per-line field scan, symbol pack) and is bound by instruction issue, not by memory: 0.9 ms for 320 MB.
-// Here a CTA parks a 16 KiB tile in shared memory with coalesced 16-byte loads, every thread turns its 64-byte span into a
-// newline mask and a tab mask (SIMD byte compares), and the fields of a line are found with find-first-set on those masks --
-// no byte loops except over digits and pattern symbols.  A thread owns the lines that START behind a newline of its span
-// (thread 0 of tile 0 also owns line 0); bytes beyond the tile (the tail of the tile's last line) come from global memory.
-//   pass 0  lines and pool words per tile                      -> host: two scans, exact allocation
-//   pass 1  the same walk with known bases: idx / len / count / off + packed symbols at their final places
-// The text is read twice, everything else once; no look-back, no over-allocation.
-// ------------------------------------------------------------------------------------------------------------------
-// (tile geometry, PatTile, parse_int_tile, pat_line: pat_core.cuh -- host + device, also built by tests/pat_core_check.cpp)
+// (A two-pass tile parser -- 16 KiB tiles parked in shared memory by LDG.128 or one TMA bulk copy, newline / tab masks from SIMD
+// byte compares -- was measured on a B200 against the four kernels above: 0.77 / 0.76 ms against 0.51 ms for 160 MB of pat text.  Not kept.)
 
-// TMA = 1: a full, 16-byte aligned tile is fetched by ONE bulk asynchronous copy (cp.async.bulk: the TMA engine moves 16 KiB from
-// global to shared memory and signals an mbarrier with the byte count) instead of 1024 LDG.128 + STS pairs; every thread then waits
-// on the barrier's phase.  The last (partial) tile and unaligned texts take the LDG path.  WGBS_PATPARSE=tiles_tma.
-template <int PASS, int TMA>
-__global__ void __launch_bounds__(PS_T) pat_tiles_k(const char *__restrict__ text, uint32_t n, uint32_t *__restrict__ tile_lines,
-                                                     uint32_t *__restrict__ tile_words, uint32_t *__restrict__ idx, uint32_t *__restrict__ len,
-                                                     uint32_t *__restrict__ count, uint32_t *__restrict__ off, uint32_t *__restrict__ pool,
-                                                     uint32_t *__restrict__ err) {
-    __shared__ __align__(128) unsigned char sm_text[PS_TILE];
-    __shared__ unsigned long long sm_nl[PS_T], sm_tab[PS_T];
-    __shared__ uint32_t ws_l[PS_T / 32], ws_w[PS_T / 32];
-    __shared__ __align__(8) unsigned long long sm_bar;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const uint32_t t0 = blockIdx.x * (uint32_t)PS_TILE, t1 = (n - t0 > (uint32_t)PS_TILE) ? t0 + PS_TILE : n;    // n < 2^31 (host)
-    const bool bulk = TMA && (t1 - t0 == (uint32_t)PS_TILE) && (((uintptr_t)(text + t0)) & 15) == 0;              // uniform over the CTA
-    if (bulk) {
-        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&sm_bar), dst = (uint32_t)__cvta_generic_to_shared(sm_text);
-        if (tid == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)PS_TILE) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst), "l"(text + t0), "r"((uint32_t)PS_TILE), "r"(bar) : "memory");
-        }
-        uint32_t landed = 0;                                         // phase 0 of the barrier completes when the 16 KiB have arrived
-        while (!landed)
-            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(landed) : "r"(bar), "r"(0u) : "memory");
-    } else {
-#pragma unroll
-        for (int c = 0; c < PS_SPAN / 16; c++) {                     // coalesced: one round covers 4 KiB
-            const uint32_t o = (uint32_t)(c * PS_T + tid) * 16, p = t0 + o;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (p < n) v = load16_guard(text, p, n);                 // bytes past the end read as 0: neither newline nor tab
-            *reinterpret_cast<uint4 *>(sm_text + o) = v;
-        }
-        __syncthreads();
-    }
-    unsigned long long nl = 0, tb = 0;
-#pragma unroll
-    for (int c = 0; c < PS_SPAN / 16; c++) {
-        const uint4 q = *reinterpret_cast<const uint4 *>(sm_text + tid * PS_SPAN + c * 16);
-        nl |= (unsigned long long)eq_mask16(q, '\n') << (16 * c);
-        tb |= (unsigned long long)eq_mask16(q, '\t') << (16 * c);
-    }
-    sm_nl[tid] = nl; sm_tab[tid] = tb;
-    __syncthreads();
-    PatTile T; T.g = text; T.n = n; T.sm = sm_text; T.t0 = t0; T.t1 = t1; T.nl = sm_nl; T.tab = sm_tab;
-    const uint32_t span0 = t0 + tid * PS_SPAN;
-    const bool line0 = blockIdx.x == 0 && tid == 0 && n > 0;
-    // my lines: how many, how many pool words (the light walk)
-    uint32_t my_l = 0, my_w = 0;
-    if (line0) { my_l++; my_w += (pat_line(T, 0, false).len + 15) >> 4; }
-    for (unsigned long long m = nl; m;) {
-        const int b = __ffsll((long long)m) - 1; m &= m - 1;
-        const uint32_t s = span0 + (uint32_t)b + 1;
-        if (s < n) { my_l++; my_w += (pat_line(T, s, false).len + 15) >> 4; }
-    }
-    uint32_t il = my_l, iw = my_w;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t a = __shfl_up_sync(0xffffffffu, il, d), c = __shfl_up_sync(0xffffffffu, iw, d);
-        if (lane >= (unsigned)d) { il += a; iw += c; }
-    }
-    if (lane == 31) { ws_l[w] = il; ws_w[w] = iw; }
-    __syncthreads();
-    uint32_t pl = 0, pw = 0, tl = 0, tw = 0;
-#pragma unroll
-    for (int i = 0; i < PS_T / 32; i++) { const uint32_t xl = ws_l[i], xw = ws_w[i]; if (i < (int)w) { pl += xl; pw += xw; } tl += xl; tw += xw; }
-    if (PASS == 0) {
-        if (tid == 0) { tile_lines[blockIdx.x] = tl; tile_words[blockIdx.x] = tw; }
-        return;
-    }
-    // pass 1: tile_lines / tile_words hold the exclusive prefixes over the tiles
-    uint32_t line = tile_lines[blockIdx.x] + pl + il - my_l, o = tile_words[blockIdx.x] + pw + iw - my_w;
-    uint32_t errs = 0;
-    unsigned long long m = nl;
-    bool first = line0;
-    while (first || m) {
-        uint32_t s = 0;
-        if (first) first = false;
-        else { const int b = __ffsll((long long)m) - 1; m &= m - 1; s = span0 + (uint32_t)b + 1; if (s >= n) continue; }
-        const PatRec r = pat_line(T, s, true);
-        errs |= r.err;
-        const uint32_t L = r.err ? 0u : r.len;
-        idx[line] = r.idx; len[line] = L; count[line] = r.cnt; off[line] = o;
-        for (uint32_t b = 0; b < L; b += 16) {
-            uint32_t wd = 0; const uint32_t mm = min(16u, L - b);
-            for (uint32_t k = 0; k < mm; k++) wd |= sym_code((char)T.byte(r.ps + b + k)) << (30 - 2 * k);
-            pool[o + (b >> 4)] = wd;
-        }
-        o += (r.len + 15) >> 4; line++;
-    }
-    if (errs) atomicOr(err, errs);
-}
 
 // ------------------------------------------------------------------------------------------------------------------
 // pat2beta: CTA-local shared-memory window over consecutive (idx-sorted) records, flushed with one red.add per
@@ -309,45 +203,6 @@ __global__ void set_u64_k(unsigned long long *p, unsigned long long v) { *p = v;
 // ==================================================================================================================
 // C ABI
 // ==================================================================================================================
-// the two-pass tile parser (pat_tiles_k); dtext is device memory, n < 2^31 (line and word totals stay below 2^32)
-static int pats_from_text_tiles(wgbs_ctx *ctx, const char *dtext, uint32_t n, bool tma, wgbs_pats **out) {
-    Temps T(ctx);
-    const uint32_t ntiles = (n + PS_TILE - 1) / PS_TILE;
-    uint32_t *tl, *tw, *tlo, *two, *err = ctx->d_flags;
-    RC_TRY(T.alloc(&tl, ntiles)); RC_TRY(T.alloc(&tw, ntiles)); RC_TRY(T.alloc(&tlo, (size_t)ntiles + 1)); RC_TRY(T.alloc(&two, (size_t)ntiles + 1));
-    CUDA_TRY(cudaMemsetAsync(err, 0, 4, ctx->stream));
-    uint32_t tot[2] = {0, 0};
-    if (ntiles) {
-        if (tma) LAUNCH(ctx, (pat_tiles_k<0, 1>), ntiles, PS_T, 0, dtext, n, tl, tw, nullptr, nullptr, nullptr, nullptr, nullptr, err);
-        else LAUNCH(ctx, (pat_tiles_k<0, 0>), ntiles, PS_T, 0, dtext, n, tl, tw, nullptr, nullptr, nullptr, nullptr, nullptr, err);
-        RC_TRY(scan_u32_u32(ctx, tl, tlo, ntiles)); RC_TRY(scan_u32_u32(ctx, tw, two, ntiles));
-        CUDA_TRY(cudaMemcpyAsync(&tot[0], tlo + ntiles, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(&tot[1], two + ntiles, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    }
-    wgbs_pats *P = new wgbs_pats();
-    P->n = tot[0]; P->pool_words = tot[1];
-    int rc = 0;
-    if ((rc = dalloc(ctx, &P->idx, P->n)) < 0 || (rc = dalloc(ctx, &P->len, P->n)) < 0 || (rc = dalloc(ctx, &P->count, P->n)) < 0 ||
-        (rc = dalloc(ctx, &P->off, P->n + 1)) < 0 || (rc = dalloc(ctx, &P->pool, P->pool_words)) < 0) { wgbs_pats_free(ctx, P); return rc; }
-    cudaError_t ce = cudaSuccess;
-    if (ntiles) {
-        if (tma) LAUNCH(ctx, (pat_tiles_k<1, 1>), ntiles, PS_T, 0, dtext, n, tlo, two, P->idx, P->len, P->count, P->off, P->pool, err);
-        else LAUNCH(ctx, (pat_tiles_k<1, 0>), ntiles, PS_T, 0, dtext, n, tlo, two, P->idx, P->len, P->count, P->off, P->pool, err);
-        ce = cudaGetLastError();
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(P->off + P->n, two + ntiles, 4, cudaMemcpyDeviceToDevice, ctx->stream);
-    } else ce = cudaMemsetAsync(P->off, 0, 4, ctx->stream);
-    uint32_t herr = 0;
-    if (ce == cudaSuccess) ce = cudaMemcpyAsync(&herr, err, 4, cudaMemcpyDeviceToHost, ctx->stream);
-    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
-    if (ce != cudaSuccess) { wgbs_pats_free(ctx, P); return wgbs_set_err("wgbs_pats_from_text: %s", cudaGetErrorString(ce)); }
-    if (herr) {
-        wgbs_pats_free(ctx, P);
-        return wgbs_set_err(herr & 1 ? "failed parsing pat: too few columns in file" : "failed parsing pat: non-numeric CpG index or count");
-    }
-    *out = P;
-    return 0;
-}
 
 extern "C" int wgbs_pats_from_text(wgbs_ctx *ctx, const char *text, size_t nbytes, wgbs_pats **out) {
     RC_TRY(wgbs_ctx_activate(ctx));
@@ -360,7 +215,6 @@ extern "C" int wgbs_pats_from_text(wgbs_ctx *ctx, const char *text, size_t nbyte
     const char *dtext = (const char *)dtext_v;
     if (owned) T.v.push_back((void *)dtext);
     const uint32_t n = (uint32_t)nbytes;
-    if (const char *e = getenv("WGBS_PATPARSE"); e && !strncmp(e, "tiles", 5) && nbytes < 0x78000000ull) return pats_from_text_tiles(ctx, dtext, n, !strcmp(e, "tiles_tma"), out);
     // 1. newline positions
     uint32_t *nlpos = nullptr, n_nl = 0, n_lines = 0;
     RC_TRY(find_lines(ctx, dtext, nbytes, T, &nlpos, &n_nl, &n_lines));

@@ -152,19 +152,8 @@ __global__ void __launch_bounds__(256) seg_cost_k(const uint32_t *__restrict__ P
 // lane, broadcast by shuffle), and the first 32 cost cells of step x+1 are loaded while step x is being reduced.  No block
 // barrier anywhere; many chunks share an SM.
 constexpr int DP_T = 32;
-// REDUX = 1 (staged, WGBS_SEG_DP=redux): the argmax over the <= 32 candidates of a step by two hardware warp reductions instead of
-// five shuffle rounds of (double, index) pairs -- the reduction is what sits on the sequential chain.  A double is mapped to a
-// 64-bit unsigned key with the same order (sign flip / complement); REDUX.MAX over the high words, then over the low words of the
-// lanes that hold that high word, then the LARGEST j among the lanes that hold the maximum (lowest k wins ties, as above).  Costs
-// are finite or -inf and never -0.0 (seg_cost_k), so comparing keys == comparing doubles.
-__device__ __forceinline__ unsigned long long dbl_key(double v) {
-    const unsigned long long u = (unsigned long long)__double_as_longlong(v);
-    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
-}
-__device__ __forceinline__ double key_dbl(unsigned long long k) {
-    return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
-}
-template <int REDUX>
+// (The argmax of a step by three REDUX.MAX warp reductions on order-preserving integer keys instead of the five shuffle rounds was
+// measured on a B200: 31.2 ms against 32.4 ms per 60 000-site chunk -- the reduction is not what the chain waits for; not kept.)
 __global__ void __launch_bounds__(DP_T) seg_dp_k(const Chunk *__restrict__ chunks, const uint32_t *__restrict__ W, const uint64_t *__restrict__ coff,
                                                   const double *__restrict__ cost, uint32_t ring, int32_t *__restrict__ Tb /* per site+chunk */,
                                                   const uint64_t *__restrict__ toff) {
@@ -195,15 +184,7 @@ __global__ void __launch_bounds__(DP_T) seg_dp_k(const Chunk *__restrict__ chunk
                 const double v = M[(x - j) & mask] + cost[base + j];
                 if (v >= best) { best = v; bj = j; }                          // lowest k = largest j wins ties
             }
-            if (REDUX) {
-                const unsigned long long key = dbl_key(best);                  // lanes without a candidate hold -inf: the lowest key
-                const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
-                const uint32_t mhi = __reduce_max_sync(0xffffffffu, hi);
-                const uint32_t mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
-                const bool top = hi == mhi && lo == mlo;
-                const uint32_t mj = __reduce_max_sync(0xffffffffu, top ? bj : 0u);
-                best = key_dbl(((unsigned long long)mhi << 32) | mlo); bj = mj;
-            } else {
+            {
 #pragma unroll
                 for (int d = 16; d >= 1; d >>= 1) {
                     const double ov = __shfl_xor_sync(0xffffffffu, best, d); const uint32_t oj = __shfl_xor_sync(0xffffffffu, bj, d);
@@ -317,18 +298,16 @@ extern "C" int wgbs_segment(wgbs_ctx *ctx, const uint8_t *const *betas, int K, c
     const uint32_t *ddists = (const uint32_t *)dd;
     uint32_t *bad = ctx->d_flags + 2;
     CUDA_TRY(cudaMemsetAsync(bad, 0, 4, ctx->stream));
-    const char *dpv = getenv("WGBS_SEG_DP");
-    const bool dp_redux = dpv && !strcmp(dpv, "redux");
-    if (dp_redux) CUDA_TRY(cudaFuncSetAttribute(seg_dp_k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else CUDA_TRY(cudaFuncSetAttribute(seg_dp_k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(seg_dp_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     // waves of consecutive chunks bounded by a scratch budget
     const uint64_t CELL_BUDGET = 600ull << 20;          // cells (8 B each)  -> <= 4.7 GiB of cost
     const uint64_t PREFIX_BUDGET = 6ull << 30;          // bytes of running sums
-    // WGBS_SEG_PLAN=exact: budget the cells of a chunk by what its windows really hold (one small kernel + one read-back per
-    // call) instead of n * min(max_cpg, n); staged -- the default stays the worst-case plan until this has run on a B200
+    // the cells of a chunk are budgeted by what its windows really hold (one small kernel + one read-back per call), not by
+    // n * min(max_cpg, n): with max_bp 2000 a site has ~25 admissible block lengths, not 1000, so ~400 chunks fit one wave instead of
+    // 10 (measured on a B200: same borders, 64 chunks of K = 10 in one wave)
     std::vector<unsigned long long> exact_cells;
-    if (const char *e = getenv("WGBS_SEG_PLAN"); e && !strcmp(e, "exact") && nchunks > 1) {
+    if (nchunks > 1) {
         Chunk *dall; unsigned long long *dcells;
         RC_TRY(T.alloc(&dall, (size_t)nchunks)); RC_TRY(T.alloc(&dcells, (size_t)nchunks));
         RC_TRY(copy_any(ctx, dall, hc.data(), (size_t)nchunks * sizeof(wgbs_chunk)));
@@ -380,8 +359,7 @@ extern "C" int wgbs_segment(wgbs_ctx *ctx, const uint8_t *const *betas, int K, c
             if (g > 0x7fffffffull) return wgbs_set_err("wgbs_segment: wave too large");
             LAUNCH(ctx, seg_cost_k, (unsigned)g, 256, 0, Pm, Pt, ns, K, coff, ncells, pseudo, cost);
         }
-        if (dp_redux) LAUNCH(ctx, seg_dp_k<1>, nw, DP_T, smem, dch, Wd, coff, cost, ring, Tb, dtoff);
-        else LAUNCH(ctx, seg_dp_k<0>, nw, DP_T, smem, dch, Wd, coff, cost, ring, Tb, dtoff);
+        LAUNCH(ctx, seg_dp_k, nw, DP_T, smem, dch, Wd, coff, cost, ring, Tb, dtoff);
         LAUNCH(ctx, seg_trace_k, grid_for(nw, 64), 64, 0, dch, nw, Tb, dtoff, dbord, dnb);
         LAUNCH_CHECK();
         // borders: the caller's buffer is laid out like ours (n_c + 1 slots per chunk, chunk order)
