@@ -4,6 +4,8 @@
 
   segment_stitch.npz : reference segment.py chunk solving + merge_df_list/stitch_2_dfs (segment.py:157-165,199-252) with
                        `segment_process` redirected to the oracle's port of `segmentor` (no tabix here), on seeded betas.
+  beta_to_table.json : reference beta_to_table.py (beta2table_generator + dump: get_table :72-107, np.add.reduceat sums, beta2vec, nanmean over
+                       groups, %.{digits}f / NA text) on seeded betas, blocks with NA rows, with and without a groups file.
   homog_host.json    : reference homog.py thresholds strings (homog.py:96-104) and trim_uxm_to_uint8 (homog.py:48-58);
                        utils_wgbs.trim_to_uint8 (utils_wgbs.py:277-290) on edge rows.
 """
@@ -57,6 +59,46 @@ def make_segment():
     print("segment_stitch.npz:", [(c["N"], len(c["merged"])) for c in cases])
 
 
+
+def beta_table_inputs(tmp):
+    """the seeded inputs of the beta_to_table cases, written into directory tmp (the test re-creates them the same way)"""
+    N = 20_000
+    betas = synth.make_betas(31, 5, N)
+    betas[3][:, 1] = np.minimum(betas[3][:, 1], 1)              # a low-coverage sample: many blocks below --min_cov
+    betas[3][:, 0] = np.minimum(betas[3][:, 0], betas[3][:, 1])
+    paths = []
+    for i, b in enumerate(betas):
+        p = os.path.join(tmp, f"s{i}.beta"); b.tofile(p); paths.append(p)
+    blocks = synth.make_blocks(7, 1, N, mean_len=6)[:900]
+    rows = []
+    for k, (a, b) in enumerate(blocks.tolist()):
+        if k % 53 == 5:
+            rows.append(f"chr1\t{1000 + k}\t{1000 + k + 1}\tNA\tNA\n")
+        rows.append(f"chr1\t{10 * a}\t{10 * b}\t{a}\t{b}\n")
+    bp = os.path.join(tmp, "blocks.bed"); open(bp, "w").write("".join(rows))
+    gp = os.path.join(tmp, "groups.csv")
+    open(gp, "w").write("name,group,include\ns0,A,True\ns1,B,True\ns2,A,True\ns3,B,True\ns4,A,False\n")
+    return paths, bp, gp
+
+
+def make_beta_table():
+    import io
+    import tempfile
+    import contextlib
+    import beta_to_table as ref_b2t
+    cases = []
+    with tempfile.TemporaryDirectory() as tmp:
+        paths, bp, gp = beta_table_inputs(tmp)
+        for groups, min_cov, digits, chunk in ((None, 4, 2, 200000), (gp, 4, 2, 300), (gp, 1, 3, 200000), (None, 30, 1, 450)):
+            outp = os.path.join(tmp, "t.tsv")
+            first = True
+            for ch in ref_b2t.beta2table_generator(paths, bp, groups, min_cov, 2, chunk, False):
+                ref_b2t.dump(outp, ch, first, digits); first = False
+            cases.append(dict(groups=bool(groups), min_cov=min_cov, digits=digits, chunk=chunk, text=open(outp).read()))
+    json.dump(cases, open(os.path.join(OUT, "beta_to_table.json"), "w"))
+    print("beta_to_table.json:", [len(c["text"]) for c in cases])
+
+
 def make_homog():
     out = {"rates": {}, "trim_uxm": [], "trim_beta": []}
     for l in range(3, 12):
@@ -91,7 +133,16 @@ def make_tutorial_reads():
     gzip.open(os.path.join(OUT, "tutorial_reads.sam.gz"), "wb").write(b"".join(out))
 
 
+def copy_tutorial_bams():
+    """two of the reference's tutorial BAMs (written by htslib): known line counts in tutorial/README.md:75,80"""
+    import shutil
+    for name in ("Lung_STL002.small.bam", "Pancreas_STL002.small.bam"):
+        shutil.copyfile(f"/root/reference/tutorial/bams/{name}", os.path.join(OUT, name))
+
+
 if __name__ == "__main__":
     make_segment()
     make_homog()
     make_tutorial_reads()
+    copy_tutorial_bams()
+    make_beta_table()

@@ -84,7 +84,7 @@ def test_homog_cli_sorted_and_unsorted_blocks(world):
     lines = synth.blocks_text("chrX", blocks, loci).splitlines(keepends=True)
     for tag, ls in (("sorted", lines), ("shuffled", [lines[i] for i in np.random.default_rng(0).permutation(len(lines))])):
         bp = w["dir"] / f"blocks_{tag}.bed"; bp.write_bytes(b"".join(ls))
-        homog.main([str(pg), "-b", str(bp), "-p", str(w["dir"] / f"hom_{tag}"), "-f", "-l", "3"])
+        homog.main([str(pg), "-b", str(bp), "-p", str(w["dir"] / f"hom_{tag}"), "-f", "-l", "3", "--genome", w["refdir"]])     # (<= 5000 blocks: the cview route)
         got = np.array([l.split(b"\t")[5:8] for l in gzip.open(str(w["dir"] / f"hom_{tag}.uxm.bed.gz")).read().splitlines()], dtype=np.int64)
         bl = np.array([[int(l.split(b"\t")[3]), int(l.split(b"\t")[4])] for l in ls])
         order = np.lexsort((bl[:, 1], bl[:, 0]))
@@ -94,7 +94,7 @@ def test_homog_cli_sorted_and_unsorted_blocks(world):
         if H.have_ref():
             refc = H.ref_homog(w["pat"], str(bp), "0,0.334,0.667,1", 3, sort_blocks=(tag == "shuffled"))
             np.testing.assert_array_equal(got[order] if tag == "shuffled" else got, refc)
-    homog.main([str(pg), "-b", str(w["dir"] / "blocks_sorted.bed"), "-p", str(w["dir"] / "hom_bin"), "-f", "--binary"])
+    homog.main([str(pg), "-b", str(w["dir"] / "blocks_sorted.bed"), "-p", str(w["dir"] / "hom_bin"), "-f", "--binary", "--genome", w["refdir"]])
     assert (w["dir"] / "hom_bin.uxm").stat().st_size == 3 * len(lines)
 
 
@@ -202,3 +202,9 @@ def test_view_cli_beta_and_beta_to_blocks_cli(world, tmp_path):
     bg = (out / "t.bedGraph").read_text().splitlines()
     assert len(bg) == sums.shape[0] and bg[-1].endswith("\t-1\t0")
     t = bg[0].split("\t"); assert t[3] == "%.2f" % (sums[0, 0] / sums[0, 1]) and int(t[4]) == sums[0, 1]
+
+
+def test_beta_to_table_cli_matches_reference_golden(ctx, tmp_path):
+    """`wgbstools beta_to_table` with the per-block sums from wgbs_beta_to_blocks: the text the reference's own beta_to_table.py printed"""
+    from test_host_logic import check_beta_table
+    check_beta_table(ctx, tmp_path)

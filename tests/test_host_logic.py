@@ -162,6 +162,18 @@ def test_csi_index_round_trip_region_queries(tmp_path):
         lo = int(base[c] + rng.integers(0, n)); hi = int(lo + rng.integers(0, (1, 10, 1000, 50_000)[rng.integers(0, 4)]))
         assert csi.read_region(str(p), c, lo, hi, ix) == b"".join(l for cc, i, l in recs if cc == c and lo <= i <= hi), (c, lo, hi)
     assert csi.read_region(str(p), "chr9", 1, 10, ix) == b"" and csi.read_region(str(p), "chr2", 1, 10 ** 9, ix) == full[1]
+    # the same file and index through an INDEPENDENT reader written from the BGZF / CSI / tabix specifications (tests/csi_spec_reader.py:
+    # no code shared with csi.py; htslib's tabix is not available here): structure validates, and region queries agree with the scan
+    import csi_spec_reader as spec
+    assert spec.validate_bgzf(p.read_bytes()) > 3
+    six = spec.Csi(out)
+    assert (six.min_shift, six.depth, six.names) == (12, 9, ["chr1", "chr2", "chrX"])
+    assert (six.format, six.col_seq, six.col_beg, six.col_end, six.meta, six.skip) == (0, 1, 2, 2, ord("#"), 0)       # tabix -b 2 -e 2 (generic format)
+    for _ in range(120):
+        c, n = sizes[rng.integers(0, 3)]
+        lo = int(base[c] + rng.integers(0, n)); hi = int(lo + rng.integers(0, (1, 10, 1000, 50_000)[rng.integers(0, 4)]))
+        assert spec.query(str(p), six, c, lo, hi) == b"".join(l for cc, i, l in recs if cc == c and lo <= i <= hi), (c, lo, hi)
+    assert spec.query(str(p), six, "chrX", 420_001, 424_001) == full[2]
     # hts_reg2bin / reg2bins at this depth: a leaf bin is 4096 sites wide; a range is always inside the bins listed for it
     assert csi.reg2bin(np.array([0]), np.array([1]), 12, 9)[0] == ((1 << 27) - 1) // 7
     for b, e in ((0, 1), (4095, 4097), (5_000_000, 5_000_001), (123, 9_999_999)):
@@ -225,3 +237,47 @@ def test_bench_roofline_object_from_a_profile():
     # a profile whose top kernel has no byte model: the next one with a model is reported
     r2 = bench.build_roofline({"mystery_k": (3, 9.0), **rep}, 3, w, 6554.9, "measured")
     assert r2["kernel"] == "nl_scan_k" and list(r2["breakdown_ms_per_step"])[0] == "mystery_k"
+
+
+def _beta_table_cases(tmp_path):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    # the same seeded inputs the golden script fed to the reference (tests/golden/make_golden.py beta_table_inputs), rebuilt here
+    N = 20_000
+    betas = synth.make_betas(31, 5, N)
+    betas[3][:, 1] = np.minimum(betas[3][:, 1], 1)
+    betas[3][:, 0] = np.minimum(betas[3][:, 0], betas[3][:, 1])
+    paths = []
+    for i, b in enumerate(betas):
+        p = str(tmp_path / f"s{i}.beta"); b.tofile(p); paths.append(p)
+    blocks = synth.make_blocks(7, 1, N, mean_len=6)[:900]
+    rows = []
+    for k, (a, b) in enumerate(blocks.tolist()):
+        if k % 53 == 5:
+            rows.append(f"chr1\t{1000 + k}\t{1000 + k + 1}\tNA\tNA\n")
+        rows.append(f"chr1\t{10 * a}\t{10 * b}\t{a}\t{b}\n")
+    bp = str(tmp_path / "blocks.bed"); open(bp, "w").write("".join(rows))
+    gp = str(tmp_path / "groups.csv")
+    open(gp, "w").write("name,group,include\ns0,A,True\ns1,B,True\ns2,A,True\ns3,B,True\ns4,A,False\n")
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "beta_to_table.json")))
+    return paths, bp, gp, gold
+
+
+def check_beta_table(ctx, tmp_path):
+    from wgbs_tools_b200 import beta_to_table as b2t
+    paths, bp, gp, gold = _beta_table_cases(tmp_path)
+    for c in gold:
+        paths_c = paths if not c["groups"] else paths          # (the groups file leaves s4 out by include == False)
+        txt = b2t.table_text(ctx, bp, paths_c, gp if c["groups"] else None, c["min_cov"], c["digits"], c["chunk"])
+        assert txt == c["text"], (c["groups"], c["min_cov"], c["digits"])
+
+
+def test_beta_to_table_host_logic_matches_reference_golden(tmp_path):
+    """beta_to_table.py (groups file, NA blocks, min_cov, digits, chunked printing) against the text the REFERENCE's beta_to_table.py
+    printed for the same seeded inputs (tests/golden/beta_to_table.json); the per-block sums come from numpy here (no GPU)"""
+    class NumpyCtx:                                             # test stand-in for Context.beta_to_blocks: np.add.reduceat like the reference
+        def beta_to_blocks(self, data, bs, be, out_bits, want_sums=False):
+            c = np.concatenate([np.zeros((1, 2), np.int64), np.cumsum(data.astype(np.int64), axis=0)])
+            sums = c[np.asarray(be) - 1] - c[np.asarray(bs) - 1]
+            return None, sums
+    check_beta_table(NumpyCtx(), tmp_path)

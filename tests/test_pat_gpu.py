@@ -135,3 +135,29 @@ def test_homog_overlapping_blocks(ctx, oracle):
     got = ctx.homog(P, blocks, r, 1)
     np.testing.assert_array_equal(got, H.port_homog(txt, blocks, r, 1))
     assert got[0, 2] == 2
+
+
+def test_collapse_of_very_long_tie_runs(ctx, oracle):
+    """amplicon-like input: 130 000 templates start at ONE CpG with the same first calls and differ further on (one 32-bit sort key,
+    so the whole pile is one run of equal keys): runs longer than 64 are sorted by whole CTAs (fix_long_runs_k), not by one thread's
+    insertion sort; plus many medium runs around the threshold.  Text == `sort -k2,2n -k3,3 | uniq -c | awk`."""
+    H = oracle
+    rng = np.random.default_rng(12)
+    sym = np.frombuffer(b"CT.H", np.uint8)
+    rows = []
+    head = b"CTCTCTCTCTCTCTCT"                                          # 16 symbols: more than the key holds
+    for _ in range(130_000):
+        tail = sym[rng.integers(0, 4, size=int(rng.integers(1, 14)))].tobytes().rstrip(b".") or b"C"
+        rows.append(b"chr1\t5000\t" + head + tail)
+    for site in range(6000, 6400):                                      # runs of 1..130 around the serial / CTA threshold
+        for _ in range(int(rng.integers(1, 131))):
+            tail = sym[rng.integers(0, 4, size=int(rng.integers(1, 9)))].tobytes().rstrip(b".") or b"T"
+            rows.append(b"chr1\t%d\t" % site + head + tail)
+    order = rng.permutation(len(rows))
+    raw3 = b"\n".join(rows[i] for i in order) + b"\n"
+    text4 = b"\n".join(rows[i] + b"\t1" for i in order) + b"\n"
+    P = ctx.pats_from_text(text4)
+    P.collapse()
+    got = P.to_text("chr1")
+    P.free()
+    assert got == H.ref_collapse(raw3) if H.have_ref() else H.port_collapse(raw3)

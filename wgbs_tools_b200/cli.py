@@ -3,7 +3,7 @@ for the four hot-path commands (+ init_genome, which builds the CpG dictionary t
 import importlib
 import sys
 
-COMMANDS = ("bam2pat", "pat2beta", "homog", "segment", "init_genome", "view", "cview", "beta_to_blocks", "index")
+COMMANDS = ("bam2pat", "pat2beta", "homog", "segment", "init_genome", "view", "cview", "beta_to_blocks", "beta_to_table", "index")
 
 
 def main():
