@@ -9,6 +9,8 @@
 //                                                      scheme (segment size SEG bytes), apply the `samtools view` filters
 //                                                      (FLAGEQ: comma list or '-', RG: read group or '-', IVFILE: "beg end"
 //                                                      lines or '-'), print the SAM text; stderr: stats
+//   bamdev_core_check inflate3 FILE.bgzf               every BGZF block through the team decoder (inflate3_core.cuh: teams of 32, 16, 8
+//                                                      lanes in lock step, and one lane) + token replay vs zlib; stderr: chain statistics
 //   bamdev_core_check tables N SEED                    two-level Huffman tables of the two-phase decoder vs a canonical-code walk
 //   bamdev_core_check fmtg N SEED                      fmt_g vs snprintf("%g") on N random floats + edge cases
 //   bamdev_core_check part FILE.bam SEG DEPTH B0 NB FIRST REFS   blocks [B0, B0+NB) as a part of a streamed file (dbam_open_impl, part mode)
@@ -27,6 +29,7 @@
 
 #include "../wgbs_tools_b200/csrc/bam_core.cuh"
 #include "../wgbs_tools_b200/csrc/inflate2_core.cuh"
+#include "../wgbs_tools_b200/csrc/inflate3_core.cuh"
 
 using namespace dflate;
 
@@ -256,6 +259,66 @@ static int cmd_inflate(const char *path, int emu_blocks) {
     return nbad ? 1 : 0;
 }
 
+// ---- the team decoder (inflate3_core.cuh): NL lanes in lock step walk one block, then the token replay of inflate2_core.cuh ----------
+template <int NL>
+static int emu_team3(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usize, uint32_t want_crc, dflate3::TeamStats *stats, bool emu_replay) {
+    static EmuSharedN<NL> sh; static dflate3::TeamMem T;
+    std::vector<dflate2::Token> tok(dflate2::token_cap(usize));
+    int rcs[NL]; uint32_t nts[NL];
+    std::vector<std::thread> th;
+    for (int l = 0; l < NL; l++) th.emplace_back([&, l]() { rcs[l] = dflate3::team_inflate(EmuLanesN<NL>{l, &sh}, &T, src, n, dst, usize, tok.data(), &nts[l], stats); });
+    for (auto &t : th) t.join();
+    for (int l = 1; l < NL; l++) if (rcs[l] != rcs[0] || nts[l] != nts[0]) { fprintf(stderr, "lanes disagree (team decoder, %d lanes)\n", NL); exit(4); }
+    int rc = rcs[0];
+    if (rc == dflate2::E_FALLBACK) { g_fallbacks++; return one_lane2(src, n, dst, usize, want_crc); }
+    if (rc == OK && !emu_replay) rc = dflate2::resolve_bytes(OneLane(), tok.data(), nts[0], dst, usize, src);
+    else if (rc == OK) {                                             // the byte-per-lane replay under the same lock-step emulation (slow: a sample)
+        const uint32_t nt = nts[0];
+        std::vector<std::thread> t2;
+        for (int l = 0; l < NL; l++) t2.emplace_back([&, l]() { rcs[l] = dflate2::resolve_bytes(EmuLanesN<NL>{l, &sh}, tok.data(), nt, dst, usize, src); });
+        for (auto &t : t2) t.join();
+        rc = rcs[0];
+    }
+    if (rc == OK && dflate2::crc32_block4(OneLane(), dst, usize, g_crc4) != want_crc) rc = E_CRC;
+    return rc;
+}
+static int one_team3(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usize, uint32_t want_crc) {
+    static dflate3::TeamMem T;
+    std::vector<dflate2::Token> tok(dflate2::token_cap(usize));
+    uint32_t nt = 0;
+    int rc = dflate3::team_inflate(OneLane(), &T, src, n, dst, usize, tok.data(), &nt);
+    if (rc == dflate2::E_FALLBACK) { g_fallbacks++; return one_lane2(src, n, dst, usize, want_crc); }
+    if (rc == OK) rc = dflate2::resolve_bytes(OneLane(), tok.data(), nt, dst, usize, src);
+    if (rc == OK && dflate2::crc32_block4(OneLane(), dst, usize, g_crc4) != want_crc) rc = E_CRC;
+    return rc;
+}
+static int cmd_inflate3(const char *path) {
+    auto f = slurp(path); uint64_t ut; auto blocks = scan_blocks(f, &ut);
+    size_t nbad = 0; uint64_t bytes = 0;
+    dflate3::TeamStats st32{}, st16{}, st8{};
+    for (size_t i = 0; i < blocks.size(); i++) {
+        const Blk &b = blocks[i];
+        const uint8_t *src = f.data() + b.coff + 12 + b.xlen; const uint32_t n = b.csize - 12 - b.xlen - 8;
+        std::vector<uint8_t> a(b.usize + 1);
+        const uint32_t want = bamcore::ld32(f.data() + b.coff + b.csize - 8);
+        int rz = zlib_inflate(src, n, a.data(), b.usize);
+        if (rz == 0 && (uint32_t)crc32(crc32(0L, Z_NULL, 0), a.data(), b.usize) != want) rz = -1;
+        for (int g : {1, 8, 16, 32}) {
+            std::vector<uint8_t> c(b.usize + 1);
+            const int rc = g == 1 ? one_team3(src, n, c.data(), b.usize, want) : g == 8 ? emu_team3<8>(src, n, c.data(), b.usize, want, &st8, i % 16 == 5)
+                         : g == 16 ? emu_team3<16>(src, n, c.data(), b.usize, want, &st16, false) : emu_team3<32>(src, n, c.data(), b.usize, want, &st32, i < 8 || i % 16 == 0);
+            const bool ok = (rz == 0) == (rc == 0) && (rz != 0 || !memcmp(a.data(), c.data(), b.usize));
+            if (!ok) { nbad++; fprintf(stderr, "block %zu: team decoder (%d lanes): rc %d (zlib %d)\n", i, g, rc, rz); }
+        }
+        bytes += b.usize;
+    }
+    for (auto [g, s] : {std::pair<int, dflate3::TeamStats *>{8, &st8}, {16, &st16}, {32, &st32}})
+        fprintf(stderr, "team %d: deflate blocks %llu lanes started %llu dropped %llu\n", g, (unsigned long long)s->blocks, (unsigned long long)s->lanes_started, (unsigned long long)s->lanes_dropped);
+    fprintf(stderr, "fallbacks %zu\n", g_fallbacks);
+    printf("blocks %zu bytes %llu mismatches %zu\n", blocks.size(), (unsigned long long)bytes, nbad);
+    return nbad ? 1 : 0;
+}
+
 static int cmd_view(const char *path, uint64_t SEG, int depth, int argc, char **argv) {
     auto f = slurp(path); uint64_t n; auto blocks = scan_blocks(f, &n);
     std::vector<uint8_t> d(n + 16, 0);
@@ -420,6 +483,43 @@ static int check_tables(dflate2::Decoder<SH> &D, const uint8_t *ln, int nlen, in
     }
     return 0;
 }
+// the team's table construction (inflate3_core.cuh: team_tables) must leave the SAME arena as Decoder::both_tables: entry by entry
+template <int NL>
+static int check_team_tables(const uint8_t *ln, int nlen, int ndist, dflate2::Decoder<0> &ref, int ref_rc) {
+    static dflate2::HostLane H; static EmuSharedN<NL> sh;
+    for (int i = 0; i < nlen + ndist; i++) H.ln[i] = ln[i];
+    int rcs[NL]; uint32_t dts[NL];
+    if (NL == 1) rcs[0] = dflate3::team_tables(OneLane(), H.mem(), (uint32_t)nlen, (uint32_t)ndist, &dts[0]);
+    else {
+        std::vector<std::thread> th;
+        for (int l = 0; l < NL; l++) th.emplace_back([&, l]() { rcs[l] = dflate3::team_tables(EmuLanesN<NL>{l, &sh}, H.mem(), (uint32_t)nlen, (uint32_t)ndist, &dts[l]); });
+        for (auto &t : th) t.join();
+        for (int l = 1; l < NL; l++) if (rcs[l] != rcs[0] || (rcs[0] == OK && dts[l] != dts[0])) { fprintf(stderr, "team_tables: lanes disagree\n"); return 1; }
+    }
+    if (rcs[0] != ref_rc) { fprintf(stderr, "team_tables (%d lanes): rc %d, one lane %d\n", NL, rcs[0], ref_rc); return 1; }
+    if (ref_rc != OK) return 0;
+    if (dts[0] != ref.dt_off) { fprintf(stderr, "team_tables (%d lanes): distance root at %u, one lane %u\n", NL, dts[0], ref.dt_off); return 1; }
+    // every entry a probe can reach: walk both decoders over all codes (second-level offsets may differ: compare what probes return)
+    for (int which = 0; which < 2; which++) {
+        const int n = which ? ndist : nlen; const uint8_t *l = ln + (which ? nlen : 0);
+        int cnt[16] = {0}, next[16] = {0};
+        for (int i = 0; i < n; i++) cnt[l[i]]++;
+        cnt[0] = 0; int code = 0;
+        for (int b = 1; b <= 15; b++) { code = (code + cnt[b - 1]) << 1; next[b] = code; }
+        dflate2::Decoder<0> D = ref; D.m = H.mem(); D.dt_off = dts[0];
+        for (int sy = 0; sy < n; sy++) {
+            if (!l[sy]) continue;
+            const uint32_t c = (uint32_t)next[l[sy]]++, rev = brev32(c) >> (32 - l[sy]);
+            for (uint32_t hi = 0; hi < 4; hi++) {
+                D.bb = (uint64_t)rev | ((uint64_t)(hi * 0x9e3779b9u) << l[sy]);
+                const uint32_t e = which ? D.probe(D.dt_off, dflate2::DB) : D.probe(0, dflate2::LB);
+                const uint32_t want = which ? dflate2::dist_entry((uint32_t)sy, l[sy]) : dflate2::litlen_entry((uint32_t)sy, l[sy]);
+                if (e != want) { fprintf(stderr, "team table %d (%d lanes) symbol %d len %d: entry %08x, want %08x\n", which, NL, sy, l[sy], e, want); return 1; }
+            }
+        }
+    }
+    return 0;
+}
 static int cmd_tables(long N, unsigned seed) {
     std::mt19937_64 rng(seed); size_t bad = 0, fallbacks = 0;
     static dflate2::HostLane H;
@@ -433,7 +533,12 @@ static int cmd_tables(long N, unsigned seed) {
         random_lengths(rng, nlen, maxl, ln);
         if (ndist >= 2) random_lengths(rng, ndist, maxd, ln + nlen); else ln[nlen] = 1;
         dflate2::Decoder<0> D0; D0.init(H.mem(), dummy, 2, dummy + 8, 0, nullptr);
+        const size_t fb0 = fallbacks;
         bad += check_tables(D0, ln, nlen, ndist, &fallbacks);
+        const int rc0 = fallbacks != fb0 ? dflate2::E_FALLBACK : OK;
+        bad += check_team_tables<1>(ln, nlen, ndist, D0, rc0);
+        if (t % 16 == 0) bad += check_team_tables<32>(ln, nlen, ndist, D0, rc0);
+        if (t % 16 == 8) bad += check_team_tables<8>(ln, nlen, ndist, D0, rc0);
         dflate2::Decoder<5> D5; D5.init(dflate2::warp_mem(base, (uint32_t)(t % 32)), dummy, 2, dummy + 8, 0, nullptr);
         size_t fb5 = 0; bad += check_tables(D5, ln, nlen, ndist, &fb5);
     }
@@ -464,6 +569,7 @@ int main(int argc, char **argv) {
     for (uint32_t i = 0; i < 256; i++) g_crc_table[i] = crc_table_entry(i);
     for (uint32_t k = 0; k < 4; k++) for (uint32_t i = 0; i < 256; i++) g_crc4[k * 256 + i] = dflate2::crc_slice_entry(k, i);
     if (argc >= 3 && !strcmp(argv[1], "inflate")) return cmd_inflate(argv[2], argc > 3 ? atoi(argv[3]) : 0);
+    if (argc >= 3 && !strcmp(argv[1], "inflate3")) return cmd_inflate3(argv[2]);
     if (argc >= 5 && !strcmp(argv[1], "view")) return cmd_view(argv[2], strtoull(argv[3], nullptr, 10), atoi(argv[4]), argc - 5, argv + 5);
     if (argc >= 4 && !strcmp(argv[1], "fmtg")) return cmd_fmtg(atol(argv[2]), (unsigned)atoi(argv[3]));
     if (argc >= 4 && !strcmp(argv[1], "tables")) return cmd_tables(atol(argv[2]), (unsigned)atoi(argv[3]));

@@ -84,6 +84,10 @@ def test_inflate_core_matches_zlib_on_every_block_type(check, sam, tmp_path):
     r = subprocess.run([check, "inflate", str(p), "8"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert f"blocks {len(parts) + len(shifted) + 1} emu 8 " in r.stdout and r.stdout.strip().endswith("mismatches 0")
+    # the team decoder (inflate3_core.cuh: bgzf_team_decode_k): one lane and lock-step teams of 8 / 16 / 32 lanes
+    r = subprocess.run([check, "inflate3", str(p)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert f"blocks {len(parts) + len(shifted) + 1} " in r.stdout and r.stdout.strip().endswith("mismatches 0")
 
 
 def test_inflate_core_rejects_what_zlib_rejects(check, sam, tmp_path, built_lib):
@@ -106,6 +110,8 @@ def test_inflate_core_rejects_what_zlib_rejects(check, sam, tmp_path, built_lib)
     r = subprocess.run([check, "inflate", str(p), "2"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr                            # 0 = no DISAGREEMENT with zlib (+ CRC32 check)
     assert r.stdout.strip().endswith("mismatches 0")
+    r = subprocess.run([check, "inflate3", str(p)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("mismatches 0"), r.stdout + r.stderr      # the team decoder: same verdicts
     # and the verdict on the last three is "reject"
     p2 = tmp_path / "bad3.bgzf"; p2.write_bytes(b"".join(parts[-3:]))
     for i in range(3):

@@ -95,6 +95,15 @@ def test_bgzf_inflate_round1_decoder_matches_zlib(ctx, sample, monkeypatch):
     _inflate_checks(ctx, sample[1])
 
 
+@pytest.mark.parametrize("variant", ("thread", "tokens", "thread,tokens"))
+def test_bgzf_inflate_yardstick_decoders_match_zlib(ctx, sample, monkeypatch, variant):
+    """the decoders the default (team decoder + byte-per-lane replay, inflate3_core.cuh) is measured against: bgzf_decode_k (one thread
+    per block) and the token-per-lane replay -- same checks, plus the deep-code blocks (second-level tables, arena overflow)"""
+    monkeypatch.setenv("WGBS_INFLATE", variant)
+    _inflate_checks(ctx, sample[1])
+    test_bgzf_inflate_deep_codes_and_the_fallback_decoder(ctx)
+
+
 def _inflate_checks(ctx, s):
     from wgbs_tools_b200.patio import BGZF_EOF, bgzf_compress
     rng = np.random.default_rng(1)

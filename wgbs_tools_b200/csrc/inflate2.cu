@@ -9,11 +9,26 @@
 //
 // Stands in for the zlib inflate inside `samtools view` (reference src/python/bam2pat.py:165).
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 #include "bgzf.cuh"
 #include "inflate2_core.cuh"
+#include "inflate3_core.cuh"
 
 namespace {
+
+// slicing-by-4 tables of the CRC-32 (dflate2::crc_slice_entry), built by the compiler and read through L1: bgzf_resolve_k holds no shared
+// memory at all, so its CTAs fit on an SM beside the team decoder's (230 KB) when several batches are in flight
+struct Crc4Table { uint32_t v[1024]; };
+constexpr uint32_t crc_byte_entry_cx(uint32_t i) { uint32_t c = i; for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ 0xEDB88320u : c >> 1; return c; }
+constexpr Crc4Table make_crc4() {
+    Crc4Table t{};
+    for (uint32_t i = 0; i < 256; i++) t.v[i] = crc_byte_entry_cx(i);
+    for (uint32_t k = 1; k < 4; k++) for (uint32_t i = 0; i < 256; i++) t.v[k * 256 + i] = t.v[t.v[(k - 1) * 256 + i] & 0xff] ^ (t.v[(k - 1) * 256 + i] >> 8);
+    return t;
+}
+__device__ const Crc4Table g_crc4 = make_crc4();
 
 constexpr int DEC_WARPS = 4;            // warps per CTA of bgzf_decode_k, DEC_LANES decoding lanes each: 32 blocks per CTA (and SM)
 constexpr int DEC_LANES = 8;            // few lanes per warp: what one lane does rarely (second-level probe, ring word) stalls only 7 others
@@ -50,20 +65,41 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 1) bgzf_decode_k(const uint8_t
     }
 }
 
+// Team decoder (inflate3_core.cuh): S lanes walk ONE block together (spans of its bit stream, verified against each other), TEAM_SLOTS
+// blocks per CTA and SM -- the block's tables and the leader's header decoder in 7.2 KB of shared memory each.
+constexpr int TEAM_SLOTS = 32;
+static_assert(TEAM_SLOTS * sizeof(dflate3::TeamMem) <= 227 * 1024, "the teams of one CTA share one SM's shared memory");
+template <int S>
+__global__ void __launch_bounds__(TEAM_SLOTS * S, 1) bgzf_team_decode_k(const uint8_t *__restrict__ comp, const BgzfBlock *__restrict__ blocks, uint32_t nblocks,
+                                                                        uint8_t *__restrict__ out, dflate2::Token *__restrict__ tok, uint32_t *__restrict__ ntok,
+                                                                        int32_t *__restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t team = threadIdx.x / S;
+    dflate3::TeamMem *T = reinterpret_cast<dflate3::TeamMem *>(smem) + team;
+    for (uint32_t base = blockIdx.x * TEAM_SLOTS; base < nblocks; base += gridDim.x * TEAM_SLOTS) {
+        const uint32_t b = base + team;
+        if (b >= nblocks) continue;                                     // whole teams skip together (collectives name the team's lanes only)
+        const BgzfBlock B = blocks[b];
+        uint32_t nt = 0;
+        const int rc = dflate3::team_inflate(dflate::SubWarp<S>(), T, comp + B.coff, B.clen, out + B.uoff, B.usize, tok + B.tok, &nt);
+        if (threadIdx.x % S == 0) { ntok[b] = nt; status[b] = rc; }
+    }
+}
+
 // (4 CTAs of 8 warps per SM = 64 registers per thread: the ~4 200 blocks of a 1M-read BAM must be ONE wave -- at 78 registers they were two)
+template <bool by_bytes>
 __global__ void __launch_bounds__(RES_WARPS * 32, 4) bgzf_resolve_k(const uint8_t *__restrict__ comp, const BgzfBlock *__restrict__ blocks, uint32_t nblocks, uint32_t block0,
                                                                   uint8_t *out, const dflate2::Token *__restrict__ tok, const uint32_t *__restrict__ ntok,
                                                                   const int32_t *__restrict__ status, unsigned long long *__restrict__ err) {
-    __shared__ uint32_t T[1024];
-    for (uint32_t i = threadIdx.x; i < 1024; i += RES_WARPS * 32) T[i] = dflate2::crc_slice_entry(i >> 8, i & 255);
-    __syncthreads();
+    const uint32_t *__restrict__ T = g_crc4.v;
     const uint32_t b = blockIdx.x * RES_WARPS + (threadIdx.x >> 5);
     if (b >= nblocks) return;                       // whole warps leave together (no block-wide barrier below)
     const BgzfBlock B = blocks[b];
     int rc = status[b];
     if (rc == dflate2::E_FALLBACK) return;          // bgzf_warp_inflate_k decodes this block
     if (rc == dflate2::OK) {
-        rc = dflate2::resolve(dflate::WarpLanes(), tok + B.tok, ntok[b], out + B.uoff, B.usize, comp + B.coff);
+        rc = by_bytes ? dflate2::resolve_bytes(dflate::WarpLanes(), tok + B.tok, ntok[b], out + B.uoff, B.usize, comp + B.coff)
+                      : dflate2::resolve(dflate::WarpLanes(), tok + B.tok, ntok[b], out + B.uoff, B.usize, comp + B.coff);
         __syncwarp();
         if (rc == dflate2::OK && dflate2::crc32_block4(dflate::WarpLanes(), out + B.uoff, B.usize, T) != B.crc) rc = dflate2::E_CRC;
     }
@@ -122,11 +158,20 @@ int bgzf_inflate2_launch(wgbs_ctx *ctx, const uint8_t *d_comp, const BgzfBlock *
     RC_TRY(ctx_scratch(ctx, (size_t)token_slots * sizeof(dflate2::Token), &sc));
     tok = (dflate2::Token *)sc;
     RC_TRY(T.alloc(&ntok, nb)); RC_TRY(T.alloc(&status, nb));
+    static const size_t team_bytes = TEAM_SLOTS * sizeof(dflate3::TeamMem);
+    // WGBS_INFLATE (read per call: tests and probes switch inside one process): "thread" = the thread-per-block decoder (round-2 first design,
+    // 1.74 ms per 1M-read BAM against 0.98 ms for the team decoder on the same B200), "tokens" = the token-per-lane replay; default: team + bytes
+    const char *ev = getenv("WGBS_INFLATE");
+    const bool team = !(ev && strstr(ev, "thread"));
+    if (team) CUDA_TRY(cudaFuncSetAttribute(bgzf_team_decode_k<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)team_bytes));
     for (uint32_t c0 = 0; c0 < nb; c0 += CHUNK_BLOCKS) {
         const uint32_t n = nb - c0 < CHUNK_BLOCKS ? nb - c0 : CHUNK_BLOCKS;
         const unsigned grid = (unsigned)std::min<uint32_t>((n + 31) / 32, (uint32_t)ctx->sm_count);
+        if (team) LAUNCH(ctx, bgzf_team_decode_k<32>, grid, TEAM_SLOTS * 32, team_bytes, d_comp, d_blocks + c0, n, out, tok, ntok + c0, status + c0);
+        else
         LAUNCH(ctx, bgzf_decode_k, grid, DEC_WARPS * 32, smem_bytes, d_comp, d_blocks + c0, n, out, tok, ntok + c0, status + c0);
-        LAUNCH(ctx, bgzf_resolve_k, grid_for(n, RES_WARPS), RES_WARPS * 32, 0, d_comp, d_blocks + c0, n, c0, out, tok, ntok + c0, status + c0, d_err);
+        if (ev && strstr(ev, "tokens")) LAUNCH(ctx, bgzf_resolve_k<false>, grid_for(n, RES_WARPS), RES_WARPS * 32, 0, d_comp, d_blocks + c0, n, c0, out, tok, ntok + c0, status + c0, d_err);
+        else LAUNCH(ctx, bgzf_resolve_k<true>, grid_for(n, RES_WARPS), RES_WARPS * 32, 0, d_comp, d_blocks + c0, n, c0, out, tok, ntok + c0, status + c0, d_err);
         LAUNCH(ctx, bgzf_warp_inflate_k, grid_for(n, OLD_WARPS), OLD_WARPS * 32, 0, d_comp, d_blocks + c0, n, c0, out, status + c0, d_err);
     }
     LAUNCH_CHECK();

@@ -104,7 +104,7 @@ struct HostLane {
     uint32_t tab[ARENA], rg[RING];
     uint16_t bk[32];
     uint8_t ln[320];
-    Mem<0> mem() { Mem<0> m; m.tab = tab; m.rg = rg; m.bk = bk; m.ln = ln; return m; }
+    WGBS_HD Mem<0> mem() { Mem<0> m; m.tab = tab; m.rg = rg; m.bk = bk; m.ln = ln; return m; }
 };
 
 enum : int { ST_HDR = 0 /* at a deflate block header */, ST_DEC = 1 /* inside a Huffman block */, ST_DONE = 2 };
@@ -127,6 +127,8 @@ struct Decoder {
     uint32_t len;                              // pending match length (0: next probe is literal/length)
     uint32_t dt_off;                           // arena offset of the distance root table
     uint32_t tab_sa;                           // shared-memory address of m.tab (device)
+    // team decoder (inflate3_core.cuh): header() stops behind the code lengths; the team builds the tables of ln[0 .. pend_nlen + pend_ndist) together
+    uint16_t defer, pend_nlen, pend_ndist;
 
     static constexpr uint32_t S = (uint32_t)SHIFT;
 
@@ -222,7 +224,7 @@ struct Decoder {
         gw = (const uint32_t *)(payload - mis);
         end_bit = 8 * (mis + clen); nwords = (mis + clen + 3) >> 2;
         dst = out; dst_len = usize; opos = 0; tok = tokens; ntok = 0; nstored = 0;
-        rc = OK; last = false; len = 0; dt_off = 1u << LB;
+        rc = OK; last = false; len = 0; dt_off = 1u << LB; defer = 0; pend_nlen = pend_ndist = 0;
         wp = 0; nw = 0; bb = 0; bc = 0; hi_c = 0;
         seek(8 * mis);
     }
@@ -304,6 +306,7 @@ struct Decoder {
     // (scratch of the table construction: the arena's last words -- 144 for the 288 literal/length symbols, 16 for the other sets)
     // literal/length tables from ln[0 .. nlen), distance tables from ln[nlen .. nlen + ndist)
     WGBS_HD int both_tables(int nlen, int ndist) {
+        if (defer) { pend_nlen = (uint16_t)nlen; pend_ndist = (uint16_t)ndist; return OK; }
         uint32_t cur = 1u << LB;
         int r = build(0, nlen, 0, LB, &cur, ARENA - 144, 0, ARENA - 144);
         if (r) return r;
@@ -530,6 +533,70 @@ WGBS_HD int resolve(L lanes, const Token *tok, uint32_t ntok, uint8_t *dst, uint
                 if (ln <= 3 * N) coop_copy<L, 3>(lane, dst, p, ln, from, wrap, d);
                 else if (ln <= 9 * N) coop_copy<L, 9>(lane, dst, p, ln, from, wrap, d);
                 else for (uint32_t k = lane; k < ln; k += N) dst[p + k] = from[wrap ? k % d : k];      // a stored block (or few lanes): plain loop
+            }
+            lanes.sync();                                            // this round's bytes are visible to the next round's loads
+            pending &= ~R;
+        }
+    }
+    (void)dst_len;
+    return OK;
+}
+
+// ---- phase 2, lane = output BYTE ---------------------------------------------------------------------------------------------------
+// The token-per-lane replay above spends ~65 warp instructions per match (ncu: 292 000 per block, issue-bound with 7 warps per
+// scheduler): every lane copies its own match byte by byte under predicates, whatever the other lanes' lengths.  Here the ready
+// matches of a round are laid end to end (exclusive sum of their lengths) and the lanes take consecutive BYTES of that space: a
+// five-step search over the lanes' offsets (shuffles) finds the byte's token, one load and one store move it.  A round's sources all
+// lie below its first unfinished match and its destinations at or above it, so the bytes of a round are independent of each other.
+template <class L>
+WGBS_HD int resolve_bytes(L lanes, const Token *tok, uint32_t ntok, uint8_t *dst, uint32_t dst_len, const uint8_t *payload) {
+    const uint32_t lane = (uint32_t)lanes.id();
+    constexpr uint32_t N = (uint32_t)L::N;
+    Token nxt; nxt.x = 0; nxt.y = 0;
+    if (lane < ntok) nxt = tok[lane];
+    for (uint32_t t0 = 0; t0 < ntok; t0 += N) {
+        const bool valid = t0 + lane < ntok;
+        const Token tk = nxt;
+        if (t0 + N + lane < ntok) nxt = tok[t0 + N + lane];
+        const uint32_t at = tk.x & 0xffffu, len = valid ? tk.x >> 16 : 0u;
+        const bool stored = (tk.y & TOK_STORED) != 0;
+        const uint32_t dist = tk.y & ~TOK_STORED;
+        const uint32_t src_end = stored ? 0u : at - dist + (len < dist ? len : dist);
+        uint32_t pending = lanes.ballot(valid);
+        while (pending) {
+            const int first = dflate::lowest_bit(pending);
+            const uint32_t hwm = lanes.shfl(at, first);              // everything below is final
+            const bool ready = ((pending >> lane) & 1u) && src_end <= hwm;
+            const uint32_t R = lanes.ballot(ready);
+            const uint32_t l = ready ? len : 0u;
+            uint32_t M = 0;
+            const uint32_t off = lanes.exscan(l, &M, l);             // where this lane's match starts in the round's byte space
+            for (uint32_t j0 = 0; j0 < M; j0 += 2 * N) {
+                uint8_t b[2]; uint32_t p[2]; bool on[2];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (uint32_t u = 0; u < 2; u++) {
+                    const uint32_t j = j0 + u * N + lane;
+                    uint32_t lo = 0;                                 // last lane whose match starts at or before byte j
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                    for (uint32_t step = N / 2; step; step >>= 1) { const uint32_t v = lanes.shfl(off, (int)(lo + step)); if (v <= j) lo += step; }
+                    const uint32_t x = lanes.shfl(tk.x, (int)lo), y = lanes.shfl(tk.y, (int)lo), o = lanes.shfl(off, (int)lo);
+                    const uint32_t r = j - o, a = x & 0xffffu, ln = x >> 16, d = y & ~TOK_STORED;
+                    on[u] = j < M; p[u] = a + r; b[u] = 0;
+                    if (on[u]) {
+                        uint32_t sr = r;                              // a run (dist < len) repeats its first dist bytes
+                        if (d < ln) { sr = 0; if (WGBS_UNLIKELY(d != 1)) sr = r % d; }
+                        const uint8_t *from = (y & TOK_STORED) ? payload + d + r : dst + a - d + sr;
+                        b[u] = *from;
+                    }
+                }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (uint32_t u = 0; u < 2; u++) if (on[u]) dst[p[u]] = b[u];
             }
             lanes.sync();                                            // this round's bytes are visible to the next round's loads
             pending &= ~R;
