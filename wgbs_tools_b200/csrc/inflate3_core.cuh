@@ -73,39 +73,13 @@ struct Walker {
 #endif
     }
     WGBS_HD uint32_t pos() const { return 32 * wp - bc; }
-    // The words behind nw (device): a ring of RING_SLOTS words per lane in the team's shared memory (the header decoder's staging area,
-    // idle while the team walks), slot j of lane l at word j * N + l.  cp.async brings word wp + RING_SLOTS - 1 in while word wp is
-    // taken out: a load into a REGISTER would stall the whole warp at its next refill -- some lane refills in every iteration, and
-    // the scoreboard of the destination register is the warp's (ncu: long_scoreboard 4.85 per issue, 15 % of the samples on the refill).
-    static constexpr uint32_t RING_SLOTS = 4;
-    uint32_t ring_sa, ring_stride;                     // shared-memory address of this lane's slot 0; bytes between its slots
-    WGBS_HD void ring_request(uint32_t i) {            // word i -> slot i % RING_SLOTS, one commit group per word
-#if defined(__CUDA_ARCH__)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" "cp.async.commit_group;\n" ::"r"(ring_sa + (i & (RING_SLOTS - 1)) * ring_stride), "l"(gw + i) : "memory");
-#else
-        (void)i;
-#endif
-    }
-    WGBS_HD uint32_t ring_take(uint32_t i) {           // word i (requested RING_SLOTS - 1 refills ago)
-#if defined(__CUDA_ARCH__)
-        uint32_t v;
-        asm volatile("cp.async.wait_group 2;\n" "ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(ring_sa + (i & (RING_SLOTS - 1)) * ring_stride) : "memory");
-        return v;
-#else
-        return gword(i);
-#endif
-    }
-    WGBS_HD void drain() {                             // nothing requested so far may land in a slot later
-#if defined(__CUDA_ARCH__)
-        asm volatile("cp.async.wait_all;\n" ::: "memory");
-#endif
-    }
+    // (word wp + 1 is loaded straight into nw at every refill.  A per-lane ring in shared memory filled by cp.async -- no register
+    // scoreboard between the request and the next refill -- was measured too: long_scoreboard 4.85 -> 2.43 per issue, but 17 % more
+    // instructions and the same 0.98 ms, profiles/README.md round 2)
     WGBS_HD void seek(uint32_t p) {
         const uint32_t w = p >> 5, s = p & 31;
-        drain();
         bb = ((uint64_t)gword(w) | ((uint64_t)gword(w + 1) << 32)) >> s;
         bc = 64 - s; wp = w + 2; nw = gword(wp);
-        for (uint32_t k = 1; k < RING_SLOTS; k++) ring_request(wp + k);
         flags = 0;
     }
     // walk on until a symbol boundary at or past `stop` (NOPOS: until the end-of-block code).  Sets F_EOB (pos() = the bit after
@@ -130,7 +104,7 @@ struct Walker {
             const uint32_t tot = e & 31, nb = tot - ((e >> 5) & 15), kind = (e >> 9) & 3;
             const uint32_t val = (e >> 16) + (((uint32_t)bb & ((1u << tot) - 1)) >> nb);      // tot <= 28 of the >= 32 valid bits
             bb >>= tot; bc -= tot; rem -= (int32_t)tot;
-            if (bc < 32) { bb |= (uint64_t)nw << bc; bc += 32; wp++; nw = ring_take(wp); ring_request(wp + RING_SLOTS - 1); }
+            if (bc < 32) { bb |= (uint64_t)nw << bc; bc += 32; wp++; nw = gword(wp); }
             const bool base = kind == K_BASE, is_lit = !wd && kind == K_LIT, is_dst = wd && base;
             const uint32_t adv = is_lit ? 1u : (is_dst ? len : 0u);
             bool odd = !(is_lit || base) || tot == 0;
@@ -315,11 +289,9 @@ WGBS_HD int team_inflate(L lanes, TeamMem *T, const uint8_t *payload, uint32_t c
         }
         Walker w;
         w.gw = T->D.gw; w.end_bit = T->D.end_bit;
-        w.tab = T->D.m.tab; w.dt_off = T->D.dt_off; w.tab_sa = 0; w.ring_sa = 0; w.ring_stride = 0;
+        w.tab = T->D.m.tab; w.dt_off = T->D.dt_off; w.tab_sa = 0;
 #if defined(__CUDA_ARCH__)
         w.tab_sa = (uint32_t)__cvta_generic_to_shared(T->D.m.tab);
-        static_assert(Walker::RING_SLOTS * S <= dflate2::RING, "the lanes' rings share the header decoder's staging area");
-        w.ring_sa = (uint32_t)__cvta_generic_to_shared(T->D.m.rg + lane); w.ring_stride = S * 4;
 #endif
         w.dst = dst; w.dst_len = usize; w.tok = tok; w.rc = OK; w.out = 0; w.ntk = 0; w.flags = F_END;
         const uint32_t h = T->h, opos0 = T->D.opos, ntok0 = T->D.ntok;
@@ -376,7 +348,6 @@ WGBS_HD int team_inflate(L lanes, TeamMem *T, const uint8_t *payload, uint32_t c
         const uint32_t c_out = alive ? w.out : 0u, c_tok = alive ? w.ntk : 0u;
         const uint32_t obase = lanes.exscan(c_out, &tot_out, c_out), tbase = lanes.exscan(c_tok, &tot_tok, c_tok);
         int rc = OK;
-        w.drain();
         if (!(tf & F_EOB)) rc = (tf & F_END) ? E_INPUT : E_SYMBOL;
         else if (eob_end > w.end_bit) rc = E_INPUT;
         else if (tot_out > usize - opos0) rc = E_OUTPUT;
@@ -390,7 +361,6 @@ WGBS_HD int team_inflate(L lanes, TeamMem *T, const uint8_t *payload, uint32_t c
                 w.run_until<true>(stop);
                 bad = lane == term ? w.flags != F_EOB : (w.flags != 0 || w.pos() != stop);
             }
-            w.drain();                                                  // the leader's header decoder gets its staging area back
             const uint32_t bm = lanes.ballot(bad);
             if (bm) { const int f = dflate::lowest_bit(bm); rc = (int)lanes.shfl((uint32_t)(w.rc ? w.rc : E_SYMBOL), f); }
         }
