@@ -281,3 +281,57 @@ def test_beta_to_table_host_logic_matches_reference_golden(tmp_path):
             sums = c[np.asarray(be) - 1] - c[np.asarray(bs) - 1]
             return None, sums
     check_beta_table(NumpyCtx(), tmp_path)
+
+
+def test_pat_shards_of_a_bgzf_file_partition_its_lines(tmp_path, monkeypatch):
+    """patio.read_pat_device_shard (pat2beta / homog under torchrun): every rank inflates only its run of BGZF blocks (+ one neighbour
+    on each side) and owns the lines that START inside its run -- the shares must partition the file's lines for any world size,
+    also when a block boundary falls exactly on a line end.  The device is stood in for by host memory (no GPU here)."""
+    import ctypes
+    import gzip
+
+    import numpy as np
+
+    from wgbs_tools_b200 import _lib, patio, synth
+
+    class FakeBuf:
+        def __init__(self, data):
+            self.a = np.frombuffer(bytearray(data), np.uint8); self.ptr = self.a.ctypes.data; self.nbytes = self.a.size
+
+        def __len__(self):
+            return self.nbytes
+
+        def free(self):
+            pass
+
+    class FakeCtx:
+        h = None
+
+        def bgzf_inflate(self, raw):
+            return FakeBuf(gzip.decompress(raw))
+
+    monkeypatch.setattr(_lib.lib, "wgbs_memcpy", lambda h, dst, src, n: ctypes.memmove(dst, src, n) and 0)
+    idx, pats, cnt = synth.make_pat_records(3, 4000, 9000)
+    text = synth.pat_text("chr1", idx, pats, cnt)
+    lines = text.splitlines(keepends=True)
+    # blocks of 4096 bytes, and one layout whose block ends coincide with line ends
+    layouts = [[text[i:i + 4096] for i in range(0, len(text), 4096)], []]
+    acc = b""
+    for l in lines:
+        acc += l
+        if len(acc) > 3000:
+            layouts[1].append(acc); acc = b""
+    if acc:
+        layouts[1].append(acc)
+    for k, chunks in enumerate(layouts):
+        p = tmp_path / f"t{k}.pat.gz"
+        p.write_bytes(b"".join(patio._bgzf_block(c) for c in chunks) + patio.BGZF_EOF)
+        for world in (1, 2, 3, 5, 16):
+            got = []
+            for rank in range(world):
+                buf, view = patio.read_pat_device_shard(FakeCtx(), str(p), rank, world)
+                got.append(ctypes.string_at(view.ptr, view.nbytes))
+            assert b"".join(got) == text, (k, world)
+            assert all(g == b"" or g.endswith(b"\n") for g in got)
+    q = tmp_path / "plain.pat.gz"; q.write_bytes(gzip.compress(text))
+    assert patio.read_pat_device_shard(FakeCtx(), str(q), 0, 2) is None          # plain gzip: the caller shards the host text

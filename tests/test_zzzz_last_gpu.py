@@ -33,23 +33,37 @@ def test_pat_files_larger_than_one_call_go_piece_by_piece(ctx, tmp_path, monkeyp
     assert len(set(out.values())) == 1 and any(out[("0", "host")][0])
 
 
-def test_direct_route_hands_mm_ml_batches_to_the_text_route(ctx, oracle, built_lib, monkeypatch):
-    """WGBS_DBAM_DIRECT=1 on a BAM whose first passing record carries an MM tag: wgbs_pileup_dbam must notice (bam_records_k) and
-    take the text route (MM/ML tags are parsed from text): same templates as with the direct route off, and == the oracle"""
+def test_direct_route_reads_mm_ml_tags_in_place(ctx, oracle, built_lib, monkeypatch):
+    """MM/ML batches over the direct route (bam_np_tags_k: the MM:Z string and the ML:B:C array are read where they stand in the
+    inflated stream; np.cu reads binary CIGARs, 4-bit bases and uint8 ML values): same templates / counters as the text route
+    (view -> SAM text -> tokenizer) and == the oracle (patter --nanopore), for auto-detected and forced --nanopore, several option
+    sets, and hand-built odd tags: legacy Mm / Ml names, two MM tags (the last one counts), ML of another subtype (ignored), no ML,
+    no tags at all, an empty ML array, tags in front of and behind others, SEQ '*'"""
     from wgbs_tools_b200 import bamio
     H = oracle
     g = synth.make_genome(7, "chrT", 400_000)
     sam = synth.make_np_sam(g, 3_000, 9)
-    ix = ctx.load_index(g.loci, g.first_idx)
-    res = []
-    with bamio.DeviceBam.from_bytes(ctx, bamio.sam_to_bam(sam, [("chrT", g.length)])) as db:
-        for direct in ("0", "1"):
-            monkeypatch.setenv("WGBS_DBAM_DIRECT", direct)
-            P, st = db.pileup(ix, "chrT")
-            P.collapse()
-            res.append((P.to_text("chrT"), {k: st[k] for k in ("lines", "pairs", "empty", "short", "invalid", "paired", "nanopore", "templates")}))
-            P.free()
-    ix.free()
-    assert res[0] == res[1] and res[0][1]["nanopore"] == 1 and res[0][1]["templates"] > 1000
-    pout, pst = H.port_patter(sam, g.loci, g.idx(), nanopore=True)
-    assert res[1][0] == H.port_collapse(pout)
+    seq = g.bases[1000:1060].tobytes()
+    odd = [b"MM:Z:C+m?,0,1;\tML:B:C,250,3", b"Mm:Z:C+m.,1;\tMl:B:C,200", b"XA:i:5\tMM:Z:C+h?,0;\tXB:Z:abc\tML:B:C,255\tXC:B:s,1,2", b"MM:Z:C+m?,5;\tMM:Z:C+m?,0;\tML:B:C,9",
+           b"MM:Z:C+m?,0;\tML:B:c,100", b"MM:Z:C+m?,0;", b"XZ:Z:none", b"MM:Z:C+m?,0;\tML:B:S,300", b"MM:Z:C+m?,0,0;C+h?,0,0;\tML:B:C,1,2,3,4", b"MM:Z:C+C?,0;\tML:B:C,77",
+           b"MM:Z:C+m?;\tML:B:C", b"ML:B:C,5\tMM:Z:C+m.,0;"]
+    extra = b"".join(b"odd%d\t%d\tchrT\t1001\t60\t60M\t*\t0\t0\t%s\t*\t%s\n" % (k, 16 * (k & 1), seq, t) for k, t in enumerate(odd))
+    extra += b"star\t0\tchrT\t1001\t60\t60M\t*\t0\t0\t*\t*\tMM:Z:C+m?,0;\tML:B:C,200\n"
+    first = sam[:sam.index(b"\n") + 1]
+    for text, force in ((sam, False), (first + extra + sam[len(first):], False), (extra, True)):
+        lines = sorted(text.splitlines(keepends=True), key=lambda l: int(l.split(b"\t")[3]))
+        text = b"".join(lines)
+        ix = ctx.load_index(g.loci, g.first_idx)
+        with bamio.DeviceBam.from_bytes(ctx, bamio.sam_to_bam(text, [("chrT", g.length)])) as db:
+            for kw in (dict(), dict(np_thresh=0.8, cpc_call="H"), dict(combine_mods=True, clip=3)):
+                res = []
+                for direct in ("0", "1"):
+                    monkeypatch.setenv("WGBS_DBAM_DIRECT", direct)
+                    P, st = db.pileup(ix, "chrT", nanopore=force, **kw)
+                    P.collapse()
+                    res.append((P.to_text("chrT"), {k: st[k] for k in ("lines", "pairs", "empty", "short", "invalid", "paired", "nanopore", "templates")}))
+                    P.free()
+                assert res[0] == res[1] and res[0][1]["nanopore"] == 1, (force, kw, res[0][1], res[1][1])
+                pout, pst = H.port_patter(text, g.loci, g.idx(), nanopore=True, **kw)
+                assert res[1][0] == H.port_collapse(pout), (force, kw)
+        ix.free()

@@ -33,6 +33,9 @@ def main():
             # wall clock of the command's own work: the process group (under torchrun) exists before the clock starts
             from . import dist as wd
             rank, world, _ = wd.init_from_env()
+            if world > 1:
+                import torch.distributed as dist
+                dist.barrier()                                      # NCCL builds its communicator at the first collective: not the command's work
             t0 = time.perf_counter()
             mod.main(sys.argv[2:])
             if world > 1:

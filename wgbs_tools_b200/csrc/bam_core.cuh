@@ -151,6 +151,31 @@ WGBS_HD const uint8_t *find_z_tag(const uint8_t *t, const uint8_t *end, char a, 
     return nullptr;
 }
 
+// the tags `patter --nanopore` reads (ont.cpp:418-438 get_np_tags, on SAM text: the LAST "MM:Z:" / "Mm:Z:" field and the LAST
+// "ML:B:C" / "Ml:B:C" field): *mm = the Z string (mm_len bytes, no NUL), *ml = the uint8 values (ml_cnt of them); nullptr when absent
+// or when the tag area is malformed
+WGBS_HD void find_np_tags(const uint8_t *t, const uint8_t *end, const uint8_t **mm, uint32_t *mm_len, const uint8_t **ml, uint32_t *ml_cnt) {
+    *mm = nullptr; *ml = nullptr; *mm_len = 0; *ml_cnt = 0;
+    while (t + 3 <= end) {
+        const char a = (char)t[0], b = (char)t[1], ty = (char)t[2]; t += 3;
+        if (ty == 'A' || ty == 'c' || ty == 'C') t += 1;
+        else if (ty == 's' || ty == 'S') t += 2;
+        else if (ty == 'i' || ty == 'I' || ty == 'f') t += 4;
+        else if (ty == 'Z' || ty == 'H') {
+            const uint8_t *z = t; while (t < end && *t) t++;
+            if (ty == 'Z' && a == 'M' && (b == 'M' || b == 'm')) { *mm = z; *mm_len = (uint32_t)(t - z); }
+            t++;
+        } else if (ty == 'B') {
+            if (t + 5 > end) return;
+            const char sub = (char)t[0]; const uint32_t cnt = ld32(t + 1); t += 5;
+            const uint32_t w = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : (sub == 'i' || sub == 'I' || sub == 'f') ? 4 : 0;
+            if (!w || (uint64_t)cnt * w > (uint64_t)(end - t)) return;
+            if (sub == 'C' && a == 'M' && (b == 'L' || b == 'l')) { *ml = t; *ml_cnt = cnt; }
+            t += (uint64_t)cnt * w;
+        } else return;
+    }
+}
+
 WGBS_HD bool passes(const Rec &R, const ViewParams &V) {
     if (V.refid >= 0 && R.refid != V.refid) return false;
     if ((int32_t)R.mapq < V.min_mapq || ((int32_t)R.flag & V.exclude_flags)) return false;

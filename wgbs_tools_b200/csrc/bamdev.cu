@@ -180,6 +180,18 @@ __global__ void __launch_bounds__(256) bam_records_k(const uint8_t *__restrict__
     }
 }
 
+// MM/ML mode of the direct route: where the MM:Z string and the ML:B:C values of every passing record stand in the inflated stream
+// (what the SAM tokenizer records as spans of its text, sam.cu tag_kind); ml_len = number of values + 1, 0 = no ML tag (np.cu)
+__global__ void __launch_bounds__(256) bam_np_tags_k(const uint8_t *__restrict__ data, const uint64_t *__restrict__ rec_abs, uint32_t n, uint64_t base, ReadBatch rb) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    Rec R; R.load(data + rec_abs[k]);
+    const uint8_t *mm, *ml; uint32_t mm_len, ml_cnt;
+    find_np_tags(R.tags(), R.end(), &mm, &mm_len, &ml, &ml_cnt);
+    rb.mm_off[k] = mm ? (uint32_t)(mm - data - base) : 0u; rb.mm_len[k] = mm ? mm_len : 0u;
+    rb.ml_off[k] = ml ? (uint32_t)(ml - data - base) : 0u; rb.ml_len[k] = ml ? ml_cnt + 1 : 0u;
+}
+
 __global__ void __launch_bounds__(128) side_len_k(BamSide S, const uint32_t *__restrict__ ids, uint32_t m, uint32_t *__restrict__ len) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;
@@ -644,10 +656,10 @@ int pileup_records(wgbs_ctx *ctx, const wgbs_index *ix, const ReadBatch &rb, con
                    uint64_t *stats_out, int32_t *mbias_out);      // pileup.cu
 
 // The direct route: filters -> descriptors of the passing records (no SAM text is formatted or tokenized); the pileup kernels
-// read binary CIGARs and 4-bit bases in place.  Returns 1 when the batch needs the text route (MM/ML mode), 0 when done.
+// read binary CIGARs, 4-bit bases and (MM/ML mode) the MM string / ML array in place.  Returns 1 when the batch needs the text route
+// (a window of the stream wider than 32-bit offsets), 0 when done.
 static int pileup_dbam_direct(wgbs_ctx *ctx, const wgbs_index *ix, const wgbs_dbam *B, const wgbs_view_opts *vo, const wgbs_pileup_opts *opts,
                               wgbs_pats **out, uint64_t *stats, int32_t *mbias) {
-    if (opts->nanopore) return 1;
     if (vo->n_flag_eq < 0 || vo->n_flag_eq > 4) return wgbs_set_err("wgbs_pileup_dbam: n_flag_eq must be 0..4");
     if (vo->n_iv && (!vo->iv_beg || !vo->iv_end)) return wgbs_set_err("wgbs_pileup_dbam: interval list is null");
     if (vo->n_iv && (is_device_ptr(vo->iv_beg) || is_device_ptr(vo->iv_end))) return wgbs_set_err("wgbs_pileup_dbam: interval lists must be host arrays");
@@ -717,7 +729,10 @@ static int pileup_dbam_direct(wgbs_ctx *ctx, const wgbs_index *ix, const wgbs_db
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         LAUNCH_CHECK();
     }
-    if (mm) return 1;                                            // first record has an MM tag: MM/ML mode, text route
+    if (mm || opts->nanopore) {                                  // MM/ML mode (forced, or the first record has an MM tag: patter.cpp:337-338)
+        RC_TRY(T.alloc(&rb.mm_off, n)); RC_TRY(T.alloc(&rb.mm_len, n)); RC_TRY(T.alloc(&rb.ml_off, n)); RC_TRY(T.alloc(&rb.ml_len, n));
+        if (n) { LAUNCH(ctx, bam_np_tags_k, grid_for(n, 256), 256, 0, B->data, rec_abs, n, base, rb); LAUNCH_CHECK(); }
+    }
     BamSide side{B->data, rec_abs, (int32_t)B->ref_names.size(), B->d_name_off, B->d_names, B->d_ref_lens};
     rb.side = &side;
     RC_TRY(pileup_records(ctx, ix, rb, opts, T, out, stats, mbias));
@@ -725,8 +740,7 @@ static int pileup_dbam_direct(wgbs_ctx *ctx, const wgbs_index *ix, const wgbs_db
 }
 
 // `samtools view ... | [match_maker |] patter ...` without leaving the device.  Direct route (WGBS_DBAM_DIRECT=1, or the
-// default below): BAM records feed the pileup kernels as they are.  Text route: wgbs_dbam_view + wgbs_pileup_sam_mbias (always
-// used for MM/ML data, whose tag parsing is textual).
+// default below): BAM records feed the pileup kernels as they are.  Text route: wgbs_dbam_view + wgbs_pileup_sam_mbias.
 #ifndef WGBS_DBAM_DIRECT_DEFAULT
 #define WGBS_DBAM_DIRECT_DEFAULT 1      // measured (round 1 driver run): 7.08 ms vs 8.30 ms per 1M-read step, identical outputs
 #endif

@@ -48,10 +48,13 @@ struct Section {
     uint32_t dp, de;            // delta list text
     uint32_t nr;                // number of deltas
     bool has_ml; uint32_t mlp, mle; uint32_t ml_base;   // ML values text; this section's values start at index ml_base
+    bool ml_bin;                // BAM flavour: the values are the bytes of the B:C array [mlp, mle), not decimal text
 };
 
-__device__ Section parse_section(const char *__restrict__ t, uint32_t mm, uint32_t mm_len, uint32_t ml, uint32_t ml_len, char mod) {
-    Section s; s.found = false; s.dot = false; s.bad = false; s.dp = s.de = 0; s.nr = 0; s.has_ml = false; s.mlp = s.mle = 0; s.ml_base = 0;
+// BAM flavour (direct route, bamdev.cu bam_np_tags_k): mm = the Z string as it stands in the record (the same bytes SAM text shows
+// behind "MM:Z:"), ml = the uint8 values of the B:C array, ml_len = their number + 1 (0: no ML tag)
+__device__ Section parse_section(const char *__restrict__ t, uint32_t mm, uint32_t mm_len, uint32_t ml, uint32_t ml_len, char mod, bool bam) {
+    Section s; s.ml_bin = bam; s.found = false; s.dot = false; s.bad = false; s.dp = s.de = 0; s.nr = 0; s.has_ml = false; s.mlp = s.mle = 0; s.ml_base = 0;
     if (mm_len == 0) return s;                                   // no MM tag -> get_np_tags false -> empty lists
     const uint32_t e = mm + mm_len;
     uint32_t st = mm, pos = 0;
@@ -67,8 +70,8 @@ __device__ Section parse_section(const char *__restrict__ t, uint32_t mm, uint32
     s.dp = after_comma(t, s.dp, s.de);
     s.nr = count_ints(t, s.dp, s.de);
     if (ml_len == 0) return s;                                    // no ML: every listed base has ML 255 (ont.cpp:292-294)
-    const uint32_t vp = after_comma(t, ml, ml + ml_len), ve = ml + ml_len;
-    const uint32_t total = count_ints(t, vp, ve);
+    const uint32_t vp = bam ? ml : after_comma(t, ml, ml + ml_len), ve = bam ? ml + ml_len - 1 : ml + ml_len;
+    const uint32_t total = bam ? ml_len - 1 : count_ints(t, vp, ve);
     if (s.nr == 0) return s;                                      // ML_str = "" (ont.cpp:398-401)
     if ((total % s.nr != 0) && total > 0) { s.bad = true; return s; }          // :403-407
     s.has_ml = true; s.mlp = vp; s.mle = ve;
@@ -79,17 +82,20 @@ __device__ Section parse_section(const char *__restrict__ t, uint32_t mm, uint32
 
 // forward walker over one section: absolute C ordinals (pos += delta; ordinal = pos++) with their ML values
 struct ModWalk {
-    const char *t; uint32_t dp, de, mlp, mle; bool has_ml; uint32_t left; int64_t pos; int64_t next; int32_t ml; bool valid;
+    const char *t; uint32_t dp, de, mlp, mle; bool has_ml, ml_bin; uint32_t left; int64_t pos; int64_t next; int32_t ml; bool valid;
     __device__ void init(const char *text, const Section &s) {
-        t = text; dp = s.dp; de = s.de; has_ml = s.has_ml; mlp = s.mlp; mle = s.mle; left = s.found && !s.bad ? s.nr : 0; pos = 0; valid = false; ml = 255; next = -1;
-        if (has_ml) { int32_t v; for (uint32_t k = 0; k < s.ml_base; k++) next_int(t, mlp, mle, &v); }
+        t = text; dp = s.dp; de = s.de; has_ml = s.has_ml; ml_bin = s.ml_bin; mlp = s.mlp; mle = s.mle; left = s.found && !s.bad ? s.nr : 0; pos = 0; valid = false; ml = 255; next = -1;
+        if (has_ml && ml_bin) mlp += s.ml_base;
+        else if (has_ml) { int32_t v; for (uint32_t k = 0; k < s.ml_base; k++) next_int(t, mlp, mle, &v); }
         step();
     }
     __device__ void step() {
         if (!left) { valid = false; return; }
         int32_t d = 0; next_int(t, dp, de, &d);
         pos += d; next = pos++; left--;
-        ml = 255; if (has_ml) { int32_t v = 0; next_int(t, mlp, mle, &v); ml = v; }
+        ml = 255;
+        if (has_ml && ml_bin) { ml = mlp < mle ? (int32_t)(uint8_t)t[mlp] : 0; mlp++; }
+        else if (has_ml) { int32_t v = 0; next_int(t, mlp, mle, &v); ml = v; }
         valid = true;
     }
     // is ordinal x listed?  x must not decrease between calls
@@ -104,10 +110,11 @@ struct NpTags {
     Section h, m, c; bool np_dot, bad;
     __device__ void load(const ReadBatchView &rb, uint32_t r) {
         const char *t = rb.text;
+        const bool bam = rb.bam != 0;
         np_dot = false;
-        h = parse_section(t, rb.mm_off[r], rb.mm_len[r], rb.ml_off[r], rb.ml_len[r], 'h'); if (h.found) np_dot = h.dot;
-        m = parse_section(t, rb.mm_off[r], rb.mm_len[r], rb.ml_off[r], rb.ml_len[r], 'm'); if (m.found) np_dot = m.dot;
-        c = parse_section(t, rb.mm_off[r], rb.mm_len[r], rb.ml_off[r], rb.ml_len[r], 'C');   // np_dot is restored to the C+m value (ont.cpp:263)
+        h = parse_section(t, rb.mm_off[r], rb.mm_len[r], rb.ml_off[r], rb.ml_len[r], 'h', bam); if (h.found) np_dot = h.dot;
+        m = parse_section(t, rb.mm_off[r], rb.mm_len[r], rb.ml_off[r], rb.ml_len[r], 'm', bam); if (m.found) np_dot = m.dot;
+        c = parse_section(t, rb.mm_off[r], rb.mm_len[r], rb.ml_off[r], rb.ml_len[r], 'C', bam);   // np_dot is restored to the C+m value (ont.cpp:263)
         bad = h.bad || m.bad || c.bad;
     }
 };
@@ -158,16 +165,16 @@ __global__ void __launch_bounds__(128) np_measure_k(ReadBatchView rb, const uint
             else {
                 const bool m_empty = !(tg.m.found && tg.m.nr) && !(o.cpc_call == 'C' && tg.c.found && tg.c.nr);
                 const bool h_empty = !(tg.h.found && tg.h.nr) && !(o.cpc_call == 'H' && tg.c.found && tg.c.nr);
-                const bool seq_star = rb.seq_len[r] == 1 && rb.text[rb.seq_off[r]] == '*';
+                const bool seq_star = rb.bam ? rb.seq_off[r] == SEQ_STAR : (rb.seq_len[r] == 1 && rb.text[rb.seq_off[r]] == '*');
                 if ((m_empty && h_empty && !tg.np_dot) || seq_star) empty = 1;              // ont.cpp:97-100
                 else if (st == REC_BADINT) inval = 1;                                        // stoul / stoi throw (ont.cpp:102-103)
                 else {
                     int64_t span = 0;
-                    bool ok = cig_validate(rb.text, rb.cig_off[r], rb.cig_off[r] + rb.cig_len[r], rb.seq_len[r], &span);
+                    bool ok = rec_cig_validate(rb, r, &span);
                     const bool bottom = (rb.flag[r] & 0x10) == 16;
                     if (ok && bottom) {                                                      // reverse_comp throws on anything but ACGTN
-                        const char *s = rb.text + rb.seq_off[r];
-                        for (uint32_t q = 0; q < rb.seq_len[r]; q++) { char ch = s[q]; if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T' && ch != 'N') { ok = false; break; } }
+                        const uint32_t so = rb.seq_off[r];
+                        for (uint32_t q = 0; q < rb.seq_len[r]; q++) { char ch = rec_base(rb, so, q); if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T' && ch != 'N') { ok = false; break; } }
                     }
                     if (!ok) inval = 1;
                     else {
@@ -199,14 +206,14 @@ __global__ void __launch_bounds__(128) np_call_k(ReadBatchView rb, const uint32_
         const uint32_t nc = r_ncand[r], lo = r_lo[r];
         const int64_t pos = (int64_t)(((uint64_t)(uint32_t)rb.pos_hi[r] << 32) | (uint32_t)rb.pos[r]);
         const bool bottom = (rb.flag[r] & 0x10) == 16;
-        int64_t span; cig_validate(rb.text, rb.cig_off[r], rb.cig_off[r] + rb.cig_len[r], rb.seq_len[r], &span);
-        const char *seq = rb.text + rb.seq_off[r];
+        int64_t span; rec_cig_validate(rb, r, &span);
+        const uint32_t so = rb.seq_off[r];
         const uint32_t slen = rb.seq_len[r];
         uint32_t *sc = scratch + (size_t)off[r] * 16;
         // phase A (ascending): candidate -> ordinal of its C in the original-orientation read
         int64_t totalG = 0;
-        if (bottom) for (uint32_t q = 0; q < slen; q++) totalG += seq[q] == 'G';
-        CigCursor cc; cc.init(rb.text, rb.cig_off[r], rb.cig_len[r]);
+        if (bottom) for (uint32_t q = 0; q < slen; q++) totalG += rec_base(rb, so, q) == 'G';
+        CigCursor cc; cc.init(rb, r);
         int64_t qscan = 0, run = 0;                  // run = # of 'C' (top) / 'G' (bottom) in seq[0, qscan)
         const char want = bottom ? 'G' : 'C';
         for (uint32_t j = 0; j < nc; j++) {
@@ -215,8 +222,8 @@ __global__ void __launch_bounds__(128) np_call_k(ReadBatchView rb, const uint32_
             uint32_t v = 0;
             if (di < span && cc.seek(di) && cc.op == 'M') {      // di >= mask.size(): skipped; deleted base: 'N' -> '.'
                 const int64_t q = cc.q0 + (di - cc.r0);
-                while (qscan < q) { run += seq[qscan] == want; qscan++; }
-                if (seq[q] == want) {
+                while (qscan < q) { run += rec_base(rb, so, qscan) == want; qscan++; }
+                if (rec_base(rb, so, q) == want) {
                     const int64_t ord = bottom ? totalG - run - 1 : run;   // G's after q / C's before q
                     const int64_t clip_pos = di;                             // ont.cpp:195-199 (di for bottom, i == di for top)
                     if ((clip_pos >= o.clip) && (clip_pos < span - o.clip)) v = (uint32_t)ord + 1;

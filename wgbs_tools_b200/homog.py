@@ -158,6 +158,12 @@ def main(argv=None):
             if not small and world == 1 and args.pat_decode in ("auto", "device"):
                 from .patio import read_pat_device
                 dtext = read_pat_device(ctx, pat)                  # BGZF: only the compressed bytes cross PCIe; None: plain gzip / text
+            shard = None
+            if not small and world > 1 and args.pat_decode in ("auto", "device"):
+                from .patio import read_pat_device_shard
+                shard = read_pat_device_shard(ctx, pat, rank, world)   # this rank's BGZF blocks only, inflated in HBM; None: not BGZF
+                if shard is not None:
+                    dtext = shard[1]
             from .patio import pat_pieces
             counts = None                                              # bins are sums over records: a text of any size goes piece by piece
             for piece in pat_pieces(ctx, vtext if small else dtext if dtext is not None else wd.shard_lines(read_pat_text(pat), rank, world)):
@@ -165,18 +171,22 @@ def main(argv=None):
                 c = homog_counts(ctx, P, lines, cols, edges, args.rlen, args.inclusive)
                 P.free()
                 counts = c if counts is None else counts + c
-            if dtext is not None:
+            if shard is not None:
+                shard[0].free()
+            elif dtext is not None:
                 dtext.free()
+            if counts is None:                                         # (a rank whose share holds no line)
+                counts = np.zeros((len(lines), len(edges) - 1), np.int32)
             counts = wd.reduce_np(counts, 0)                           # bins are sums over records: exact under any record split
             if rank != 0:
                 continue
             if args.binary:
                 trim_uxm_to_uint8(counts, args.nr_bits).tofile(opath)
             else:
-                with gzip.open(opath, "wb") as f:
-                    for l, row in zip(lines, counts.tolist()):
-                        t = l.rstrip(b"\n").split(b"\t")[:5]
-                        f.write(b"\t".join(t) + b"\t" + b"\t".join(b"%d" % v for v in row) + b"\n")
+                fmt = b"\t".join([b"%d"] * counts.shape[1]) + b"\n"
+                text = b"".join(b"\t".join(l.rstrip(b"\n").split(b"\t")[:5]) + b"\t" + fmt % tuple(row) for l, row in zip(lines, counts.tolist()))
+                with gzip.open(opath, "wb", compresslevel=6) as f:     # (one write of the whole table; the text is what counts, not the gzip level)
+                    f.write(text)
 
 
 if __name__ == "__main__":

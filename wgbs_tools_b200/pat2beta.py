@@ -32,6 +32,23 @@ def pat2beta(ctx, pat_path: str, out_dir: str, nr_sites: int, lbeta: bool = Fals
             P.free()
         return mc
 
+    shard = None
+    if world > 1 and decode in ("auto", "device"):
+        from .patio import read_pat_device_shard
+        shard = read_pat_device_shard(ctx, pat_path, rank, world)   # this rank's BGZF blocks only, inflated in HBM; None: not BGZF
+    if shard is not None:                                           # record-sharded: ONE reduce of the int32 counts, trim afterwards (it is non-linear)
+        buf, mine = shard
+        if len(mine):
+            d = counts(mine); mc = d.to_host(np.int32).reshape(-1, 2); d.free()
+        else:
+            mc = np.zeros((nr_sites, 2), np.int32)
+        buf.free()
+        mc = wd.reduce_np(mc, 0)
+        if rank != 0:
+            return None
+        beta = ctx.trim(mc, nr_sites, 16 if lbeta else 8)
+        beta.tofile(out_beta)
+        return out_beta
     if dtext is not None:
         mc = counts(dtext)
         beta = ctx.trim(mc, nr_sites, 16 if lbeta else 8)

@@ -61,6 +61,52 @@ def read_pat_device(ctx, path: str):
     return ctx.bgzf_inflate(raw)
 
 
+def read_pat_device_shard(ctx, path: str, rank: int, world: int):
+    """One rank's share of a bgzip-compressed X.pat.gz under torchrun, inflated in HBM: the rank reads only ITS run of BGZF blocks
+    (+ the block before and the block after), and owns the lines that START inside its run -- the same rule on both sides of every
+    boundary, so the ranks' shares partition the records.  Returns (DevBuf to free, DevView of the owned lines), or None when the
+    file is not BGZF (the caller then shards the host text, dist.shard_lines).  pat2beta and homog are sums over records
+    (reference pat2beta.py / homog.cpp:84 shard by chromosome; any record split gives the same sums)."""
+    from .api import DevView
+    from .bamio import bgzf_block_table
+    if not path.endswith(".pat.gz"):
+        return None
+    with open(path, "rb") as f:
+        if not is_bgzf(f.read(18)):
+            return None
+    coff, csize, usize = bgzf_block_table(path)
+    nb = int(coff.size)
+    b0, b1 = nb * rank // world, nb * (rank + 1) // world
+    lo, hi = max(b0 - 1, 0), min(b1 + 1, nb)                      # neighbours: where the first / last owned line starts and ends
+    if hi <= lo:
+        return None
+    with open(path, "rb") as f:
+        f.seek(int(coff[lo])); raw = f.read(int(coff[hi - 1] + csize[hi - 1] - coff[lo]))
+    buf = ctx.bgzf_inflate(raw + BGZF_EOF)
+    S = int(usize[lo:b0].sum()); E = S + int(usize[b0:b1].sum()); n = len(buf)
+
+    def line_start_at_or_after(pos: int) -> int:
+        """first offset >= pos where a line starts (offset 0, or the byte behind a newline)"""
+        if pos <= 0:
+            return 0
+        if pos >= n:
+            return n
+        a = max(pos - 1, 0); w = min(n - a, 1 << 20)
+        import numpy as np
+        from ._lib import check, lib
+        win = np.empty(w, np.uint8)
+        check(lib.wgbs_memcpy(ctx.h, win.ctypes.data, buf.ptr + a, w))
+        k = win.tobytes().find(b"\n")
+        if k < 0:
+            if a + w >= n:
+                return n
+            raise ValueError("pat line longer than 1 MiB")
+        return a + k + 1
+    start = line_start_at_or_after(S) if b0 > 0 else 0
+    end = line_start_at_or_after(E) if b1 < nb else n
+    return buf, DevView(buf.ptr + start, max(end - start, 0))
+
+
 def pat_pieces(ctx, text, limit: int | None = None):
     """A pat text (bytes, or a DevBuf of device-resident text) as pieces of at most `limit` bytes that end at line ends: one
     wgbs_pats_from_text call takes < 4 GiB, a 30x pat file is more.  pat2beta and homog are sums over records, so the pieces are
@@ -72,7 +118,7 @@ def pat_pieces(ctx, text, limit: int | None = None):
     if n <= limit:
         yield text
         return
-    dev = isinstance(text, DevBuf)
+    dev = isinstance(text, (DevBuf, DevView))
     mv = None if dev else memoryview(text)
     lo = 0
     while lo < n:
