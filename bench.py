@@ -680,8 +680,11 @@ def main():
     ms_dev, _, launches = timed(lambda w: step_sam(w), args.steps, args.warmup, 1)
     ms_bam, _, _ = timed(lambda w: step_bam(w, False), args.steps, args.warmup, 1)
     ms_serial, wall_serial, _ = timed(lambda w: step_bam(w, True), args.steps, args.warmup, 1)
-    per = max(1, (args.steps + S - 1) // S)                   # steps per worker: per * S >= K batches go through
-    ms_e2e, wall_e2e, _ = timed(lambda w: step_bam(w, True), per, args.warmup, S)
+    # steps per worker: per * S >= K batches go through, and at least 6 per worker -- a 12-batch region lasts ~45 ms, and at N > 1 one
+    # hiccup of a rank moved the whole number by 15 % (2 GPUs: 406 M reads/s with 3 steps per worker, 474 M with 10)
+    per = max(6, (args.steps + S - 1) // S)
+    e2e_reduce = os.environ.get("WGBS_BENCH_E2E_REDUCE", "1") != "0"    # diagnostic: 0 = the in-flight leg without its per-step reduce (how much of the N > 1 step it is)
+    ms_e2e, wall_e2e, _ = timed(lambda w: step_bam(w, True, e2e_reduce), per, args.warmup, S)
     n_e2e = per * S
     if ms_dev + ms_e2e < 1500:                       # keep the GPU busy long enough for a few clock samples
         t_end = time.time() + 1.0

@@ -155,7 +155,7 @@ def main():
                 if n == gpu_counts[0]:
                     ref_digest[name] = d
                 import re
-                m = re.search(r"\]: ([0-9.]+) s after start-up", r.stderr)
+                m = re.search(r"\] \w+: ([0-9.]+) s after start-up", r.stderr)
                 work_s = float(m.group(1)) if m else max(t - t_noop, 1e-3)       # the command's own clock (process group up before it starts)
                 run[name] = {"wall_s": t, "work_s": work_s, "rate": units / work_s, "unit": unit, "rc": r.returncode, "identical_to_first_run": d == ref_digest.get(name), "digest": d}
                 if not ok:

@@ -1,7 +1,12 @@
 #!/bin/bash
-# GPU call (2 GPUs): the four CLIs under torchrun at 1 and 2 GPUs on a 25-chromosome data set, then the bench line at 2 GPUs
+# GPU call (2 GPUs): what the per-step NCCL reduce costs the end-to-end leg with batches in flight
 set -u
 mkdir -p gpurun_out
-timeout 200 python -m pytest tests/test_zz_bamdev_gpu.py -m gpu -x -q -p no:cacheprovider -k "inflate" > gpurun_out/r2m_tests.log 2>&1; echo "tests rc=$? $(tail -1 gpurun_out/r2m_tests.log)"
-timeout 700 python tools/multigpu_cli.py --scale 0.2 --reads 6000000 --pat_records 40000000 --K 20 --gpus 1,2 --out gpurun_out/r2m_multigpu.json > gpurun_out/r2m_multigpu.log 2>&1; echo "mg rc=$?"; tail -12 gpurun_out/r2m_multigpu.log | cut -c1-400
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2m_bench_2gpu.json 2> gpurun_out/r2m_bench_2gpu.err; echo "bench2 rc=$?"; tail -c 400 gpurun_out/r2m_bench_2gpu.json
+for mode in 1 0; do
+  WGBS_BENCH_E2E_REDUCE=$mode timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2951$mode bench.py --gpus 2 --steps 40 --warmup 3 --no-extras > gpurun_out/r2q_bench_2gpu_reduce$mode.json 2> gpurun_out/r2q_bench_2gpu_reduce$mode.err; echo "reduce=$mode rc=$?"
+  python - <<PY
+import json
+d=json.loads(open('gpurun_out/r2q_bench_2gpu_reduce$mode.json').read().strip().splitlines()[-1])
+print('value',round(d['value']/1e6,1),'ms',round(d['ms_per_step'],3),'e2e',round(d['e2e']['value']/1e6,1),'ms',round(d['e2e']['ms_per_step'],3),'serial',round(d['e2e']['serial']['ms_per_step'],3))
+PY
+done

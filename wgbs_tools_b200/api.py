@@ -230,7 +230,7 @@ class Context:
         return b
 
     def bgzf_inflate(self, data) -> DevBuf:
-        """the bytes of a BGZF file (host) -> its inflated bytes in device memory (one warp per BGZF block; deflate, ISIZE and
+        """the bytes of a BGZF file (host) -> its inflated bytes in device memory (one warp per BGZF block, its lanes on spans of the bit stream; deflate, ISIZE and
         CRC32 are verified)"""
         a = np.frombuffer(data, np.uint8)
         p = C.c_void_p(); n = C.c_size_t()
