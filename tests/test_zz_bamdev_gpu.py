@@ -426,7 +426,6 @@ def test_bam2pat_cli_template_windows(ctx, bamio, tmp_path, monkeypatch, decode,
     assert outs[0] == outs[1] and len(outs[0][0]) > 1000
 
 
-@pytest.mark.staged
 def test_device_parts_equal_host_parts_and_streamed_cli(ctx, bamio, tmp_path, monkeypatch):
     """wgbs_dbam_open_part / last_record / first_key: a file streamed as parts decoded on the device gives the same items (same
     views, same tails) as the host part reader, and `bam2pat --bam_decode stream` with WGBS_STREAM_BACKEND=device the same files
@@ -453,7 +452,6 @@ def test_device_parts_equal_host_parts_and_streamed_cli(ctx, bamio, tmp_path, mo
     assert outs[0] == outs[1] == outs[2] and len(outs[0][0]) > 1000
 
 
-@pytest.mark.staged
 @pytest.mark.parametrize("decode", ["host", "device"])
 def test_bam2pat_cli_chromosomes_in_flight(ctx, bamio, tmp_path, monkeypatch, decode):
     """--gpu_streams 2: two chromosomes at a time, each on its own Context (stream) and host thread, all adding into the one
