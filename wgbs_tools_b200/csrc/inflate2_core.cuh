@@ -614,9 +614,10 @@ WGBS_HD int resolve_bytes(L lanes, const Token *tok, uint32_t ntok, uint8_t *dst
                     const uint32_t r = j - o, a = x & 0xffffu, ln = x >> 16, d = y & ~TOK_STORED;
                     on[u] = j < M; p[u] = a + r; b[u] = 0;
                     if (on[u]) {
+                        const bool st = (y & TOK_STORED) != 0;
                         uint32_t sr = r;                              // a run (dist < len) repeats its first dist bytes
-                        if (d < ln) { sr = 0; if (WGBS_UNLIKELY(d != 1)) sr = r % d; }
-                        const uint8_t *from = (y & TOK_STORED) ? payload + d + r : dst + a - d + sr;
+                        if (!st && d < ln) { sr = 0; if (WGBS_UNLIKELY(d != 1)) sr = r % d; }
+                        const uint8_t *from = st ? payload + d + r : dst + a - d + sr;
                         b[u] = *from;
                     }
                 }

@@ -28,7 +28,10 @@ using dflate2::Token; using dflate2::LB; using dflate2::DB; using dflate2::K_LIT
 using dflate::OK; using dflate::E_INPUT; using dflate::E_SYMBOL; using dflate::E_DIST; using dflate::E_OUTPUT;
 
 constexpr uint32_t NOPOS = 0xffffffffu;
-constexpr uint32_t SYNC_BITS = 1536;      // a walk started anywhere is taken to be in step this many bits later (pass B verifies it)
+#ifndef WGBS_SYNC_BITS
+#define WGBS_SYNC_BITS 1024
+#endif
+constexpr uint32_t SYNC_BITS = WGBS_SYNC_BITS;      // a walk started anywhere is taken to be in step this many bits later (pass B verifies it)
 constexpr uint32_t MIN_SPAN = 3072;       // shortest span worth a lane of its own (> SYNC_BITS: a lane's run-up stays inside the block)
 enum : uint32_t { F_EOB = 1, F_BAD = 2, F_END = 4 };
 
@@ -310,6 +313,9 @@ WGBS_HD int team_inflate(L lanes, TeamMem *T, const uint8_t *payload, uint32_t c
             else {
                 w.seek(t0 - SYNC_BITS);
                 w.run_until<false>(t0);
+                // a guessed walk that runs into an invalid code or a bogus end-of-block code goes on from where it stands: a new guess
+                for (int k = 0; k < 8 && w.flags && !(w.flags & F_END) && w.pos() < t0; k++) { w.flags = 0; w.rc = OK; w.run_until<false>(t0); }
+                if (w.flags && !(w.flags & F_END) && w.pos() >= t0) { w.flags = 0; w.rc = OK; }     // (the failing guess ended past the span's start: guess on from there)
                 if (!w.flags) { anchor = w.pos(); w.out = 0; w.ntk = 0; }
             }
         }
