@@ -487,7 +487,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=1_000_000)
-    ap.add_argument("--streams", type=int, default=4, help="batches in flight per GPU in the end-to-end leg: S Contexts (own stream each) on S host threads [4]")
+    ap.add_argument("--streams", type=int, default=8, help="batches in flight per GPU in the end-to-end leg: S Contexts (own stream each) on S host threads [8]")
     ap.add_argument("--no-extras", dest="no_extras", action="store_true", help="skip the pat2beta / homog / segment / MM-ML side measurements and the CPU baseline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
