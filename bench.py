@@ -275,7 +275,6 @@ def algorithmic_bytes(kernel: str, w: dict):
         "merge_templates_k": 12 * n_rec + 16 * n_rec + 8 * n_rec,
         "line_write_k": 16 * n_tmpl + 8 * n_tmpl + w["out_text_bytes"],
         # BAM front end: compressed bytes in; literals (~1/16 of the output) + one 8-byte token per match out / tokens in, inflated bytes out, and read once more for the CRC
-        "bgzf_decode_k": w.get("bam_bytes", 0) + w.get("inflated", 0) // 16 + 8 * (w.get("inflated", 0) // 16),
         "bgzf_team_decode_k": w.get("bam_bytes", 0) + w.get("inflated", 0) // 16 + 8 * (w.get("inflated", 0) // 16),
         "bgzf_resolve_k": 8 * (w.get("inflated", 0) // 16) + 2 * w.get("inflated", 0),
         "bam_records_k": 36 * n_rec + 57 * n_rec, "bam_pass_k": 36 * n_rec + 4 * n_rec,

@@ -128,96 +128,11 @@ static int emu_team2(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usiz
 static int emu_warp2(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usize, uint32_t want_crc) { return emu_team2<32>(src, n, dst, usize, want_crc); }
 
 
-// ---- the two-phase decoder (inflate2_core.cuh) ----------------------------------------------------------------------------------
-// phase 1 = one lane per block: plain arrays (layout 0) or the warp's lane-interleaved arrays seen from lane `lane` (layout 5);
-// phase 2 = the token replay by one lane, or by 32 lanes in lock step.  *ntok_out / *nsym_out: statistics.
 static size_t g_fallbacks = 0;
-static int one_lane2(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usize, uint32_t want_crc);
-static int two_phase(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t usize, uint32_t want_crc, int layout, bool emu, uint32_t *ntok_out = nullptr) {
-    std::vector<dflate2::Token> tok(dflate2::token_cap(usize));
-    int rc;
-    auto fallback = [&]() { g_fallbacks++; return one_lane2(src, n, dst, usize, want_crc); };      // what bgzf_warp_inflate_k does for such a block
-    if (layout == 0) {
-        static dflate2::HostLane H; dflate2::Decoder<0> D; D.init(H.mem(), src, n, dst, usize, tok.data()); rc = D.run();
-        if (ntok_out) *ntok_out = D.ntok;
-        if (rc == dflate2::E_FALLBACK) return fallback();
-        if (rc != OK) return rc;
-        if (!emu) rc = dflate2::resolve(OneLane(), tok.data(), D.ntok, dst, usize, src);
-        else {
-            static EmuShared sh; int rcs[32]; const uint32_t nt = D.ntok;
-            std::vector<std::thread> th;
-            for (int l = 0; l < 32; l++) th.emplace_back([&, l]() {
-                EmuLanes L{l, &sh};
-                rcs[l] = dflate2::resolve(L, tok.data(), nt, dst, usize, src);
-                L.sync();
-                if (rcs[l] == OK && dflate2::crc32_block4(L, dst, usize, g_crc4) != want_crc) rcs[l] = E_CRC;
-            });
-            for (auto &t : th) t.join();
-            for (int l = 1; l < 32; l++) if (rcs[l] != rcs[0]) { fprintf(stderr, "lanes disagree on rc (two-phase)\n"); exit(4); }
-            return rcs[0];
-        }
-    } else {
-        static std::vector<unsigned char> smem(32 * dflate2::LANE_BYTES + 16);
-        unsigned char *base = smem.data() + ((16 - ((uintptr_t)smem.data() & 15)) & 15);
-        const uint32_t lane = (uint32_t)(n % 32);
-        dflate2::Decoder<5> D; D.init(dflate2::warp_mem(base, lane), src, n, dst, usize, tok.data());
-        // the kernel's schedule: header / bounded runs of probes
-        int st = dflate2::ST_HDR;
-        while (st != dflate2::ST_DONE) { if (st == dflate2::ST_HDR) st = D.header(); else { D.ring_top_up(); st = D.decode_burst(); } }
-        rc = D.rc;
-        if (ntok_out) *ntok_out = D.ntok;
-        if (rc == dflate2::E_FALLBACK) return fallback();
-        if (rc != OK) return rc;
-        rc = dflate2::resolve(OneLane(), tok.data(), D.ntok, dst, usize, src);
-    }
-    if (rc == OK && dflate2::crc32_block4(OneLane(), dst, usize, g_crc4) != want_crc) rc = E_CRC;
-    return rc;
-}
-
-
-// the schedule of bgzf_decode_k on the host: 32 decoding lanes share one lane-interleaved buffer; per round every lane at a header
-// takes it, then every lane inside a Huffman block tops its ring up and runs one burst.  Blocks are taken 32 at a time.
-static size_t group_check(const std::vector<uint8_t> &f, const std::vector<Blk> &blocks) {
-    static std::vector<unsigned char> smem(32 * dflate2::LANE_BYTES + 16);
-    unsigned char *base = smem.data() + ((16 - ((uintptr_t)smem.data() & 15)) & 15);
-    size_t bad = 0;
-    for (size_t g0 = 0; g0 < blocks.size(); g0 += 32) {
-        const size_t ng = std::min<size_t>(32, blocks.size() - g0);
-        std::vector<dflate2::Decoder<5>> D(ng); std::vector<int> st(ng, dflate2::ST_HDR);
-        std::vector<std::vector<uint8_t>> out(ng); std::vector<std::vector<dflate2::Token>> tok(ng);
-        for (size_t i = 0; i < ng; i++) {
-            const Blk &b = blocks[g0 + i];
-            out[i].assign(b.usize + 1, 0); tok[i].resize(dflate2::token_cap(b.usize));
-            D[i].init(dflate2::warp_mem(base, (uint32_t)i), f.data() + b.coff + 12 + b.xlen, b.csize - 12 - b.xlen - 8, out[i].data(), b.usize, tok[i].data());
-        }
-        for (bool any = true; any;) {
-            any = false;
-            for (size_t i = 0; i < ng; i++) if (st[i] == dflate2::ST_HDR) st[i] = D[i].header();
-            for (size_t i = 0; i < ng; i++) if (st[i] == dflate2::ST_DEC) D[i].ring_top_up();
-            for (size_t i = 0; i < ng; i++) if (st[i] == dflate2::ST_DEC) st[i] = D[i].decode_burst();
-            for (size_t i = 0; i < ng; i++) any = any || st[i] != dflate2::ST_DONE;
-        }
-        for (size_t i = 0; i < ng; i++) {
-            const Blk &b = blocks[g0 + i];
-            const uint8_t *src = f.data() + b.coff + 12 + b.xlen; const uint32_t n = b.csize - 12 - b.xlen - 8;
-            std::vector<uint8_t> a(b.usize + 1);
-            const uint32_t want = bamcore::ld32(f.data() + b.coff + b.csize - 8);
-            int rz = zlib_inflate(src, n, a.data(), b.usize);
-            if (rz == 0 && (uint32_t)crc32(crc32(0L, Z_NULL, 0), a.data(), b.usize) != want) rz = -1;
-            int rc = D[i].rc;
-            if (rc == dflate2::E_FALLBACK) continue;
-            if (rc == OK) rc = dflate2::resolve(OneLane(), tok[i].data(), D[i].ntok, out[i].data(), b.usize, src);
-            if (rc == OK && dflate2::crc32_block4(OneLane(), out[i].data(), b.usize, g_crc4) != want) rc = E_CRC;
-            const bool ok = (rz == 0) == (rc == 0) && (rz != 0 || !memcmp(a.data(), out[i].data(), b.usize));
-            if (!ok) { fprintf(stderr, "block %zu: 32-lane schedule: rc %d (zlib %d)\n", g0 + i, rc, rz); bad++; }
-        }
-    }
-    return bad;
-}
 
 static int cmd_inflate(const char *path, int emu_blocks) {
     auto f = slurp(path); uint64_t ut; auto blocks = scan_blocks(f, &ut);
-    size_t nbad = 0, nemu = 0; uint64_t bytes = 0, tokens = 0;
+    size_t nbad = 0, nemu = 0; uint64_t bytes = 0;
     for (size_t i = 0; i < blocks.size(); i++) {
         const Blk &b = blocks[i];
         const uint8_t *src = f.data() + b.coff + 12 + b.xlen; const uint32_t n = b.csize - 12 - b.xlen - 8;
@@ -228,18 +143,8 @@ static int cmd_inflate(const char *path, int emu_blocks) {
         const int r1 = one_lane(src, n, c.data(), b.usize, want, true);
         bool ok = (rz == 0) == (r1 == 0) && (rz != 0 || !memcmp(a.data(), c.data(), b.usize));
         { std::vector<uint8_t> c2(b.usize + 1); const int r3 = one_lane2(src, n, c2.data(), b.usize, want); ok = ok && (rz == 0) == (r3 == 0) && (rz != 0 || !memcmp(a.data(), c2.data(), b.usize)); }
-        for (int layout : {0, 5}) {
-            std::vector<uint8_t> c3(b.usize + 1); uint32_t nt = 0; const int r5 = two_phase(src, n, c3.data(), b.usize, want, layout, false, &nt);
-            const bool ok3 = (rz == 0) == (r5 == 0) && (rz != 0 || !memcmp(a.data(), c3.data(), b.usize));
-            if (!ok3) fprintf(stderr, "block %zu: two-phase decoder (layout %d): rc %d (zlib %d)\n", i, layout, r5, rz);
-            ok = ok && ok3; if (layout == 0) tokens += nt;
-        }
         if ((int)i < emu_blocks) {
             const int r2 = emu_warp(src, n, e.data(), b.usize, want); ok = ok && r2 == r1 && (r1 != 0 || !memcmp(a.data(), e.data(), b.usize)); nemu++;
-            { std::vector<uint8_t> e3(b.usize + 1); const int r6 = two_phase(src, n, e3.data(), b.usize, want, 0, true);
-              const bool ok6 = (rz == 0) == (r6 == 0) && (rz != 0 || !memcmp(a.data(), e3.data(), b.usize));
-              if (!ok6) fprintf(stderr, "block %zu: two-phase decoder, 32-lane replay: rc %d (zlib %d)\n", i, r6, rz);
-              ok = ok && ok6; }
             std::vector<uint8_t> e2(b.usize + 1); const int r4 = emu_warp2(src, n, e2.data(), b.usize, want); ok = ok && (rz == 0) == (r4 == 0) && (rz != 0 || !memcmp(a.data(), e2.data(), b.usize));
             // the team decoders (bgzf_inflate_team_k<G>): the same Inflater2 with batches of 4 / 8 / 16 symbols
             for (int g : {4, 8, 16}) {
@@ -253,8 +158,6 @@ static int cmd_inflate(const char *path, int emu_blocks) {
         if (!ok) { nbad++; fprintf(stderr, "block %zu: zlib %d core %d\n", i, rz, r1); }
         bytes += b.usize;
     }
-    nbad += group_check(f, blocks);
-    fprintf(stderr, "tokens %llu fallbacks %zu\n", (unsigned long long)tokens, g_fallbacks);
     printf("blocks %zu emu %zu bytes %llu mismatches %zu\n", blocks.size(), nemu, (unsigned long long)bytes, nbad);
     return nbad ? 1 : 0;
 }
@@ -523,8 +426,6 @@ static int check_team_tables(const uint8_t *ln, int nlen, int ndist, dflate2::De
 static int cmd_tables(long N, unsigned seed) {
     std::mt19937_64 rng(seed); size_t bad = 0, fallbacks = 0;
     static dflate2::HostLane H;
-    static std::vector<unsigned char> smem(32 * dflate2::LANE_BYTES + 16);
-    unsigned char *base = smem.data() + ((16 - ((uintptr_t)smem.data() & 15)) & 15);
     static uint8_t dummy[64] = {3, 0};
     for (long t = 0; t < N; t++) {
         uint8_t ln[320] = {0};
@@ -539,8 +440,6 @@ static int cmd_tables(long N, unsigned seed) {
         bad += check_team_tables<1>(ln, nlen, ndist, D0, rc0);
         if (t % 16 == 0) bad += check_team_tables<32>(ln, nlen, ndist, D0, rc0);
         if (t % 16 == 8) bad += check_team_tables<8>(ln, nlen, ndist, D0, rc0);
-        dflate2::Decoder<5> D5; D5.init(dflate2::warp_mem(base, (uint32_t)(t % 32)), dummy, 2, dummy + 8, 0, nullptr);
-        size_t fb5 = 0; bad += check_tables(D5, ln, nlen, ndist, &fb5);
     }
     printf("tables %ld fallbacks %zu mismatches %zu\n", N, fallbacks, bad);
     return bad ? 1 : 0;

@@ -325,8 +325,9 @@ def deep_code_block(rng, data: bytes, maxbits: int = 15, lens=None) -> bytes:
 
 
 def test_two_phase_decoder_tables_and_fallback(check, tmp_path):
-    """(1) the two-level Huffman tables of the two-phase decoder on 4 000 random complete code sets, in both memory layouts: every
-    symbol decodes to itself through root + second level, sets that exceed the per-lane arena are handed back (E_FALLBACK);
+    """(1) the two-level Huffman tables of the two-phase decoder on 4 000 random complete code sets, built by one lane and by teams of
+    1 / 8 / 32 lanes (team_tables): every symbol decodes to itself through root + second level, sets that exceed the arena are handed
+    back (E_FALLBACK) by both alike;
     (2) hand-written deflate blocks with deep literal codes: output == zlib's, and some of them do take the fallback decoder"""
     from wgbs_tools_b200.patio import BGZF_EOF
     r = subprocess.run([check, "tables", "4000", "7"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
@@ -347,7 +348,7 @@ def test_two_phase_decoder_tables_and_fallback(check, tmp_path):
         parts.insert(5 * k + 1, blk)
     p = tmp_path / "deep.bgzf"
     p.write_bytes(b"".join(parts) + BGZF_EOF)
-    r = subprocess.run([check, "inflate", str(p), "6"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    r = subprocess.run([check, "inflate3", str(p)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.strip().endswith("mismatches 0"), r.stdout + r.stderr
     fb = int(r.stderr.split("fallbacks")[1].split()[0])
     assert fb > 0, "no block exceeded the arena: the fallback path was not exercised"

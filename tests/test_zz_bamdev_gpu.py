@@ -46,7 +46,7 @@ def _block(data: bytes, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, mem=8) -> byt
 
 
 def test_bgzf_inflate_kernel_matches_zlib(ctx, sample):
-    """the two-phase decoder (bgzf_decode_k + bgzf_resolve_k, wgbs_bgzf_inflate): stored / fixed / dynamic blocks, long codes,
+    """the two-phase decoder (bgzf_team_decode_k + bgzf_resolve_k, wgbs_bgzf_inflate): stored / fixed / dynamic blocks, long codes,
     overlapping matches, several deflate blocks per BGZF block, empty blocks, incompressible bytes -- output == zlib's, byte
     for byte; a corrupt block is reported with its number"""
     _inflate_checks(ctx, sample[1])
@@ -61,7 +61,7 @@ def test_bgzf_inflate_kernel_matches_zlib(ctx, sample):
 
 def test_bgzf_inflate_deep_codes_and_the_fallback_decoder(ctx):
     """hand-written deflate blocks with deep literal codes (test_bamdev_core.deep_code_block): large second-level tables in
-    bgzf_decode_k, and blocks whose tables exceed a lane's arena (handed to bgzf_warp_inflate_k inside the same call) -- all == zlib"""
+    bgzf_team_decode_k, and blocks whose tables exceed the arena (handed to bgzf_warp_inflate_k inside the same call) -- all == zlib"""
     from test_bamdev_core import deep_code_block
     from wgbs_tools_b200.patio import BGZF_EOF
     rng = np.random.default_rng(11)
@@ -93,15 +93,6 @@ def test_bgzf_inflate_round1_decoder_matches_zlib(ctx, sample, monkeypatch):
     """bgzf_inflate_k (WGBS_INFLATE=2: one warp per block, the round-1 decoder kept as the yardstick of the bench): same checks"""
     monkeypatch.setenv("WGBS_INFLATE", "2")
     _inflate_checks(ctx, sample[1])
-
-
-@pytest.mark.parametrize("variant", ("thread", "tokens", "thread,tokens"))
-def test_bgzf_inflate_yardstick_decoders_match_zlib(ctx, sample, monkeypatch, variant):
-    """the decoders the default (team decoder + byte-per-lane replay, inflate3_core.cuh) is measured against: bgzf_decode_k (one thread
-    per block) and the token-per-lane replay -- same checks, plus the deep-code blocks (second-level tables, arena overflow)"""
-    monkeypatch.setenv("WGBS_INFLATE", variant)
-    _inflate_checks(ctx, sample[1])
-    test_bgzf_inflate_deep_codes_and_the_fallback_decoder(ctx)
 
 
 def _inflate_checks(ctx, s):

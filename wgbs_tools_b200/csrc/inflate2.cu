@@ -1,11 +1,11 @@
-// inflate2.cu -- the two kernels of the two-phase BGZF decoder (inflate2_core.cuh):
+// inflate2.cu -- the kernels of the two-phase BGZF decoder (inflate2_core.cuh, inflate3_core.cuh):
 //
-//   bgzf_decode_k        one THREAD per BGZF block, 4 warps x 8 decoding lanes (= 32 blocks) per CTA and SM: lane-interleaved
-//                        two-level Huffman tables in 220 KB of shared memory; literals go to their final place, matches to a
-//                        token list.  Lanes take the deflate-block headers of their blocks together (table construction is
-//                        the same instruction stream for all of them) and then run bursts of table probes.
-//   bgzf_resolve_k       one WARP per block: token replay (LZ77 copies), then ISIZE and CRC32 of the block.
-//   bgzf_warp_inflate_k  the round-1 decoder (one warp per block): blocks whose tables exceed a lane's arena, and the yardstick.
+//   bgzf_team_decode_k   one WARP per BGZF block, 32 blocks per CTA and SM (7.2 KB of shared memory each): the leader lane parses the
+//                        deflate block header, the team builds the two-level Huffman tables, then the lanes walk spans of the bit stream
+//                        and verify each other; literals go to their final place, matches to a token list.
+//   bgzf_resolve_k       one WARP per block: token replay (LZ77 copies, lane = output byte), then ISIZE and CRC32 of the block.
+//   bgzf_warp_inflate_k  the round-1 decoder (one warp per block, every lane the same walk): blocks whose tables exceed the arena, and the
+//                        yardstick (WGBS_INFLATE=2).
 //
 // Stands in for the zlib inflate inside `samtools view` (reference src/python/bam2pat.py:165).
 #include <algorithm>
@@ -30,40 +30,9 @@ constexpr Crc4Table make_crc4() {
 }
 __device__ const Crc4Table g_crc4 = make_crc4();
 
-constexpr int DEC_WARPS = 4;            // warps per CTA of bgzf_decode_k, DEC_LANES decoding lanes each: 32 blocks per CTA (and SM)
-constexpr int DEC_LANES = 8;            // few lanes per warp: what one lane does rarely (second-level probe, ring word) stalls only 7 others
 constexpr int RES_WARPS = 8;            // warps (= blocks) per CTA of bgzf_resolve_k
 constexpr int OLD_WARPS = 4;            // warps (= blocks) per CTA of bgzf_warp_inflate_k
 constexpr uint32_t CHUNK_BLOCKS = 8192; // blocks per launch pair: bounds the token scratch (~175 KB per block) to 1.4 GB
-
-__global__ void __launch_bounds__(DEC_WARPS * 32, 1) bgzf_decode_k(const uint8_t *__restrict__ comp, const BgzfBlock *__restrict__ blocks, uint32_t nblocks,
-                                                                   uint8_t *__restrict__ out, dflate2::Token *__restrict__ tok, uint32_t *__restrict__ ntok,
-                                                                   int32_t *__restrict__ status) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr unsigned MASK = 0xffffffffu;                          // lanes >= DEC_LANES idle along (state DONE): whole-warp barriers stay valid
-    const uint32_t slot = warp * DEC_LANES + (lane & (DEC_LANES - 1));
-    for (uint32_t base = blockIdx.x * 32; base < nblocks; base += gridDim.x * 32) {
-        const uint32_t b = base + slot;
-        const bool active = lane < DEC_LANES && b < nblocks;
-        dflate2::Decoder<5> D;
-        int st = dflate2::ST_DONE;
-        if (active) {
-            const BgzfBlock B = blocks[b];
-            D.init(dflate2::warp_mem(smem, slot), comp + B.coff, B.clen, out + B.uoff, B.usize, tok + B.tok);
-            st = dflate2::ST_HDR;
-        }
-        __syncwarp(MASK);
-        while (__any_sync(MASK, st != dflate2::ST_DONE)) {
-            if (st == dflate2::ST_HDR) st = D.header();             // lanes at a deflate block header build their tables together
-            __syncwarp(MASK);
-            if (st == dflate2::ST_DEC) { D.ring_top_up(); st = D.decode_burst(); }
-            __syncwarp(MASK);
-        }
-        if (active) { ntok[b] = D.ntok; status[b] = D.rc; }
-        __syncwarp(MASK);
-    }
-}
 
 // Team decoder (inflate3_core.cuh): S lanes walk ONE block together (spans of its bit stream, verified against each other), TEAM_SLOTS
 // blocks per CTA and SM -- the block's tables and the leader's header decoder in 7.2 KB of shared memory each.
@@ -87,7 +56,6 @@ __global__ void __launch_bounds__(TEAM_SLOTS * S, 1) bgzf_team_decode_k(const ui
 }
 
 // (4 CTAs of 8 warps per SM = 64 registers per thread: the ~4 200 blocks of a 1M-read BAM must be ONE wave -- at 78 registers they were two)
-template <bool by_bytes>
 __global__ void __launch_bounds__(RES_WARPS * 32, 4) bgzf_resolve_k(const uint8_t *__restrict__ comp, const BgzfBlock *__restrict__ blocks, uint32_t nblocks, uint32_t block0,
                                                                   uint8_t *out, const dflate2::Token *__restrict__ tok, const uint32_t *__restrict__ ntok,
                                                                   const int32_t *__restrict__ status, unsigned long long *__restrict__ err) {
@@ -98,8 +66,7 @@ __global__ void __launch_bounds__(RES_WARPS * 32, 4) bgzf_resolve_k(const uint8_
     int rc = status[b];
     if (rc == dflate2::E_FALLBACK) return;          // bgzf_warp_inflate_k decodes this block
     if (rc == dflate2::OK) {
-        rc = by_bytes ? dflate2::resolve_bytes(dflate::WarpLanes(), tok + B.tok, ntok[b], out + B.uoff, B.usize, comp + B.coff)
-                      : dflate2::resolve(dflate::WarpLanes(), tok + B.tok, ntok[b], out + B.uoff, B.usize, comp + B.coff);
+        rc = dflate2::resolve_bytes(dflate::WarpLanes(), tok + B.tok, ntok[b], out + B.uoff, B.usize, comp + B.coff);
         __syncwarp();
         if (rc == dflate2::OK && dflate2::crc32_block4(dflate::WarpLanes(), out + B.uoff, B.usize, T) != B.crc) rc = dflate2::E_CRC;
     }
@@ -108,7 +75,7 @@ __global__ void __launch_bounds__(RES_WARPS * 32, 4) bgzf_resolve_k(const uint8_
 }
 
 // One warp per BGZF block, every lane running the same Huffman walk (dflate::Inflater2, inflate_core.cuh): the round-1 decoder.
-// status != nullptr: only the blocks bgzf_decode_k handed back (E_FALLBACK: their Huffman tables exceed its per-lane arena);
+// status != nullptr: only the blocks bgzf_team_decode_k handed back (E_FALLBACK: their Huffman tables exceed the arena);
 // status == nullptr: every block (WGBS_INFLATE=2: the yardstick the two-phase decoder is measured against).
 __global__ void __launch_bounds__(OLD_WARPS * 32, 8) bgzf_warp_inflate_k(const uint8_t *__restrict__ comp, const BgzfBlock *__restrict__ blocks, uint32_t nblocks, uint32_t block0,
                                                                           uint8_t *out, const int32_t *__restrict__ status, unsigned long long *__restrict__ err) {
@@ -148,8 +115,6 @@ uint64_t bgzf_inflate2_plan(BgzfBlock *h_blocks, uint32_t nb) {
 int bgzf_inflate2_launch(wgbs_ctx *ctx, const uint8_t *d_comp, const BgzfBlock *d_blocks, uint32_t nb, uint64_t token_slots, uint8_t *out,
                          unsigned long long *d_err) {
     if (!nb) return 0;
-    static const size_t smem_bytes = 32 * dflate2::LANE_BYTES;
-    CUDA_TRY(cudaFuncSetAttribute(bgzf_decode_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     Temps T(ctx);
     dflate2::Token *tok; uint32_t *ntok; int32_t *status;
     // the token lists (~2.7 bytes per inflated byte in the worst case every block is sized for) live in the context's own scratch:
@@ -159,19 +124,12 @@ int bgzf_inflate2_launch(wgbs_ctx *ctx, const uint8_t *d_comp, const BgzfBlock *
     tok = (dflate2::Token *)sc;
     RC_TRY(T.alloc(&ntok, nb)); RC_TRY(T.alloc(&status, nb));
     static const size_t team_bytes = TEAM_SLOTS * sizeof(dflate3::TeamMem);
-    // WGBS_INFLATE (read per call: tests and probes switch inside one process): "thread" = the thread-per-block decoder (round-2 first design,
-    // 1.74 ms per 1M-read BAM against 0.98 ms for the team decoder on the same B200), "tokens" = the token-per-lane replay; default: team + bytes
-    const char *ev = getenv("WGBS_INFLATE");
-    const bool team = !(ev && strstr(ev, "thread"));
-    if (team) CUDA_TRY(cudaFuncSetAttribute(bgzf_team_decode_k<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)team_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(bgzf_team_decode_k<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)team_bytes));
     for (uint32_t c0 = 0; c0 < nb; c0 += CHUNK_BLOCKS) {
         const uint32_t n = nb - c0 < CHUNK_BLOCKS ? nb - c0 : CHUNK_BLOCKS;
-        const unsigned grid = (unsigned)std::min<uint32_t>((n + 31) / 32, (uint32_t)ctx->sm_count);
-        if (team) LAUNCH(ctx, bgzf_team_decode_k<32>, grid, TEAM_SLOTS * 32, team_bytes, d_comp, d_blocks + c0, n, out, tok, ntok + c0, status + c0);
-        else
-        LAUNCH(ctx, bgzf_decode_k, grid, DEC_WARPS * 32, smem_bytes, d_comp, d_blocks + c0, n, out, tok, ntok + c0, status + c0);
-        if (ev && strstr(ev, "tokens")) LAUNCH(ctx, bgzf_resolve_k<false>, grid_for(n, RES_WARPS), RES_WARPS * 32, 0, d_comp, d_blocks + c0, n, c0, out, tok, ntok + c0, status + c0, d_err);
-        else LAUNCH(ctx, bgzf_resolve_k<true>, grid_for(n, RES_WARPS), RES_WARPS * 32, 0, d_comp, d_blocks + c0, n, c0, out, tok, ntok + c0, status + c0, d_err);
+        const unsigned grid = (unsigned)std::min<uint32_t>((n + TEAM_SLOTS - 1) / TEAM_SLOTS, (uint32_t)ctx->sm_count);
+        LAUNCH(ctx, bgzf_team_decode_k<32>, grid, TEAM_SLOTS * 32, team_bytes, d_comp, d_blocks + c0, n, out, tok, ntok + c0, status + c0);
+        LAUNCH(ctx, bgzf_resolve_k, grid_for(n, RES_WARPS), RES_WARPS * 32, 0, d_comp, d_blocks + c0, n, c0, out, tok, ntok + c0, status + c0, d_err);
         LAUNCH(ctx, bgzf_warp_inflate_k, grid_for(n, OLD_WARPS), OLD_WARPS * 32, 0, d_comp, d_blocks + c0, n, c0, out, status + c0, d_err);
     }
     LAUNCH_CHECK();

@@ -1,24 +1,20 @@
-// inflate2_core.cuh -- two-phase raw DEFLATE (RFC 1951) decoder for BGZF blocks.
+// inflate2_core.cuh -- raw DEFLATE (RFC 1951) for BGZF blocks in two phases: the pieces shared by the team decoder (inflate3_core.cuh).
 //
-// The warp-per-block decoder of inflate_core.cuh is bound by instruction issue: every lane of a warp executes the same
-// serial Huffman walk for ONE block (ncu, round 1: 94 warp-instructions per symbol, 28 warps per SM competing for the
-// issue slots, 4.08 ms per 1M-read BAM).  A block's symbol chain is inherently serial, so here
+//   phase 1  walks the Huffman stream: literals go to their final place at once, a match becomes an 8-byte token
+//            (output position, length, distance) in a per-block list.  Here: the table entries (32 bits, everything precomputed:
+//            code bits + extra bits, base value, kind; two-level tables in one arena), the tokens, and `Decoder` -- the bit reader
+//            of ONE lane that parses deflate block headers (stored blocks, code lengths) and can build the tables serially.  The
+//            walk itself, by the 32 lanes of a team, is inflate3_core.cuh.
+//   phase 2  (resolve_bytes) one WARP per block replays the token list: per round the matches whose sources are final are laid end
+//            to end and the lanes copy consecutive BYTES; then ISIZE and CRC32 (crc32_block4).
 //
-//   phase 1  (Decoder)   ONE THREAD per BGZF block walks the Huffman stream; the 32 lanes of a warp decode 32 different
-//                        blocks in the same instruction stream.  Tables are 32-bit entries with everything precomputed
-//                        (code bits + extra bits, base value, kind), lane-interleaved in shared memory so any 32 probes
-//                        are conflict-free; every loop iteration is ONE table probe -- a literal/length probe or, for the
-//                        lanes that just decoded a length, a distance probe -- so all lanes run one uniform path.
-//                        Literals are stored at their final place at once; a match becomes an 8-byte token
-//                        (output position, length, distance) in a per-block list.  The compressed bytes reach the lane
-//                        through a 64-word shared-memory ring filled by cp.async (no stall, no registers).
-//   phase 2  (resolve)   one WARP per block replays the token list: 32 matches per round, everything whose source lies
-//                        below the first unfinished match is copied at once (multi-round resolution), short matches by
-//                        their own lane, long / overlapping / stored ones by the whole warp; then ISIZE and CRC32.
+// History (numbers in DESIGN.md section 7 / profiles/README.md): round 1 decoded a block with one warp, every lane the same walk
+// (inflate_core.cuh, 4.08 ms per 1M-read BAM; still the fallback for blocks whose tables exceed the arena); the first decoder of
+// round 2 walked one block per THREAD with lane-interleaved tables (1.74 ms) and replayed one match per lane (1.28 ms); both
+// were removed when the team decoder (0.94 ms) and the byte-per-lane replay replaced them.
 //
-// Host + device code: tests/bamdev_core_check.cpp builds it with g++ and pins both phases against zlib (phase 2 under the
-// 32-lane lock-step emulation).  Stands in for the zlib inflate of the reference's `samtools view` stage
-// (reference src/python/bam2pat.py:165).
+// Host + device code: tests/bamdev_core_check.cpp builds it with g++ and pins it against zlib.  Stands in for the zlib inflate of
+// the reference's `samtools view` stage (reference src/python/bam2pat.py:165).
 #pragma once
 #include "inflate_core.cuh"
 
@@ -67,39 +63,26 @@ constexpr uint32_t TOK_STORED = 0x80000000u;
 constexpr uint32_t MAX_STORED_TOKENS = 16;   // further stored blocks of one BGZF block are copied by the decoding lane itself
 WGBS_HD uint32_t token_cap(uint32_t usize) { return usize / 3 + 2 + MAX_STORED_TOKENS; }
 
-// ---- per-lane working memory -------------------------------------------------------------------------------------------
-// element i of an array lives at p[i << SHIFT]: SHIFT 0 = plain arrays (host), SHIFT 5 = the arrays of 32 decoding lanes
-// interleaved element by element (shared memory: lane slot s has its pointers offset by s, so any set of lanes probing any
-// indices of the same 32-bit array hit different banks).
+// ---- working memory of one block ----------------------------------------------------------------------------------------------
+// element i of an array lives at p[i << SHIFT] (SHIFT 0: plain arrays; the round-2 thread-per-block decoder interleaved the arrays
+// of 32 lanes with SHIFT 5).
 //
-// Tables: ONE arena of ARENA entries per lane.  [0, 1 << LB) is the literal/length root table; second-level tables of the
-// literal/length codes longer than LB bits follow; then the distance root table (1 << DB entries, at dt_off) and its second-level
-// tables.  A root entry with (e & 31) == 0 is indirect: bits 5..8 = index bits of the second-level table, bits 16.. = its offset.
+// Tables: ONE arena of ARENA entries.  [0, 1 << LB) is the literal/length root table; second-level tables of the literal/length
+// codes longer than LB bits follow; then the distance root table (1 << DB entries, at dt_off) and its second-level tables.  A root
+// entry with (e & 31) == 0 is indirect: bits 5..8 = index bits of the second-level table, bits 16.. = its offset.
 // The worst case of RFC 1951 code sets needs ~1750 entries; real streams need 1300-1400.  A block whose tables do not fit is
 // reported as E_FALLBACK and decoded by the warp-per-block decoder of inflate_core.cuh instead.
 constexpr uint32_t ARENA = 1536;
-constexpr uint32_t RING = 128;         // words of compressed stream staged per lane: 32 chunks of 16 bytes
+constexpr uint32_t RING = 128;         // words of compressed stream staged for the header parser: 32 chunks of 16 bytes
 constexpr int E_FALLBACK = -20;        // not an error of the stream: the tables of this block need more than ARENA entries
 template <int SHIFT>
 struct Mem {
     uint32_t *tab;                // ARENA entries
-    uint32_t *rg;                 // RING words (layout: see Decoder::ring_word)
+    uint32_t *rg;                 // RING words
     uint16_t *bk;                 // 32 words of bookkeeping for the table construction (count / cursor per code length)
     uint8_t *ln;                  // 320 code lengths
     static constexpr int shift = SHIFT;
 };
-constexpr size_t LANE_BYTES = (ARENA + RING) * 4 + 32 * 2 + 320;     // 7040
-// carve the interleaved arrays of 32 lanes out of `smem` (32 * LANE_BYTES bytes, 16-byte aligned)
-WGBS_HD Mem<5> warp_mem(unsigned char *smem, uint32_t slot) {
-    Mem<5> m;
-    uint32_t *w = reinterpret_cast<uint32_t *>(smem);
-    m.rg = w + slot * 4; w += RING * 32;                       // 16-byte chunks per lane: chunk c of lane l at word (c * 32 + l) * 4
-    m.tab = w + slot; w += ARENA * 32;
-    uint16_t *h = reinterpret_cast<uint16_t *>(w);
-    m.bk = h + slot; h += 32 * 32;
-    m.ln = reinterpret_cast<uint8_t *>(h) + slot;
-    return m;
-}
 struct HostLane {
     uint32_t tab[ARENA], rg[RING];
     uint16_t bk[32];
@@ -108,7 +91,6 @@ struct HostLane {
 };
 
 enum : int { ST_HDR = 0 /* at a deflate block header */, ST_DEC = 1 /* inside a Huffman block */, ST_DONE = 2 };
-constexpr int BURST = 64;      // table probes between two ring top-ups: 64 * 28 bits < the half ring a top-up guarantees
 
 template <int SHIFT>
 struct Decoder {
@@ -126,63 +108,23 @@ struct Decoder {
     // decode state
     uint32_t len;                              // pending match length (0: next probe is literal/length)
     uint32_t dt_off;                           // arena offset of the distance root table
-    uint32_t tab_sa;                           // shared-memory address of m.tab (device)
     // team decoder (inflate3_core.cuh): header() stops behind the code lengths; the team builds the tables of ln[0 .. pend_nlen + pend_ndist) together
     uint16_t defer, pend_nlen, pend_ndist;
 
     static constexpr uint32_t S = (uint32_t)SHIFT;
 
-    // One table probe.  On the device the load is a volatile asm statement: the compiler then keeps it where the source puts it --
-    // BEFORE the bookkeeping and the end-of-block branch of the previous probe -- instead of sinking it below that branch.
-    WGBS_HD uint32_t tab_load(uint32_t idx) const {
-#if defined(__CUDA_ARCH__)
-        if (SHIFT) {
-            uint32_t v;
-            asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(tab_sa + (idx << (S + 2))));
-            return v;
-        }
-#endif
-        return m.tab[idx << S];
-    }
     // ---- ring ----------------------------------------------------------------------------------------------------------
     WGBS_HD uint32_t ring_word(uint32_t k) const {
         const uint32_t s = k & (RING - 1);
         return SHIFT ? m.rg[((s >> 2) << 7) + (s & 3)] : m.rg[s];
     }
-    // stage chunk c (words [4c, 4c + 4)) into its ring slot; asynchronous on the device.  Chunks past the stream are skipped.
+    // stage chunk c (words [4c, 4c + 4)) into its ring slot.  Chunks past the stream are skipped.
     WGBS_HD void ring_load_chunk(uint32_t c) {
         const uint32_t w = 4 * c, s = w & (RING - 1);
         if (w >= nwords) return;
-#if defined(__CUDA_ARCH__)
-        if (SHIFT) {
-            const uint32_t sa = (uint32_t)__cvta_generic_to_shared(m.rg + ((s >> 2) << 7));
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gw + w) : "memory");
-            return;
-        }
-#endif
         for (uint32_t k = 0; k < 4; k++) m.rg[SHIFT ? ((s >> 2) << 7) + k : s + k] = gw[w + k];      // (the buffer is padded: whole chunks are readable)
     }
-    WGBS_HD void ring_commit_wait() {
-#if defined(__CUDA_ARCH__)
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
-        asm volatile("cp.async.wait_all;\n" ::: "memory");
-#endif
-    }
-    // Before a burst: everything issued earlier has landed; then fill every free slot (the ring then holds chunks [wp / 4, wp / 4 + 32),
-    // the newly requested ones arriving while the burst consumes older ones).  The same instructions for all lanes.
-    WGBS_HD void ring_top_up() {
-#if defined(__CUDA_ARCH__)
-        asm volatile("cp.async.wait_all;\n" ::: "memory");
-#endif
-        const uint32_t limit = (wp >> 2) + RING / 4;
-#if defined(__CUDA_ARCH__)
-#pragma unroll 4
-#endif
-        for (int k = 0; k < 16; k++) if (hi_c < limit) { ring_load_chunk(hi_c); hi_c++; }      // a burst consumes at most 15 chunks
-#if defined(__CUDA_ARCH__)
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
-#endif
-    }
+    WGBS_HD void ring_commit_wait() {}         // (the thread-per-block decoder staged with cp.async and waited here)
     // make the ring complete up to its capacity, synchronously (after a header: its reads are not paced like a burst's)
     WGBS_HD void ring_fill_sync() {
         ring_commit_wait();
@@ -216,10 +158,6 @@ struct Decoder {
 
     WGBS_HD void init(Mem<SHIFT> mem, const uint8_t *payload, uint32_t clen, uint8_t *out, uint32_t usize, Token *tokens) {
         m = mem;
-        tab_sa = 0;
-#if defined(__CUDA_ARCH__)
-        if (SHIFT) tab_sa = (uint32_t)__cvta_generic_to_shared(m.tab);
-#endif
         src = payload; mis = (uint32_t)((uintptr_t)payload & 15);
         gw = (const uint32_t *)(payload - mis);
         end_bit = 8 * (mis + clen); nwords = (mis + clen + 3) >> 2;
@@ -391,160 +329,13 @@ struct Decoder {
         ring_fill_sync();
         return ST_DEC;
     }
-
-    // ---- one burst of table probes of the current Huffman block: returns the next state ---------------------------------------
-    // Every iteration is ONE root probe -- literal/length, or the distance of the match whose length the previous probe gave --
-    // with the same instructions whatever the lane is doing.  The probe of iteration i + 1 is issued before the bookkeeping of
-    // iteration i (stores, counters, checks), which then runs while the probe is in flight.  The bit buffer takes the next word by
-    // an unconditional OR (stream bits above bc are simply there early; OR-ing them again is harmless), only the count is conditional.
-    // The ring must hold BURST * 28 bits beyond the read position (ring_top_up before every call).
-    // (A lone warp issues one instruction every ~3.5 cycles -- each waits for the one before -- so a block takes as long as the
-    // instruction stream of its probes: ~80 instructions per probe here.  Splitting the burst into a lean walk that only records
-    // (entry, bit-buffer word) and an interpreting pass was measured: more instructions in total, 2.8 ms instead of 1.7 ms.)
-    WGBS_HD int decode_burst() {
-        if (bc < 32) refill_careful();         // a header may leave fewer bits than one probe consumes (the loop below counts on >= 28)
-        uint32_t want_dist = len != 0 ? 1u : 0u;
-        bb |= (uint64_t)nw << bc;
-        uint32_t e_next = tab_load(want_dist ? dt_off + ((uint32_t)bb & ((1u << DB) - 1)) : (uint32_t)bb & ((1u << LB) - 1));
-        for (int it = 0; it < BURST; it++) {
-            uint32_t e = e_next;
-            if (WGBS_UNLIKELY(!(e & 31)))                          // second level (3.7 % of the probes of a BAM stream)
-                e = tab_load((e >> 16) + (((uint32_t)(bb >> (want_dist ? DB : LB))) & ((1u << ((e >> 5) & 15)) - 1)));
-            const uint32_t tot = e & 31, eb = (e >> 5) & 15, kind = (e >> 9) & 3;
-            const uint32_t val = (e >> 16) + ((uint32_t)(bb >> (tot - eb)) & ((1u << eb) - 1));
-            const uint32_t was_dist = want_dist;
-            // the reader moves on; the next word joins the buffer as soon as it fits
-            bc -= tot;
-            bb = (bb >> tot) | ((uint64_t)nw << bc);
-            if (bc < 32) { bc += 32; wp++; nw = ring_word(wp); }
-            const bool is_len = !was_dist && kind == K_BASE;
-            want_dist = is_len ? 1u : 0u;
-            e_next = tab_load(want_dist ? dt_off + ((uint32_t)bb & ((1u << DB) - 1)) : (uint32_t)bb & ((1u << LB) - 1));
-            // bookkeeping of this probe
-            const bool is_lit = !was_dist && kind == K_LIT, is_dst = was_dist && kind == K_BASE;
-            const uint32_t adv = is_lit ? 1u : (is_dst ? len : 0u);
-            const bool odd = !(is_lit || is_len || is_dst) || opos + adv > dst_len || (is_dst && val > opos);
-            if (WGBS_UNLIKELY(odd)) {                              // end of block, or an error
-                if (!was_dist && kind == K_EOB) {
-                    if (bitpos() > end_bit) { rc = E_INPUT; return ST_DONE; }
-                    len = 0;
-                    return ST_HDR;
-                }
-                rc = !(is_lit || is_len || is_dst) ? E_SYMBOL : (is_dst && val > opos) ? E_DIST : E_OUTPUT;
-                return ST_DONE;
-            }
-            if (is_lit) dst[opos] = (uint8_t)val;
-            if (is_dst) { Token t; t.x = opos | (len << 16); t.y = val; tok[ntok] = t; }      // fits: every match is >= 3 bytes of output (token_cap)
-            ntok += is_dst ? 1u : 0u; opos += adv; len = is_len ? val : (is_dst ? 0u : len);
-        }
-        return ST_DEC;
-    }
-
-    // whole block, one lane (host tests; the kernel interleaves header() / ring_top_up() / decode_burst() over the lanes of a warp)
-    WGBS_HD int run() {
-        int st = ST_HDR;
-        while (st != ST_DONE) {
-            if (st == ST_HDR) st = header();
-            else { ring_top_up(); st = decode_burst(); }
-        }
-        return rc;
-    }
 };
 
-// ---- phase 2: replay the token list of one block ------------------------------------------------------------------------------
-constexpr uint32_t OWN_MAX = 16;      // matches up to this length are copied by the lane that holds their token
-
-// lanes: dflate::WarpLanes / dflate::OneLane / the test's lock-step emulation.  dst: the block's output (literals already in
-// place), payload: the block's deflate payload (stored blocks).  Every lane returns the same verdict.
-// bytes lane `lane` copies of one cooperative match: k = lane, lane + N, ... < ln -- at most 9 of them for the longest match (258)
-template <class L, uint32_t SLOTS>
-WGBS_HD void coop_copy(uint32_t lane, uint8_t *dst, uint32_t p, uint32_t ln, const uint8_t *from, bool wrap, uint32_t d) {
-    // every load before the first store: the bytes of one match make ONE memory round trip (a load-store-load-store loop makes one per 32 bytes)
-    constexpr uint32_t N = (uint32_t)L::N;
-    uint8_t c[SLOTS];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (uint32_t q = 0; q < SLOTS; q++) { const uint32_t k = lane + q * N; if (k < ln) c[q] = from[wrap ? k % d : k]; }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (uint32_t q = 0; q < SLOTS; q++) { const uint32_t k = lane + q * N; if (k < ln) dst[p + k] = c[q]; }
-}
-template <class L>
-WGBS_HD int resolve(L lanes, const Token *tok, uint32_t ntok, uint8_t *dst, uint32_t dst_len, const uint8_t *payload) {
-    const uint32_t lane = (uint32_t)lanes.id();
-    constexpr uint32_t N = (uint32_t)L::N;
-    Token nxt; nxt.x = 0; nxt.y = 0;
-    if (lane < ntok) nxt = tok[lane];
-    for (uint32_t t0 = 0; t0 < ntok; t0 += N) {
-        const bool valid = t0 + lane < ntok;
-        const Token tk = nxt;
-        if (t0 + N + lane < ntok) nxt = tok[t0 + N + lane];          // the next batch's tokens travel while this batch is replayed
-        const uint32_t at = tk.x & 0xffffu, len = tk.x >> 16;
-        const bool stored = (tk.y & TOK_STORED) != 0;
-        const uint32_t dist = tk.y & ~TOK_STORED;
-        // first byte past what the copy reads from the output (a run, dist < len, reads only the dist bytes before itself)
-        const uint32_t src_end = stored ? 0u : at - dist + (len < dist ? len : dist);
-        const bool own_kind = valid && !stored && len <= OWN_MAX && (dist >= len || dist == 1);
-        uint32_t pending = lanes.ballot(valid);
-        while (pending) {
-            const int first = dflate::lowest_bit(pending);
-            const uint32_t hwm = lanes.shfl(at, first);              // everything below is final
-            const bool ready = ((pending >> lane) & 1u) && src_end <= hwm;
-            const uint32_t R = lanes.ballot(ready);
-            uint32_t C = lanes.ballot(ready && !own_kind);
-            // own copies: all loads first, then all stores -- one memory round trip for the whole batch.  Most matches of a BAM
-            // stream are 3..8 bytes long: the 16-byte form runs only when some lane of this round needs it.
-            const bool mine = ready && own_kind;
-            if (lanes.ballot(mine && len > 8)) {
-                if (mine) {
-                    uint8_t b[OWN_MAX];
-                    const uint8_t *from = dst + at - dist;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-                    for (uint32_t k = 0; k < OWN_MAX; k++) if (k < len) b[k] = from[dist == 1 ? 0 : k];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-                    for (uint32_t k = 0; k < OWN_MAX; k++) if (k < len) dst[at + k] = b[k];
-                }
-            } else if (mine) {
-                uint8_t b[8];
-                const uint8_t *from = dst + at - dist;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-                for (uint32_t k = 0; k < 8; k++) if (k < len) b[k] = from[dist == 1 ? 0 : k];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-                for (uint32_t k = 0; k < 8; k++) if (k < len) dst[at + k] = b[k];
-            }
-            // cooperative copies (long, overlapping, stored): the whole warp on one match at a time
-            while (C) {
-                const int i = dflate::lowest_bit(C);
-                C &= C - 1;
-                const uint32_t x = lanes.shfl(tk.x, i), y = lanes.shfl(tk.y, i);
-                const uint32_t p = x & 0xffffu, ln = x >> 16, d = y & ~TOK_STORED;
-                const bool st = (y & TOK_STORED) != 0, wrap = !st && d < ln;
-                const uint8_t *from = st ? payload + d : dst + p - d;
-                if (ln <= 3 * N) coop_copy<L, 3>(lane, dst, p, ln, from, wrap, d);
-                else if (ln <= 9 * N) coop_copy<L, 9>(lane, dst, p, ln, from, wrap, d);
-                else for (uint32_t k = lane; k < ln; k += N) dst[p + k] = from[wrap ? k % d : k];      // a stored block (or few lanes): plain loop
-            }
-            lanes.sync();                                            // this round's bytes are visible to the next round's loads
-            pending &= ~R;
-        }
-    }
-    (void)dst_len;
-    return OK;
-}
-
-// ---- phase 2, lane = output BYTE ---------------------------------------------------------------------------------------------------
-// The token-per-lane replay above spends ~65 warp instructions per match (ncu: 292 000 per block, issue-bound with 7 warps per
-// scheduler): every lane copies its own match byte by byte under predicates, whatever the other lanes' lengths.  Here the ready
+// ---- phase 2: replay the token list of one block, lane = output BYTE ------------------------------------------------------------------
+// lanes: dflate::WarpLanes / dflate::OneLane / the test's lock-step emulation.  dst: the block's output (literals already in place),
+// payload: the block's deflate payload (stored blocks).  Every lane returns the same verdict.
+// A replay with one MATCH per lane (each lane copying its own match byte by byte under predicates, long ones by the whole warp) spent
+// ~65 warp instructions per match (ncu: 292 000 per block, 64 registers + spills) and was removed.  Here the ready
 // matches of a round are laid end to end (exclusive sum of their lengths) and the lanes take consecutive BYTES of that space: a
 // five-step search over the lanes' offsets (shuffles) finds the byte's token, one load and one store move it.  A round's sources all
 // lie below its first unfinished match and its destinations at or above it, so the bytes of a round are independent of each other.
