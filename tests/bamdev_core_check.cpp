@@ -11,6 +11,7 @@
 //                                                      lines or '-'), print the SAM text; stderr: stats
 //   bamdev_core_check inflate3 FILE.bgzf               every BGZF block through the team decoder (inflate3_core.cuh: teams of 32, 16, 8
 //                                                      lanes in lock step, and one lane) + token replay vs zlib; stderr: chain statistics
+//   bamdev_core_check nptags FILE.bam                  the MM:Z string and the ML:B:C values of every record as the direct route finds them
 //   bamdev_core_check tables N SEED                    two-level Huffman tables of the two-phase decoder vs a canonical-code walk
 //   bamdev_core_check fmtg N SEED                      fmt_g vs snprintf("%g") on N random floats + edge cases
 //   bamdev_core_check part FILE.bam SEG DEPTH B0 NB FIRST REFS   blocks [B0, B0+NB) as a part of a streamed file (dbam_open_impl, part mode)
@@ -220,6 +221,31 @@ static int cmd_inflate3(const char *path) {
     fprintf(stderr, "fallbacks %zu\n", g_fallbacks);
     printf("blocks %zu bytes %llu mismatches %zu\n", blocks.size(), (unsigned long long)bytes, nbad);
     return nbad ? 1 : 0;
+}
+
+// the MM / ML tags of every record as the direct route finds them (bam_core.cuh find_np_tags): "qname \t MM string | - \t ML values | -" per record
+static int cmd_nptags(const char *path) {
+    auto f = slurp(path); uint64_t n; auto blocks = scan_blocks(f, &n);
+    std::vector<uint8_t> d(n + 16, 0);
+    for (const Blk &b : blocks) if (one_lane(f.data() + b.coff + 12 + b.xlen, b.csize - 12 - b.xlen - 8, d.data() + b.uoff, b.usize)) { fprintf(stderr, "inflate failed\n"); return 3; }
+    using namespace bamcore;
+    if (n < 12 || memcmp(d.data(), "BAM\1", 4)) { fprintf(stderr, "not a BAM\n"); return 3; }
+    uint64_t p = 8ull + ld32(d.data() + 4); const int32_t n_ref = ldi32(d.data() + p); p += 4;
+    for (int32_t i = 0; i < n_ref; i++) { const uint32_t l = ld32(d.data() + p); p += 4 + l + 4; }
+    while (p + 4 <= n) {
+        const uint32_t bs = ld32(d.data() + p);
+        if (bs < 32 || p + 4 + bs > n) { fprintf(stderr, "corrupt BAM record at %llu\n", (unsigned long long)p); return 3; }
+        Rec R; R.load(d.data() + p);
+        const uint8_t *mm, *ml; uint32_t mm_len, ml_cnt;
+        find_np_tags(R.tags(), R.end(), &mm, &mm_len, &ml, &ml_cnt);
+        fwrite(R.name(), 1, strlen((const char *)R.name()), stdout); putchar('\t');
+        if (mm) fwrite(mm, 1, mm_len, stdout); else putchar('-');
+        putchar('\t');
+        if (ml) { for (uint32_t k = 0; k < ml_cnt; k++) printf(k ? ",%u" : "%u", ml[k]); if (!ml_cnt) putchar('.'); } else putchar('-');
+        putchar('\n');
+        p += 4 + bs;
+    }
+    return 0;
 }
 
 static int cmd_view(const char *path, uint64_t SEG, int depth, int argc, char **argv) {
@@ -469,6 +495,7 @@ int main(int argc, char **argv) {
     for (uint32_t k = 0; k < 4; k++) for (uint32_t i = 0; i < 256; i++) g_crc4[k * 256 + i] = dflate2::crc_slice_entry(k, i);
     if (argc >= 3 && !strcmp(argv[1], "inflate")) return cmd_inflate(argv[2], argc > 3 ? atoi(argv[3]) : 0);
     if (argc >= 3 && !strcmp(argv[1], "inflate3")) return cmd_inflate3(argv[2]);
+    if (argc >= 3 && !strcmp(argv[1], "nptags")) return cmd_nptags(argv[2]);
     if (argc >= 5 && !strcmp(argv[1], "view")) return cmd_view(argv[2], strtoull(argv[3], nullptr, 10), atoi(argv[4]), argc - 5, argv + 5);
     if (argc >= 4 && !strcmp(argv[1], "fmtg")) return cmd_fmtg(atol(argv[2]), (unsigned)atoi(argv[3]));
     if (argc >= 4 && !strcmp(argv[1], "tables")) return cmd_tables(atol(argv[2]), (unsigned)atoi(argv[3]));

@@ -352,3 +352,28 @@ def test_two_phase_decoder_tables_and_fallback(check, tmp_path):
     assert r.returncode == 0 and r.stdout.strip().endswith("mismatches 0"), r.stdout + r.stderr
     fb = int(r.stderr.split("fallbacks")[1].split()[0])
     assert fb > 0, "no block exceeded the arena: the fallback path was not exercised"
+
+
+def test_mm_ml_tags_found_in_bam_records_like_in_sam_text(check, sam, tmp_path, built_lib):
+    """bam_core.cuh find_np_tags (MM/ML mode of the direct route, bamdev.cu bam_np_tags_k) against the rule the SAM tokenizer applies to
+    text (sam.cu tag_kind; reference ont.cpp:418-438): the LAST "MM:Z:" / "Mm:Z:" field and the LAST "ML:B:C" / "Ml:B:C" field -- other
+    array subtypes, other tags in front, behind and between, empty arrays, no tags at all"""
+    import re
+    from wgbs_tools_b200 import bamio
+    g, _ = sam
+    seq = g.bases[1000:1040].tobytes()
+    odd = [b"MM:Z:C+m?,0,1;\tML:B:C,250,3", b"Mm:Z:C+m.,1;\tMl:B:C,200", b"XA:i:5\tMM:Z:C+h?,0;\tXB:Z:abc\tML:B:C,255\tXC:B:s,1,2", b"MM:Z:C+m?,5;\tMM:Z:C+m?,0;\tML:B:C,9\tML:B:C,7,8",
+           b"MM:Z:C+m?,0;\tML:B:c,100", b"MM:Z:C+m?,0;", b"XZ:Z:none", b"MM:Z:C+m?,0;\tML:B:S,300", b"XF:f:1.5\tXH:H:1AE3\tMM:Z:C+C?,0;\tXI:B:f,0.25,2\tML:B:C,77\tXJ:A:q",
+           b"MM:Z:C+m?;\tML:B:C", b"ML:B:C,5\tMM:Z:C+m.,0;", b"MM:Z:\tML:B:C,1", b"MN:Z:x\tMK:B:C,1,2"]
+    lines = [b"r%d\t0\tchrT\t%d\t60\t40M\t*\t0\t0\t%s\t*\t%s\n" % (k, 1001 + k, seq, t) for k, t in enumerate(odd)]
+    lines.append(b"bare\t0\tchrT\t2000\t60\t40M\t*\t0\t0\t%s\t*\n" % seq)
+    p = tmp_path / "tags.bam"; p.write_bytes(bamio.sam_to_bam(b"".join(lines), [("chrT", g.length)]))
+    r = subprocess.run([check, "nptags", str(p)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    assert r.returncode == 0, r.stderr
+    want = []
+    for l in lines:
+        f = l.rstrip(b"\n").split(b"\t")
+        mm = [x[5:] for x in f[11:] if re.match(rb"M[Mm]:Z:", x)]
+        ml = [x[6:] for x in f[11:] if re.match(rb"M[Ll]:B:C", x)]
+        want.append(b"\t".join([f[0], mm[-1] if mm else b"-", (ml[-1].lstrip(b",") or b".") if ml else b"-"]) + b"\n")
+    assert r.stdout == b"".join(want)
