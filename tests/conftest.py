@@ -10,18 +10,6 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
-    config.addinivalue_line("markers", "staged: GPU test of an opt-in code path that has not run on a B200 yet (WGBS_STAGED=1 to run)")
-
-
-def pytest_collection_modifyitems(config, items):
-    """staged tests exercise kernels written without GPU access (selected by environment variables, never the default
-    path).  A first run may hang or fault, so they only run when asked for -- wrapped in a `timeout` on the GPU box."""
-    if os.environ.get("WGBS_STAGED") == "1":
-        return
-    skip = pytest.mark.skip(reason="staged (not yet run on a B200): set WGBS_STAGED=1")
-    for it in items:
-        if "staged" in it.keywords:
-            it.add_marker(skip)
 
 
 @pytest.fixture(scope="session")

@@ -423,7 +423,7 @@ def main(argv=None):
                 from .bamio import BamPart, DeviceBamPart, stream_parts
                 by_chrom = {r.split(":")[0]: (ri, r) for ri, r in enumerate(regions) if ri in mine}
                 piles: dict[str, ChromPile] = {}; finished: set[str] = set()
-                # parts decoded on host threads, or (WGBS_STREAM_BACKEND=device; staged) uploaded compressed and decoded in HBM
+                # parts decoded on host threads, or (WGBS_STREAM_BACKEND=device) uploaded compressed and decoded in HBM
                 on_dev = os.environ.get("WGBS_STREAM_BACKEND", "host") == "device"
                 if on_dev:
                     opener = lambda data, refs, lens, first: DeviceBamPart(ctx, data, refs, lens, first)

@@ -16,7 +16,7 @@
 //            from its anchor, now writing literals to their final place and matches to the token list -- the same
 //            (output position | length << 16, distance) tokens bgzf_resolve_k replays.
 //
-// A lane walks ~2 spans + SYNC_BITS instead of the whole block: with 32 lanes ~8 000 bits instead of ~100 000.
+// A lane walks ~2 spans + SYNC_BITS instead of the whole block: with 32 lanes ~7 500 bits instead of ~100 000.
 // Host + device code (lane policies of inflate_core.cuh; tests/bamdev_core_check.cpp runs it under the lock-step emulation
 // against zlib).  Stands in for the zlib inflate inside `samtools view` (reference src/python/bam2pat.py:165).
 #pragma once
@@ -259,7 +259,7 @@ WGBS_HD int team_tables(L lanes, dflate2::Mem<0> m, uint32_t nlen, uint32_t ndis
 }
 
 // Statistics of the host tests (nullptr on the device): how the chain went
-struct TeamStats { uint64_t blocks, lanes_started, lanes_dropped, spans_serial; };
+struct TeamStats { uint64_t blocks, lanes_started, lanes_dropped; };
 
 // All lanes of the team call this together; every lane returns the same verdict.  *ntok_out: tokens written to `tok`.
 template <class L>
