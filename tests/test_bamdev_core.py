@@ -4,6 +4,7 @@ the source SAM text and the library's host BAM reader (csrc/bam.cu, itself round
 The warp-cooperative part of the inflater runs here under a 32-lane lock-step emulation (one thread per lane, every
 shuffle / ballot / __syncwarp a barrier)."""
 import os
+import re
 import struct
 import subprocess
 import zlib
@@ -377,3 +378,30 @@ def test_mm_ml_tags_found_in_bam_records_like_in_sam_text(check, sam, tmp_path, 
         ml = [x[6:] for x in f[11:] if re.match(rb"M[Ll]:B:C", x)]
         want.append(b"\t".join([f[0], mm[-1] if mm else b"-", (ml[-1].lstrip(b",") or b".") if ml else b"-"]) + b"\n")
     assert r.stdout == b"".join(want)
+
+
+def test_team_decoder_is_exact_however_badly_the_lanes_guess(sam, tmp_path):
+    """inflate3_core.cuh: a lane's guessed walk is only USED once its predecessor has arrived exactly at its anchor; lanes whose anchor is
+    missed are dropped and the predecessor walks on.  With a run-up of 8 bits instead of 1024 (-DWGBS_SYNC_BITS=8) four lanes in five
+    are dropped -- the output must still equal zlib's on every block type, for teams of 1 / 8 / 16 / 32 lanes, and the verdicts on
+    corrupt streams must still agree"""
+    from wgbs_tools_b200.patio import BGZF_EOF
+    exe = str(tmp_path / "check_sb8")
+    r = subprocess.run(["g++", "-std=c++20", "-O2", "-DWGBS_SYNC_BITS=8", "-o", exe, os.path.join(ROOT, "tests", "bamdev_core_check.cpp"), "-lz", "-lpthread"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    _, s = sam
+    rng = np.random.default_rng(2)
+    parts = [block(s[:60000]), block(s[60000:125000], 9), block(s[130000:190000], 1), block(rng.integers(0, 4, 65000, dtype=np.uint8).tobytes()),
+             block(b"ab" * 30000), block(s[200000:260000], 6, zlib.Z_FIXED), block(s[:3000], 0), block(b"")]
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    d = s[300000:360000]
+    parts.append(frame(co.compress(d[:20000]) + co.flush(zlib.Z_SYNC_FLUSH) + co.compress(d[20000:45000]) + co.flush(zlib.Z_FULL_FLUSH) + co.compress(d[45000:]) + co.flush(), d))
+    good = block(s[:50000])
+    for k in range(12):
+        b = bytearray(good); b[int(rng.integers(18, len(b) - 8))] ^= 1 << int(rng.integers(0, 8)); parts.append(bytes(b))
+    p = tmp_path / "m.bgzf"; p.write_bytes(b"".join(parts) + BGZF_EOF)
+    r = subprocess.run([exe, "inflate3", str(p)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert r.returncode == 0 and r.stdout.strip().endswith("mismatches 0"), r.stdout + r.stderr
+    started, dropped = (int(x) for x in re.search(r"team 32: deflate blocks \d+ lanes started (\d+) dropped (\d+)", r.stderr).groups())
+    assert dropped * 2 > started, "the short run-up was meant to make most guesses fail"
